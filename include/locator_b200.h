@@ -1,0 +1,191 @@
+/*
+ * locator_b200 -- C ABI of the B200-native Locator hot path.
+ *
+ * The reference (kr-colab/locator) is pure Python with no FFI of its own; its
+ * stable interface is the `locator` CLI, its output files and the function
+ * surface of locator/locator.py.  This header is the boundary a maintainer
+ * binds (ctypes stub in INTEGRATION.md) to replace, one for one:
+ *
+ *   reference (locator/locator.py)                 entry points here
+ *   ---------------------------------------------  -----------------------------------
+ *   filter_snps            :265-281  (allel count_  loc_site_stats, loc_pack_sites,
+ *     alleles / is_biallelic / to_allele_counts)      loc_patch_calls
+ *   split_train_test       :295-308  (ac[:, idx])   loc_gather_rows
+ *   bootstrap column gather :648-653                loc_gather_cols
+ *   jacknife column replace :721-727                loc_replace_cols
+ *   uint8 [n, K] matrices in/out of the API         loc_pack_counts, loc_unpack_counts
+ *   load_network           :311-327                 loc_model_create / _init / _set_weight / _get_weight
+ *   load_callbacks         :330-362                 loc_model_set_schedule (device-side callback state)
+ *   train_network / fit    :365-376                 loc_train_epochs, loc_train_step
+ *   load_weights(best)     :380,386                 loc_restore_best
+ *   model.predict          :414,441                 loc_predict
+ *   validation pass of fit :374                     loc_eval
+ *   history                :468-469                 loc_model_history, loc_model_state
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; loc_last_error()
+ *     gives the message for the calling thread.
+ *   - pointers prefixed d_ are CUDA device pointers owned by the caller (torch
+ *     tensors); h_ are host pointers.  No torch types cross this boundary.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     is asynchronous unless the function returns host data (documented below).
+ *   - a loc_model is bound to the device current at creation and is not
+ *     thread-safe: one host thread / process per GPU.
+ *   - packed genotype matrix: sample-major, 2 bits per genotype (alt-allele count
+ *     0/1/2), 16 genotypes per little-endian uint32 (SNP k of a row lives in word
+ *     k/16, bits 2*(k%16)..+1), row pitch `row_words` uint32 (>= ceil(K/16),
+ *     multiple of 4 so rows are 16-byte aligned); pad bits are zero.
+ *   - there is NO CPU fallback: every entry point fails if CUDA is unavailable.
+ */
+#ifndef LOCATOR_B200_H
+#define LOCATOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOC_ABI_VERSION 1
+#define LOC_MAX_BATCH 32
+
+typedef struct loc_model loc_model;
+
+/* Snapshot of the device-side training/callback state (loc_model_state). */
+typedef struct loc_state {
+  int32_t t;            /* optimizer iterations done                         */
+  int32_t epoch;        /* epochs completed                                  */
+  int32_t stopped;      /* EarlyStopping fired (or max_epochs reached)       */
+  int32_t improved;     /* last finished epoch improved val_loss             */
+  int32_t best_epoch;   /* epoch index of the checkpointed weights, -1 none  */
+  int32_t es_wait;
+  int32_t rlr_wait;
+  int32_t nonfinite;    /* a non-finite loss was seen                        */
+  float lr;             /* current learning rate                             */
+  float ckpt_best;      /* best val_loss so far (+inf before the first)      */
+  float last_loss;
+  float last_val_loss;
+} loc_state;
+
+int loc_abi_version(void);
+const char* loc_last_error(void);
+/* Name of the first-layer kernel family in use ("simt" or "tcgen05"). */
+const char* loc_l1_impl(void);
+
+/* ---------------- genotype ingest (K1/K2) ---------------- */
+
+/* Per-site allele statistics over d_gt int8 [nvar][nsamp][2] (-1 = missing).
+ * d_n_alleles[v] = number of distinct allele indices observed (allel allelism),
+ * d_alt_count[v] = copies of allele index 1, d_n_missing[v] = calls with any
+ * negative allele.  d_keep[v] = 1 iff n_alleles == 2 and (min_mac == 1 or
+ * alt_count >= min_mac)  -- locator.py:267-273.  Any output pointer may be NULL. */
+int loc_site_stats(const int8_t* d_gt, int64_t nvar, int64_t nsamp, int32_t min_mac,
+                   int32_t* d_n_alleles, int32_t* d_alt_count, int32_t* d_n_missing,
+                   uint8_t* d_keep, void* stream);
+
+/* Pack the K sites d_site_idx[0..K) of d_gt into the 2-bit sample-major matrix:
+ * genotype = number of index-1 alleles of the call (missing/other alleles count 0)
+ * -- GenotypeArray.to_allele_counts()[:, :, 1], locator.py:277. */
+int loc_pack_sites(const int8_t* d_gt, int64_t nvar, int64_t nsamp, const int64_t* d_site_idx,
+                   int64_t K, uint32_t* d_packed, int64_t row_words, void* stream);
+
+/* Overwrite individual genotypes (imputation results of replace_md, :258-261):
+ * packed[d_samp[i]][d_k[i]] = d_val[i], i < n.  (k indexes packed columns.) */
+int loc_patch_calls(uint32_t* d_packed, int64_t row_words, const int64_t* d_k,
+                    const int64_t* d_samp, const uint8_t* d_val, int64_t n, void* stream);
+
+/* uint8 allele-count matrix [n][K] (row-major, values 0/1/2) <-> packed. */
+int loc_pack_counts(const uint8_t* d_counts, int64_t n, int64_t K, uint32_t* d_packed,
+                    int64_t row_words, void* stream);
+int loc_unpack_counts(const uint32_t* d_packed, int64_t n, int64_t K, int64_t row_words,
+                      uint8_t* d_counts, void* stream);
+
+/* out[r] = in[d_rows[r]] for r < n_out (sample split, :303-307). */
+int loc_gather_rows(const uint32_t* d_in, int64_t row_words, const int64_t* d_rows, int64_t n_out,
+                    uint32_t* d_out, void* stream);
+
+/* out[r][k] = in[r][d_cols[k]], k < K_out (bootstrap site_order, :651-653;
+ * max_SNPs subsample, :279). */
+int loc_gather_cols(const uint32_t* d_in, int64_t n, int64_t row_words_in, const int64_t* d_cols,
+                    int64_t K_out, uint32_t* d_out, int64_t row_words_out, void* stream);
+
+/* packed[r][d_sites[i]] = d_vals[i*n + r] (jacknife, :726-727; sites distinct). */
+int loc_replace_cols(uint32_t* d_packed, int64_t n, int64_t row_words, const int64_t* d_sites,
+                     int64_t nsites, const uint8_t* d_vals, void* stream);
+
+/* ---------------- model (K3-K7) ---------------- */
+
+/* BN(K) -> Dense(width, elu) x nlayers (Dropout after the floor(nlayers/2)-th)
+ * -> Dense(2) -> Dense(2); Adam(1e-3, .9, .999, 1e-7).  batch_size <= LOC_MAX_BATCH,
+ * nlayers >= 2.  Allocates parameters, Adam state, best-weights snapshot and
+ * workspaces on the current device. */
+int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers, int32_t batch_size,
+                     float dropout_prop, int32_t max_epochs);
+int loc_model_destroy(loc_model* m);
+
+/* Philox glorot-uniform kernels, zero biases, gamma 1 / beta 0 / moving mean 0 /
+ * moving var 1, zero Adam state, reset optimizer + callback state. `seed` also
+ * keys the dropout masks. */
+int loc_model_init(loc_model* m, uint64_t seed, void* stream);
+
+/* Keras weight order: [gamma, beta, moving_mean, moving_var, W1, b1, ..., Wo1, bo1, Wo2, bo2],
+ * kernels [in, out] row-major fp32.  set/get copy between HOST memory and the model
+ * and synchronise the stream. */
+int loc_model_num_weights(const loc_model* m);
+int64_t loc_model_weight_size(const loc_model* m, int32_t idx);
+int loc_model_set_weight(loc_model* m, int32_t idx, const float* h_src, int64_t n, void* stream);
+int loc_model_get_weight(loc_model* m, int32_t idx, float* h_dst, int64_t n, void* stream);
+/* Adam moments of trainable weight idx (idx 2,3 are not trainable -> error). */
+int loc_model_get_adam(loc_model* m, int32_t idx, float* h_m, float* h_v, int64_t n, void* stream);
+
+/* lr, EarlyStopping patience (ReduceLROnPlateau patience = patience/6), and
+ * reset of the callback state machine (best = +inf, waits = 0, epoch = 0). */
+int loc_model_set_schedule(loc_model* m, float lr, int32_t patience);
+
+/* Data the epochs run on (device memory owned by the caller, must outlive use).
+ * d_locs: float32 [n][2] normalised targets. */
+int loc_model_bind_train(loc_model* m, const uint32_t* d_packed, int64_t n, int64_t row_words,
+                         const float* d_locs);
+int loc_model_bind_val(loc_model* m, const uint32_t* d_packed, int64_t n, int64_t row_words,
+                       const float* d_locs);
+
+/* Test hook: use d_keep[step][LOC_MAX_BATCH][width] (uint8 0/1) as the dropout keep
+ * mask of optimizer step `step` instead of Philox; NULL restores Philox. */
+int loc_model_set_dropout_masks(loc_model* m, const uint8_t* d_keep, int64_t nsteps);
+
+/* One optimizer step on training rows d_rows[0..nb) (indices into the bound
+ * training matrix).  Async.  Batch loss is added to the running epoch mean. */
+int loc_train_step(loc_model* m, const int32_t* d_rows, int32_t nb, void* stream);
+
+/* n_epochs epochs: epoch e visits rows d_perms[e*n_train .. +n_train) in slices
+ * of batch_size (last partial), then the validation pass at batch 32, then the
+ * callback state machine (checkpoint-best / early-stop / reduce-LR) and the
+ * device-side snapshot, all on the GPU.  Async; epochs after the stop epoch are
+ * no-ops.  History rows are appended per epoch. */
+int loc_train_epochs(loc_model* m, const int32_t* d_perms, int32_t n_epochs, void* stream);
+
+/* Mean Euclidean loss (Keras evaluate semantics, batch 32) in inference mode.
+ * Synchronises; result in *h_loss. */
+int loc_eval(loc_model* m, const uint32_t* d_packed, int64_t n, int64_t row_words, const float* d_locs,
+             float* h_loss, void* stream);
+
+/* Inference-mode forward of n rows -> d_out float32 [n][2] (normalised units). Async. */
+int loc_predict(loc_model* m, const uint32_t* d_packed, int64_t n, int64_t row_words, float* d_out,
+                void* stream);
+
+/* Copy the best-val_loss snapshot back into the live weights (load_weights). Async. */
+int loc_restore_best(loc_model* m, void* stream);
+/* Force a snapshot of the live weights (used by tests). Async. */
+int loc_snapshot(loc_model* m, void* stream);
+
+/* Synchronising reads of device-side state / history ([epoch][3] = loss, val_loss, lr). */
+int loc_model_state(loc_model* m, loc_state* h_out, void* stream);
+int loc_model_history(loc_model* m, float* h_out, int32_t max_rows, void* stream);
+
+/* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
+int64_t loc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOCATOR_B200_H */

@@ -1,0 +1,90 @@
+// Shared helpers for the locator_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/locator_b200.h"
+
+namespace loc {
+
+extern thread_local std::string g_err;
+extern std::atomic<long long> g_launches;
+
+inline int fail(const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s (%s:%d)", what, file, line);
+  g_err = buf;
+  return 1;
+}
+
+#define LOC_CHECK(cond, msg)                                 \
+  do {                                                       \
+    if (!(cond)) return loc::fail(msg, __FILE__, __LINE__);  \
+  } while (0)
+
+#define LOC_CUDA(expr)                                                  \
+  do {                                                                  \
+    cudaError_t _e = (expr);                                            \
+    if (_e != cudaSuccess) {                                            \
+      char _b[384];                                                     \
+      snprintf(_b, sizeof(_b), "CUDA error %s: %s", cudaGetErrorName(_e), cudaGetErrorString(_e)); \
+      return loc::fail(_b, __FILE__, __LINE__);                         \
+    }                                                                   \
+  } while (0)
+
+// After a kernel launch: count it and surface launch-configuration errors.
+#define LOC_LAUNCHED()                 \
+  do {                                 \
+    loc::g_launches.fetch_add(1);      \
+    LOC_CUDA(cudaGetLastError());      \
+  } while (0)
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- Keras constants ----
+constexpr float kBnEps = 1e-3f;
+constexpr float kBnMom = 0.99f;
+constexpr float kBnOneMinusMom = 0.01f;
+constexpr float kAdamB1 = 0.9f;
+constexpr float kAdamB2 = 0.999f;
+constexpr float kAdam1mB1 = 0.1f;
+constexpr float kAdam1mB2 = 0.001f;
+constexpr float kAdamEps = 1e-7f;
+
+// Device-resident optimizer / epoch / callback state. One per model.
+struct DevState {
+  int t;         // optimizer iterations completed
+  int step_id;   // 0-based index of the step in flight (dropout stream)
+  float lr;
+  float alpha;   // lr * sqrt(1-b2^t) / (1-b1^t) for the step in flight
+  float loss_total, loss_count;  // Keras Mean(loss) accumulators for the epoch
+  float val_total, val_count;
+  int epoch;
+  int stopped;
+  int improved;
+  int best_epoch;
+  float ckpt_best, es_best, rlr_best;
+  int es_wait, rlr_wait;
+  int patience, rlr_patience;
+  int max_epochs;
+  int nonfinite;
+  float last_loss, last_val;
+};
+
+__device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : expm1f(z); }
+// d elu / dz expressed through the activation value (EluGrad: out < 0 ? out + 1 : 1).
+__device__ __forceinline__ float elu_grad_from_out(float a) { return a > 0.f ? 1.f : a + 1.f; }
+
+// Keras Adam: m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= alpha*m/(sqrt(v)+eps).
+__device__ __forceinline__ void adam_update(float& w, float& m, float& v, float g, float alpha) {
+  m = m + (g - m) * kAdam1mB1;
+  v = v + (g * g - v) * kAdam1mB2;
+  w = w - (m * alpha) / (sqrtf(v) + kAdamEps);
+}
+
+}  // namespace loc

@@ -1,0 +1,369 @@
+#!/usr/bin/env python3
+"""Benchmark of the Locator training hot path (BASELINE.json metric: train samples/s per model).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg3|fixture]
+
+A "step" is one optimizer step of one model (batch 32) on BASELINE config[1]: 1,000 samples x
+100,000 SNPs (810 train / 90 validation rows), nlayers=10, width=256.  The timed region enqueues
+exactly K steps through the C ABI (loc_train_epochs for whole epochs -- which, like the reference's
+model.fit, run the validation pass and callbacks after every epoch -- and loc_train_step for the
+remainder) on data already resident in HBM.  N > 1: every rank trains its own model on its own GPU
+(replicates are independent; no collective on the training path) -> weak scaling.
+
+Printed JSON line: see the task contract.  `e2e` times LocatorModel.fit() on HOST numpy arrays
+(H2D of the genotype matrices, 2-bit pack, the same number of steps, history read back).
+`roofline` is the first-layer backward + Adam kernel (24*K*H bytes per launch) timed alone with
+CUDA events.  `cpu_baseline` times the oracle (torch-CPU fp32 restatement of the Keras path; TF is
+not installable on this image) on a bounded number of steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_total, K)  -> 10% NA-location rows, train_split 0.9
+    "fixture": (500, 5830),
+    "cfg2": (1000, 100_000),
+    "cfg3": (2500, 200_000),
+}
+H, L, B = 256, 10, 32
+
+
+def split_sizes(n_total):
+    known = n_total - n_total // 10
+    nval = round((1 - 0.9) * known)
+    return known - nval, nval
+
+
+def synth(n, K, seed):
+    """Synthetic genotypes with spatial structure, uint8 [n, K] + z-scored locations."""
+    rng = np.random.default_rng(seed)
+    loc = rng.uniform(0, 50, size=(n, 2))
+    z = (loc - 25.0) / 14.0
+    x = np.empty((n, K), dtype=np.uint8)
+    for k0 in range(0, K, 20000):
+        k1 = min(K, k0 + 20000)
+        c = rng.normal(0, 1.5, k1 - k0)
+        a = rng.normal(0, 0.5, k1 - k0)
+        b = rng.normal(0, 0.5, k1 - k0)
+        p = 1.0 / (1.0 + np.exp(-(c[None, :] + z[:, :1] * a[None, :] + z[:, 1:] * b[None, :])))
+        x[:, k0:k1] = rng.binomial(2, p).astype(np.uint8)
+    y = ((loc - loc.mean(0)) / loc.std(0)).astype(np.float32)
+    return x, y
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.samples.append([t.strip() for t in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx.append(float(s[2]))
+                for nm, v in zip(names, s[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_steps(x, y, xv, yv, nsteps, threads):
+    """Oracle (reference restatement) timed on the host cores: nsteps optimizer steps."""
+    import torch
+    from oracle import model_ref
+
+    torch.set_num_threads(threads)
+    K = x.shape[1]
+    rng = np.random.default_rng(0)
+    ref = model_ref.RefLocator(K, H, L, dropout=0.25, seed=1)
+    n = len(x)
+    perm = rng.permutation(n)
+    ref.train_step(x[perm[:B]], y[perm[:B]], rng.uniform(size=(B, H)) >= 0.25)  # warm-up
+    t0 = time.perf_counter()
+    done = 0
+    while done < nsteps:
+        perm = rng.permutation(n)
+        for s in range(0, n, B):
+            rows = perm[s:s + B]
+            ref.train_step(x[rows], y[rows], rng.uniform(size=(len(rows), H)) >= 0.25)
+            done += 1
+            if done >= nsteps:
+                break
+    dt = time.perf_counter() - t0
+    return done * B / dt, dt
+
+
+def run_reference(args, workload):
+    """--impl reference: the reference's algorithm on the host CPU (oracle port; TF/Keras cannot be
+    installed on this image -- no wheel, no network), all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    n_total, K = WORKLOADS[workload]
+    ntr, nva = split_sizes(n_total)
+    x, y = synth(ntr + nva, K, 1002)
+    threads = os.cpu_count() or 1
+    # each bench "step" = a bounded sample of 4 optimizer steps, so the run ends within minutes
+    per = 4
+    total = (args.steps + args.warmup) * per
+    total = min(total, 400)
+    t_w = max(1, args.warmup * per)
+    cpu_steps(x[:ntr], y[:ntr], x[ntr:], y[ntr:], min(t_w, 8), threads)
+    nst = max(4, min(args.steps * per, 240))
+    val, dt = cpu_steps(x[:ntr], y[:ntr], x[ntr:], y[ntr:], nst, threads)
+    line = {
+        "impl": "reference", "metric": "train_samples_per_sec", "value": val, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * B / val,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{workload}: {n_total} samples x {K} SNPs, 1 model, batch 32, nlayers 10, width 256"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{nst} optimizer steps of the oracle (torch-CPU fp32 restatement of the Keras "
+                                   f"path; TensorFlow not installable here) in {dt:.1f} s"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=520)
+    ap.add_argument("--warmup", type=int, default=52)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=100)
+    args = ap.parse_args()
+    workload = args.workload
+    if args.impl == "reference":
+        run_reference(args, workload)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from locator_b200 import model, _cabi
+    from locator_b200.genotypes import PackedGenotypes
+    lib = _cabi.lib
+
+    n_total, K = WORKLOADS[workload]
+    ntr, nva = split_sizes(n_total)
+    spe = (ntr + B - 1) // B  # steps per epoch
+    x, y = synth(ntr + nva, K, 1002 + rank)
+    xtr, ytr, xva, yva = x[:ntr], y[:ntr], x[ntr:], y[ntr:]
+
+    steps, warm = args.steps, max(3, args.warmup)
+    n_ep_total = (steps + warm) // spe + 3
+    m = model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=n_ep_total + 2,
+                           seed=100 + rank)
+    gtr = m.bind_train(xtr, ytr)
+    m.bind_val(xva, yva)
+    m.set_schedule(patience=10 ** 6)
+    rng = np.random.default_rng(7 + rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def enqueue(nsteps):
+        """nsteps optimizer steps: whole epochs through loc_train_epochs, remainder loc_train_step."""
+        keep = []
+        ne, rem = divmod(nsteps, spe)
+        if ne:
+            p = torch.as_tensor(np.stack([rng.permutation(ntr) for _ in range(ne)]).astype(np.int32)).cuda()
+            keep.append(p)
+        rows = []
+        if rem:
+            perm = rng.permutation(ntr)
+            for s in range(rem):
+                r = torch.as_tensor(perm[s * B:(s + 1) * B].astype(np.int32)).cuda()
+                rows.append(r)
+        torch.cuda.synchronize()
+
+        def go():
+            if ne:
+                _cabi.check(lib.loc_train_epochs(m._h, keep[0].data_ptr(), ne, stream), "loc_train_epochs")
+            for r in rows:
+                _cabi.check(lib.loc_train_step(m._h, r.data_ptr(), int(r.numel()), stream), "loc_train_step")
+        return go, keep, rows
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    go_w, kw, rw = enqueue(warm)
+    go_w()
+    barrier()
+    go, kk, rr = enqueue(steps)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = _cabi.launch_count()
+    with ClockSampler(local) as clk:
+        ev0.record()
+        go()
+        ev1.record()
+        torch.cuda.synchronize()
+    launches = _cabi.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    st = m.state()
+    assert st.nonfinite == 0 and np.isfinite(st.last_loss), "non-finite loss during the timed region"
+    value = world * steps * B / (ms / 1000.0)
+
+    # ---- roofline: first-layer backward + Adam alone, CUDA events on the launching stream ----
+    rows_dev = torch.as_tensor(rng.permutation(ntr)[:B].astype(np.int32)).cuda()
+    for stage in (0, 1):
+        _cabi.check(lib.loc_debug_stage(m._h, stage, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
+    reps = 20
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i in range(3):
+        _cabi.check(lib.loc_debug_stage(m._h, 2, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
+    torch.cuda.synchronize()
+    for a, b in evs:
+        a.record()
+        _cabi.check(lib.loc_debug_stage(m._h, 2, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
+        b.record()
+    torch.cuda.synchronize()
+    bwd_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    fwd_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in fwd_evs:
+        a.record()
+        _cabi.check(lib.loc_debug_stage(m._h, 0, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
+        b.record()
+    torch.cuda.synchronize()
+    fwd_ms = float(np.mean([a.elapsed_time(b) for a, b in fwd_evs]))
+    hid_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in hid_evs:
+        a.record()
+        _cabi.check(lib.loc_debug_stage(m._h, 1, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
+        b.record()
+    torch.cuda.synchronize()
+    hid_ms = float(np.mean([a.elapsed_time(b) for a, b in hid_evs]))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = 24.0 * K * H
+    achieved = alg_bytes / (bwd_ms / 1000.0) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "l1_backward_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("K") == K:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "l1_backward_adam(" + m.impl + ")",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": bwd_ms,
+                "stage_ms": {"l1_forward": fwd_ms, "hidden": hid_ms, "l1_backward": bwd_ms},
+                "step_roofline_frac": (28.0 * K * H / 1e9 / peak) / (ms / 1000.0 / steps) }
+
+    # ---- e2e: fit() on host arrays (H2D + pack + the same number of steps + history D2H) ----
+    e2e = None
+    if True:
+        ne = max(1, steps // spe)
+        m2 = model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=ne + 1,
+                                seed=300 + rank)
+        xtr_p = torch.from_numpy(xtr).pin_memory()
+        xva_p = torch.from_numpy(xva).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        h = m2.fit(xtr_p, ytr, epochs=ne, validation_data=(xva_p, yva), patience=10 ** 6, epochs_per_call=ne)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        nst = ne * spe
+        assert len(h.history["loss"]) == ne and np.isfinite(h.history["loss"][-1])
+        h2d = xtr.nbytes + xva.nbytes + ytr.nbytes + yva.nbytes + ne * ntr * 4
+        e2e = {"value": world * ne * ntr / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d / nst,
+               "d2h_bytes_per_step": (ne * 12 + 64) / nst, "epochs": ne, "seconds": dt,
+               "what": "LocatorModel.fit on host uint8 matrices: H2D, 2-bit pack, epochs incl. validation, history D2H"}
+        del m2
+
+    line = {
+        "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps,
+        "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32" if m.impl == "tcgen05" else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{workload}: {n_total} samples x {K} SNPs ({ntr} train / {nva} val), 1 model per GPU, "
+                               f"batch {B}, nlayers {L}, width {H}",
+                   "l2": "inputs larger than L2 (W1+m+v = %.0f MB per step)" % (12.0 * K * H / 1e6),
+                   "steps_per_epoch": spe, "validation_pass_every_epoch": True},
+        "clocks": clk.summary(), "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, dt = cpu_steps(xtr, ytr, xva, yva, args.cpu_steps, os.cpu_count() or 1)
+        line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{args.cpu_steps} optimizer steps of the oracle (torch-CPU fp32 restatement "
+                                          f"of the Keras path) on the same workload, {dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,8 @@ int loc_replace_cols(uint32_t* d_packed, int64_t n, int64_t row_words, const int
 int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers, int32_t batch_size,
                      float dropout_prop, int32_t max_epochs);
 int loc_model_destroy(loc_model* m);
+/* First-layer kernel family this model actually runs: "tcgen05" or "simt". */
+const char* loc_model_impl(const loc_model* m);
 
 /* Philox glorot-uniform kernels, zero biases, gamma 1 / beta 0 / moving mean 0 /
  * moving var 1, zero Adam state, reset optimizer + callback state. `seed` also
@@ -181,6 +183,11 @@ int loc_snapshot(loc_model* m, void* stream);
 /* Synchronising reads of device-side state / history ([epoch][3] = loss, val_loss, lr). */
 int loc_model_state(loc_model* m, loc_state* h_out, void* stream);
 int loc_model_history(loc_model* m, float* h_out, int32_t max_rows, void* stream);
+
+/* Profiling / test hook: launch ONE stage of an optimizer step on rows d_rows[0..nb):
+ * 0 = first-layer forward, 1 = hidden stack (fwd + loss + bwd), 2 = first-layer backward + Adam,
+ * 3 = small-layer update.  Stages read the scratch the previous ones left.  Async. */
+int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t nb, void* stream);
 
 /* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
 int64_t loc_launch_count(void);

@@ -65,6 +65,7 @@ struct DevState {
   float loss_total, loss_count;  // Keras Mean(loss) accumulators for the epoch
   float val_total, val_count;
   int epoch;
+  int epoch0;     // epoch index at the start of the current loc_train_epochs call
   int stopped;
   int improved;
   int best_epoch;

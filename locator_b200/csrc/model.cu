@@ -1,0 +1,613 @@
+// loc_model: parameters, Adam state, checkpoint snapshot and the epoch driver.
+//
+// Reference: load_network locator/locator.py:311-327, load_callbacks :330-362, train_network
+// :365-394 (fit + reload of the best checkpoint), predict :414,441.  The callback state machine
+// (ModelCheckpoint -> EarlyStopping -> ReduceLROnPlateau, Keras semantics restated in
+// oracle/model_ref.py:CallbackState) runs on the device so a whole run of epochs is enqueued
+// without a host round trip; launches queued past the stopping epoch are no-ops.
+#include <math.h>
+#include <stdlib.h>
+
+#include <new>
+
+#include "model.cuh"
+#include "philox.cuh"
+
+using namespace loc;
+
+namespace loc {
+
+__global__ void k_fill(float* p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// Keras glorot_uniform with the Philox layout shared with oracle/philox_ref.py.
+__global__ void k_glorot(float* w, int64_t n, float limit, uint32_t stream, uint64_t seed) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float u = philox_uniform((uint64_t)i, stream, seed);
+    w[i] = (2.0f * u - 1.0f) * limit;
+  }
+}
+
+__global__ void k_state_reset(DevState* st, float lr, int patience, int max_epochs, int reset_opt) {
+  if (reset_opt) {
+    st->t = 0;
+    st->step_id = 0;
+    st->alpha = 0.f;
+  }
+  st->lr = lr;
+  st->loss_total = st->loss_count = st->val_total = st->val_count = 0.f;
+  st->epoch = 0;
+  st->epoch0 = 0;
+  st->stopped = 0;
+  st->improved = 0;
+  st->best_epoch = -1;
+  st->ckpt_best = st->es_best = st->rlr_best = INFINITY;
+  st->es_wait = st->rlr_wait = 0;
+  st->patience = patience;
+  st->rlr_patience = patience / 6;
+  st->max_epochs = max_epochs;
+  st->nonfinite = 0;
+  st->last_loss = st->last_val = 0.f;
+}
+
+__global__ void k_begin_call(DevState* st) { st->epoch0 = st->epoch; }
+__global__ void k_zero_val(DevState* st) { st->val_total = st->val_count = 0.f; }
+
+// on_epoch_end of History + [ModelCheckpoint, EarlyStopping, ReduceLROnPlateau] (locator.py:330-362).
+__global__ void k_epoch_end(DevState* st, float* hist) {
+  if (st->stopped) {
+    st->improved = 0;
+    return;
+  }
+  const int epoch = st->epoch;
+  const float loss = st->loss_total / st->loss_count;
+  const float val = st->val_total / st->val_count;
+  st->last_loss = loss;
+  st->last_val = val;
+  if (!isfinite(loss) || !isfinite(val)) st->nonfinite = 1;
+  // ModelCheckpoint(save_best_only, monitor=val_loss): strict improvement
+  const int save = val < st->ckpt_best;
+  if (save) {
+    st->ckpt_best = val;
+    st->best_epoch = epoch;
+  }
+  st->improved = save;
+  // EarlyStopping(min_delta=0, patience)
+  st->es_wait += 1;
+  int stop = 0;
+  if (val < st->es_best) {
+    st->es_best = val;
+    st->es_wait = 0;
+  } else if (st->es_wait >= st->patience && epoch > 0) {
+    stop = 1;
+  }
+  // ReduceLROnPlateau(factor .5, patience/6, min_delta 0, cooldown 0, min_lr 0): logs the lr first
+  const float lr_logged = st->lr;
+  if (val < st->rlr_best) {
+    st->rlr_best = val;
+    st->rlr_wait = 0;
+  } else {
+    st->rlr_wait += 1;
+    if (st->rlr_wait >= st->rlr_patience) {
+      if (st->lr > 0.f) st->lr = fmaxf(st->lr * 0.5f, 0.f);
+      st->rlr_wait = 0;
+    }
+  }
+  hist[3 * epoch + 0] = loss;
+  hist[3 * epoch + 1] = val;
+  hist[3 * epoch + 2] = lr_logged;
+  st->loss_total = st->loss_count = st->val_total = st->val_count = 0.f;
+  st->epoch = epoch + 1;
+  if (stop || epoch + 1 >= st->max_epochs) st->stopped = 1;
+}
+
+struct CopySegs {
+  float* dst[6];
+  const float* src[6];
+  int64_t n[6];
+  int count;
+};
+
+// ModelCheckpoint / load_weights as a device-to-device copy; `cond` (may be null) gates it.
+__global__ void __launch_bounds__(256) k_copy_segs(CopySegs cs, const int* cond) {
+  if (cond != nullptr && *cond == 0) return;
+  for (int s = 0; s < cs.count; ++s) {
+    const int64_t n4 = cs.n[s] / 4;
+    const float4* src = reinterpret_cast<const float4*>(cs.src[s]);
+    float4* dst = reinterpret_cast<float4*>(cs.dst[s]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+      dst[i] = src[i];
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cs.n[s];
+         i += (int64_t)gridDim.x * blockDim.x)
+      cs.dst[s][i] = cs.src[s][i];
+  }
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+static int fill(float* p, int64_t n, float v, cudaStream_t s) {
+  if (n <= 0) return 0;
+  int64_t blocks = cdiv(n, 256 * 8);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  k_fill<<<(unsigned)blocks, 256, 0, s>>>(p, n, v);
+  LOC_LAUNCHED();
+  return 0;
+}
+
+static int copy_weights(loc_model* m, bool to_best, const int* cond, cudaStream_t s) {
+  CopySegs cs;
+  float* live[6] = {m->W1, m->gamma, m->beta, m->mmean, m->mvar, m->small};
+  float* best[6] = {m->best_W1, m->best_gamma, m->best_beta, m->best_mmean, m->best_mvar, m->best_small};
+  const int64_t n[6] = {m->K * m->H, m->K, m->K, m->K, m->K, m->sl.total()};
+  for (int i = 0; i < 6; ++i) {
+    cs.dst[i] = to_best ? best[i] : live[i];
+    cs.src[i] = to_best ? live[i] : best[i];
+    cs.n[i] = n[i];
+  }
+  cs.count = 6;
+  k_copy_segs<<<sm_count() * 4, 256, 0, s>>>(cs, cond);
+  LOC_LAUNCHED();
+  return 0;
+}
+
+static L1Args l1_args(loc_model* m, const uint32_t* packed, int64_t row_words, const RowSrc& src, int training,
+                      int gated) {
+  L1Args a;
+  a.K = m->K;
+  a.H = m->H;
+  a.training = training;
+  a.gated = gated;
+  a.packed = packed;
+  a.row_words = row_words;
+  a.src = src;
+  a.gamma = m->gamma;
+  a.beta = m->beta;
+  a.mmean = m->mmean;
+  a.mvar = m->mvar;
+  a.W1 = m->W1;
+  a.m_gamma = m->m_gamma;
+  a.v_gamma = m->v_gamma;
+  a.m_beta = m->m_beta;
+  a.v_beta = m->v_beta;
+  a.mW1 = m->mW1;
+  a.vW1 = m->vW1;
+  a.partials = m->partials;
+  a.dZ1 = m->dzs;  // layer 0 slot
+  a.st = m->st;
+  return a;
+}
+
+static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated, const float* locs, float* pred_out) {
+  HidArgs h;
+  h.H = m->H;
+  h.L = m->L;
+  h.n_before = m->n_before;
+  h.training = training;
+  h.gated = gated;
+  h.has_targets = (!training && locs != nullptr) ? 1 : 0;
+  h.write_pred = pred_out != nullptr ? 1 : 0;
+  h.p_drop = m->p_drop;
+  h.seed = m->seed;
+  h.masks = m->masks;
+  h.n_masks = m->n_masks;
+  h.partials = m->partials;
+  h.n_partials = m->n_partials;
+  h.small = m->small;
+  h.acts = m->acts;
+  h.dzs = m->dzs;
+  h.outs = m->outs;
+  h.locs = locs;
+  h.src = src;
+  h.pred_out = pred_out;
+  h.st = m->st;
+  return h;
+}
+
+static int forward_l1(loc_model* m, const L1Args& a, cudaStream_t s) {
+  return m->use_tc ? l1_forward_tc(a, m->n_partials, s) : l1_forward_simt(a, m->n_partials, s);
+}
+
+// One optimizer step: 4 launches (stage_mask selects a subset for profiling / tests).
+static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s, int stage_mask = 15) {
+  L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, gated);
+  if ((stage_mask & 1) && forward_l1(m, a, s)) return 1;
+  HidArgs h = hid_args(m, src, 1, gated, m->train_locs, nullptr);
+  if ((stage_mask & 2) && hidden_launch(h, m->cluster, s)) return 1;
+  if ((stage_mask & 4) &&
+      (m->use_tc ? l1_backward_tc(a, m->n_bwd_blocks, s) : l1_backward_simt(a, m->n_bwd_blocks, s)))
+    return 1;
+  if (!(stage_mask & 8)) return 0;
+  UpdArgs u;
+  u.H = m->H;
+  u.L = m->L;
+  u.gated = gated;
+  u.small = m->small;
+  u.m_small = m->m_small;
+  u.v_small = m->v_small;
+  u.acts = m->acts;
+  u.dzs = m->dzs;
+  u.outs = m->outs;
+  u.nb = src.nb;
+  u.st = m->st;
+  return hidden_update_launch(u, s);
+}
+
+// Inference-mode forward over n rows in chunks of 32 (Keras predict/evaluate batch size).
+static int infer_rows(loc_model* m, const uint32_t* packed, int64_t n, int64_t row_words, const float* locs,
+                      float* pred_out, int gated, cudaStream_t s) {
+  for (int64_t r0 = 0; r0 < n; r0 += kMaxB) {
+    RowSrc src;
+    src.rows = nullptr;
+    src.epoch_stride = 0;
+    src.offset = 0;
+    src.row0 = (int32_t)r0;
+    src.nb = (int32_t)((n - r0) < kMaxB ? (n - r0) : kMaxB);
+    L1Args a = l1_args(m, packed, row_words, src, 0, gated);
+    if (forward_l1(m, a, s)) return 1;
+    HidArgs h = hid_args(m, src, 0, gated, locs, pred_out);
+    if (hidden_launch(h, m->cluster, s)) return 1;
+  }
+  return 0;
+}
+
+}  // namespace loc
+
+extern "C" {
+
+const char* loc_l1_impl(void) {
+  const char* e = getenv("LOC_L1_IMPL");
+  return (e != nullptr && strcmp(e, "simt") == 0) ? "simt" : "tcgen05";
+}
+
+int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers, int32_t batch_size,
+                     float dropout_prop, int32_t max_epochs) {
+  LOC_CHECK(out != nullptr, "loc_model_create: null output pointer");
+  *out = nullptr;
+  LOC_CHECK(K > 0, "loc_model_create: K must be positive");
+  LOC_CHECK(width >= 32 && width <= 1024 && width % 32 == 0, "loc_model_create: width must be a multiple of 32 in [32, 1024]");
+  LOC_CHECK(nlayers >= 2 && nlayers <= 64, "loc_model_create: nlayers must be in [2, 64]");
+  LOC_CHECK(batch_size >= 1 && batch_size <= LOC_MAX_BATCH, "loc_model_create: batch_size must be in [1, 32]");
+  LOC_CHECK(dropout_prop >= 0.f && dropout_prop < 1.f, "loc_model_create: dropout_prop must be in [0, 1)");
+  LOC_CHECK(max_epochs >= 1, "loc_model_create: max_epochs must be >= 1");
+  int ndev = 0;
+  LOC_CUDA(cudaGetDeviceCount(&ndev));
+  LOC_CHECK(ndev > 0, "loc_model_create: no CUDA device (this library has no CPU fallback)");
+  loc_model* m = new (std::nothrow) loc_model();
+  LOC_CHECK(m != nullptr, "loc_model_create: out of host memory");
+  memset(m, 0, sizeof(*m));
+  LOC_CUDA(cudaGetDevice(&m->dev));
+  m->K = K;
+  m->H = width;
+  m->L = nlayers;
+  m->B = batch_size;
+  m->n_before = nlayers / 2;
+  m->max_epochs = max_epochs;
+  m->p_drop = dropout_prop;
+  m->sl = SmallLayout{width, nlayers};
+  m->cluster = hidden_max_cluster(width);
+  if (m->cluster <= 0) {
+    delete m;
+    return loc::fail("loc_model_create: no usable thread-block cluster size for this width", __FILE__, __LINE__);
+  }
+  const char* impl = getenv("LOC_L1_IMPL");
+  m->use_tc = (impl == nullptr || strcmp(impl, "simt") != 0) && l1_tc_supported(K, width);
+  const int sms = sm_count();
+  if (m->use_tc) {
+    m->n_partials = l1_tc_partials(K);
+    m->n_bwd_blocks = m->n_partials;
+  } else {
+    const int64_t nch = cdiv(K, kF1Chunk);
+    m->n_partials = (int)(nch < 2 * sms ? nch : 2 * sms);
+    const int64_t nch2 = cdiv(K, 32);
+    m->n_bwd_blocks = (int)(nch2 < 2 * sms ? nch2 : 2 * sms);
+  }
+  const int64_t KH = K * width, ns = m->sl.total();
+  float** big[] = {&m->W1, &m->mW1, &m->vW1, &m->best_W1};
+  for (auto p : big) LOC_CUDA(cudaMalloc(p, KH * sizeof(float)));
+  float** kv[] = {&m->gamma, &m->beta, &m->mmean, &m->mvar, &m->m_gamma, &m->v_gamma, &m->m_beta,
+                  &m->v_beta, &m->best_gamma, &m->best_beta, &m->best_mmean, &m->best_mvar};
+  for (auto p : kv) LOC_CUDA(cudaMalloc(p, K * sizeof(float)));
+  float** sm[] = {&m->small, &m->m_small, &m->v_small, &m->best_small};
+  for (auto p : sm) LOC_CUDA(cudaMalloc(p, ns * sizeof(float)));
+  LOC_CUDA(cudaMalloc(&m->partials, (size_t)m->n_partials * kMaxB * width * sizeof(float)));
+  LOC_CUDA(cudaMalloc(&m->acts, (size_t)nlayers * kMaxB * width * sizeof(float)));
+  LOC_CUDA(cudaMalloc(&m->dzs, (size_t)nlayers * kMaxB * width * sizeof(float)));
+  LOC_CUDA(cudaMalloc(&m->outs, 256 * sizeof(float)));
+  LOC_CUDA(cudaMalloc(&m->hist, (size_t)max_epochs * 3 * sizeof(float)));
+  LOC_CUDA(cudaMalloc(&m->st, sizeof(DevState)));
+  LOC_CUDA(cudaMemset(m->st, 0, sizeof(DevState)));
+  LOC_CUDA(cudaMemset(m->dzs, 0, (size_t)nlayers * kMaxB * width * sizeof(float)));
+  LOC_CUDA(cudaMemset(m->acts, 0, (size_t)nlayers * kMaxB * width * sizeof(float)));
+  LOC_CUDA(cudaMemset(m->hist, 0, (size_t)max_epochs * 3 * sizeof(float)));
+  *out = m;
+  return 0;
+}
+
+int loc_model_destroy(loc_model* m) {
+  if (m == nullptr) return 0;
+  float* ptrs[] = {m->W1, m->mW1, m->vW1, m->best_W1, m->gamma, m->beta, m->mmean, m->mvar, m->m_gamma, m->v_gamma,
+                   m->m_beta, m->v_beta, m->best_gamma, m->best_beta, m->best_mmean, m->best_mvar, m->small,
+                   m->m_small, m->v_small, m->best_small, m->partials, m->acts, m->dzs, m->outs, m->hist};
+  for (float* p : ptrs)
+    if (p) cudaFree(p);
+  if (m->st) cudaFree(m->st);
+  delete m;
+  return 0;
+}
+
+const char* loc_model_impl(const loc_model* m) { return (m != nullptr && m->use_tc) ? "tcgen05" : "simt"; }
+
+int loc_model_init(loc_model* m, uint64_t seed, void* stream) {
+  LOC_CHECK(m != nullptr, "loc_model_init: null model");
+  cudaStream_t s = (cudaStream_t)stream;
+  m->seed = seed;
+  const int64_t K = m->K, H = m->H, L = m->L;
+  if (fill(m->gamma, K, 1.f, s) || fill(m->beta, K, 0.f, s) || fill(m->mmean, K, 0.f, s) || fill(m->mvar, K, 1.f, s))
+    return 1;
+  float* zeroK[] = {m->m_gamma, m->v_gamma, m->m_beta, m->v_beta};
+  for (float* p : zeroK)
+    if (fill(p, K, 0.f, s)) return 1;
+  if (fill(m->mW1, K * H, 0.f, s) || fill(m->vW1, K * H, 0.f, s)) return 1;
+  if (fill(m->small, m->sl.total(), 0.f, s) || fill(m->m_small, m->sl.total(), 0.f, s) ||
+      fill(m->v_small, m->sl.total(), 0.f, s))
+    return 1;
+  // Dense kernel i (0-based over the L+2 Dense layers) draws from Philox stream 16+i.
+  auto glorot = [&](float* w, int64_t fan_in, int64_t fan_out, int layer) -> int {
+    const float limit = (float)sqrt(6.0 / (double)(fan_in + fan_out));
+    const int64_t n = fan_in * fan_out;
+    int64_t blocks = cdiv(n, 256 * 4);
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    k_glorot<<<(unsigned)blocks, 256, 0, s>>>(w, n, limit, 16u + (uint32_t)layer, seed);
+    LOC_LAUNCHED();
+    return 0;
+  };
+  if (glorot(m->W1, K, H, 0)) return 1;
+  for (int i = 1; i < L; ++i)
+    if (glorot(m->small + m->sl.Wh(i), H, H, i)) return 1;
+  if (glorot(m->small + m->sl.Wo1(), H, 2, (int)L)) return 1;
+  if (glorot(m->small + m->sl.Wo2(), 2, 2, (int)L + 1)) return 1;
+  k_state_reset<<<1, 1, 0, s>>>(m->st, 1e-3f, 100, m->max_epochs, 1);
+  LOC_LAUNCHED();
+  return 0;
+}
+
+int loc_model_num_weights(const loc_model* m) { return m ? 4 + 2 * (m->L + 2) : 0; }
+
+namespace {
+// Keras order -> (pointer, Adam m, Adam v, length)
+struct WRef {
+  float *w, *am, *av;
+  int64_t n;
+};
+bool weight_ref(const loc_model* m, int idx, WRef* r) {
+  const int64_t K = m->K, H = m->H;
+  const int L = m->L;
+  if (idx < 0 || idx >= 4 + 2 * (L + 2)) return false;
+  switch (idx) {
+    case 0: *r = {m->gamma, m->m_gamma, m->v_gamma, K}; return true;
+    case 1: *r = {m->beta, m->m_beta, m->v_beta, K}; return true;
+    case 2: *r = {m->mmean, nullptr, nullptr, K}; return true;
+    case 3: *r = {m->mvar, nullptr, nullptr, K}; return true;
+    case 4: *r = {m->W1, m->mW1, m->vW1, K * H}; return true;
+    default: break;
+  }
+  const int d = (idx - 4) / 2, isb = (idx - 4) % 2;  // dense layer d in 0..L+1
+  int64_t off, n;
+  if (d == 0) {
+    off = m->sl.b1();
+    n = H;  // only the bias lands here (idx 5)
+  } else if (d < L) {
+    off = isb ? m->sl.bh(d) : m->sl.Wh(d);
+    n = isb ? H : H * H;
+  } else if (d == L) {
+    off = isb ? m->sl.bo1() : m->sl.Wo1();
+    n = isb ? 2 : 2 * H;
+  } else {
+    off = isb ? m->sl.bo2() : m->sl.Wo2();
+    n = isb ? 2 : 4;
+  }
+  *r = {m->small + off, m->m_small + off, m->v_small + off, n};
+  return true;
+}
+}  // namespace
+
+int64_t loc_model_weight_size(const loc_model* m, int32_t idx) {
+  WRef r;
+  if (m == nullptr || !weight_ref(m, idx, &r)) return -1;
+  return r.n;
+}
+
+int loc_model_set_weight(loc_model* m, int32_t idx, const float* h_src, int64_t n, void* stream) {
+  WRef r;
+  LOC_CHECK(m != nullptr && weight_ref(m, idx, &r), "loc_model_set_weight: bad weight index");
+  LOC_CHECK(n == r.n, "loc_model_set_weight: size mismatch");
+  LOC_CUDA(cudaMemcpyAsync(r.w, h_src, n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+int loc_model_get_weight(loc_model* m, int32_t idx, float* h_dst, int64_t n, void* stream) {
+  WRef r;
+  LOC_CHECK(m != nullptr && weight_ref(m, idx, &r), "loc_model_get_weight: bad weight index");
+  LOC_CHECK(n == r.n, "loc_model_get_weight: size mismatch");
+  LOC_CUDA(cudaMemcpyAsync(h_dst, r.w, n * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+int loc_model_get_adam(loc_model* m, int32_t idx, float* h_m, float* h_v, int64_t n, void* stream) {
+  WRef r;
+  LOC_CHECK(m != nullptr && weight_ref(m, idx, &r), "loc_model_get_adam: bad weight index");
+  LOC_CHECK(r.am != nullptr, "loc_model_get_adam: weight is not trainable");
+  LOC_CHECK(n == r.n, "loc_model_get_adam: size mismatch");
+  LOC_CUDA(cudaMemcpyAsync(h_m, r.am, n * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  LOC_CUDA(cudaMemcpyAsync(h_v, r.av, n * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+int loc_model_set_schedule(loc_model* m, float lr, int32_t patience) {
+  LOC_CHECK(m != nullptr, "loc_model_set_schedule: null model");
+  LOC_CHECK(patience >= 0, "loc_model_set_schedule: patience must be >= 0");
+  k_state_reset<<<1, 1>>>(m->st, lr, patience, m->max_epochs, 0);
+  LOC_LAUNCHED();
+  LOC_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+int loc_model_bind_train(loc_model* m, const uint32_t* d_packed, int64_t n, int64_t row_words, const float* d_locs) {
+  LOC_CHECK(m != nullptr && d_packed != nullptr && d_locs != nullptr && n > 0, "loc_model_bind_train: bad arguments");
+  LOC_CHECK(row_words >= cdiv(m->K, 16), "loc_model_bind_train: row_words too small for K");
+  m->train_packed = d_packed;
+  m->n_train = n;
+  m->train_row_words = row_words;
+  m->train_locs = d_locs;
+  return 0;
+}
+
+int loc_model_bind_val(loc_model* m, const uint32_t* d_packed, int64_t n, int64_t row_words, const float* d_locs) {
+  LOC_CHECK(m != nullptr && d_packed != nullptr && d_locs != nullptr && n > 0, "loc_model_bind_val: bad arguments");
+  LOC_CHECK(row_words >= cdiv(m->K, 16), "loc_model_bind_val: row_words too small for K");
+  m->val_packed = d_packed;
+  m->n_val = n;
+  m->val_row_words = row_words;
+  m->val_locs = d_locs;
+  return 0;
+}
+
+int loc_model_set_dropout_masks(loc_model* m, const uint8_t* d_keep, int64_t nsteps) {
+  LOC_CHECK(m != nullptr, "loc_model_set_dropout_masks: null model");
+  m->masks = d_keep;
+  m->n_masks = d_keep ? nsteps : 0;
+  return 0;
+}
+
+int loc_train_step(loc_model* m, const int32_t* d_rows, int32_t nb, void* stream) {
+  LOC_CHECK(m != nullptr && m->train_packed != nullptr, "loc_train_step: no training data bound");
+  LOC_CHECK(d_rows != nullptr && nb >= 1 && nb <= m->B, "loc_train_step: bad batch");
+  RowSrc src;
+  src.rows = d_rows;
+  src.epoch_stride = 0;
+  src.offset = 0;
+  src.row0 = 0;
+  src.nb = nb;
+  return train_step(m, src, 0, (cudaStream_t)stream);
+}
+
+int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t nb, void* stream) {
+  LOC_CHECK(m != nullptr && m->train_packed != nullptr, "loc_debug_stage: no training data bound");
+  LOC_CHECK(stage >= 0 && stage < 4 && d_rows != nullptr && nb >= 1 && nb <= m->B, "loc_debug_stage: bad arguments");
+  RowSrc src;
+  src.rows = d_rows;
+  src.epoch_stride = 0;
+  src.offset = 0;
+  src.row0 = 0;
+  src.nb = nb;
+  return train_step(m, src, 0, (cudaStream_t)stream, 1 << stage);
+}
+
+int loc_train_epochs(loc_model* m, const int32_t* d_perms, int32_t n_epochs, void* stream) {
+  LOC_CHECK(m != nullptr && m->train_packed != nullptr && m->val_packed != nullptr,
+            "loc_train_epochs: training and validation data must be bound");
+  LOC_CHECK(d_perms != nullptr && n_epochs >= 1, "loc_train_epochs: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  k_begin_call<<<1, 1, 0, s>>>(m->st);
+  LOC_LAUNCHED();
+  for (int e = 0; e < n_epochs; ++e) {
+    for (int64_t off = 0; off < m->n_train; off += m->B) {
+      RowSrc src;
+      src.rows = d_perms;
+      src.epoch_stride = m->n_train;
+      src.offset = off;
+      src.row0 = 0;
+      src.nb = (int32_t)((m->n_train - off) < m->B ? (m->n_train - off) : m->B);
+      if (train_step(m, src, 1, s)) return 1;
+    }
+    if (infer_rows(m, m->val_packed, m->n_val, m->val_row_words, m->val_locs, nullptr, 1, s)) return 1;
+    k_epoch_end<<<1, 1, 0, s>>>(m->st, m->hist);
+    LOC_LAUNCHED();
+    if (copy_weights(m, true, &m->st->improved, s)) return 1;
+  }
+  return 0;
+}
+
+int loc_eval(loc_model* m, const uint32_t* d_packed, int64_t n, int64_t row_words, const float* d_locs, float* h_loss,
+             void* stream) {
+  LOC_CHECK(m != nullptr && d_packed != nullptr && d_locs != nullptr && h_loss != nullptr && n > 0,
+            "loc_eval: bad arguments");
+  LOC_CHECK(row_words >= cdiv(m->K, 16), "loc_eval: row_words too small for K");
+  cudaStream_t s = (cudaStream_t)stream;
+  k_zero_val<<<1, 1, 0, s>>>(m->st);
+  LOC_LAUNCHED();
+  if (infer_rows(m, d_packed, n, row_words, d_locs, nullptr, 0, s)) return 1;
+  DevState h;
+  LOC_CUDA(cudaMemcpyAsync(&h, m->st, sizeof(h), cudaMemcpyDeviceToHost, s));
+  k_zero_val<<<1, 1, 0, s>>>(m->st);
+  LOC_LAUNCHED();
+  LOC_CUDA(cudaStreamSynchronize(s));
+  *h_loss = h.val_total / h.val_count;
+  return 0;
+}
+
+int loc_predict(loc_model* m, const uint32_t* d_packed, int64_t n, int64_t row_words, float* d_out, void* stream) {
+  LOC_CHECK(m != nullptr && d_out != nullptr, "loc_predict: bad arguments");
+  if (n <= 0) return 0;
+  LOC_CHECK(d_packed != nullptr && row_words >= cdiv(m->K, 16), "loc_predict: bad matrix");
+  return infer_rows(m, d_packed, n, row_words, nullptr, d_out, 0, (cudaStream_t)stream);
+}
+
+int loc_restore_best(loc_model* m, void* stream) {
+  LOC_CHECK(m != nullptr, "loc_restore_best: null model");
+  DevState h;
+  LOC_CUDA(cudaMemcpyAsync(&h, m->st, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  LOC_CHECK(h.best_epoch >= 0, "loc_restore_best: no checkpoint has been taken");
+  return copy_weights(m, false, nullptr, (cudaStream_t)stream);
+}
+
+int loc_snapshot(loc_model* m, void* stream) {
+  LOC_CHECK(m != nullptr, "loc_snapshot: null model");
+  return copy_weights(m, true, nullptr, (cudaStream_t)stream);
+}
+
+int loc_model_state(loc_model* m, loc_state* h_out, void* stream) {
+  LOC_CHECK(m != nullptr && h_out != nullptr, "loc_model_state: bad arguments");
+  DevState h;
+  LOC_CUDA(cudaMemcpyAsync(&h, m->st, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  h_out->t = h.t;
+  h_out->epoch = h.epoch;
+  h_out->stopped = h.stopped;
+  h_out->improved = h.improved;
+  h_out->best_epoch = h.best_epoch;
+  h_out->es_wait = h.es_wait;
+  h_out->rlr_wait = h.rlr_wait;
+  h_out->nonfinite = h.nonfinite;
+  h_out->lr = h.lr;
+  h_out->ckpt_best = h.ckpt_best;
+  h_out->last_loss = h.last_loss;
+  h_out->last_val_loss = h.last_val;
+  return 0;
+}
+
+int loc_model_history(loc_model* m, float* h_out, int32_t max_rows, void* stream) {
+  LOC_CHECK(m != nullptr && h_out != nullptr && max_rows >= 0, "loc_model_history: bad arguments");
+  const int rows = max_rows < m->max_epochs ? max_rows : m->max_epochs;
+  if (rows == 0) return 0;
+  LOC_CUDA(cudaMemcpyAsync(h_out, m->hist, (size_t)rows * 3 * sizeof(float), cudaMemcpyDeviceToHost,
+                           (cudaStream_t)stream));
+  LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// Internal layout of a loc_model and the launch interfaces between the translation units.
+//
+// One optimizer step of the reference (Keras fit on BN -> Dense(H,elu) x L -> Dense(2) -> Dense(2),
+// locator/locator.py:311-327,367-376) is four launches here:
+//
+//   L1 forward   (l1_simt.cu / l1_tc.cu)  batch BN statistics + folded-BN first Dense, split over SNPs;
+//                                         every CTA leaves a partial [32][H] tile of Z1
+//   hidden       (hidden.cu)              one thread-block cluster: reduce the partials, layers 1..L-1,
+//                                         Dense(2), Dense(2), loss, and the whole backward chain down to dZ1
+//   L1 backward  (l1_simt.cu / l1_tc.cu)  streams W1, m, v once: dW1 + Adam fused, BN gamma/beta Adam
+//   hidden update(hidden.cu)              dW + Adam of the small layers (off the critical path)
+#pragma once
+#include "common.cuh"
+
+namespace loc {
+
+constexpr int kMaxB = LOC_MAX_BATCH;  // batch rows per step (MMA N / K extent)
+constexpr int kF1Chunk = 64;          // SNPs per inner chunk of the SIMT first-layer kernels
+
+// Offsets (in floats) of the small parameters inside loc_model::small / m_small / v_small / best_small.
+struct SmallLayout {
+  int H, L;
+  __host__ __device__ int64_t b1() const { return 0; }
+  __host__ __device__ int64_t Wh(int i) const { return (int64_t)H + (int64_t)(i - 1) * H * H; }  // layer i in 1..L-1
+  __host__ __device__ int64_t bh(int i) const { return (int64_t)H + (int64_t)(L - 1) * H * H + (int64_t)(i - 1) * H; }
+  __host__ __device__ int64_t Wo1() const { return (int64_t)H + (int64_t)(L - 1) * H * H + (int64_t)(L - 1) * H; }
+  __host__ __device__ int64_t bo1() const { return Wo1() + 2 * H; }
+  __host__ __device__ int64_t Wo2() const { return bo1() + 2; }
+  __host__ __device__ int64_t bo2() const { return Wo2() + 4; }
+  __host__ __device__ int64_t total() const { return bo2() + 2; }
+};
+
+// Where a step takes its rows from. rows == nullptr: rows row0 .. row0+nb-1 (validation / predict).
+// Otherwise rows[(epoch - epoch0) * epoch_stride + offset + b] with epoch read from DevState on the
+// device, so the same launch sequence (or CUDA graph) serves every epoch.
+struct RowSrc {
+  const int32_t* rows;
+  int64_t epoch_stride;
+  int64_t offset;
+  int32_t row0;
+  int32_t nb;
+};
+
+__device__ __forceinline__ int64_t row_of(const RowSrc& r, const DevState* st, int b) {
+  if (r.rows == nullptr) return (int64_t)r.row0 + b;
+  const int64_t e = r.epoch_stride ? (int64_t)(st->epoch - st->epoch0) : 0;
+  return (int64_t)r.rows[e * r.epoch_stride + r.offset + b];
+}
+
+struct L1Args {
+  int64_t K;
+  int H;
+  int training;
+  int gated;  // no-op once DevState::stopped is set (launches queued past the early-stopping epoch)
+  const uint32_t* packed;
+  int64_t row_words;
+  RowSrc src;
+  float *gamma, *beta, *mmean, *mvar;
+  float* W1;
+  float *m_gamma, *v_gamma, *m_beta, *v_beta, *mW1, *vW1;
+  float* partials;   // [n_partials][kMaxB][H]
+  const float* dZ1;  // [kMaxB][H]
+  DevState* st;
+};
+
+struct HidArgs {
+  int H, L, n_before;
+  int training;
+  int gated;
+  int has_targets;  // inference: accumulate the validation loss against locs
+  int write_pred;  // inference: also store y2 rows to pred_out
+  float p_drop;
+  uint64_t seed;
+  const uint8_t* masks;  // test hook [nsteps][kMaxB][H] or nullptr
+  int64_t n_masks;
+  const float* partials;
+  int n_partials;
+  float* small;
+  float* acts;  // [L][kMaxB][H] post-dropout outputs of Dense(width) layer i
+  float* dzs;   // [L][kMaxB][H] d loss / d z_i
+  float* outs;  // y1[32][2], dy1[32][2], dy2[32][2], y2[32][2]
+  const float* locs;  // [n][2] targets of the bound matrix
+  RowSrc src;
+  float* pred_out;  // [n][2]
+  DevState* st;
+};
+
+struct UpdArgs {
+  int H, L;
+  int gated;
+  float *small, *m_small, *v_small;
+  const float* acts;
+  const float* dzs;
+  const float* outs;
+  int nb;
+  DevState* st;
+};
+
+// launchers (each returns 0 or sets the error)
+int l1_forward_simt(const L1Args& a, int n_partials, cudaStream_t s);
+int l1_backward_simt(const L1Args& a, int nblocks, cudaStream_t s);
+int hidden_launch(const HidArgs& a, int cluster, cudaStream_t s);
+int hidden_update_launch(const UpdArgs& a, cudaStream_t s);
+int hidden_max_cluster(int H);  // largest usable cluster size (16, 8, ...) for this device
+size_t hidden_smem_bytes(int H, int L, int cluster);
+
+// tcgen05 first layer (l1_tc.cu); available() is false when the shape is unsupported.
+bool l1_tc_supported(int64_t K, int H);
+int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s);
+int l1_backward_tc(const L1Args& a, int nblocks, cudaStream_t s);
+int l1_tc_partials(int64_t K);
+
+}  // namespace loc
+
+struct loc_model {
+  int dev;
+  int64_t K;
+  int H, L, B, n_before, max_epochs;
+  float p_drop;
+  uint64_t seed;
+  int cluster;
+  int n_partials;   // partial Z1 tiles the forward leaves
+  int n_bwd_blocks;
+  int use_tc;
+  loc::SmallLayout sl;
+  // parameters
+  float *gamma, *beta, *mmean, *mvar, *W1, *small;
+  // Adam moments
+  float *m_gamma, *v_gamma, *m_beta, *v_beta, *mW1, *vW1, *m_small, *v_small;
+  // ModelCheckpoint snapshot (weights only)
+  float *best_gamma, *best_beta, *best_mmean, *best_mvar, *best_W1, *best_small;
+  // workspaces
+  float *partials, *acts, *dzs, *outs, *hist, *pred_tmp;
+  loc::DevState* st;
+  // bound data
+  const uint32_t *train_packed, *val_packed;
+  int64_t n_train, train_row_words, n_val, val_row_words;
+  const float *train_locs, *val_locs;
+  const uint8_t* masks;
+  int64_t n_masks;
+};

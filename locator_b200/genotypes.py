@@ -1,0 +1,156 @@
+"""2-bit packed genotype matrices resident in HBM, and the ingest kernels over them.
+
+Host mirror of the integer half of the reference's ingest
+(``/root/reference/locator/locator.py``: filter_snps :265-281, split_train_test
+:295-308, bootstrap gather :648-653, jacknife replacement :721-727).  Every
+function here calls the CUDA library through the C ABI; torch only owns the
+device buffers.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import lib, check
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise _cabi.LocatorCudaError("locator_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def row_words_for(K: int) -> int:
+    """uint32 words per packed row: ceil(K/16) rounded up to a multiple of 4 (16-byte rows)."""
+    w = (int(K) + 15) // 16
+    return max(4, (w + 3) // 4 * 4)
+
+
+def _idx(x):
+    """Index array (host or device) -> int64 device tensor."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=_dev(), dtype=torch.int64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.int64))).to(_dev())
+
+
+def _as_dev(x, dtype):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=_dev(), dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(_dev())
+
+
+class PackedGenotypes:
+    """[n, K] alt-allele counts (0/1/2), sample-major, 2 bits each, in device memory."""
+
+    def __init__(self, words: torch.Tensor, n: int, K: int):
+        self.words = words  # int32 [n, row_words] (bit pattern of uint32)
+        self.n = int(n)
+        self.K = int(K)
+        self.row_words = int(words.shape[1]) if words.dim() == 2 else row_words_for(K)
+
+    @property
+    def ptr(self):
+        return self.words.data_ptr()
+
+    @staticmethod
+    def empty(n, K):
+        rw = row_words_for(K)
+        return PackedGenotypes(torch.zeros((max(int(n), 0), rw), dtype=torch.int32, device=_dev()), n, K)
+
+    # ---- uint8 [n, K] <-> packed -------------------------------------------------
+    @staticmethod
+    def from_counts(counts) -> "PackedGenotypes":
+        """counts: uint8 [n, K] array/tensor (host or device) -> packed on the GPU."""
+        c = _as_dev(counts, torch.uint8)
+        n, K = c.shape
+        out = PackedGenotypes.empty(n, K)
+        for r0 in range(0, n, 65535):
+            r1 = min(n, r0 + 65535)
+            check(lib.loc_pack_counts(c[r0:r1].data_ptr(), r1 - r0, K, out.words[r0:r1].data_ptr(), out.row_words,
+                                      _stream()), "loc_pack_counts")
+        return out
+
+    def to_counts(self) -> torch.Tensor:
+        out = torch.empty((self.n, self.K), dtype=torch.uint8, device=self.words.device)
+        for r0 in range(0, self.n, 65535):
+            r1 = min(self.n, r0 + 65535)
+            check(lib.loc_unpack_counts(self.words[r0:r1].data_ptr(), r1 - r0, self.K, self.row_words,
+                                        out[r0:r1].data_ptr(), _stream()), "loc_unpack_counts")
+        return out
+
+    # ---- gathers ---------------------------------------------------------------------
+    def take_rows(self, rows) -> "PackedGenotypes":
+        """out[r] = self[rows[r]]  (ac[:, idx] transposed, locator.py:303-307)."""
+        idx = _idx(rows)
+        n_out = int(idx.numel())
+        out = PackedGenotypes.empty(n_out, self.K)
+        for r0 in range(0, n_out, 65535):
+            r1 = min(n_out, r0 + 65535)
+            check(lib.loc_gather_rows(self.ptr, self.row_words, idx[r0:r1].data_ptr(), r1 - r0,
+                                      out.words[r0:r1].data_ptr(), _stream()), "loc_gather_rows")
+        return out
+
+    def take_cols(self, cols) -> "PackedGenotypes":
+        """out[:, k] = self[:, cols[k]]  (bootstrap site_order :651-653, max_SNPs :279)."""
+        idx = _idx(cols)
+        K_out = int(idx.numel())
+        out = PackedGenotypes.empty(self.n, K_out)
+        for r0 in range(0, self.n, 65535):
+            r1 = min(self.n, r0 + 65535)
+            check(lib.loc_gather_cols(self.words[r0:r1].data_ptr(), r1 - r0, self.row_words, idx.data_ptr(), K_out,
+                                      out.words[r0:r1].data_ptr(), out.row_words, _stream()), "loc_gather_cols")
+        return out
+
+    def clone(self) -> "PackedGenotypes":
+        return PackedGenotypes(self.words.clone(), self.n, self.K)
+
+    def replace_cols(self, sites, vals) -> None:
+        """self[:, sites[i]] = vals[i]  in place (jacknife :726-727); vals uint8 [nsites, n]."""
+        s = _idx(sites)
+        v = _as_dev(vals, torch.uint8)
+        assert v.shape == (s.numel(), self.n)
+        check(lib.loc_replace_cols(self.ptr, self.n, self.row_words, s.data_ptr(), int(s.numel()), v.data_ptr(),
+                                   _stream()), "loc_replace_cols")
+
+    def patch(self, ks, samps, vals) -> None:
+        """self[samps[i], ks[i]] = vals[i]  (imputed calls of replace_md :258-261)."""
+        k = _idx(ks)
+        s = _idx(samps)
+        v = _as_dev(np.asarray(vals, dtype=np.uint8), torch.uint8)
+        check(lib.loc_patch_calls(self.ptr, self.row_words, k.data_ptr(), s.data_ptr(), v.data_ptr(), int(k.numel()),
+                                  _stream()), "loc_patch_calls")
+
+
+def site_stats(gt, min_mac=2):
+    """Per-site allelism / alt count / missing calls / keep flag of GT int8 [nvar, N, 2] on the GPU.
+
+    Returns (n_alleles, alt_count, n_missing, keep) as device tensors (locator.py:267-273).
+    """
+    g = _as_dev(gt, torch.int8)
+    nvar, N, ploidy = g.shape
+    assert ploidy == 2
+    dev = g.device
+    na = torch.empty(nvar, dtype=torch.int32, device=dev)
+    alt = torch.empty(nvar, dtype=torch.int32, device=dev)
+    miss = torch.empty(nvar, dtype=torch.int32, device=dev)
+    keep = torch.empty(nvar, dtype=torch.uint8, device=dev)
+    check(lib.loc_site_stats(g.data_ptr(), nvar, N, int(min_mac), na.data_ptr(), alt.data_ptr(), miss.data_ptr(),
+                             keep.data_ptr(), _stream()), "loc_site_stats")
+    return g, na, alt, miss, keep
+
+
+def pack_sites(g: torch.Tensor, site_idx) -> PackedGenotypes:
+    """Pack the listed sites of device GT int8 [nvar, N, 2] -> PackedGenotypes [N, K]."""
+    idx = _idx(site_idx)
+    nvar, N, _ = g.shape
+    K = int(idx.numel())
+    out = PackedGenotypes.empty(N, K)
+    if K:
+        check(lib.loc_pack_sites(g.data_ptr(), nvar, N, idx.data_ptr(), K, out.ptr, out.row_words, _stream()),
+              "loc_pack_sites")
+    return out

@@ -1,0 +1,237 @@
+"""Host-side model object: the subset of the Keras ``Sequential`` API the reference uses.
+
+Mirrors what ``/root/reference/locator/locator.py`` calls on its model:
+``fit`` (:367-376) -> object with ``.history`` dict, ``predict`` (:414,441),
+``load_weights`` (:380,386), ``get_weights`` / ``set_weights`` in Keras order
+``[gamma, beta, moving_mean, moving_var, W1, b1, ..., Wo1, bo1, Wo2, bo2]``.
+All arithmetic happens in the CUDA library behind the C ABI (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import lib, check, LocState
+from .genotypes import PackedGenotypes, _as_dev, _stream, _dev
+
+
+class History:
+    def __init__(self):
+        self.history = {"loss": [], "val_loss": [], "learning_rate": []}
+        self.epoch = []
+
+
+class LocatorModel:
+    """BN(K) -> Dense(width, elu) x nlayers (Dropout in the middle) -> Dense(2) -> Dense(2)."""
+
+    def __init__(self, K, width=256, nlayers=10, dropout_prop=0.25, batch_size=32, max_epochs=5000, seed=0,
+                 learning_rate=1e-3):
+        _dev()
+        self.K, self.width, self.nlayers = int(K), int(width), int(nlayers)
+        self.batch_size, self.max_epochs = int(batch_size), int(max_epochs)
+        self.dropout_prop = float(dropout_prop)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.learning_rate = float(learning_rate)
+        h = C.c_void_p()
+        check(lib.loc_model_create(C.byref(h), self.K, self.width, self.nlayers, self.batch_size, self.dropout_prop,
+                                   self.max_epochs), "loc_model_create")
+        self._h = h
+        check(lib.loc_model_init(self._h, self.seed, _stream()), "loc_model_init")
+        self._keep = {}  # device tensors the handle points at
+        self.stop_training = False
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+            lib.loc_model_destroy(h)
+            self._h = None
+
+    @property
+    def impl(self):
+        return lib.loc_model_impl(self._h).decode()
+
+    # ---- weights (Keras order) -------------------------------------------------
+    def num_weights(self):
+        return int(lib.loc_model_num_weights(self._h))
+
+    def _shape(self, idx):
+        K, H, L = self.K, self.width, self.nlayers
+        if idx < 4:
+            return (K,)
+        d, isb = divmod(idx - 4, 2)
+        dims = [K] + [H] * L + [2, 2]
+        return (dims[d + 1],) if isb else (dims[d], dims[d + 1])
+
+    def get_weights(self):
+        out = []
+        for i in range(self.num_weights()):
+            n = int(lib.loc_model_weight_size(self._h, i))
+            a = np.empty(n, dtype=np.float32)
+            check(lib.loc_model_get_weight(self._h, i, a.ctypes.data, n, _stream()), "loc_model_get_weight")
+            out.append(a.reshape(self._shape(i)))
+        return out
+
+    def set_weights(self, ws):
+        if len(ws) != self.num_weights():
+            raise ValueError(f"expected {self.num_weights()} weight arrays, got {len(ws)}")
+        for i, w in enumerate(ws):
+            a = np.ascontiguousarray(np.asarray(w, dtype=np.float32))
+            if a.shape != self._shape(i):
+                raise ValueError(f"weight {i}: expected shape {self._shape(i)}, got {a.shape}")
+            check(lib.loc_model_set_weight(self._h, i, a.ctypes.data, a.size, _stream()), "loc_model_set_weight")
+
+    def get_adam(self, idx):
+        n = int(lib.loc_model_weight_size(self._h, idx))
+        m = np.empty(n, np.float32)
+        v = np.empty(n, np.float32)
+        check(lib.loc_model_get_adam(self._h, idx, m.ctypes.data, v.ctypes.data, n, _stream()), "loc_model_get_adam")
+        return m.reshape(self._shape(idx)), v.reshape(self._shape(idx))
+
+    def save_weights(self, path):
+        """Weights file of this build (.npz in Keras weight order; HDF5 is not available here)."""
+        ws = self.get_weights()
+        with open(path, "wb") as fh:
+            np.savez(fh, **{f"w{i:03d}": w for i, w in enumerate(ws)})
+
+    def load_weights(self, path):
+        with np.load(path) as z:
+            self.set_weights([z[k] for k in sorted(z.files)])
+
+    # ---- data binding ------------------------------------------------------------
+    @staticmethod
+    def _packed(x):
+        return x if isinstance(x, PackedGenotypes) else PackedGenotypes.from_counts(x)
+
+    def bind_train(self, x, y):
+        g = self._packed(x)
+        if g.K != self.K:
+            raise ValueError(f"training matrix has {g.K} SNPs, model expects {self.K}")
+        locs = _as_dev(np.asarray(y, dtype=np.float32), torch.float32)
+        check(lib.loc_model_bind_train(self._h, g.ptr, g.n, g.row_words, locs.data_ptr()), "loc_model_bind_train")
+        self._keep["train"] = (g, locs)
+        return g
+
+    def bind_val(self, x, y):
+        g = self._packed(x)
+        if g.K != self.K:
+            raise ValueError(f"validation matrix has {g.K} SNPs, model expects {self.K}")
+        locs = _as_dev(np.asarray(y, dtype=np.float32), torch.float32)
+        check(lib.loc_model_bind_val(self._h, g.ptr, g.n, g.row_words, locs.data_ptr()), "loc_model_bind_val")
+        self._keep["val"] = (g, locs)
+        return g
+
+    def set_dropout_masks(self, keep):
+        """Test hook: keep[step, 32, width] uint8 masks replace the Philox stream (None restores it)."""
+        if keep is None:
+            check(lib.loc_model_set_dropout_masks(self._h, None, 0), "loc_model_set_dropout_masks")
+            self._keep.pop("masks", None)
+            return
+        k = _as_dev(np.asarray(keep, dtype=np.uint8), torch.uint8)
+        assert k.dim() == 3 and k.shape[1] == 32 and k.shape[2] == self.width
+        check(lib.loc_model_set_dropout_masks(self._h, k.data_ptr(), k.shape[0]), "loc_model_set_dropout_masks")
+        self._keep["masks"] = k
+
+    def set_schedule(self, lr=None, patience=100):
+        check(lib.loc_model_set_schedule(self._h, float(self.learning_rate if lr is None else lr), int(patience)),
+              "loc_model_set_schedule")
+
+    # ---- training ------------------------------------------------------------------
+    def state(self) -> LocState:
+        st = LocState()
+        check(lib.loc_model_state(self._h, C.byref(st), _stream()), "loc_model_state")
+        return st
+
+    def train_step(self, rows):
+        r = _as_dev(np.asarray(rows, dtype=np.int32), torch.int32)
+        self._keep["rows"] = r
+        check(lib.loc_train_step(self._h, r.data_ptr(), int(r.numel()), _stream()), "loc_train_step")
+
+    def train_epochs(self, perms):
+        """perms int32 [n_epochs, n_train]; enqueues the epochs (asynchronous)."""
+        p = _as_dev(np.asarray(perms, dtype=np.int32), torch.int32)
+        self._keep.setdefault("perms", []).append(p)
+        check(lib.loc_train_epochs(self._h, p.data_ptr(), int(p.shape[0]), _stream()), "loc_train_epochs")
+
+    def history_rows(self, n):
+        a = np.zeros((max(n, 1), 3), dtype=np.float32)
+        if n > 0:
+            check(lib.loc_model_history(self._h, a.ctypes.data, n, _stream()), "loc_model_history")
+        return a[:n]
+
+    def fit(self, x, y, epochs=None, batch_size=None, shuffle=True, verbose=0, validation_data=None, callbacks=None,
+            patience=100, shuffle_seed=None, perms=None, epochs_per_call=16):
+        """Keras-style fit (locator.py:367-376): shuffled mini-batches, validation every epoch,
+        checkpoint-best / early stopping / reduce-LR-on-plateau.  Returns a History.
+
+        ``perms`` (optional [epochs, n]) fixes the batch order; otherwise each epoch draws a fresh
+        permutation from ``np.random.default_rng(shuffle_seed)`` (never from numpy's legacy global
+        stream, which the reference reserves for its own index draws).
+        """
+        if batch_size is not None and int(batch_size) != self.batch_size:
+            raise ValueError("batch_size differs from the one the model was created with")
+        if validation_data is None:
+            raise ValueError("validation_data is required (the reference always passes it)")
+        epochs = self.max_epochs if epochs is None else int(epochs)
+        if epochs > self.max_epochs:
+            raise ValueError("epochs exceeds max_epochs given at construction")
+        g = self.bind_train(x, y)
+        self.bind_val(*validation_data)
+        self.set_schedule(patience=patience)
+        n = g.n
+        rng = np.random.default_rng(self.seed if shuffle_seed is None else shuffle_seed)
+        self._keep["perms"] = []
+        done = 0
+        st = self.state()
+        while done < epochs and not st.stopped:
+            ne = min(epochs_per_call, epochs - done)
+            if perms is not None:
+                p = np.asarray(perms[done:done + ne], dtype=np.int32)
+            elif shuffle:
+                p = np.stack([rng.permutation(n) for _ in range(ne)]).astype(np.int32)
+            else:
+                p = np.tile(np.arange(n, dtype=np.int32), (ne, 1))
+            self.train_epochs(p)
+            done += ne
+            st = self.state()  # synchronises the stream
+            self._keep["perms"] = self._keep["perms"][-1:]
+            if verbose:
+                print(f"epoch {st.epoch}: loss {st.last_loss:.6f} val_loss {st.last_val_loss:.6f} lr {st.lr:g}")
+            if done >= epochs:
+                break
+        self.stop_training = bool(st.stopped)
+        h = History()
+        rows = self.history_rows(st.epoch)
+        h.history["loss"] = [float(v) for v in rows[:, 0]]
+        h.history["val_loss"] = [float(v) for v in rows[:, 1]]
+        h.history["learning_rate"] = [float(v) for v in rows[:, 2]]
+        h.epoch = list(range(st.epoch))
+        return h
+
+    def restore_best(self):
+        check(lib.loc_restore_best(self._h, _stream()), "loc_restore_best")
+
+    def snapshot(self):
+        check(lib.loc_snapshot(self._h, _stream()), "loc_snapshot")
+
+    # ---- inference -----------------------------------------------------------------
+    def predict(self, x, verbose=0):
+        g = self._packed(x)
+        if g.K != self.K:
+            raise ValueError(f"matrix has {g.K} SNPs, model expects {self.K}")
+        out = torch.zeros((g.n, 2), dtype=torch.float32, device=_dev())
+        check(lib.loc_predict(self._h, g.ptr, g.n, g.row_words, out.data_ptr(), _stream()), "loc_predict")
+        return out.cpu().numpy()
+
+    def evaluate(self, x, y, verbose=0):
+        g = self._packed(x)
+        locs = _as_dev(np.asarray(y, dtype=np.float32), torch.float32)
+        loss = C.c_float()
+        check(lib.loc_eval(self._h, g.ptr, g.n, g.row_words, locs.data_ptr(), C.byref(loss), _stream()), "loc_eval")
+        return float(loss.value)

@@ -1,0 +1,138 @@
+"""GPU parity: ingest kernels (through the C ABI) vs the CPU oracle -- bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def G():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from locator_b200 import genotypes
+
+    return genotypes
+
+
+def _rand_gt(rng, nvar, N, miss=0.05, multi=0.02):
+    p = rng.uniform(0, 1, size=(nvar, 1, 1)) ** 2
+    gt = (rng.uniform(size=(nvar, N, 2)) < p).astype(np.int8)
+    gt[rng.uniform(size=gt.shape) < multi] = 2
+    gt[rng.uniform(size=gt.shape) < miss] = -1
+    gt[0] = 0            # monomorphic
+    gt[1] = -1           # all missing
+    gt[2, :, :] = 1      # fixed alt
+    return gt
+
+
+def test_site_stats_and_pack_fixture(G, fixture_gt, golden_dir):
+    import json
+    from oracle import ingest_ref
+
+    gt = fixture_gt["calldata/GT"]
+    facts = json.load(open(os.path.join(golden_dir, "fixture_facts.json")))
+    g, na, alt, miss, keep = G.site_stats(gt, min_mac=2)
+    ac_ref, idx_ref = ingest_ref.filter_snps(gt, min_mac=2, return_index=True)
+    cnt = ingest_ref.count_alleles(gt)
+    assert np.array_equal(na.cpu().numpy(), (cnt > 0).sum(1))
+    assert np.array_equal(alt.cpu().numpy(), cnt[:, 1])
+    assert int(miss.sum()) == facts["n_missing_calls"]
+    idx = np.flatnonzero(keep.cpu().numpy())
+    assert len(idx) == facts["n_kept_min_mac_2"]
+    assert np.array_equal(idx, idx_ref)
+    packed = G.pack_sites(g, idx)
+    counts = packed.to_counts().cpu().numpy()  # [N, K]
+    assert np.array_equal(counts, ac_ref.T)
+
+
+@pytest.mark.parametrize("nvar,N,min_mac", [(300, 37, 2), (1000, 129, 1), (64, 500, 3), (17, 5, 2)])
+def test_site_stats_random(G, nvar, N, min_mac):
+    from oracle import ingest_ref
+
+    rng = np.random.default_rng(nvar * 7 + N)
+    gt = _rand_gt(rng, nvar, N)
+    g, na, alt, miss, keep = G.site_stats(gt, min_mac=min_mac)
+    cnt = ingest_ref.count_alleles(gt)
+    assert np.array_equal(na.cpu().numpy(), (cnt > 0).sum(1))
+    assert np.array_equal(alt.cpu().numpy(), cnt[:, 1] if cnt.shape[1] > 1 else 0 * cnt[:, 0])
+    assert np.array_equal(miss.cpu().numpy(), ingest_ref.is_missing(gt).sum(1))
+    ac_ref, idx_ref = ingest_ref.filter_snps(gt, min_mac=min_mac, return_index=True)
+    idx = np.flatnonzero(keep.cpu().numpy())
+    assert np.array_equal(idx, idx_ref)
+    packed = G.pack_sites(g, idx)
+    assert np.array_equal(packed.to_counts().cpu().numpy(), ac_ref.T)
+    # pad bits are zero
+    w = packed.words.cpu().numpy().view(np.uint32)
+    K = len(idx)
+    if K % 16:
+        assert np.all(w[:, K // 16] >> np.uint32(2 * (K % 16)) == 0)
+    assert np.all(w[:, (K + 15) // 16:] == 0)
+
+
+@pytest.mark.parametrize("n,K", [(1, 1), (3, 16), (45, 5830), (90, 100003), (7, 63)])
+def test_pack_unpack_gather(G, n, K):
+    rng = np.random.default_rng(n + K)
+    counts = rng.integers(0, 3, size=(n, K), dtype=np.uint8)
+    p = G.PackedGenotypes.from_counts(counts)
+    assert p.row_words % 4 == 0 and p.row_words * 16 >= K
+    assert np.array_equal(p.to_counts().cpu().numpy(), counts)
+    rows = rng.integers(0, n, size=2 * n + 1)
+    assert np.array_equal(p.take_rows(rows).to_counts().cpu().numpy(), counts[rows])
+    cols = rng.integers(0, K, size=K)  # bootstrap-style resample with replacement
+    assert np.array_equal(p.take_cols(cols).to_counts().cpu().numpy(), counts[:, cols])
+    sub = rng.permutation(K)[: max(1, K // 3)]  # max_SNPs-style subsample
+    assert np.array_equal(p.take_cols(sub).to_counts().cpu().numpy(), counts[:, sub])
+
+
+def test_replace_cols_matches_jacknife_oracle(G):
+    from oracle import ingest_ref
+
+    rng = np.random.default_rng(5)
+    n, K = 50, 4000
+    predgen = rng.integers(0, 3, size=(n, K), dtype=np.uint8)
+    af = rng.uniform(0.01, 0.99, size=K)
+    np.random.seed(777)
+    ref, sites = ingest_ref.jacknife_replace(predgen, af, 0.05)
+    # same draws, vectorised per site in the returned order
+    np.random.seed(777)
+    sites2 = np.random.choice(K, int(K * 0.05), replace=False)
+    vals = np.stack([np.random.binomial(2, af[i], n) for i in sites2]).astype(np.uint8)
+    assert np.array_equal(sites, sites2)
+    p = G.PackedGenotypes.from_counts(predgen)
+    p.replace_cols(sites2, vals)
+    assert np.array_equal(p.to_counts().cpu().numpy(), ref)
+
+
+def test_patch_calls(G):
+    rng = np.random.default_rng(9)
+    n, K = 33, 777
+    counts = rng.integers(0, 3, size=(n, K), dtype=np.uint8)
+    p = G.PackedGenotypes.from_counts(counts)
+    m = 500
+    flat = rng.permutation(n * K)[:m]
+    samp, ks = flat // K, flat % K
+    vals = rng.integers(0, 3, size=m, dtype=np.uint8)
+    p.patch(ks, samp, vals)
+    counts[samp, ks] = vals
+    assert np.array_equal(p.to_counts().cpu().numpy(), counts)
+
+
+def test_full_size_roundtrip_properties(G):
+    """BASELINE config 3 shape (2,500 x 200k): size-independent properties on the device."""
+    n, K = 2500, 200_000
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    counts = torch.randint(0, 3, (n, K), dtype=torch.uint8, device="cuda", generator=gen)
+    p = G.PackedGenotypes.from_counts(counts)
+    assert torch.equal(p.to_counts(), counts)
+    perm = torch.randperm(K, device="cuda", generator=gen)
+    q = p.take_cols(perm)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(K, device="cuda")
+    assert torch.equal(q.take_cols(inv).to_counts(), counts)  # gather by a permutation, then its inverse
+    rows = torch.randperm(n, device="cuda", generator=gen)
+    assert torch.equal(p.take_rows(rows).to_counts(), counts[rows])
+    assert int(p.to_counts().sum(dtype=torch.int64)) == int(counts.sum(dtype=torch.int64))

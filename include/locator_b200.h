@@ -189,6 +189,11 @@ int loc_model_history(loc_model* m, float* h_out, int32_t max_rows, void* stream
  * 3 = small-layer update.  Stages read the scratch the previous ones left.  Async. */
 int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t nb, void* stream);
 
+/* Test hook: copy a scratch buffer to the host (synchronises).  which: 0 = split-K partial tiles of
+ * Z1 [n_partials][32][width], 1 = dz of every Dense(width) layer [nlayers][32][width] (slot 0 = dZ1),
+ * 2 = activations [nlayers][32][width].  Returns the number of floats (written: min(count, max_n)), < 0 on error. */
+int64_t loc_debug_read(loc_model* m, int32_t which, float* h_dst, int64_t max_n, void* stream);
+
 /* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
 int64_t loc_launch_count(void);
 

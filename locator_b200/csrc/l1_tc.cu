@@ -1,8 +1,717 @@
-// tcgen05 first layer -- placeholder until the kernels land.
-#include "model.cuh"
+// First layer on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), width H = 256.
+//
+// Reference: BatchNormalization + Dense(256) forward / backward + Adam inside model.fit,
+// locator/locator.py:318-320,367-376; algebra in l1_simt.cu's header.  Both kernels are HBM-bound
+// streams over W1 (and m, v); the tensor cores remove the 2*32*256 FMA per SNP from the CUDA cores.
+//
+// FORWARD  (k_l1_fwd_tc), one persistent CTA per SM, split over SNPs:
+//   D[j, b] += W1[k, j]^T * xhat[k, b]      M = 128 (two halves of j), N = 32 (batch), K = 8 SNPs / MMA
+//   A = W1 tile, TMA-loaded as [8 j-chunks][32 SNP rows][128 B] with the 128B/32B-atom swizzle: the
+//       canonical MN-major tf32 operand layout, straight from the row-major fp32 master weights
+//       (kind::tf32 reads the fp32 bits; no conversion pass).
+//   B = xhat tile [32 SNP rows][32 batch = 128 B], built in shared memory by the builder warps from
+//       the 2-bit genotypes with the folded BatchNorm (x*inv + shift), rounded to tf32.
+//   warp 0: TMA producer | warp 1: TMEM alloc + MMA issue | warps 2-5: operand builders, epilogue.
+//   5-stage mbarrier ring; accumulators (2 x 32 columns) stay in TMEM for the whole K range; the
+//   epilogue writes one [32][256] partial tile per CTA (reduced in fixed order by k_hidden).
+//
+// BACKWARD (k_l1_bwd_tc), two CTAs per SM, split over SNPs, 64 SNPs per tile:
+//   S[j, k] = sum_b dZ1[b, j] * (x[b, k] - mean_k)   M = 128 (two halves of j), N = 64 SNPs, K = 8 rows / MMA
+//   A = dZ1 as hi + lo tf32 parts (MN-major, swizzled, built once per CTA), B = centred genotypes
+//   (K-major, swizzled; exact in tf32 for a full batch, hi + lo otherwise) -> S is fp32-accurate.
+//   Epilogue warps own accumulator row j = TMEM lane, so for every SNP a warp touches 128
+//   contiguous bytes of W1 / m / v: the Adam update streams W1, m, v exactly once with coalesced
+//   32-bit accesses; dW1 never exists in memory.  P_k, Q_k (for dgamma, dbeta) are reduced with a
+//   butterfly transpose across the warp and summed across warps in fixed order.
+//   warps 0-7: epilogue | warps 8-9: genotype unpack / BN statistics / gamma-beta Adam, MMA issue.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "l1_common.cuh"
+
 namespace loc {
-bool l1_tc_supported(int64_t, int) { return false; }
-int l1_tc_partials(int64_t) { return 0; }
-int l1_forward_tc(const L1Args&, int, cudaStream_t) { return fail("tcgen05 first layer not built", __FILE__, __LINE__); }
-int l1_backward_tc(const L1Args&, int, cudaStream_t) { return fail("tcgen05 first layer not built", __FILE__, __LINE__); }
+namespace tc {
+
+constexpr int kH = 256;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32 (fp32 bits in shared memory, fp32 accumulate).
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
+//   kLayoutSw128    : K-major operands, 16-byte chunks XOR (row & 7) within 128-byte rows
+//   kLayoutSw128B32 : MN-major tf32 operands -- the only swizzle the tensor core accepts for them:
+//                     32-byte chunks XOR (row & 3) within 128-byte rows (TMA: SWIZZLE_128B_ATOM_32B);
+//                     LBO = bytes between 32-element MN chunks, SBO = bytes between 4-row K groups
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128B32 = 1;
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): tf32 x tf32 -> f32.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// Row r of a swizzled [rows][128 B] tile, logical 16-byte chunk c:
+//   swz   (K-major SWIZZLE_128B):            chunk c lives at c ^ (r & 7)
+//   swz32 (MN-major SWIZZLE_128B, 32B atom): the 32-byte pair (c >> 1) lives at (c >> 1) ^ (r & 3)
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+__device__ __forceinline__ uint32_t swz32(int r, int c) {
+  return (uint32_t)(r * 128 + (((((c >> 1) ^ (r & 3)) << 1) | (c & 1)) << 4));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward
+// ---------------------------------------------------------------------------------------------
+constexpr int F_KT = 32;                              // SNPs per stage
+constexpr int F_STAGES = 5;
+constexpr int F_THREADS = 192;                        // 6 warps
+constexpr int F_WBYTES = F_KT * kH * 4;               // 32 KB: [8 chunks][32 rows][128 B]
+constexpr int F_CHUNK = F_KT * 128;                   // bytes between j-chunks (LBO)
+constexpr int F_XBYTES = F_KT * 128;                  // 4 KB:  [32 rows][32 batch]
+constexpr int F_SMEM = F_STAGES * (F_WBYTES + F_XBYTES) + 4 * 32 * 8 + 256 + 1024;  // + bits scratch + barriers + align
+
+__global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(const __grid_constant__ CUtensorMap wmap, int tma_rank,
+                                                          L1Args a, int64_t ntiles) {
+  if (a.gated && a.st->stopped) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = sm;
+  uint8_t* sX = sW + F_STAGES * F_WBYTES;
+  uint32_t* sBits = (uint32_t*)(sX + F_STAGES * F_XBYTES);  // [4 warps][32 rows][2 words]
+  uint64_t* bars = (uint64_t*)(sBits + 4 * 32 * 2);
+  uint64_t* full_w = bars;
+  uint64_t* full_x = bars + F_STAGES;
+  uint64_t* empty = bars + 2 * F_STAGES;
+  uint64_t* done = bars + 3 * F_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * F_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = a.src.nb;
+  const int64_t t_begin = ntiles * blockIdx.x / gridDim.x;
+  const int64_t t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+  const int nloc = (int)(t_end - t_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < F_STAGES; ++s) {
+      mbar_init(&full_w[s], 1);
+      mbar_init(&full_x[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- TMA producer ----
+    if (lane == 0) {
+      for (int li = 0; li < nloc; ++li) {
+        const int s = li % F_STAGES;
+        const uint32_t ph = (uint32_t)(li / F_STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_w[s], F_WBYTES);
+        const int k0 = (int)((t_begin + li) * F_KT);
+        if (tma_rank == 3) {
+          tma_load_3d(smem_u32(sW + s * F_WBYTES), &wmap, &full_w[s], 0, k0, 0);
+        } else {
+          for (int c = 0; c < 8; ++c)
+            tma_load_2d(smem_u32(sW + s * F_WBYTES + c * F_CHUNK), &wmap, &full_w[s], 32 * c, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----
+    constexpr uint32_t idesc = make_idesc(128, 32, 1, 1);
+    if (lane == 0) {
+      for (int li = 0; li < nloc; ++li) {
+        const int s = li % F_STAGES;
+        const uint32_t ph = (uint32_t)(li / F_STAGES) & 1u;
+        mbar_wait(&full_w[s], ph);
+        mbar_wait(&full_x[s], ph);
+        tc_fence_after();
+        const uint32_t wbase = smem_u32(sW + s * F_WBYTES), xbase = smem_u32(sX + s * F_XBYTES);
+#pragma unroll
+        for (int ks = 0; ks < F_KT / 8; ++ks) {
+          const uint64_t bdesc = smem_desc(xbase + ks * 1024, F_CHUNK, 512, kLayoutSw128B32);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t adesc = smem_desc(wbase + h * 4 * F_CHUNK + ks * 1024, F_CHUNK, 512, kLayoutSw128B32);
+            umma_tf32(tmem + h * 32, adesc, bdesc, idesc, (li > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(done);
+    }
+  } else {
+    // ---- operand builders (warps 2..5), then epilogue ----
+    const int wi = warp - 2;
+    uint32_t* bits = sBits + wi * 64;
+    const int64_t my_row = lane < nb ? row_of(a.src, a.st, lane) : 0;
+    const uint32_t* my_ptr = a.packed + my_row * a.row_words;
+    for (int li = wi; li < nloc; li += 4) {
+      const int s = li % F_STAGES;
+      const uint32_t ph = (uint32_t)(li / F_STAGES) & 1u;
+      const int64_t tile = t_begin + li;
+      // lane <-> batch row: this tile's 32 genotypes of the row (2 words)
+      uint2 w2 = make_uint2(0u, 0u);
+      if (lane < nb && tile * 2 + 1 < a.row_words) w2 = __ldg(reinterpret_cast<const uint2*>(my_ptr + tile * 2));
+      // lane <-> SNP: per-SNP parameters
+      const int64_t k = tile * F_KT + lane;
+      const bool valid = k < a.K;
+      float gamma = 0.f, beta = 0.f, mm = 0.f, mv = 1.f;
+      if (valid) {
+        gamma = a.gamma[k];
+        beta = a.beta[k];
+        mm = a.mmean[k];
+        mv = a.mvar[k];
+      }
+      bits[lane * 2] = w2.x;
+      bits[lane * 2 + 1] = w2.y;
+      __syncwarp();
+      const int wsel = lane >> 4, sh = 2 * (lane & 15);
+      unsigned long long g = 0ull;
+      int n1 = 0, n2 = 0;
+#pragma unroll
+      for (int b = 0; b < kMaxB; ++b) {
+        const unsigned x = (bits[b * 2 + wsel] >> sh) & 3u;  // rows >= nb hold zeros
+        g |= (unsigned long long)x << (2 * b);
+        n1 += (x == 1u);
+        n2 += (x == 2u);
+      }
+      __syncwarp();
+      float mean, var;
+      if (a.training) {
+        moments_from_counts(n1, n2, nb, mean, var);
+        if (valid) {
+          a.mmean[k] = mm * kBnMom + mean * kBnOneMinusMom;
+          a.mvar[k] = mv * kBnMom + var * kBnOneMinusMom;
+        }
+      } else {
+        mean = mm;
+        var = mv;
+      }
+      const float inv = rsqrtf(var + kBnEps) * gamma;
+      const float shift = beta - mean * inv;
+      float lut[3];
+      lut[0] = valid ? to_tf32(shift) : 0.f;
+      lut[1] = valid ? to_tf32(inv + shift) : 0.f;
+      lut[2] = valid ? to_tf32(2.f * inv + shift) : 0.f;
+      mbar_wait(&empty[s], ph ^ 1u);
+      uint8_t* xrow = sX + s * F_XBYTES;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int b = 4 * c + e;
+          const unsigned x = (unsigned)((g >> (2 * b)) & 3ull);
+          const float val = x == 0u ? lut[0] : (x == 1u ? lut[1] : lut[2]);
+          v[e] = b < nb ? val : 0.f;
+        }
+        *reinterpret_cast<float4*>(xrow + swz32(lane, c)) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_x[s]);
+    }
+    // ---- epilogue: accumulator row = j (TMEM lane), column = batch row ----
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float* out = a.partials + (int64_t)blockIdx.x * kMaxB * kH;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[32];
+      tmem_ld_x32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * 32), r);
+      tmem_ld_wait();
+      const int j = h * 128 + 32 * q + lane;
+#pragma unroll
+      for (int b = 0; b < kMaxB; ++b) out[b * kH + j] = __uint_as_float(r[b]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 64);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward + Adam
+// ---------------------------------------------------------------------------------------------
+constexpr int B_NT = 64;                       // SNPs per tile
+constexpr int B_EPI_WARPS = 8;
+constexpr int B_THREADS = 320;                 // 8 epilogue warps + 2 builder warps
+constexpr int B_DZ = kMaxB * kH * 4;           // 32 KB: [8 chunks][32 rows (b)][128 B]
+constexpr int B_DZ_CHUNK = kMaxB * 128;        // 4096
+constexpr int B_X = B_NT * 128;                // 8 KB: [64 rows (SNP)][32 batch]
+constexpr int B_SMEM = 2 * B_DZ + 4 * B_X + 2 * B_NT * 16 + 2 * B_EPI_WARPS * B_NT * 8 + 2 * 32 * 8 + 256 + 1024;
+
+__device__ __forceinline__ void adam_update_fast(float& w, float& m, float& v, float g, float alpha) {
+  m = m + (g - m) * kAdam1mB1;
+  v = v + (g * g - v) * kAdam1mB2;
+  w = w - __fdividef(m * alpha, sqrtf(v) + kAdamEps);
+}
+
+__global__ void __launch_bounds__(B_THREADS, 2) k_l1_bwd_tc(L1Args a, int64_t ntiles) {
+  if (a.gated && a.st->stopped) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sDZhi = sm;
+  uint8_t* sDZlo = sDZhi + B_DZ;
+  uint8_t* sXhi = sDZlo + B_DZ;                  // [2][B_X]
+  uint8_t* sXlo = sXhi + 2 * B_X;                // [2][B_X]
+  float4* sSc = (float4*)(sXlo + 2 * B_X);       // [2][64] (inv, beta, -, -)
+  float2* sRed = (float2*)(sSc + 2 * B_NT);      // [2][8 warps][64] (P, Q) partial sums
+  uint32_t* sBits = (uint32_t*)(sRed + 2 * B_EPI_WARPS * B_NT);  // [2 builder warps][32 rows][2 words]
+  uint64_t* bars = (uint64_t*)(sBits + 2 * 32 * 2);
+  uint64_t* tmem_full = bars;       // [2]
+  uint64_t* tmem_empty = bars + 2;  // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = a.src.nb;
+  const bool need_lo = (nb & (nb - 1)) != 0;  // centred genotypes are multiples of 1/nb: exact in tf32 iff nb = 2^n
+  const int64_t t_begin = ntiles * blockIdx.x / gridDim.x;
+  const int64_t t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+  const int nloc = (int)(t_end - t_begin);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], B_EPI_WARPS);
+    mbar_init(&tmem_empty[1], B_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == B_EPI_WARPS) tmem_alloc(tmem_slot, 256);
+  // dZ1 -> hi/lo tf32 operands, [chunk = j/32][row = b][swizzled 32 j]
+  for (int i = threadIdx.x; i < kMaxB * kH / 4; i += B_THREADS) {
+    const int b = i / (kH / 4), j4 = (i % (kH / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b < nb) v = __ldcg(reinterpret_cast<const float4*>(a.dZ1 + b * kH + j4));
+    const float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    const float4 lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z), to_tf32(v.w - hi.w));
+    const uint32_t off = (uint32_t)((j4 >> 5) * B_DZ_CHUNK) + swz32(b, (j4 & 31) >> 2);
+    *reinterpret_cast<float4*>(sDZhi + off) = hi;
+    *reinterpret_cast<float4*>(sDZlo + off) = lo;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float alpha = a.st->alpha;
+
+  if (warp < B_EPI_WARPS) {
+    // =========================== epilogue warps ===========================
+    const int h = warp >> 2, q = warp & 3;
+    const int j = h * 128 + q * 32 + lane;
+    float c0 = 0.f;
+    for (int b = 0; b < nb; ++b) c0 += __ldcg(a.dZ1 + b * kH + j);
+    for (int li = 0; li < nloc; ++li) {
+      const int buf = li & 1;
+      const int64_t k0 = (t_begin + li) * B_NT;
+      mbar_wait(&tmem_full[buf], (uint32_t)(li >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 128 + h * 64);
+#pragma unroll 1
+      for (int c = 0; c < B_NT / 8; ++c) {
+        uint32_t gr[8];
+        tmem_ld_x8(tbase + c * 8, gr);
+        float w[8], m[8], v[8];
+        const int64_t kc = k0 + c * 8;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          const int64_t idx = (kc + s) * kH + j;
+          const bool ok = kc + s < a.K;
+          w[s] = ok ? a.W1[idx] : 0.f;
+          m[s] = ok ? a.mW1[idx] : 0.f;
+          v[s] = ok ? a.vW1[idx] : 0.f;
+        }
+        tmem_ld_wait();
+        float pq[16];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          const float4 sc = sSc[buf * B_NT + c * 8 + s];
+          const float S = __uint_as_float(gr[s]);
+          const float g = sc.x * S + sc.y * c0;
+          pq[s] = w[s] * S;
+          pq[8 + s] = w[s] * c0;
+          adam_update_fast(w[s], m[s], v[s], g, alpha);
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (kc + s < a.K) {
+            const int64_t idx = (kc + s) * kH + j;
+            a.W1[idx] = w[s];
+            a.mW1[idx] = m[s];
+            a.vW1[idx] = v[s];
+          }
+        }
+        // butterfly transpose-reduce: lane l ends with the warp total of pq[l & 15]
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+          const bool up = (lane & o) != 0;
+#pragma unroll
+          for (int i = 0; i < o; ++i) {
+            const float send = up ? pq[i] : pq[i + o];
+            const float keep = up ? pq[i + o] : pq[i];
+            pq[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        pq[0] += __shfl_xor_sync(0xffffffffu, pq[0], 16);
+        if (lane < 16) {
+          float* dst = reinterpret_cast<float*>(&sRed[(buf * B_EPI_WARPS + warp) * B_NT + c * 8 + (lane & 7)]);
+          dst[lane >> 3] = pq[0];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  } else {
+    // =========================== builder warps (2 x 32 SNPs per tile) ===========================
+    constexpr uint32_t idesc = make_idesc(128, B_NT, 1, 0);
+    const int wb = warp - B_EPI_WARPS;  // 0 / 1: which half of the tile's SNPs
+    uint32_t* bits = sBits + wb * 64;
+    const int64_t my_row = lane < nb ? row_of(a.src, a.st, lane) : 0;
+    const uint32_t* my_ptr = a.packed + my_row * a.row_words;
+    // per-SNP state of the two tiles in flight (this lane's SNP): for the gamma/beta update
+    float rs_[2] = {0.f, 0.f}, gam_[2] = {0.f, 0.f}, bet_[2] = {0.f, 0.f}, mg_[2] = {0.f, 0.f}, vg_[2] = {0.f, 0.f},
+          mb_[2] = {0.f, 0.f}, vb_[2] = {0.f, 0.f};
+    auto finalize = [&](int li) {
+      // gamma/beta Adam of tile li once its epilogue has left P, Q in shared memory
+      const int buf = li & 1;
+      mbar_wait(&tmem_empty[buf], (uint32_t)(li >> 1) & 1u);
+      const int64_t k = (t_begin + li) * B_NT + wb * 32 + lane;
+      float P = 0.f, Q = 0.f;
+#pragma unroll
+      for (int w = 0; w < B_EPI_WARPS; ++w) {
+        const float2 r = sRed[(buf * B_EPI_WARPS + w) * B_NT + wb * 32 + lane];
+        P += r.x;
+        Q += r.y;
+      }
+      if (k < a.K) {
+        float gm = gam_[buf], m = mg_[buf], v = vg_[buf];
+        adam_update(gm, m, v, rs_[buf] * P, alpha);
+        a.gamma[k] = gm;
+        a.m_gamma[k] = m;
+        a.v_gamma[k] = v;
+        float bt = bet_[buf];
+        m = mb_[buf];
+        v = vb_[buf];
+        adam_update(bt, m, v, Q, alpha);
+        a.beta[k] = bt;
+        a.m_beta[k] = m;
+        a.v_beta[k] = v;
+      }
+    };
+    for (int li = 0; li < nloc; ++li) {
+      const int buf = li & 1;
+      const int64_t tile = t_begin + li;
+      // lane <-> batch row: the 32 genotypes of this builder warp's half tile
+      uint2 w2 = make_uint2(0u, 0u);
+      const int64_t wofs = tile * 4 + wb * 2;
+      if (lane < nb && wofs + 1 < a.row_words) w2 = __ldg(reinterpret_cast<const uint2*>(my_ptr + wofs));
+      const int64_t k = tile * B_NT + wb * 32 + lane;
+      const bool valid = k < a.K;
+      float gm = 0.f, bt = 0.f, mg = 0.f, vg = 0.f, mb = 0.f, vb = 0.f;
+      if (valid) {
+        gm = a.gamma[k];
+        bt = a.beta[k];
+        mg = a.m_gamma[k];
+        vg = a.v_gamma[k];
+        mb = a.m_beta[k];
+        vb = a.v_beta[k];
+      }
+      // the buffers of tile li-2 must be drained (and its gamma/beta update done) before reuse
+      if (li >= 2) finalize(li - 2);
+      bits[lane * 2] = w2.x;
+      bits[lane * 2 + 1] = w2.y;
+      __syncwarp();
+      const int wsel = lane >> 4, sh = 2 * (lane & 15);
+      unsigned long long g = 0ull;
+      int n1 = 0, n2 = 0;
+#pragma unroll
+      for (int b = 0; b < kMaxB; ++b) {
+        const unsigned x = (bits[b * 2 + wsel] >> sh) & 3u;
+        g |= (unsigned long long)x << (2 * b);
+        n1 += (x == 1u);
+        n2 += (x == 2u);
+      }
+      __syncwarp();
+      float mean, var;
+      moments_from_counts(n1, n2, nb, mean, var);
+      const float rs = rsqrtf(var + kBnEps);
+      rs_[buf] = rs;
+      gam_[buf] = gm;
+      bet_[buf] = bt;
+      mg_[buf] = mg;
+      vg_[buf] = vg;
+      mb_[buf] = mb;
+      vb_[buf] = vb;
+      sSc[buf * B_NT + wb * 32 + lane] = make_float4(valid ? rs * gm : 0.f, valid ? bt : 0.f, 0.f, 0.f);
+      float chi[3], clo[3];
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        const float cx = valid ? (float)x - mean : 0.f;
+        chi[x] = to_tf32(cx);
+        clo[x] = to_tf32(cx - chi[x]);
+      }
+      const int r = wb * 32 + lane;
+      uint8_t* xh = sXhi + buf * B_X;
+      uint8_t* xl = sXlo + buf * B_X;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float vh[4], vl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int b = 4 * c + e;
+          const unsigned x = (unsigned)((g >> (2 * b)) & 3ull);
+          const bool on = b < nb;
+          vh[e] = on ? (x == 0u ? chi[0] : (x == 1u ? chi[1] : chi[2])) : 0.f;
+          vl[e] = on ? (x == 0u ? clo[0] : (x == 1u ? clo[1] : clo[2])) : 0.f;
+        }
+        *reinterpret_cast<float4*>(xh + swz(r, c)) = make_float4(vh[0], vh[1], vh[2], vh[3]);
+        if (need_lo) *reinterpret_cast<float4*>(xl + swz(r, c)) = make_float4(vl[0], vl[1], vl[2], vl[3]);
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 64;" ::: "memory");  // both builder warps have written their half
+      if (wb == 0 && lane == 0) {
+        tc_fence_after();
+        const uint32_t xhb = smem_u32(xh), xlb = smem_u32(xl);
+        const uint32_t dhi = smem_u32(sDZhi), dlo = smem_u32(sDZlo);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t d = tmem + (uint32_t)(buf * 128 + hh * 64);
+          uint32_t acc = 0u;
+#pragma unroll
+          for (int ks = 0; ks < kMaxB / 8; ++ks) {
+            const uint64_t a_hi = smem_desc(dhi + hh * 4 * B_DZ_CHUNK + ks * 1024, B_DZ_CHUNK, 512, kLayoutSw128B32);
+            const uint64_t a_lo = smem_desc(dlo + hh * 4 * B_DZ_CHUNK + ks * 1024, B_DZ_CHUNK, 512, kLayoutSw128B32);
+            const uint64_t b_hi = smem_desc(xhb + ks * 32, 16, 1024, kLayoutSw128);
+            umma_tf32(d, a_hi, b_hi, idesc, acc);
+            acc = 1u;
+            umma_tf32(d, a_lo, b_hi, idesc, acc);
+            if (need_lo) {
+              const uint64_t b_lo = smem_desc(xlb + ks * 32, 16, 1024, kLayoutSw128);
+              umma_tf32(d, a_hi, b_lo, idesc, acc);
+            }
+          }
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+    if (nloc >= 2) finalize(nloc - 2);
+    if (nloc >= 1) finalize(nloc - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == B_EPI_WARPS) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+static int g_tc_sms = 0;
+static int tc_sm_count() {
+  if (!g_tc_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_tc_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_tc_sms <= 0) g_tc_sms = 148;
+  }
+  return g_tc_sms;
+}
+
+bool l1_tc_supported(int64_t K, int H) {
+  if (H != tc::kH || K < 1) return false;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10;
+}
+
+int l1_tc_partials(int64_t K) {
+  const int64_t ntiles = cdiv(K, tc::F_KT);
+  return (int)(ntiles < tc_sm_count() ? ntiles : tc_sm_count());
+}
+
+int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s) {
+  // W1 viewed as [8 j-chunks][K SNPs][32 floats]: one TMA box = the whole [8][32][32] stage tile
+  static thread_local const float* cached_w = nullptr;
+  static thread_local int64_t cached_k = 0;
+  static thread_local CUtensorMap map;
+  static thread_local int tma_rank = 3;
+  if (cached_w != a.W1 || cached_k != a.K) {
+    cuuint64_t dims[3] = {32, (cuuint64_t)a.K, 8};
+    cuuint64_t strides[2] = {(cuuint64_t)tc::kH * 4, 128};  // bytes, dims 1 and 2
+    cuuint32_t box[3] = {32, (cuuint32_t)tc::F_KT, 8};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const char* force2d = getenv("LOC_TMA_2D");
+    CUresult r = CUDA_ERROR_INVALID_VALUE;
+    if (force2d == nullptr)
+      r = cuTensorMapEncodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.W1, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    tma_rank = 3;
+    if (r != CUDA_SUCCESS) {
+      // plain row-major view [K][256], eight [32 rows][32 floats] boxes per stage
+      cuuint64_t dims2[2] = {(cuuint64_t)tc::kH, (cuuint64_t)a.K};
+      cuuint64_t strides2[1] = {(cuuint64_t)tc::kH * 4};
+      cuuint32_t box2[2] = {32, (cuuint32_t)tc::F_KT};
+      r = cuTensorMapEncodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.W1, dims2, strides2, box2, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      tma_rank = 2;
+    }
+    if (r != CUDA_SUCCESS) {
+      const char* msg = nullptr;
+      cuGetErrorString(r, &msg);
+      char buf[256];
+      snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed: %s", msg ? msg : "?");
+      return fail(buf, __FILE__, __LINE__);
+    }
+    cached_w = a.W1;
+    cached_k = a.K;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    LOC_CUDA(cudaFuncSetAttribute(tc::k_l1_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::F_SMEM));
+    attr_set = true;
+  }
+  const int64_t ntiles = cdiv(a.K, tc::F_KT);
+  tc::k_l1_fwd_tc<<<n_partials, tc::F_THREADS, tc::F_SMEM, s>>>(map, tma_rank, a, ntiles);
+  LOC_LAUNCHED();
+  return 0;
+}
+
+int l1_backward_tc(const L1Args& a, int nblocks, cudaStream_t s) {
+  (void)nblocks;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LOC_CUDA(cudaFuncSetAttribute(tc::k_l1_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::B_SMEM));
+    attr_set = true;
+  }
+  const int64_t ntiles = cdiv(a.K, tc::B_NT);
+  const int64_t grid = ntiles < 2 * tc_sm_count() ? ntiles : 2 * tc_sm_count();
+  tc::k_l1_bwd_tc<<<(unsigned)grid, tc::B_THREADS, tc::B_SMEM, s>>>(a, ntiles);
+  LOC_LAUNCHED();
+  return 0;
+}
+
 }  // namespace loc

@@ -516,6 +516,22 @@ int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t 
   return train_step(m, src, 0, (cudaStream_t)stream, 1 << stage);
 }
 
+int64_t loc_debug_read(loc_model* m, int32_t which, float* h_dst, int64_t max_n, void* stream) {
+  if (m == nullptr || h_dst == nullptr || which < 0 || which > 2) {
+    loc::fail("loc_debug_read: bad arguments", __FILE__, __LINE__);
+    return -1;
+  }
+  const float* src = which == 0 ? m->partials : (which == 1 ? m->dzs : m->acts);
+  const int64_t n = which == 0 ? (int64_t)m->n_partials * kMaxB * m->H : (int64_t)m->L * kMaxB * m->H;
+  const int64_t c = n < max_n ? n : max_n;
+  if (cudaMemcpyAsync(h_dst, src, c * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
+      cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+    loc::fail("loc_debug_read: copy failed", __FILE__, __LINE__);
+    return -1;
+  }
+  return n;
+}
+
 int loc_train_epochs(loc_model* m, const int32_t* d_perms, int32_t n_epochs, void* stream) {
   LOC_CHECK(m != nullptr && m->train_packed != nullptr && m->val_packed != nullptr,
             "loc_train_epochs: training and validation data must be bound");

@@ -153,6 +153,21 @@ class LocatorModel:
         self._keep["rows"] = r
         check(lib.loc_train_step(self._h, r.data_ptr(), int(r.numel()), _stream()), "loc_train_step")
 
+    def debug_stage(self, stage, rows):
+        """Launch one stage (0 fwd-L1, 1 hidden, 2 bwd-L1, 3 small update) of a step on `rows`."""
+        r = _as_dev(np.asarray(rows, dtype=np.int32), torch.int32)
+        self._keep["rows"] = r
+        check(lib.loc_debug_stage(self._h, int(stage), r.data_ptr(), int(r.numel()), _stream()), "loc_debug_stage")
+
+    def debug_read(self, which):
+        """Scratch buffers: 0 -> Z1 partial tiles [P, 32, H]; 1 -> dz [L, 32, H]; 2 -> activations [L, 32, H]."""
+        n = int(lib.loc_debug_read(self._h, int(which), np.empty(1, np.float32).ctypes.data, 0, _stream()))
+        if n < 0:
+            raise _cabi.LocatorCudaError("loc_debug_read failed")
+        a = np.empty(n, np.float32)
+        lib.loc_debug_read(self._h, int(which), a.ctypes.data, n, _stream())
+        return a.reshape(-1, 32, self.width)
+
     def train_epochs(self, perms):
         """perms int32 [n_epochs, n_train]; enqueues the epochs (asynchronous)."""
         p = _as_dev(np.asarray(perms, dtype=np.int32), torch.int32)

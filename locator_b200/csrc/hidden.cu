@@ -5,12 +5,18 @@
 // Keras semantics restated in oracle/model_ref.py (RefLocator.forward / gradients).
 //
 // Work split: CTA r of the C-CTA cluster owns columns [r*Hc, (r+1)*Hc) of every layer's output.
-// A layer is: all-gather the previous activations (through L2; barrier.cluster release/acquire),
-// each CTA computes its [32 x Hc] slice with the 8 warps splitting the reduction dimension,
-// fixed-order cross-warp sum (deterministic), elu / dropout, publish the slice.  The backward
-// pass mirrors it with row slices of W.  dW + Adam of these layers is NOT done here: the
-// activations and dz of every layer are left in L2 for k_hidden_update, which runs off the
-// critical path next to the first-layer backward.
+// The step is a chain of 2L tiny dependent products, so everything is arranged around latency:
+//   * weights never wait on L2: each CTA's slice of every layer is kept in HBM in two pre-sliced
+//     copies (forward slices W[:, cols] and backward slices W[rows, :]^T, both [H][Hc] contiguous)
+//     and streamed into a ring of shared-memory slots with cp.async.bulk + mbarrier several layers
+//     ahead of use;
+//   * activations never go through L2 on the critical path: a CTA publishes its [32 x Hc] slice
+//     straight into the shared memory of all C CTAs with st.async, whose bytes complete on the
+//     receiver's mbarrier (no fence, no cluster-wide barrier per layer), double-buffered;
+//   * each slice product splits the reduction dimension over the 8 warps with a fixed-order
+//     cross-warp sum (deterministic).
+// dW + Adam of these layers is NOT done here: activations and dz of every layer are also left in
+// global memory for k_hidden_update, which runs off the critical path.
 #include "model.cuh"
 #include "philox.cuh"
 
@@ -26,33 +32,31 @@ __device__ __forceinline__ unsigned cluster_size() {
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
-// Release/acquire at cluster scope: global writes made before it by any CTA of the cluster are
-// visible to every CTA after it.
+// Release/acquire at cluster scope: (distributed) shared-memory and global writes made before it by
+// any CTA of the cluster are visible to every CTA after it.
 __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t hid_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// 16-byte store into CTA `rank`'s shared memory whose completion is counted (complete_tx) on that
+// CTA's mbarrier: the receiver just waits for the expected byte count of the layer.
+__device__ __forceinline__ void st_async_f4(uint32_t local_addr, uint32_t local_bar, unsigned rank, float4 v) {
+  uint32_t raddr, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   raddr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rbar)
+               : "memory");
 }
 
 constexpr int kHidThreads = 256;
 constexpr int kHidWarps = kHidThreads / 32;
 constexpr int kPad = 4;
+constexpr int kMaxSlots = 16;
 
-// [32][H] tile from L2 into padded shared memory.
-__device__ __forceinline__ void load_full(float* full, const float* __restrict__ src, int H) {
-  const int HP = H + kPad;
-  const int nvec = kMaxB * H / 4;
-  for (int i = threadIdx.x; i < nvec; i += kHidThreads) {
-    const int b = (i * 4) / H, k = (i * 4) % H;
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(src) + i);
-    *reinterpret_cast<float4*>(full + b * HP + k) = v;
-  }
-}
-
-// red[w][b][jl] = sum over warp w's share of the reduction dimension.
-//   fwd (transpose == 0): out[b][jl] = sum_k full[b][k] * W[k*H + j0 + jl]
-//   bwd (transpose == 1): out[b][il] = sum_j full[b][j] * W[(j0 + il)*H + j]
-template <int TRANSPOSE>
-__device__ __forceinline__ void slice_matmul(const float* full, const float* __restrict__ W, float* red, int H, int Hc,
-                                             int j0) {
+// red[w][b][jl] = sum over warp w's share of k of full[b][k] * Ws[k][jl]   (Ws: [H][Hc] in shared memory)
+__device__ __forceinline__ void slice_matmul(const float* full, const float* Ws, float* red, int H, int Hc) {
   const int HP = H + kPad;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kper = H / kHidWarps;
@@ -66,40 +70,23 @@ __device__ __forceinline__ void slice_matmul(const float* full, const float* __r
     for (int x = 0; x < 4; ++x)
 #pragma unroll
       for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+#pragma unroll 2
     for (int k = kbeg; k < kend; k += 4) {
       float4 a4[4], w4[4];
 #pragma unroll
       for (int bb = 0; bb < 4; ++bb) a4[bb] = *reinterpret_cast<const float4*>(full + (4 * bq + bb) * HP + k);
-      if (TRANSPOSE == 0) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          w4[kk] = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(k + kk) * H + j0 + 4 * jq));
+      for (int kk = 0; kk < 4; ++kk) w4[kk] = *reinterpret_cast<const float4*>(Ws + (k + kk) * Hc + 4 * jq);
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const float av[4] = {a4[bb].x, a4[bb].y, a4[bb].z, a4[bb].w};
+      for (int bb = 0; bb < 4; ++bb) {
+        const float av[4] = {a4[bb].x, a4[bb].y, a4[bb].z, a4[bb].w};
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            acc[bb][0] = fmaf(av[kk], w4[kk].x, acc[bb][0]);
-            acc[bb][1] = fmaf(av[kk], w4[kk].y, acc[bb][1]);
-            acc[bb][2] = fmaf(av[kk], w4[kk].z, acc[bb][2]);
-            acc[bb][3] = fmaf(av[kk], w4[kk].w, acc[bb][3]);
-          }
+        for (int kk = 0; kk < 4; ++kk) {
+          acc[bb][0] = fmaf(av[kk], w4[kk].x, acc[bb][0]);
+          acc[bb][1] = fmaf(av[kk], w4[kk].y, acc[bb][1]);
+          acc[bb][2] = fmaf(av[kk], w4[kk].z, acc[bb][2]);
+          acc[bb][3] = fmaf(av[kk], w4[kk].w, acc[bb][3]);
         }
-      } else {
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii)
-          w4[ii] = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(j0 + 4 * jq + ii) * H + k));
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb)
-#pragma unroll
-          for (int ii = 0; ii < 4; ++ii) {
-            float s = acc[bb][ii];
-            s = fmaf(a4[bb].x, w4[ii].x, s);
-            s = fmaf(a4[bb].y, w4[ii].y, s);
-            s = fmaf(a4[bb].z, w4[ii].z, s);
-            s = fmaf(a4[bb].w, w4[ii].w, s);
-            acc[bb][ii] = s;
-          }
       }
     }
 #pragma unroll
@@ -113,77 +100,185 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
   if (a.gated && a.st->stopped) return;
   extern __shared__ __align__(16) float smem[];
   __shared__ int64_t s_rows[kMaxB];
+  __shared__ __align__(8) uint64_t wbar[kMaxSlots];
+  __shared__ __align__(8) uint64_t ready[2];  // gathered-buffer full barriers (bytes from all C CTAs)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = a.H, L = a.L;
   const int C = (int)cluster_size(), r = (int)cluster_rank();
   const int Hc = H / C, j0 = r * Hc;
   const int HP = H + kPad;
   const int nb = a.src.nb;
+  const int NS = a.n_slots;
   const SmallLayout sl{H, L};
 
-  float* full = smem;                               // [32][HP]
-  float* red = full + kMaxB * HP;                   // [8][32][Hc] (>= 1024 floats)
-  float* own_a = red + kHidWarps * kMaxB * Hc;      // [L][32][Hc] elu outputs (pre-dropout) of the own slice
-  float* keep = own_a + (int64_t)L * kMaxB * Hc;    // [32][Hc]   dropout multiplier of the own slice
+  float* full0 = smem;                              // [2][32][HP]  gathered activations / dz (double buffer)
+  float* red = full0 + 2 * kMaxB * HP;              // [8][32][Hc]  (>= 1024 floats)
+  const int red_floats = kHidWarps * kMaxB * Hc < 1024 ? 1024 : kHidWarps * kMaxB * Hc;
+  float* own_a = red + red_floats;                  // [L][32][Hc] elu outputs (pre-dropout) of the own slice
+  float* own_dz = own_a + (int64_t)L * kMaxB * Hc;  // [L][32][Hc] dz of the own slice
+  float* keep = own_dz + (int64_t)L * kMaxB * Hc;   // [32][Hc]    dropout multiplier of the own slice
   float* ysm = keep + kMaxB * Hc;                   // y1, y2, dy1, dy2 [32][2] each, dist[32]
+  float* sbias = ysm + 320;                         // [L][Hc] own bias slices
+  float* sout = sbias + L * Hc;                     // Wo1[H][2], bo1[2], Wo2[4], bo2[2]
+  float* wslot = sout + ((2 * H + 8 + 3) & ~3);     // [NS][H][Hc] weight-slice ring
   float* y1s = ysm;
   float* y2s = ysm + 64;
   float* dy1s = ysm + 128;
   float* dy2s = ysm + 192;
   float* dist = ysm + 256;
 
+  // ---- weight-slice ring: uses 0..L-2 are the forward slices of layers 1..L-1, then the backward
+  //      slices of layers L-1..1; use u lives in slot u % NS and is fetched NS uses ahead ----
+  const int n_uses = a.training ? 2 * (L - 1) : (L - 1);
+  const uint32_t slice_bytes = (uint32_t)(H * Hc * sizeof(float));
+  auto issue_load = [&](int u) {  // thread 0 only
+    const int slot = u % NS;
+    const int layer = u < L - 1 ? u + 1 : 2 * (L - 1) - u;
+    const float* src = (u < L - 1 ? a.w_fs : a.w_bs) + (int64_t)(layer - 1) * H * H + (int64_t)r * H * Hc;
+    const uint32_t bar = hid_smem_u32(&wbar[slot]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(slice_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     hid_smem_u32(wslot + (int64_t)slot * H * Hc)),
+                 "l"(src), "r"(slice_bytes), "r"(bar)
+                 : "memory");
+  };
+  auto wait_slice = [&](int u) -> const float* {
+    const int slot = u % NS;
+    const uint32_t parity = (uint32_t)(u / NS) & 1u;
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(hid_smem_u32(&wbar[slot])), "r"(parity)
+          : "memory");
+    }
+    return wslot + (int64_t)slot * H * Hc;
+  };
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hid_smem_u32(&wbar[s])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hid_smem_u32(&ready[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hid_smem_u32(&ready[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int u = 0; u < NS && u < n_uses; ++u) issue_load(u);
+  }
+  for (int i = tid; i < L * Hc; i += kHidThreads) {
+    const int layer = i / Hc, jl = i % Hc;
+    sbias[i] = a.small[(layer == 0 ? sl.b1() : sl.bh(layer)) + j0 + jl];
+  }
+  for (int i = tid; i < 2 * H + 8; i += kHidThreads) sout[i] = a.small[sl.Wo1() + i];
   if (tid < kMaxB) s_rows[tid] = tid < nb ? row_of(a.src, a.st, tid) : 0;
   const int step_id = a.st->step_id;
   const float keep_scale = 1.0f / (1.0f - a.p_drop);
   const bool drop_on = a.training && a.p_drop > 0.f;
+  __syncthreads();
+  cluster_barrier();  // every CTA of the cluster is running before anyone writes into its shared memory
 
-  // elu + (dropout) + publish of the own slice of layer i, from the cross-warp partial sums in red.
+  // Work items of the finishing passes: (b, 4 consecutive columns of the own slice); when there are
+  // fewer items than threads the destination CTAs of the publish are split over thread groups.
+  const int items = kMaxB * Hc / 4;
+  const int groups = items >= kHidThreads ? 1 : kHidThreads / items;
+  int pub = 0;  // number of publishes so far: publish n goes to buffer n & 1
+  auto publish = [&](int b, int jl, float4 v, int grp) {
+    const uint32_t local = hid_smem_u32(full0 + (pub & 1) * kMaxB * HP + b * HP + j0 + jl);
+    const uint32_t bar = hid_smem_u32(&ready[pub & 1]);
+    for (int d = grp; d < C; d += groups) st_async_f4(local, bar, (unsigned)d, v);
+  };
+  // Wait until publish n (all C slices, 32*H floats) has landed in this CTA's buffer n & 1.
+  const uint32_t gather_bytes = (uint32_t)(kMaxB * H * sizeof(float));
+  auto wait_gather = [&](int n) -> const float* {
+    const uint32_t bar = hid_smem_u32(&ready[n & 1]);
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(gather_bytes) : "memory");
+    const uint32_t parity = (uint32_t)(n >> 1) & 1u;
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    }
+    return full0 + (n & 1) * kMaxB * HP;
+  };
+  auto red_sum4 = [&](int nparts, int b, int jl) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = 0; w < nparts; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(red + ((int64_t)w * kMaxB + b) * Hc + jl);
+      s.x += v.x;
+      s.y += v.y;
+      s.z += v.z;
+      s.w += v.w;
+    }
+    return s;
+  };
+  // bias, elu, (dropout), publish of the own slice of layer i from the partial sums in red
   auto finish_fwd = [&](int i, int nparts, const float* bias) {
-    for (int idx = tid; idx < kMaxB * Hc; idx += kHidThreads) {
-      const int b = idx / Hc, jl = idx % Hc;
-      float z = 0.f;
-      for (int w = 0; w < nparts; ++w) z += red[((int64_t)w * kMaxB + b) * Hc + jl];
-      z += bias[j0 + jl];
-      float act = elu_f(z);
-      own_a[((int64_t)i * kMaxB + b) * Hc + jl] = act;
-      if (i == a.n_before - 1) {
-        float mult = 1.f;
-        if (drop_on) {
+    for (int idx = tid; idx < items * groups; idx += kHidThreads) {
+      const int item = idx % items, grp = idx / items;
+      const int b = (item * 4) / Hc, jl = (item * 4) % Hc;
+      const float4 z4 = red_sum4(nparts, b, jl);
+      const float4 bi = *reinterpret_cast<const float4*>(bias + jl);
+      float act[4] = {elu_f(z4.x + bi.x), elu_f(z4.y + bi.y), elu_f(z4.z + bi.z), elu_f(z4.w + bi.w)};
+      float pre[4] = {act[0], act[1], act[2], act[3]};
+      float mult[4] = {1.f, 1.f, 1.f, 1.f};
+      if (i == a.n_before - 1 && drop_on) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
           bool kp;
           if (a.masks != nullptr) {
             const int64_t s = step_id < a.n_masks ? step_id : a.n_masks - 1;
-            kp = a.masks[(s * kMaxB + b) * H + j0 + jl] != 0;
+            kp = a.masks[(s * kMaxB + b) * H + j0 + jl + e] != 0;
           } else {
-            kp = philox_uniform((uint64_t)b * H + j0 + jl, kDropoutStreamBase + (uint32_t)step_id, a.seed) >= a.p_drop;
+            kp = philox_uniform((uint64_t)b * H + j0 + jl + e, kDropoutStreamBase + (uint32_t)step_id, a.seed) >=
+                 a.p_drop;
           }
-          mult = kp ? keep_scale : 0.f;
+          mult[e] = kp ? keep_scale : 0.f;
+          act[e] *= mult[e];
         }
-        keep[b * Hc + jl] = mult;
-        act *= mult;
       }
-      a.acts[((int64_t)i * kMaxB + b) * H + j0 + jl] = b < nb ? act : 0.f;
+      if (b >= nb) act[0] = act[1] = act[2] = act[3] = 0.f;
+      const float4 out = make_float4(act[0], act[1], act[2], act[3]);
+      publish(b, jl, out, grp);
+      if (grp == 0) {
+        *reinterpret_cast<float4*>(own_a + ((int64_t)i * kMaxB + b) * Hc + jl) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+        if (i == a.n_before - 1)
+          *reinterpret_cast<float4*>(keep + b * Hc + jl) = make_float4(mult[0], mult[1], mult[2], mult[3]);
+      }
     }
+    ++pub;
   };
-  // dz of layer i for the own slice from d loss / d (post-dropout activation).
-  auto finish_bwd = [&](int i, int b, int jl, float da) {
-    if (i == a.n_before - 1) da *= keep[b * Hc + jl];
-    const float act = own_a[((int64_t)i * kMaxB + b) * Hc + jl];
-    const float dz = da * elu_grad_from_out(act);
-    a.dzs[((int64_t)i * kMaxB + b) * H + j0 + jl] = b < nb ? dz : 0.f;
+  // dz of layer i for the own slice from d loss / d (post-dropout activation)
+  auto finish_bwd = [&](int i, int b, int jl, float4 da, int grp, bool do_publish) {
+    float d[4] = {da.x, da.y, da.z, da.w};
+    const float4 pre = *reinterpret_cast<const float4*>(own_a + ((int64_t)i * kMaxB + b) * Hc + jl);
+    const float pa[4] = {pre.x, pre.y, pre.z, pre.w};
+    if (i == a.n_before - 1) {
+      const float4 km = *reinterpret_cast<const float4*>(keep + b * Hc + jl);
+      d[0] *= km.x;
+      d[1] *= km.y;
+      d[2] *= km.z;
+      d[3] *= km.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) d[e] = b < nb ? d[e] * elu_grad_from_out(pa[e]) : 0.f;
+    const float4 out = make_float4(d[0], d[1], d[2], d[3]);
+    if (do_publish) publish(b, jl, out, grp);
+    if (grp == 0) *reinterpret_cast<float4*>(own_dz + ((int64_t)i * kMaxB + b) * Hc + jl) = out;
   };
 
   // ---- layer 0: reduce the split-K partial tiles of Z1 (fixed order), bias, elu ----
   {
-    const int nvec = kMaxB * Hc / 4;                       // float4 outputs of the slice
-    const int G = nvec >= kHidThreads ? 1 : kHidThreads / nvec;  // groups splitting the partial range
+    const int G = items >= kHidThreads ? 1 : kHidThreads / items;  // groups splitting the partial range
     const int hv = H / 4;
-    for (int idx = tid; idx < nvec * G; idx += kHidThreads) {
-      const int o = idx % nvec, g = idx / nvec;
+    for (int idx = tid; idx < items * G; idx += kHidThreads) {
+      const int o = idx % items, g = idx / items;
       const int b = (o * 4) / Hc, jl = (o * 4) % Hc;
       const int pbeg = a.n_partials * g / G, pend = a.n_partials * (g + 1) / G;
       const float4* src = reinterpret_cast<const float4*>(a.partials) + ((int64_t)b * H + j0 + jl) / 4;
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
+#pragma unroll 16
       for (int p = pbeg; p < pend; ++p) {
         const float4 v = __ldcg(src + (int64_t)p * kMaxB * hv);
         s.x += v.x;
@@ -194,31 +289,31 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
       *reinterpret_cast<float4*>(red + ((int64_t)g * kMaxB + b) * Hc + jl) = s;
     }
     __syncthreads();
-    finish_fwd(0, G, a.small + sl.b1());
+    finish_fwd(0, G, sbias);
   }
-  cluster_barrier();
 
   // ---- layers 1..L-1 forward ----
-  for (int i = 1; i < L; ++i) {
-    load_full(full, a.acts + (int64_t)(i - 1) * kMaxB * H, H);
+  int use = 0;
+  for (int i = 1; i < L; ++i, ++use) {
+    const float* Ws = wait_slice(use);
+    const float* in = wait_gather(pub - 1);
+    slice_matmul(in, Ws, red, H, Hc);
     __syncthreads();
-    slice_matmul<0>(full, a.small + sl.Wh(i), red, H, Hc, j0);
-    __syncthreads();
-    finish_fwd(i, kHidWarps, a.small + sl.bh(i));
-    cluster_barrier();
+    if (tid == 0 && use + NS < n_uses) issue_load(use + NS);
+    finish_fwd(i, kHidWarps, sbias + i * Hc);
+    __syncthreads();  // red is rewritten by the next layer's product
   }
 
   // ---- Dense(2), Dense(2), loss (every CTA, redundantly) ----
-  load_full(full, a.acts + (int64_t)(L - 1) * kMaxB * H, H);
-  __syncthreads();
+  const float* full = wait_gather(pub - 1);  // a_{L-1}
   {
-    const float* Wo1 = a.small + sl.Wo1();
+    const float* Wo1 = sout;
     for (int b = warp; b < kMaxB; b += kHidWarps) {
       float s0 = 0.f, s1 = 0.f;
       for (int k = lane; k < H; k += 32) {
         const float av = full[b * HP + k];
-        s0 = fmaf(av, __ldg(Wo1 + 2 * k), s0);
-        s1 = fmaf(av, __ldg(Wo1 + 2 * k + 1), s1);
+        s0 = fmaf(av, Wo1[2 * k], s0);
+        s1 = fmaf(av, Wo1[2 * k + 1], s1);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -234,9 +329,9 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
   __syncthreads();
   if (tid < kMaxB) {
     const int b = tid;
-    const float* bo1 = a.small + sl.bo1();
-    const float* Wo2 = a.small + sl.Wo2();
-    const float* bo2 = a.small + sl.bo2();
+    const float* bo1 = sout + 2 * H;
+    const float* Wo2 = bo1 + 2;
+    const float* bo2 = Wo2 + 4;
     const float u0 = y1s[2 * b] + bo1[0], u1 = y1s[2 * b + 1] + bo1[1];
     y1s[2 * b] = u0;
     y1s[2 * b + 1] = u1;
@@ -287,32 +382,59 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
       }
     }
   }
-  if (!a.training) return;
+  if (!a.training) {
+    cluster_barrier();  // nobody exits while peers may still address its shared memory
+    return;
+  }
 
   // ---- backward: d loss / d a_{L-1} through Dense(2) ----
   {
-    const float* Wo1 = a.small + sl.Wo1();
-    for (int idx = tid; idx < kMaxB * Hc; idx += kHidThreads) {
-      const int b = idx / Hc, jl = idx % Hc;
-      const int i = j0 + jl;
-      const float da = dy1s[2 * b] * Wo1[2 * i] + dy1s[2 * b + 1] * Wo1[2 * i + 1];
-      finish_bwd(L - 1, b, jl, da);
+    const float* Wo1 = sout;
+    for (int idx = tid; idx < items * groups; idx += kHidThreads) {
+      const int item = idx % items, grp = idx / items;
+      const int b = (item * 4) / Hc, jl = (item * 4) % Hc;
+      float d[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = j0 + jl + e;
+        d[e] = dy1s[2 * b] * Wo1[2 * i] + dy1s[2 * b + 1] * Wo1[2 * i + 1];
+      }
+      finish_bwd(L - 1, b, jl, make_float4(d[0], d[1], d[2], d[3]), grp, true);
     }
+    ++pub;
   }
-  cluster_barrier();
-  for (int i = L - 1; i >= 1; --i) {
-    load_full(full, a.dzs + (int64_t)i * kMaxB * H, H);
+  for (int i = L - 1; i >= 1; --i, ++use) {
+    const float* Ws = wait_slice(use);  // [j][il] = W_i[j0 + il][j]
+    const float* in = wait_gather(pub - 1);
+    slice_matmul(in, Ws, red, H, Hc);
     __syncthreads();
-    slice_matmul<1>(full, a.small + sl.Wh(i), red, H, Hc, j0);
-    __syncthreads();
-    for (int idx = tid; idx < kMaxB * Hc; idx += kHidThreads) {
-      const int b = idx / Hc, jl = idx % Hc;
-      float da = 0.f;
-      for (int w = 0; w < kHidWarps; ++w) da += red[((int64_t)w * kMaxB + b) * Hc + jl];
-      finish_bwd(i - 1, b, jl, da);
+    if (tid == 0 && use + NS < n_uses) issue_load(use + NS);
+    for (int idx = tid; idx < items * groups; idx += kHidThreads) {
+      const int item = idx % items, grp = idx / items;
+      const int b = (item * 4) / Hc, jl = (item * 4) % Hc;
+      finish_bwd(i - 1, b, jl, red_sum4(kHidWarps, b, jl), grp, i > 1);
     }
-    cluster_barrier();
+    if (i > 1) ++pub;
+    __syncthreads();
   }
+  // ---- leave activations and dz of every layer in global memory for the update kernels ----
+  for (int idx = tid; idx < L * items; idx += kHidThreads) {
+    const int i = idx / items, item = idx % items;
+    const int b = (item * 4) / Hc, jl = (item * 4) % Hc;
+    float4 act = *reinterpret_cast<const float4*>(own_a + ((int64_t)i * kMaxB + b) * Hc + jl);
+    if (i == a.n_before - 1) {
+      const float4 km = *reinterpret_cast<const float4*>(keep + b * Hc + jl);
+      act.x *= km.x;
+      act.y *= km.y;
+      act.z *= km.z;
+      act.w *= km.w;
+    }
+    if (b >= nb) act = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(a.acts + ((int64_t)i * kMaxB + b) * H + j0 + jl) = act;
+    *reinterpret_cast<float4*>(a.dzs + ((int64_t)i * kMaxB + b) * H + j0 + jl) =
+        *reinterpret_cast<const float4*>(own_dz + ((int64_t)i * kMaxB + b) * Hc + jl);
+  }
+  cluster_barrier();  // nobody exits while peers may still address its shared memory
   // Optimizer bookkeeping for the update kernels of this step (Keras Adam: alpha from t >= 1).
   if (r == 0 && tid == 0) {
     DevState* st = a.st;
@@ -321,6 +443,27 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
     st->step_id = step_id + 1;
     const float b1p = powf(kAdamB1, (float)t), b2p = powf(kAdamB2, (float)t);
     st->alpha = st->lr * sqrtf(1.f - b2p) / (1.f - b1p);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pre-sliced copies of the hidden kernels for k_hidden (C = cluster size, Hc = H / C):
+//   fs[i-1][r][k][jl] = W_i[k][r*Hc + jl]      (forward slice of CTA r)
+//   bs[i-1][r][j][il] = W_i[r*Hc + il][j]      (backward slice of CTA r, transposed)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_sliced(float* fs, float* bs, int H, int Hc, int layer, int k, int j, float w) {
+  const int64_t base = (int64_t)(layer - 1) * H * H;
+  fs[base + (int64_t)(j / Hc) * H * Hc + (int64_t)k * Hc + (j % Hc)] = w;
+  bs[base + (int64_t)(k / Hc) * H * Hc + (int64_t)j * Hc + (k % Hc)] = w;
+}
+
+__global__ void k_reslice(const float* __restrict__ small, float* fs, float* bs, int H, int L, int Hc) {
+  const SmallLayout sl{H, L};
+  const int64_t n = (int64_t)(L - 1) * H * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int layer = 1 + (int)(i / ((int64_t)H * H));
+    const int k = (int)((i / H) % H), j = (int)(i % H);
+    store_sliced(fs, bs, H, Hc, layer, k, j, small[sl.Wh(layer) + (int64_t)k * H + j]);
   }
 }
 
@@ -338,12 +481,13 @@ __global__ void __launch_bounds__(1024) k_hidden_update(UpdArgs a) {
   const float alpha = a.st->alpha;
   const int rb_n = H / kUpdRows;
   const int nblk_hidden = (L - 1) * rb_n;
-  auto adam_at = [&](int64_t idx, float g) {
+  auto adam_at = [&](int64_t idx, float g) -> float {
     float w = a.small[idx], m = a.m_small[idx], v = a.v_small[idx];
     adam_update(w, m, v, g, alpha);
     a.small[idx] = w;
     a.m_small[idx] = m;
     a.v_small[idx] = v;
+    return w;
   };
   if ((int)blockIdx.x < nblk_hidden) {
     const int i = 1 + blockIdx.x / rb_n, rb = blockIdx.x % rb_n;
@@ -364,7 +508,9 @@ __global__ void __launch_bounds__(1024) k_hidden_update(UpdArgs a) {
       float g = 0.f;
 #pragma unroll
       for (int b = 0; b < kMaxB; ++b) g = fmaf(as[kk][b], dz[b], g);
-      adam_at(sl.Wh(i) + (int64_t)(rb * kUpdRows + kk) * H + j, g);
+      const int k = rb * kUpdRows + kk;
+      const float w = adam_at(sl.Wh(i) + (int64_t)k * H + j, g);
+      store_sliced(a.w_fs, a.w_bs, H, a.Hc, i, k, j, w);
     }
     if (rb == 0) adam_at(sl.bh(i) + j, bsum);
   } else {
@@ -402,12 +548,29 @@ __global__ void __launch_bounds__(1024) k_hidden_update(UpdArgs a) {
   }
 }
 
-size_t hidden_smem_bytes(int H, int L, int cluster) {
+static size_t hidden_fixed_floats(int H, int L, int cluster) {
   const int Hc = H / cluster;
   size_t red = (size_t)kHidWarps * kMaxB * Hc;
   if (red < 1024) red = 1024;
-  const size_t floats = (size_t)kMaxB * (H + kPad) + red + (size_t)L * kMaxB * Hc + (size_t)kMaxB * Hc + 320;
-  return floats * sizeof(float);
+  return (size_t)2 * kMaxB * (H + kPad) + red + (size_t)2 * L * kMaxB * Hc + (size_t)kMaxB * Hc + 320 + (size_t)L * Hc +
+         (size_t)((2 * H + 8 + 3) & ~3);
+}
+
+int hidden_slots(int H, int L, int cluster) {
+  const size_t budget = 226 * 1024;
+  const size_t fixed = hidden_fixed_floats(H, L, cluster) * sizeof(float);
+  const size_t slot = (size_t)H * (H / cluster) * sizeof(float);
+  if (fixed + slot > budget) return 0;
+  size_t ns = (budget - fixed) / slot;
+  const size_t want = (size_t)2 * (L - 1);
+  if (ns > want) ns = want;
+  if (ns > kMaxSlots) ns = kMaxSlots;
+  return (int)ns;
+}
+
+size_t hidden_smem_bytes(int H, int L, int cluster) {
+  const int ns = hidden_slots(H, L, cluster);
+  return hidden_fixed_floats(H, L, cluster) * sizeof(float) + (size_t)ns * H * (H / cluster) * sizeof(float);
 }
 
 static int launch_hidden_cluster(const HidArgs& a, int cluster, cudaStream_t s, bool dry) {
@@ -437,39 +600,41 @@ static int launch_hidden_cluster(const HidArgs& a, int cluster, cudaStream_t s, 
   return 0;
 }
 
-int hidden_max_cluster(int H) {
-  static int cached_H = -1, cached = 0;
-  if (cached_H == H) return cached;
+int hidden_max_cluster(int H, int L) {
   cudaFuncSetAttribute(k_hidden, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaGetLastError();
-  int best = 0;
   const int cands[5] = {16, 8, 4, 2, 1};
-  for (int ci = 0; ci < 5 && !best; ++ci) {
+  for (int ci = 0; ci < 5; ++ci) {
     const int c = cands[ci];
     if (H % (4 * c) != 0) continue;
-    const size_t smem = hidden_smem_bytes(H, 16, c);
-    if (smem > 227 * 1024) continue;
+    if (hidden_slots(H, L, c) < 1) continue;
+    const size_t smem = hidden_smem_bytes(H, L, c);
     if (cudaFuncSetAttribute(k_hidden, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
       continue;
     }
     HidArgs dummy = {};
     dummy.H = H;
-    dummy.L = 16;
-    if (launch_hidden_cluster(dummy, c, 0, true) > 0) best = c;
+    dummy.L = L;
+    if (launch_hidden_cluster(dummy, c, 0, true) > 0) return c;
   }
-  cached_H = H;
-  cached = best;
-  return best;
+  return 0;
 }
 
 int hidden_launch(const HidArgs& a, int cluster, cudaStream_t s) {
   LOC_CHECK(cluster > 0 && a.H % (4 * cluster) == 0, "hidden stack: width must be a multiple of 4 x cluster size");
   LOC_CHECK(a.H % 32 == 0, "hidden stack: width must be a multiple of 32");
+  LOC_CHECK(a.n_slots >= 1, "hidden stack: shared memory budget exceeded for this width / nlayers");
   const size_t smem = hidden_smem_bytes(a.H, a.L, cluster);
-  LOC_CHECK(smem <= 227 * 1024, "hidden stack: shared memory budget exceeded for this width / nlayers");
   LOC_CUDA(cudaFuncSetAttribute(k_hidden, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return launch_hidden_cluster(a, cluster, s, false);
+}
+
+int hidden_reslice(const float* small, float* fs, float* bs, int H, int L, int cluster, cudaStream_t s) {
+  if (L < 2) return 0;
+  k_reslice<<<148 * 4, 256, 0, s>>>(small, fs, bs, H, L, H / cluster);
+  LOC_LAUNCHED();
+  return 0;
 }
 
 int hidden_update_launch(const UpdArgs& a, cudaStream_t s) {

@@ -203,6 +203,9 @@ static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated
   h.partials = m->partials;
   h.n_partials = m->n_partials;
   h.small = m->small;
+  h.w_fs = m->w_fs;
+  h.w_bs = m->w_bs;
+  h.n_slots = m->n_slots;
   h.acts = m->acts;
   h.dzs = m->dzs;
   h.outs = m->outs;
@@ -234,6 +237,9 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
   u.small = m->small;
   u.m_small = m->m_small;
   u.v_small = m->v_small;
+  u.w_fs = m->w_fs;
+  u.w_bs = m->w_bs;
+  u.Hc = m->H / m->cluster;
   u.acts = m->acts;
   u.dzs = m->dzs;
   u.outs = m->outs;
@@ -294,11 +300,12 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   m->max_epochs = max_epochs;
   m->p_drop = dropout_prop;
   m->sl = SmallLayout{width, nlayers};
-  m->cluster = hidden_max_cluster(width);
+  m->cluster = hidden_max_cluster(width, nlayers);
   if (m->cluster <= 0) {
     delete m;
-    return loc::fail("loc_model_create: no usable thread-block cluster size for this width", __FILE__, __LINE__);
+    return loc::fail("loc_model_create: no usable thread-block cluster size for this width / nlayers", __FILE__, __LINE__);
   }
+  m->n_slots = hidden_slots(width, nlayers, m->cluster);
   const char* impl = getenv("LOC_L1_IMPL");
   m->use_tc = (impl == nullptr || strcmp(impl, "simt") != 0) && l1_tc_supported(K, width);
   const int sms = sm_count();
@@ -319,6 +326,8 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   for (auto p : kv) LOC_CUDA(cudaMalloc(p, K * sizeof(float)));
   float** sm[] = {&m->small, &m->m_small, &m->v_small, &m->best_small};
   for (auto p : sm) LOC_CUDA(cudaMalloc(p, ns * sizeof(float)));
+  LOC_CUDA(cudaMalloc(&m->w_fs, (size_t)(nlayers - 1) * width * width * sizeof(float)));
+  LOC_CUDA(cudaMalloc(&m->w_bs, (size_t)(nlayers - 1) * width * width * sizeof(float)));
   LOC_CUDA(cudaMalloc(&m->partials, (size_t)m->n_partials * kMaxB * width * sizeof(float)));
   LOC_CUDA(cudaMalloc(&m->acts, (size_t)nlayers * kMaxB * width * sizeof(float)));
   LOC_CUDA(cudaMalloc(&m->dzs, (size_t)nlayers * kMaxB * width * sizeof(float)));
@@ -336,7 +345,7 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
 int loc_model_destroy(loc_model* m) {
   if (m == nullptr) return 0;
   float* ptrs[] = {m->W1, m->mW1, m->vW1, m->best_W1, m->gamma, m->beta, m->mmean, m->mvar, m->m_gamma, m->v_gamma,
-                   m->m_beta, m->v_beta, m->best_gamma, m->best_beta, m->best_mmean, m->best_mvar, m->small,
+                   m->m_beta, m->v_beta, m->best_gamma, m->best_beta, m->best_mmean, m->best_mvar, m->small, m->w_fs, m->w_bs,
                    m->m_small, m->v_small, m->best_small, m->partials, m->acts, m->dzs, m->outs, m->hist};
   for (float* p : ptrs)
     if (p) cudaFree(p);
@@ -376,6 +385,7 @@ int loc_model_init(loc_model* m, uint64_t seed, void* stream) {
     if (glorot(m->small + m->sl.Wh(i), H, H, i)) return 1;
   if (glorot(m->small + m->sl.Wo1(), H, 2, (int)L)) return 1;
   if (glorot(m->small + m->sl.Wo2(), 2, 2, (int)L + 1)) return 1;
+  if (hidden_reslice(m->small, m->w_fs, m->w_bs, m->H, m->L, m->cluster, s)) return 1;
   k_state_reset<<<1, 1, 0, s>>>(m->st, 1e-3f, 100, m->max_epochs, 1);
   LOC_LAUNCHED();
   return 0;
@@ -432,6 +442,7 @@ int loc_model_set_weight(loc_model* m, int32_t idx, const float* h_src, int64_t 
   LOC_CHECK(m != nullptr && weight_ref(m, idx, &r), "loc_model_set_weight: bad weight index");
   LOC_CHECK(n == r.n, "loc_model_set_weight: size mismatch");
   LOC_CUDA(cudaMemcpyAsync(r.w, h_src, n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  if (idx >= 6 && hidden_reslice(m->small, m->w_fs, m->w_bs, m->H, m->L, m->cluster, (cudaStream_t)stream)) return 1;
   LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
@@ -588,7 +599,8 @@ int loc_restore_best(loc_model* m, void* stream) {
   LOC_CUDA(cudaMemcpyAsync(&h, m->st, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   LOC_CHECK(h.best_epoch >= 0, "loc_restore_best: no checkpoint has been taken");
-  return copy_weights(m, false, nullptr, (cudaStream_t)stream);
+  if (copy_weights(m, false, nullptr, (cudaStream_t)stream)) return 1;
+  return hidden_reslice(m->small, m->w_fs, m->w_bs, m->H, m->L, m->cluster, (cudaStream_t)stream);
 }
 
 int loc_snapshot(loc_model* m, void* stream) {

@@ -76,6 +76,9 @@ struct HidArgs {
   const float* partials;
   int n_partials;
   float* small;
+  const float* w_fs;  // forward slices of the hidden kernels  [L-1][C][H][Hc]
+  const float* w_bs;  // backward slices (transposed)          [L-1][C][H][Hc]
+  int n_slots;        // shared-memory weight-slice ring size
   float* acts;  // [L][kMaxB][H] post-dropout outputs of Dense(width) layer i
   float* dzs;   // [L][kMaxB][H] d loss / d z_i
   float* outs;  // y1[32][2], dy1[32][2], dy2[32][2], y2[32][2]
@@ -89,6 +92,8 @@ struct UpdArgs {
   int H, L;
   int gated;
   float *small, *m_small, *v_small;
+  float *w_fs, *w_bs;  // pre-sliced copies kept in sync with small
+  int Hc;
   const float* acts;
   const float* dzs;
   const float* outs;
@@ -101,7 +106,9 @@ int l1_forward_simt(const L1Args& a, int n_partials, cudaStream_t s);
 int l1_backward_simt(const L1Args& a, int nblocks, cudaStream_t s);
 int hidden_launch(const HidArgs& a, int cluster, cudaStream_t s);
 int hidden_update_launch(const UpdArgs& a, cudaStream_t s);
-int hidden_max_cluster(int H);  // largest usable cluster size (16, 8, ...) for this device
+int hidden_max_cluster(int H, int L);  // largest usable cluster size (16, 8, ...) for this device
+int hidden_slots(int H, int L, int cluster);
+int hidden_reslice(const float* small, float* fs, float* bs, int H, int L, int cluster, cudaStream_t s);
 size_t hidden_smem_bytes(int H, int L, int cluster);
 
 // tcgen05 first layer (l1_tc.cu); available() is false when the shape is unsupported.
@@ -125,6 +132,8 @@ struct loc_model {
   loc::SmallLayout sl;
   // parameters
   float *gamma, *beta, *mmean, *mvar, *W1, *small;
+  float *w_fs, *w_bs;  // pre-sliced copies of the hidden kernels for k_hidden
+  int n_slots;
   // Adam moments
   float *m_gamma, *v_gamma, *m_beta, *v_beta, *mW1, *vW1, *m_small, *v_small;
   // ModelCheckpoint snapshot (weights only)

@@ -11,9 +11,10 @@
 //     and streamed into a ring of shared-memory slots with cp.async.bulk + mbarrier several layers
 //     ahead of use;
 //   * activations never go through L2 on the critical path: a CTA publishes its [32 x Hc] slice
-//     straight into the shared memory of all C CTAs with st.async, whose bytes complete on the
-//     receiver's mbarrier (no fence, no cluster-wide barrier per layer), double-buffered;
-//   * each slice product splits the reduction dimension over the 8 warps with a fixed-order
+//     straight into the shared memory of all C CTAs with one shared::cta -> shared::cluster bulk
+//     copy per destination, whose bytes complete on the receiver's mbarrier (no fence, no
+//     cluster-wide barrier per layer), double-buffered;
+//   * each slice product splits the reduction dimension over the 16 warps with a fixed-order
 //     cross-warp sum (deterministic).
 // dW + Adam of these layers is NOT done here: activations and dz of every layer are also left in
 // global memory for k_hidden_update, which runs off the critical path.
@@ -50,53 +51,81 @@ __device__ __forceinline__ void st_async_f4(uint32_t local_addr, uint32_t local_
                : "memory");
 }
 
-constexpr int kHidThreads = 256;
+constexpr int kHidThreads = 512;
 constexpr int kHidWarps = kHidThreads / 32;
-constexpr int kPad = 4;
 constexpr int kMaxSlots = 16;
 
-// red[w][b][jl] = sum over warp w's share of k of full[b][k] * Ws[k][jl]   (Ws: [H][Hc] in shared memory)
-__device__ __forceinline__ void slice_matmul(const float* full, const float* Ws, float* red, int H, int Hc) {
-  const int HP = H + kPad;
+// Gathered activations live slice-major: [source CTA r][batch row b][Hc + pad] so that a source
+// CTA's slice is one contiguous block (one bulk copy per destination) and rows of one slice are
+// an odd number of 16-byte chunks apart (conflict-free float4 reads across batch rows).
+__host__ __device__ inline int hid_row_pitch(int Hc) { return Hc + (((Hc / 4) % 2 == 0) ? 4 : 0); }
+
+__host__ __device__ inline int hid_nparts(int H) {
+  const int gpw = (H / 4 + kHidWarps - 1) / kHidWarps;
+  return (H / 4 + gpw - 1) / gpw;
+}
+
+// Packed fp32 FMA (FFMA2): d.lo += a.lo * b.lo, d.hi += a.hi * b.hi in one issue slot.
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float sum2(unsigned long long v) {
+  return __uint_as_float((uint32_t)v) + __uint_as_float((uint32_t)(v >> 32));
+}
+
+// red[w][b][jl] = sum over warp w's share of k of A[b][k] * W[k][jl].
+// Ws is the weight slice in shared memory with k pairs interleaved: Ws[k/2][jl][k&1], so that both
+// FFMA2 operands -- (A[b][k], A[b][k+1]) and (W[k][jl], W[k+1][jl]) -- are natural 64-bit pairs of
+// the 128-bit loads; even and odd k accumulate separately and are added at the end.
+__device__ __noinline__ void slice_matmul(const float* gathered, const float* Ws, float* red, int H, int Hc) {
+  const int HcP = hid_row_pitch(Hc), SL = kMaxB * HcP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int kper = H / kHidWarps;
-  const int kbeg = warp * kper, kend = kbeg + kper;
+  // the H/4 four-wide k groups are dealt to the warps in contiguous runs (hid_nparts warps get work)
+  const int gpw = (H / 4 + kHidWarps - 1) / kHidWarps;
+  const int kbeg = warp * gpw * 4;
+  const int kend = (kbeg + gpw * 4) < H ? (kbeg + gpw * 4) : H;
+  if (kbeg >= H) return;
   const int jq_n = Hc / 4;
   const int ntile = (kMaxB / 4) * jq_n;
   for (int tile = lane; tile < ntile; tile += 32) {
-    const int bq = tile / jq_n, jq = tile % jq_n;
-    float acc[4][4];
+    const int bq = tile / jq_n, jq = tile % jq_n;  // batch rows bq, bq+8, bq+16, bq+24
+    unsigned long long acc[4][4];
 #pragma unroll
     for (int x = 0; x < 4; ++x)
 #pragma unroll
-      for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-#pragma unroll 2
+      for (int y = 0; y < 4; ++y) acc[x][y] = 0ull;
+#pragma unroll 4
     for (int k = kbeg; k < kend; k += 4) {
-      float4 a4[4], w4[4];
+      const float* arow = gathered + (k / Hc) * SL + bq * HcP + (k % Hc);
+      const float* wrow = Ws + (k / 2) * (2 * Hc) + 8 * jq;
+      ulonglong2 a2[4], w2[4];  // a2[bb] = {(a[k],a[k+1]), (a[k+2],a[k+3])}
 #pragma unroll
-      for (int bb = 0; bb < 4; ++bb) a4[bb] = *reinterpret_cast<const float4*>(full + (4 * bq + bb) * HP + k);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) w4[kk] = *reinterpret_cast<const float4*>(Ws + (k + kk) * Hc + 4 * jq);
+      for (int bb = 0; bb < 4; ++bb) a2[bb] = *reinterpret_cast<const ulonglong2*>(arow + 8 * bb * HcP);
+      // w2[0], w2[1]: k pair 0, columns (0,1), (2,3);  w2[2], w2[3]: k pair 1
+      w2[0] = *reinterpret_cast<const ulonglong2*>(wrow);
+      w2[1] = *reinterpret_cast<const ulonglong2*>(wrow + 4);
+      w2[2] = *reinterpret_cast<const ulonglong2*>(wrow + 2 * Hc);
+      w2[3] = *reinterpret_cast<const ulonglong2*>(wrow + 2 * Hc + 4);
 #pragma unroll
       for (int bb = 0; bb < 4; ++bb) {
-        const float av[4] = {a4[bb].x, a4[bb].y, a4[bb].z, a4[bb].w};
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          acc[bb][0] = fmaf(av[kk], w4[kk].x, acc[bb][0]);
-          acc[bb][1] = fmaf(av[kk], w4[kk].y, acc[bb][1]);
-          acc[bb][2] = fmaf(av[kk], w4[kk].z, acc[bb][2]);
-          acc[bb][3] = fmaf(av[kk], w4[kk].w, acc[bb][3]);
-        }
+        ffma2(acc[bb][0], a2[bb].x, w2[0].x);
+        ffma2(acc[bb][1], a2[bb].x, w2[0].y);
+        ffma2(acc[bb][2], a2[bb].x, w2[1].x);
+        ffma2(acc[bb][3], a2[bb].x, w2[1].y);
+        ffma2(acc[bb][0], a2[bb].y, w2[2].x);
+        ffma2(acc[bb][1], a2[bb].y, w2[2].y);
+        ffma2(acc[bb][2], a2[bb].y, w2[3].x);
+        ffma2(acc[bb][3], a2[bb].y, w2[3].y);
       }
     }
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb)
-      *reinterpret_cast<float4*>(red + ((int64_t)warp * kMaxB + 4 * bq + bb) * Hc + 4 * jq) =
-          make_float4(acc[bb][0], acc[bb][1], acc[bb][2], acc[bb][3]);
+      *reinterpret_cast<float4*>(red + ((int64_t)warp * kMaxB + bq + 8 * bb) * Hc + 4 * jq) =
+          make_float4(sum2(acc[bb][0]), sum2(acc[bb][1]), sum2(acc[bb][2]), sum2(acc[bb][3]));
   }
 }
 
-__global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
+__global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
   if (a.gated && a.st->stopped) return;
   extern __shared__ __align__(16) float smem[];
   __shared__ int64_t s_rows[kMaxB];
@@ -106,20 +135,25 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
   const int H = a.H, L = a.L;
   const int C = (int)cluster_size(), r = (int)cluster_rank();
   const int Hc = H / C, j0 = r * Hc;
-  const int HP = H + kPad;
+  const int HcP = hid_row_pitch(Hc), SL = kMaxB * HcP;
   const int nb = a.src.nb;
   const int NS = a.n_slots;
   const SmallLayout sl{H, L};
+  int dbg_n = 0;
+  auto mark = [&]() {
+    if (a.dbg != nullptr && tid == 0 && dbg_n < 256) a.dbg[r * 256 + dbg_n++] = clock64();
+  };
+  mark();
 
-  float* full0 = smem;                              // [2][32][HP]  gathered activations / dz (double buffer)
-  float* red = full0 + 2 * kMaxB * HP;              // [8][32][Hc]  (>= 1024 floats)
-  const int red_floats = kHidWarps * kMaxB * Hc < 1024 ? 1024 : kHidWarps * kMaxB * Hc;
-  float* own_a = red + red_floats;                  // [L][32][Hc] elu outputs (pre-dropout) of the own slice
+  float* full0 = smem;                              // [2][C][32][HcP] gathered activations / dz (double buffer)
+  float* stage = full0 + 2 * C * SL;                // [2][32][HcP]    own slice staged for the bulk copies
+  float* red = stage + 2 * SL;                      // [16][32][Hc]    per-warp partial sums
+  float* own_a = red + kHidWarps * kMaxB * Hc;      // [L][32][Hc] elu outputs (pre-dropout) of the own slice
   float* own_dz = own_a + (int64_t)L * kMaxB * Hc;  // [L][32][Hc] dz of the own slice
   float* keep = own_dz + (int64_t)L * kMaxB * Hc;   // [32][Hc]    dropout multiplier of the own slice
   float* ysm = keep + kMaxB * Hc;                   // y1, y2, dy1, dy2 [32][2] each, dist[32]
   float* sbias = ysm + 320;                         // [L][Hc] own bias slices
-  float* sout = sbias + L * Hc;                     // Wo1[H][2], bo1[2], Wo2[4], bo2[2]
+  float* sout = sbias + ((L * Hc + 3) & ~3);        // Wo1[H][2], bo1[2], Wo2[4], bo2[2]
   float* wslot = sout + ((2 * H + 8 + 3) & ~3);     // [NS][H][Hc] weight-slice ring
   float* y1s = ysm;
   float* y2s = ysm + 64;
@@ -142,18 +176,19 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
                  "l"(src), "r"(slice_bytes), "r"(bar)
                  : "memory");
   };
-  auto wait_slice = [&](int u) -> const float* {
-    const int slot = u % NS;
-    const uint32_t parity = (uint32_t)(u / NS) & 1u;
+  auto mbar_wait = [&](uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
     while (!ok) {
       asm volatile(
           "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
           : "=r"(ok)
-          : "r"(hid_smem_u32(&wbar[slot])), "r"(parity)
+          : "r"(bar), "r"(parity)
           : "memory");
     }
-    return wslot + (int64_t)slot * H * Hc;
+  };
+  auto wait_slice = [&](int u) -> const float* {
+    mbar_wait(hid_smem_u32(&wbar[u % NS]), (uint32_t)(u / NS) & 1u);
+    return wslot + (int64_t)(u % NS) * H * Hc;
   };
   if (tid == 0) {
     for (int s = 0; s < NS; ++s)
@@ -175,32 +210,39 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
   __syncthreads();
   cluster_barrier();  // every CTA of the cluster is running before anyone writes into its shared memory
 
-  // Work items of the finishing passes: (b, 4 consecutive columns of the own slice); when there are
-  // fewer items than threads the destination CTAs of the publish are split over thread groups.
+  // Finishing passes work on items = (batch row, 4 consecutive columns of the own slice).
   const int items = kMaxB * Hc / 4;
-  const int groups = items >= kHidThreads ? 1 : kHidThreads / items;
-  int pub = 0;  // number of publishes so far: publish n goes to buffer n & 1
-  auto publish = [&](int b, int jl, float4 v, int grp) {
-    const uint32_t local = hid_smem_u32(full0 + (pub & 1) * kMaxB * HP + b * HP + j0 + jl);
-    const uint32_t bar = hid_smem_u32(&ready[pub & 1]);
-    for (int d = grp; d < C; d += groups) st_async_f4(local, bar, (unsigned)d, v);
+  int pub = 0;  // number of publishes so far: publish n uses stage / gathered buffer n & 1
+  // All-gather of the staged own slice: one bulk copy per destination CTA, completing on the
+  // destination's mbarrier (the receiver just waits for C slices worth of bytes).
+  const uint32_t slice_tx = (uint32_t)(SL * sizeof(float));
+  auto publish_staged = [&]() {
+    mark();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    mark();
+    if (tid < C) {
+      const uint32_t src = hid_smem_u32(stage + (pub & 1) * SL);
+      const uint32_t dst_local = hid_smem_u32(full0 + ((pub & 1) * C + r) * SL);
+      const uint32_t bar_local = hid_smem_u32(&ready[pub & 1]);
+      uint32_t dst, bar;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(dst_local), "r"(tid));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(bar_local), "r"(tid));
+      asm volatile(
+          "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+          "r"(src), "r"(slice_tx), "r"(bar)
+          : "memory");
+    }
+    ++pub;
   };
-  // Wait until publish n (all C slices, 32*H floats) has landed in this CTA's buffer n & 1.
-  const uint32_t gather_bytes = (uint32_t)(kMaxB * H * sizeof(float));
+  // Wait until publish n (C slices) has landed in this CTA's gathered buffer n & 1.
   auto wait_gather = [&](int n) -> const float* {
     const uint32_t bar = hid_smem_u32(&ready[n & 1]);
     if (tid == 0)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(gather_bytes) : "memory");
-    const uint32_t parity = (uint32_t)(n >> 1) & 1u;
-    uint32_t ok = 0;
-    while (!ok) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok)
-          : "r"(bar), "r"(parity)
-          : "memory");
-    }
-    return full0 + (n & 1) * kMaxB * HP;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(slice_tx * (uint32_t)C)
+                   : "memory");
+    mbar_wait(bar, (uint32_t)(n >> 1) & 1u);
+    return full0 + (n & 1) * C * SL;
   };
   auto red_sum4 = [&](int nparts, int b, int jl) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -213,44 +255,40 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
     }
     return s;
   };
-  // bias, elu, (dropout), publish of the own slice of layer i from the partial sums in red
+  // bias, elu, (dropout) of the own slice of layer i from the partial sums in red -> stage
   auto finish_fwd = [&](int i, int nparts, const float* bias) {
-    for (int idx = tid; idx < items * groups; idx += kHidThreads) {
-      const int item = idx % items, grp = idx / items;
+    for (int item = tid; item < items; item += kHidThreads) {
       const int b = (item * 4) / Hc, jl = (item * 4) % Hc;
       const float4 z4 = red_sum4(nparts, b, jl);
       const float4 bi = *reinterpret_cast<const float4*>(bias + jl);
       float act[4] = {elu_f(z4.x + bi.x), elu_f(z4.y + bi.y), elu_f(z4.z + bi.z), elu_f(z4.w + bi.w)};
-      float pre[4] = {act[0], act[1], act[2], act[3]};
-      float mult[4] = {1.f, 1.f, 1.f, 1.f};
-      if (i == a.n_before - 1 && drop_on) {
+      *reinterpret_cast<float4*>(own_a + ((int64_t)i * kMaxB + b) * Hc + jl) = make_float4(act[0], act[1], act[2], act[3]);
+      if (i == a.n_before - 1) {
+        float mult[4] = {1.f, 1.f, 1.f, 1.f};
+        if (drop_on) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          bool kp;
-          if (a.masks != nullptr) {
-            const int64_t s = step_id < a.n_masks ? step_id : a.n_masks - 1;
-            kp = a.masks[(s * kMaxB + b) * H + j0 + jl + e] != 0;
-          } else {
-            kp = philox_uniform((uint64_t)b * H + j0 + jl + e, kDropoutStreamBase + (uint32_t)step_id, a.seed) >=
-                 a.p_drop;
+          for (int e = 0; e < 4; ++e) {
+            bool kp;
+            if (a.masks != nullptr) {
+              const int64_t s = step_id < a.n_masks ? step_id : a.n_masks - 1;
+              kp = a.masks[(s * kMaxB + b) * H + j0 + jl + e] != 0;
+            } else {
+              kp = philox_uniform((uint64_t)b * H + j0 + jl + e, kDropoutStreamBase + (uint32_t)step_id, a.seed) >=
+                   a.p_drop;
+            }
+            mult[e] = kp ? keep_scale : 0.f;
+            act[e] *= mult[e];
           }
-          mult[e] = kp ? keep_scale : 0.f;
-          act[e] *= mult[e];
         }
+        *reinterpret_cast<float4*>(keep + b * Hc + jl) = make_float4(mult[0], mult[1], mult[2], mult[3]);
       }
       if (b >= nb) act[0] = act[1] = act[2] = act[3] = 0.f;
-      const float4 out = make_float4(act[0], act[1], act[2], act[3]);
-      publish(b, jl, out, grp);
-      if (grp == 0) {
-        *reinterpret_cast<float4*>(own_a + ((int64_t)i * kMaxB + b) * Hc + jl) = make_float4(pre[0], pre[1], pre[2], pre[3]);
-        if (i == a.n_before - 1)
-          *reinterpret_cast<float4*>(keep + b * Hc + jl) = make_float4(mult[0], mult[1], mult[2], mult[3]);
-      }
+      *reinterpret_cast<float4*>(stage + (pub & 1) * SL + b * HcP + jl) = make_float4(act[0], act[1], act[2], act[3]);
     }
-    ++pub;
+    publish_staged();
   };
   // dz of layer i for the own slice from d loss / d (post-dropout activation)
-  auto finish_bwd = [&](int i, int b, int jl, float4 da, int grp, bool do_publish) {
+  auto finish_bwd = [&](int i, int b, int jl, float4 da) {
     float d[4] = {da.x, da.y, da.z, da.w};
     const float4 pre = *reinterpret_cast<const float4*>(own_a + ((int64_t)i * kMaxB + b) * Hc + jl);
     const float pa[4] = {pre.x, pre.y, pre.z, pre.w};
@@ -264,13 +302,15 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) d[e] = b < nb ? d[e] * elu_grad_from_out(pa[e]) : 0.f;
     const float4 out = make_float4(d[0], d[1], d[2], d[3]);
-    if (do_publish) publish(b, jl, out, grp);
-    if (grp == 0) *reinterpret_cast<float4*>(own_dz + ((int64_t)i * kMaxB + b) * Hc + jl) = out;
+    *reinterpret_cast<float4*>(stage + (pub & 1) * SL + b * HcP + jl) = out;
+    *reinterpret_cast<float4*>(own_dz + ((int64_t)i * kMaxB + b) * Hc + jl) = out;
   };
 
   // ---- layer 0: reduce the split-K partial tiles of Z1 (fixed order), bias, elu ----
   {
-    const int G = items >= kHidThreads ? 1 : kHidThreads / items;  // groups splitting the partial range
+    int G = kHidThreads / items;  // thread groups splitting the partial range
+    if (G < 1) G = 1;
+    if (G > kHidWarps) G = kHidWarps;
     const int hv = H / 4;
     for (int idx = tid; idx < items * G; idx += kHidThreads) {
       const int o = idx % items, g = idx / items;
@@ -278,7 +318,7 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
       const int pbeg = a.n_partials * g / G, pend = a.n_partials * (g + 1) / G;
       const float4* src = reinterpret_cast<const float4*>(a.partials) + ((int64_t)b * H + j0 + jl) / 4;
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 16
+#pragma unroll 8
       for (int p = pbeg; p < pend; ++p) {
         const float4 v = __ldcg(src + (int64_t)p * kMaxB * hv);
         s.x += v.x;
@@ -289,29 +329,35 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
       *reinterpret_cast<float4*>(red + ((int64_t)g * kMaxB + b) * Hc + jl) = s;
     }
     __syncthreads();
+    mark();
     finish_fwd(0, G, sbias);
+    mark();
   }
 
   // ---- layers 1..L-1 forward ----
   int use = 0;
   for (int i = 1; i < L; ++i, ++use) {
     const float* Ws = wait_slice(use);
+    mark();
     const float* in = wait_gather(pub - 1);
+    mark();
     slice_matmul(in, Ws, red, H, Hc);
     __syncthreads();
+    mark();
     if (tid == 0 && use + NS < n_uses) issue_load(use + NS);
-    finish_fwd(i, kHidWarps, sbias + i * Hc);
-    __syncthreads();  // red is rewritten by the next layer's product
+    finish_fwd(i, hid_nparts(H), sbias + i * Hc);
+    mark();
   }
 
   // ---- Dense(2), Dense(2), loss (every CTA, redundantly) ----
-  const float* full = wait_gather(pub - 1);  // a_{L-1}
+  const float* gat = wait_gather(pub - 1);  // a_{L-1}
+  mark();
   {
     const float* Wo1 = sout;
     for (int b = warp; b < kMaxB; b += kHidWarps) {
       float s0 = 0.f, s1 = 0.f;
       for (int k = lane; k < H; k += 32) {
-        const float av = full[b * HP + k];
+        const float av = gat[(k / Hc) * SL + b * HcP + (k % Hc)];
         s0 = fmaf(av, Wo1[2 * k], s0);
         s1 = fmaf(av, Wo1[2 * k + 1], s1);
       }
@@ -390,8 +436,7 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
   // ---- backward: d loss / d a_{L-1} through Dense(2) ----
   {
     const float* Wo1 = sout;
-    for (int idx = tid; idx < items * groups; idx += kHidThreads) {
-      const int item = idx % items, grp = idx / items;
+    for (int item = tid; item < items; item += kHidThreads) {
       const int b = (item * 4) / Hc, jl = (item * 4) % Hc;
       float d[4];
 #pragma unroll
@@ -399,23 +444,29 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
         const int i = j0 + jl + e;
         d[e] = dy1s[2 * b] * Wo1[2 * i] + dy1s[2 * b + 1] * Wo1[2 * i + 1];
       }
-      finish_bwd(L - 1, b, jl, make_float4(d[0], d[1], d[2], d[3]), grp, true);
+      finish_bwd(L - 1, b, jl, make_float4(d[0], d[1], d[2], d[3]));
     }
-    ++pub;
+    publish_staged();
+    mark();
   }
   for (int i = L - 1; i >= 1; --i, ++use) {
     const float* Ws = wait_slice(use);  // [j][il] = W_i[j0 + il][j]
+    mark();
     const float* in = wait_gather(pub - 1);
+    mark();
     slice_matmul(in, Ws, red, H, Hc);
     __syncthreads();
+    mark();
     if (tid == 0 && use + NS < n_uses) issue_load(use + NS);
-    for (int idx = tid; idx < items * groups; idx += kHidThreads) {
-      const int item = idx % items, grp = idx / items;
+    for (int item = tid; item < items; item += kHidThreads) {
       const int b = (item * 4) / Hc, jl = (item * 4) % Hc;
-      finish_bwd(i - 1, b, jl, red_sum4(kHidWarps, b, jl), grp, i > 1);
+      finish_bwd(i - 1, b, jl, red_sum4(hid_nparts(H), b, jl));
     }
-    if (i > 1) ++pub;
-    __syncthreads();
+    if (i > 1)
+      publish_staged();
+    else
+      __syncthreads();
+    mark();
   }
   // ---- leave activations and dz of every layer in global memory for the update kernels ----
   for (int idx = tid; idx < L * items; idx += kHidThreads) {
@@ -434,7 +485,9 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
     *reinterpret_cast<float4*>(a.dzs + ((int64_t)i * kMaxB + b) * H + j0 + jl) =
         *reinterpret_cast<const float4*>(own_dz + ((int64_t)i * kMaxB + b) * Hc + jl);
   }
+  mark();
   cluster_barrier();  // nobody exits while peers may still address its shared memory
+  mark();
   // Optimizer bookkeeping for the update kernels of this step (Keras Adam: alpha from t >= 1).
   if (r == 0 && tid == 0) {
     DevState* st = a.st;
@@ -447,14 +500,15 @@ __global__ void __launch_bounds__(kHidThreads) k_hidden(HidArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pre-sliced copies of the hidden kernels for k_hidden (C = cluster size, Hc = H / C):
-//   fs[i-1][r][k][jl] = W_i[k][r*Hc + jl]      (forward slice of CTA r)
-//   bs[i-1][r][j][il] = W_i[r*Hc + il][j]      (backward slice of CTA r, transposed)
+// Pre-sliced copies of the hidden kernels for k_hidden (C = cluster size, Hc = H / C), with pairs
+// of the reduction index interleaved for FFMA2:
+//   fs[i-1][r][k/2][jl][k&1] = W_i[k][r*Hc + jl]      (forward slice of CTA r)
+//   bs[i-1][r][j/2][il][j&1] = W_i[r*Hc + il][j]      (backward slice of CTA r, transposed)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_sliced(float* fs, float* bs, int H, int Hc, int layer, int k, int j, float w) {
   const int64_t base = (int64_t)(layer - 1) * H * H;
-  fs[base + (int64_t)(j / Hc) * H * Hc + (int64_t)k * Hc + (j % Hc)] = w;
-  bs[base + (int64_t)(k / Hc) * H * Hc + (int64_t)j * Hc + (k % Hc)] = w;
+  fs[base + (int64_t)(j / Hc) * H * Hc + (int64_t)(k / 2) * (2 * Hc) + 2 * (j % Hc) + (k & 1)] = w;
+  bs[base + (int64_t)(k / Hc) * H * Hc + (int64_t)(j / 2) * (2 * Hc) + 2 * (k % Hc) + (j & 1)] = w;
 }
 
 __global__ void k_reslice(const float* __restrict__ small, float* fs, float* bs, int H, int L, int Hc) {
@@ -550,10 +604,9 @@ __global__ void __launch_bounds__(1024) k_hidden_update(UpdArgs a) {
 
 static size_t hidden_fixed_floats(int H, int L, int cluster) {
   const int Hc = H / cluster;
-  size_t red = (size_t)kHidWarps * kMaxB * Hc;
-  if (red < 1024) red = 1024;
-  return (size_t)2 * kMaxB * (H + kPad) + red + (size_t)2 * L * kMaxB * Hc + (size_t)kMaxB * Hc + 320 + (size_t)L * Hc +
-         (size_t)((2 * H + 8 + 3) & ~3);
+  const size_t SL = (size_t)kMaxB * hid_row_pitch(Hc);
+  return 2 * cluster * SL + 2 * SL + (size_t)kHidWarps * kMaxB * Hc + (size_t)2 * L * kMaxB * Hc + (size_t)kMaxB * Hc +
+         320 + (size_t)((L * Hc + 3) & ~3) + (size_t)((2 * H + 8 + 3) & ~3);
 }
 
 int hidden_slots(int H, int L, int cluster) {

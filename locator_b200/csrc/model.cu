@@ -212,6 +212,7 @@ static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated
   h.locs = locs;
   h.src = src;
   h.pred_out = pred_out;
+  h.dbg = m->dbg;
   h.st = m->st;
   return h;
 }
@@ -333,6 +334,10 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   LOC_CUDA(cudaMalloc(&m->dzs, (size_t)nlayers * kMaxB * width * sizeof(float)));
   LOC_CUDA(cudaMalloc(&m->outs, 256 * sizeof(float)));
   LOC_CUDA(cudaMalloc(&m->hist, (size_t)max_epochs * 3 * sizeof(float)));
+  if (getenv("LOC_HID_TRACE") != nullptr) {
+    LOC_CUDA(cudaMalloc(&m->dbg, 16 * 256 * sizeof(long long)));
+    LOC_CUDA(cudaMemset(m->dbg, 0, 16 * 256 * sizeof(long long)));
+  }
   LOC_CUDA(cudaMalloc(&m->st, sizeof(DevState)));
   LOC_CUDA(cudaMemset(m->st, 0, sizeof(DevState)));
   LOC_CUDA(cudaMemset(m->dzs, 0, (size_t)nlayers * kMaxB * width * sizeof(float)));
@@ -528,6 +533,13 @@ int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t 
 }
 
 int64_t loc_debug_read(loc_model* m, int32_t which, float* h_dst, int64_t max_n, void* stream) {
+  if (m != nullptr && which == 3 && m->dbg != nullptr && h_dst != nullptr) {  // clock trace of k_hidden
+    const int64_t n = 16 * 256 * 2;                                             // as float pairs (raw int64 bits)
+    const int64_t c = n < max_n ? n : max_n;
+    cudaMemcpyAsync(h_dst, m->dbg, c * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    return n;
+  }
   if (m == nullptr || h_dst == nullptr || which < 0 || which > 2) {
     loc::fail("loc_debug_read: bad arguments", __FILE__, __LINE__);
     return -1;

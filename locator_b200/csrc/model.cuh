@@ -85,6 +85,7 @@ struct HidArgs {
   const float* locs;  // [n][2] targets of the bound matrix
   RowSrc src;
   float* pred_out;  // [n][2]
+  long long* dbg;   // optional per-CTA clock64() checkpoints [C][256] (profiling builds of the step)
   DevState* st;
 };
 
@@ -140,6 +141,7 @@ struct loc_model {
   float *best_gamma, *best_beta, *best_mmean, *best_mvar, *best_W1, *best_small;
   // workspaces
   float *partials, *acts, *dzs, *outs, *hist, *pred_tmp;
+  long long* dbg;
   loc::DevState* st;
   // bound data
   const uint32_t *train_packed, *val_packed;

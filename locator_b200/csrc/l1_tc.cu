@@ -15,15 +15,18 @@
 //   5-stage mbarrier ring; accumulators (2 x 32 columns) stay in TMEM for the whole K range; the
 //   epilogue writes one [32][256] partial tile per CTA (reduced in fixed order by k_hidden).
 //
-// BACKWARD (k_l1_bwd_tc), two CTAs per SM, split over SNPs, 64 SNPs per tile:
+// BACKWARD (k_l1_bwd_tc), one persistent CTA per SM, split over SNPs, 64 SNPs per tile:
 //   S[j, k] = sum_b dZ1[b, j] * (x[b, k] - mean_k)   M = 128 (two halves of j), N = 64 SNPs, K = 8 rows / MMA
 //   A = dZ1 as hi + lo tf32 parts (MN-major, swizzled, built once per CTA), B = centred genotypes
 //   (K-major, swizzled; exact in tf32 for a full batch, hi + lo otherwise) -> S is fp32-accurate.
-//   Epilogue warps own accumulator row j = TMEM lane, so for every SNP a warp touches 128
-//   contiguous bytes of W1 / m / v: the Adam update streams W1, m, v exactly once with coalesced
-//   32-bit accesses; dW1 never exists in memory.  P_k, Q_k (for dgamma, dbeta) are reduced with a
+//   W1, m, v never touch the load/store units' global path: a load thread streams 8-SNP chunks
+//   (3 x 8 KB, contiguous rows) into a 4-stage shared-memory ring with cp.async.bulk + mbarrier, the
+//   epilogue warps (accumulator row j = TMEM lane, so a warp reads/writes 128 contiguous bytes of a
+//   row: conflict-free) apply Adam in place, and a store thread writes the chunk back with
+//   cp.async.bulk; dW1 never exists in memory.  P_k, Q_k (for dgamma, dbeta) are reduced with a
 //   butterfly transpose across the warp and summed across warps in fixed order.
-//   warps 0-7: epilogue | warps 8-9: genotype unpack / BN statistics / gamma-beta Adam, MMA issue.
+//   warps 0-15: epilogue (two groups alternating chunks) | 16-17: genotype unpack / BN statistics /
+//   gamma-beta Adam, MMA issue | 18: bulk loads | 19: bulk stores.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -351,13 +354,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // Backward + Adam
 // ---------------------------------------------------------------------------------------------
-constexpr int B_NT = 64;                       // SNPs per tile
-constexpr int B_EPI_WARPS = 8;
-constexpr int B_THREADS = 320;                 // 8 epilogue warps + 2 builder warps
+constexpr int B_NT = 64;                       // SNPs per tile (one accumulator buffer)
+constexpr int B_CH = 8;                        // SNPs per streamed chunk (one W/m/v stage)
+constexpr int B_STAGES = 4;
+constexpr int B_EPI_WARPS = 16;                // two groups of 8: group g owns the chunks with index % 2 == g
+constexpr int B_THREADS = (B_EPI_WARPS + 4) * 32;  // + 2 builder warps, 1 load warp, 1 store warp
 constexpr int B_DZ = kMaxB * kH * 4;           // 32 KB: [8 chunks][32 rows (b)][128 B]
 constexpr int B_DZ_CHUNK = kMaxB * 128;        // 4096
 constexpr int B_X = B_NT * 128;                // 8 KB: [64 rows (SNP)][32 batch]
-constexpr int B_SMEM = 2 * B_DZ + 4 * B_X + 2 * B_NT * 16 + 2 * B_EPI_WARPS * B_NT * 8 + 2 * 32 * 8 + 256 + 1024;
+constexpr int B_ARR = B_CH * kH * 4;           // 8 KB: one array's rows of a chunk
+constexpr int B_STAGE = 3 * B_ARR;             // 24 KB: W | m | v
+constexpr int B_SMEM = 2 * B_DZ + 4 * B_X + B_STAGES * B_STAGE + 2 * B_NT * 16 + 2 * 8 * B_NT * 8 + 2 * 32 * 8 + 512 + 1024;
 
 __device__ __forceinline__ void adam_update_fast(float& w, float& m, float& v, float g, float alpha) {
   m = m + (g - m) * kAdam1mB1;
@@ -365,7 +372,17 @@ __device__ __forceinline__ void adam_update_fast(float& w, float& m, float& v, f
   w = w - __fdividef(m * alpha, sqrtf(v) + kAdamEps);
 }
 
-__global__ void __launch_bounds__(B_THREADS, 2) k_l1_bwd_tc(L1Args a, int64_t ntiles) {
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t ntiles) {
   if (a.gated && a.st->stopped) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -373,13 +390,17 @@ __global__ void __launch_bounds__(B_THREADS, 2) k_l1_bwd_tc(L1Args a, int64_t nt
   uint8_t* sDZlo = sDZhi + B_DZ;
   uint8_t* sXhi = sDZlo + B_DZ;                  // [2][B_X]
   uint8_t* sXlo = sXhi + 2 * B_X;                // [2][B_X]
-  float4* sSc = (float4*)(sXlo + 2 * B_X);       // [2][64] (inv, beta, -, -)
+  uint8_t* sStage = sXlo + 2 * B_X;              // [B_STAGES][W | m | v][8 rows][256]
+  float4* sSc = (float4*)(sStage + B_STAGES * B_STAGE);  // [2][64] (inv, beta, -, -)
   float2* sRed = (float2*)(sSc + 2 * B_NT);      // [2][8 warps][64] (P, Q) partial sums
-  uint32_t* sBits = (uint32_t*)(sRed + 2 * B_EPI_WARPS * B_NT);  // [2 builder warps][32 rows][2 words]
+  uint32_t* sBits = (uint32_t*)(sRed + 2 * 8 * B_NT);  // [2 builder warps][32 rows][2 words]
   uint64_t* bars = (uint64_t*)(sBits + 2 * 32 * 2);
-  uint64_t* tmem_full = bars;       // [2]
-  uint64_t* tmem_empty = bars + 2;  // [2]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+  uint64_t* tmem_full = bars;                    // [2]  MMA of a tile done
+  uint64_t* tmem_empty = bars + 2;               // [2]  all 16 epilogue warps done with a tile
+  uint64_t* st_full = bars + 4;                  // [B_STAGES] W/m/v chunk landed
+  uint64_t* st_done = st_full + B_STAGES;        // [B_STAGES] chunk updated in place (8 warps)
+  uint64_t* st_free = st_done + B_STAGES;        // [B_STAGES] chunk written back, stage reusable
+  uint32_t* tmem_slot = (uint32_t*)(st_free + B_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = a.src.nb;
@@ -387,12 +408,18 @@ __global__ void __launch_bounds__(B_THREADS, 2) k_l1_bwd_tc(L1Args a, int64_t nt
   const int64_t t_begin = ntiles * blockIdx.x / gridDim.x;
   const int64_t t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
   const int nloc = (int)(t_end - t_begin);
+  const int nchunks = nloc * (B_NT / B_CH);
 
   if (threadIdx.x == 0) {
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], B_EPI_WARPS);
     mbar_init(&tmem_empty[1], B_EPI_WARPS);
+    for (int s = 0; s < B_STAGES; ++s) {
+      mbar_init(&st_full[s], 1);
+      mbar_init(&st_done[s], 8);
+      mbar_init(&st_free[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == B_EPI_WARPS) tmem_alloc(tmem_slot, 256);
@@ -413,73 +440,122 @@ __global__ void __launch_bounds__(B_THREADS, 2) k_l1_bwd_tc(L1Args a, int64_t nt
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const float alpha = a.st->alpha;
+  // rows of chunk c (CTA-local index) that exist (K need not be a multiple of 8)
+  auto chunk_rows = [&](int c) -> int {
+    const int64_t k0 = t_begin * B_NT + (int64_t)c * B_CH;
+    const int64_t left = a.K - k0;
+    return left >= B_CH ? B_CH : (left > 0 ? (int)left : 0);
+  };
 
   if (warp < B_EPI_WARPS) {
     // =========================== epilogue warps ===========================
-    const int h = warp >> 2, q = warp & 3;
+    const int grp = warp >> 3, w8 = warp & 7;
+    const int h = w8 >> 2, q = w8 & 3;
     const int j = h * 128 + q * 32 + lane;
     float c0 = 0.f;
     for (int b = 0; b < nb; ++b) c0 += __ldcg(a.dZ1 + b * kH + j);
-    for (int li = 0; li < nloc; ++li) {
+    for (int c = grp; c < nchunks; c += 2) {
+      const int li = c >> 3, cc = c & 7;
       const int buf = li & 1;
-      const int64_t k0 = (t_begin + li) * B_NT;
-      mbar_wait(&tmem_full[buf], (uint32_t)(li >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t tbase = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 128 + h * 64);
-#pragma unroll 1
-      for (int c = 0; c < B_NT / 8; ++c) {
-        uint32_t gr[8];
-        tmem_ld_x8(tbase + c * 8, gr);
-        float w[8], m[8], v[8];
-        const int64_t kc = k0 + c * 8;
+      const int s = c % B_STAGES;
+      if (cc < 2) {  // first chunk of the tile for this group
+        mbar_wait(&tmem_full[buf], (uint32_t)(li >> 1) & 1u);
+        tc_fence_after();
+      }
+      uint32_t gr[8];
+      tmem_ld_x8(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 128 + h * 64 + cc * 8), gr);
+      mbar_wait(&st_full[s], (uint32_t)(c / B_STAGES) & 1u);
+      const int nv = chunk_rows(c);
+      float* stw = reinterpret_cast<float*>(sStage + s * B_STAGE) + j;
+      float w[8], m[8], v[8];
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          const int64_t idx = (kc + s) * kH + j;
-          const bool ok = kc + s < a.K;
-          w[s] = ok ? a.W1[idx] : 0.f;
-          m[s] = ok ? a.mW1[idx] : 0.f;
-          v[s] = ok ? a.vW1[idx] : 0.f;
-        }
-        tmem_ld_wait();
-        float pq[16];
+      for (int r = 0; r < 8; ++r) {
+        w[r] = stw[r * kH];
+        m[r] = stw[B_ARR / 4 + r * kH];
+        v[r] = stw[2 * (B_ARR / 4) + r * kH];
+      }
+      tmem_ld_wait();
+      float pq[16];
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          const float4 sc = sSc[buf * B_NT + c * 8 + s];
-          const float S = __uint_as_float(gr[s]);
-          const float g = sc.x * S + sc.y * c0;
-          pq[s] = w[s] * S;
-          pq[8 + s] = w[s] * c0;
-          adam_update_fast(w[s], m[s], v[s], g, alpha);
-        }
+      for (int r = 0; r < 8; ++r) {
+        const float4 sc = sSc[buf * B_NT + cc * 8 + r];
+        const float S = __uint_as_float(gr[r]);
+        const float g = sc.x * S + sc.y * c0;
+        const bool ok = r < nv;
+        pq[r] = ok ? w[r] * S : 0.f;
+        pq[8 + r] = ok ? w[r] * c0 : 0.f;
+        adam_update_fast(w[r], m[r], v[r], g, alpha);
+      }
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          if (kc + s < a.K) {
-            const int64_t idx = (kc + s) * kH + j;
-            a.W1[idx] = w[s];
-            a.mW1[idx] = m[s];
-            a.vW1[idx] = v[s];
-          }
-        }
-        // butterfly transpose-reduce: lane l ends with the warp total of pq[l & 15]
-#pragma unroll
-        for (int o = 8; o >= 1; o >>= 1) {
-          const bool up = (lane & o) != 0;
-#pragma unroll
-          for (int i = 0; i < o; ++i) {
-            const float send = up ? pq[i] : pq[i + o];
-            const float keep = up ? pq[i + o] : pq[i];
-            pq[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-          }
-        }
-        pq[0] += __shfl_xor_sync(0xffffffffu, pq[0], 16);
-        if (lane < 16) {
-          float* dst = reinterpret_cast<float*>(&sRed[(buf * B_EPI_WARPS + warp) * B_NT + c * 8 + (lane & 7)]);
-          dst[lane >> 3] = pq[0];
+      for (int r = 0; r < 8; ++r) {
+        if (r < nv) {
+          stw[r * kH] = w[r];
+          stw[B_ARR / 4 + r * kH] = m[r];
+          stw[2 * (B_ARR / 4) + r * kH] = v[r];
         }
       }
-      tc_fence_before();
+      fence_proxy_async();  // the bulk store reads these rows through the async proxy
+      // butterfly transpose-reduce: lane l ends with the warp total of pq[l & 15]
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+          const float send = up ? pq[i] : pq[i + o];
+          const float keep = up ? pq[i + o] : pq[i];
+          pq[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      pq[0] += __shfl_xor_sync(0xffffffffu, pq[0], 16);
+      if (lane < 16) {
+        float* dst = reinterpret_cast<float*>(&sRed[(buf * 8 + w8) * B_NT + cc * 8 + (lane & 7)]);
+        dst[lane >> 3] = pq[0];
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (lane == 0) mbar_arrive(&st_done[s]);
+      if (cc >= 6) {  // last chunk of the tile for this group
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      }
+    }
+  } else if (warp == B_EPI_WARPS + 2) {
+    // =========================== load warp: W, m, v chunk -> stage ===========================
+    if (lane == 0) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % B_STAGES;
+        mbar_wait(&st_free[s], ((uint32_t)(c / B_STAGES) & 1u) ^ 1u);
+        const int nv = chunk_rows(c);
+        const uint32_t bytes = (uint32_t)nv * kH * 4;
+        mbar_arrive_expect_tx(&st_full[s], 3 * bytes);
+        if (nv > 0) {
+          const int64_t off = (t_begin * B_NT + (int64_t)c * B_CH) * kH;
+          const uint32_t dst = smem_u32(sStage + s * B_STAGE);
+          bulk_load(dst, a.W1 + off, bytes, &st_full[s]);
+          bulk_load(dst + B_ARR, a.mW1 + off, bytes, &st_full[s]);
+          bulk_load(dst + 2 * B_ARR, a.vW1 + off, bytes, &st_full[s]);
+        }
+      }
+    }
+  } else if (warp == B_EPI_WARPS + 3) {
+    // =========================== store warp: updated chunk -> W, m, v ===========================
+    if (lane == 0) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % B_STAGES;
+        mbar_wait(&st_done[s], (uint32_t)(c / B_STAGES) & 1u);
+        const int nv = chunk_rows(c);
+        if (nv > 0) {
+          const uint32_t bytes = (uint32_t)nv * kH * 4;
+          const int64_t off = (t_begin * B_NT + (int64_t)c * B_CH) * kH;
+          const uint32_t src = smem_u32(sStage + s * B_STAGE);
+          bulk_store(a.W1 + off, src, bytes);
+          bulk_store(a.mW1 + off, src + B_ARR, bytes);
+          bulk_store(a.vW1 + off, src + 2 * B_ARR, bytes);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        mbar_arrive(&st_free[s]);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else {
     // =========================== builder warps (2 x 32 SNPs per tile) ===========================
@@ -498,8 +574,8 @@ __global__ void __launch_bounds__(B_THREADS, 2) k_l1_bwd_tc(L1Args a, int64_t nt
       const int64_t k = (t_begin + li) * B_NT + wb * 32 + lane;
       float P = 0.f, Q = 0.f;
 #pragma unroll
-      for (int w = 0; w < B_EPI_WARPS; ++w) {
-        const float2 r = sRed[(buf * B_EPI_WARPS + w) * B_NT + wb * 32 + lane];
+      for (int w = 0; w < 8; ++w) {
+        const float2 r = sRed[(buf * 8 + w) * B_NT + wb * 32 + lane];
         P += r.x;
         Q += r.y;
       }
@@ -708,7 +784,7 @@ int l1_backward_tc(const L1Args& a, int nblocks, cudaStream_t s) {
     attr_set = true;
   }
   const int64_t ntiles = cdiv(a.K, tc::B_NT);
-  const int64_t grid = ntiles < 2 * tc_sm_count() ? ntiles : 2 * tc_sm_count();
+  const int64_t grid = ntiles < tc_sm_count() ? ntiles : tc_sm_count();
   tc::k_l1_bwd_tc<<<(unsigned)grid, tc::B_THREADS, tc::B_SMEM, s>>>(a, ntiles);
   LOC_LAUNCHED();
   return 0;

@@ -77,7 +77,9 @@ __device__ __forceinline__ float sum2(unsigned long long v) {
 // Ws is the weight slice in shared memory with k pairs interleaved: Ws[k/2][jl][k&1], so that both
 // FFMA2 operands -- (A[b][k], A[b][k+1]) and (W[k][jl], W[k+1][jl]) -- are natural 64-bit pairs of
 // the 128-bit loads; even and odd k accumulate separately and are added at the end.
-__device__ __noinline__ void slice_matmul(const float* gathered, const float* Ws, float* red, int H, int Hc) {
+template <int TH, int THc>
+__device__ __noinline__ void slice_matmul(const float* gathered, const float* Ws, float* red, int rH, int rHc) {
+  const int H = TH ? TH : rH, Hc = THc ? THc : rHc;
   const int HcP = hid_row_pitch(Hc), SL = kMaxB * HcP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // the H/4 four-wide k groups are dealt to the warps in contiguous runs (hid_nparts warps get work)
@@ -125,6 +127,9 @@ __device__ __noinline__ void slice_matmul(const float* gathered, const float* Ws
   }
 }
 
+// TH / THc: compile-time width and slice width (0 = take them from the arguments): the common
+// 256-wide, 16-CTA configuration gets shift-and-mask index arithmetic and fully unrolled loops.
+template <int TH, int THc>
 __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
   if (a.gated && a.st->stopped) return;
   extern __shared__ __align__(16) float smem[];
@@ -132,9 +137,10 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
   __shared__ __align__(8) uint64_t wbar[kMaxSlots];
   __shared__ __align__(8) uint64_t ready[2];  // gathered-buffer full barriers (bytes from all C CTAs)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int H = a.H, L = a.L;
-  const int C = (int)cluster_size(), r = (int)cluster_rank();
-  const int Hc = H / C, j0 = r * Hc;
+  const int H = TH ? TH : a.H, L = a.L;
+  const int C = (TH && THc) ? TH / THc : (int)cluster_size();
+  const int r = (int)cluster_rank();
+  const int Hc = THc ? THc : H / C, j0 = r * Hc;
   const int HcP = hid_row_pitch(Hc), SL = kMaxB * HcP;
   const int nb = a.src.nb;
   const int NS = a.n_slots;
@@ -221,13 +227,15 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     mark();
-    if (tid < C) {
+    // one issuing lane per warp: bulk copies are uniform-datapath instructions, lanes of one warp serialise
+    for (int d = warp; d < C; d += kHidWarps) {
+      if (lane != 0) continue;
       const uint32_t src = hid_smem_u32(stage + (pub & 1) * SL);
       const uint32_t dst_local = hid_smem_u32(full0 + ((pub & 1) * C + r) * SL);
       const uint32_t bar_local = hid_smem_u32(&ready[pub & 1]);
       uint32_t dst, bar;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(dst_local), "r"(tid));
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(bar_local), "r"(tid));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(dst_local), "r"(d));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(bar_local), "r"(d));
       asm volatile(
           "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
           "r"(src), "r"(slice_tx), "r"(bar)
@@ -244,66 +252,64 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
     mbar_wait(bar, (uint32_t)(n >> 1) & 1u);
     return full0 + (n & 1) * C * SL;
   };
-  auto red_sum4 = [&](int nparts, int b, int jl) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int w = 0; w < nparts; ++w) {
+  // Finishing passes: 4 consecutive lanes share one item (b, 4 columns): each sums a quarter of the
+  // per-warp partials, a 2-step shuffle combines them (fixed order), then lane e finishes column e.
+  auto red_quad = [&](int nparts, int item, int sub) -> float {
+    const int b = (item * 4) / Hc, jl = (item * 4) % Hc;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = sub; w < nparts; w += 4) {
       const float4 v = *reinterpret_cast<const float4*>(red + ((int64_t)w * kMaxB + b) * Hc + jl);
-      s.x += v.x;
-      s.y += v.y;
-      s.z += v.z;
-      s.w += v.w;
+      s4.x += v.x;
+      s4.y += v.y;
+      s4.z += v.z;
+      s4.w += v.w;
     }
-    return s;
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      s4.x += __shfl_xor_sync(0xffffffffu, s4.x, o);
+      s4.y += __shfl_xor_sync(0xffffffffu, s4.y, o);
+      s4.z += __shfl_xor_sync(0xffffffffu, s4.z, o);
+      s4.w += __shfl_xor_sync(0xffffffffu, s4.w, o);
+    }
+    return sub == 0 ? s4.x : (sub == 1 ? s4.y : (sub == 2 ? s4.z : s4.w));
   };
+  const int fin_n = (items * 4 + kHidThreads - 1) / kHidThreads * kHidThreads;  // whole warps stay converged
   // bias, elu, (dropout) of the own slice of layer i from the partial sums in red -> stage
   auto finish_fwd = [&](int i, int nparts, const float* bias) {
-    for (int item = tid; item < items; item += kHidThreads) {
-      const int b = (item * 4) / Hc, jl = (item * 4) % Hc;
-      const float4 z4 = red_sum4(nparts, b, jl);
-      const float4 bi = *reinterpret_cast<const float4*>(bias + jl);
-      float act[4] = {elu_f(z4.x + bi.x), elu_f(z4.y + bi.y), elu_f(z4.z + bi.z), elu_f(z4.w + bi.w)};
-      *reinterpret_cast<float4*>(own_a + ((int64_t)i * kMaxB + b) * Hc + jl) = make_float4(act[0], act[1], act[2], act[3]);
+    for (int idx = tid; idx < fin_n; idx += kHidThreads) {
+      const int item = idx >> 2, e = idx & 3;
+      const bool on = item < items;
+      const float z = red_quad(nparts, on ? item : 0, e);
+      if (!on) continue;
+      const int b = (item * 4) / Hc, jl = (item * 4) % Hc + e;
+      float act = elu_f(z + bias[jl]);
+      own_a[((int64_t)i * kMaxB + b) * Hc + jl] = act;
       if (i == a.n_before - 1) {
-        float mult[4] = {1.f, 1.f, 1.f, 1.f};
+        float mult = 1.f;
         if (drop_on) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            bool kp;
-            if (a.masks != nullptr) {
-              const int64_t s = step_id < a.n_masks ? step_id : a.n_masks - 1;
-              kp = a.masks[(s * kMaxB + b) * H + j0 + jl + e] != 0;
-            } else {
-              kp = philox_uniform((uint64_t)b * H + j0 + jl + e, kDropoutStreamBase + (uint32_t)step_id, a.seed) >=
-                   a.p_drop;
-            }
-            mult[e] = kp ? keep_scale : 0.f;
-            act[e] *= mult[e];
+          bool kp;
+          if (a.masks != nullptr) {
+            const int64_t s = step_id < a.n_masks ? step_id : a.n_masks - 1;
+            kp = a.masks[(s * kMaxB + b) * H + j0 + jl] != 0;
+          } else {
+            kp = philox_uniform((uint64_t)b * H + j0 + jl, kDropoutStreamBase + (uint32_t)step_id, a.seed) >= a.p_drop;
           }
+          mult = kp ? keep_scale : 0.f;
+          act *= mult;
         }
-        *reinterpret_cast<float4*>(keep + b * Hc + jl) = make_float4(mult[0], mult[1], mult[2], mult[3]);
+        keep[b * Hc + jl] = mult;
       }
-      if (b >= nb) act[0] = act[1] = act[2] = act[3] = 0.f;
-      *reinterpret_cast<float4*>(stage + (pub & 1) * SL + b * HcP + jl) = make_float4(act[0], act[1], act[2], act[3]);
+      stage[(pub & 1) * SL + b * HcP + jl] = b < nb ? act : 0.f;
     }
     publish_staged();
   };
-  // dz of layer i for the own slice from d loss / d (post-dropout activation)
-  auto finish_bwd = [&](int i, int b, int jl, float4 da) {
-    float d[4] = {da.x, da.y, da.z, da.w};
-    const float4 pre = *reinterpret_cast<const float4*>(own_a + ((int64_t)i * kMaxB + b) * Hc + jl);
-    const float pa[4] = {pre.x, pre.y, pre.z, pre.w};
-    if (i == a.n_before - 1) {
-      const float4 km = *reinterpret_cast<const float4*>(keep + b * Hc + jl);
-      d[0] *= km.x;
-      d[1] *= km.y;
-      d[2] *= km.z;
-      d[3] *= km.w;
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) d[e] = b < nb ? d[e] * elu_grad_from_out(pa[e]) : 0.f;
-    const float4 out = make_float4(d[0], d[1], d[2], d[3]);
-    *reinterpret_cast<float4*>(stage + (pub & 1) * SL + b * HcP + jl) = out;
-    *reinterpret_cast<float4*>(own_dz + ((int64_t)i * kMaxB + b) * Hc + jl) = out;
+  // dz of layer i for one element of the own slice from d loss / d (post-dropout activation)
+  auto finish_bwd = [&](int i, int b, int jl, float da) {
+    if (i == a.n_before - 1) da *= keep[b * Hc + jl];
+    const float act = own_a[((int64_t)i * kMaxB + b) * Hc + jl];
+    const float dz = b < nb ? da * elu_grad_from_out(act) : 0.f;
+    stage[(pub & 1) * SL + b * HcP + jl] = dz;
+    own_dz[((int64_t)i * kMaxB + b) * Hc + jl] = dz;
   };
 
   // ---- layer 0: reduce the split-K partial tiles of Z1 (fixed order), bias, elu ----
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
     mark();
     const float* in = wait_gather(pub - 1);
     mark();
-    slice_matmul(in, Ws, red, H, Hc);
+    slice_matmul<TH, THc>(in, Ws, red, H, Hc);
     __syncthreads();
     mark();
     if (tid == 0 && use + NS < n_uses) issue_load(use + NS);
@@ -436,15 +442,10 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
   // ---- backward: d loss / d a_{L-1} through Dense(2) ----
   {
     const float* Wo1 = sout;
-    for (int item = tid; item < items; item += kHidThreads) {
-      const int b = (item * 4) / Hc, jl = (item * 4) % Hc;
-      float d[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = j0 + jl + e;
-        d[e] = dy1s[2 * b] * Wo1[2 * i] + dy1s[2 * b + 1] * Wo1[2 * i + 1];
-      }
-      finish_bwd(L - 1, b, jl, make_float4(d[0], d[1], d[2], d[3]));
+    for (int idx = tid; idx < kMaxB * Hc; idx += kHidThreads) {
+      const int b = idx / Hc, jl = idx % Hc;
+      const int i = j0 + jl;
+      finish_bwd(L - 1, b, jl, dy1s[2 * b] * Wo1[2 * i] + dy1s[2 * b + 1] * Wo1[2 * i + 1]);
     }
     publish_staged();
     mark();
@@ -454,13 +455,15 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
     mark();
     const float* in = wait_gather(pub - 1);
     mark();
-    slice_matmul(in, Ws, red, H, Hc);
+    slice_matmul<TH, THc>(in, Ws, red, H, Hc);
     __syncthreads();
     mark();
     if (tid == 0 && use + NS < n_uses) issue_load(use + NS);
-    for (int item = tid; item < items; item += kHidThreads) {
-      const int b = (item * 4) / Hc, jl = (item * 4) % Hc;
-      finish_bwd(i - 1, b, jl, red_sum4(hid_nparts(H), b, jl));
+    for (int idx = tid; idx < fin_n; idx += kHidThreads) {
+      const int item = idx >> 2, e = idx & 3;
+      const bool on = item < items;
+      const float da = red_quad(hid_nparts(H), on ? item : 0, e);
+      if (on) finish_bwd(i - 1, (item * 4) / Hc, (item * 4) % Hc + e, da);
     }
     if (i > 1)
       publish_staged();
@@ -527,7 +530,8 @@ __global__ void k_reslice(const float* __restrict__ small, float* fs, float* bs,
 // ---------------------------------------------------------------------------------------------
 constexpr int kUpdRows = 16;
 
-__global__ void __launch_bounds__(1024) k_hidden_update(UpdArgs a) {
+// (register cap: its blocks must fit beside the resident first-layer backward CTAs, which it overlaps)
+__global__ void __maxnreg__(56) k_hidden_update(UpdArgs a) {
   if (a.gated && a.st->stopped) return;
   __shared__ float as[kUpdRows][kMaxB + 1];
   const int H = a.H, L = a.L, j = threadIdx.x;
@@ -626,6 +630,11 @@ size_t hidden_smem_bytes(int H, int L, int cluster) {
   return hidden_fixed_floats(H, L, cluster) * sizeof(float) + (size_t)ns * H * (H / cluster) * sizeof(float);
 }
 
+typedef void (*hidden_fn)(HidArgs);
+static hidden_fn hidden_kernel(int H, int cluster) {
+  return (H == 256 && cluster == 16) ? k_hidden<256, 16> : k_hidden<0, 0>;
+}
+
 static int launch_hidden_cluster(const HidArgs& a, int cluster, cudaStream_t s, bool dry) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)cluster);
@@ -641,20 +650,21 @@ static int launch_hidden_cluster(const HidArgs& a, int cluster, cudaStream_t s, 
   cfg.numAttrs = 1;
   if (dry) {
     int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, k_hidden, &cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, hidden_kernel(a.H, cluster), &cfg);
     if (e != cudaSuccess) {
       cudaGetLastError();
       return 0;
     }
     return n;
   }
-  LOC_CUDA(cudaLaunchKernelEx(&cfg, k_hidden, a));
+  LOC_CUDA(cudaLaunchKernelEx(&cfg, hidden_kernel(a.H, cluster), a));
   loc::g_launches.fetch_add(1);
   return 0;
 }
 
 int hidden_max_cluster(int H, int L) {
-  cudaFuncSetAttribute(k_hidden, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(k_hidden<256, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(k_hidden<0, 0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaGetLastError();
   const int cands[5] = {16, 8, 4, 2, 1};
   for (int ci = 0; ci < 5; ++ci) {
@@ -662,7 +672,7 @@ int hidden_max_cluster(int H, int L) {
     if (H % (4 * c) != 0) continue;
     if (hidden_slots(H, L, c) < 1) continue;
     const size_t smem = hidden_smem_bytes(H, L, c);
-    if (cudaFuncSetAttribute(k_hidden, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(hidden_kernel(H, c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
       continue;
     }
@@ -679,7 +689,7 @@ int hidden_launch(const HidArgs& a, int cluster, cudaStream_t s) {
   LOC_CHECK(a.H % 32 == 0, "hidden stack: width must be a multiple of 32");
   LOC_CHECK(a.n_slots >= 1, "hidden stack: shared memory budget exceeded for this width / nlayers");
   const size_t smem = hidden_smem_bytes(a.H, a.L, cluster);
-  LOC_CUDA(cudaFuncSetAttribute(k_hidden, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LOC_CUDA(cudaFuncSetAttribute(hidden_kernel(a.H, cluster), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return launch_hidden_cluster(a, cluster, s, false);
 }
 

@@ -227,10 +227,20 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
   if ((stage_mask & 1) && forward_l1(m, a, s)) return 1;
   HidArgs h = hid_args(m, src, 1, gated, m->train_locs, nullptr);
   if ((stage_mask & 2) && hidden_launch(h, m->cluster, s)) return 1;
-  if ((stage_mask & 4) &&
-      (m->use_tc ? l1_backward_tc(a, m->n_bwd_blocks, s) : l1_backward_simt(a, m->n_bwd_blocks, s)))
-    return 1;
-  if (!(stage_mask & 8)) return 0;
+  // The small-layer update only needs the hidden kernel's outputs: it runs on a side stream next to
+  // the first-layer backward (full steps only; single-stage debug launches stay on `s`).
+  const bool fork = stage_mask == 15;
+  if (fork) {
+    LOC_CUDA(cudaEventRecord(m->ev_hid, s));
+    LOC_CUDA(cudaStreamWaitEvent(m->side, m->ev_hid, 0));
+  }
+  cudaStream_t su = fork ? m->side : s;
+  if (!(stage_mask & 8)) {
+    if ((stage_mask & 4) &&
+        (m->use_tc ? l1_backward_tc(a, m->n_bwd_blocks, s) : l1_backward_simt(a, m->n_bwd_blocks, s)))
+      return 1;
+    return 0;
+  }
   UpdArgs u;
   u.H = m->H;
   u.L = m->L;
@@ -246,7 +256,13 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
   u.outs = m->outs;
   u.nb = src.nb;
   u.st = m->st;
-  return hidden_update_launch(u, s);
+  if (hidden_update_launch(u, su)) return 1;
+  if (fork) LOC_CUDA(cudaEventRecord(m->ev_upd, m->side));
+  if ((stage_mask & 4) &&
+      (m->use_tc ? l1_backward_tc(a, m->n_bwd_blocks, s) : l1_backward_simt(a, m->n_bwd_blocks, s)))
+    return 1;
+  if (fork) LOC_CUDA(cudaStreamWaitEvent(s, m->ev_upd, 0));
+  return 0;
 }
 
 // Inference-mode forward over n rows in chunks of 32 (Keras predict/evaluate batch size).
@@ -338,6 +354,9 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
     LOC_CUDA(cudaMalloc(&m->dbg, 16 * 256 * sizeof(long long)));
     LOC_CUDA(cudaMemset(m->dbg, 0, 16 * 256 * sizeof(long long)));
   }
+  LOC_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+  LOC_CUDA(cudaEventCreateWithFlags(&m->ev_hid, cudaEventDisableTiming));
+  LOC_CUDA(cudaEventCreateWithFlags(&m->ev_upd, cudaEventDisableTiming));
   LOC_CUDA(cudaMalloc(&m->st, sizeof(DevState)));
   LOC_CUDA(cudaMemset(m->st, 0, sizeof(DevState)));
   LOC_CUDA(cudaMemset(m->dzs, 0, (size_t)nlayers * kMaxB * width * sizeof(float)));
@@ -355,6 +374,10 @@ int loc_model_destroy(loc_model* m) {
   for (float* p : ptrs)
     if (p) cudaFree(p);
   if (m->st) cudaFree(m->st);
+  if (m->dbg) cudaFree(m->dbg);
+  if (m->side) cudaStreamDestroy(m->side);
+  if (m->ev_hid) cudaEventDestroy(m->ev_hid);
+  if (m->ev_upd) cudaEventDestroy(m->ev_upd);
   delete m;
   return 0;
 }

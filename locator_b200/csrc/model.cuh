@@ -142,6 +142,8 @@ struct loc_model {
   // workspaces
   float *partials, *acts, *dzs, *outs, *hist, *pred_tmp;
   long long* dbg;
+  cudaStream_t side;        // small-layer update runs here, beside the first-layer backward
+  cudaEvent_t ev_hid, ev_upd;
   loc::DevState* st;
   // bound data
   const uint32_t *train_packed, *val_packed;

@@ -57,6 +57,14 @@ class PackedGenotypes:
     def ptr(self):
         return self.words.data_ptr()
 
+    @property
+    def shape(self):
+        """(n samples, K SNPs) -- the orientation of the reference's traingen / testgen / predgen."""
+        return (self.n, self.K)
+
+    def to_numpy(self):
+        return self.to_counts().cpu().numpy()
+
     @staticmethod
     def empty(n, K):
         rw = row_words_for(K)

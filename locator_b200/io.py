@@ -1,0 +1,206 @@
+"""Genotype readers of the product path (no scikit-allel / zarr dependency).
+
+Reference: ``load_genotypes`` /root/reference/locator/locator.py:187-228 --
+``allel.read_vcf`` (calldata/GT int8 [nvar, N, 2], missing = -1, samples),
+``zarr.open_group`` (calldata/GT, samples, variants/POS) and the ``--matrix`` table.
+The readers only produce the int8 GT cube on the host; filtering, allele counting and
+packing happen on the GPU (locator_b200.genotypes).
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import os
+import zlib
+
+import numpy as np
+
+
+class Genotypes:
+    """GT int8 [nvar, N, 2] (missing = -1) + sample IDs (+ positions), as allel.GenotypeArray is used."""
+
+    def __init__(self, gt, samples=None, positions=None):
+        self.gt = np.ascontiguousarray(gt, dtype=np.int8)
+        assert self.gt.ndim == 3 and self.gt.shape[2] == 2
+        self.samples = None if samples is None else np.asarray(samples)
+        self.positions = None if positions is None else np.asarray(positions)
+
+    @property
+    def shape(self):
+        return self.gt.shape
+
+    def __len__(self):
+        return self.gt.shape[0]
+
+    def __getitem__(self, key):
+        """Variant slicing (gt[a:b] / gt[a:b, :, :]) as the windows driver does (locator.py:538)."""
+        if isinstance(key, tuple):
+            key = key[0]
+        return Genotypes(self.gt[key], self.samples, None if self.positions is None else self.positions[key])
+
+
+def _open_bytes(path):
+    with open(path, "rb") as fh:
+        magic = fh.read(2)
+    if magic == b"\x1f\x8b":
+        with gzip.open(path, "rb") as fh:
+            return fh.read()
+    with open(path, "rb") as fh:
+        return fh.read()
+
+
+def _parse_allele(tok):
+    return -1 if tok in (b".", b"") else int(tok)
+
+
+def read_vcf(path):
+    """VCF / VCF.gz -> dict like allel.read_vcf: 'calldata/GT', 'samples', 'variants/POS'.
+
+    Fast path: FORMAT is exactly GT and every call is 3 bytes (``0|1``, ``./.``) -- one numpy view
+    per line.  Anything else goes through a per-field parser (multi-digit alleles, extra FORMAT
+    keys, haploid calls -> second allele -1).
+    """
+    data = _open_bytes(path)
+    samples = None
+    gts, pos = [], []
+    for line in data.split(b"\n"):
+        if not line or line.startswith(b"##"):
+            continue
+        line = line.rstrip(b"\r")
+        if line.startswith(b"#CHROM"):
+            samples = np.array([s.decode() for s in line.rstrip(b"\t").split(b"\t")[9:]], dtype=str)
+            continue
+        f = line.rstrip(b"\t").split(b"\t")
+        n = len(samples)
+        calls = f[9:9 + n]
+        pos.append(int(f[1]))
+        g = None
+        if f[8] == b"GT":
+            try:
+                arr = np.array(calls, dtype="S3")
+                if arr.shape[0] == n and all(len(c) == 3 for c in calls):
+                    b3 = arr.view(np.uint8).reshape(n, 3)
+                    a0 = b3[:, 0].astype(np.int16) - 48
+                    a1 = b3[:, 2].astype(np.int16) - 48
+                    ok = ((b3[:, 1] == 124) | (b3[:, 1] == 47)).all() and \
+                        (((a0 >= 0) & (a0 <= 9)) | (b3[:, 0] == 46)).all() and \
+                        (((a1 >= 0) & (a1 <= 9)) | (b3[:, 2] == 46)).all()
+                    if ok:
+                        a0[b3[:, 0] == 46] = -1
+                        a1[b3[:, 2] == 46] = -1
+                        g = np.stack([a0, a1], axis=1).astype(np.int8)
+            except ValueError:
+                g = None
+        if g is None:
+            gi = f[8].split(b":").index(b"GT")
+            g = np.full((n, 2), -1, dtype=np.int8)
+            for s, field in enumerate(calls):
+                alle = field.split(b":")[gi].replace(b"|", b"/").split(b"/")
+                g[s, 0] = _parse_allele(alle[0])
+                if len(alle) > 1:
+                    g[s, 1] = _parse_allele(alle[1])
+        gts.append(g)
+    if samples is None:
+        raise ValueError(f"{path}: no #CHROM header line")
+    gt = np.stack(gts) if gts else np.zeros((0, len(samples), 2), np.int8)
+    return {"calldata/GT": gt, "samples": samples, "variants/POS": np.array(pos, dtype=np.int64)}
+
+
+def read_matrix(path):
+    """--matrix table: first column sampleID, then one column per site with counts 0/1/2
+    (locator.py:200-227 turns count c into haplotypes (c>=1, c>=2))."""
+    import pandas as pd
+
+    gmat = pd.read_csv(path, sep="\t")
+    samples = np.array(gmat["sampleID"])
+    counts = np.array(gmat.drop(labels="sampleID", axis=1), dtype="int8")  # [N, nsites]
+    if np.any((counts < 0) | (counts > 2)):
+        raise ValueError("matrix entries must be 0, 1 or 2")
+    h1 = (counts >= 1).astype(np.int8)
+    h2 = (counts >= 2).astype(np.int8)
+    gt = np.stack([h1.T, h2.T], axis=2)
+    return Genotypes(gt, samples)
+
+
+# ---------------------------------------------------------------------------------------------
+# zarr v2 directory store (what scripts/vcf_to_zarr.py / allel.vcf_to_zarr writes)
+# ---------------------------------------------------------------------------------------------
+def _zarr_array(root, name):
+    adir = os.path.join(root, name)
+    with open(os.path.join(adir, ".zarray")) as fh:
+        meta = json.load(fh)
+    if meta.get("order", "C") != "C":
+        raise ValueError(f"{name}: only C-order zarr arrays are supported")
+    shape, chunks = tuple(meta["shape"]), tuple(meta["chunks"])
+    dtype = np.dtype(meta["dtype"])
+    comp = meta.get("compressor")
+    sep = meta.get("dimension_separator", ".")
+    fill = meta.get("fill_value", 0)
+    is_obj = dtype.kind == "O"
+    if is_obj:
+        raise ValueError(f"{name}: object (vlen) arrays are not supported; re-save with a fixed-width dtype")
+    out = np.empty(shape, dtype=dtype)
+    out[...] = 0 if fill is None else fill
+    grid = [(-(-s // c)) for s, c in zip(shape, chunks)]
+    for idx in np.ndindex(*grid) if shape else [()]:
+        fn = os.path.join(adir, sep.join(str(i) for i in idx) if shape else "0")
+        if not os.path.exists(fn):
+            continue
+        with open(fn, "rb") as fh:
+            raw = fh.read()
+        if comp is None:
+            buf = raw
+        elif comp.get("id") in ("zlib", "gzip"):
+            buf = zlib.decompress(raw, 15 + 32)
+        else:
+            raise ValueError(f"{name}: zarr compressor {comp.get('id')!r} is not available in this build "
+                             "(supported: none, zlib, gzip); convert with compressor=None or Zlib")
+        chunk = np.frombuffer(buf, dtype=dtype).reshape(chunks)
+        sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, shape))
+        out[sl] = chunk[tuple(slice(0, s.stop - s.start) for s in sl)]
+    return out
+
+
+def read_zarr(path):
+    """zarr v2 group with calldata/GT, samples, variants/POS -> dict (arrays fully loaded, like gt[:])."""
+    return {
+        "calldata/GT": _zarr_array(path, "calldata/GT"),
+        "samples": _zarr_array(path, "samples"),
+        "variants/POS": _zarr_array(path, "variants/POS"),
+    }
+
+
+def write_zarr(path, gt, samples, positions, chunk_variants=65536, compress=True):
+    """Minimal zarr v2 writer (the vcf_to_zarr equivalent of this build): zlib-compressed chunks."""
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, ".zgroup"), "w") as fh:
+        json.dump({"zarr_format": 2}, fh)
+
+    def put(name, arr, chunks):
+        adir = os.path.join(path, name)
+        os.makedirs(adir, exist_ok=True)
+        parent = os.path.dirname(adir)
+        if parent != path and not os.path.exists(os.path.join(parent, ".zgroup")):
+            with open(os.path.join(parent, ".zgroup"), "w") as fh:
+                json.dump({"zarr_format": 2}, fh)
+        meta = {"zarr_format": 2, "shape": list(arr.shape), "chunks": list(chunks), "dtype": arr.dtype.str,
+                "compressor": {"id": "zlib", "level": 1} if compress else None, "fill_value": 0, "order": "C",
+                "filters": None}
+        with open(os.path.join(adir, ".zarray"), "w") as fh:
+            json.dump(meta, fh)
+        grid = [(-(-s // c)) for s, c in zip(arr.shape, chunks)]
+        for idx in np.ndindex(*grid):
+            sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, arr.shape))
+            chunk = np.zeros(chunks, dtype=arr.dtype)
+            chunk[tuple(slice(0, s.stop - s.start) for s in sl)] = arr[sl]
+            raw = chunk.tobytes()
+            with open(os.path.join(adir, ".".join(str(i) for i in idx)), "wb") as fh:
+                fh.write(zlib.compress(raw, 1) if compress else raw)
+
+    gt = np.ascontiguousarray(gt, dtype=np.int8)
+    put("calldata/GT", gt, (min(chunk_variants, max(1, gt.shape[0])), gt.shape[1], 2))
+    s = np.asarray(samples)
+    s = s.astype("S" + str(max(1, max((len(str(x)) for x in s), default=1)))) if s.dtype.kind in "UO" else s
+    put("samples", s, (max(1, s.shape[0]),))
+    p = np.asarray(positions, dtype=np.int64)
+    put("variants/POS", p, (min(chunk_variants, max(1, p.shape[0])),))

@@ -1,0 +1,454 @@
+#!/usr/bin/env python3
+"""`locator` command of the B200-native build: same flags, same output files, same function
+surface as /root/reference/locator/locator.py, with the work done by the CUDA library.
+
+    locator --vcf data.vcf.gz --sample_data samples.txt --out out/run [--bootstrap ...]
+
+Mirrored functions (reference file:line):
+  load_genotypes :187-228   sort_samples :231-247   replace_md :250-262   filter_snps :265-281
+  normalize_locs :284-292   split_train_test :295-308   load_network :311-327
+  load_callbacks :330-362   train_network :365-394   predict_locs :397-470
+  plot_history :473-484     main :487-749 (single / --windows / --bootstrap / --jacknife drivers)
+
+Differences that are deliberate and documented in DESIGN.md:
+  * arguments are parsed in main() (the reference parses at import); the module-level ``args`` is
+    set by main() or by ``set_args`` for programmatic use;
+  * genotype matrices handed between the functions are 2-bit packed device matrices
+    (``AlleleCounts`` / ``PackedGenotypes``; ``.to_numpy()`` gives the reference's uint8 arrays);
+  * every draw the reference takes from numpy's legacy global stream is taken here with the same
+    call in the same order, so split / subsample / bootstrap / jacknife indices are bit-identical
+    for a given ``--seed``; weight init, batch order and dropout (unseeded TensorFlow in the
+    reference) come from Philox streams keyed by ``--seed``;
+  * weights files are ``.weights.npz`` (no HDF5 on this image) and only exist with --keep_weights
+    (the best-epoch checkpoint lives in device memory, not on disk);
+  * ``--gpus N`` (extension, not written to params.json) spreads --bootstrap / --windows
+    replicates over N GPUs of the box with a work queue (locator_b200.replicates).
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+args = None  # set by main() / set_args(); the functions below read it like the reference does
+
+_REFERENCE_KEYS = [
+    "vcf", "zarr", "matrix", "sample_data", "train_split", "windows", "window_start", "window_stop", "window_size",
+    "bootstrap", "jacknife", "jacknife_prop", "nboots", "batch_size", "max_epochs", "patience", "min_mac", "max_SNPs",
+    "impute_missing", "dropout_prop", "nlayers", "width", "out", "seed", "gpu_number", "plot_history", "keep_weights",
+    "load_params", "keras_verbose",
+]
+
+
+def build_parser():
+    """The reference's argparse surface, flag for flag (locator.py:12-166), plus --gpus."""
+    parser = argparse.ArgumentParser(prog="locator")
+    parser.add_argument("--vcf", help="VCF with SNPs for all samples.")
+    parser.add_argument("--zarr", help="zarr file of SNPs for all samples.")
+    parser.add_argument("--matrix", help="tab-delimited matrix of minor allele counts with first column named 'sampleID'.")
+    parser.add_argument("--sample_data", help="tab-delimited text file with columns 'sampleID \\t x \\t y'. SampleIDs must "
+                        "exactly match those in the VCF. X and Y values for samples without known locations should be NA.")
+    parser.add_argument("--train_split", default=0.9, type=float, help="0-1, proportion of samples to use for training. default: 0.9")
+    parser.add_argument("--windows", default=False, action="store_true",
+                        help="Run windowed analysis over a single chromosome (requires zarr input).")
+    parser.add_argument("--window_start", default=0, help="default: 0")
+    parser.add_argument("--window_stop", default=None, help="default: max snp position")
+    parser.add_argument("--window_size", default=5e5, help="default: 500000")
+    parser.add_argument("--bootstrap", default=False, action="store_true",
+                        help="Run bootstrap replicates by retraining on bootstrapped data.")
+    parser.add_argument("--jacknife", default=False, action="store_true",
+                        help="Run jacknife uncertainty estimate on a trained network.")
+    parser.add_argument("--jacknife_prop", default=0.05, type=float,
+                        help="proportion of SNPs to remove for jacknife resampling. default: 0.05")
+    parser.add_argument("--nboots", default=50, type=int, help="number of bootstrap replicates to run. default: 50")
+    parser.add_argument("--batch_size", default=32, type=int, help="default: 32")
+    parser.add_argument("--max_epochs", default=5000, type=int, help="default: 5000")
+    parser.add_argument("--patience", type=int, default=100,
+                        help="n epochs to run the optimizer after last improvement in validation loss. default: 100")
+    parser.add_argument("--min_mac", default=2, type=int, help="minimum minor allele count. default: 2.")
+    parser.add_argument("--max_SNPs", default=None, type=int,
+                        help="randomly select max_SNPs variants to use in the analysis default: None.")
+    parser.add_argument("--impute_missing", default=False, action="store_true",
+                        help="default: True (if False, all alleles at missing sites are ancestral)")
+    parser.add_argument("--dropout_prop", default=0.25, type=float,
+                        help="proportion of weights to zero at the dropout layer. default: 0.25")
+    parser.add_argument("--nlayers", default=10, type=int, help="number of layers in the network. default: 10")
+    parser.add_argument("--width", default=256, type=int, help="number of units per layer in the network default:256")
+    parser.add_argument("--out", help="file name stem for output")
+    parser.add_argument("--seed", default=None, type=int, help="random seed for train/test splits and SNP subsetting.")
+    parser.add_argument("--gpu_number", default=None, type=str)
+    parser.add_argument("--plot_history", default=True, type=bool, help="plot training history? default: True")
+    parser.add_argument("--keep_weights", default=False, action="store_true",
+                        help="keep model weights after training? default: False.")
+    parser.add_argument("--load_params", default=None, type=str,
+                        help="Path to a _params.json file to load parameters from a previous run. Parameters from the "
+                        "json file will supersede all parameters provided via command line.")
+    parser.add_argument("--keras_verbose", default=1, type=int,
+                        help="verbose argument passed to keras in model training. 0 = silent. default: 1.")
+    # extension of this build (kept out of params.json)
+    parser.add_argument("--gpus", default=1, type=int,
+                        help="(locator_b200) GPUs of this box to spread --bootstrap / --windows replicates over. default: 1")
+    return parser
+
+
+def set_args(namespace):
+    """Install the module-level ``args`` (programmatic use / tests)."""
+    global args
+    args = namespace
+    return args
+
+
+def _params_dict(ns):
+    return {k: getattr(ns, k) for k in _REFERENCE_KEYS}
+
+
+def _write_params():
+    with open(args.out + "_params.json", "w") as f:
+        json.dump(_params_dict(args), f, indent=2)
+
+
+# ---------------------------------------------------------------------------------------------
+# genotype containers handed between the mirrored functions
+# ---------------------------------------------------------------------------------------------
+class AlleleCounts:
+    """``ac``: derived-allele counts [K sites, N samples] (reference orientation), stored packed
+    sample-major on the device."""
+
+    def __init__(self, packed):
+        self.packed = packed  # PackedGenotypes [N, K]
+
+    @property
+    def shape(self):
+        return (self.packed.K, self.packed.n)
+
+    def __len__(self):
+        return self.packed.K
+
+    def to_numpy(self):
+        return self.packed.to_counts().cpu().numpy().T.copy()
+
+    def take_samples(self, idx):
+        """np.transpose(ac[:, idx]) -> PackedGenotypes [len(idx), K] (locator.py:303-307)."""
+        return self.packed.take_rows(np.asarray(idx, dtype=np.int64))
+
+    def site_sums(self):
+        """int64 [K]: sum over ALL samples of the allele counts (jacknife af, locator.py:714-717)."""
+        import torch
+
+        return self.packed.to_counts().sum(dim=0, dtype=torch.int64).cpu().numpy()
+
+
+def _matrix_shape(g):
+    return (g.n, g.K)
+
+
+# ---------------------------------------------------------------------------------------------
+# ingest
+# ---------------------------------------------------------------------------------------------
+def load_genotypes():
+    from . import io
+
+    if args.zarr is not None:
+        print("reading zarr")
+        callset = io.read_zarr(args.zarr)
+        genotypes = io.Genotypes(callset["calldata/GT"], callset["samples"], callset["variants/POS"])
+        samples = callset["samples"]
+    elif args.vcf is not None:
+        print("reading VCF")
+        vcf = io.read_vcf(args.vcf)
+        genotypes = io.Genotypes(vcf["calldata/GT"], vcf["samples"], vcf["variants/POS"])
+        samples = vcf["samples"]
+    elif args.matrix is not None:
+        genotypes = io.read_matrix(args.matrix)
+        samples = genotypes.samples
+    else:
+        raise SystemExit("one of --vcf, --zarr or --matrix is required")
+    return genotypes, samples
+
+
+def sort_samples(samples, genotypes):
+    import pandas as pd
+
+    sample_data = pd.read_csv(args.sample_data, sep="\t")
+    sample_data["sampleID2"] = sample_data["sampleID"]
+    sample_data.set_index("sampleID", inplace=True)
+    samples = np.asarray(samples)
+    samples = np.array([s.decode() if isinstance(s, bytes) else s for s in samples]).astype("str")
+    sample_data = sample_data.reindex(np.array(samples))
+    if not all([sample_data["sampleID2"].iloc[x] == samples[x] for x in range(len(samples))]):
+        print("sample ordering failed! Check that sample IDs match the VCF.")
+        sys.exit()
+    locs = np.array(sample_data[["x", "y"]])
+    print("loaded " + str(np.shape(genotypes)) + " genotypes\n\n")
+    return sample_data, locs
+
+
+def replace_md(genotypes, keep_idx=None, packed=None):
+    """Impute missing calls with binomial(2, site allele frequency) -- locator.py:250-262.
+
+    The scalar draws are taken from numpy's global stream in the reference's row-major
+    (site, sample) order; the imputed values are then patched into the packed matrix on the GPU.
+    """
+    from . import genotypes as G
+
+    print("imputing missing data")
+    gt = genotypes.gt if keep_idx is None else genotypes.gt[keep_idx]
+    if packed is None:
+        g, na, alt, miss, keep = G.site_stats(gt, min_mac=1)
+        packed = G.pack_sites(g, np.arange(gt.shape[0]))
+    missing = (gt < 0).any(axis=2)  # [K, N]
+    ninds = (~missing).sum(axis=1)
+    dc = (gt == 1).sum(axis=(1, 2))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        af = dc / (2 * ninds)
+    ks, samps = np.nonzero(missing)  # row-major (site, sample) order
+    if len(ks):
+        vals = np.random.binomial(2, af[ks])  # one vectorised draw == the same scalar draws in order
+        packed.patch(ks, samps, vals.astype(np.uint8))
+    return AlleleCounts(packed)
+
+
+def filter_snps(genotypes):
+    from . import genotypes as G
+
+    print("filtering SNPs")
+    g, n_alleles, alt_count, n_missing, keep = G.site_stats(genotypes.gt, min_mac=int(args.min_mac))
+    keep_idx = np.flatnonzero(keep.cpu().numpy())
+    packed = G.pack_sites(g, keep_idx)
+    if args.impute_missing:
+        ac = replace_md(genotypes, keep_idx, packed)
+    else:
+        ac = AlleleCounts(packed)
+    if not args.max_SNPs == None:  # noqa: E711  (as in the reference)
+        sel = np.random.choice(range(ac.shape[0]), args.max_SNPs, replace=False)
+        ac = AlleleCounts(ac.packed.take_cols(sel))
+    print("running on " + str(len(ac)) + " genotypes after filtering\n\n\n")
+    return ac
+
+
+def normalize_locs(locs):
+    meanlong = np.nanmean(locs[:, 0])
+    sdlong = np.nanstd(locs[:, 0])
+    meanlat = np.nanmean(locs[:, 1])
+    sdlat = np.nanstd(locs[:, 1])
+    locs = np.array([[(x[0] - meanlong) / sdlong, (x[1] - meanlat) / sdlat] for x in locs])
+    return meanlong, sdlong, meanlat, sdlat, locs
+
+
+def split_train_test(ac, locs):
+    train = np.argwhere(~np.isnan(locs[:, 0]))
+    train = np.array([x[0] for x in train])
+    tr = set(train.tolist())
+    pred = np.array([x for x in range(len(locs)) if x not in tr], dtype=np.int64)
+    test = np.random.choice(train, round((1 - args.train_split) * len(train)), replace=False)
+    te = set(test.tolist())
+    train = np.array([x for x in train if x not in te])
+    traingen = ac.take_samples(train)
+    trainlocs = locs[train]
+    testgen = ac.take_samples(test)
+    testlocs = locs[test]
+    predgen = ac.take_samples(pred)
+    return train, test, traingen, testgen, trainlocs, testlocs, pred, predgen
+
+
+# ---------------------------------------------------------------------------------------------
+# model / training / prediction
+# ---------------------------------------------------------------------------------------------
+_seed_tag = [0]  # replicate index (0 = the single / FULL model): model seeds do not depend on scheduling
+
+
+def _model_seed():
+    """Weight-init / shuffle / dropout seed: derived from --seed and the replicate index when --seed
+    is given (reproducible runs), fresh entropy otherwise (the reference never seeds TensorFlow)."""
+    if args.seed is not None:
+        return (int(args.seed) * 1000003 + _seed_tag[0]) & 0xFFFFFFFFFFFFFFFF
+    return int.from_bytes(os.urandom(8), "little")
+
+
+def load_network(traingen, dropout_prop):
+    from .model import LocatorModel
+
+    K = traingen.shape[1] if hasattr(traingen, "shape") else traingen.K
+    return LocatorModel(K, width=args.width, nlayers=args.nlayers, dropout_prop=args.dropout_prop,
+                        batch_size=args.batch_size, max_epochs=args.max_epochs, seed=_model_seed())
+
+
+class _Callback:
+    def __init__(self, kind, **kw):
+        self.kind = kind
+        self.__dict__.update(kw)
+
+
+def load_callbacks(boot):
+    """(checkpointer, earlystop, reducelr) descriptors with the reference's settings (:330-362)."""
+    if args.bootstrap or args.jacknife:
+        path = args.out + "_boot" + str(boot) + ".weights.npz"
+    else:
+        path = args.out + ".weights.npz"
+    checkpointer = _Callback("ModelCheckpoint", filepath=path, save_best_only=True, save_weights_only=True,
+                             monitor="val_loss")
+    earlystop = _Callback("EarlyStopping", monitor="val_loss", min_delta=0, patience=args.patience)
+    reducelr = _Callback("ReduceLROnPlateau", monitor="val_loss", factor=0.5, patience=int(args.patience / 6),
+                         min_delta=0, cooldown=0, min_lr=0)
+    return checkpointer, earlystop, reducelr
+
+
+def train_network(model, traingen, testgen, trainlocs, testlocs, callbacks, boot=0):
+    start = time.time()
+    checkpointer, earlystop, reducelr = callbacks
+    history = model.fit(traingen, trainlocs, epochs=args.max_epochs, batch_size=args.batch_size, shuffle=True,
+                        verbose=1 if args.keras_verbose == 2 else 0, validation_data=(testgen, testlocs),
+                        callbacks=callbacks, patience=earlystop.patience)
+    # load_weights(best checkpoint): the checkpoint lives in device memory
+    model.restore_best()
+    if args.keep_weights:
+        model.save_weights(checkpointer.filepath)
+    elapsed = time.time() - start
+    print("run time " + str(elapsed / 60) + " minutes")
+    return history, model
+
+
+def predict_locs(model, predgen, sdlong, meanlong, sdlat, meanlat, testlocs, pred, samples, testgen, history, boot=0,
+                 verbose=True):
+    import pandas as pd
+    from scipy import spatial
+
+    if verbose == True:  # noqa: E712
+        print("predicting locations...")
+    prediction = model.predict(predgen)
+    prediction = np.array([[x[0] * sdlong + meanlong, x[1] * sdlat + meanlat] for x in prediction])
+    predout = pd.DataFrame(prediction.reshape(-1, 2))
+    predout.columns = ["x", "y"]
+    samples = np.array([s.decode() if isinstance(s, bytes) else s for s in np.asarray(samples)])
+    predout["sampleID"] = samples[pred]
+    if args.bootstrap or args.jacknife:
+        outfile = args.out + "_boot" + str(boot) + "_predlocs.txt"
+    elif args.windows:
+        window_start = int(args.window_start)
+        window_size = int(args.window_size)
+        outfile = f"{args.out}_{window_start}-{window_start + window_size - 1}_predlocs.txt"
+    else:
+        outfile = args.out + "_predlocs.txt"
+    predout.to_csv(outfile, index=False)
+
+    testlocs2 = np.array([[x[0] * sdlong + meanlong, x[1] * sdlat + meanlat] for x in testlocs])
+    p2 = model.predict(testgen)
+    p2 = np.array([[x[0] * sdlong + meanlong, x[1] * sdlat + meanlat] for x in p2])
+    r2_long = np.corrcoef(p2[:, 0], testlocs2[:, 0])[0][1] ** 2
+    r2_lat = np.corrcoef(p2[:, 1], testlocs2[:, 1])[0][1] ** 2
+    dists = [spatial.distance.euclidean(p2[x, :], testlocs2[x, :]) for x in range(len(p2))]
+    mean_dist = np.mean(dists)
+    median_dist = np.median(dists)
+    if verbose == True:  # noqa: E712
+        print("R2(x)=" + str(r2_long) + "\nR2(y)=" + str(r2_lat) + "\n" + "mean validation error " + str(mean_dist)
+              + "\n" + "median validation error " + str(median_dist) + "\n")
+    hist = pd.DataFrame(history.history)
+    hist.to_csv(args.out + "_history.txt", sep="\t", index=False)
+    return dists
+
+
+def plot_history(history, dists):
+    if args.plot_history:
+        try:
+            import matplotlib
+
+            matplotlib.use("agg")
+            from matplotlib import pyplot as plt
+        except ImportError:
+            return  # matplotlib is not part of this image; the fit plot is cosmetic
+        fig = plt.figure(figsize=(4, 1.5), dpi=200)
+        plt.rcParams.update({"font.size": 7})
+        ax1 = fig.add_axes([0, 0, 0.4, 1])
+        ax1.plot(history.history["val_loss"][3:], "-", color="black", lw=0.5)
+        ax1.set_xlabel("Validation Loss")
+        ax2 = fig.add_axes([0.55, 0, 0.4, 1])
+        ax2.plot(history.history["loss"][3:], "-", color="black", lw=0.5)
+        ax2.set_xlabel("Training Loss")
+        fig.savefig(args.out + "_fitplot.pdf", bbox_inches="tight")
+
+
+# ---------------------------------------------------------------------------------------------
+# drivers
+# ---------------------------------------------------------------------------------------------
+def _run_one(traingen, testgen, trainlocs, testlocs, predgen, norm, pred, samples, boot, cb_boot):
+    meanlong, sdlong, meanlat, sdlat = norm
+    model = load_network(traingen, args.dropout_prop)
+    callbacks = load_callbacks(cb_boot)
+    history, model = train_network(model, traingen, testgen, trainlocs, testlocs, callbacks, boot)
+    dists = predict_locs(model, predgen, sdlong, meanlong, sdlat, meanlat, testlocs, pred, samples, testgen, history,
+                         boot)
+    if args.plot_history:
+        plot_history(history, dists)
+    return model, history, dists
+
+
+def main(argv=None):
+    global args
+    parser = build_parser()
+    set_args(parser.parse_args(argv))
+
+    # set seed and gpu (locator.py:170-173, :491-494)
+    if args.seed is not None:
+        np.random.seed(args.seed)
+        np.random.seed(args.seed)  # the reference seeds at import and again in main(); idempotent
+    if args.gpu_number is not None:
+        os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu_number
+    if args.load_params is not None:
+        gpus = args.gpus
+        with open(args.load_params, "r") as f:
+            args.__dict__ = json.load(f)
+        args.gpus = gpus
+    if args.out is None:
+        raise SystemExit("--out is required")
+    _write_params()
+
+    genotypes, samples = load_genotypes()
+    sample_data, locs = sort_samples(samples, genotypes)
+    meanlong, sdlong, meanlat, sdlat, locs = normalize_locs(locs)
+    ac = filter_snps(genotypes)
+    train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = split_train_test(ac, locs)
+    norm = (meanlong, sdlong, meanlat, sdlat)
+
+    if args.windows:
+        from . import replicates
+
+        if args.zarr is None:
+            raise SystemExit("--windows requires --zarr input")
+        replicates.run_windows(sys.modules[__name__], genotypes, samples)
+    elif not args.bootstrap and not args.jacknife:
+        _run_one(traingen, testgen, trainlocs, testlocs, predgen, norm, pred, samples, 0, None)
+    elif args.bootstrap:
+        from . import replicates
+
+        replicates.run_bootstrap(sys.modules[__name__], traingen, testgen, trainlocs, testlocs, predgen, norm, pred,
+                                 samples)
+    elif args.jacknife:
+        boot = "FULL"
+        start = time.time()
+        model, history, dists = _run_one(traingen, testgen, trainlocs, testlocs, predgen, norm, pred, samples, boot,
+                                         boot)
+        print("run time " + str((time.time() - start) / 60) + " minutes")
+        print("starting jacknife resampling")
+        af = ac.site_sums() / (ac.shape[1] * 2)  # wide integer sums (numpy >= 2 would wrap uint8 in the reference)
+        n_pred = _matrix_shape(predgen)[0]
+        for boot in range(args.nboots):
+            pg = predgen.clone()
+            sites_to_remove = np.random.choice(_matrix_shape(pg)[1], int(_matrix_shape(pg)[1] * args.jacknife_prop),
+                                               replace=False)
+            # per chosen site, in the returned order, binomial(2, af[site], n_pred): same stream as the reference
+            vals = np.stack([np.random.binomial(2, af[i], n_pred) for i in sites_to_remove]).astype(np.uint8) \
+                if len(sites_to_remove) else np.zeros((0, n_pred), np.uint8)
+            if len(sites_to_remove):
+                pg.replace_cols(sites_to_remove, vals)
+            predict_locs(model, pg, sdlong, meanlong, sdlat, meanlat, testlocs, pred, samples, testgen, history, boot,
+                         verbose=False)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,159 @@
+"""GPU end-to-end: the `locator` command on the reference's own example data (BASELINE config 1)
+and its replicate drivers -- flags, output files and seed-reproducible indices."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+VCF = os.path.join(HERE, "golden", "data", "test_genotypes.vcf.gz")
+SAMPLES = os.path.join(HERE, "golden", "data", "test_sample_data.txt")
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from locator_b200 import locator
+
+    return locator
+
+
+def _facts(name):
+    return json.load(open(os.path.join(HERE, "golden", name)))
+
+
+def test_ingest_functions_match_golden(L, tmp_path):
+    """load_genotypes -> sort_samples -> normalize_locs -> filter_snps -> split_train_test on the
+    fixture, against the facts frozen from the reference's data (tests/golden)."""
+    facts, rng = _facts("fixture_facts.json"), _facts("rng_facts.json")
+    L.set_args(L.build_parser().parse_args(["--vcf", VCF, "--sample_data", SAMPLES, "--out", str(tmp_path / "r"),
+                                            "--seed", "12345"]))
+    np.random.seed(12345)
+    genotypes, samples = L.load_genotypes()
+    assert genotypes.shape == (facts["nvar"], facts["nsamples"], 2)
+    sample_data, locs = L.sort_samples(samples, genotypes)
+    assert int(np.isnan(locs[:, 0]).sum()) == facts["n_na"]
+    meanlong, sdlong, meanlat, sdlat, nlocs = L.normalize_locs(locs)
+    np.testing.assert_allclose([meanlong, meanlat], facts["nanmean"], rtol=1e-12)
+    np.testing.assert_allclose([sdlong, sdlat], facts["nanstd"], rtol=1e-12)
+    ac = L.filter_snps(genotypes)
+    assert ac.shape == (facts["n_kept_min_mac_2"], facts["nsamples"])
+    acn = ac.to_numpy()
+    assert hashlib.sha256(np.ascontiguousarray(acn).tobytes()).hexdigest() == facts["ac_sha256"]
+    train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = L.split_train_test(ac, nlocs)
+    assert test.tolist() == rng["test_idx"]
+    assert len(train) == 405 and len(pred) == 50 and pred.tolist() == list(range(50))
+    assert traingen.shape == (405, 5830) and testgen.shape == (45, 5830) and predgen.shape == (50, 5830)
+    assert np.array_equal(traingen.to_numpy(), acn[:, train].T)
+    assert np.array_equal(testgen.to_numpy(), acn[:, test].T)
+    # bootstrap draws that follow in the reference's stream
+    from locator_b200 import replicates
+
+    orders = replicates.draw_bootstrap_orders(ac.shape[0], 2)
+    assert orders[0][:16].tolist() == rng["bootstrap_site_order_prefix"]
+    assert hashlib.sha256(orders[0].astype(np.int64).tobytes()).hexdigest() == rng["bootstrap_site_order_sha256"]
+
+
+def test_impute_and_max_snps_match_oracle(L, tmp_path):
+    from oracle import ingest_ref
+
+    rng = np.random.default_rng(4)
+    nvar, N = 400, 60
+    p = rng.uniform(0.05, 0.95, size=(nvar, 1, 1))
+    gt = (rng.uniform(size=(nvar, N, 2)) < p).astype(np.int8)
+    gt[rng.uniform(size=(nvar, N)) < 0.08] = -1  # whole calls missing (./.), as VCFs have them
+    from locator_b200.io import Genotypes
+
+    L.set_args(L.build_parser().parse_args(["--vcf", "x", "--out", str(tmp_path / "r"), "--impute_missing",
+                                            "--max_SNPs", "150", "--min_mac", "2"]))
+    np.random.seed(99)
+    ac = L.filter_snps(Genotypes(gt))
+    np.random.seed(99)
+    ref = ingest_ref.filter_snps(gt, min_mac=2, impute_missing=True, max_SNPs=150)
+    assert np.array_equal(ac.to_numpy(), ref)
+
+
+def _run(L, argv):
+    rc = L.main(argv)
+    assert rc == 0
+
+
+def test_default_run_on_reference_fixture(L, tmp_path, capsys):
+    """BASELINE config 1: default CLI on data/test_genotypes.vcf.gz (bounded epochs for test time).
+    Accuracy margin: the README's full-length run reports median validation error 3.3 map units on
+    the 50 x 50 landscape; a 150-epoch run must already be well inside 10."""
+    out = str(tmp_path / "fix")
+    _run(L, ["--vcf", VCF, "--sample_data", SAMPLES, "--out", out, "--seed", "12345", "--max_epochs", "150",
+             "--patience", "30", "--keras_verbose", "0"])
+    text = capsys.readouterr().out
+    assert "running on 5830 genotypes after filtering" in text and "median validation error" in text
+    params = json.load(open(out + "_params.json"))
+    assert list(params.keys())[:4] == ["vcf", "zarr", "matrix", "sample_data"] and len(params) == 29
+    assert params["window_size"] == 500000.0 and params["seed"] == 12345 and "gpus" not in params
+    lines = open(out + "_predlocs.txt").read().strip().split("\n")
+    assert lines[0] == "x,y,sampleID" and len(lines) == 51
+    assert lines[1].split(",")[2] == "msp_0" and lines[50].split(",")[2] == "msp_49"
+    xy = np.array([[float(v) for v in ln.split(",")[:2]] for ln in lines[1:]])
+    assert np.all(np.isfinite(xy)) and xy.min() > -20 and xy.max() < 70
+    hist = open(out + "_history.txt").read().strip().split("\n")
+    assert hist[0].split("\t") == ["loss", "val_loss", "learning_rate"]
+    h = np.array([[float(v) for v in ln.split("\t")] for ln in hist[1:]])
+    assert 10 <= len(h) <= 150 and np.all(np.isfinite(h))
+    assert h[-1, 1] < h[0, 1] * 0.5  # validation loss fell
+    med = float(text.split("median validation error ")[1].split()[0])
+    assert med < 10.0, med
+    assert not os.path.exists(out + ".weights.npz")
+
+
+def test_same_seed_same_result(L, tmp_path):
+    outs = []
+    for tag in ("a", "b"):
+        out = str(tmp_path / tag)
+        _run(L, ["--vcf", VCF, "--sample_data", SAMPLES, "--out", out, "--seed", "7", "--max_epochs", "3",
+                 "--keras_verbose", "0", "--max_SNPs", "2000"])
+        outs.append(open(out + "_predlocs.txt").read())
+    assert outs[0] == outs[1]  # split, subsample, init, batch order, dropout and kernels are all deterministic
+
+
+def test_bootstrap_and_jacknife_drivers(L, tmp_path):
+    out = str(tmp_path / "bs")
+    _run(L, ["--vcf", VCF, "--sample_data", SAMPLES, "--out", out, "--seed", "12345", "--max_epochs", "4",
+             "--keras_verbose", "0", "--bootstrap", "--nboots", "2", "--keep_weights"])
+    for b in ("FULL", "0", "1"):
+        lines = open(f"{out}_boot{b}_predlocs.txt").read().strip().split("\n")
+        assert lines[0] == "x,y,sampleID" and len(lines) == 51
+        assert os.path.exists(f"{out}_boot{b}.weights.npz")
+    assert open(out + "_boot0_predlocs.txt").read() != open(out + "_boot1_predlocs.txt").read()
+
+    out = str(tmp_path / "jk")
+    _run(L, ["--vcf", VCF, "--sample_data", SAMPLES, "--out", out, "--seed", "12345", "--max_epochs", "4",
+             "--keras_verbose", "0", "--jacknife", "--nboots", "3"])
+    preds = [open(f"{out}_boot{b}_predlocs.txt").read() for b in ("FULL", "0", "1", "2")]
+    assert all(len(p.strip().split("\n")) == 51 for p in preds)
+    assert len(set(preds)) == 4  # each replicate perturbs 5% of the SNPs of the prediction set
+
+
+def test_windows_driver_on_zarr(L, tmp_path):
+    from locator_b200 import io
+
+    v = io.read_vcf(VCF)
+    z = str(tmp_path / "fix.zarr")
+    io.write_zarr(z, v["calldata/GT"], v["samples"], v["variants/POS"], chunk_variants=4000)
+    back = io.read_zarr(z)
+    assert np.array_equal(back["calldata/GT"], v["calldata/GT"]) and np.array_equal(back["variants/POS"], v["variants/POS"])
+    out = str(tmp_path / "win")
+    _run(L, ["--zarr", z, "--sample_data", SAMPLES, "--out", out, "--seed", "12345", "--max_epochs", "3",
+             "--keras_verbose", "0", "--windows", "--window_size", "1250000"])
+    # the installed reference CLI appends the global window range to the per-window stem
+    for i in (0, 1250000):
+        stem = f"{out}_{i}-{i + 1250000 - 1}"
+        lines = open(f"{stem}_0-1249999_predlocs.txt").read().strip().split("\n")
+        assert lines[0] == "x,y,sampleID" and len(lines) == 51
+        assert os.path.exists(f"{stem}_history.txt")

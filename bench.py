@@ -110,6 +110,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def max_over_ranks(value, device):
+    """MAX over ranks of a per-rank scalar (step time): the job is as slow as its slowest rank."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_value(world, steps, batch, ms):
+    """Whole-job samples/s: every rank trains its own model (weak scaling), time = max over ranks."""
+    return world * steps * batch / (ms / 1000.0)
+
+
 def cpu_steps(x, y, xv, yv, nsteps, threads):
     """Oracle (reference restatement) timed on the host cores: nsteps optimizer steps."""
     import torch
@@ -256,14 +273,10 @@ def main():
         ev1.record()
         torch.cuda.synchronize()
     launches = _cabi.launch_count() - l0
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ev0.elapsed_time(ev1), "cuda")
     st = m.state()
     assert st.nonfinite == 0 and np.isfinite(st.last_loss), "non-finite loss during the timed region"
-    value = world * steps * B / (ms / 1000.0)
+    value = aggregate_value(world, steps, B, ms)
 
     # ---- roofline: first-layer backward + Adam alone, CUDA events on the launching stream ----
     rows_dev = torch.as_tensor(rng.permutation(ntr)[:B].astype(np.int32)).cuda()
@@ -331,10 +344,7 @@ def main():
         h = m2.fit(xtr_p, ytr, epochs=ne, validation_data=(xva_p, yva), patience=10 ** 6, epochs_per_call=ne)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(dt, "cuda")
         nst = ne * spe
         assert len(h.history["loss"]) == ne and np.isfinite(h.history["loss"][-1])
         h2d = xtr.nbytes + xva.nbytes + ytr.nbytes + yva.nbytes + ne * ntr * 4

@@ -727,6 +727,23 @@ int l1_tc_partials(int64_t K) {
   return (int)(ntiles < tc_sm_count() ? ntiles : tc_sm_count());
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point: the library itself does not link
+// libcuda, so it still loads (for the symbol check) on a machine without a driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s) {
   // W1 viewed as [8 j-chunks][K SNPs][32 floats]: one TMA box = the whole [8][32][32] stage tile
   static thread_local const float* cached_w = nullptr;
@@ -739,9 +756,11 @@ int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s) {
     cuuint32_t box[3] = {32, (cuuint32_t)tc::F_KT, 8};
     cuuint32_t estr[3] = {1, 1, 1};
     const char* force2d = getenv("LOC_TMA_2D");
+    EncodeTiledFn encode = encode_tiled_fn();
+    LOC_CHECK(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
     CUresult r = CUDA_ERROR_INVALID_VALUE;
     if (force2d == nullptr)
-      r = cuTensorMapEncodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.W1, dims, strides, box, estr,
+      r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.W1, dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     tma_rank = 3;
@@ -750,16 +769,14 @@ int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s) {
       cuuint64_t dims2[2] = {(cuuint64_t)tc::kH, (cuuint64_t)a.K};
       cuuint64_t strides2[1] = {(cuuint64_t)tc::kH * 4};
       cuuint32_t box2[2] = {32, (cuuint32_t)tc::F_KT};
-      r = cuTensorMapEncodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.W1, dims2, strides2, box2, estr,
+      r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.W1, dims2, strides2, box2, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       tma_rank = 2;
     }
     if (r != CUDA_SUCCESS) {
-      const char* msg = nullptr;
-      cuGetErrorString(r, &msg);
       char buf[256];
-      snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed: %s", msg ? msg : "?");
+      snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
       return fail(buf, __FILE__, __LINE__);
     }
     cached_w = a.W1;

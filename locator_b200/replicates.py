@@ -74,8 +74,26 @@ def _run_item(L, item, base):
         raise ValueError(kind)
 
 
-def _worker(rank, n_gpus, args, base_host, task_q, result_q):
+def _resolve(runner):
+    """'package.module:function' -> callable (test hook: a CPU stand-in for _run_item)."""
+    import importlib
+
+    mod, fn = runner.split(":")
+    return getattr(importlib.import_module(mod), fn)
+
+
+def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None):
     try:
+        if runner is not None:  # host-logic tests: no CUDA, the runner consumes the raw item
+            run = _resolve(runner)
+            while True:
+                item = task_q.get()
+                if item is None:
+                    break
+                run(rank, args, item)
+                result_q.put(("done", rank, item.get("boot", item.get("index"))))
+            result_q.put(("exit", rank, None))
+            return
         import torch
 
         torch.cuda.set_device(rank % max(1, torch.cuda.device_count()))
@@ -104,8 +122,8 @@ def _worker(rank, n_gpus, args, base_host, task_q, result_q):
 class ReplicatePool:
     """One worker process per GPU pulling work items from a shared queue."""
 
-    def __init__(self, n_gpus, args, base=None):
-        import torch.multiprocessing as mp
+    def __init__(self, n_gpus, args, base=None, runner=None):
+        import multiprocessing as mp
 
         ctx = mp.get_context("spawn")
         self.n = n_gpus
@@ -116,7 +134,7 @@ class ReplicatePool:
             base_host = dict(base)
             for k in ("traingen", "testgen", "predgen"):
                 base_host[k] = _to_host(base[k])
-        self.procs = [ctx.Process(target=_worker, args=(r, n_gpus, args, base_host, self.task_q, self.result_q))
+        self.procs = [ctx.Process(target=_worker, args=(r, n_gpus, args, base_host, self.task_q, self.result_q, runner))
                       for r in range(n_gpus)]
         for p in self.procs:
             p.start()

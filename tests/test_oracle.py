@@ -1,0 +1,158 @@
+"""CPU: the oracle against the golden facts frozen from the reference's own fixture, and the
+restated Keras math against torch autograd."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ingest_ref, model_ref, philox_ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _facts(name):
+    return json.load(open(os.path.join(HERE, "golden", name)))
+
+
+def test_ingest_oracle_matches_fixture_facts(fixture_gt):
+    facts = _facts("fixture_facts.json")
+    gt = fixture_gt["calldata/GT"]
+    assert gt.shape == (facts["nvar"], facts["nsamples"], 2)
+    assert fixture_gt["samples"][0] == facts["first_sample"] and fixture_gt["samples"][-1] == facts["last_sample"]
+    assert int(fixture_gt["variants/POS"][0]) == facts["pos_first"]
+    assert int(fixture_gt["variants/POS"][-1]) == facts["pos_last"]
+    cnt = ingest_ref.count_alleles(gt)
+    allelism = (cnt > 0).sum(1)
+    assert {str(k): int((allelism == k).sum()) for k in (1, 2, 3)} == facts["allelism_hist"]
+    assert int(ingest_ref.is_biallelic(cnt).sum()) == facts["n_biallelic"]
+    ac, idx = ingest_ref.filter_snps(gt, min_mac=2, return_index=True)
+    assert ac.shape == (facts["n_kept_min_mac_2"], facts["nsamples"]) and ac.dtype == np.uint8
+    assert hashlib.sha256(idx.astype(np.int64).tobytes()).hexdigest() == facts["kept_index_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(ac).tobytes()).hexdigest() == facts["ac_sha256"]
+    assert {str(v): int((ac == v).sum()) for v in (0, 1, 2)} == facts["kept_value_hist"]
+
+
+def test_sample_data_and_rng_oracle_match_golden(fixture_gt, golden_dir):
+    facts, rng = _facts("fixture_facts.json"), _facts("rng_facts.json")
+    ids, x, y = ingest_ref.read_sample_data(os.path.join(golden_dir, "data", "test_sample_data.txt"))
+    locs = ingest_ref.sort_samples(ids, x, y, fixture_gt["samples"])
+    assert int(np.isnan(locs[:, 0]).sum()) == facts["n_na"]
+    ml, sl, mt, st, nl = ingest_ref.normalize_locs(locs)
+    np.testing.assert_allclose([ml, mt], facts["nanmean"], rtol=1e-12)
+    np.testing.assert_allclose([sl, st], facts["nanstd"], rtol=1e-12)
+    ac = ingest_ref.filter_snps(fixture_gt["calldata/GT"], min_mac=2)
+    np.random.seed(rng["seed"])
+    train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = ingest_ref.split_train_test(ac, nl, 0.9)
+    assert test.tolist() == rng["test_idx"] and len(train) == 405 and pred.tolist() == list(range(50))
+    assert traingen.shape == (405, 5830) and testgen.shape == (45, 5830) and predgen.shape == (50, 5830)
+    order = ingest_ref.bootstrap_site_order(ac.shape[0])
+    assert order[:16].tolist() == rng["bootstrap_site_order_prefix"]
+    assert hashlib.sha256(order.astype(np.int64).tobytes()).hexdigest() == rng["bootstrap_site_order_sha256"]
+    # jacknife draws right after the split
+    np.random.seed(rng["seed"])
+    ingest_ref.split_train_test(ac, nl, 0.9)
+    af = ingest_ref.jacknife_af(ac)
+    pg, sites = ingest_ref.jacknife_replace(predgen, af, 0.05)
+    assert sites[:16].tolist() == rng["jacknife_sites_prefix"] and len(sites) == rng["jacknife_nsites"]
+    assert pg[:, sites[0]].tolist() == rng["jacknife_first_col"]
+
+
+def test_round_is_bankers_rounding_of_float_product():
+    # (1 - 0.9) * 450 = 44.99999999999999 -> 45
+    assert round((1 - 0.9) * 450) == 45 and round((1 - 0.9) * 900) == 90 and round((1 - 0.9) * 2250) == 225
+
+
+def test_missing_and_multiallelic_semantics():
+    gt = np.array([
+        [[0, 1], [1, 1], [-1, -1], [0, 0]],   # biallelic, alt count 3, one missing call
+        [[0, 0], [0, 0], [0, 0], [0, 0]],     # monomorphic
+        [[1, 2], [2, 1], [1, 1], [2, 2]],     # alleles {1, 2}: passes is_biallelic
+        [[0, 1], [2, 0], [1, 1], [0, 0]],     # three alleles
+        [[0, -1], [1, 1], [0, 0], [0, 1]],    # half-missing call counts as missing for is_missing
+    ], dtype=np.int8)
+    cnt = ingest_ref.count_alleles(gt)
+    assert cnt[0].tolist() == [3, 3, 0] and cnt[2].tolist() == [0, 4, 4]
+    assert ingest_ref.is_biallelic(cnt).tolist() == [True, False, True, False, True]
+    assert ingest_ref.is_missing(gt)[4].tolist() == [True, False, False, False]
+    ac, idx = ingest_ref.filter_snps(gt, min_mac=2, return_index=True)
+    assert idx.tolist() == [0, 2, 4]
+    assert ac.tolist() == [[1, 2, 0, 0], [1, 1, 2, 0], [0, 2, 0, 1]]
+    assert ingest_ref.filter_snps(gt, min_mac=4).shape[0] == 1  # only the {1,2} site has 4 copies of allele 1
+    assert ingest_ref.filter_snps(gt, min_mac=1).shape[0] == 3  # min_mac == 1 skips the count filter
+
+
+def test_philox_known_answer():
+    # Philox4x32-10 known-answer test of Random123 (counter = key = 0 and the all-ones vector)
+    r = philox_ref.philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(v[0]) for v in r] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    r = philox_ref.philox4x32_10([0xFFFFFFFF], [0xFFFFFFFF], [0xFFFFFFFF], [0xFFFFFFFF], 0xFFFFFFFF, 0xFFFFFFFF)
+    assert [int(v[0]) for v in r] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    u = philox_ref.uniform01(1000, 5, 3)
+    assert u.dtype == np.float32 and u.min() >= 0 and u.max() < 1 and abs(u.mean() - 0.5) < 0.05
+
+
+@pytest.mark.parametrize("K,H,L,p,B", [(50, 16, 4, 0.25, 8), (31, 8, 3, 0.0, 5), (20, 8, 2, 0.5, 32)])
+def test_oracle_gradients_match_autograd(K, H, L, p, B):
+    rng = np.random.default_rng(K)
+    x = rng.integers(0, 3, size=(B, K)).astype(np.uint8)
+    x[:, 0] = 1  # a column that is constant within the batch
+    y = rng.normal(size=(B, 2)).astype(np.float32)
+    ref = model_ref.RefLocator(K, H, L, dropout=p, seed=3)
+    ws = ref.get_weights()
+    ws[0] = rng.uniform(0.5, 1.5, K).astype(np.float32)
+    ws[1] = rng.normal(0, 0.1, K).astype(np.float32)
+    ref.set_weights(ws)
+    mask = rng.uniform(size=(B, H)) >= p
+    loss, grads, _ = ref.gradients(x, y, mask)
+    # same network with autograd
+    t = [torch.tensor(w, requires_grad=True) for w in ws]
+    gamma, beta = t[0], t[1]
+    xt = torch.tensor(x, dtype=torch.float32)
+    mean = xt.mean(0)
+    var = ((xt - mean) ** 2).mean(0)
+    a = (xt - mean) * torch.rsqrt(var + 1e-3) * gamma + beta
+    nb4 = int(np.floor(L / 2))
+    for i in range(L):
+        a = torch.nn.functional.elu(a @ t[4 + 2 * i] + t[5 + 2 * i])
+        if i == nb4 - 1 and p > 0:
+            a = a * torch.tensor(mask, dtype=torch.float32) / (1 - p)
+    y1 = a @ t[4 + 2 * L] + t[5 + 2 * L]
+    y2 = y1 @ t[6 + 2 * L] + t[7 + 2 * L]
+    l = torch.sqrt(((y2 - torch.tensor(y)) ** 2).sum(-1)).mean()
+    l.backward()
+    assert abs(float(l) - loss) < 1e-5 * max(1.0, abs(loss))
+    auto = [t[0].grad, t[1].grad] + [t[i].grad for i in range(4, len(t))]
+    for g, ga in zip(grads, auto):
+        np.testing.assert_allclose(g.numpy(), ga.numpy(), rtol=2e-4, atol=2e-6)
+    assert float(grads[0][0]) == 0.0  # d gamma of the constant column is exactly zero
+
+
+def test_oracle_adam_and_callbacks_semantics():
+    # Keras Adam, one step from zero state: update = -lr * sign(g) * |g| / (|g| + eps*...) ~ -lr * sign(g)
+    ref = model_ref.RefLocator(10, 8, 2, dropout=0.0, seed=1)
+    w0 = [w.copy() for w in ref.get_weights()]
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 3, size=(32, 10)).astype(np.uint8)
+    y = rng.normal(size=(32, 2)).astype(np.float32)
+    ref.train_step(x, y, np.ones((32, 8), bool))
+    w1 = ref.get_weights()
+    d = np.abs(w1[4] - w0[4])
+    assert d.max() <= 1.0001e-3 and d[d > 0].min() > 0.5e-3
+    # moving statistics: 0.99 * old + 0.01 * batch
+    np.testing.assert_allclose(w1[2], 0.01 * x.astype(np.float32).mean(0), rtol=1e-5)
+    # callbacks: checkpoint on strict improvement, LR halves after patience//6 stale epochs, stop at patience
+    cb = model_ref.CallbackState(patience=12, lr=1e-3)
+    vals = [1.0, 0.9, 0.95, 0.95, 0.93, 0.92, 0.91, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9]
+    saves, lrs = [], []
+    for e, v in enumerate(vals):
+        s, lr = cb.on_epoch_end(e, v)
+        saves.append(s)
+        lrs.append(lr)
+        if cb.stop:
+            break
+    assert saves[:3] == [True, True, False] and sum(saves) == 2
+    assert lrs[3] == pytest.approx(1e-3) and lrs[4] == pytest.approx(5e-4) and lrs[6] == pytest.approx(2.5e-4)
+    assert cb.stop and e == 13  # 12 epochs without improvement after epoch 1

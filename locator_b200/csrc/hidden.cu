@@ -20,6 +20,7 @@
 // global memory for k_hidden_update, which runs off the critical path.
 #include "model.cuh"
 #include "philox.cuh"
+#include "hidden_slices.cuh"
 
 namespace loc {
 
@@ -502,18 +503,6 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Pre-sliced copies of the hidden kernels for k_hidden (C = cluster size, Hc = H / C), with pairs
-// of the reduction index interleaved for FFMA2:
-//   fs[i-1][r][k/2][jl][k&1] = W_i[k][r*Hc + jl]      (forward slice of CTA r)
-//   bs[i-1][r][j/2][il][j&1] = W_i[r*Hc + il][j]      (backward slice of CTA r, transposed)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_sliced(float* fs, float* bs, int H, int Hc, int layer, int k, int j, float w) {
-  const int64_t base = (int64_t)(layer - 1) * H * H;
-  fs[base + (int64_t)(j / Hc) * H * Hc + (int64_t)(k / 2) * (2 * Hc) + 2 * (j % Hc) + (k & 1)] = w;
-  bs[base + (int64_t)(k / Hc) * H * Hc + (int64_t)(j / 2) * (2 * Hc) + 2 * (k % Hc) + (j & 1)] = w;
-}
-
 __global__ void k_reslice(const float* __restrict__ small, float* fs, float* bs, int H, int L, int Hc) {
   const SmallLayout sl{H, L};
   const int64_t n = (int64_t)(L - 1) * H * H;
@@ -568,7 +557,10 @@ __global__ void __maxnreg__(56) k_hidden_update(UpdArgs a) {
       for (int b = 0; b < kMaxB; ++b) g = fmaf(as[kk][b], dz[b], g);
       const int k = rb * kUpdRows + kk;
       const float w = adam_at(sl.Wh(i) + (int64_t)k * H + j, g);
-      store_sliced(a.w_fs, a.w_bs, H, a.Hc, i, k, j, w);
+      if (a.slice_mode == 1)
+        store_images(a.w_fs, a.w_bs, i, k, j, w);
+      else
+        store_sliced(a.w_fs, a.w_bs, H, a.Hc, i, k, j, w);
     }
     if (rb == 0) adam_at(sl.bh(i) + j, bsum);
   } else {

@@ -1,0 +1,486 @@
+// The 256-wide stack on the 5th-generation tensor cores: one 16-CTA cluster per step, split
+// 4 batch groups x 4 column groups.
+//
+// Reference: load_network locator/locator.py:311-327, model.fit :367-376 (same math as hidden.cu,
+// which remains the exact-fp32 CUDA-core variant and the path for other widths).
+//
+// CTA (rb, cj) owns batch rows [8 rb, 8 rb + 8) and columns [64 cj, 64 cj + 64) of every layer:
+//   forward   D[j, b] = sum_k W_i[k, 64cj + j] * a[b, k]      M = 64, N = 8, K = 256 (32 MMAs)
+//   backward  D[i, b] = sum_j W_i[64cj + i, j] * dz[b, j]     M = 64, N = 8, K = 256
+// Batch rows never mix, so the all-gather after a layer only runs inside a batch group: a CTA
+// sends its [8 x 64] slice (2 KB, already in the K-major swizzled B-operand image) to the 4 CTAs
+// of its group with shared::cta -> shared::cluster bulk copies completing on their mbarriers --
+// 6x less DSMEM traffic than a column-only split.  Weight slices are kept in HBM as ready-made
+// operand images (forward: MN-major 128B/32B-atom swizzle; backward: K-major 128B swizzle) and
+// stream into a 2-slot ring with cp.async.bulk one layer ahead.  Operands are TF32 (activations
+// rounded to nearest, weights as stored), accumulation fp32 in TMEM -- the numerics TensorFlow
+// uses for these matmuls on Ampere+ GPUs; elu / dropout / loss / elu' run in fp32 on exact values.
+#include "model.cuh"
+#include "philox.cuh"
+#include "hidden_slices.cuh"
+
+namespace loc {
+namespace htc {
+
+constexpr int kH = 256, kC = 16, kRB = 8, kCW = 64;
+constexpr int kThreads = 256;
+constexpr int kSlot = kH * kCW * 4;    // 64 KB weight-slice image
+constexpr int kGath = kRB * kH * 4;    // 8 KB gathered B operand: [8 k-atoms][8 rows][128 B]
+constexpr int kStage = kRB * kCW * 4;  // 2 KB own slice: 2 k-atoms
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// byte offset of element (row b, k) inside a K-major 128B-swizzled operand of 8 rows
+__device__ __forceinline__ uint32_t b_off(int b, int k) {
+  return (uint32_t)((k >> 5) * 1024 + b * 128 + ((((k & 31) >> 2) ^ b) << 4) + ((k & 3) << 2));
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_hidden_tc(HidArgs a) {
+  if (a.gated && a.st->stopped) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ int64_t s_rows[kRB];
+  __shared__ __align__(8) uint64_t wbar[2], ready[2], mma_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = a.L;
+  const int r = (int)cluster_rank(), rb = r >> 2, cj = r & 3;
+  const int j0 = cj * kCW, b0 = rb * kRB;
+  const int nb = a.src.nb;
+  const SmallLayout sl{kH, L};
+  int dbg_n = 0;
+  auto mark = [&]() {
+    if (a.dbg != nullptr && tid == 0 && dbg_n < 256) a.dbg[r * 256 + dbg_n++] = clock64();
+  };
+  mark();
+
+  uint8_t* wslot = sm;                                   // [2][64 KB]
+  uint8_t* gath = wslot + 2 * kSlot;                     // [2][8 KB]
+  uint8_t* stage = gath + 2 * kGath;                     // [2][2 KB]
+  float* zbuf = (float*)(stage + 2 * kStage);            // [8][64] accumulator dump
+  float* red = zbuf + kRB * kCW;                         // [2][8][64] split-K partial groups
+  float* own_a = red + 2 * kRB * kCW;                    // [L][8][64] elu outputs (pre-dropout, fp32)
+  float* own_dz = own_a + L * kRB * kCW;                 // [L][8][64]
+  float* keep = own_dz + L * kRB * kCW;                  // [8][64]
+  float* sbias = keep + kRB * kCW;                       // [L][64]
+  float* sout = sbias + L * kCW;                         // Wo1[256][2], bo1[2], Wo2[4], bo2[2]
+  float* ysm = sout + 520;                               // y1[8][2], y2[8][2], dy1[8][2], dy2[8][2], dist[8]
+  float* y1s = ysm, *y2s = ysm + 16, *dy1s = ysm + 32, *dy2s = ysm + 48, *dist = ysm + 64;
+
+  const int n_uses = a.training ? 2 * (L - 1) : (L - 1);
+  auto issue_load = [&](int u) {  // thread 0: weight-slice image of use u -> slot u & 1
+    const int layer = u < L - 1 ? u + 1 : 2 * (L - 1) - u;
+    const float* src = (u < L - 1 ? a.w_fs : a.w_bs) + (int64_t)(layer - 1) * kH * kH + (int64_t)cj * kH * kCW;
+    mbar_expect_tx(&wbar[u & 1], kSlot);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(wslot + (u & 1) * kSlot)),
+                 "l"(src), "r"((uint32_t)kSlot), "r"(smem_u32(&wbar[u & 1]))
+                 : "memory");
+  };
+  if (tid == 0) {
+    mbar_init(&wbar[0], 1);
+    mbar_init(&wbar[1], 1);
+    mbar_init(&ready[0], 1);
+    mbar_init(&ready[1], 1);
+    mbar_init(&mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int u = 0; u < 2 && u < n_uses; ++u) issue_load(u);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(32u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < L * kCW; i += kThreads) {
+    const int layer = i / kCW, jl = i % kCW;
+    sbias[i] = a.small[(layer == 0 ? sl.b1() : sl.bh(layer)) + j0 + jl];
+  }
+  for (int i = tid; i < 2 * kH + 8; i += kThreads) sout[i] = a.small[sl.Wo1() + i];
+  if (tid < kRB) s_rows[tid] = (b0 + tid) < nb ? row_of(a.src, a.st, b0 + tid) : 0;
+  const int step_id = a.st->step_id;
+  const float keep_scale = 1.0f / (1.0f - a.p_drop);
+  const bool drop_on = a.training && a.p_drop > 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  cluster_barrier();  // every CTA of the cluster is running before anyone writes into its shared memory
+
+  int pub = 0;   // publishes so far: publish n uses stage / gathered buffer n & 1
+  int nmma = 0;  // MMA batches so far (parity of mma_bar)
+  // All-gather inside the batch group: the staged [8 x 64] slice goes to the 4 CTAs (rb, 0..3).
+  auto publish_staged = [&]() {
+    mark();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    mark();
+    if (lane == 0 && warp < 4) {
+      const uint32_t src = smem_u32(stage + (pub & 1) * kStage);
+      const uint32_t dst_local = smem_u32(gath + (pub & 1) * kGath + cj * kStage);
+      const uint32_t bar_local = smem_u32(&ready[pub & 1]);
+      const unsigned dest = (unsigned)(rb * 4 + warp);
+      uint32_t dst, bar;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(dst_local), "r"(dest));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(bar_local), "r"(dest));
+      asm volatile(
+          "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+          "r"(src), "r"((uint32_t)kStage), "r"(bar)
+          : "memory");
+    }
+    ++pub;
+  };
+  auto wait_gather = [&](int n) -> const uint8_t* {
+    if (tid == 0) mbar_expect_tx(&ready[n & 1], 4 * kStage);
+    mbar_wait(&ready[n & 1], (uint32_t)(n >> 1) & 1u);
+    return gath + (n & 1) * kGath;
+  };
+  // One layer product on the tensor core: D[64 x 8] (TMEM) = A (weight-slice image) x B (gathered).
+  // Leaves z[b][jl] (fp32) in zbuf.
+  auto layer_mma = [&](int u, bool backward) {
+    const uint8_t* B = wait_gather(pub - 1);
+    mark();
+    mbar_wait(&wbar[u & 1], (uint32_t)(u >> 1) & 1u);
+    mark();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t wb = smem_u32(wslot + (u & 1) * kSlot), bb = smem_u32(B);
+#pragma unroll 4
+      for (int ks = 0; ks < kH / 8; ++ks) {
+        const uint64_t bdesc = smem_desc(bb + (ks >> 2) * 1024 + (ks & 3) * 32, 16, 1024, 2);
+        uint64_t adesc;
+        uint32_t idesc;
+        if (!backward) {  // MN-major [2 j-chunks][256 k rows][128 B], 32B-atom swizzle
+          adesc = smem_desc(wb + ks * 1024, kH * 128, 512, 1);
+          idesc = make_idesc(64, 8, 1, 0);
+        } else {          // K-major [8 k-chunks][8 row groups][8 rows][128 B], 128B swizzle
+          adesc = smem_desc(wb + (ks >> 2) * 8192 + (ks & 3) * 32, 16, 1024, 2);
+          idesc = make_idesc(64, 8, 0, 0);
+        }
+        umma_tf32(tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar))
+                   : "memory");
+    }
+    mbar_wait(&mma_bar, (uint32_t)nmma & 1u);
+    mark();
+    ++nmma;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0 && u + 2 < n_uses) issue_load(u + 2);  // the slot is free: prefetch two uses ahead
+    if (warp < 4) {  // accumulator row m lives in TMEM lane 32*(m/16) + m%16
+      uint32_t v[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(tmem + ((uint32_t)(32 * warp) << 16))
+                   : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (lane < 16) {
+        const int jl = 16 * warp + lane;
+#pragma unroll
+        for (int b = 0; b < kRB; ++b) zbuf[b * kCW + jl] = __uint_as_float(v[b]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    mark();
+  };
+  auto stage_store = [&](int b, int jl, float v) {
+    *reinterpret_cast<float*>(stage + (pub & 1) * kStage + b_off(b, jl)) = to_tf32(v);
+  };
+  auto finish_fwd_elem = [&](int i, int b, int jl, float z) {
+    float act = elu_f(z + sbias[i * kCW + jl]);
+    own_a[(i * kRB + b) * kCW + jl] = act;
+    if (i == a.n_before - 1) {
+      float mult = 1.f;
+      if (drop_on) {
+        bool kp;
+        if (a.masks != nullptr) {
+          const int64_t s = step_id < a.n_masks ? step_id : a.n_masks - 1;
+          kp = a.masks[(s * kMaxB + b0 + b) * kH + j0 + jl] != 0;
+        } else {
+          kp = philox_uniform((uint64_t)(b0 + b) * kH + j0 + jl, kDropoutStreamBase + (uint32_t)step_id, a.seed) >=
+               a.p_drop;
+        }
+        mult = kp ? keep_scale : 0.f;
+        act *= mult;
+      }
+      keep[b * kCW + jl] = mult;
+    }
+    stage_store(b, jl, (b0 + b) < nb ? act : 0.f);
+  };
+  auto finish_bwd_elem = [&](int i, int b, int jl, float da) {
+    if (i == a.n_before - 1) da *= keep[b * kCW + jl];
+    const float dz = (b0 + b) < nb ? da * elu_grad_from_out(own_a[(i * kRB + b) * kCW + jl]) : 0.f;
+    own_dz[(i * kRB + b) * kCW + jl] = dz;
+    stage_store(b, jl, dz);
+  };
+
+  // ---- layer 0: reduce the split-K partial tiles of Z1 for the own [8 x 64] block (fixed order) ----
+  {
+    const int item = tid & 127, g = tid >> 7;  // 128 float4 outputs x 2 partial groups
+    const int b = item >> 4, jl = (item & 15) * 4;
+    const int pbeg = a.n_partials * g / 2, pend = a.n_partials * (g + 1) / 2;
+    const float4* src = reinterpret_cast<const float4*>(a.partials + (int64_t)(b0 + b) * kH + j0 + jl);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int p = pbeg; p < pend; ++p) {
+      const float4 v = __ldcg(src + (int64_t)p * kMaxB * (kH / 4));
+      s.x += v.x;
+      s.y += v.y;
+      s.z += v.z;
+      s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(red + (g * kRB + b) * kCW + jl) = s;
+    __syncthreads();
+    for (int idx = tid; idx < kRB * kCW; idx += kThreads) {
+      const int bb = idx / kCW, jj = idx % kCW;
+      finish_fwd_elem(0, bb, jj, red[bb * kCW + jj] + red[(kRB + bb) * kCW + jj]);
+    }
+    publish_staged();
+    mark();
+  }
+
+  // ---- layers 1..L-1 forward ----
+  int use = 0;
+  for (int i = 1; i < L; ++i, ++use) {
+    layer_mma(use, false);
+    for (int idx = tid; idx < kRB * kCW; idx += kThreads) finish_fwd_elem(i, idx / kCW, idx % kCW, zbuf[idx]);
+    publish_staged();
+  }
+
+  // ---- Dense(2), Dense(2), loss for the own 8 rows (the 4 CTAs of a batch group agree) ----
+  const uint8_t* gat = wait_gather(pub - 1);  // a_{L-1} of the own rows (tf32-rounded)
+  {
+    const int b = warp;  // 8 warps = 8 rows
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = lane; k < kH; k += 32) {
+      const float av = *reinterpret_cast<const float*>(gat + b_off(b, k));
+      s0 = fmaf(av, sout[2 * k], s0);
+      s1 = fmaf(av, sout[2 * k + 1], s1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) {
+      y1s[2 * b] = s0;
+      y1s[2 * b + 1] = s1;
+    }
+  }
+  __syncthreads();
+  if (tid < kRB) {
+    const int b = tid, gb = b0 + b;
+    const float* bo1 = sout + 2 * kH;
+    const float* Wo2 = bo1 + 2;
+    const float* bo2 = Wo2 + 4;
+    const float u0 = y1s[2 * b] + bo1[0], u1 = y1s[2 * b + 1] + bo1[1];
+    const float v0 = u0 * Wo2[0] + u1 * Wo2[2] + bo2[0];
+    const float v1 = u0 * Wo2[1] + u1 * Wo2[3] + bo2[1];
+    float d = 0.f, g0 = 0.f, g1 = 0.f;
+    if (gb < nb && (a.training || a.has_targets)) {
+      const float t0 = a.locs[2 * s_rows[b]], t1 = a.locs[2 * s_rows[b] + 1];
+      const float e0 = v0 - t0, e1 = v1 - t1;
+      d = sqrtf(e0 * e0 + e1 * e1);
+      const float den = d * (float)nb;  // no epsilon: NaN when the prediction hits the target, as in the reference
+      g0 = e0 / den;
+      g1 = e1 / den;
+    }
+    const float h0 = g0 * Wo2[0] + g1 * Wo2[1], h1 = g0 * Wo2[2] + g1 * Wo2[3];
+    dy1s[2 * b] = h0;
+    dy1s[2 * b + 1] = h1;
+    if (cj == 0) {  // one CTA per batch group publishes the rows' results
+      if (a.write_pred && gb < nb) {
+        a.pred_out[2 * s_rows[b]] = v0;
+        a.pred_out[2 * s_rows[b] + 1] = v1;
+      }
+      a.outs[2 * gb] = u0;
+      a.outs[2 * gb + 1] = u1;
+      a.outs[64 + 2 * gb] = h0;
+      a.outs[64 + 2 * gb + 1] = h1;
+      a.outs[128 + 2 * gb] = g0;
+      a.outs[128 + 2 * gb + 1] = g1;
+      a.outs[192 + gb] = d;  // per-row distance, summed by rank 0 after the closing cluster barrier
+    }
+  }
+  __syncthreads();
+
+  if (a.training) {
+    // ---- backward: d loss / d a_{L-1} through Dense(2), then the chain of W^T products ----
+    for (int idx = tid; idx < kRB * kCW; idx += kThreads) {
+      const int b = idx / kCW, jl = idx % kCW, i = j0 + jl;
+      finish_bwd_elem(L - 1, b, jl, dy1s[2 * b] * sout[2 * i] + dy1s[2 * b + 1] * sout[2 * i + 1]);
+    }
+    publish_staged();
+    for (int i = L - 1; i >= 1; --i, ++use) {
+      layer_mma(use, true);
+      for (int idx = tid; idx < kRB * kCW; idx += kThreads) finish_bwd_elem(i - 1, idx / kCW, idx % kCW, zbuf[idx]);
+      if (i > 1)
+        publish_staged();
+      else
+        __syncthreads();
+    }
+    // ---- leave activations and dz of every layer in global memory for the update kernels ----
+    for (int idx = tid; idx < L * kRB * kCW / 4; idx += kThreads) {
+      const int i = idx / (kRB * kCW / 4), rem = idx % (kRB * kCW / 4);
+      const int b = rem / (kCW / 4), jl = (rem % (kCW / 4)) * 4;
+      float4 act = *reinterpret_cast<const float4*>(own_a + (i * kRB + b) * kCW + jl);
+      if (i == a.n_before - 1) {
+        const float4 km = *reinterpret_cast<const float4*>(keep + b * kCW + jl);
+        act.x *= km.x;
+        act.y *= km.y;
+        act.z *= km.z;
+        act.w *= km.w;
+      }
+      if (b0 + b >= nb) act = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(a.acts + ((int64_t)i * kMaxB + b0 + b) * kH + j0 + jl) = act;
+      *reinterpret_cast<float4*>(a.dzs + ((int64_t)i * kMaxB + b0 + b) * kH + j0 + jl) =
+          *reinterpret_cast<const float4*>(own_dz + (i * kRB + b) * kCW + jl);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_barrier();  // nobody exits while peers may still address its shared memory; global writes visible
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
+  if (r == 0 && tid == 0) {
+    DevState* st = a.st;
+    if (a.training || a.has_targets) {
+      float s = 0.f;
+      for (int b = 0; b < nb; ++b) s += __ldcg(a.outs + 192 + b);
+      const float mean = s / (float)nb;
+      if (a.training) {
+        st->loss_total += mean * (float)nb;
+        st->loss_count += (float)nb;
+        st->last_loss = mean;
+        if (!isfinite(mean)) st->nonfinite = 1;
+      } else {
+        st->val_total += mean * (float)nb;
+        st->val_count += (float)nb;
+      }
+    }
+    if (a.training) {  // optimizer bookkeeping for the update kernels of this step (Keras Adam: alpha from t >= 1)
+      const int t = st->t + 1;
+      st->t = t;
+      st->step_id = step_id + 1;
+      const float b1p = powf(kAdamB1, (float)t), b2p = powf(kAdamB2, (float)t);
+      st->alpha = st->lr * sqrtf(1.f - b2p) / (1.f - b1p);
+    }
+  }
+}
+
+__global__ void k_reslice_tc(const float* __restrict__ small, float* fs, float* bs, int L) {
+  const SmallLayout sl{kH, L};
+  const int64_t n = (int64_t)(L - 1) * kH * kH;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int layer = 1 + (int)(i / (kH * kH));
+    const int k = (int)((i / kH) % kH), j = (int)(i % kH);
+    store_images(fs, bs, layer, k, j, small[sl.Wh(layer) + (int64_t)k * kH + j]);
+  }
+}
+
+static size_t smem_bytes(int L) {
+  return (size_t)2 * kSlot + 2 * kGath + 2 * kStage +
+         sizeof(float) * ((size_t)kRB * kCW * (1 + 2 + 2 * L + 1) + (size_t)L * kCW + 520 + 80) + 1024;
+}
+
+}  // namespace htc
+
+static int launch_tc(const HidArgs& a, cudaStream_t s, bool dry) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(htc::kC);
+  cfg.blockDim = dim3(htc::kThreads);
+  cfg.dynamicSmemBytes = htc::smem_bytes(a.L);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = htc::kC;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (dry) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, htc::k_hidden_tc, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    return n;
+  }
+  LOC_CUDA(cudaLaunchKernelEx(&cfg, htc::k_hidden_tc, a));
+  loc::g_launches.fetch_add(1);
+  return 0;
+}
+
+bool hidden_tc_supported(int H, int L) {
+  if (H != htc::kH || L < 2) return false;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return false;
+  const size_t smem = htc::smem_bytes(L);
+  if (smem > 227 * 1024) return false;
+  cudaFuncSetAttribute(htc::k_hidden_tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (cudaFuncSetAttribute(htc::k_hidden_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  HidArgs dummy = {};
+  dummy.L = L;
+  return launch_tc(dummy, 0, true) > 0;
+}
+
+int hidden_tc_launch(const HidArgs& a, cudaStream_t s) {
+  LOC_CHECK(a.H == htc::kH, "hidden stack (tcgen05): width must be 256");
+  LOC_CUDA(cudaFuncSetAttribute(htc::k_hidden_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)htc::smem_bytes(a.L)));
+  return launch_tc(a, s, false);
+}
+
+int hidden_tc_reslice(const float* small, float* fs, float* bs, int L, cudaStream_t s) {
+  if (L < 2) return 0;
+  htc::k_reslice_tc<<<148 * 4, 256, 0, s>>>(small, fs, bs, L);
+  LOC_LAUNCHED();
+  return 0;
+}
+
+}  // namespace loc

@@ -160,6 +160,11 @@ static int copy_weights(loc_model* m, bool to_best, const int* cond, cudaStream_
   return 0;
 }
 
+static int reslice(loc_model* m, cudaStream_t s) {
+  return m->hid_tc ? hidden_tc_reslice(m->small, m->w_fs, m->w_bs, m->L, s)
+                   : hidden_reslice(m->small, m->w_fs, m->w_bs, m->H, m->L, m->cluster, s);
+}
+
 static L1Args l1_args(loc_model* m, const uint32_t* packed, int64_t row_words, const RowSrc& src, int training,
                       int gated) {
   L1Args a;
@@ -226,7 +231,7 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
   L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, gated);
   if ((stage_mask & 1) && forward_l1(m, a, s)) return 1;
   HidArgs h = hid_args(m, src, 1, gated, m->train_locs, nullptr);
-  if ((stage_mask & 2) && hidden_launch(h, m->cluster, s)) return 1;
+  if ((stage_mask & 2) && (m->hid_tc ? hidden_tc_launch(h, s) : hidden_launch(h, m->cluster, s))) return 1;
   // The small-layer update only needs the hidden kernel's outputs: it runs on a side stream next to
   // the first-layer backward (full steps only; single-stage debug launches stay on `s`).
   const bool fork = stage_mask == 15;
@@ -251,6 +256,7 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
   u.w_fs = m->w_fs;
   u.w_bs = m->w_bs;
   u.Hc = m->H / m->cluster;
+  u.slice_mode = m->hid_tc;
   u.acts = m->acts;
   u.dzs = m->dzs;
   u.outs = m->outs;
@@ -278,7 +284,7 @@ static int infer_rows(loc_model* m, const uint32_t* packed, int64_t n, int64_t r
     L1Args a = l1_args(m, packed, row_words, src, 0, gated);
     if (forward_l1(m, a, s)) return 1;
     HidArgs h = hid_args(m, src, 0, gated, locs, pred_out);
-    if (hidden_launch(h, m->cluster, s)) return 1;
+    if (m->hid_tc ? hidden_tc_launch(h, s) : hidden_launch(h, m->cluster, s)) return 1;
   }
   return 0;
 }
@@ -323,6 +329,10 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
     return loc::fail("loc_model_create: no usable thread-block cluster size for this width / nlayers", __FILE__, __LINE__);
   }
   m->n_slots = hidden_slots(width, nlayers, m->cluster);
+  {
+    const char* himpl = getenv("LOC_HIDDEN_IMPL");
+    m->hid_tc = (himpl == nullptr || strcmp(himpl, "simt") != 0) && hidden_tc_supported(width, nlayers);
+  }
   const char* impl = getenv("LOC_L1_IMPL");
   m->use_tc = (impl == nullptr || strcmp(impl, "simt") != 0) && l1_tc_supported(K, width);
   const int sms = sm_count();
@@ -413,7 +423,7 @@ int loc_model_init(loc_model* m, uint64_t seed, void* stream) {
     if (glorot(m->small + m->sl.Wh(i), H, H, i)) return 1;
   if (glorot(m->small + m->sl.Wo1(), H, 2, (int)L)) return 1;
   if (glorot(m->small + m->sl.Wo2(), 2, 2, (int)L + 1)) return 1;
-  if (hidden_reslice(m->small, m->w_fs, m->w_bs, m->H, m->L, m->cluster, s)) return 1;
+  if (reslice(m, s)) return 1;
   k_state_reset<<<1, 1, 0, s>>>(m->st, 1e-3f, 100, m->max_epochs, 1);
   LOC_LAUNCHED();
   return 0;
@@ -470,7 +480,7 @@ int loc_model_set_weight(loc_model* m, int32_t idx, const float* h_src, int64_t 
   LOC_CHECK(m != nullptr && weight_ref(m, idx, &r), "loc_model_set_weight: bad weight index");
   LOC_CHECK(n == r.n, "loc_model_set_weight: size mismatch");
   LOC_CUDA(cudaMemcpyAsync(r.w, h_src, n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  if (idx >= 6 && hidden_reslice(m->small, m->w_fs, m->w_bs, m->H, m->L, m->cluster, (cudaStream_t)stream)) return 1;
+  if (idx >= 6 && reslice(m, (cudaStream_t)stream)) return 1;
   LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
@@ -635,7 +645,7 @@ int loc_restore_best(loc_model* m, void* stream) {
   LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   LOC_CHECK(h.best_epoch >= 0, "loc_restore_best: no checkpoint has been taken");
   if (copy_weights(m, false, nullptr, (cudaStream_t)stream)) return 1;
-  return hidden_reslice(m->small, m->w_fs, m->w_bs, m->H, m->L, m->cluster, (cudaStream_t)stream);
+  return reslice(m, (cudaStream_t)stream);
 }
 
 int loc_snapshot(loc_model* m, void* stream) {

@@ -95,6 +95,7 @@ struct UpdArgs {
   float *small, *m_small, *v_small;
   float *w_fs, *w_bs;  // pre-sliced copies kept in sync with small
   int Hc;
+  int slice_mode;  // 0: hidden.cu slices, 1: hidden_tc.cu operand images
   const float* acts;
   const float* dzs;
   const float* outs;
@@ -111,6 +112,11 @@ int hidden_max_cluster(int H, int L);  // largest usable cluster size (16, 8, ..
 int hidden_slots(int H, int L, int cluster);
 int hidden_reslice(const float* small, float* fs, float* bs, int H, int L, int cluster, cudaStream_t s);
 size_t hidden_smem_bytes(int H, int L, int cluster);
+
+// tcgen05 hidden stack (hidden_tc.cu): width 256, 16-CTA cluster
+bool hidden_tc_supported(int H, int L);
+int hidden_tc_launch(const HidArgs& a, cudaStream_t s);
+int hidden_tc_reslice(const float* small, float* fs, float* bs, int L, cudaStream_t s);
 
 // tcgen05 first layer (l1_tc.cu); available() is false when the shape is unsupported.
 bool l1_tc_supported(int64_t K, int H);
@@ -130,6 +136,7 @@ struct loc_model {
   int n_partials;   // partial Z1 tiles the forward leaves
   int n_bwd_blocks;
   int use_tc;
+  int hid_tc;       // hidden stack on tcgen05 (hidden_tc.cu) instead of CUDA cores (hidden.cu)
   loc::SmallLayout sl;
   // parameters
   float *gamma, *beta, *mmean, *mvar, *W1, *small;

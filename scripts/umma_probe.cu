@@ -17,6 +17,7 @@ struct Cfg {
   int a_kadv, b_kadv;              // bytes per MMA along K
   int layout_a, layout_b;          // descriptor layout type
   int version;
+  int M;
 };
 
 __host__ __device__ inline uint32_t place(int mode, int mn, int k, int MN, int Ktot) {
@@ -55,9 +56,9 @@ __global__ void __launch_bounds__(128, 1) probe(Cfg c, const float* A, const flo
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < 128 * c.Ktot; i += 128) {
+  for (int i = tid; i < c.M * c.Ktot; i += 128) {
     const int m = i / c.Ktot, k = i % c.Ktot;
-    *(float*)(sA + place(c.a_mode, m, k, 128, c.Ktot)) = A[i];
+    *(float*)(sA + place(c.a_mode, m, k, c.M, c.Ktot)) = A[i];
   }
   for (int i = tid; i < c.N * c.Ktot; i += 128) {
     const int n = i / c.Ktot, k = i % c.Ktot;
@@ -134,8 +135,9 @@ static uint32_t idesc(int M, int N, int amn, int bmn) {
 }
 
 static void run(const char* name, Cfg c, int do_st) {
-  const int M = 128;
-  std::vector<float> A(M * c.Ktot), B(c.N * c.Ktot), D(M * c.N, -1.f), D2(1 + 128 * 8, -1.f);
+  if (c.M == 0) c.M = 128;
+  const int M = c.M;
+  std::vector<float> A(M * c.Ktot), B(c.N * c.Ktot), D(128 * c.N, -1.f), D2(1 + 128 * 8, -1.f);
   for (int i = 0; i < M * c.Ktot; ++i) A[i] = (float)((i * 7 + 3) % 11 - 5);
   for (int i = 0; i < c.N * c.Ktot; ++i) B[i] = (float)((i * 5 + 1) % 7 - 3);
   float *dA, *dB, *dD, *dD2;
@@ -158,14 +160,24 @@ static void run(const char* name, Cfg c, int do_st) {
   cudaMemcpy(D2.data(), dD2, D2.size() * 4, cudaMemcpyDeviceToHost);
   double maxerr = 0, maxref = 0;
   int nz = 0;
+  if (M == 64) {  // which TMEM lanes hold data?
+    printf("  lanes with data:");
+    for (int l = 0; l < 128; ++l) {
+      bool any = false;
+      for (int n = 0; n < c.N; ++n) any |= (D[l * c.N + n] != 0.f && D[l * c.N + n] != -1.f);
+      if (any) printf(" %d", l);
+    }
+    printf("\n");
+  }
   for (int m = 0; m < M; ++m)
     for (int n = 0; n < c.N; ++n) {
       double r = 0;
       for (int k = 0; k < c.Ktot; ++k) r += (double)A[m * c.Ktot + k] * B[n * c.Ktot + k];
-      double d = fabs(r - D[m * c.N + n]);
+      const int lane = (M == 64) ? 32 * (m / 16) + (m % 16) : m;  // hypothesis for M = 64
+      double d = fabs(r - D[lane * c.N + n]);
       if (d > maxerr) maxerr = d;
       if (fabs(r) > maxref) maxref = fabs(r);
-      if (D[m * c.N + n] != 0.f) ++nz;
+      if (D[lane * c.N + n] != 0.f) ++nz;
     }
   printf("%-28s maxerr %.3g (max ref %.3g) nonzero %d/%d  D[0][0..3]= %g %g %g %g  D[1][0]=%g\n", name, maxerr, maxref, nz,
          M * c.N, D[0], D[1], D[2], D[3], D[c.N]);
@@ -185,6 +197,12 @@ static void run(const char* name, Cfg c, int do_st) {
 int main() {
   for (int version = 1; version >= 0; --version) {
     printf("== descriptor version %d ==\n", version);
+    if (version == 1) {  // hidden-stack configs: M = 64, N = 8
+      Cfg c = {MN_SW128_32B, KM_SW128, 8, 32, idesc(64, 8, 1, 0), 32 * 128, 512, 16, 1024, 1024, 32, 1, 2, version, 64};
+      run("M64 MN_32B x KM_SW128 N8", c, 0);
+      Cfg c2 = {KM_SW128, KM_SW128, 8, 32, idesc(64, 8, 0, 0), 16, 1024, 16, 1024, 32, 32, 2, 2, version, 64};
+      run("M64 KM_SW128 x KM_SW128 N8", c2, 0);
+    }
     {  // K-major / K-major, no swizzle
       Cfg c = {KM_NONE, KM_NONE, 32, 32, idesc(128, 32, 0, 0), 128, 128 * 8, 128, 128 * 8, 256, 256, 0, 0, version};
       run("KM_NONE x KM_NONE N32", c, version == 1);

@@ -1,8 +1,9 @@
 """GPU parity: the CUDA training / prediction path (through the C ABI) vs the CPU oracle.
 
-Tolerances.  The SIMT first layer is plain fp32 (differences = summation order only); the
-tcgen05 first layer multiplies in TF32 (10-bit mantissa, as TensorFlow does by default on
-Ampere+ GPUs), fp32 accumulate.  Stated tolerances:
+Tolerances.  The CUDA-core kernels (LOC_L1_IMPL=simt / LOC_HIDDEN_IMPL=simt, other widths) are
+plain fp32 (differences = summation order only); the tcgen05 first layer and hidden stack multiply
+in TF32 (10-bit mantissa, as TensorFlow does by default on Ampere+ GPUs), fp32 accumulate.
+Stated tolerances:
   forward / predict      |dy| <= 2e-3 * (1 + |y|)      (tf32) ; 2e-5 (fp32)
   per-step loss          rel 2e-3 (tf32) ; 1e-4 (fp32)
   weights after N steps  compared through the *update* (w - w0), whose scale is lr = 1e-3
@@ -128,8 +129,9 @@ def test_train_steps_match_oracle(M, K, H, L, p, nsteps):
     # Adam moments of the first layer against the oracle
     mW, vW = m.get_adam(4)
     idx = ref.trainable().index(ref.W[0]) if False else 2
-    np.testing.assert_allclose(mW, ref.m[idx].numpy(), rtol=0.02, atol=2e-3 * float(np.abs(ref.m[idx].numpy()).max()))
-    np.testing.assert_allclose(vW, ref.v[idx].numpy(), rtol=0.05, atol=2e-3 * float(np.abs(ref.v[idx].numpy()).max()))
+    am = 6e-3 if _impl() == "tcgen05" else 2e-3  # tf32 products in the first layer and the hidden stack
+    np.testing.assert_allclose(mW, ref.m[idx].numpy(), rtol=0.02, atol=am * float(np.abs(ref.m[idx].numpy()).max()))
+    np.testing.assert_allclose(vW, ref.v[idx].numpy(), rtol=0.05, atol=am * float(np.abs(ref.v[idx].numpy()).max()))
     # moving statistics are exact integer-derived quantities
     np.testing.assert_allclose(w1[2], r1[2], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(w1[3], r1[3], rtol=1e-5, atol=1e-6)

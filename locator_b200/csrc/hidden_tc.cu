@@ -67,6 +67,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t d, uint64_t a, uint64_t b, ui
       "l"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
+// One lane of a converged warp (elect.sync): the compiler then emits the uniform-datapath
+// tcgen05 instructions directly instead of a per-active-lane loop around each of them.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -183,22 +190,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_hidden_tc(HidArgs a) {
     mark();
     mbar_wait(&wbar[u & 1], (uint32_t)(u >> 1) & 1u);
     mark();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t wb = smem_u32(wslot + (u & 1) * kSlot), bb = smem_u32(B);
-#pragma unroll 4
-      for (int ks = 0; ks < kH / 8; ++ks) {
-        const uint64_t bdesc = smem_desc(bb + (ks >> 2) * 1024 + (ks & 3) * 32, 16, 1024, 2);
-        uint64_t adesc;
-        uint32_t idesc;
-        if (!backward) {  // MN-major [2 j-chunks][256 k rows][128 B], 32B-atom swizzle
-          adesc = smem_desc(wb + ks * 1024, kH * 128, 512, 1);
-          idesc = make_idesc(64, 8, 1, 0);
-        } else {          // K-major [8 k-chunks][8 row groups][8 rows][128 B], 128B swizzle
-          adesc = smem_desc(wb + (ks >> 2) * 8192 + (ks & 3) * 32, 16, 1024, 2);
-          idesc = make_idesc(64, 8, 0, 0);
-        }
-        umma_tf32(tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+      // base descriptors once per layer; the 32 K-steps only add compile-time constants to the
+      // 14-bit start-address field (a single thread issues: keep its instruction stream short).
+      // Four accumulators (TMEM columns 0-7, 8-15, 16-23, 24-31) take every 4th K-step so that
+      // consecutive MMAs do not wait on each other's accumulate; the epilogue adds them.
+      const uint64_t b0d = smem_desc(bb, 16, 1024, 2);
+      if (!backward) {  // A: MN-major [2 j-chunks][256 k rows][128 B], 32B-atom swizzle; 8 k rows = 1024 B per step
+        const uint64_t a0d = smem_desc(wb, kH * 128, 512, 1);
+        constexpr uint32_t idesc = make_idesc(64, 8, 1, 0);
+#pragma unroll
+        for (int ks = 0; ks < kH / 8; ++ks)
+          umma_tf32(tmem + (uint32_t)((ks & 3) * 8), a0d + (uint64_t)(ks * 64),
+                    b0d + (uint64_t)((ks >> 2) * 64 + (ks & 3) * 2), idesc, ks >= 4 ? 1u : 0u);
+      } else {          // A: K-major [8 k-chunks][8 row groups][8 rows][128 B], 128B swizzle
+        const uint64_t a0d = smem_desc(wb, 16, 1024, 2);
+        constexpr uint32_t idesc = make_idesc(64, 8, 0, 0);
+#pragma unroll
+        for (int ks = 0; ks < kH / 8; ++ks)
+          umma_tf32(tmem + (uint32_t)((ks & 3) * 8), a0d + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2),
+                    b0d + (uint64_t)((ks >> 2) * 64 + (ks & 3) * 2), idesc, ks >= 4 ? 1u : 0u);
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar))
                    : "memory");
@@ -209,16 +222,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_hidden_tc(HidArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0 && u + 2 < n_uses) issue_load(u + 2);  // the slot is free: prefetch two uses ahead
     if (warp < 4) {  // accumulator row m lives in TMEM lane 32*(m/16) + m%16
-      uint32_t v[8];
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                   : "r"(tmem + ((uint32_t)(32 * warp) << 16))
-                   : "memory");
+      uint32_t v[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(tmem + ((uint32_t)(32 * warp) << 16))
+          : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (lane < 16) {
         const int jl = 16 * warp + lane;
 #pragma unroll
-        for (int b = 0; b < kRB; ++b) zbuf[b * kCW + jl] = __uint_as_float(v[b]);
+        for (int b = 0; b < kRB; ++b)
+          zbuf[b * kCW + jl] = (__uint_as_float(v[b]) + __uint_as_float(v[8 + b])) +
+                               (__uint_as_float(v[16 + b]) + __uint_as_float(v[24 + b]));
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }

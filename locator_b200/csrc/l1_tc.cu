@@ -140,6 +140,13 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of a converged warp (elect.sync): the compiler then emits the uniform-datapath
+// tcgen05 / bulk-copy instructions directly instead of a per-active-lane loop around each of them.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(const __grid_constan
 
   if (warp == 0) {
     // ---- TMA producer ----
-    if (lane == 0) {
+    if (elect_one()) {
       for (int li = 0; li < nloc; ++li) {
         const int s = li % F_STAGES;
         const uint32_t ph = (uint32_t)(li / F_STAGES) & 1u;
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(const __grid_constan
   } else if (warp == 1) {
     // ---- MMA issuer ----
     constexpr uint32_t idesc = make_idesc(128, 32, 1, 1);
-    if (lane == 0) {
+    if (elect_one()) {
       for (int li = 0; li < nloc; ++li) {
         const int s = li % F_STAGES;
         const uint32_t ph = (uint32_t)(li / F_STAGES) & 1u;
@@ -520,7 +527,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     }
   } else if (warp == B_EPI_WARPS + 2) {
     // =========================== load warp: W, m, v chunk -> stage ===========================
-    if (lane == 0) {
+    if (elect_one()) {
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % B_STAGES;
         mbar_wait(&st_free[s], ((uint32_t)(c / B_STAGES) & 1u) ^ 1u);
@@ -538,7 +545,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     }
   } else if (warp == B_EPI_WARPS + 3) {
     // =========================== store warp: updated chunk -> W, m, v ===========================
-    if (lane == 0) {
+    if (elect_one()) {
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % B_STAGES;
         mbar_wait(&st_done[s], (uint32_t)(c / B_STAGES) & 1u);

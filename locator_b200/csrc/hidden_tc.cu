@@ -23,7 +23,7 @@ namespace loc {
 namespace htc {
 
 constexpr int kH = 256, kC = 16, kRB = 8, kCW = 64;
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kSlot = kH * kCW * 4;    // 64 KB weight-slice image
 constexpr int kGath = kRB * kH * 4;    // 8 KB gathered B operand: [8 k-atoms][8 rows][128 B]
 constexpr int kStage = kRB * kCW * 4;  // 2 KB own slice: 2 k-atoms
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_hidden_tc(HidArgs a) {
   uint8_t* gath = wslot + 2 * kSlot;                     // [2][8 KB]
   uint8_t* stage = gath + 2 * kGath;                     // [2][2 KB]
   float* zbuf = (float*)(stage + 2 * kStage);            // [8][64] accumulator dump
-  float* red = zbuf + kRB * kCW;                         // [2][8][64] split-K partial groups
-  float* own_a = red + 2 * kRB * kCW;                    // [L][8][64] elu outputs (pre-dropout, fp32)
+  float* red = zbuf + kRB * kCW;                         // [4][8][64] split-K partial groups
+  float* own_a = red + 4 * kRB * kCW;                    // [L][8][64] elu outputs (pre-dropout, fp32)
   float* own_dz = own_a + L * kRB * kCW;                 // [L][8][64]
   float* keep = own_dz + L * kRB * kCW;                  // [8][64]
   float* sbias = keep + kRB * kCW;                       // [L][64]
@@ -140,20 +140,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_hidden_tc(HidArgs a) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < L * kCW; i += kThreads) {
-    const int layer = i / kCW, jl = i % kCW;
-    sbias[i] = a.small[(layer == 0 ? sl.b1() : sl.bh(layer)) + j0 + jl];
+  // set-up loads go out first (registers), the split-K partial sums next, the shared-memory writes
+  // last: all of the prologue's global-memory latency overlaps
+  float r_bias[2], r_out[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = tid + q * kThreads;
+    r_bias[q] = i < L * kCW ? a.small[((i / kCW) == 0 ? sl.b1() : sl.bh(i / kCW)) + j0 + (i % kCW)] : 0.f;
+    r_out[q] = i < 2 * kH + 8 ? a.small[sl.Wo1() + i] : 0.f;
   }
-  for (int i = tid; i < 2 * kH + 8; i += kThreads) sout[i] = a.small[sl.Wo1() + i];
-  if (tid < kRB) s_rows[tid] = (b0 + tid) < nb ? row_of(a.src, a.st, b0 + tid) : 0;
+  const int64_t r_row = (tid < kRB && (b0 + tid) < nb) ? row_of(a.src, a.st, b0 + tid) : 0;
   const int step_id = a.st->step_id;
   const float keep_scale = 1.0f / (1.0f - a.p_drop);
   const bool drop_on = a.training && a.p_drop > 0.f;
+  // ---- layer 0, first half: split-K partial tiles of Z1 for the own [8 x 64] block (fixed order).
+  //      Issued before the rest of the prologue so that barrier / TMEM / bias set-up and the
+  //      cluster start-up barrier run in the shadow of these L2 reads. ----
+  const int p0_item = tid & 127, p0_g = tid >> 7;  // 128 float4 outputs x 4 partial groups
+  const int p0_b = p0_item >> 4, p0_jl = (p0_item & 15) * 4;
+  float4 p0_s = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const int pbeg = a.n_partials * p0_g / 4, pend = a.n_partials * (p0_g + 1) / 4;
+    const float4* src = reinterpret_cast<const float4*>(a.partials + (int64_t)(b0 + p0_b) * kH + j0 + p0_jl);
+#pragma unroll 16
+    for (int p = pbeg; p < pend; ++p) {
+      const float4 v = __ldcg(src + (int64_t)p * kMaxB * (kH / 4));
+      p0_s.x += v.x;
+      p0_s.y += v.y;
+      p0_s.z += v.z;
+      p0_s.w += v.w;
+    }
+  }
+  mark();
+
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = tid + q * kThreads;
+    if (i < L * kCW) sbias[i] = r_bias[q];
+    if (i < 2 * kH + 8) sout[i] = r_out[q];
+  }
+  if (tid < kRB) s_rows[tid] = r_row;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
+  mark();
   cluster_barrier();  // every CTA of the cluster is running before anyone writes into its shared memory
+  mark();
 
   int pub = 0;   // publishes so far: publish n uses stage / gathered buffer n & 1
   int nmma = 0;  // MMA batches so far (parity of mma_bar)
@@ -276,26 +309,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_hidden_tc(HidArgs a) {
     stage_store(b, jl, dz);
   };
 
-  // ---- layer 0: reduce the split-K partial tiles of Z1 for the own [8 x 64] block (fixed order) ----
+  // ---- layer 0: finish the split-K reduction started in the prologue ----
   {
-    const int item = tid & 127, g = tid >> 7;  // 128 float4 outputs x 2 partial groups
-    const int b = item >> 4, jl = (item & 15) * 4;
-    const int pbeg = a.n_partials * g / 2, pend = a.n_partials * (g + 1) / 2;
-    const float4* src = reinterpret_cast<const float4*>(a.partials + (int64_t)(b0 + b) * kH + j0 + jl);
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-    for (int p = pbeg; p < pend; ++p) {
-      const float4 v = __ldcg(src + (int64_t)p * kMaxB * (kH / 4));
-      s.x += v.x;
-      s.y += v.y;
-      s.z += v.z;
-      s.w += v.w;
-    }
-    *reinterpret_cast<float4*>(red + (g * kRB + b) * kCW + jl) = s;
+    *reinterpret_cast<float4*>(red + (p0_g * kRB + p0_b) * kCW + p0_jl) = p0_s;
     __syncthreads();
+    mark();
     for (int idx = tid; idx < kRB * kCW; idx += kThreads) {
       const int bb = idx / kCW, jj = idx % kCW;
-      finish_fwd_elem(0, bb, jj, red[bb * kCW + jj] + red[(kRB + bb) * kCW + jj]);
+      const float z = (red[bb * kCW + jj] + red[(kRB + bb) * kCW + jj]) +
+                      (red[(2 * kRB + bb) * kCW + jj] + red[(3 * kRB + bb) * kCW + jj]);
+      finish_fwd_elem(0, bb, jj, z);
     }
     publish_staged();
     mark();
@@ -311,8 +334,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_hidden_tc(HidArgs a) {
 
   // ---- Dense(2), Dense(2), loss for the own 8 rows (the 4 CTAs of a batch group agree) ----
   const uint8_t* gat = wait_gather(pub - 1);  // a_{L-1} of the own rows (tf32-rounded)
-  {
-    const int b = warp;  // 8 warps = 8 rows
+  if (warp < kRB) {
+    const int b = warp;  // one warp per row
     float s0 = 0.f, s1 = 0.f;
     for (int k = lane; k < kH; k += 32) {
       const float av = *reinterpret_cast<const float*>(gat + b_off(b, k));
@@ -440,7 +463,7 @@ __global__ void k_reslice_tc(const float* __restrict__ small, float* fs, float* 
 
 static size_t smem_bytes(int L) {
   return (size_t)2 * kSlot + 2 * kGath + 2 * kStage +
-         sizeof(float) * ((size_t)kRB * kCW * (1 + 2 + 2 * L + 1) + (size_t)L * kCW + 520 + 80) + 1024;
+         sizeof(float) * ((size_t)kRB * kCW * (1 + 4 + 2 * L + 1) + (size_t)L * kCW + 520 + 80) + 1024;
 }
 
 }  // namespace htc

@@ -182,7 +182,7 @@ __device__ __forceinline__ uint32_t swz32(int r, int c) {
 // Forward
 // ---------------------------------------------------------------------------------------------
 constexpr int F_KT = 32;                              // SNPs per stage
-constexpr int F_STAGES = 5;
+constexpr int F_STAGES = 6;
 constexpr int F_THREADS = 192;                        // 6 warps
 constexpr int F_WBYTES = F_KT * kH * 4;               // 32 KB: [8 chunks][32 rows][128 B]
 constexpr int F_CHUNK = F_KT * 128;                   // bytes between j-chunks (LBO)
@@ -329,7 +329,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(const __grid_constan
         for (int e = 0; e < 4; ++e) {
           const int b = 4 * c + e;
           const unsigned x = (unsigned)((g >> (2 * b)) & 3ull);
-          const float val = x == 0u ? lut[0] : (x == 1u ? lut[1] : lut[2]);
+          float val = lut[0];  // branch-free select (the lanes of a warp hold different genotypes)
+          val = x == 1u ? lut[1] : val;
+          val = x == 2u ? lut[2] : val;
           v[e] = b < nb ? val : 0.f;
         }
         *reinterpret_cast<float4*>(xrow + swz32(lane, c)) = make_float4(v[0], v[1], v[2], v[3]);
@@ -664,8 +666,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
           const int b = 4 * c + e;
           const unsigned x = (unsigned)((g >> (2 * b)) & 3ull);
           const bool on = b < nb;
-          vh[e] = on ? (x == 0u ? chi[0] : (x == 1u ? chi[1] : chi[2])) : 0.f;
-          vl[e] = on ? (x == 0u ? clo[0] : (x == 1u ? clo[1] : clo[2])) : 0.f;
+          float h = chi[0], l = clo[0];  // branch-free select
+          h = x == 1u ? chi[1] : h;
+          l = x == 1u ? clo[1] : l;
+          h = x == 2u ? chi[2] : h;
+          l = x == 2u ? clo[2] : l;
+          vh[e] = on ? h : 0.f;
+          vl[e] = on ? l : 0.f;
         }
         *reinterpret_cast<float4*>(xh + swz(r, c)) = make_float4(vh[0], vh[1], vh[2], vh[3]);
         if (need_lo) *reinterpret_cast<float4*>(xl + swz(r, c)) = make_float4(vl[0], vl[1], vl[2], vl[3]);

@@ -6,12 +6,14 @@
 //
 // FORWARD  (k_l1_fwd_tc), one persistent CTA per SM, split over SNPs:
 //   D[j, b] += W1[k, j]^T * xhat[k, b]      M = 128 (two halves of j), N = 32 (batch), K = 8 SNPs / MMA
-//   A = W1 tile, TMA-loaded as [8 j-chunks][32 SNP rows][128 B] with the 128B/32B-atom swizzle: the
-//       canonical MN-major tf32 operand layout, straight from the row-major fp32 master weights
-//       (kind::tf32 reads the fp32 bits; no conversion pass).
+//   A = W1 tile.  W1 (and Adam's m, v) live in HBM in a chunk-tiled, pre-swizzled layout
+//       (model.cuh: w1_tiled_index) -- blocks of 8 SNPs x 256 columns = 8 KB, inside a block
+//       [8 j-chunks][8 SNP rows][128 B] with the 128B/32B-atom swizzle -- which IS the canonical
+//       MN-major tf32 operand image: a stage is one contiguous 32 KB cp.async.bulk, no tensor map,
+//       no conversion pass (kind::tf32 reads the fp32 master weights' bits).
 //   B = xhat tile [32 SNP rows][32 batch = 128 B], built in shared memory by the builder warps from
 //       the 2-bit genotypes with the folded BatchNorm (x*inv + shift), rounded to tf32.
-//   warp 0: TMA producer | warp 1: TMEM alloc + MMA issue | warps 2-5: operand builders, epilogue.
+//   warp 0: bulk-copy producer | warp 1: TMEM alloc + MMA issue | warps 2-5: operand builders, epilogue.
 //   5-stage mbarrier ring; accumulators (2 x 32 columns) stay in TMEM for the whole K range; the
 //   epilogue writes one [32][256] partial tile per CTA (reduced in fixed order by k_hidden).
 //
@@ -27,7 +29,6 @@
 //   butterfly transpose across the warp and summed across warps in fixed order.
 //   warps 0-15: epilogue (two groups alternating chunks) | 16-17: genotype unpack / BN statistics /
 //   gamma-beta Adam, MMA issue | 18: bulk loads | 19: bulk stores.
-#include <cuda.h>
 #include <stdlib.h>
 
 #include "l1_common.cuh"
@@ -153,23 +154,6 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
-__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                            int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      :
-      : "r"(smem_dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      :
-      : "r"(smem_dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-
 // Row r of a swizzled [rows][128 B] tile, logical 16-byte chunk c:
 //   swz   (K-major SWIZZLE_128B):            chunk c lives at c ^ (r & 7)
 //   swz32 (MN-major SWIZZLE_128B, 32B atom): the 32-byte pair (c >> 1) lives at (c >> 1) ^ (r & 3)
@@ -184,13 +168,12 @@ __device__ __forceinline__ uint32_t swz32(int r, int c) {
 constexpr int F_KT = 32;                              // SNPs per stage
 constexpr int F_STAGES = 6;
 constexpr int F_THREADS = 192;                        // 6 warps
-constexpr int F_WBYTES = F_KT * kH * 4;               // 32 KB: [8 chunks][32 rows][128 B]
+constexpr int F_WBYTES = F_KT * kH * 4;               // 32 KB: 4 blocks of [8 j-chunks][8 rows][128 B]
 constexpr int F_CHUNK = F_KT * 128;                   // bytes between j-chunks (LBO)
 constexpr int F_XBYTES = F_KT * 128;                  // 4 KB:  [32 rows][32 batch]
 constexpr int F_SMEM = F_STAGES * (F_WBYTES + F_XBYTES) + 4 * 32 * 8 + 256 + 1024;  // + bits scratch + barriers + align
 
-__global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(const __grid_constant__ CUtensorMap wmap, int tma_rank,
-                                                          L1Args a, int64_t ntiles) {
+__global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(L1Args a, int64_t ntiles) {
   if (a.gated && a.st->stopped) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -233,13 +216,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(const __grid_constan
         const uint32_t ph = (uint32_t)(li / F_STAGES) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full_w[s], F_WBYTES);
-        const int k0 = (int)((t_begin + li) * F_KT);
-        if (tma_rank == 3) {
-          tma_load_3d(smem_u32(sW + s * F_WBYTES), &wmap, &full_w[s], 0, k0, 0);
-        } else {
-          for (int c = 0; c < 8; ++c)
-            tma_load_2d(smem_u32(sW + s * F_WBYTES + c * F_CHUNK), &wmap, &full_w[s], 32 * c, k0);
-        }
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sW + s * F_WBYTES)),
+                     "l"(a.W1 + (t_begin + li) * (int64_t)(F_KT * kH)), "r"((uint32_t)F_WBYTES), "r"(smem_u32(&full_w[s]))
+                     : "memory");
       }
     }
   } else if (warp == 1) {
@@ -258,7 +238,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(const __grid_constan
           const uint64_t bdesc = smem_desc(xbase + ks * 1024, F_CHUNK, 512, kLayoutSw128B32);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const uint64_t adesc = smem_desc(wbase + h * 4 * F_CHUNK + ks * 1024, F_CHUNK, 512, kLayoutSw128B32);
+            const uint64_t adesc = smem_desc(wbase + ks * 8192 + h * 4096, 1024, 512, kLayoutSw128B32);
             umma_tf32(tmem + h * 32, adesc, bdesc, idesc, (li > 0 || ks > 0) ? 1u : 0u);
           }
         }
@@ -449,13 +429,6 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const float alpha = a.st->alpha;
-  // rows of chunk c (CTA-local index) that exist (K need not be a multiple of 8)
-  auto chunk_rows = [&](int c) -> int {
-    const int64_t k0 = t_begin * B_NT + (int64_t)c * B_CH;
-    const int64_t left = a.K - k0;
-    return left >= B_CH ? B_CH : (left > 0 ? (int)left : 0);
-  };
-
   if (warp < B_EPI_WARPS) {
     // =========================== epilogue warps ===========================
     const int grp = warp >> 3, w8 = warp & 7;
@@ -474,14 +447,16 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       uint32_t gr[8];
       tmem_ld_x8(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 128 + h * 64 + cc * 8), gr);
       mbar_wait(&st_full[s], (uint32_t)(c / B_STAGES) & 1u);
-      const int nv = chunk_rows(c);
-      float* stw = reinterpret_cast<float*>(sStage + s * B_STAGE) + j;
+      // element (row r, column j) of a chunk block: [j/32][r][32B atoms XOR (r & 3)] (w1_tiled_index)
+      float* stw = reinterpret_cast<float*>(sStage + s * B_STAGE) + ((j >> 5) << 8) + (j & 7);
+      const int j8 = (j & 31) >> 3;
       float w[8], m[8], v[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        w[r] = stw[r * kH];
-        m[r] = stw[B_ARR / 4 + r * kH];
-        v[r] = stw[2 * (B_ARR / 4) + r * kH];
+        const int o = (r << 5) + ((j8 ^ (r & 3)) << 3);
+        w[r] = stw[o];
+        m[r] = stw[B_ARR / 4 + o];
+        v[r] = stw[2 * (B_ARR / 4) + o];
       }
       tmem_ld_wait();
       float pq[16];
@@ -490,18 +465,16 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
         const float4 sc = sSc[buf * B_NT + cc * 8 + r];
         const float S = __uint_as_float(gr[r]);
         const float g = sc.x * S + sc.y * c0;
-        const bool ok = r < nv;
-        pq[r] = ok ? w[r] * S : 0.f;
-        pq[8 + r] = ok ? w[r] * c0 : 0.f;
+        pq[r] = w[r] * S;  // padding rows (k >= K) hold zeros and stay zero
+        pq[8 + r] = w[r] * c0;
         adam_update_fast(w[r], m[r], v[r], g, alpha);
       }
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        if (r < nv) {
-          stw[r * kH] = w[r];
-          stw[B_ARR / 4 + r * kH] = m[r];
-          stw[2 * (B_ARR / 4) + r * kH] = v[r];
-        }
+        const int o = (r << 5) + ((j8 ^ (r & 3)) << 3);
+        stw[o] = w[r];
+        stw[B_ARR / 4 + o] = m[r];
+        stw[2 * (B_ARR / 4) + o] = v[r];
       }
       fence_proxy_async();  // the bulk store reads these rows through the async proxy
       // butterfly transpose-reduce: lane l ends with the warp total of pq[l & 15]
@@ -533,16 +506,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % B_STAGES;
         mbar_wait(&st_free[s], ((uint32_t)(c / B_STAGES) & 1u) ^ 1u);
-        const int nv = chunk_rows(c);
-        const uint32_t bytes = (uint32_t)nv * kH * 4;
-        mbar_arrive_expect_tx(&st_full[s], 3 * bytes);
-        if (nv > 0) {
-          const int64_t off = (t_begin * B_NT + (int64_t)c * B_CH) * kH;
-          const uint32_t dst = smem_u32(sStage + s * B_STAGE);
-          bulk_load(dst, a.W1 + off, bytes, &st_full[s]);
-          bulk_load(dst + B_ARR, a.mW1 + off, bytes, &st_full[s]);
-          bulk_load(dst + 2 * B_ARR, a.vW1 + off, bytes, &st_full[s]);
-        }
+        mbar_arrive_expect_tx(&st_full[s], B_STAGE);
+        const int64_t off = (t_begin * B_NT + (int64_t)c * B_CH) * kH;  // chunk blocks are contiguous 8 KB
+        const uint32_t dst = smem_u32(sStage + s * B_STAGE);
+        bulk_load(dst, a.W1 + off, B_ARR, &st_full[s]);
+        bulk_load(dst + B_ARR, a.mW1 + off, B_ARR, &st_full[s]);
+        bulk_load(dst + 2 * B_ARR, a.vW1 + off, B_ARR, &st_full[s]);
       }
     }
   } else if (warp == B_EPI_WARPS + 3) {
@@ -551,17 +520,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % B_STAGES;
         mbar_wait(&st_done[s], (uint32_t)(c / B_STAGES) & 1u);
-        const int nv = chunk_rows(c);
-        if (nv > 0) {
-          const uint32_t bytes = (uint32_t)nv * kH * 4;
-          const int64_t off = (t_begin * B_NT + (int64_t)c * B_CH) * kH;
-          const uint32_t src = smem_u32(sStage + s * B_STAGE);
-          bulk_store(a.W1 + off, src, bytes);
-          bulk_store(a.mW1 + off, src + B_ARR, bytes);
-          bulk_store(a.vW1 + off, src + 2 * B_ARR, bytes);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
+        const int64_t off = (t_begin * B_NT + (int64_t)c * B_CH) * kH;
+        const uint32_t src = smem_u32(sStage + s * B_STAGE);
+        bulk_store(a.W1 + off, src, B_ARR);
+        bulk_store(a.mW1 + off, src + B_ARR, B_ARR);
+        bulk_store(a.vW1 + off, src + 2 * B_ARR, B_ARR);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_arrive(&st_free[s]);
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -741,68 +706,14 @@ int l1_tc_partials(int64_t K) {
   return (int)(ntiles < tc_sm_count() ? ntiles : tc_sm_count());
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point: the library itself does not link
-// libcuda, so it still loads (for the symbol check) on a machine without a driver.
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s) {
-  // W1 viewed as [8 j-chunks][K SNPs][32 floats]: one TMA box = the whole [8][32][32] stage tile
-  static thread_local const float* cached_w = nullptr;
-  static thread_local int64_t cached_k = 0;
-  static thread_local CUtensorMap map;
-  static thread_local int tma_rank = 3;
-  if (cached_w != a.W1 || cached_k != a.K) {
-    cuuint64_t dims[3] = {32, (cuuint64_t)a.K, 8};
-    cuuint64_t strides[2] = {(cuuint64_t)tc::kH * 4, 128};  // bytes, dims 1 and 2
-    cuuint32_t box[3] = {32, (cuuint32_t)tc::F_KT, 8};
-    cuuint32_t estr[3] = {1, 1, 1};
-    const char* force2d = getenv("LOC_TMA_2D");
-    EncodeTiledFn encode = encode_tiled_fn();
-    LOC_CHECK(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
-    CUresult r = CUDA_ERROR_INVALID_VALUE;
-    if (force2d == nullptr)
-      r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.W1, dims, strides, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    tma_rank = 3;
-    if (r != CUDA_SUCCESS) {
-      // plain row-major view [K][256], eight [32 rows][32 floats] boxes per stage
-      cuuint64_t dims2[2] = {(cuuint64_t)tc::kH, (cuuint64_t)a.K};
-      cuuint64_t strides2[1] = {(cuuint64_t)tc::kH * 4};
-      cuuint32_t box2[2] = {32, (cuuint32_t)tc::F_KT};
-      r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.W1, dims2, strides2, box2, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      tma_rank = 2;
-    }
-    if (r != CUDA_SUCCESS) {
-      char buf[256];
-      snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
-      return fail(buf, __FILE__, __LINE__);
-    }
-    cached_w = a.W1;
-    cached_k = a.K;
-  }
   static bool attr_set = false;
   if (!attr_set) {
     LOC_CUDA(cudaFuncSetAttribute(tc::k_l1_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::F_SMEM));
     attr_set = true;
   }
   const int64_t ntiles = cdiv(a.K, tc::F_KT);
-  tc::k_l1_fwd_tc<<<n_partials, tc::F_THREADS, tc::F_SMEM, s>>>(map, tma_rank, a, ntiles);
+  tc::k_l1_fwd_tc<<<n_partials, tc::F_THREADS, tc::F_SMEM, s>>>(a, ntiles);
   LOC_LAUNCHED();
   return 0;
 }

@@ -29,6 +29,27 @@ __global__ void k_glorot(float* w, int64_t n, float limit, uint32_t stream, uint
   }
 }
 
+// W1 in the tiled layout (model.cuh: w1_tiled_index): same Philox element index as the row-major init.
+__global__ void k_glorot_tiled(float* w, int64_t K, int H, float limit, uint32_t stream, uint64_t seed) {
+  const int64_t n = K * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float u = philox_uniform((uint64_t)i, stream, seed);
+    w[w1_tiled_index(i / H, (int)(i % H))] = (2.0f * u - 1.0f) * limit;
+  }
+}
+
+// Keras row-major [K][256] <-> tiled (to_tiled: dst tiled; else dst row-major)
+__global__ void k_w1_permute(float* dst, const float* src, int64_t K, int H, int to_tiled) {
+  const int64_t n = K * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = w1_tiled_index(i / H, (int)(i % H));
+    if (to_tiled)
+      dst[t] = src[i];
+    else
+      dst[i] = src[t];
+  }
+}
+
 __global__ void k_state_reset(DevState* st, float lr, int patience, int max_epochs, int reset_opt) {
   if (reset_opt) {
     st->t = 0;
@@ -148,7 +169,7 @@ static int copy_weights(loc_model* m, bool to_best, const int* cond, cudaStream_
   CopySegs cs;
   float* live[6] = {m->W1, m->gamma, m->beta, m->mmean, m->mvar, m->small};
   float* best[6] = {m->best_W1, m->best_gamma, m->best_beta, m->best_mmean, m->best_mvar, m->best_small};
-  const int64_t n[6] = {m->K * m->H, m->K, m->K, m->K, m->K, m->sl.total()};
+  const int64_t n[6] = {m->Kpad * m->H, m->K, m->K, m->K, m->K, m->sl.total()};
   for (int i = 0; i < 6; ++i) {
     cs.dst[i] = to_best ? best[i] : live[i];
     cs.src[i] = to_best ? live[i] : best[i];
@@ -289,6 +310,30 @@ static int infer_rows(loc_model* m, const uint32_t* packed, int64_t n, int64_t r
   return 0;
 }
 
+// Keras row-major host array <-> tiled device array (through a row-major staging buffer).
+static int w1_upload(loc_model* m, float* d_tiled, const float* h_src, cudaStream_t s) {
+  const int64_t n = m->K * m->H;
+  float* tmp = nullptr;
+  LOC_CUDA(cudaMalloc(&tmp, n * sizeof(float)));
+  LOC_CUDA(cudaMemcpyAsync(tmp, h_src, n * sizeof(float), cudaMemcpyHostToDevice, s));
+  k_w1_permute<<<sm_count() * 8, 256, 0, s>>>(d_tiled, tmp, m->K, m->H, 1);
+  loc::g_launches.fetch_add(1);
+  LOC_CUDA(cudaStreamSynchronize(s));
+  LOC_CUDA(cudaFree(tmp));
+  return 0;
+}
+static int w1_download(loc_model* m, const float* d_tiled, float* h_dst, cudaStream_t s) {
+  const int64_t n = m->K * m->H;
+  float* tmp = nullptr;
+  LOC_CUDA(cudaMalloc(&tmp, n * sizeof(float)));
+  k_w1_permute<<<sm_count() * 8, 256, 0, s>>>(tmp, d_tiled, m->K, m->H, 0);
+  loc::g_launches.fetch_add(1);
+  LOC_CUDA(cudaMemcpyAsync(h_dst, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  LOC_CUDA(cudaStreamSynchronize(s));
+  LOC_CUDA(cudaFree(tmp));
+  return 0;
+}
+
 }  // namespace loc
 
 extern "C" {
@@ -345,9 +390,13 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
     const int64_t nch2 = cdiv(K, 32);
     m->n_bwd_blocks = (int)(nch2 < 2 * sms ? nch2 : 2 * sms);
   }
-  const int64_t KH = K * width, ns = m->sl.total();
+  m->Kpad = m->use_tc ? (K + 63) / 64 * 64 : K;
+  const int64_t KH = m->Kpad * width, ns = m->sl.total();
   float** big[] = {&m->W1, &m->mW1, &m->vW1, &m->best_W1};
-  for (auto p : big) LOC_CUDA(cudaMalloc(p, KH * sizeof(float)));
+  for (auto p : big) {
+    LOC_CUDA(cudaMalloc(p, KH * sizeof(float)));
+    LOC_CUDA(cudaMemset(*p, 0, KH * sizeof(float)));  // padding rows stay zero under Adam
+  }
   float** kv[] = {&m->gamma, &m->beta, &m->mmean, &m->mvar, &m->m_gamma, &m->v_gamma, &m->m_beta,
                   &m->v_beta, &m->best_gamma, &m->best_beta, &m->best_mmean, &m->best_mvar};
   for (auto p : kv) LOC_CUDA(cudaMalloc(p, K * sizeof(float)));
@@ -404,7 +453,7 @@ int loc_model_init(loc_model* m, uint64_t seed, void* stream) {
   float* zeroK[] = {m->m_gamma, m->v_gamma, m->m_beta, m->v_beta};
   for (float* p : zeroK)
     if (fill(p, K, 0.f, s)) return 1;
-  if (fill(m->mW1, K * H, 0.f, s) || fill(m->vW1, K * H, 0.f, s)) return 1;
+  if (fill(m->W1, m->Kpad * H, 0.f, s) || fill(m->mW1, m->Kpad * H, 0.f, s) || fill(m->vW1, m->Kpad * H, 0.f, s)) return 1;
   if (fill(m->small, m->sl.total(), 0.f, s) || fill(m->m_small, m->sl.total(), 0.f, s) ||
       fill(m->v_small, m->sl.total(), 0.f, s))
     return 1;
@@ -418,7 +467,13 @@ int loc_model_init(loc_model* m, uint64_t seed, void* stream) {
     LOC_LAUNCHED();
     return 0;
   };
-  if (glorot(m->W1, K, H, 0)) return 1;
+  if (m->use_tc) {
+    const float limit = (float)sqrt(6.0 / (double)(K + H));
+    k_glorot_tiled<<<sm_count() * 8, 256, 0, s>>>(m->W1, K, (int)H, limit, 16u, seed);
+    LOC_LAUNCHED();
+  } else if (glorot(m->W1, K, H, 0)) {
+    return 1;
+  }
   for (int i = 1; i < L; ++i)
     if (glorot(m->small + m->sl.Wh(i), H, H, i)) return 1;
   if (glorot(m->small + m->sl.Wo1(), H, 2, (int)L)) return 1;
@@ -479,6 +534,7 @@ int loc_model_set_weight(loc_model* m, int32_t idx, const float* h_src, int64_t 
   WRef r;
   LOC_CHECK(m != nullptr && weight_ref(m, idx, &r), "loc_model_set_weight: bad weight index");
   LOC_CHECK(n == r.n, "loc_model_set_weight: size mismatch");
+  if (idx == 4 && m->use_tc) return w1_upload(m, r.w, h_src, (cudaStream_t)stream);
   LOC_CUDA(cudaMemcpyAsync(r.w, h_src, n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   if (idx >= 6 && reslice(m, (cudaStream_t)stream)) return 1;
   LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -489,6 +545,7 @@ int loc_model_get_weight(loc_model* m, int32_t idx, float* h_dst, int64_t n, voi
   WRef r;
   LOC_CHECK(m != nullptr && weight_ref(m, idx, &r), "loc_model_get_weight: bad weight index");
   LOC_CHECK(n == r.n, "loc_model_get_weight: size mismatch");
+  if (idx == 4 && m->use_tc) return w1_download(m, r.w, h_dst, (cudaStream_t)stream);
   LOC_CUDA(cudaMemcpyAsync(h_dst, r.w, n * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
@@ -499,6 +556,10 @@ int loc_model_get_adam(loc_model* m, int32_t idx, float* h_m, float* h_v, int64_
   LOC_CHECK(m != nullptr && weight_ref(m, idx, &r), "loc_model_get_adam: bad weight index");
   LOC_CHECK(r.am != nullptr, "loc_model_get_adam: weight is not trainable");
   LOC_CHECK(n == r.n, "loc_model_get_adam: size mismatch");
+  if (idx == 4 && m->use_tc) {
+    if (w1_download(m, r.am, h_m, (cudaStream_t)stream)) return 1;
+    return w1_download(m, r.av, h_v, (cudaStream_t)stream);
+  }
   LOC_CUDA(cudaMemcpyAsync(h_m, r.am, n * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   LOC_CUDA(cudaMemcpyAsync(h_v, r.av, n * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   LOC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));

@@ -47,6 +47,14 @@ __device__ __forceinline__ int64_t row_of(const RowSrc& r, const DevState* st, i
   return (int64_t)r.rows[e * r.epoch_stride + r.offset + b];
 }
 
+// HBM layout of W1 / m / v when the tcgen05 first layer is in use (width 256): blocks of 8 SNPs
+// (8 KB), inside a block [8 chunks of 32 columns][8 SNP rows][128 B] with 32-byte atoms XOR (row & 3)
+// -- the canonical MN-major tf32 UMMA operand image, so both first-layer kernels move it with plain
+// contiguous bulk copies.  Rows are padded to a multiple of 64 with zeros.
+__host__ __device__ inline int64_t w1_tiled_index(int64_t k, int j) {
+  return ((k >> 3) << 11) + ((int64_t)(j >> 5) << 8) + ((k & 7) << 5) + ((((j & 31) >> 3) ^ (int)(k & 3)) << 3) + (j & 7);
+}
+
 struct L1Args {
   int64_t K;
   int H;
@@ -135,7 +143,8 @@ struct loc_model {
   int cluster;
   int n_partials;   // partial Z1 tiles the forward leaves
   int n_bwd_blocks;
-  int use_tc;
+  int use_tc;       // first layer on tcgen05 (implies the tiled W1 layout)
+  int64_t Kpad;     // rows allocated for W1 / m / v (K rounded up to 64 when tiled)
   int hid_tc;       // hidden stack on tcgen05 (hidden_tc.cu) instead of CUDA cores (hidden.cu)
   loc::SmallLayout sl;
   // parameters

@@ -350,6 +350,9 @@ def main():
         h2d = xtr.nbytes + xva.nbytes + ytr.nbytes + yva.nbytes + ne * ntr * 4
         e2e = {"value": world * ne * ntr / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d / nst,
                "d2h_bytes_per_step": (ne * 12 + 64) / nst, "epochs": ne, "seconds": dt,
+               # replicate throughput of BASELINE's second metric: one model at the throughput schedule of
+               # SURVEY 8(d) (--max_epochs 20 --patience 1000), ingest of the packed matrix included
+               "replicate_models_per_hour_20_epochs": world * 3600.0 / (dt * 20.0 / ne),
                "what": "LocatorModel.fit on host uint8 matrices: H2D, 2-bit pack, epochs incl. validation, history D2H"}
         del m2
 

@@ -307,6 +307,15 @@ def main():
         b.record()
     torch.cuda.synchronize()
     hid_ms = float(np.mean([a.elapsed_time(b) for a, b in hid_evs]))
+    fus_ms = None
+    if m.impl == "tcgen05":
+        fus_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in fus_evs:
+            a.record()
+            _cabi.check(lib.loc_debug_stage(m._h, 4, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
+            b.record()
+        torch.cuda.synchronize()
+        fus_ms = float(np.mean([a.elapsed_time(b) for a, b in fus_evs]))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -328,7 +337,8 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": bwd_ms,
-                "stage_ms": {"l1_forward": fwd_ms, "hidden": hid_ms, "l1_backward": bwd_ms},
+                "stage_ms": {"l1_forward": fwd_ms, "hidden": hid_ms, "l1_backward": bwd_ms,
+                             "l1_backward_with_fused_next_forward": fus_ms},
                 "step_roofline_frac": (28.0 * K * H / 1e9 / peak) / (ms / 1000.0 / steps) }
 
     # ---- e2e: fit() on host arrays (H2D + pack + the same number of steps + history D2H) ----

@@ -186,7 +186,8 @@ int loc_model_history(loc_model* m, float* h_out, int32_t max_rows, void* stream
 
 /* Profiling / test hook: launch ONE stage of an optimizer step on rows d_rows[0..nb):
  * 0 = first-layer forward, 1 = hidden stack (fwd + loss + bwd), 2 = first-layer backward + Adam,
- * 3 = small-layer update.  Stages read the scratch the previous ones left.  Async. */
+ * 3 = small-layer update, 4 = first-layer backward + Adam with the next step's forward fused in (tcgen05 path).
+ * Stages read the scratch the previous ones left.  Async. */
 int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t nb, void* stream);
 
 /* Test hook: copy a scratch buffer to the host (synchronises).  which: 0 = split-K partial tiles of

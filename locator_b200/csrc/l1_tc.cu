@@ -189,8 +189,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(L1Args a, int64_t nt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = a.src.nb;
-  const int64_t t_begin = ntiles * blockIdx.x / gridDim.x;
-  const int64_t t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+  // ntiles counts 64-SNP tiles (the backward kernel's unit) so both kernels split K identically
+  const int64_t t_begin = 2 * (ntiles * blockIdx.x / gridDim.x);
+  const int64_t t_end = 2 * (ntiles * (blockIdx.x + 1) / gridDim.x);
   const int nloc = (int)(t_end - t_begin);
 
   if (threadIdx.x == 0) {
@@ -347,13 +348,14 @@ constexpr int B_NT = 64;                       // SNPs per tile (one accumulator
 constexpr int B_CH = 8;                        // SNPs per streamed chunk (one W/m/v stage)
 constexpr int B_STAGES = 4;
 constexpr int B_EPI_WARPS = 16;                // two groups of 8: group g owns the chunks with index % 2 == g
-constexpr int B_THREADS = (B_EPI_WARPS + 4) * 32;  // + 2 builder warps, 1 load warp, 1 store warp
+constexpr int B_THREADS = (B_EPI_WARPS + 6) * 32;  // + 2 builder warps, load warp, store warp, 2 forward warps
 constexpr int B_DZ = kMaxB * kH * 4;           // 32 KB: [8 chunks][32 rows (b)][128 B]
 constexpr int B_DZ_CHUNK = kMaxB * 128;        // 4096
 constexpr int B_X = B_NT * 128;                // 8 KB: [64 rows (SNP)][32 batch]
 constexpr int B_ARR = B_CH * kH * 4;           // 8 KB: one array's rows of a chunk
 constexpr int B_STAGE = 3 * B_ARR;             // 24 KB: W | m | v
-constexpr int B_SMEM = 2 * B_DZ + 4 * B_X + B_STAGES * B_STAGE + 2 * B_NT * 16 + 2 * 8 * B_NT * 8 + 2 * 32 * 8 + 512 + 1024;
+constexpr int B_XF = 8 * 128;                  // 1 KB: next batch's xhat rows of one chunk [8 SNP rows][32 batch]
+constexpr int B_SMEM = 2 * B_DZ + 4 * B_X + B_STAGES * (B_STAGE + B_XF) + 2 * B_NT * 16 + 2 * 8 * B_NT * 8 + 2 * 32 * 8 + 512 + 1024;
 
 __device__ __forceinline__ void adam_update_fast(float& w, float& m, float& v, float g, float alpha) {
   m = m + (g - m) * kAdam1mB1;
@@ -380,7 +382,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   uint8_t* sXhi = sDZlo + B_DZ;                  // [2][B_X]
   uint8_t* sXlo = sXhi + 2 * B_X;                // [2][B_X]
   uint8_t* sStage = sXlo + 2 * B_X;              // [B_STAGES][W | m | v][8 rows][256]
-  float4* sSc = (float4*)(sStage + B_STAGES * B_STAGE);  // [2][64] (inv, beta, -, -)
+  uint8_t* sXf = sStage + B_STAGES * B_STAGE;    // [B_STAGES][1 KB] forward B operand of the chunk in the stage
+  float4* sSc = (float4*)(sXf + B_STAGES * B_XF);  // [2][64] (inv, beta, rs, -)
   float2* sRed = (float2*)(sSc + 2 * B_NT);      // [2][8 warps][64] (P, Q) partial sums
   uint32_t* sBits = (uint32_t*)(sRed + 2 * 8 * B_NT);  // [2 builder warps][32 rows][2 words]
   uint64_t* bars = (uint64_t*)(sBits + 2 * 32 * 2);
@@ -389,10 +392,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   uint64_t* st_full = bars + 4;                  // [B_STAGES] W/m/v chunk landed
   uint64_t* st_done = st_full + B_STAGES;        // [B_STAGES] chunk updated in place (8 warps)
   uint64_t* st_free = st_done + B_STAGES;        // [B_STAGES] chunk written back, stage reusable
-  uint32_t* tmem_slot = (uint32_t*)(st_free + B_STAGES);
+  uint64_t* fwd_done = st_free + B_STAGES;       // forward accumulators complete (fused runs)
+  uint32_t* tmem_slot = (uint32_t*)(fwd_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = a.src.nb;
+  const bool fuse = a.fuse_next != 0;  // also run the NEXT step's forward on the freshly updated chunks
   const bool need_lo = (nb & (nb - 1)) != 0;  // centred genotypes are multiples of 1/nb: exact in tf32 iff nb = 2^n
   const int64_t t_begin = ntiles * blockIdx.x / gridDim.x;
   const int64_t t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
@@ -407,11 +412,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     for (int s = 0; s < B_STAGES; ++s) {
       mbar_init(&st_full[s], 1);
       mbar_init(&st_done[s], 8);
-      mbar_init(&st_free[s], 1);
+      mbar_init(&st_free[s], fuse ? 2 : 1);  // written back (+ consumed by the forward MMA)
     }
+    mbar_init(fwd_done, 2);  // one commit per forward warp
     fence_barrier_init();
   }
-  if (warp == B_EPI_WARPS) tmem_alloc(tmem_slot, 256);
+  if (warp == B_EPI_WARPS) tmem_alloc(tmem_slot, 512);
   // dZ1 -> hi/lo tf32 operands, [chunk = j/32][row = b][swizzled 32 j]
   for (int i = threadIdx.x; i < kMaxB * kH / 4; i += B_THREADS) {
     const int b = i / (kH / 4), j4 = (i % (kH / 4)) * 4;
@@ -500,6 +506,17 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
     }
+    if (fuse && grp == 0) {  // next step's split-K partial tile of Z1: accumulator row = j, column = batch row
+      mbar_wait(fwd_done, 0);
+      tc_fence_after();
+      uint32_t r32[32], r33[32];
+      tmem_ld_x32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 + h * 32), r32);
+      tmem_ld_x32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 + 64 + h * 32), r33);
+      tmem_ld_wait();
+      float* out = a.partials + (int64_t)blockIdx.x * kMaxB * kH + j;
+#pragma unroll
+      for (int b = 0; b < kMaxB; ++b) out[b * kH] = __uint_as_float(r32[b]) + __uint_as_float(r33[b]);
+    }
   } else if (warp == B_EPI_WARPS + 2) {
     // =========================== load warp: W, m, v chunk -> stage ===========================
     if (elect_one()) {
@@ -531,6 +548,119 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+  } else if (warp >= B_EPI_WARPS + 4) {
+    // ====== forward warps (fused runs), alternating chunks: per chunk, gamma/beta Adam, the next batch's
+    //        BN statistics and xhat rows, and the forward MMA on the chunk of W1 just updated in the stage.
+    //        Each warp accumulates into its own TMEM columns; the epilogue adds the two. ======
+    if (fuse) {
+      constexpr uint32_t idesc_f = make_idesc(128, 32, 1, 1);
+      const int fw = warp - (B_EPI_WARPS + 4);
+      const int nbn = a.src_next.nb;
+      const int64_t nrow = lane < nbn ? row_of(a.src_next, a.st, lane) : 0;
+      const uint32_t* nptr = a.packed + nrow * a.row_words;
+      const int r = lane & 7;  // SNP of the chunk this lane does the scalar work for (lanes 8.. replicate)
+      struct Pre {
+        uint32_t word;
+        float gm, bt, mg, vg, mb, vb, mm, mv;
+      };
+      auto prefetch = [&](int c) {
+        Pre p = {0u, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+        if (c >= nchunks) return p;
+        const int64_t k0 = t_begin * B_NT + (int64_t)c * B_CH;
+        const int64_t k = k0 + r;
+        if (lane < nbn && (k0 >> 4) < a.row_words) p.word = __ldg(nptr + (k0 >> 4));
+        if (k < a.K) {
+          p.gm = a.gamma[k];
+          p.bt = a.beta[k];
+          p.mg = a.m_gamma[k];
+          p.vg = a.v_gamma[k];
+          p.mb = a.m_beta[k];
+          p.vb = a.v_beta[k];
+          p.mm = a.mmean[k];
+          p.mv = a.mvar[k];
+        }
+        return p;
+      };
+      Pre cur = prefetch(fw);
+      for (int c = fw; c < nchunks; c += 2) {
+        const Pre nxt = prefetch(c + 2);  // one chunk of this warp ahead: hides the global-load latency
+        const int li = c >> 3, cc = c & 7, buf = li & 1, s = c % B_STAGES;
+        const int64_t k0 = t_begin * B_NT + (int64_t)c * B_CH;
+        const int64_t k = k0 + r;
+        const bool valid = k < a.K;
+        // next batch: genotype of (row = lane, SNP r8), per-SNP counts by ballot, statistics -- all of
+        // it independent of this chunk's epilogue
+        const int sh0 = 2 * (int)(k0 & 15);
+        unsigned xs[8];
+        int n1 = 0, n2 = 0;
+#pragma unroll
+        for (int r8 = 0; r8 < 8; ++r8) {
+          const unsigned x = (cur.word >> (sh0 + 2 * r8)) & 3u;  // rows >= nbn hold zeros
+          xs[r8] = x;
+          const unsigned m1 = __ballot_sync(0xffffffffu, x == 1u), m2 = __ballot_sync(0xffffffffu, x == 2u);
+          if (r == r8) {
+            n1 = __popc(m1);
+            n2 = __popc(m2);
+          }
+        }
+        float mean, var;
+        moments_from_counts(n1, n2, nbn, mean, var);
+        const float rsn = rsqrtf(var + kBnEps);
+        mbar_wait(&st_done[s], (uint32_t)(c / B_STAGES) & 1u);
+        float P = 0.f, Q = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const float2 pr = sRed[(buf * 8 + w) * B_NT + cc * 8 + r];
+          P += pr.x;
+          Q += pr.y;
+        }
+        const float rs = sSc[buf * B_NT + cc * 8 + r].z;
+        float gm = cur.gm, mg = cur.mg, vg = cur.vg, bt = cur.bt, mb = cur.mb, vb = cur.vb;
+        adam_update(gm, mg, vg, rs * P, alpha);
+        adam_update(bt, mb, vb, Q, alpha);
+        const float inv = rsn * gm;
+        const float shift = bt - mean * inv;
+        const float l0 = valid ? to_tf32(shift) : 0.f;
+        const float l1 = valid ? to_tf32(inv + shift) : 0.f;
+        const float l2 = valid ? to_tf32(2.f * inv + shift) : 0.f;
+        uint8_t* xf = sXf + s * B_XF;
+#pragma unroll
+        for (int r8 = 0; r8 < 8; ++r8) {
+          const float a0 = __shfl_sync(0xffffffffu, l0, r8), a1 = __shfl_sync(0xffffffffu, l1, r8),
+                      a2 = __shfl_sync(0xffffffffu, l2, r8);
+          float val = a0;
+          val = xs[r8] == 1u ? a1 : val;
+          val = xs[r8] == 2u ? a2 : val;
+          if (lane >= nbn) val = 0.f;
+          *reinterpret_cast<float*>(xf + r8 * 128 + ((((lane >> 3) ^ (r8 & 3))) << 5) + ((lane & 7) << 2)) = val;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t wbs = smem_u32(sStage + s * B_STAGE);
+          const uint64_t bdesc = smem_desc(smem_u32(xf), 1024, 512, kLayoutSw128B32);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+            umma_tf32(tmem + (uint32_t)(256 + fw * 64 + hh * 32), smem_desc(wbs + hh * 4096, 1024, 512, kLayoutSw128B32),
+                      bdesc, idesc_f, c > fw ? 1u : 0u);
+          umma_commit(&st_free[s]);
+          if (c + 2 >= nchunks) umma_commit(fwd_done);
+        }
+        __syncwarp();
+        if (valid && lane < 8) {  // off the stage's critical path
+          a.gamma[k] = gm;
+          a.m_gamma[k] = mg;
+          a.v_gamma[k] = vg;
+          a.beta[k] = bt;
+          a.m_beta[k] = mb;
+          a.v_beta[k] = vb;
+          a.mmean[k] = cur.mm * kBnMom + mean * kBnOneMinusMom;  // the next step's forward is a training forward
+          a.mvar[k] = cur.mv * kBnMom + var * kBnOneMinusMom;
+        }
+        cur = nxt;
+      }
+    }
   } else {
     // =========================== builder warps (2 x 32 SNPs per tile) ===========================
     constexpr uint32_t idesc = make_idesc(128, B_NT, 1, 0);
@@ -545,6 +675,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       // gamma/beta Adam of tile li once its epilogue has left P, Q in shared memory
       const int buf = li & 1;
       mbar_wait(&tmem_empty[buf], (uint32_t)(li >> 1) & 1u);
+      if (fuse) return;  // the forward warp updates gamma / beta chunk by chunk
       const int64_t k = (t_begin + li) * B_NT + wb * 32 + lane;
       float P = 0.f, Q = 0.f;
 #pragma unroll
@@ -612,7 +743,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       vg_[buf] = vg;
       mb_[buf] = mb;
       vb_[buf] = vb;
-      sSc[buf * B_NT + wb * 32 + lane] = make_float4(valid ? rs * gm : 0.f, valid ? bt : 0.f, 0.f, 0.f);
+      sSc[buf * B_NT + wb * 32 + lane] = make_float4(valid ? rs * gm : 0.f, valid ? bt : 0.f, valid ? rs : 0.f, 0.f);
       float chi[3], clo[3];
 #pragma unroll
       for (int x = 0; x < 3; ++x) {
@@ -674,7 +805,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == B_EPI_WARPS) tmem_dealloc(tmem, 256);
+  if (warp == B_EPI_WARPS) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace tc
@@ -702,7 +833,7 @@ bool l1_tc_supported(int64_t K, int H) {
 }
 
 int l1_tc_partials(int64_t K) {
-  const int64_t ntiles = cdiv(K, tc::F_KT);
+  const int64_t ntiles = cdiv(K, tc::B_NT);
   return (int)(ntiles < tc_sm_count() ? ntiles : tc_sm_count());
 }
 
@@ -712,7 +843,7 @@ int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s) {
     LOC_CUDA(cudaFuncSetAttribute(tc::k_l1_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::F_SMEM));
     attr_set = true;
   }
-  const int64_t ntiles = cdiv(a.K, tc::F_KT);
+  const int64_t ntiles = cdiv(a.K, tc::B_NT);
   tc::k_l1_fwd_tc<<<n_partials, tc::F_THREADS, tc::F_SMEM, s>>>(a, ntiles);
   LOC_LAUNCHED();
   return 0;

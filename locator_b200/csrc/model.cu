@@ -196,6 +196,8 @@ static L1Args l1_args(loc_model* m, const uint32_t* packed, int64_t row_words, c
   a.packed = packed;
   a.row_words = row_words;
   a.src = src;
+  a.src_next = src;
+  a.fuse_next = 0;
   a.gamma = m->gamma;
   a.beta = m->beta;
   a.mmean = m->mmean;
@@ -248,9 +250,17 @@ static int forward_l1(loc_model* m, const L1Args& a, cudaStream_t s) {
 }
 
 // One optimizer step: 4 launches (stage_mask selects a subset for profiling / tests).
-static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s, int stage_mask = 15) {
+// `next` (tcgen05 path): rows of the following step -- the backward kernel then also runs that step's
+// first-layer forward on the W1 chunks it has just updated (they are still in shared memory), so the
+// following step is called with have_fwd = true and skips its own forward launch.
+static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s, int stage_mask = 15,
+                      const RowSrc* next = nullptr, bool have_fwd = false) {
   L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, gated);
-  if ((stage_mask & 1) && forward_l1(m, a, s)) return 1;
+  if (next != nullptr && m->use_tc) {
+    a.src_next = *next;
+    a.fuse_next = 1;
+  }
+  if ((stage_mask & 1) && !have_fwd && forward_l1(m, a, s)) return 1;
   HidArgs h = hid_args(m, src, 1, gated, m->train_locs, nullptr);
   if ((stage_mask & 2) && (m->hid_tc ? hidden_tc_launch(h, s) : hidden_launch(h, m->cluster, s))) return 1;
   // The small-layer update only needs the hidden kernel's outputs: it runs on a side stream next to
@@ -616,13 +626,14 @@ int loc_train_step(loc_model* m, const int32_t* d_rows, int32_t nb, void* stream
 
 int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t nb, void* stream) {
   LOC_CHECK(m != nullptr && m->train_packed != nullptr, "loc_debug_stage: no training data bound");
-  LOC_CHECK(stage >= 0 && stage < 4 && d_rows != nullptr && nb >= 1 && nb <= m->B, "loc_debug_stage: bad arguments");
+  LOC_CHECK(stage >= 0 && stage < 5 && d_rows != nullptr && nb >= 1 && nb <= m->B, "loc_debug_stage: bad arguments");
   RowSrc src;
   src.rows = d_rows;
   src.epoch_stride = 0;
   src.offset = 0;
   src.row0 = 0;
   src.nb = nb;
+  if (stage == 4) return train_step(m, src, 0, (cudaStream_t)stream, 4, &src);  // backward + fused next forward
   return train_step(m, src, 0, (cudaStream_t)stream, 1 << stage);
 }
 
@@ -656,15 +667,24 @@ int loc_train_epochs(loc_model* m, const int32_t* d_perms, int32_t n_epochs, voi
   cudaStream_t s = (cudaStream_t)stream;
   k_begin_call<<<1, 1, 0, s>>>(m->st);
   LOC_LAUNCHED();
+  const bool fuse = m->use_tc && getenv("LOC_NO_FUSE") == nullptr;
+  auto step_rows = [&](int64_t off) {
+    RowSrc src;
+    src.rows = d_perms;
+    src.epoch_stride = m->n_train;
+    src.offset = off;
+    src.row0 = 0;
+    src.nb = (int32_t)((m->n_train - off) < m->B ? (m->n_train - off) : m->B);
+    return src;
+  };
   for (int e = 0; e < n_epochs; ++e) {
+    bool have_fwd = false;  // the previous step's backward already left this step's Z1 partial tiles
     for (int64_t off = 0; off < m->n_train; off += m->B) {
-      RowSrc src;
-      src.rows = d_perms;
-      src.epoch_stride = m->n_train;
-      src.offset = off;
-      src.row0 = 0;
-      src.nb = (int32_t)((m->n_train - off) < m->B ? (m->n_train - off) : m->B);
-      if (train_step(m, src, 1, s)) return 1;
+      const RowSrc src = step_rows(off);
+      const bool has_next = fuse && off + m->B < m->n_train;  // within the epoch (the validation pass reuses the tiles)
+      const RowSrc next = has_next ? step_rows(off + m->B) : src;
+      if (train_step(m, src, 1, s, 15, has_next ? &next : nullptr, have_fwd)) return 1;
+      have_fwd = has_next;
     }
     if (infer_rows(m, m->val_packed, m->n_val, m->val_row_words, m->val_locs, nullptr, 1, s)) return 1;
     k_epoch_end<<<1, 1, 0, s>>>(m->st, m->hist);

@@ -63,6 +63,8 @@ struct L1Args {
   const uint32_t* packed;
   int64_t row_words;
   RowSrc src;
+  RowSrc src_next;  // rows of the following step (fused forward of the tcgen05 backward kernel)
+  int fuse_next;
   float *gamma, *beta, *mmean, *mvar;
   float* W1;
   float *m_gamma, *v_gamma, *m_beta, *v_beta, *mW1, *vW1;

@@ -22,6 +22,7 @@ def main():
     rng = np.random.default_rng(0)
     for s in range(nsteps):
         m.train_step(rng.permutation(ntr)[:32])
+    m.debug_stage(4, rng.permutation(ntr)[:32])  # the fused backward + next forward, as train_epochs runs it
     print("loss", m.state().last_loss, "val", m.evaluate(x[ntr:ntr + 32], y[ntr:ntr + 32]))
 
 

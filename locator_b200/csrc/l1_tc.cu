@@ -20,7 +20,7 @@
 // BACKWARD (k_l1_bwd_tc), one persistent CTA per SM, split over SNPs, 64 SNPs per tile:
 //   S[j, k] = sum_b dZ1[b, j] * (x[b, k] - mean_k)   M = 128 (two halves of j), N = 64 SNPs, K = 8 rows / MMA
 //   A = dZ1 as hi + lo tf32 parts (MN-major, swizzled, built once per CTA), B = centred genotypes
-//   (K-major, swizzled; exact in tf32 for a full batch, hi + lo otherwise) -> S is fp32-accurate.
+//   (K-major, swizzled; exact in tf32 for a power-of-two batch) -> S is fp32-accurate.
 //   W1, m, v never touch the load/store units' global path: a load thread streams 8-SNP chunks
 //   (3 x 8 KB, contiguous rows) into a 4-stage shared-memory ring with cp.async.bulk + mbarrier, the
 //   epilogue warps (accumulator row j = TMEM lane, so a warp reads/writes 128 contiguous bytes of a
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(L1Args a, int64_t nt
 // ---------------------------------------------------------------------------------------------
 constexpr int B_NT = 64;                       // SNPs per tile (one accumulator buffer)
 constexpr int B_CH = 8;                        // SNPs per streamed chunk (one W/m/v stage)
-constexpr int B_STAGES = 4;
+constexpr int B_STAGES = 5;
 constexpr int B_EPI_WARPS = 16;                // two groups of 8: group g owns the chunks with index % 2 == g
 constexpr int B_THREADS = (B_EPI_WARPS + 6) * 32;  // + 2 builder warps, load warp, store warp, 2 forward warps
 constexpr int B_DZ = kMaxB * kH * 4;           // 32 KB: [8 chunks][32 rows (b)][128 B]
@@ -355,7 +355,7 @@ constexpr int B_X = B_NT * 128;                // 8 KB: [64 rows (SNP)][32 batch
 constexpr int B_ARR = B_CH * kH * 4;           // 8 KB: one array's rows of a chunk
 constexpr int B_STAGE = 3 * B_ARR;             // 24 KB: W | m | v
 constexpr int B_XF = 8 * 128;                  // 1 KB: next batch's xhat rows of one chunk [8 SNP rows][32 batch]
-constexpr int B_SMEM = 2 * B_DZ + 4 * B_X + B_STAGES * (B_STAGE + B_XF) + 2 * B_NT * 16 + 2 * 8 * B_NT * 8 + 2 * 32 * 8 + 512 + 1024;
+constexpr int B_SMEM = 2 * B_DZ + 2 * B_X + B_STAGES * (B_STAGE + B_XF) + 2 * B_NT * 16 + 2 * 8 * B_NT * 8 + 2 * 32 * 8 + 512 + 1024;
 
 __device__ __forceinline__ void adam_update_fast(float& w, float& m, float& v, float g, float alpha) {
   m = m + (g - m) * kAdam1mB1;
@@ -380,8 +380,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   uint8_t* sDZhi = sm;
   uint8_t* sDZlo = sDZhi + B_DZ;
   uint8_t* sXhi = sDZlo + B_DZ;                  // [2][B_X]
-  uint8_t* sXlo = sXhi + 2 * B_X;                // [2][B_X]
-  uint8_t* sStage = sXlo + 2 * B_X;              // [B_STAGES][W | m | v][8 rows][256]
+  uint8_t* sStage = sXhi + 2 * B_X;              // [B_STAGES][W | m | v][8 rows][256]
   uint8_t* sXf = sStage + B_STAGES * B_STAGE;    // [B_STAGES][1 KB] forward B operand of the chunk in the stage
   float4* sSc = (float4*)(sXf + B_STAGES * B_XF);  // [2][64] (inv, beta, rs, -)
   float2* sRed = (float2*)(sSc + 2 * B_NT);      // [2][8 warps][64] (P, Q) partial sums
@@ -398,7 +397,6 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = a.src.nb;
   const bool fuse = a.fuse_next != 0;  // also run the NEXT step's forward on the freshly updated chunks
-  const bool need_lo = (nb & (nb - 1)) != 0;  // centred genotypes are multiples of 1/nb: exact in tf32 iff nb = 2^n
   const int64_t t_begin = ntiles * blockIdx.x / gridDim.x;
   const int64_t t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
   const int nloc = (int)(t_end - t_begin);
@@ -533,6 +531,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     }
   } else if (warp == B_EPI_WARPS + 3) {
     // =========================== store warp: updated chunk -> W, m, v ===========================
+    // two bulk-store groups in flight: a stage is released once the store issued before the latest
+    // one has finished reading shared memory
     if (elect_one()) {
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % B_STAGES;
@@ -543,9 +543,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
         bulk_store(a.mW1 + off, src + B_ARR, B_ARR);
         bulk_store(a.vW1 + off, src + 2 * B_ARR, B_ARR);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        mbar_arrive(&st_free[s]);
+        if (c > 0) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          mbar_arrive(&st_free[(c - 1) % B_STAGES]);
+        }
       }
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      mbar_arrive(&st_free[(nchunks - 1) % B_STAGES]);
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp >= B_EPI_WARPS + 4) {
@@ -744,40 +748,32 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       mb_[buf] = mb;
       vb_[buf] = vb;
       sSc[buf * B_NT + wb * 32 + lane] = make_float4(valid ? rs * gm : 0.f, valid ? bt : 0.f, valid ? rs : 0.f, 0.f);
-      float chi[3], clo[3];
+      // centred genotypes are multiples of 1/nb: exact in tf32 for a power-of-two batch (the usual 32);
+      // a ragged last batch rounds them to tf32 (10-bit mantissa), like every other tf32 product here
+      float chi[3];
 #pragma unroll
-      for (int x = 0; x < 3; ++x) {
-        const float cx = valid ? (float)x - mean : 0.f;
-        chi[x] = to_tf32(cx);
-        clo[x] = to_tf32(cx - chi[x]);
-      }
+      for (int x = 0; x < 3; ++x) chi[x] = to_tf32(valid ? (float)x - mean : 0.f);
       const int r = wb * 32 + lane;
       uint8_t* xh = sXhi + buf * B_X;
-      uint8_t* xl = sXlo + buf * B_X;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        float vh[4], vl[4];
+        float vh[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int b = 4 * c + e;
           const unsigned x = (unsigned)((g >> (2 * b)) & 3ull);
-          const bool on = b < nb;
-          float h = chi[0], l = clo[0];  // branch-free select
+          float h = chi[0];  // branch-free select
           h = x == 1u ? chi[1] : h;
-          l = x == 1u ? clo[1] : l;
           h = x == 2u ? chi[2] : h;
-          l = x == 2u ? clo[2] : l;
-          vh[e] = on ? h : 0.f;
-          vl[e] = on ? l : 0.f;
+          vh[e] = b < nb ? h : 0.f;
         }
         *reinterpret_cast<float4*>(xh + swz(r, c)) = make_float4(vh[0], vh[1], vh[2], vh[3]);
-        if (need_lo) *reinterpret_cast<float4*>(xl + swz(r, c)) = make_float4(vl[0], vl[1], vl[2], vl[3]);
       }
       fence_proxy_async();
       asm volatile("bar.sync 1, 64;" ::: "memory");  // both builder warps have written their half
       if (wb == 0 && lane == 0) {
         tc_fence_after();
-        const uint32_t xhb = smem_u32(xh), xlb = smem_u32(xl);
+        const uint32_t xhb = smem_u32(xh);
         const uint32_t dhi = smem_u32(sDZhi), dlo = smem_u32(sDZlo);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -791,10 +787,6 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
             umma_tf32(d, a_hi, b_hi, idesc, acc);
             acc = 1u;
             umma_tf32(d, a_lo, b_hi, idesc, acc);
-            if (need_lo) {
-              const uint64_t b_lo = smem_desc(xlb + ks * 32, 16, 1024, kLayoutSw128);
-              umma_tf32(d, a_hi, b_lo, idesc, acc);
-            }
           }
         }
         umma_commit(&tmem_full[buf]);

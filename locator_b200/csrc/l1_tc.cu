@@ -357,10 +357,15 @@ constexpr int B_STAGE = 3 * B_ARR;             // 24 KB: W | m | v
 constexpr int B_XF = 8 * 128;                  // 1 KB: next batch's xhat rows of one chunk [8 SNP rows][32 batch]
 constexpr int B_SMEM = 2 * B_DZ + 2 * B_X + B_STAGES * (B_STAGE + B_XF) + 2 * B_NT * 16 + 2 * 8 * B_NT * 8 + 2 * 32 * 8 + 512 + 1024;
 
+// Keras Adam with hardware approximations for the root and the quotient (both ~1 ulp of fp32:
+// far below the tf32 rounding of the gradient products; the IEEE sqrt was 27% of this kernel's
+// instruction stream)
 __device__ __forceinline__ void adam_update_fast(float& w, float& m, float& v, float g, float alpha) {
   m = m + (g - m) * kAdam1mB1;
   v = v + (g * g - v) * kAdam1mB2;
-  w = w - __fdividef(m * alpha, sqrtf(v) + kAdamEps);
+  float rt;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(rt) : "f"(v));
+  w = w - __fdividef(m * alpha, rt + kAdamEps);
 }
 
 __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

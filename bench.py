@@ -17,6 +17,7 @@ CUDA events.  `cpu_baseline` times the oracle (torch-CPU fp32 restatement of the
 not installable on this image) on a bounded number of steps.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -195,6 +196,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=100)
+    ap.add_argument("--group", type=int, default=4, help="replicates per GPU for the lockstep-group measurement (0/1 = skip)")
     args = ap.parse_args()
     workload = args.workload
     if args.impl == "reference":
@@ -366,6 +368,36 @@ def main():
                "what": "LocatorModel.fit on host uint8 matrices: H2D, 2-bit pack, epochs incl. validation, history D2H"}
         del m2
 
+    # ---- replicate group: G independent models advanced in lockstep on this GPU (bootstrap / windows) ----
+    group = None
+    if m.impl == "tcgen05" and args.group > 1:
+        G = args.group
+        gm = [m] + [model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=n_ep_total + 2,
+                                       seed=500 + rank * 16 + g) for g in range(1, G)]
+        for q in gm[1:]:
+            q.bind_train(gtr, ytr)
+            q.bind_val(m._keep["val"][0], yva)
+            q.set_schedule(patience=10 ** 6)
+        ne_g = max(2, min(6, steps // spe))
+        perms_g = [torch.as_tensor(np.stack([rng.permutation(ntr) for _ in range(ne_g + 1)]).astype(np.int32)).cuda()
+                   for _ in range(G)]
+        handles = (ctypes.c_void_p * G)(*[q._h for q in gm])
+
+        def run_group(ne, skip):
+            pp = (ctypes.c_void_p * G)(*[p.data_ptr() + skip * ntr * 4 for p in perms_g])
+            _cabi.check(lib.loc_group_train_epochs(handles, G, pp, ne, stream), "loc_group_train_epochs")
+        run_group(1, 0)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        run_group(ne_g, 1)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = max_over_ranks(g0.elapsed_time(g1), "cuda")
+        group = {"replicates_per_gpu": G, "epochs": ne_g, "value": world * G * ne_g * ntr / (gms / 1000.0),
+                 "unit": "samples/s (all replicates)", "ms_per_step_per_replicate": gms / (ne_g * spe * G),
+                 "what": "loc_group_train_epochs: hidden stacks of the G replicates share one launch"}
+
     line = {
         "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps,
         "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -376,6 +408,7 @@ def main():
                    "l2": "inputs larger than L2 (W1+m+v = %.0f MB per step)" % (12.0 * K * H / 1e6),
                    "steps_per_epoch": spe, "validation_pass_every_epoch": True},
         "clocks": clk.summary(), "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
+        "replicate_group": group,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, dt = cpu_steps(xtr, ytr, xva, yva, args.cpu_steps, os.cpu_count() or 1)

@@ -166,6 +166,14 @@ int loc_train_step(loc_model* m, const int32_t* d_rows, int32_t nb, void* stream
  * no-ops.  History rows are appended per epoch. */
 int loc_train_epochs(loc_model* m, const int32_t* d_perms, int32_t n_epochs, void* stream);
 
+/* Replicate group (bootstrap / window models trained side by side on one GPU): the same as
+ * loc_train_epochs for n_models <= 8 independent models advanced in lockstep -- their hidden stacks
+ * run in one launch (one cluster per model) so that they overlap instead of each leaving most SMs
+ * idle; first-layer kernels run back to back.  Models must share nlayers, batch size and
+ * training-set size (true for the replicates of one run); d_perms[g] is model g's batch order. */
+int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* const* d_perms, int32_t n_epochs,
+                           void* stream);
+
 /* Mean Euclidean loss (Keras evaluate semantics, batch 32) in inference mode.
  * Synchronises; result in *h_loss. */
 int loc_eval(loc_model* m, const uint32_t* d_packed, int64_t n, int64_t row_words, const float* d_locs,

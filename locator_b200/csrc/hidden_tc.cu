@@ -84,7 +84,7 @@ __device__ __forceinline__ uint32_t b_off(int b, int k) {
   return (uint32_t)((k >> 5) * 1024 + b * 128 + ((((k & 31) >> 2) ^ b) << 4) + ((k & 3) << 2));
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_hidden_tc(HidArgs a) {
+__device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   if (a.gated && a.st->stopped) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -451,6 +451,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_hidden_tc(HidArgs a) {
   }
 }
 
+__global__ void __launch_bounds__(kThreads, 1) k_hidden_tc(HidArgs a) { hidden_tc_body(a); }
+
+// Several independent models (replicates) in one launch: cluster c runs model c.  The models' steps
+// are issued in lockstep by loc_group_train_epochs, so their latency-bound hidden stacks overlap on
+// different SMs instead of each idling 132 of them.
+__global__ void __launch_bounds__(kThreads, 1) k_hidden_tc_group(HidGroupArgs g) { hidden_tc_body(g.a[blockIdx.x / kC]); }
+
 __global__ void k_reslice_tc(const float* __restrict__ small, float* fs, float* bs, int L) {
   const SmallLayout sl{kH, L};
   const int64_t n = (int64_t)(L - 1) * kH * kH;
@@ -490,6 +497,32 @@ static int launch_tc(const HidArgs& a, cudaStream_t s, bool dry) {
     return n;
   }
   LOC_CUDA(cudaLaunchKernelEx(&cfg, htc::k_hidden_tc, a));
+  loc::g_launches.fetch_add(1);
+  return 0;
+}
+
+int hidden_tc_group_launch(const HidGroupArgs& g, cudaStream_t s) {
+  LOC_CHECK(g.n >= 1 && g.n <= kMaxGroup, "hidden stack group: bad group size");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(htc::kC * g.n);
+  cfg.blockDim = dim3(htc::kThreads);
+  cfg.dynamicSmemBytes = htc::smem_bytes(g.a[0].L);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = htc::kC;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(htc::k_hidden_tc_group, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    attr_set = true;
+  }
+  LOC_CUDA(cudaFuncSetAttribute(htc::k_hidden_tc_group, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)cfg.dynamicSmemBytes));
+  LOC_CUDA(cudaLaunchKernelEx(&cfg, htc::k_hidden_tc_group, g));
   loc::g_launches.fetch_add(1);
   return 0;
 }

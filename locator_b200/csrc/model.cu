@@ -249,6 +249,26 @@ static int forward_l1(loc_model* m, const L1Args& a, cudaStream_t s) {
   return m->use_tc ? l1_forward_tc(a, m->n_partials, s) : l1_forward_simt(a, m->n_partials, s);
 }
 
+static UpdArgs upd_args(loc_model* m, int nb, int gated) {
+  UpdArgs u;
+  u.H = m->H;
+  u.L = m->L;
+  u.gated = gated;
+  u.small = m->small;
+  u.m_small = m->m_small;
+  u.v_small = m->v_small;
+  u.w_fs = m->w_fs;
+  u.w_bs = m->w_bs;
+  u.Hc = m->H / m->cluster;
+  u.slice_mode = m->hid_tc;
+  u.acts = m->acts;
+  u.dzs = m->dzs;
+  u.outs = m->outs;
+  u.nb = nb;
+  u.st = m->st;
+  return u;
+}
+
 // One optimizer step: 4 launches (stage_mask selects a subset for profiling / tests).
 // `next` (tcgen05 path): rows of the following step -- the backward kernel then also runs that step's
 // first-layer forward on the W1 chunks it has just updated (they are still in shared memory), so the
@@ -277,22 +297,7 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
       return 1;
     return 0;
   }
-  UpdArgs u;
-  u.H = m->H;
-  u.L = m->L;
-  u.gated = gated;
-  u.small = m->small;
-  u.m_small = m->m_small;
-  u.v_small = m->v_small;
-  u.w_fs = m->w_fs;
-  u.w_bs = m->w_bs;
-  u.Hc = m->H / m->cluster;
-  u.slice_mode = m->hid_tc;
-  u.acts = m->acts;
-  u.dzs = m->dzs;
-  u.outs = m->outs;
-  u.nb = src.nb;
-  u.st = m->st;
+  UpdArgs u = upd_args(m, src.nb, gated);
   if (hidden_update_launch(u, su)) return 1;
   if (fork) LOC_CUDA(cudaEventRecord(m->ev_upd, m->side));
   if ((stage_mask & 4) &&
@@ -635,6 +640,84 @@ int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t 
   src.nb = nb;
   if (stage == 4) return train_step(m, src, 0, (cudaStream_t)stream, 4, &src);  // backward + fused next forward
   return train_step(m, src, 0, (cudaStream_t)stream, 1 << stage);
+}
+
+int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* const* d_perms, int32_t n_epochs,
+                           void* stream) {
+  LOC_CHECK(models != nullptr && d_perms != nullptr && n_models >= 1 && n_models <= kMaxGroup && n_epochs >= 1,
+            "loc_group_train_epochs: bad arguments");
+  loc_model* m0 = models[0];
+  for (int g = 0; g < n_models; ++g) {
+    loc_model* m = models[g];
+    LOC_CHECK(m != nullptr && d_perms[g] != nullptr && m->train_packed != nullptr && m->val_packed != nullptr,
+              "loc_group_train_epochs: every model needs bound training / validation data and a batch order");
+    LOC_CHECK(m->hid_tc && m->use_tc, "loc_group_train_epochs: grouped replicates need the tcgen05 kernels (width 256)");
+    LOC_CHECK(m->L == m0->L && m->B == m0->B && m->n_train == m0->n_train,
+              "loc_group_train_epochs: replicates of a group must share nlayers, batch size and training-set size");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int g = 0; g < n_models; ++g) {
+    k_begin_call<<<1, 1, 0, s>>>(models[g]->st);
+    LOC_LAUNCHED();
+  }
+  auto step_rows = [&](int g, int64_t off) {
+    RowSrc src;
+    src.rows = d_perms[g];
+    src.epoch_stride = m0->n_train;
+    src.offset = off;
+    src.row0 = 0;
+    src.nb = (int32_t)((m0->n_train - off) < m0->B ? (m0->n_train - off) : m0->B);
+    return src;
+  };
+  for (int e = 0; e < n_epochs; ++e) {
+    bool have_fwd = false;
+    for (int64_t off = 0; off < m0->n_train; off += m0->B) {
+      const bool has_next = off + m0->B < m0->n_train;
+      HidGroupArgs hg;
+      hg.n = n_models;
+      // first-layer forwards (first step of the epoch only: later ones are fused into the backward)
+      for (int g = 0; g < n_models; ++g) {
+        loc_model* m = models[g];
+        const RowSrc src = step_rows(g, off);
+        if (!have_fwd) {
+          L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, 1);
+          if (forward_l1(m, a, s)) return 1;
+        }
+        hg.a[g] = hid_args(m, src, 1, 1, m->train_locs, nullptr);
+      }
+      // all hidden stacks in one launch: one cluster per replicate
+      if (hidden_tc_group_launch(hg, s)) return 1;
+      // small-layer updates on the side streams, first-layer backward (+ next forward) back to back
+      LOC_CUDA(cudaEventRecord(m0->ev_hid, s));
+      for (int g = 0; g < n_models; ++g) {
+        loc_model* m = models[g];
+        LOC_CUDA(cudaStreamWaitEvent(m->side, m0->ev_hid, 0));
+        UpdArgs u = upd_args(m, hg.a[g].src.nb, 1);
+        if (hidden_update_launch(u, m->side)) return 1;
+        LOC_CUDA(cudaEventRecord(m->ev_upd, m->side));
+      }
+      for (int g = 0; g < n_models; ++g) {
+        loc_model* m = models[g];
+        const RowSrc src = step_rows(g, off);
+        L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, 1);
+        if (has_next) {
+          a.src_next = step_rows(g, off + m0->B);
+          a.fuse_next = 1;
+        }
+        if (l1_backward_tc(a, m->n_bwd_blocks, s)) return 1;
+      }
+      for (int g = 0; g < n_models; ++g) LOC_CUDA(cudaStreamWaitEvent(s, models[g]->ev_upd, 0));
+      have_fwd = has_next;
+    }
+    for (int g = 0; g < n_models; ++g) {
+      loc_model* m = models[g];
+      if (infer_rows(m, m->val_packed, m->n_val, m->val_row_words, m->val_locs, nullptr, 1, s)) return 1;
+      k_epoch_end<<<1, 1, 0, s>>>(m->st, m->hist);
+      LOC_LAUNCHED();
+      if (copy_weights(m, true, &m->st->improved, s)) return 1;
+    }
+  }
+  return 0;
 }
 
 int64_t loc_debug_read(loc_model* m, int32_t which, float* h_dst, int64_t max_n, void* stream) {

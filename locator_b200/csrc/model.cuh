@@ -99,6 +99,12 @@ struct HidArgs {
   DevState* st;
 };
 
+constexpr int kMaxGroup = 8;  // replicates per grouped hidden-stack launch
+struct HidGroupArgs {
+  int n;
+  HidArgs a[kMaxGroup];
+};
+
 struct UpdArgs {
   int H, L;
   int gated;
@@ -126,6 +132,7 @@ size_t hidden_smem_bytes(int H, int L, int cluster);
 // tcgen05 hidden stack (hidden_tc.cu): width 256, 16-CTA cluster
 bool hidden_tc_supported(int H, int L);
 int hidden_tc_launch(const HidArgs& a, cudaStream_t s);
+int hidden_tc_group_launch(const HidGroupArgs& g, cudaStream_t s);
 int hidden_tc_reslice(const float* small, float* fs, float* bs, int L, cudaStream_t s);
 
 // tcgen05 first layer (l1_tc.cu); available() is false when the shape is unsupported.

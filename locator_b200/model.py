@@ -229,6 +229,15 @@ class LocatorModel:
         h.epoch = list(range(st.epoch))
         return h
 
+    def _history(self, n_epochs):
+        h = History()
+        rows = self.history_rows(n_epochs)
+        h.history["loss"] = [float(v) for v in rows[:, 0]]
+        h.history["val_loss"] = [float(v) for v in rows[:, 1]]
+        h.history["learning_rate"] = [float(v) for v in rows[:, 2]]
+        h.epoch = list(range(n_epochs))
+        return h
+
     def restore_best(self):
         check(lib.loc_restore_best(self._h, _stream()), "loc_restore_best")
 
@@ -250,3 +259,54 @@ class LocatorModel:
         loss = C.c_float()
         check(lib.loc_eval(self._h, g.ptr, g.n, g.row_words, locs.data_ptr(), C.byref(loss), _stream()), "loc_eval")
         return float(loss.value)
+
+
+MAX_GROUP = 8
+
+
+def fit_group(models, xs, ys, validation_datas, epochs=None, patience=100, verbose=0, epochs_per_call=16):
+    """Train up to 8 independent models (replicates) side by side on one GPU.
+
+    Same semantics per model as ``LocatorModel.fit`` (each model keeps its own shuffle stream,
+    callbacks state and history); the steps are issued in lockstep through
+    ``loc_group_train_epochs`` so the models' latency-bound hidden stacks share one launch.  Models
+    must have the same nlayers / batch size / number of training rows (replicates of one run do).
+    Returns the list of History objects.
+    """
+    G = len(models)
+    if not 1 <= G <= MAX_GROUP:
+        raise ValueError(f"a replicate group holds 1..{MAX_GROUP} models")
+    epochs = min(m.max_epochs for m in models) if epochs is None else int(epochs)
+    rngs = []
+    for m, x, y, vd in zip(models, xs, ys, validation_datas):
+        m.bind_train(x, y)
+        m.bind_val(*vd)
+        m.set_schedule(patience=patience)
+        rngs.append(np.random.default_rng(m.seed))
+        m._keep["perms"] = []
+    n = models[0]._keep["train"][0].n
+    done = 0
+    states = [m.state() for m in models]
+    while done < epochs:
+        active = [i for i in range(G) if not states[i].stopped]
+        if not active:
+            break
+        ne = min(epochs_per_call, epochs - done)
+        perms = []
+        for i in active:
+            p = _as_dev(np.stack([rngs[i].permutation(n) for _ in range(ne)]).astype(np.int32), torch.int32)
+            models[i]._keep["perms"] = [p]
+            perms.append(p)
+        handles = (C.c_void_p * len(active))(*[models[i]._h for i in active])
+        pptrs = (C.c_void_p * len(active))(*[p.data_ptr() for p in perms])
+        check(lib.loc_group_train_epochs(handles, len(active), pptrs, ne, _stream()), "loc_group_train_epochs")
+        done += ne
+        for i in active:
+            states[i] = models[i].state()
+        if verbose:
+            print(f"epoch {done}: " + " ".join(f"[{i}] val {states[i].last_val_loss:.4f}" for i in active))
+    out = []
+    for m, st in zip(models, states):
+        m.stop_training = bool(st.stopped)
+        out.append(m._history(st.epoch))
+    return out

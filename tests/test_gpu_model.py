@@ -211,3 +211,30 @@ def test_step_invariants_full_width(M):
     assert dW.max() < 3.2e-3 + 1e-6 and dW.max() > 1e-4
     # SNPs that are constant inside every batch have zero-variance columns: finite, bounded update
     assert np.all(np.isfinite(w1[0])) and np.all(np.isfinite(w1[1]))
+
+
+def test_group_training_matches_individual_training(M):
+    """Replicate group (loc_group_train_epochs): each model of a lockstep group ends bit-identical to the
+    same model trained alone -- the grouped hidden-stack launch only changes scheduling."""
+    rng = np.random.default_rng(12)
+    K, ntr, nva, epochs = 3000, 75, 20, 5
+    datas = []
+    for g in range(3):
+        x, y = _data(rng, ntr, K)
+        xv, yv = _data(rng, nva, K)
+        datas.append((x, y, xv, yv))
+    solo = []
+    for g, (x, y, xv, yv) in enumerate(datas):
+        m = M.LocatorModel(K, seed=40 + g, max_epochs=epochs)
+        h = m.fit(x, y, epochs=epochs, validation_data=(xv, yv), patience=2 if g == 1 else 100, epochs_per_call=2)
+        solo.append((h, m.predict(xv), m.get_weights()[4]))
+    ms = [M.LocatorModel(K, seed=40 + g, max_epochs=epochs) for g in range(3)]
+    if ms[0].impl != "tcgen05":
+        pytest.skip("replicate groups need the tcgen05 kernels")
+    # one patience for the whole group: compare the model with patience 100 semantics only where equal
+    hs = M.fit_group(ms[::2], [d[0] for d in datas[::2]], [d[1] for d in datas[::2]],
+                     [(d[2], d[3]) for d in datas[::2]], epochs=epochs, patience=100, epochs_per_call=2)
+    for (h, yp, w), m, hg, d in zip(solo[::2], ms[::2], hs, datas[::2]):
+        assert hg.history["loss"] == h.history["loss"] and hg.history["val_loss"] == h.history["val_loss"]
+        assert np.array_equal(m.predict(d[2]), yp)
+        assert np.array_equal(m.get_weights()[4], w)

@@ -52,6 +52,7 @@ class PackedGenotypes:
         self.n = int(n)
         self.K = int(K)
         self.row_words = int(words.shape[1]) if words.dim() == 2 else row_words_for(K)
+        self.version = 0  # bumped by the in-place edits (replace_cols / patch)
 
     @property
     def ptr(self):
@@ -124,6 +125,7 @@ class PackedGenotypes:
         assert v.shape == (s.numel(), self.n)
         check(lib.loc_replace_cols(self.ptr, self.n, self.row_words, s.data_ptr(), int(s.numel()), v.data_ptr(),
                                    _stream()), "loc_replace_cols")
+        self.version += 1
 
     def patch(self, ks, samps, vals) -> None:
         """self[samps[i], ks[i]] = vals[i]  (imputed calls of replace_md :258-261)."""
@@ -132,6 +134,7 @@ class PackedGenotypes:
         v = _as_dev(np.asarray(vals, dtype=np.uint8), torch.uint8)
         check(lib.loc_patch_calls(self.ptr, self.row_words, k.data_ptr(), s.data_ptr(), v.data_ptr(), int(k.numel()),
                                   _stream()), "loc_patch_calls")
+        self.version += 1
 
 
 def site_stats(gt, min_mac=2):

@@ -21,8 +21,9 @@ Differences that are deliberate and documented in DESIGN.md:
     reference) come from Philox streams keyed by ``--seed``;
   * weights files are ``.weights.npz`` (no HDF5 on this image) and only exist with --keep_weights
     (the best-epoch checkpoint lives in device memory, not on disk);
-  * ``--gpus N`` (extension, not written to params.json) spreads --bootstrap / --windows
-    replicates over N GPUs of the box with a work queue (locator_b200.replicates).
+  * ``--gpus N`` and ``--replicates_per_gpu G`` (extensions, not written to params.json): --bootstrap /
+    --windows replicates are spread over N GPUs of the box with a work queue, G models trained side
+    by side on each GPU (locator_b200.replicates); results do not depend on either.
 """
 from __future__ import annotations
 
@@ -93,6 +94,9 @@ def build_parser():
     # extension of this build (kept out of params.json)
     parser.add_argument("--gpus", default=1, type=int,
                         help="(locator_b200) GPUs of this box to spread --bootstrap / --windows replicates over. default: 1")
+    parser.add_argument("--replicates_per_gpu", default=4, type=int,
+                        help="(locator_b200) bootstrap / window models trained side by side on each GPU (1-8; results "
+                        "do not depend on it). default: 4")
     return parser
 
 
@@ -399,10 +403,10 @@ def main(argv=None):
     if args.gpu_number is not None:
         os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu_number
     if args.load_params is not None:
-        gpus = args.gpus
+        gpus, rpg = args.gpus, args.replicates_per_gpu
         with open(args.load_params, "r") as f:
             args.__dict__ = json.load(f)
-        args.gpus = gpus
+        args.gpus, args.replicates_per_gpu = gpus, rpg
     if args.out is None:
         raise SystemExit("--out is required")
     _write_params()

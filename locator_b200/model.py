@@ -41,6 +41,8 @@ class LocatorModel:
         self._h = h
         check(lib.loc_model_init(self._h, self.seed, _stream()), "loc_model_init")
         self._keep = {}  # device tensors the handle points at
+        self._wver = 0   # bumped whenever the weights may have changed (prediction memo key)
+        self._memo = {}
         self.stop_training = False
 
     def __del__(self):
@@ -79,6 +81,7 @@ class LocatorModel:
         return out
 
     def set_weights(self, ws):
+        self._wver += 1
         if len(ws) != self.num_weights():
             raise ValueError(f"expected {self.num_weights()} weight arrays, got {len(ws)}")
         for i, w in enumerate(ws):
@@ -149,11 +152,13 @@ class LocatorModel:
         return st
 
     def train_step(self, rows):
+        self._wver += 1
         r = _as_dev(np.asarray(rows, dtype=np.int32), torch.int32)
         self._keep["rows"] = r
         check(lib.loc_train_step(self._h, r.data_ptr(), int(r.numel()), _stream()), "loc_train_step")
 
     def debug_stage(self, stage, rows):
+        self._wver += 1
         """Launch one stage (0 fwd-L1, 1 hidden, 2 bwd-L1, 3 small update) of a step on `rows`."""
         r = _as_dev(np.asarray(rows, dtype=np.int32), torch.int32)
         self._keep["rows"] = r
@@ -169,6 +174,7 @@ class LocatorModel:
         return a.reshape(-1, 32, self.width)
 
     def train_epochs(self, perms):
+        self._wver += 1
         """perms int32 [n_epochs, n_train]; enqueues the epochs (asynchronous)."""
         p = _as_dev(np.asarray(perms, dtype=np.int32), torch.int32)
         self._keep.setdefault("perms", []).append(p)
@@ -239,6 +245,7 @@ class LocatorModel:
         return h
 
     def restore_best(self):
+        self._wver += 1
         check(lib.loc_restore_best(self._h, _stream()), "loc_restore_best")
 
     def snapshot(self):
@@ -249,9 +256,17 @@ class LocatorModel:
         g = self._packed(x)
         if g.K != self.K:
             raise ValueError(f"matrix has {g.K} SNPs, model expects {self.K}")
+        # the reference re-predicts the unchanged validation set for every jacknife replicate
+        # (locator.py:441 inside :729-743): same weights + same device matrix -> same answer
+        key = (id(g), g.version, self._wver) if isinstance(x, PackedGenotypes) else None
+        if key is not None and self._memo.get("key") == key:
+            return self._memo["val"].copy()
         out = torch.zeros((g.n, 2), dtype=torch.float32, device=_dev())
         check(lib.loc_predict(self._h, g.ptr, g.n, g.row_words, out.data_ptr(), _stream()), "loc_predict")
-        return out.cpu().numpy()
+        res = out.cpu().numpy()
+        if key is not None:
+            self._memo = {"key": key, "val": res.copy(), "ref": g}
+        return res
 
     def evaluate(self, x, y, verbose=0):
         g = self._packed(x)
@@ -300,6 +315,8 @@ def fit_group(models, xs, ys, validation_datas, epochs=None, patience=100, verbo
         handles = (C.c_void_p * len(active))(*[models[i]._h for i in active])
         pptrs = (C.c_void_p * len(active))(*[p.data_ptr() for p in perms])
         check(lib.loc_group_train_epochs(handles, len(active), pptrs, ne, _stream()), "loc_group_train_epochs")
+        for i in active:
+            models[i]._wver += 1
         done += ne
         for i in active:
             states[i] = models[i].state()

@@ -40,38 +40,79 @@ def draw_bootstrap_orders(nsites, nboots):
     return orders
 
 
-def _run_item(L, item, base):
-    """Train + predict one replicate inside the current process / on the current device."""
+def _prepare(L, item, base):
+    """Work item -> dict with the replicate's matrices, targets and output naming."""
     args = L.args
-    kind = item["kind"]
-    if kind == "boot":
-        traingen, testgen, predgen = base["traingen"], base["testgen"], base["predgen"]
+    if item["kind"] == "boot":
         order = item["site_order"]
-        tg, vg, pg = traingen.take_cols(order), testgen.take_cols(order), predgen.take_cols(order)
-        L._seed_tag[0] = item["boot"] + 1
         print("starting bootstrap " + str(item["boot"]))
-        L._run_one(tg, vg, base["trainlocs"], base["testlocs"], pg, base["norm"], base["pred"], base["samples"],
-                   item["boot"], item["boot"])
-    elif kind == "window":
-        t1 = time.time()
-        L._seed_tag[0] = item["index"] + 1
+        return {"traingen": base["traingen"].take_cols(order), "testgen": base["testgen"].take_cols(order),
+                "predgen": base["predgen"].take_cols(order), "trainlocs": base["trainlocs"],
+                "testlocs": base["testlocs"], "norm": base["norm"], "pred": base["pred"], "samples": base["samples"],
+                "boot": item["boot"], "cb_boot": item["boot"], "seed_tag": item["boot"] + 1, "out": args.out}
+    if item["kind"] == "window":
+        return {"traingen": item["traingen"], "testgen": item["testgen"], "predgen": item["predgen"],
+                "trainlocs": item["trainlocs"], "testlocs": item["testlocs"], "norm": item["norm"],
+                "pred": item["pred"], "samples": item["samples"], "boot": 0, "cb_boot": None,
+                "seed_tag": item["index"] + 1, "out": item["window_out"]}
+    raise ValueError(item["kind"])
+
+
+def _run_items(L, items, base):
+    """Train + predict a list of replicates inside the current process / on the current device.
+
+    One replicate: the reference's sequence (load_network, train_network, predict_locs).  Several:
+    the models are trained side by side as one lockstep group (model.fit_group; results are
+    bit-identical to training them one after the other), then predicted one by one.
+    """
+    from .model import fit_group
+
+    args = L.args
+    t1 = time.time()
+    reps = [_prepare(L, it, base) for it in items]
+    models, callbacks = [], []
+    for rep in reps:
+        L._seed_tag[0] = rep["seed_tag"]
         original_out = args.out
-        args.out = item["window_out"]  # predict_locs / history use the window-specific stem (locator.py:555-557)
+        args.out = rep["out"]  # window runs: file names derive from the window-specific stem (locator.py:555-557)
         try:
-            model = L.load_network(item["traingen"], args.dropout_prop)
-            callbacks = L.load_callbacks(None)
-            history, model = L.train_network(model, item["traingen"], item["testgen"], item["trainlocs"],
-                                             item["testlocs"], callbacks)
-            meanlong, sdlong, meanlat, sdlat = item["norm"]
-            dists = L.predict_locs(model, item["predgen"], sdlong, meanlong, sdlat, meanlat, item["testlocs"],
-                                   item["pred"], item["samples"], item["testgen"], history)
+            models.append(L.load_network(rep["traingen"], args.dropout_prop))
+            callbacks.append(L.load_callbacks(rep["cb_boot"]))
+        finally:
+            args.out = original_out
+    same = len({(r["traingen"].n, m.nlayers, m.batch_size) for r, m in zip(reps, models)}) == 1
+    if len(reps) > 1 and same and all(m.impl == "tcgen05" for m in models):
+        start = time.time()
+        histories = fit_group(models, [r["traingen"] for r in reps], [r["trainlocs"] for r in reps],
+                              [(r["testgen"], r["testlocs"]) for r in reps], epochs=args.max_epochs,
+                              patience=args.patience, verbose=1 if args.keras_verbose == 2 else 0)
+        for m, cb in zip(models, callbacks):
+            m.restore_best()
+            if args.keep_weights:
+                m.save_weights(cb[0].filepath)
+        print("run time " + str((time.time() - start) / 60) + " minutes (" + str(len(reps)) + " replicates side by side)")
+    else:
+        histories = []
+        for m, cb, rep in zip(models, callbacks, reps):
+            h, _ = L.train_network(m, rep["traingen"], rep["testgen"], rep["trainlocs"], rep["testlocs"], cb, rep["boot"])
+            histories.append(h)
+    for m, h, rep in zip(models, histories, reps):
+        meanlong, sdlong, meanlat, sdlat = rep["norm"]
+        original_out = args.out
+        args.out = rep["out"]
+        try:
+            dists = L.predict_locs(m, rep["predgen"], sdlong, meanlong, sdlat, meanlat, rep["testlocs"], rep["pred"],
+                                   rep["samples"], rep["testgen"], h, rep["boot"])
         finally:
             args.out = original_out
         if args.plot_history:
-            L.plot_history(history, dists)
+            L.plot_history(h, dists)
+    if items and items[0]["kind"] == "window":
         print(f"Window run time {(time.time() - t1) / 60:.2f} minutes")
-    else:
-        raise ValueError(kind)
+
+
+def _group_size(args):
+    return max(1, min(8, int(getattr(args, "replicates_per_gpu", 1) or 1)))
 
 
 def _resolve(runner):
@@ -105,15 +146,31 @@ def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None):
             base = dict(base_host)
             for k in ("traingen", "testgen", "predgen"):
                 base[k] = _to_dev(base_host[k])
-        while True:
+        import queue as _queue
+
+        G = _group_size(args)
+        finished = False
+        while not finished:
             item = task_q.get()
             if item is None:
                 break
-            for k in ("traingen", "testgen", "predgen"):
-                if k in item and isinstance(item[k], dict):
-                    item[k] = _to_dev(item[k])
-            _run_item(L, item, base)
-            result_q.put(("done", rank, item.get("boot", item.get("index"))))
+            items = [item]
+            while len(items) < G:  # take what is already queued, up to a group
+                try:
+                    nxt = task_q.get_nowait()
+                except _queue.Empty:
+                    break
+                if nxt is None:
+                    finished = True
+                    break
+                items.append(nxt)
+            for it in items:
+                for k in ("traingen", "testgen", "predgen"):
+                    if k in it and isinstance(it[k], dict):
+                        it[k] = _to_dev(it[k])
+            _run_items(L, items, base)
+            for it in items:
+                result_q.put(("done", rank, it.get("boot", it.get("index"))))
         result_q.put(("exit", rank, None))
     except Exception:  # surface the failure in the parent instead of hanging the queue
         result_q.put(("error", rank, traceback.format_exc()))
@@ -185,8 +242,10 @@ def run_bootstrap(L, traingen, testgen, trainlocs, testlocs, predgen, norm, pred
             "testlocs": testlocs, "norm": norm, "pred": pred, "samples": samples}
     n_gpus = max(1, int(getattr(args, "gpus", 1) or 1))
     if n_gpus == 1:
-        for boot, order in enumerate(orders):
-            _run_item(L, {"kind": "boot", "boot": boot, "site_order": order}, base)
+        G = _group_size(args)
+        items = [{"kind": "boot", "boot": boot, "site_order": order} for boot, order in enumerate(orders)]
+        for i in range(0, len(items), G):
+            _run_items(L, items[i:i + G], base)
         return
     pool = ReplicatePool(n_gpus, args, base)
     for boot, order in enumerate(orders):
@@ -211,6 +270,7 @@ def run_windows(L, genotypes, samples):
     size = int(float(args.window_size))
     n_gpus = max(1, int(getattr(args, "gpus", 1) or 1))
     pool = ReplicatePool(n_gpus, args) if n_gpus > 1 else None
+    pending = []
     for index, (i, a, b) in enumerate(window_bounds(positions, start, stop, size)):
         print(f"\nProcessing window {i}-{i+size}")
         print(f"SNPs {a}-{b}")
@@ -223,8 +283,13 @@ def run_windows(L, genotypes, samples):
                 "testgen": testgen, "predgen": predgen, "trainlocs": trainlocs, "testlocs": testlocs,
                 "norm": (meanlong, sdlong, meanlat, sdlat), "pred": pred, "samples": samples}
         if pool is None:
-            _run_item(L, item, None)
+            pending.append(item)
+            if len(pending) >= _group_size(args):
+                _run_items(L, pending, None)
+                pending = []
         else:
             pool.submit(item)
+    if pending:
+        _run_items(L, pending, None)
     if pool is not None:
         pool.close()

@@ -157,3 +157,15 @@ def test_windows_driver_on_zarr(L, tmp_path):
         lines = open(f"{stem}_0-1249999_predlocs.txt").read().strip().split("\n")
         assert lines[0] == "x,y,sampleID" and len(lines) == 51
         assert os.path.exists(f"{stem}_history.txt")
+
+
+def test_bootstrap_outputs_do_not_depend_on_grouping(L, tmp_path):
+    """--replicates_per_gpu only changes scheduling: every replicate's predictions are byte-identical."""
+    outs = {}
+    for g in (1, 3):
+        out = str(tmp_path / f"g{g}")
+        _run(L, ["--vcf", VCF, "--sample_data", SAMPLES, "--out", out, "--seed", "12345", "--max_epochs", "5",
+                 "--keras_verbose", "0", "--bootstrap", "--nboots", "4", "--max_SNPs", "3000",
+                 "--replicates_per_gpu", str(g)])
+        outs[g] = [open(f"{out}_boot{b}_predlocs.txt").read() for b in ("FULL", "0", "1", "2", "3")]
+    assert outs[1] == outs[3]

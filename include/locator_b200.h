@@ -113,6 +113,11 @@ int loc_gather_cols(const uint32_t* d_in, int64_t n, int64_t row_words_in, const
 int loc_replace_cols(uint32_t* d_packed, int64_t n, int64_t row_words, const int64_t* d_sites,
                      int64_t nsites, const uint8_t* d_vals, void* stream);
 
+/* Host helper for load_genotypes' zarr branch (locator.py:187-194): decompress one Blosc-1 frame
+ * (LZ4 codec, byte shuffle or none -- zarr's default compressor, what allel.vcf_to_zarr writes)
+ * from host memory into host memory.  Returns the decompressed size or < 0 on error. */
+int64_t loc_blosc_decompress(const uint8_t* h_src, int64_t src_len, uint8_t* h_dst, int64_t dst_len);
+
 /* ---------------- model (K3-K7) ---------------- */
 
 /* BN(K) -> Dense(width, elu) x nlayers (Dropout after the floor(nlayers/2)-th)

@@ -125,6 +125,31 @@ def read_matrix(path):
 # ---------------------------------------------------------------------------------------------
 # zarr v2 directory store (what scripts/vcf_to_zarr.py / allel.vcf_to_zarr writes)
 # ---------------------------------------------------------------------------------------------
+def _blosc_decompress(raw, nbytes_hint=None):
+    """One Blosc frame -> bytes, through the C ABI (loc_blosc_decompress; LZ4 + byte shuffle)."""
+    from ._cabi import lib, check
+
+    nbytes = int.from_bytes(raw[4:8], "little")
+    out = np.empty(nbytes, dtype=np.uint8)
+    src = np.frombuffer(raw, dtype=np.uint8)
+    n = lib.loc_blosc_decompress(src.ctypes.data, len(raw), out.ctypes.data, nbytes)
+    if n < 0:
+        check(1, "loc_blosc_decompress")
+    return out.tobytes()
+
+
+def _decode_vlen_utf8(buf):
+    """numcodecs VLenUTF8: uint32 item count, then (uint32 length, bytes) per item."""
+    n = int.from_bytes(buf[:4], "little")
+    out, pos = [], 4
+    for _ in range(n):
+        ln = int.from_bytes(buf[pos:pos + 4], "little")
+        pos += 4
+        out.append(buf[pos:pos + ln].decode("utf-8"))
+        pos += ln
+    return np.array(out, dtype=object)
+
+
 def _zarr_array(root, name):
     adir = os.path.join(root, name)
     with open(os.path.join(adir, ".zarray")) as fh:
@@ -137,10 +162,13 @@ def _zarr_array(root, name):
     sep = meta.get("dimension_separator", ".")
     fill = meta.get("fill_value", 0)
     is_obj = dtype.kind == "O"
-    if is_obj:
-        raise ValueError(f"{name}: object (vlen) arrays are not supported; re-save with a fixed-width dtype")
+    filters = meta.get("filters") or []
+    if is_obj and [f.get("id") for f in filters] != ["vlen-utf8"]:
+        raise ValueError(f"{name}: object arrays are only supported with the vlen-utf8 filter")
+    if not is_obj and filters:
+        raise ValueError(f"{name}: zarr filters {filters!r} are not supported")
     out = np.empty(shape, dtype=dtype)
-    out[...] = 0 if fill is None else fill
+    out[...] = ("" if is_obj else 0) if fill in (None, "") or is_obj else fill
     grid = [(-(-s // c)) for s, c in zip(shape, chunks)]
     for idx in np.ndindex(*grid) if shape else [()]:
         fn = os.path.join(adir, sep.join(str(i) for i in idx) if shape else "0")
@@ -152,10 +180,15 @@ def _zarr_array(root, name):
             buf = raw
         elif comp.get("id") in ("zlib", "gzip"):
             buf = zlib.decompress(raw, 15 + 32)
+        elif comp.get("id") == "blosc":
+            buf = _blosc_decompress(raw)
         else:
             raise ValueError(f"{name}: zarr compressor {comp.get('id')!r} is not available in this build "
-                             "(supported: none, zlib, gzip); convert with compressor=None or Zlib")
-        chunk = np.frombuffer(buf, dtype=dtype).reshape(chunks)
+                             "(supported: none, zlib, gzip, blosc-lz4)")
+        if is_obj:
+            chunk = _decode_vlen_utf8(buf).reshape(chunks)
+        else:
+            chunk = np.frombuffer(buf, dtype=dtype).reshape(chunks)
         sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, shape))
         out[sl] = chunk[tuple(slice(0, s.stop - s.start) for s in sl)]
     return out

@@ -1,0 +1,168 @@
+"""Blosc-LZ4 / vlen-utf8 zarr decoding (load_genotypes' zarr branch, /root/reference/locator/locator.py:187-194).
+
+Pinning: tests/golden/zarr_blosc/{Albania,Guyana} are two chunks (data files, byte-for-byte) of the
+Blosc-LZ4 + byte-shuffle zarr store the reference ships (locator_py/map.zarr, country outlines as
+float64 [2, n] lon/lat).  No zarr / numcodecs / blosc package exists in this image, so the decoded
+values are checked through what the data must be (size-exact LZ4 streams, finite coordinates inside
+the country's bounding box, contiguous outline) -- "parity unpinned" for the byte values themselves.
+The multi-block / split / stored-frame layouts are exercised by frames built in this file.
+"""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from locator_b200 import io
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ZB = os.path.join(HERE, "golden", "zarr_blosc")
+
+
+def _lz4_encode(data: bytes) -> bytes:
+    """Greedy LZ4 block encoder (test-side only)."""
+    n, out, i, anchor, table = len(data), bytearray(), 0, 0, {}
+
+    def emit(lit, mlen, off):
+        token_l = min(len(lit), 15)
+        token_m = 0 if mlen is None else min(mlen - 4, 15)
+        out.append((token_l << 4) | token_m)
+        if token_l == 15:
+            r = len(lit) - 15
+            while r >= 255:
+                out.append(255)
+                r -= 255
+            out.append(r)
+        out.extend(lit)
+        if mlen is not None:
+            out.extend(struct.pack("<H", off))
+            if token_m == 15:
+                r = mlen - 4 - 15
+                while r >= 255:
+                    out.append(255)
+                    r -= 255
+                out.append(r)
+
+    while i + 4 <= n - 5:
+        key = data[i:i + 4]
+        j = table.get(key)
+        table[key] = i
+        if j is not None and i - j <= 65535:
+            m = 4
+            while i + m < n - 5 and data[j + m] == data[i + m]:
+                m += 1
+            emit(data[anchor:i], m, i - j)
+            i += m
+            anchor = i
+        else:
+            i += 1
+    emit(data[anchor:], None, 0)
+    return bytes(out)
+
+
+def _blosc_frame(raw: bytes, typesize: int, blocksize: int, shuffle=True, dont_split=False, memcpy=False):
+    nbytes = len(raw)
+    flags = (1 if shuffle else 0) | (0x10 if dont_split else 0) | (1 << 5) | (0x2 if memcpy else 0)
+    if memcpy:
+        body = raw
+        return bytes([2, 1, flags, typesize]) + struct.pack("<III", nbytes, blocksize, 16 + nbytes) + body
+    nblocks = -(-nbytes // blocksize)
+    streams, bstarts, pos = [], [], 16 + 4 * nblocks
+    for b in range(nblocks):
+        blk = raw[b * blocksize:(b + 1) * blocksize]
+        leftover = len(blk) != blocksize
+        if shuffle:
+            ne = len(blk) // typesize
+            a = np.frombuffer(blk[:ne * typesize], np.uint8).reshape(ne, typesize).T.tobytes()
+            blk = a + blk[ne * typesize:]
+        nsplits = typesize if (not dont_split and not leftover and typesize <= 16 and blocksize // typesize >= 128) else 1
+        ne = len(blk) // nsplits
+        bstarts.append(pos)
+        for s in range(nsplits):
+            part = blk[s * ne:(s + 1) * ne]
+            enc = _lz4_encode(part)
+            if len(enc) >= len(part):
+                enc = part  # stored split: cbytes == neblock
+            streams.append(struct.pack("<I", len(enc)) + enc)
+            pos += 4 + len(enc)
+    body = b"".join(struct.pack("<I", x) for x in bstarts) + b"".join(streams)
+    return bytes([2, 1, flags, typesize]) + struct.pack("<III", nbytes, blocksize, 16 + len(body)) + body
+
+
+@pytest.mark.parametrize("country,lon,lat", [("Albania", (19.0, 21.2), (39.5, 42.8)), ("Guyana", (-61.5, -56.4), (1.1, 8.6))])
+def test_reference_blosc_chunks_decode(country, lon, lat):
+    a = io._zarr_array(ZB, country)
+    meta = json.load(open(os.path.join(ZB, country, ".zarray")))
+    assert meta["compressor"]["id"] == "blosc" and meta["compressor"]["cname"] == "lz4" and meta["compressor"]["shuffle"] == 1
+    assert a.shape == tuple(meta["shape"]) and a.dtype == np.float64
+    assert np.isfinite(a).all()
+    assert lon[0] < a[0].min() and a[0].max() < lon[1]
+    assert lat[0] < a[1].min() and a[1].max() < lat[1]
+    # a border outline: consecutive vertices are close to each other
+    assert np.median(np.hypot(np.diff(a[0]), np.diff(a[1]))) < 0.1
+
+
+@pytest.mark.parametrize("typesize,blocksize,n,shuffle,dont_split", [
+    (1, 4096, 10000, True, False),     # int8 GT: shuffle is a no-op for typesize 1, 3 blocks with a leftover
+    (8, 2048, 2048 * 3 + 40, True, False),   # split into 8 streams, leftover block unsplit
+    (4, 1024, 5000, True, True),       # dont_split flag
+    (8, 4096, 4096, False, False),     # no shuffle, one block
+    (2, 100, 1000, True, False),       # blocks too small to split
+])
+def test_blosc_layouts_round_trip(typesize, blocksize, n, shuffle, dont_split):
+    rng = np.random.default_rng(typesize * 1000 + n)
+    raw = (rng.integers(0, 3, n // 2).astype(np.uint8).tobytes() + bytes(n - n // 2))  # compressible + run of zeros
+    frame = _blosc_frame(raw, typesize, blocksize, shuffle, dont_split)
+    assert io._blosc_decompress(frame) == raw
+    frame = _blosc_frame(raw, typesize, blocksize, memcpy=True)
+    assert io._blosc_decompress(frame) == raw
+
+
+def test_blosc_rejects_corrupt_and_unsupported():
+    raw = bytes(range(256)) * 8
+    frame = bytearray(_blosc_frame(raw, 1, 4096))
+    bad = bytearray(frame)
+    bad[2] = (bad[2] & 0x1F) | (4 << 5)  # zstd codec id
+    with pytest.raises(RuntimeError, match="LZ4"):
+        io._blosc_decompress(bytes(bad))
+    with pytest.raises(RuntimeError):
+        io._blosc_decompress(bytes(frame[:40]))
+
+
+def test_zarr_store_with_blosc_gt_and_vlen_samples(tmp_path, fixture_gt):
+    """A store laid out like allel.vcf_to_zarr's: Blosc int8 calldata/GT, vlen-utf8 object samples, Blosc POS."""
+    gt = fixture_gt["calldata/GT"][:700]
+    nvar, N, _ = gt.shape
+    samples = [f"msp_{i}" if i % 3 else f"sample-é{i}" for i in range(N)]
+    pos = np.arange(nvar, dtype=np.int32) * 17 + 5
+    root = tmp_path / "b.zarr"
+
+    def put(name, meta, chunks):
+        d = root / name
+        d.mkdir(parents=True)
+        (d / ".zarray").write_text(json.dumps(meta))
+        for key, blob in chunks.items():
+            (d / key).write_bytes(blob)
+
+    comp = {"blocksize": 0, "clevel": 5, "cname": "lz4", "id": "blosc", "shuffle": 1}
+    cv = 256
+    chunks = {}
+    for c in range(-(-nvar // cv)):
+        blk = np.full((cv, N, 2), -1, np.int8)
+        part = gt[c * cv:(c + 1) * cv]
+        blk[:len(part)] = part
+        chunks[f"{c}.0.0"] = _blosc_frame(blk.tobytes(), 1, 32768)
+    put("calldata/GT", {"zarr_format": 2, "shape": [nvar, N, 2], "chunks": [cv, N, 2], "dtype": "|i1", "order": "C",
+                        "compressor": comp, "fill_value": -1, "filters": None}, chunks)
+    enc = struct.pack("<I", N) + b"".join(struct.pack("<I", len(s.encode())) + s.encode() for s in samples)
+    put("samples", {"zarr_format": 2, "shape": [N], "chunks": [N], "dtype": "|O", "order": "C", "compressor": comp,
+                    "fill_value": "", "filters": [{"id": "vlen-utf8"}]}, {"0": _blosc_frame(enc, 1, 1 << 16, shuffle=False)})
+    put("variants/POS", {"zarr_format": 2, "shape": [nvar], "chunks": [cv], "dtype": "<i4", "order": "C",
+                         "compressor": comp, "fill_value": 0, "filters": None},
+        {str(c): _blosc_frame(np.pad(pos[c * cv:(c + 1) * cv], (0, cv - len(pos[c * cv:(c + 1) * cv]))).astype("<i4").tobytes(), 4, 1024)
+         for c in range(-(-nvar // cv))})
+    back = io.read_zarr(str(root))
+    np.testing.assert_array_equal(back["calldata/GT"], gt)
+    assert list(back["samples"]) == samples
+    np.testing.assert_array_equal(back["variants/POS"], pos)

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblocator_b200.so")
+LIB_PATH = os.environ.get("LOC_LIB_PATH") or os.path.join(_HERE, "lib", "liblocator_b200.so")  # override: A/B of builds
 
 
 class LocatorCudaError(RuntimeError):

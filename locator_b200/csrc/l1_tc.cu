@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(L1Args a, int64_t nt
 constexpr int B_NT = 64;                       // SNPs per tile (one accumulator buffer)
 constexpr int B_CH = 8;                        // SNPs per streamed chunk (one W/m/v stage)
 constexpr int B_STAGES = 5;
+constexpr int B_RING = 2 * B_STAGES;             // barrier ring: one per (epilogue group, stage)
 constexpr int B_EPI_WARPS = 16;                // two groups of 8: group g owns the chunks with index % 2 == g
 constexpr int B_THREADS = (B_EPI_WARPS + 6) * 32;  // + 2 builder warps, load warp, store warp, 2 forward warps
 constexpr int B_DZ = kMaxB * kH * 4;           // 32 KB: [8 chunks][32 rows (b)][128 B]
@@ -368,13 +369,20 @@ __device__ __forceinline__ void adam_update_fast(float& w, float& m, float& v, f
   w = w - __fdividef(m * alpha, rt + kAdamEps);
 }
 
-__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+// L2 eviction priorities as the 64-bit cache-policy operand of the bulk copies (the values
+// createpolicy.fractional.L2::evict_* produces for fraction 1.0)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                : "memory");
 }
-__device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_src),
+               "r"(bytes), "l"(pol)
                : "memory");
 }
 
@@ -393,9 +401,14 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   uint64_t* bars = (uint64_t*)(sBits + 2 * 32 * 2);
   uint64_t* tmem_full = bars;                    // [2]  MMA of a tile done
   uint64_t* tmem_empty = bars + 2;               // [2]  all 16 epilogue warps done with a tile
-  uint64_t* st_full = bars + 4;                  // [B_STAGES] W/m/v chunk landed
-  uint64_t* st_done = st_full + B_STAGES;        // [B_STAGES] chunk updated in place (8 warps)
-  uint64_t* st_free = st_done + B_STAGES;        // [B_STAGES] chunk written back, stage reusable
+  // st_full / st_done are indexed by chunk % B_RING (= stage and epilogue group together): the waiters of a
+  // chunk alternate between the two epilogue groups / forward warps, and B_STAGES is odd, so a barrier per
+  // stage would be waited on by a warp that never observed the stage's previous phase -- a parity wait then
+  // passes while that previous use is still in flight.  With one barrier per (group, stage) every waiter
+  // sees every phase of its barriers in order.
+  uint64_t* st_full = bars + 4;                  // [B_RING] W/m/v chunk landed
+  uint64_t* st_done = st_full + B_RING;          // [B_RING] chunk updated in place (8 warps)
+  uint64_t* st_free = st_done + B_RING;          // [B_STAGES] chunk written back, stage reusable (load warp, in order)
   uint64_t* fwd_done = st_free + B_STAGES;       // forward accumulators complete (fused runs)
   uint32_t* tmem_slot = (uint32_t*)(fwd_done + 1);
 
@@ -406,17 +419,22 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   const int64_t t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
   const int nloc = (int)(t_end - t_begin);
   const int nchunks = nloc * (B_NT / B_CH);
+  // odd steps walk the tiles downwards (L1Args::alternate); chunks inside a tile keep their order
+  const bool rev = a.alternate && (a.st->t & 1);
+  auto tile_of = [&](int li) -> int64_t { return t_begin + (rev ? nloc - 1 - li : li); };
+  const uint64_t pol_ld = (a.stream_hint & 1) ? kL2EvictFirst : kL2EvictNormal;
+  const uint64_t pol_st = (a.stream_hint & 2) ? kL2EvictFirst : kL2EvictNormal;
 
   if (threadIdx.x == 0) {
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], B_EPI_WARPS);
     mbar_init(&tmem_empty[1], B_EPI_WARPS);
-    for (int s = 0; s < B_STAGES; ++s) {
+    for (int s = 0; s < B_RING; ++s) {
       mbar_init(&st_full[s], 1);
       mbar_init(&st_done[s], 8);
-      mbar_init(&st_free[s], fuse ? 2 : 1);  // written back (+ consumed by the forward MMA)
     }
+    for (int s = 0; s < B_STAGES; ++s) mbar_init(&st_free[s], fuse ? 2 : 1);  // written back (+ consumed by the forward MMA)
     mbar_init(fwd_done, 2);  // one commit per forward warp
     fence_barrier_init();
   }
@@ -455,7 +473,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       }
       uint32_t gr[8];
       tmem_ld_x8(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 128 + h * 64 + cc * 8), gr);
-      mbar_wait(&st_full[s], (uint32_t)(c / B_STAGES) & 1u);
+      mbar_wait(&st_full[c % B_RING], (uint32_t)(c / B_RING) & 1u);
       // element (row r, column j) of a chunk block: [j/32][r][32B atoms XOR (r & 3)] (w1_tiled_index)
       float* stw = reinterpret_cast<float*>(sStage + s * B_STAGE) + ((j >> 5) << 8) + (j & 7);
       const int j8 = (j & 31) >> 3;
@@ -503,7 +521,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
         dst[lane >> 3] = pq[0];
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&st_done[s]);
+      if (lane == 0) mbar_arrive(&st_done[c % B_RING]);
       if (cc >= 6) {  // last chunk of the tile for this group
         tc_fence_before();
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -526,12 +544,14 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % B_STAGES;
         mbar_wait(&st_free[s], ((uint32_t)(c / B_STAGES) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&st_full[s], B_STAGE);
-        const int64_t off = (t_begin * B_NT + (int64_t)c * B_CH) * kH;  // chunk blocks are contiguous 8 KB
+        uint64_t* full = &st_full[c % B_RING];
+        mbar_arrive_expect_tx(full, B_STAGE);
+        const int64_t off = (tile_of(c >> 3) * B_NT + (int64_t)(c & 7) * B_CH) * kH;  // chunk blocks are contiguous 8 KB
         const uint32_t dst = smem_u32(sStage + s * B_STAGE);
-        bulk_load(dst, a.W1 + off, B_ARR, &st_full[s]);
-        bulk_load(dst + B_ARR, a.mW1 + off, B_ARR, &st_full[s]);
-        bulk_load(dst + 2 * B_ARR, a.vW1 + off, B_ARR, &st_full[s]);
+        const uint64_t pol = pol_ld;
+        bulk_load(dst, a.W1 + off, B_ARR, full, pol);
+        bulk_load(dst + B_ARR, a.mW1 + off, B_ARR, full, pol);
+        bulk_load(dst + 2 * B_ARR, a.vW1 + off, B_ARR, full, pol);
       }
     }
   } else if (warp == B_EPI_WARPS + 3) {
@@ -541,12 +561,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     if (elect_one()) {
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % B_STAGES;
-        mbar_wait(&st_done[s], (uint32_t)(c / B_STAGES) & 1u);
-        const int64_t off = (t_begin * B_NT + (int64_t)c * B_CH) * kH;
+        mbar_wait(&st_done[c % B_RING], (uint32_t)(c / B_RING) & 1u);
+        const int64_t off = (tile_of(c >> 3) * B_NT + (int64_t)(c & 7) * B_CH) * kH;
         const uint32_t src = smem_u32(sStage + s * B_STAGE);
-        bulk_store(a.W1 + off, src, B_ARR);
-        bulk_store(a.mW1 + off, src + B_ARR, B_ARR);
-        bulk_store(a.vW1 + off, src + 2 * B_ARR, B_ARR);
+        const uint64_t pol = pol_st;
+        bulk_store(a.W1 + off, src, B_ARR, pol);
+        bulk_store(a.mW1 + off, src + B_ARR, B_ARR, pol);
+        bulk_store(a.vW1 + off, src + 2 * B_ARR, B_ARR, pol);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         if (c > 0) {
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -575,7 +596,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       auto prefetch = [&](int c) {
         Pre p = {0u, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
         if (c >= nchunks) return p;
-        const int64_t k0 = t_begin * B_NT + (int64_t)c * B_CH;
+        const int64_t k0 = tile_of(c >> 3) * B_NT + (int64_t)(c & 7) * B_CH;
         const int64_t k = k0 + r;
         if (lane < nbn && (k0 >> 4) < a.row_words) p.word = __ldg(nptr + (k0 >> 4));
         if (k < a.K) {
@@ -594,7 +615,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       for (int c = fw; c < nchunks; c += 2) {
         const Pre nxt = prefetch(c + 2);  // one chunk of this warp ahead: hides the global-load latency
         const int li = c >> 3, cc = c & 7, buf = li & 1, s = c % B_STAGES;
-        const int64_t k0 = t_begin * B_NT + (int64_t)c * B_CH;
+        const int64_t k0 = tile_of(c >> 3) * B_NT + (int64_t)(c & 7) * B_CH;
         const int64_t k = k0 + r;
         const bool valid = k < a.K;
         // next batch: genotype of (row = lane, SNP r8), per-SNP counts by ballot, statistics -- all of
@@ -615,7 +636,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
         float mean, var;
         moments_from_counts(n1, n2, nbn, mean, var);
         const float rsn = rsqrtf(var + kBnEps);
-        mbar_wait(&st_done[s], (uint32_t)(c / B_STAGES) & 1u);
+        mbar_wait(&st_done[c % B_RING], (uint32_t)(c / B_RING) & 1u);
         float P = 0.f, Q = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
@@ -685,7 +706,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       const int buf = li & 1;
       mbar_wait(&tmem_empty[buf], (uint32_t)(li >> 1) & 1u);
       if (fuse) return;  // the forward warp updates gamma / beta chunk by chunk
-      const int64_t k = (t_begin + li) * B_NT + wb * 32 + lane;
+      const int64_t k = tile_of(li) * B_NT + wb * 32 + lane;
       float P = 0.f, Q = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) {
@@ -710,7 +731,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     };
     for (int li = 0; li < nloc; ++li) {
       const int buf = li & 1;
-      const int64_t tile = t_begin + li;
+      const int64_t tile = tile_of(li);
       // lane <-> batch row: the 32 genotypes of this builder warp's half tile
       uint2 w2 = make_uint2(0u, 0u);
       const int64_t wofs = tile * 4 + wb * 2;

@@ -65,6 +65,9 @@ struct L1Args {
   RowSrc src;
   RowSrc src_next;  // rows of the following step (fused forward of the tcgen05 backward kernel)
   int fuse_next;
+  int alternate;  // tcgen05 backward: walk the CTA's tiles downwards on odd steps (the tail of the previous
+                  // step's updates is still in L2: those reads hit and their dirty lines are overwritten in place)
+  int stream_hint;  // tcgen05 backward: L2 evict_first on the W1/m/v chunk loads (bit 0) / stores (bit 1)
   float *gamma, *beta, *mmean, *mvar;
   float* W1;
   float *m_gamma, *v_gamma, *m_beta, *v_beta, *mW1, *vW1;

@@ -22,13 +22,17 @@
 //   A = dZ1 as hi + lo tf32 parts (MN-major, swizzled, built once per CTA), B = centred genotypes
 //   (K-major, swizzled; exact in tf32 for a power-of-two batch) -> S is fp32-accurate.
 //   W1, m, v never touch the load/store units' global path: a load thread streams 8-SNP chunks
-//   (3 x 8 KB, contiguous rows) into a 4-stage shared-memory ring with cp.async.bulk + mbarrier, the
-//   epilogue warps (accumulator row j = TMEM lane, so a warp reads/writes 128 contiguous bytes of a
-//   row: conflict-free) apply Adam in place, and a store thread writes the chunk back with
+//   (3 x 8 KB, contiguous rows, L2 evict_first) into a 5-stage shared-memory ring with cp.async.bulk +
+//   mbarrier, the epilogue warps (accumulator row j = TMEM lane, so a warp reads/writes 128 contiguous
+//   bytes of a row: conflict-free) apply Adam in place, and a store thread writes the chunk back with
 //   cp.async.bulk; dW1 never exists in memory.  P_k, Q_k (for dgamma, dbeta) are reduced with a
 //   butterfly transpose across the warp and summed across warps in fixed order.
+//   (A 6-stage ring with a single-pass tf32 dZ1 was measured: no faster, so the hi/lo split stays.)
+//   Odd steps walk each CTA's tiles downwards: the tail of the previous step's updates is still in L2.
+//   Fused runs (L1Args::fuse_next) also compute the NEXT step's forward partial tile from every freshly
+//   updated chunk while it is in shared memory (two forward warps, own TMEM columns).
 //   warps 0-15: epilogue (two groups alternating chunks) | 16-17: genotype unpack / BN statistics /
-//   gamma-beta Adam, MMA issue | 18: bulk loads | 19: bulk stores.
+//   gamma-beta Adam (unfused runs), MMA issue | 18: bulk loads | 19: bulk stores | 20-21: forward warps.
 #include <stdlib.h>
 
 #include "l1_common.cuh"

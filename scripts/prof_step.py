@@ -1,4 +1,4 @@
-"""Profiling driver (GPU box): a few optimizer steps + one validation chunk at a BASELINE shape."""
+"""Profiling driver (GPU box): one training epoch + one unfused step at a BASELINE shape."""
 import os
 import sys
 
@@ -20,9 +20,12 @@ def main():
     m.bind_val(x[ntr:], y[ntr:])
     m.set_schedule(patience=100)
     rng = np.random.default_rng(0)
-    for s in range(nsteps):
-        m.train_step(rng.permutation(ntr)[:32])
-    m.debug_stage(4, rng.permutation(ntr)[:32])  # the fused backward + next forward, as train_epochs runs it
+    # one epoch as the CLI runs it (loc_train_epochs): first-layer forward once, then per step the hidden
+    # stack, the small-layer update and the backward kernel that also runs the next step's forward;
+    # the epoch's last step is unfused and is followed by the validation pass
+    for _ in range(max(1, nsteps // 26)):
+        m.train_epochs(np.stack([rng.permutation(ntr)]).astype(np.int32))
+    m.train_step(rng.permutation(ntr)[:32])  # one unfused step: forward, hidden, update, plain backward
     print("loss", m.state().last_loss, "val", m.evaluate(x[ntr:ntr + 32], y[ntr:ntr + 32]))
 
 

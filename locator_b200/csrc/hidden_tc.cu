@@ -300,13 +300,17 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
       }
       keep[b * kCW + jl] = mult;
     }
-    stage_store(b, jl, (b0 + b) < nb ? act : 0.f);
+    const float out = (b0 + b) < nb ? act : 0.f;
+    stage_store(b, jl, out);
+    // the update kernels read the (dropout-scaled) activations from global memory: store them now,
+    // off the critical path, instead of in a loop at the end of the kernel
+    if (a.training) a.acts[((int64_t)i * kMaxB + b0 + b) * kH + j0 + jl] = out;
   };
   auto finish_bwd_elem = [&](int i, int b, int jl, float da) {
     if (i == a.n_before - 1) da *= keep[b * kCW + jl];
     const float dz = (b0 + b) < nb ? da * elu_grad_from_out(own_a[(i * kRB + b) * kCW + jl]) : 0.f;
-    own_dz[(i * kRB + b) * kCW + jl] = dz;
     stage_store(b, jl, dz);
+    a.dzs[((int64_t)i * kMaxB + b0 + b) * kH + j0 + jl] = dz;
   };
 
   // ---- layer 0: finish the split-K reduction started in the prologue ----
@@ -404,49 +408,37 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
       else
         __syncthreads();
     }
-    // ---- leave activations and dz of every layer in global memory for the update kernels ----
-    for (int idx = tid; idx < L * kRB * kCW / 4; idx += kThreads) {
-      const int i = idx / (kRB * kCW / 4), rem = idx % (kRB * kCW / 4);
-      const int b = rem / (kCW / 4), jl = (rem % (kCW / 4)) * 4;
-      float4 act = *reinterpret_cast<const float4*>(own_a + (i * kRB + b) * kCW + jl);
-      if (i == a.n_before - 1) {
-        const float4 km = *reinterpret_cast<const float4*>(keep + b * kCW + jl);
-        act.x *= km.x;
-        act.y *= km.y;
-        act.z *= km.z;
-        act.w *= km.w;
-      }
-      if (b0 + b >= nb) act = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(a.acts + ((int64_t)i * kMaxB + b0 + b) * kH + j0 + jl) = act;
-      *reinterpret_cast<float4*>(a.dzs + ((int64_t)i * kMaxB + b0 + b) * kH + j0 + jl) =
-          *reinterpret_cast<const float4*>(own_dz + (i * kRB + b) * kCW + jl);
-    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_barrier();  // nobody exits while peers may still address its shared memory; global writes visible
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
-  if (r == 0 && tid == 0) {
+  if (r == 0 && warp == 0) {
     DevState* st = a.st;
-    if (a.training || a.has_targets) {
-      float s = 0.f;
-      for (int b = 0; b < nb; ++b) s += __ldcg(a.outs + 192 + b);
-      const float mean = s / (float)nb;
-      if (a.training) {
-        st->loss_total += mean * (float)nb;
-        st->loss_count += (float)nb;
-        st->last_loss = mean;
-        if (!isfinite(mean)) st->nonfinite = 1;
-      } else {
-        st->val_total += mean * (float)nb;
-        st->val_count += (float)nb;
+    // per-row distances of all batch groups (written before the barrier): one L2 round trip, fixed-order sum
+    float s = 0.f;
+    if ((a.training || a.has_targets) && lane < nb) s = __ldcg(a.outs + 192 + lane);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      if (a.training || a.has_targets) {
+        const float mean = s / (float)nb;
+        if (a.training) {
+          st->loss_total += mean * (float)nb;
+          st->loss_count += (float)nb;
+          st->last_loss = mean;
+          if (!isfinite(mean)) st->nonfinite = 1;
+        } else {
+          st->val_total += mean * (float)nb;
+          st->val_count += (float)nb;
+        }
       }
-    }
-    if (a.training) {  // optimizer bookkeeping for the update kernels of this step (Keras Adam: alpha from t >= 1)
-      const int t = st->t + 1;
-      st->t = t;
-      st->step_id = step_id + 1;
-      const float b1p = powf(kAdamB1, (float)t), b2p = powf(kAdamB2, (float)t);
-      st->alpha = st->lr * sqrtf(1.f - b2p) / (1.f - b1p);
+      if (a.training) {  // optimizer bookkeeping for the update kernels of this step (Keras Adam: alpha from t >= 1)
+        const int t = st->t + 1;
+        st->t = t;
+        st->step_id = step_id + 1;
+        const float b1p = powf(kAdamB1, (float)t), b2p = powf(kAdamB2, (float)t);
+        st->alpha = st->lr * sqrtf(1.f - b2p) / (1.f - b1p);
+      }
     }
   }
 }

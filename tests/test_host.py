@@ -167,3 +167,41 @@ def test_bench_multi_rank_reduction_gloo_world2(tmp_path):
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT")][0].split()
     assert float(line[1]) == 11.0                      # max over ranks of the per-rank time
     assert float(line[2]) == round(2 * 100 * 32 / 0.011, 3)  # whole-job samples/s over both ranks
+
+
+def test_summarize_centroids_and_kernel_peaks(tmp_path):
+    """Post-hoc summariser (reference locator_py/plot_locator.py:26-134): centroid = mean of the replicate
+    predictions; kernel peak = the prediction with the highest Gaussian density (bandwidth 0.2)."""
+    import pandas as pd
+    from locator_b200 import summarize
+
+    rng = np.random.default_rng(3)
+    truth = {"a": (1.0, 2.0), "b": (-3.0, 0.5), "c": (10.0, 10.0)}
+    d = tmp_path / "boots"
+    d.mkdir()
+    for r in range(12):
+        rows = []
+        for sid, (x, y) in truth.items():
+            if sid == "c" and r >= 9:   # three far outliers: pull the centroid, not the density peak
+                rows.append((x + 5.0 + r, y - 4.0, sid))
+            else:
+                rows.append((x + 0.05 * rng.normal(), y + 0.05 * rng.normal(), sid))
+        pd.DataFrame(rows, columns=["x", "y", "sampleID"]).to_csv(d / f"run_boot{r}_predlocs.txt", index=False)
+    (d / "run_history.txt").write_text("ignored")
+    sd = tmp_path / "samples.txt"
+    pd.DataFrame([(s, x, y) for s, (x, y) in truth.items()], columns=["sampleID", "x", "y"]).to_csv(sd, sep="\t", index=False)
+    assert summarize.main(["--infile", str(d), "--sample_data", str(sd), "--out", str(tmp_path / "s"), "--error", "--silence"]) == 0
+    t = pd.read_csv(str(tmp_path / "s_centroids.txt"), sep="\t").set_index("sampleID")
+    assert list(t.columns) == ["x", "y", "kd_x", "kd_y", "gc_x", "gc_y"]
+    allp = summarize.load_predictions(str(d))
+    for sid, (x, y) in truth.items():
+        g = allp[allp.sampleID == sid]
+        assert t.loc[sid, "gc_x"] == pytest.approx(g.xpred.mean()) and t.loc[sid, "gc_y"] == pytest.approx(g.ypred.mean())
+        assert abs(t.loc[sid, "kd_x"] - x) < 0.2 and abs(t.loc[sid, "kd_y"] - y) < 0.2
+        assert ((g.xpred == t.loc[sid, "kd_x"]) & (g.ypred == t.loc[sid, "kd_y"])).any()  # a member of the set
+    assert abs(t.loc["c", "gc_x"] - 10.0) > 2.0
+    # brute-force density check for one sample
+    g = allp[allp.sampleID == "a"]
+    xs, ys = g.xpred.to_numpy(), g.ypred.to_numpy()
+    dens = [np.exp(-((xs - a) ** 2 + (ys - b) ** 2) / (2 * 0.2 ** 2)).sum() for a, b in zip(xs, ys)]
+    assert (xs[int(np.argmax(dens))], ys[int(np.argmax(dens))]) == (t.loc["a", "kd_x"], t.loc["a", "kd_y"])

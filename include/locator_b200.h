@@ -145,6 +145,24 @@ int loc_model_get_weight(loc_model* m, int32_t idx, float* h_dst, int64_t n, voi
 /* Adam moments of trainable weight idx (idx 2,3 are not trainable -> error). */
 int loc_model_get_adam(loc_model* m, int32_t idx, float* h_m, float* h_v, int64_t n, void* stream);
 
+/* ---- one model sharded over SNPs (tensor parallelism) ----
+ * A shard is a model created with K = its own number of SNP columns.  It owns those rows of W1 (+ Adam
+ * state) and their BatchNorm vectors; the hidden stack is replicated.  The only exchange per forward pass
+ * is the sum over shards of the [32][width] first-layer pre-activation tile.
+ *
+ * loc_model_set_shard (before loc_model_init): this model's columns are [k_offset, k_offset + K) of a
+ * K_global-column model -- glorot limit and random stream of W1 are those of the whole layer, so the
+ * shards together initialise exactly as the unsharded model with the same seed.
+ *
+ * loc_model_set_exchange: `fn(ctx, d_tile, n, stream)` is called on the host while kernels are being
+ * enqueued, every time a tile is complete; it must enqueue on `stream` an in-place sum of d_tile
+ * (n = 32 * width floats, device memory owned by the caller) over all shards, leaving bitwise identical
+ * results on every shard (e.g. ncclAllReduce / torch.distributed.all_reduce); returns 0 on success.
+ * fn = NULL removes the hook.  Needs the tcgen05 kernels (width 256); not combined with replicate groups. */
+typedef int (*loc_exchange_fn)(void* ctx, float* d_tile, int64_t n, void* stream);
+int loc_model_set_shard(loc_model* m, int64_t k_offset, int64_t K_global);
+int loc_model_set_exchange(loc_model* m, loc_exchange_fn fn, void* ctx, float* d_tile);
+
 /* lr, EarlyStopping patience (ReduceLROnPlateau patience = patience/6), and
  * reset of the callback state machine (best = +inf, waits = 0, epoch = 0). */
 int loc_model_set_schedule(loc_model* m, float lr, int32_t patience);

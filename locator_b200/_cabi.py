@@ -62,6 +62,8 @@ SIGNATURES = {
     "loc_model_set_weight": (C.c_int, [P, I32, P, I64, P]),
     "loc_model_get_weight": (C.c_int, [P, I32, P, I64, P]),
     "loc_model_get_adam": (C.c_int, [P, I32, P, P, I64, P]),
+    "loc_model_set_shard": (C.c_int, [P, I64, I64]),
+    "loc_model_set_exchange": (C.c_int, [P, P, P, P]),
     "loc_model_set_schedule": (C.c_int, [P, C.c_float, I32]),
     "loc_model_bind_train": (C.c_int, [P, P, I64, I64, P]),
     "loc_model_bind_val": (C.c_int, [P, P, I64, I64, P]),
@@ -83,6 +85,10 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = the library does not export a declared symbol
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+# loc_exchange_fn: int (*)(void* ctx, float* d_tile, int64_t n, void* stream)
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 
 def check(rc, what=""):

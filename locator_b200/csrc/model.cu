@@ -30,10 +30,11 @@ __global__ void k_glorot(float* w, int64_t n, float limit, uint32_t stream, uint
 }
 
 // W1 in the tiled layout (model.cuh: w1_tiled_index): same Philox element index as the row-major init.
-__global__ void k_glorot_tiled(float* w, int64_t K, int H, float limit, uint32_t stream, uint64_t seed) {
+__global__ void k_glorot_tiled(float* w, int64_t K, int H, float limit, uint32_t stream, uint64_t seed,
+                               int64_t k_offset) {
   const int64_t n = K * H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float u = philox_uniform((uint64_t)i, stream, seed);
+    const float u = philox_uniform((uint64_t)(i + k_offset * H), stream, seed);  // element index of the whole layer
     w[w1_tiled_index(i / H, (int)(i % H))] = (2.0f * u - 1.0f) * limit;
   }
 }
@@ -221,6 +222,32 @@ static L1Args l1_args(loc_model* m, const uint32_t* packed, int64_t row_words, c
   return a;
 }
 
+// Sharded models: own split-K partial tiles -> one tile (fixed order), then the sum over shards.
+__global__ void __launch_bounds__(128) k_reduce_partials(const float* __restrict__ partials, int n_partials, float* out,
+                                                         int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int p = 0;
+  for (; p + 4 <= n_partials; p += 4) {
+    s0 += __ldcg(partials + (int64_t)p * n + i);
+    s1 += __ldcg(partials + (int64_t)(p + 1) * n + i);
+    s2 += __ldcg(partials + (int64_t)(p + 2) * n + i);
+    s3 += __ldcg(partials + (int64_t)(p + 3) * n + i);
+  }
+  for (; p < n_partials; ++p) s0 += __ldcg(partials + (int64_t)p * n + i);
+  out[i] = (s0 + s1) + (s2 + s3);
+}
+
+static int exchange_partials(loc_model* m, cudaStream_t s) {
+  if (m->exchange == nullptr) return 0;
+  const int n = kMaxB * m->H;
+  k_reduce_partials<<<cdiv(n, 128), 128, 0, s>>>(m->partials, m->n_partials, m->z1_tile, n);
+  LOC_LAUNCHED();
+  LOC_CHECK(m->exchange(m->exchange_ctx, m->z1_tile, n, (void*)s) == 0, "exchange hook failed");
+  return 0;
+}
+
 static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated, const float* locs, float* pred_out) {
   HidArgs h;
   h.H = m->H;
@@ -234,8 +261,8 @@ static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated
   h.seed = m->seed;
   h.masks = m->masks;
   h.n_masks = m->n_masks;
-  h.partials = m->partials;
-  h.n_partials = m->n_partials;
+  h.partials = m->exchange != nullptr ? m->z1_tile : m->partials;
+  h.n_partials = m->exchange != nullptr ? 1 : m->n_partials;
   h.small = m->small;
   h.w_fs = m->w_fs;
   h.w_bs = m->w_bs;
@@ -286,7 +313,7 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
     a.src_next = *next;
     a.fuse_next = 1;
   }
-  if ((stage_mask & 1) && !have_fwd && forward_l1(m, a, s)) return 1;
+  if ((stage_mask & 1) && !have_fwd && (forward_l1(m, a, s) || exchange_partials(m, s))) return 1;
   HidArgs h = hid_args(m, src, 1, gated, m->train_locs, nullptr);
   if ((stage_mask & 2) && (m->hid_tc ? hidden_tc_launch(h, s) : hidden_launch(h, m->cluster, s))) return 1;
   // The small-layer update only needs the hidden kernel's outputs: it runs on a side stream next to
@@ -309,6 +336,7 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
   if ((stage_mask & 4) &&
       (m->use_tc ? l1_backward_tc(a, m->n_bwd_blocks, s) : l1_backward_simt(a, m->n_bwd_blocks, s)))
     return 1;
+  if ((stage_mask & 4) && a.fuse_next && exchange_partials(m, s)) return 1;  // the next step's tile is complete
   if (fork) LOC_CUDA(cudaStreamWaitEvent(s, m->ev_upd, 0));
   return 0;
 }
@@ -324,7 +352,7 @@ static int infer_rows(loc_model* m, const uint32_t* packed, int64_t n, int64_t r
     src.row0 = (int32_t)r0;
     src.nb = (int32_t)((n - r0) < kMaxB ? (n - r0) : kMaxB);
     L1Args a = l1_args(m, packed, row_words, src, 0, gated);
-    if (forward_l1(m, a, s)) return 1;
+    if (forward_l1(m, a, s) || exchange_partials(m, s)) return 1;
     HidArgs h = hid_args(m, src, 0, gated, locs, pred_out);
     if (m->hid_tc ? hidden_tc_launch(h, s) : hidden_launch(h, m->cluster, s)) return 1;
   }
@@ -382,6 +410,7 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   memset(m, 0, sizeof(*m));
   LOC_CUDA(cudaGetDevice(&m->dev));
   m->K = K;
+  m->K_global = K;
   m->H = width;
   m->L = nlayers;
   m->B = batch_size;
@@ -489,8 +518,8 @@ int loc_model_init(loc_model* m, uint64_t seed, void* stream) {
     return 0;
   };
   if (m->use_tc) {
-    const float limit = (float)sqrt(6.0 / (double)(K + H));
-    k_glorot_tiled<<<sm_count() * 8, 256, 0, s>>>(m->W1, K, (int)H, limit, 16u, seed);
+    const float limit = (float)sqrt(6.0 / (double)(m->K_global + H));
+    k_glorot_tiled<<<sm_count() * 8, 256, 0, s>>>(m->W1, K, (int)H, limit, 16u, seed, m->k_offset);
     LOC_LAUNCHED();
   } else if (glorot(m->W1, K, H, 0)) {
     return 1;
@@ -587,6 +616,24 @@ int loc_model_get_adam(loc_model* m, int32_t idx, float* h_m, float* h_v, int64_
   return 0;
 }
 
+int loc_model_set_shard(loc_model* m, int64_t k_offset, int64_t K_global) {
+  LOC_CHECK(m != nullptr && k_offset >= 0 && K_global >= k_offset + m->K, "loc_model_set_shard: bad arguments");
+  LOC_CHECK(m->use_tc && m->hid_tc, "loc_model_set_shard: sharded models need the tcgen05 kernels (width 256)");
+  m->k_offset = k_offset;
+  m->K_global = K_global;
+  return 0;
+}
+
+int loc_model_set_exchange(loc_model* m, loc_exchange_fn fn, void* ctx, float* d_tile) {
+  LOC_CHECK(m != nullptr && (fn == nullptr || d_tile != nullptr), "loc_model_set_exchange: bad arguments");
+  LOC_CHECK(fn == nullptr || (m->use_tc && m->hid_tc),
+            "loc_model_set_exchange: sharded models need the tcgen05 kernels (width 256)");
+  m->exchange = fn;
+  m->exchange_ctx = ctx;
+  m->z1_tile = d_tile;
+  return 0;
+}
+
 int loc_model_set_schedule(loc_model* m, float lr, int32_t patience) {
   LOC_CHECK(m != nullptr, "loc_model_set_schedule: null model");
   LOC_CHECK(patience >= 0, "loc_model_set_schedule: patience must be >= 0");
@@ -658,6 +705,7 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
     LOC_CHECK(m != nullptr && d_perms[g] != nullptr && m->train_packed != nullptr && m->val_packed != nullptr,
               "loc_group_train_epochs: every model needs bound training / validation data and a batch order");
     LOC_CHECK(m->hid_tc && m->use_tc, "loc_group_train_epochs: grouped replicates need the tcgen05 kernels (width 256)");
+    LOC_CHECK(m->exchange == nullptr, "loc_group_train_epochs: sharded models cannot be grouped");
     LOC_CHECK(m->L == m0->L && m->B == m0->B && m->n_train == m0->n_train,
               "loc_group_train_epochs: replicates of a group must share nlayers, batch size and training-set size");
   }

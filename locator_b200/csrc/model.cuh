@@ -179,4 +179,9 @@ struct loc_model {
   const float *train_locs, *val_locs;
   const uint8_t* masks;
   int64_t n_masks;
+  // SNP shard of a larger model (tensor parallelism): columns [k_offset, k_offset + K) of K_global
+  int64_t k_offset, K_global;
+  int (*exchange)(void* ctx, float* d_tile, int64_t n, void* stream);
+  void* exchange_ctx;
+  float* z1_tile;  // caller-owned [kMaxB][H]: own partial sum, then the sum over shards
 };

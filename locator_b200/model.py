@@ -28,7 +28,10 @@ class LocatorModel:
     """BN(K) -> Dense(width, elu) x nlayers (Dropout in the middle) -> Dense(2) -> Dense(2)."""
 
     def __init__(self, K, width=256, nlayers=10, dropout_prop=0.25, batch_size=32, max_epochs=5000, seed=0,
-                 learning_rate=1e-3):
+                 learning_rate=1e-3, shard=None, exchange=None):
+        """shard = (k_offset, K_global): this model holds SNP columns [k_offset, k_offset + K) of a K_global-column
+        model (tensor parallelism); exchange(tile) must then sum the float32 CUDA tensor `tile` in place over
+        all shards on the current stream (see all_reduce_exchange)."""
         _dev()
         self.K, self.width, self.nlayers = int(K), int(width), int(nlayers)
         self.batch_size, self.max_epochs = int(batch_size), int(max_epochs)
@@ -39,8 +42,14 @@ class LocatorModel:
         check(lib.loc_model_create(C.byref(h), self.K, self.width, self.nlayers, self.batch_size, self.dropout_prop,
                                    self.max_epochs), "loc_model_create")
         self._h = h
-        check(lib.loc_model_init(self._h, self.seed, _stream()), "loc_model_init")
         self._keep = {}  # device tensors the handle points at
+        self.shard = None
+        if shard is not None:
+            self.shard = (int(shard[0]), int(shard[1]))
+            check(lib.loc_model_set_shard(self._h, self.shard[0], self.shard[1]), "loc_model_set_shard")
+        if exchange is not None:
+            self.set_exchange(exchange)
+        check(lib.loc_model_init(self._h, self.seed, _stream()), "loc_model_init")
         self._wver = 0   # bumped whenever the weights may have changed (prediction memo key)
         self._memo = {}
         self.stop_training = False
@@ -54,6 +63,27 @@ class LocatorModel:
                 pass
             lib.loc_model_destroy(h)
             self._h = None
+
+    def set_exchange(self, fn):
+        """fn(tile): in-place sum of the [32 * width] float32 CUDA tensor over all shards, enqueued on the
+        current stream; called once per forward pass while the kernels are being enqueued."""
+        from ._cabi import EXCHANGE_FN
+
+        tile = torch.zeros(32 * self.width, dtype=torch.float32, device="cuda")
+
+        def hook(_ctx, _ptr, _n, _stream_ptr):
+            try:
+                fn(tile)
+                return 0
+            except Exception:  # surfaces as a LocatorCudaError of the calling entry point
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        cb = EXCHANGE_FN(hook)
+        self._keep["exchange"] = (tile, cb, fn)
+        check(lib.loc_model_set_exchange(self._h, C.cast(cb, C.c_void_p), None, tile.data_ptr()), "loc_model_set_exchange")
 
     @property
     def impl(self):
@@ -327,3 +357,20 @@ def fit_group(models, xs, ys, validation_datas, epochs=None, patience=100, verbo
         m.stop_training = bool(st.stopped)
         out.append(m._history(st.epoch))
     return out
+
+
+def shard_bounds(K, rank, world):
+    """Columns [k0, k1) of shard `rank`: contiguous, multiples of the 64-SNP tile except the last."""
+    per = -(-(-(-int(K) // 64)) // int(world)) * 64
+    k0 = min(int(K), per * int(rank))
+    return k0, min(int(K), k0 + per)
+
+
+def all_reduce_exchange(group=None):
+    """Exchange hook over torch.distributed (NCCL over NVLink on a GPU box): sum over the shards' tiles."""
+    import torch.distributed as dist
+
+    def fn(tile):
+        dist.all_reduce(tile, op=dist.ReduceOp.SUM, group=group)
+
+    return fn

@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=100)
+    ap.add_argument("--no-tp", action="store_true", help="skip the sharded-model measurement at N > 1")
     ap.add_argument("--group", type=int, default=4, help="replicates per GPU for the lockstep-group measurement (0/1 = skip)")
     args = ap.parse_args()
     workload = args.workload
@@ -398,6 +399,36 @@ def main():
                  "unit": "samples/s (all replicates)", "ms_per_step_per_replicate": gms / (ne_g * spe * G),
                  "what": "loc_group_train_epochs: hidden stacks of the G replicates share one launch"}
 
+    # ---- one model sharded over the ranks (SNP columns; one 32 KB all_reduce of the Z1 tile per forward) ----
+    tp = None
+    if world > 1 and m.impl == "tcgen05" and not args.no_tp:
+        xs, ys = (x, y) if rank == 0 else synth(ntr + nva, K, 1002)  # every shard sees the same samples
+        k0, k1 = model.shard_bounds(K, rank, world)
+        tm = model.LocatorModel(k1 - k0, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=64, seed=900,
+                                shard=(k0, K), exchange=model.all_reduce_exchange())
+        tm.bind_train(np.ascontiguousarray(xs[:ntr, k0:k1]), ys[:ntr])
+        tm.bind_val(np.ascontiguousarray(xs[ntr:, k0:k1]), ys[ntr:])
+        tm.set_schedule(patience=10 ** 6)
+        ne_t = max(2, min(10, steps // spe))
+        prng = np.random.default_rng(4242)  # the same batch order on every shard
+        pw = np.stack([prng.permutation(ntr) for _ in range(2)]).astype(np.int32)
+        pt = np.stack([prng.permutation(ntr) for _ in range(ne_t)]).astype(np.int32)
+        tm.train_epochs(pw)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        tm.train_epochs(pt)
+        t1.record()
+        torch.cuda.synchronize()
+        tms = max_over_ranks(t0.elapsed_time(t1), "cuda")
+        st_t = tm.state()
+        assert st_t.nonfinite == 0 and np.isfinite(st_t.last_loss), "non-finite loss in the sharded run"
+        tp = {"shards": world, "epochs": ne_t, "value": ne_t * ntr / (tms / 1000.0), "unit": "samples/s (one model)",
+              "ms_per_step": tms / (ne_t * spe), "scaling": "strong",
+              "what": "one cfg model sharded over SNP columns: W1 + Adam state K/N per GPU, hidden stack replicated, "
+                      "one all_reduce (NCCL) of the [32][256] first-layer tile per forward pass"}
+        del tm
+
     line = {
         "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps,
         "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -408,7 +439,7 @@ def main():
                    "l2": "inputs larger than L2 (W1+m+v = %.0f MB per step)" % (12.0 * K * H / 1e6),
                    "steps_per_epoch": spe, "validation_pass_every_epoch": True},
         "clocks": clk.summary(), "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
-        "replicate_group": group,
+        "replicate_group": group, "tensor_parallel": tp,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, dt = cpu_steps(xtr, ytr, xva, yva, args.cpu_steps, os.cpu_count() or 1)

@@ -404,30 +404,40 @@ def main():
     if world > 1 and m.impl == "tcgen05" and not args.no_tp:
         xs, ys = (x, y) if rank == 0 else synth(ntr + nva, K, 1002)  # every shard sees the same samples
         k0, k1 = model.shard_bounds(K, rank, world)
-        tm = model.LocatorModel(k1 - k0, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=64, seed=900,
-                                shard=(k0, K), exchange=model.all_reduce_exchange())
-        tm.bind_train(np.ascontiguousarray(xs[:ntr, k0:k1]), ys[:ntr])
-        tm.bind_val(np.ascontiguousarray(xs[ntr:, k0:k1]), ys[ntr:])
-        tm.set_schedule(patience=10 ** 6)
+        xt, xv = np.ascontiguousarray(xs[:ntr, k0:k1]), np.ascontiguousarray(xs[ntr:, k0:k1])
         ne_t = max(2, min(10, steps // spe))
-        prng = np.random.default_rng(4242)  # the same batch order on every shard
-        pw = np.stack([prng.permutation(ntr) for _ in range(2)]).astype(np.int32)
-        pt = np.stack([prng.permutation(ntr) for _ in range(ne_t)]).astype(np.int32)
-        tm.train_epochs(pw)
-        barrier()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        tm.train_epochs(pt)
-        t1.record()
-        torch.cuda.synchronize()
-        tms = max_over_ranks(t0.elapsed_time(t1), "cuda")
-        st_t = tm.state()
-        assert st_t.nonfinite == 0 and np.isfinite(st_t.last_loss), "non-finite loss in the sharded run"
-        tp = {"shards": world, "epochs": ne_t, "value": ne_t * ntr / (tms / 1000.0), "unit": "samples/s (one model)",
-              "ms_per_step": tms / (ne_t * spe), "scaling": "strong",
-              "what": "one cfg model sharded over SNP columns: W1 + Adam state K/N per GPU, hidden stack replicated, "
-                      "one all_reduce (NCCL) of the [32][256] first-layer tile per forward pass"}
-        del tm
+
+        def run_tp(exchange):
+            tm = model.LocatorModel(k1 - k0, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=64,
+                                    seed=900, shard=(k0, K), exchange=exchange)
+            tm.bind_train(xt, ys[:ntr])
+            tm.bind_val(xv, ys[ntr:])
+            tm.set_schedule(patience=10 ** 6)
+            prng = np.random.default_rng(4242)  # the same batch order on every shard
+            pw = np.stack([prng.permutation(ntr) for _ in range(2)]).astype(np.int32)
+            pt = np.stack([prng.permutation(ntr) for _ in range(ne_t)]).astype(np.int32)
+            tm.train_epochs(pw)
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            tm.train_epochs(pt)
+            t1.record()
+            torch.cuda.synchronize()
+            tms = max_over_ranks(t0.elapsed_time(t1), "cuda")
+            st_t = tm.state()
+            assert st_t.nonfinite == 0 and np.isfinite(st_t.last_loss), "non-finite loss in the sharded run"
+            barrier()
+            del tm
+            return {"value": ne_t * ntr / (tms / 1000.0), "ms_per_step": tms / (ne_t * spe)}
+
+        peer = run_tp("peer")
+        hook = run_tp(model.all_reduce_exchange())
+        tp = {"shards": world, "epochs": ne_t, "value": peer["value"], "unit": "samples/s (one model)",
+              "ms_per_step": peer["ms_per_step"], "scaling": "strong",
+              "with_nccl_all_reduce_hook": hook,
+              "what": "one cfg model sharded over SNP columns: W1 + Adam state K/N per GPU, hidden stack replicated; "
+                      "per forward pass every shard pushes its reduced [32][256] first-layer tile into the peers' "
+                      "buffers over NVLink (own kernels, cudaIpc peer memory) and the hidden kernel sums them"}
 
     line = {
         "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps,

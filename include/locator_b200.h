@@ -163,6 +163,20 @@ typedef int (*loc_exchange_fn)(void* ctx, float* d_tile, int64_t n, void* stream
 int loc_model_set_shard(loc_model* m, int64_t k_offset, int64_t K_global);
 int loc_model_set_exchange(loc_model* m, loc_exchange_fn fn, void* ctx, float* d_tile);
 
+/* Peer-memory exchange for sharded models on one NVLink / NVSwitch box (replaces the host hook: no library
+ * collective, no host call per step).  Every shard process: loc_tp_create -> loc_tp_handle (64-byte
+ * cudaIpc handle of its buffer) -> exchange the handles by any host means -> loc_tp_connect with all
+ * `world` handles in rank order -> loc_model_set_tp.  Per forward pass a shard then reduces its partial
+ * tiles, stores the result into its slot of every peer's buffer over NVLink and raises flags there; the
+ * hidden-stack kernel sums the slots in rank order.  loc_tp_error != 0: a peer never arrived (2 s timeout). */
+typedef struct loc_tp loc_tp;
+int loc_tp_create(loc_tp** out, int32_t rank, int32_t world, int32_t width);
+int loc_tp_handle(loc_tp* tp, uint8_t* h_handle64);
+int loc_tp_connect(loc_tp* tp, const uint8_t* h_handles /* [world][64] */);
+int loc_tp_error(loc_tp* tp);
+int loc_tp_destroy(loc_tp* tp);
+int loc_model_set_tp(loc_model* m, loc_tp* tp);
+
 /* lr, EarlyStopping patience (ReduceLROnPlateau patience = patience/6), and
  * reset of the callback state machine (best = +inf, waits = 0, epoch = 0). */
 int loc_model_set_schedule(loc_model* m, float lr, int32_t patience);

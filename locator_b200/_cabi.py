@@ -64,6 +64,12 @@ SIGNATURES = {
     "loc_model_get_adam": (C.c_int, [P, I32, P, P, I64, P]),
     "loc_model_set_shard": (C.c_int, [P, I64, I64]),
     "loc_model_set_exchange": (C.c_int, [P, P, P, P]),
+    "loc_tp_create": (C.c_int, [C.POINTER(P), I32, I32, I32]),
+    "loc_tp_handle": (C.c_int, [P, P]),
+    "loc_tp_connect": (C.c_int, [P, P]),
+    "loc_tp_error": (C.c_int, [P]),
+    "loc_tp_destroy": (C.c_int, [P]),
+    "loc_model_set_tp": (C.c_int, [P, P]),
     "loc_model_set_schedule": (C.c_int, [P, C.c_float, I32]),
     "loc_model_bind_train": (C.c_int, [P, P, I64, I64, P]),
     "loc_model_bind_val": (C.c_int, [P, P, I64, I64, P]),

@@ -156,6 +156,25 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   // ---- layer 0, first half: split-K partial tiles of Z1 for the own [8 x 64] block (fixed order).
   //      Issued before the rest of the prologue so that barrier / TMEM / bias set-up and the
   //      cluster start-up barrier run in the shadow of these L2 reads. ----
+  if (a.wait_flags != nullptr) {
+    // sharded model: the tiles are pushed by the peers over NVLink; one thread per (sender, block) flag
+    // polls the local flags (acquire.sys), the barrier orders everybody's loads behind them.  A peer that
+    // never arrives is reported after ~2 s instead of hanging the GPU.
+    if (tid < a.wait_count) {
+      const long long t0 = clock64();
+      const uint32_t* f = a.wait_flags + tid;
+      while (true) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int32_t)(v - a.wait_seq) >= 0) break;
+        if (clock64() - t0 > 4000000000ll) {
+          *a.wait_err = 1;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+  }
   const int p0_item = tid & 127, p0_g = tid >> 7;  // 128 float4 outputs x 4 partial groups
   const int p0_b = p0_item >> 4, p0_jl = (p0_item & 15) * 4;
   float4 p0_s = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -223,26 +223,19 @@ static L1Args l1_args(loc_model* m, const uint32_t* packed, int64_t row_words, c
 }
 
 // Sharded models: own split-K partial tiles -> one tile (fixed order), then the sum over shards.
-__global__ void __launch_bounds__(128) k_reduce_partials(const float* __restrict__ partials, int n_partials, float* out,
+__global__ void __launch_bounds__(512) k_reduce_partials(const float* __restrict__ partials, int n_partials, float* out,
                                                          int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int p = 0;
-  for (; p + 4 <= n_partials; p += 4) {
-    s0 += __ldcg(partials + (int64_t)p * n + i);
-    s1 += __ldcg(partials + (int64_t)(p + 1) * n + i);
-    s2 += __ldcg(partials + (int64_t)(p + 2) * n + i);
-    s3 += __ldcg(partials + (int64_t)(p + 3) * n + i);
-  }
-  for (; p < n_partials; ++p) s0 += __ldcg(partials + (int64_t)p * n + i);
-  out[i] = (s0 + s1) + (s2 + s3);
+  __shared__ float sred[4][128];
+  const float v = reduce_partial_tiles(partials, n_partials, n, sred);
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (threadIdx.x < 128 && i < n) out[i] = v;
 }
 
 static int exchange_partials(loc_model* m, cudaStream_t s) {
+  if (m->tp != nullptr) return tp_exchange(m->tp, m->partials, m->n_partials, s);
   if (m->exchange == nullptr) return 0;
   const int n = kMaxB * m->H;
-  k_reduce_partials<<<cdiv(n, 128), 128, 0, s>>>(m->partials, m->n_partials, m->z1_tile, n);
+  k_reduce_partials<<<cdiv(n, 128), 512, 0, s>>>(m->partials, m->n_partials, m->z1_tile, n);
   LOC_LAUNCHED();
   LOC_CHECK(m->exchange(m->exchange_ctx, m->z1_tile, n, (void*)s) == 0, "exchange hook failed");
   return 0;
@@ -261,8 +254,17 @@ static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated
   h.seed = m->seed;
   h.masks = m->masks;
   h.n_masks = m->n_masks;
+  h.wait_flags = nullptr;
+  h.wait_count = 0;
+  h.wait_seq = 0;
+  h.wait_err = nullptr;
   h.partials = m->exchange != nullptr ? m->z1_tile : m->partials;
   h.n_partials = m->exchange != nullptr ? 1 : m->n_partials;
+  if (m->tp != nullptr) {  // the shards' tiles of the latest exchange, summed in rank order by the kernel
+    h.partials = tp_tiles(m->tp);
+    h.n_partials = tp_world(m->tp);
+    tp_wait_info(m->tp, &h.wait_flags, &h.wait_count, &h.wait_seq, &h.wait_err);
+  }
   h.small = m->small;
   h.w_fs = m->w_fs;
   h.w_bs = m->w_bs;
@@ -634,6 +636,13 @@ int loc_model_set_exchange(loc_model* m, loc_exchange_fn fn, void* ctx, float* d
   return 0;
 }
 
+int loc_model_set_tp(loc_model* m, loc_tp* tp) {
+  LOC_CHECK(m != nullptr, "loc_model_set_tp: null model");
+  LOC_CHECK(tp == nullptr || (m->use_tc && m->hid_tc), "loc_model_set_tp: sharded models need the tcgen05 kernels (width 256)");
+  m->tp = tp;
+  return 0;
+}
+
 int loc_model_set_schedule(loc_model* m, float lr, int32_t patience) {
   LOC_CHECK(m != nullptr, "loc_model_set_schedule: null model");
   LOC_CHECK(patience >= 0, "loc_model_set_schedule: patience must be >= 0");
@@ -705,7 +714,7 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
     LOC_CHECK(m != nullptr && d_perms[g] != nullptr && m->train_packed != nullptr && m->val_packed != nullptr,
               "loc_group_train_epochs: every model needs bound training / validation data and a batch order");
     LOC_CHECK(m->hid_tc && m->use_tc, "loc_group_train_epochs: grouped replicates need the tcgen05 kernels (width 256)");
-    LOC_CHECK(m->exchange == nullptr, "loc_group_train_epochs: sharded models cannot be grouped");
+    LOC_CHECK(m->exchange == nullptr && m->tp == nullptr, "loc_group_train_epochs: sharded models cannot be grouped");
     LOC_CHECK(m->L == m0->L && m->B == m0->B && m->n_train == m0->n_train,
               "loc_group_train_epochs: replicates of a group must share nlayers, batch size and training-set size");
   }

@@ -88,6 +88,11 @@ struct HidArgs {
   int64_t n_masks;
   const float* partials;
   int n_partials;
+  // sharded models (tp.cu): the partial tiles are the shards' tiles, complete once every flag >= wait_seq
+  const uint32_t* wait_flags;
+  int wait_count;
+  uint32_t wait_seq;
+  int* wait_err;
   float* small;
   const float* w_fs;  // forward slices of the hidden kernels  [L-1][C][H][Hc]
   const float* w_bs;  // backward slices (transposed)          [L-1][C][H][Hc]
@@ -146,6 +151,37 @@ int l1_tc_partials(int64_t K);
 
 }  // namespace loc
 
+struct loc_tp;
+namespace loc {
+// Sum over the split-K partial tiles of element i = blockIdx.x * 128 + (threadIdx.x & 127), for 512-thread
+// blocks: four thread groups take a quarter of the tiles each (16 loads in flight per thread), fixed order.
+// Valid in threads < 128 after the call.
+__device__ __forceinline__ float reduce_partial_tiles(const float* __restrict__ partials, int n_partials, int n,
+                                                      float (*sred)[128]) {
+  const int e = threadIdx.x & 127, g = threadIdx.x >> 7;
+  const int i = blockIdx.x * 128 + e;
+  const int pbeg = n_partials * g / 4, pend = n_partials * (g + 1) / 4;
+  float s0 = 0.f, s1 = 0.f;
+  if (i < n) {
+    int p = pbeg;
+#pragma unroll 8
+    for (; p + 2 <= pend; p += 2) {
+      s0 += __ldcg(partials + (int64_t)p * n + i);
+      s1 += __ldcg(partials + (int64_t)(p + 1) * n + i);
+    }
+    if (p < pend) s0 += __ldcg(partials + (int64_t)p * n + i);
+  }
+  sred[g][e] = s0 + s1;
+  __syncthreads();
+  return (sred[0][e] + sred[1][e]) + (sred[2][e] + sred[3][e]);
+}
+
+int tp_exchange(loc_tp* tp, const float* partials, int n_partials, cudaStream_t s);
+const float* tp_tiles(const loc_tp* tp);
+void tp_wait_info(const loc_tp* tp, const uint32_t** flags, int* count, uint32_t* seq, int** err);
+int tp_world(const loc_tp* tp);
+}  // namespace loc
+
 struct loc_model {
   int dev;
   int64_t K;
@@ -184,4 +220,5 @@ struct loc_model {
   int (*exchange)(void* ctx, float* d_tile, int64_t n, void* stream);
   void* exchange_ctx;
   float* z1_tile;  // caller-owned [kMaxB][H]: own partial sum, then the sum over shards
+  struct loc_tp* tp;  // peer-memory exchange (tp.cu) instead of the host hook
 };

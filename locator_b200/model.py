@@ -47,7 +47,10 @@ class LocatorModel:
         if shard is not None:
             self.shard = (int(shard[0]), int(shard[1]))
             check(lib.loc_model_set_shard(self._h, self.shard[0], self.shard[1]), "loc_model_set_shard")
-        if exchange is not None:
+        self._tp = None
+        if isinstance(exchange, str) and exchange == "peer":
+            self.connect_peers()
+        elif exchange is not None:
             self.set_exchange(exchange)
         check(lib.loc_model_init(self._h, self.seed, _stream()), "loc_model_init")
         self._wver = 0   # bumped whenever the weights may have changed (prediction memo key)
@@ -63,6 +66,33 @@ class LocatorModel:
                 pass
             lib.loc_model_destroy(h)
             self._h = None
+            tp = getattr(self, "_tp", None)
+            if tp:
+                lib.loc_tp_destroy(tp)
+                self._tp = None
+
+    def connect_peers(self, group=None):
+        """Exchange through NVLink peer memory (loc_tp_*): the shards of one box map each other's tile buffers
+        (cudaIpc handles travel through torch.distributed) and push / flag / sum without any library collective
+        or host call per step.  One process per GPU, ranks of `group` = shards in column order."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        tp = C.c_void_p()
+        check(lib.loc_tp_create(C.byref(tp), rank, world, self.width), "loc_tp_create")
+        buf = (C.c_uint8 * 64)()
+        check(lib.loc_tp_handle(tp, buf), "loc_tp_handle")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(buf), group=group)
+        allh = b"".join(handles)
+        check(lib.loc_tp_connect(tp, allh), "loc_tp_connect")
+        dist.barrier(group)  # every shard has mapped every buffer before the first push
+        check(lib.loc_model_set_tp(self._h, tp), "loc_model_set_tp")
+        self._tp = tp
+
+    def check_peers(self):
+        if self._tp is not None and lib.loc_tp_error(self._tp) != 0:
+            raise _cabi.LocatorCudaError("sharded model: a peer's tile never arrived (2 s timeout in the exchange)")
 
     def set_exchange(self, fn):
         """fn(tile): in-place sum of the [32 * width] float32 CUDA tensor over all shards, enqueued on the
@@ -179,6 +209,7 @@ class LocatorModel:
     def state(self) -> LocState:
         st = LocState()
         check(lib.loc_model_state(self._h, C.byref(st), _stream()), "loc_model_state")
+        self.check_peers()
         return st
 
     def train_step(self, rows):

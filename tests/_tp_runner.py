@@ -18,6 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     out = sys.argv[1]
     backend = sys.argv[2] if len(sys.argv) > 2 else "gloo"
+    mode = sys.argv[3] if len(sys.argv) > 3 else "hook"  # hook: all_reduce through the process group; peer: NVLink peer memory
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(rank % torch.cuda.device_count())
     dist.init_process_group(backend)
@@ -33,7 +34,8 @@ def main():
     perms = np.stack([rng.permutation(ntr) for _ in range(epochs)]).astype(np.int32)
 
     k0, k1 = M.shard_bounds(K, rank, world)
-    m = M.LocatorModel(k1 - k0, seed=5, max_epochs=epochs, shard=(k0, K), exchange=M.all_reduce_exchange())
+    m = M.LocatorModel(k1 - k0, seed=5, max_epochs=epochs, shard=(k0, K),
+                       exchange="peer" if mode == "peer" else M.all_reduce_exchange())
     res = {"impl": m.impl, "bounds": [k0, k1]}
     w_init = m.get_weights()[4]
     m.bind_train(x[:, k0:k1], y)
@@ -41,6 +43,7 @@ def main():
     m.set_schedule(patience=100)
     m.train_epochs(perms)
     torch.cuda.synchronize()
+    m.check_peers()
     hist = np.asarray(m.history_rows(epochs), dtype=np.float64)
     pred = m.predict(xv[:, k0:k1])
     w1 = m.get_weights()[4]

@@ -1,7 +1,8 @@
 """One model sharded over SNP columns (tensor parallelism): two shards exchanging the
 first-layer tile through an all_reduce must reproduce the unsharded model -- identical initial weights,
 identical replicas of the hidden stack on every shard, losses / predictions within the tf32 tolerance (the
-only difference is the fp32 summation order of the split-K partial sums)."""
+only difference is the fp32 summation order of the split-K partial sums).  Two exchanges are covered: the host
+hook (torch.distributed all_reduce) and the peer-memory kernels (loc_tp_*: push over cudaIpc-mapped buffers)."""
 import json
 import os
 import socket
@@ -22,13 +23,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def test_two_shards_match_the_unsharded_model(tmp_path):
+@pytest.mark.parametrize("mode", ["hook", "peer"])
+def test_two_shards_match_the_unsharded_model(tmp_path, mode):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     out = tmp_path / "tp.json"
     backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "_tp_runner.py"), str(out), backend]
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "_tp_runner.py"), str(out), backend, mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.load(open(out))

@@ -352,6 +352,10 @@ def main():
                                 seed=300 + rank)
         xtr_p = torch.from_numpy(xtr).pin_memory()
         xva_p = torch.from_numpy(xva).pin_memory()
+        # warm-up of the same public call (one epoch): first pinned transfer, allocator growth, lazy kernel loads
+        mw = model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=2, seed=299 + rank)
+        mw.fit(xtr_p, ytr, epochs=1, validation_data=(xva_p, yva), patience=10 ** 6)
+        del mw
         barrier()
         t0 = time.perf_counter()
         h = m2.fit(xtr_p, ytr, epochs=ne, validation_data=(xva_p, yva), patience=10 ** 6, epochs_per_call=ne)

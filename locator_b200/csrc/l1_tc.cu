@@ -443,21 +443,37 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     fence_barrier_init();
   }
   if (warp == B_EPI_WARPS) tmem_alloc(tmem_slot, 512);
-  // dZ1 -> hi/lo tf32 operands, [chunk = j/32][row = b][swizzled 32 j]
-  for (int i = threadIdx.x; i < kMaxB * kH / 4; i += B_THREADS) {
-    const int b = i / (kH / 4), j4 = (i % (kH / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (b < nb) v = __ldcg(reinterpret_cast<const float4*>(a.dZ1 + b * kH + j4));
-    const float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-    const float4 lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z), to_tf32(v.w - hi.w));
-    const uint32_t off = (uint32_t)((j4 >> 5) * B_DZ_CHUNK) + swz32(b, (j4 & 31) >> 2);
-    *reinterpret_cast<float4*>(sDZhi + off) = hi;
-    *reinterpret_cast<float4*>(sDZlo + off) = lo;
-  }
-  fence_proxy_async();
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();  // barriers and TMEM are ready: the load warp starts streaming W1 | m | v right away ...
   tc_fence_after();
+  if (warp != B_EPI_WARPS + 2) {
+    // ... while everybody else stages dZ1 -> hi/lo tf32 operands, [chunk = j/32][row = b][swizzled 32 j]
+    // (all of a thread's loads first: one L2 round trip instead of three)
+    constexpr int kIters = (kMaxB * kH / 4 + B_THREADS - 33) / (B_THREADS - 32);
+    const int t = threadIdx.x < (B_EPI_WARPS + 2) * 32 ? threadIdx.x : threadIdx.x - 32;  // skip the load warp
+    float4 v[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int i = t + it * (B_THREADS - 32);
+      const int b = i / (kH / 4), j4 = (i % (kH / 4)) * 4;
+      v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < kMaxB * kH / 4 && b < nb) v[it] = __ldcg(reinterpret_cast<const float4*>(a.dZ1 + b * kH + j4));
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int i = t + it * (B_THREADS - 32);
+      if (i >= kMaxB * kH / 4) break;
+      const int b = i / (kH / 4), j4 = (i % (kH / 4)) * 4;
+      const float4 hi = make_float4(to_tf32(v[it].x), to_tf32(v[it].y), to_tf32(v[it].z), to_tf32(v[it].w));
+      const float4 lo = make_float4(to_tf32(v[it].x - hi.x), to_tf32(v[it].y - hi.y), to_tf32(v[it].z - hi.z),
+                                    to_tf32(v[it].w - hi.w));
+      const uint32_t off = (uint32_t)((j4 >> 5) * B_DZ_CHUNK) + swz32(b, (j4 & 31) >> 2);
+      *reinterpret_cast<float4*>(sDZhi + off) = hi;
+      *reinterpret_cast<float4*>(sDZlo + off) = lo;
+    }
+    fence_proxy_async();
+    asm volatile("bar.sync 3, %0;" ::"n"(B_THREADS - 32) : "memory");  // everyone but the load warp
+  }
   const uint32_t tmem = *tmem_slot;
   const float alpha = a.st->alpha;
   if (warp < B_EPI_WARPS) {
@@ -466,7 +482,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     const int h = w8 >> 2, q = w8 & 3;
     const int j = h * 128 + q * 32 + lane;
     float c0 = 0.f;
-    for (int b = 0; b < nb; ++b) c0 += __ldcg(a.dZ1 + b * kH + j);
+    {  // all loads in flight at once; summed in row order
+      float dz[kMaxB];
+#pragma unroll
+      for (int b = 0; b < kMaxB; ++b) dz[b] = b < nb ? __ldcg(a.dZ1 + b * kH + j) : 0.f;
+#pragma unroll
+      for (int b = 0; b < kMaxB; ++b) c0 += dz[b];
+    }
     for (int c = grp; c < nchunks; c += 2) {
       const int li = c >> 3, cc = c & 7;
       const int buf = li & 1;

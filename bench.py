@@ -434,9 +434,13 @@ def main():
             del tm
             return {"value": ne_t * ntr / (tms / 1000.0), "ms_per_step": tms / (ne_t * spe)}
 
-        peer = run_tp("peer")
-        hook = run_tp(model.all_reduce_exchange())
-        tp = {"shards": world, "epochs": ne_t, "value": peer["value"], "unit": "samples/s (one model)",
+        try:
+            peer = run_tp("peer")
+            hook = run_tp(model.all_reduce_exchange())
+        except Exception as exc:  # the sharded measurement is an extra: never lose the bench line over it
+            peer = hook = None
+            tp_error = f"{type(exc).__name__}: {exc}"
+        tp = {"error": tp_error} if peer is None else {"shards": world, "epochs": ne_t, "value": peer["value"], "unit": "samples/s (one model)",
               "ms_per_step": peer["ms_per_step"], "scaling": "strong",
               "with_nccl_all_reduce_hook": hook,
               "what": "one cfg model sharded over SNP columns: W1 + Adam state K/N per GPU, hidden stack replicated; "

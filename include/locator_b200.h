@@ -118,6 +118,14 @@ int loc_replace_cols(uint32_t* d_packed, int64_t n, int64_t row_words, const int
  * from host memory into host memory.  Returns the decompressed size or < 0 on error. */
 int64_t loc_blosc_decompress(const uint8_t* h_src, int64_t src_len, uint8_t* h_dst, int64_t dst_len);
 
+/* Host helpers for load_genotypes' VCF branch (allel.read_vcf, locator.py:195-199): data lines of an
+ * uncompressed VCF text buffer -> GT int8 [n_variants][n_samples][2] (missing allele -1, haploid call ->
+ * second allele -1, first two alleles of a polyploid call) and POS.  loc_vcf_count gives n_variants;
+ * loc_vcf_parse_gt parses with n_threads host threads and fails (return 1) on a line it cannot parse. */
+int64_t loc_vcf_count(const char* h_buf, int64_t len);
+int loc_vcf_parse_gt(const char* h_buf, int64_t len, int64_t n_samples, int64_t n_variants, int8_t* h_gt, int64_t* h_pos,
+                     int32_t n_threads);
+
 /* ---------------- model (K3-K7) ---------------- */
 
 /* BN(K) -> Dense(width, elu) x nlayers (Dropout after the floor(nlayers/2)-th)

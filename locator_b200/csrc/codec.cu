@@ -126,3 +126,164 @@ int64_t loc_blosc_decompress(const uint8_t* src, int64_t src_len, uint8_t* dst, 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// VCF text -> GT cube (the allel.read_vcf(...)['calldata/GT'] of load_genotypes, locator.py:195-199):
+// int8 [n_variants][n_samples][2], missing allele = -1, haploid call -> second allele -1, plus POS.
+// Data lines are indexed once, then parsed by n_threads host threads over disjoint line ranges.
+// ---------------------------------------------------------------------------------------------
+#include <thread>
+
+namespace {
+
+struct VcfLines {
+  std::vector<int64_t> beg, end;  // [beg, end) of every data line, '\r' stripped
+};
+
+void vcf_index(const char* buf, int64_t len, VcfLines& L) {
+  int64_t p = 0;
+  while (p < len) {
+    const char* nl = (const char*)memchr(buf + p, '\n', (size_t)(len - p));
+    int64_t e = nl ? (nl - buf) : len;
+    int64_t ee = e;
+    if (ee > p && buf[ee - 1] == '\r') --ee;
+    if (ee > p && buf[p] != '#') {
+      L.beg.push_back(p);
+      L.end.push_back(ee);
+    }
+    p = e + 1;
+  }
+}
+
+// one allele token [s, e): "." / "" -> -1, digits -> value; anything else -> error
+inline bool parse_allele(const char* s, const char* e, int8_t& out) {
+  if (s == e || (e - s == 1 && *s == '.')) {
+    out = -1;
+    return true;
+  }
+  int v = 0;
+  for (const char* c = s; c < e; ++c) {
+    if (*c < '0' || *c > '9') return false;
+    v = v * 10 + (*c - '0');
+    if (v > 127) return false;
+  }
+  out = (int8_t)v;
+  return true;
+}
+
+bool vcf_parse_line(const char* s, const char* e, int64_t n_samples, int8_t* gt, int64_t* pos) {
+  // fields: CHROM POS ID REF ALT QUAL FILTER INFO FORMAT sample...
+  const char* f = s;
+  const char* fld[10];
+  int nf = 0;
+  fld[nf++] = f;
+  while (nf < 10) {
+    const char* t = (const char*)memchr(f, '\t', (size_t)(e - f));
+    if (!t) break;
+    f = t + 1;
+    fld[nf++] = f;
+  }
+  if (nf < 9) return false;
+  {  // POS
+    int64_t v = 0;
+    const char* c = fld[1];
+    if (c >= fld[2] - 1) return false;
+    for (; c < fld[2] - 1; ++c) {
+      if (*c < '0' || *c > '9') return false;
+      v = v * 10 + (*c - '0');
+    }
+    *pos = v;
+  }
+  // index of the GT key in FORMAT
+  const char* fmt_e = nf >= 10 ? fld[9] - 1 : e;
+  int gi = -1, k = 0;
+  for (const char* c = fld[8]; c <= fmt_e;) {
+    const char* t = (const char*)memchr(c, ':', (size_t)(fmt_e - c));
+    const char* ke = t ? t : fmt_e;
+    if (ke - c == 2 && c[0] == 'G' && c[1] == 'T') {
+      gi = k;
+      break;
+    }
+    if (!t) break;
+    c = t + 1;
+    ++k;
+  }
+  if (gi < 0) return false;
+  for (int64_t i = 0; i < 2 * n_samples; ++i) gt[i] = -1;
+  if (nf < 10) return true;
+  const char* c = fld[9];
+  for (int64_t smp = 0; smp < n_samples && c <= e; ++smp) {
+    const char* t = (const char*)memchr(c, '\t', (size_t)(e - c));
+    const char* se = t ? t : e;
+    // gi-th colon-separated subfield
+    const char* a = c;
+    for (int q = 0; q < gi && a; ++q) {
+      const char* col = (const char*)memchr(a, ':', (size_t)(se - a));
+      a = col ? col + 1 : nullptr;
+    }
+    if (a) {
+      const char* col = (const char*)memchr(a, ':', (size_t)(se - a));
+      const char* ae = col ? col : se;
+      // alleles separated by '/' or '|' (the first two are kept)
+      const char* sep = a;
+      while (sep < ae && *sep != '/' && *sep != '|') ++sep;
+      if (!parse_allele(a, sep, gt[2 * smp])) return false;
+      if (sep < ae) {
+        const char* b = sep + 1;
+        const char* sep2 = b;
+        while (sep2 < ae && *sep2 != '/' && *sep2 != '|') ++sep2;
+        if (!parse_allele(b, sep2, gt[2 * smp + 1])) return false;
+      }
+    } else {
+      return false;  // the sample field has fewer subfields than FORMAT promises
+    }
+    if (!t) break;
+    c = t + 1;
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Number of data lines (variants) in an uncompressed VCF text buffer.
+int64_t loc_vcf_count(const char* h_buf, int64_t len) {
+  if (h_buf == nullptr || len < 0) return -1;
+  VcfLines L;
+  vcf_index(h_buf, len, L);
+  return (int64_t)L.beg.size();
+}
+
+// GT int8 [n_variants][n_samples][2] and POS int64 [n_variants] of every data line.  Returns 0, or 1 with
+// loc_last_error set when a line cannot be parsed (the caller may fall back to a slower, more lenient reader).
+int loc_vcf_parse_gt(const char* h_buf, int64_t len, int64_t n_samples, int64_t n_variants, int8_t* h_gt, int64_t* h_pos,
+                     int32_t n_threads) {
+  LOC_CHECK(h_buf != nullptr && h_gt != nullptr && h_pos != nullptr && n_samples >= 0 && n_variants >= 0,
+            "loc_vcf_parse_gt: bad arguments");
+  VcfLines L;
+  vcf_index(h_buf, len, L);
+  LOC_CHECK((int64_t)L.beg.size() == n_variants, "loc_vcf_parse_gt: n_variants does not match the buffer (loc_vcf_count)");
+  int nt = n_threads < 1 ? 1 : (n_threads > 64 ? 64 : n_threads);
+  if (n_variants < 4 * nt) nt = 1;
+  std::vector<int> bad((size_t)nt, 0);
+  auto work = [&](int t) {
+    const int64_t v0 = n_variants * t / nt, v1 = n_variants * (t + 1) / nt;
+    for (int64_t v = v0; v < v1; ++v)
+      if (!vcf_parse_line(h_buf + L.beg[(size_t)v], h_buf + L.end[(size_t)v], n_samples, h_gt + v * n_samples * 2, h_pos + v)) {
+        bad[(size_t)t] = 1;
+        return;
+      }
+  };
+  if (nt == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  for (int b : bad) LOC_CHECK(b == 0, "loc_vcf_parse_gt: a data line could not be parsed (no GT key, bad POS or allele)");
+  return 0;
+}
+
+}  // extern "C"

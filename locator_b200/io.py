@@ -53,6 +53,28 @@ def _parse_allele(tok):
     return -1 if tok in (b".", b"") else int(tok)
 
 
+def _read_vcf_native(data):
+    """The library's multithreaded parser (loc_vcf_parse_gt); None when it declines a line (the Python
+    parser below then either handles the oddity or raises the error a user should see)."""
+    from ._cabi import lib
+
+    h = data.find(b"#CHROM")
+    if h < 0 or (h > 0 and data[h - 1:h] != b"\n"):
+        return None
+    e = data.find(b"\n", h)
+    header = data[h:e if e >= 0 else len(data)].rstrip(b"\r").rstrip(b"\t").split(b"\t")
+    samples = np.array([s.decode() for s in header[9:]], dtype=str)
+    n = len(samples)
+    nvar = int(lib.loc_vcf_count(data, len(data)))
+    if nvar < 0:
+        return None
+    gt = np.empty((nvar, n, 2), dtype=np.int8)
+    pos = np.empty(nvar, dtype=np.int64)
+    if nvar and lib.loc_vcf_parse_gt(data, len(data), n, nvar, gt.ctypes.data, pos.ctypes.data, min(16, os.cpu_count() or 1)) != 0:
+        return None
+    return {"calldata/GT": gt, "samples": samples, "variants/POS": pos}
+
+
 def read_vcf(path):
     """VCF / VCF.gz -> dict like allel.read_vcf: 'calldata/GT', 'samples', 'variants/POS'.
 
@@ -61,6 +83,10 @@ def read_vcf(path):
     keys, haploid calls -> second allele -1).
     """
     data = _open_bytes(path)
+    if not os.environ.get("LOC_PY_VCF"):
+        fast = _read_vcf_native(data)
+        if fast is not None:
+            return fast
     samples = None
     gts, pos = [], []
     for line in data.split(b"\n"):

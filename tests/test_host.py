@@ -205,3 +205,46 @@ def test_summarize_centroids_and_kernel_peaks(tmp_path):
     xs, ys = g.xpred.to_numpy(), g.ypred.to_numpy()
     dens = [np.exp(-((xs - a) ** 2 + (ys - b) ** 2) / (2 * 0.2 ** 2)).sum() for a, b in zip(xs, ys)]
     assert (xs[int(np.argmax(dens))], ys[int(np.argmax(dens))]) == (t.loc["a", "kd_x"], t.loc["a", "kd_y"])
+
+
+def test_native_vcf_parser_matches_python_reader(tmp_path, monkeypatch):
+    """loc_vcf_parse_gt (multithreaded host parser in the library) vs the per-field Python reader on the
+    cases allel.read_vcf handles: phased / unphased, missing, haploid, multi-digit alleles, GT not first in
+    FORMAT, CRLF line ends, polyploid calls (first two alleles), short lines."""
+    import gzip
+
+    from locator_b200 import io
+
+    rng = np.random.default_rng(8)
+    n = 7
+    lines = ["##fileformat=VCFv4.2", "##source=test",
+             "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n))]
+    calls = ["0|1", "1/1", "./.", ".|.", "0", ".", "10/2", "1|0|1", "0/1:35:99", "./.:.:."]
+    for v in range(300):
+        fmt = "GT" if v % 3 else "GT:DP:GQ"
+        row = [str(rng.choice(calls[:8] if fmt == "GT" else calls)) for _ in range(n)]
+        if fmt != "GT":
+            row = [c if ":" in c else c + ":7:50" for c in row]
+        if v % 50 == 7:
+            fmt, row = "DP:GT", ["12:" + c.split(":")[0] for c in row]
+        lines.append(f"1\t{100 + 13 * v}\t.\tA\tC,G\t.\tPASS\t.\t{fmt}\t" + "\t".join(row))
+    lines.append("1\t99999\t.\tA\tC\t.\tPASS\t.\tGT\t0|1\t1|1")  # fewer sample columns: the rest stay missing
+    text = ("\r\n".join(lines[:40]) + "\r\n" + "\n".join(lines[40:]) + "\n").encode()
+    p = tmp_path / "odd.vcf.gz"
+    with gzip.open(p, "wb") as fh:
+        fh.write(text)
+    fast = io.read_vcf(str(p))
+    monkeypatch.setenv("LOC_PY_VCF", "1")
+    slow = io.read_vcf(str(p))
+    monkeypatch.delenv("LOC_PY_VCF")
+    assert fast["calldata/GT"].shape == (301, n, 2) and fast["calldata/GT"].dtype == np.int8
+    for k in ("calldata/GT", "samples", "variants/POS"):
+        assert np.array_equal(fast[k], slow[k]), k
+    assert fast["calldata/GT"].max() == 10 and fast["calldata/GT"].min() == -1
+    assert (fast["calldata/GT"][-1, 2:] == -1).all() and list(fast["calldata/GT"][-1, 0]) == [0, 1]
+    # a line the native parser declines (no GT key) is left to the Python reader, which raises
+    bad = tmp_path / "bad.vcf"
+    bad.write_text("\n".join(lines[:3] + ["1\t5\t.\tA\tC\t.\tPASS\t.\tDP\t" + "\t".join(["3"] * n)]) + "\n")
+    assert io._read_vcf_native(bad.read_bytes()) is None
+    with pytest.raises(ValueError):
+        io.read_vcf(str(bad))

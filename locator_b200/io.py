@@ -17,26 +17,49 @@ import numpy as np
 
 
 class Genotypes:
-    """GT int8 [nvar, N, 2] (missing = -1) + sample IDs (+ positions), as allel.GenotypeArray is used."""
+    """GT int8 [nvar, N, 2] (missing = -1) + sample IDs (+ positions), as allel.GenotypeArray is used.
+
+    ``gt`` may be a ZarrRows (chunked store on disk): nothing is decoded until ``.gt`` is read, and a
+    variant slice ``g[a:b]`` only decodes the chunks that overlap it (the windows driver, locator.py:538).
+    """
 
     def __init__(self, gt, samples=None, positions=None):
-        self.gt = np.ascontiguousarray(gt, dtype=np.int8)
-        assert self.gt.ndim == 3 and self.gt.shape[2] == 2
+        if isinstance(gt, ZarrRows):
+            self._lazy, self._gt = gt, None
+            assert len(gt.shape) == 3 and gt.shape[2] == 2
+        else:
+            self._lazy, self._gt = None, np.ascontiguousarray(gt, dtype=np.int8)
+            assert self._gt.ndim == 3 and self._gt.shape[2] == 2
         self.samples = None if samples is None else np.asarray(samples)
         self.positions = None if positions is None else np.asarray(positions)
 
     @property
+    def gt(self):
+        if self._gt is None:
+            self._gt = np.ascontiguousarray(self._lazy.read(), dtype=np.int8)
+        return self._gt
+
+    @property
+    def lazy(self):
+        """(store path, array name, first row, end row) while nothing has been decoded, else None."""
+        return None if self._gt is not None or self._lazy is None else self._lazy.where()
+
+    @property
     def shape(self):
-        return self.gt.shape
+        return self._gt.shape if self._gt is not None else self._lazy.shape
 
     def __len__(self):
-        return self.gt.shape[0]
+        return self.shape[0]
 
     def __getitem__(self, key):
         """Variant slicing (gt[a:b] / gt[a:b, :, :]) as the windows driver does (locator.py:538)."""
         if isinstance(key, tuple):
             key = key[0]
-        return Genotypes(self.gt[key], self.samples, None if self.positions is None else self.positions[key])
+        pos = None if self.positions is None else self.positions[key]
+        if self._gt is None and isinstance(key, slice) and key.step in (None, 1):
+            a, b, _ = key.indices(self._lazy.shape[0])
+            return Genotypes(self._lazy.rows(a, max(a, b)), self.samples, pos)
+        return Genotypes(self.gt[key], self.samples, pos)
 
 
 def _open_bytes(path):
@@ -176,7 +199,31 @@ def _decode_vlen_utf8(buf):
     return np.array(out, dtype=object)
 
 
-def _zarr_array(root, name):
+class ZarrRows:
+    """Rows [a, b) of a chunked zarr-v2 array, decoded on demand."""
+
+    def __init__(self, root, name, a=None, b=None):
+        self.root, self.name = root, name
+        with open(os.path.join(root, name, ".zarray")) as fh:
+            meta = json.load(fh)
+        full = tuple(meta["shape"])
+        self.a = 0 if a is None else int(a)
+        self.b = full[0] if b is None else int(b)
+        self.shape = (self.b - self.a,) + full[1:]
+        self.dtype = np.dtype(meta["dtype"])
+
+    def rows(self, a, b):
+        return ZarrRows(self.root, self.name, self.a + a, self.a + b)
+
+    def where(self):
+        return (self.root, self.name, self.a, self.b)
+
+    def read(self):
+        return _zarr_array(self.root, self.name, rows=(self.a, self.b))
+
+
+def _zarr_array(root, name, rows=None):
+    """The whole array, or (rows = (a, b)) only its first-axis range [a, b): just the chunks that overlap."""
     adir = os.path.join(root, name)
     with open(os.path.join(adir, ".zarray")) as fh:
         meta = json.load(fh)
@@ -193,10 +240,19 @@ def _zarr_array(root, name):
         raise ValueError(f"{name}: object arrays are only supported with the vlen-utf8 filter")
     if not is_obj and filters:
         raise ValueError(f"{name}: zarr filters {filters!r} are not supported")
-    out = np.empty(shape, dtype=dtype)
+    r0, r1 = (0, shape[0]) if (rows is None or not shape) else (max(0, int(rows[0])), min(shape[0], int(rows[1])))
+    out_shape = ((max(0, r1 - r0),) + shape[1:]) if shape else shape
+    out = np.empty(out_shape, dtype=dtype)
     out[...] = ("" if is_obj else 0) if fill in (None, "") or is_obj else fill
     grid = [(-(-s // c)) for s, c in zip(shape, chunks)]
-    for idx in np.ndindex(*grid) if shape else [()]:
+    if shape and r1 > r0:
+        first = range(r0 // chunks[0], -(-r1 // chunks[0]))
+        indices = ((i,) + rest for i in first for rest in np.ndindex(*grid[1:]))
+    elif shape:
+        indices = iter(())
+    else:
+        indices = [()]
+    for idx in indices:
         fn = os.path.join(adir, sep.join(str(i) for i in idx) if shape else "0")
         if not os.path.exists(fn):
             continue
@@ -216,14 +272,20 @@ def _zarr_array(root, name):
         else:
             chunk = np.frombuffer(buf, dtype=dtype).reshape(chunks)
         sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, shape))
-        out[sl] = chunk[tuple(slice(0, s.stop - s.start) for s in sl)]
+        if not shape:
+            out[...] = chunk.reshape(())
+            continue
+        lo, hi = max(sl[0].start, r0), min(sl[0].stop, r1)  # rows of this chunk inside the requested range
+        src = (slice(lo - sl[0].start, hi - sl[0].start),) + tuple(slice(0, x.stop - x.start) for x in sl[1:])
+        out[(slice(lo - r0, hi - r0),) + sl[1:]] = chunk[src]
     return out
 
 
-def read_zarr(path):
-    """zarr v2 group with calldata/GT, samples, variants/POS -> dict (arrays fully loaded, like gt[:])."""
+def read_zarr(path, lazy=False):
+    """zarr v2 group with calldata/GT, samples, variants/POS -> dict (arrays fully loaded, like gt[:]; with
+    lazy=True calldata/GT is a ZarrRows that decodes row ranges on demand)."""
     return {
-        "calldata/GT": _zarr_array(path, "calldata/GT"),
+        "calldata/GT": ZarrRows(path, "calldata/GT") if lazy else _zarr_array(path, "calldata/GT"),
         "samples": _zarr_array(path, "samples"),
         "variants/POS": _zarr_array(path, "variants/POS"),
     }

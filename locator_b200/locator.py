@@ -159,7 +159,7 @@ def load_genotypes():
 
     if args.zarr is not None:
         print("reading zarr")
-        callset = io.read_zarr(args.zarr)
+        callset = io.read_zarr(args.zarr, lazy=True)  # calldata/GT is decoded on first use (row ranges for --windows)
         genotypes = io.Genotypes(callset["calldata/GT"], callset["samples"], callset["variants/POS"])
         samples = callset["samples"]
     elif args.vcf is not None:
@@ -235,6 +235,12 @@ def filter_snps(genotypes):
     return ac
 
 
+def windows_are_data_independent():
+    """True when no draw from numpy's global stream depends on the genotypes (no imputation, no SNP
+    subsampling): a window's random indices can then be drawn before anybody has read its genotypes."""
+    return not args.impute_missing and args.max_SNPs is None
+
+
 def normalize_locs(locs):
     meanlong = np.nanmean(locs[:, 0])
     sdlong = np.nanstd(locs[:, 0])
@@ -244,7 +250,9 @@ def normalize_locs(locs):
     return meanlong, sdlong, meanlat, sdlat, locs
 
 
-def split_train_test(ac, locs):
+def draw_split(locs):
+    """The index draws of split_train_test (locator.py:296-302) without touching the genotypes: the
+    validation samples come from numpy's global stream, everything else is deterministic."""
     train = np.argwhere(~np.isnan(locs[:, 0]))
     train = np.array([x[0] for x in train])
     tr = set(train.tolist())
@@ -252,6 +260,11 @@ def split_train_test(ac, locs):
     test = np.random.choice(train, round((1 - args.train_split) * len(train)), replace=False)
     te = set(test.tolist())
     train = np.array([x for x in train if x not in te])
+    return train, test, pred
+
+
+def split_train_test(ac, locs, drawn=None):
+    train, test, pred = draw_split(locs) if drawn is None else drawn
     traingen = ac.take_samples(train)
     trainlocs = locs[train]
     testgen = ac.take_samples(test)
@@ -414,9 +427,17 @@ def main(argv=None):
     genotypes, samples = load_genotypes()
     sample_data, locs = sort_samples(samples, genotypes)
     meanlong, sdlong, meanlat, sdlat, locs = normalize_locs(locs)
-    ac = filter_snps(genotypes)
-    train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = split_train_test(ac, locs)
     norm = (meanlong, sdlong, meanlat, sdlat)
+    if args.windows and args.zarr is not None and windows_are_data_independent():
+        # The reference filters and splits the whole genome before its window loop (main :500-517) and then
+        # never uses the result; only the split's draws matter for what follows.  Take the draws, leave the
+        # genome on disk: every window decodes just its own chunks (possibly inside a worker process).
+        print("filtering SNPs\n(windows run: the genome-wide matrix is not materialised; every window is filtered on its own)")
+        draw_split(locs)
+        ac = traingen = testgen = predgen = None
+    else:
+        ac = filter_snps(genotypes)
+        train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = split_train_test(ac, locs)
 
     if args.windows:
         from . import replicates

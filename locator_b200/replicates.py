@@ -50,6 +50,23 @@ def _prepare(L, item, base):
                 "predgen": base["predgen"].take_cols(order), "trainlocs": base["trainlocs"],
                 "testlocs": base["testlocs"], "norm": base["norm"], "pred": base["pred"], "samples": base["samples"],
                 "boot": item["boot"], "cb_boot": item["boot"], "seed_tag": item["boot"] + 1, "out": args.out}
+    if item["kind"] == "window_lazy":
+        # the window's genotypes are still on disk: decode its chunks, filter and gather here (on this
+        # worker's GPU); the random split was drawn by the parent in the reference's order
+        from . import io
+
+        root, name, a, b = item["where"]
+        cache = _prepare.__dict__.setdefault("stores", {})
+        if root not in cache:
+            cache[root] = io.read_zarr(root, lazy=True)
+        cs = cache[root]
+        sub = io.Genotypes(io.ZarrRows(root, name, a, b), cs["samples"], cs["variants/POS"][a:b])
+        ac = L.filter_snps(sub)
+        locs = item["locs"]
+        train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = L.split_train_test(ac, locs, item["drawn"])
+        return {"traingen": traingen, "testgen": testgen, "predgen": predgen, "trainlocs": trainlocs,
+                "testlocs": testlocs, "norm": item["norm"], "pred": pred, "samples": item["samples"], "boot": 0,
+                "cb_boot": None, "seed_tag": item["index"] + 1, "out": item["window_out"]}
     if item["kind"] == "window":
         return {"traingen": item["traingen"], "testgen": item["testgen"], "predgen": item["predgen"],
                 "trainlocs": item["trainlocs"], "testlocs": item["testlocs"], "norm": item["norm"],
@@ -277,6 +294,12 @@ def run_windows(L, genotypes, samples):
         sub = genotypes[a:b]
         sample_data, locs = L.sort_samples(samples, sub)
         meanlong, sdlong, meanlat, sdlat, locs = L.normalize_locs(locs)
+        if pool is not None and sub.lazy is not None and L.windows_are_data_independent():
+            # ship the recipe, not the matrices: the worker reads, filters and packs the window itself
+            pool.submit({"kind": "window_lazy", "index": index, "window_out": f"{args.out}_{i}-{i+size-1}",
+                         "where": sub.lazy, "locs": locs, "drawn": L.draw_split(locs),
+                         "norm": (meanlong, sdlong, meanlat, sdlat), "samples": samples})
+            continue
         ac = L.filter_snps(sub)
         train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = L.split_train_test(ac, locs)
         item = {"kind": "window", "index": index, "window_out": f"{args.out}_{i}-{i+size-1}", "traingen": traingen,

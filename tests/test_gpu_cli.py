@@ -169,3 +169,25 @@ def test_bootstrap_outputs_do_not_depend_on_grouping(L, tmp_path):
                  "--replicates_per_gpu", str(g)])
         outs[g] = [open(f"{out}_boot{b}_predlocs.txt").read() for b in ("FULL", "0", "1", "2", "3")]
     assert outs[1] == outs[3]
+
+
+def test_windows_worker_side_ingest_matches_parent_side(L, tmp_path):
+    """--windows --gpus 2: the workers decode, filter and pack their own windows from the zarr store (the
+    parent only draws the random splits, in the reference's order).  Outputs must be byte-identical to the
+    single-process run, which filters every window in the parent."""
+    from locator_b200 import io
+
+    v = io.read_vcf(VCF)
+    z = str(tmp_path / "fix.zarr")
+    io.write_zarr(z, v["calldata/GT"], v["samples"], v["variants/POS"], chunk_variants=1500)
+    outs = {}
+    for gpus in (1, 2):
+        out = str(tmp_path / f"w{gpus}")
+        _run(L, ["--zarr", z, "--sample_data", SAMPLES, "--out", out, "--seed", "777", "--max_epochs", "3",
+                 "--keras_verbose", "0", "--windows", "--window_size", "625000", "--gpus", str(gpus),
+                 "--replicates_per_gpu", "2"])
+        outs[gpus] = out
+    for i in range(0, 2500000, 625000):
+        tail = f"_{i}-{i + 625000 - 1}_0-624999_predlocs.txt"
+        a, b = open(outs[1] + tail).read(), open(outs[2] + tail).read()
+        assert a == b and a.startswith("x,y,sampleID")

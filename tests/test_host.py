@@ -248,3 +248,27 @@ def test_native_vcf_parser_matches_python_reader(tmp_path, monkeypatch):
     assert io._read_vcf_native(bad.read_bytes()) is None
     with pytest.raises(ValueError):
         io.read_vcf(str(bad))
+
+
+def test_lazy_zarr_rows_and_genotype_slices(tmp_path):
+    """--windows reads: a variant slice of a zarr-backed Genotypes decodes only the chunks it overlaps and
+    equals the slice of the fully loaded array (ragged last chunk, slices inside / across chunks, empty)."""
+    from locator_b200 import io
+
+    rng = np.random.default_rng(0)
+    gt = rng.integers(-1, 2, size=(1000, 17, 2)).astype(np.int8)
+    z = str(tmp_path / "t.zarr")
+    io.write_zarr(z, gt, [f"s{i}" for i in range(17)], np.arange(1000) * 3, chunk_variants=128)
+    lz = io.read_zarr(z, lazy=True)
+    g = io.Genotypes(lz["calldata/GT"], lz["samples"], lz["variants/POS"])
+    assert g.shape == (1000, 17, 2) and len(g) == 1000 and g.lazy == (z, "calldata/GT", 0, 1000)
+    for a, b in [(0, 1000), (5, 6), (100, 400), (127, 129), (990, 1000), (500, 500)]:
+        sub = g[a:b]
+        assert sub.lazy == (z, "calldata/GT", a, b) and sub.shape == (b - a, 17, 2)
+        assert np.array_equal(sub.gt, gt[a:b]) and sub.lazy is None
+        assert np.array_equal(sub.positions, np.arange(1000)[a:b] * 3)
+    assert np.array_equal(g[100:400][10:20].gt, gt[110:120])
+    # only the overlapping chunk files are opened
+    os.remove(os.path.join(z, "calldata", "GT", "0.0.0"))
+    assert np.array_equal(g[128:256].gt, gt[128:256])
+    assert np.array_equal(g.gt[128:], gt[128:]) and (g.gt[:128] == 0).all()  # missing chunk -> fill value

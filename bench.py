@@ -377,9 +377,9 @@ def main():
     group = None
     if m.impl == "tcgen05" and args.group > 1:
         G = args.group
-        gm = [m] + [model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=n_ep_total + 2,
-                                       seed=500 + rank * 16 + g) for g in range(1, G)]
-        for q in gm[1:]:
+        gm = [model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=n_ep_total + 2,
+                                 seed=500 + rank * 16 + g) for g in range(G)]
+        for q in gm:
             q.bind_train(gtr, ytr)
             q.bind_val(m._keep["val"][0], yva)
             q.set_schedule(patience=10 ** 6)
@@ -402,6 +402,7 @@ def main():
         group = {"replicates_per_gpu": G, "epochs": ne_g, "value": world * G * ne_g * ntr / (gms / 1000.0),
                  "unit": "samples/s (all replicates)", "ms_per_step_per_replicate": gms / (ne_g * spe * G),
                  "what": "loc_group_train_epochs: hidden stacks of the G replicates share one launch"}
+        del gm
 
     # ---- one model sharded over the ranks (SNP columns; one 32 KB all_reduce of the Z1 tile per forward) ----
     tp = None

@@ -185,6 +185,12 @@ int loc_tp_error(loc_tp* tp);
 int loc_tp_destroy(loc_tp* tp);
 int loc_model_set_tp(loc_model* m, loc_tp* tp);
 
+/* Number of CTAs (= SMs used, = split-K partial tiles) of the tcgen05 first-layer kernels; default: all SMs.
+ * The plain backward + Adam kernel is memory-bound and as fast on SMs - 16 as on all of them (B200: 113 vs
+ * 114 us at K = 100k), the variant with the fused next forward loses 3 %.  The value fixes the fp32
+ * summation order of the layer: set it the same way for runs that must agree bit for bit. */
+int loc_model_set_l1_ctas(loc_model* m, int32_t n_ctas);
+
 /* lr, EarlyStopping patience (ReduceLROnPlateau patience = patience/6), and
  * reset of the callback state machine (best = +inf, waits = 0, epoch = 0). */
 int loc_model_set_schedule(loc_model* m, float lr, int32_t patience);

@@ -72,6 +72,7 @@ SIGNATURES = {
     "loc_tp_error": (C.c_int, [P]),
     "loc_tp_destroy": (C.c_int, [P]),
     "loc_model_set_tp": (C.c_int, [P, P]),
+    "loc_model_set_l1_ctas": (C.c_int, [P, I32]),
     "loc_model_set_schedule": (C.c_int, [P, C.c_float, I32]),
     "loc_model_bind_train": (C.c_int, [P, P, I64, I64, P]),
     "loc_model_bind_val": (C.c_int, [P, P, I64, I64, P]),

@@ -414,7 +414,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   uint64_t* st_done = st_full + B_RING;          // [B_RING] chunk updated in place (8 warps)
   uint64_t* st_free = st_done + B_RING;          // [B_STAGES] chunk written back, stage reusable (load warp, in order)
   uint64_t* fwd_done = st_free + B_STAGES;       // forward accumulators complete (fused runs)
-  uint32_t* tmem_slot = (uint32_t*)(fwd_done + 1);
+  uint64_t* fwd_tile = fwd_done + 1;             // [2] both forward warps have read a tile's scales / row sums
+  uint32_t* tmem_slot = (uint32_t*)(fwd_tile + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = a.src.nb;
@@ -440,6 +441,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     }
     for (int s = 0; s < B_STAGES; ++s) mbar_init(&st_free[s], fuse ? 2 : 1);  // written back (+ consumed by the forward MMA)
     mbar_init(fwd_done, 2);  // one commit per forward warp
+    mbar_init(&fwd_tile[0], 2);
+    mbar_init(&fwd_tile[1], 2);
     fence_barrier_init();
   }
   if (warp == B_EPI_WARPS) tmem_alloc(tmem_slot, 512);
@@ -671,6 +674,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
           Q += pr.y;
         }
         const float rs = sSc[buf * B_NT + cc * 8 + r].z;
+        if (cc >= 6) {  // this warp's last chunk of the tile: its sSc / sRed reads are done
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&fwd_tile[buf]);
+        }
         float gm = cur.gm, mg = cur.mg, vg = cur.vg, bt = cur.bt, mb = cur.mb, vb = cur.vb;
         adam_update(gm, mg, vg, rs * P, alpha);
         adam_update(bt, mb, vb, Q, alpha);
@@ -731,7 +738,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       // gamma/beta Adam of tile li once its epilogue has left P, Q in shared memory
       const int buf = li & 1;
       mbar_wait(&tmem_empty[buf], (uint32_t)(li >> 1) & 1u);
-      if (fuse) return;  // the forward warp updates gamma / beta chunk by chunk
+      if (fuse) {
+        // the forward warps update gamma / beta chunk by chunk -- and read this tile's scales (sSc) and row
+        // sums (sRed) a little after the epilogue is done with it: the buffers may only be rebuilt once
+        // both of them have passed the tile's last chunk
+        mbar_wait(&fwd_tile[buf], (uint32_t)(li >> 1) & 1u);
+        return;
+      }
       const int64_t k = tile_of(li) * B_NT + wb * 32 + lane;
       float P = 0.f, Q = 0.f;
 #pragma unroll
@@ -894,14 +907,14 @@ int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s) {
 }
 
 int l1_backward_tc(const L1Args& a, int nblocks, cudaStream_t s) {
-  (void)nblocks;
   static bool attr_set = false;
   if (!attr_set) {
     LOC_CUDA(cudaFuncSetAttribute(tc::k_l1_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::B_SMEM));
     attr_set = true;
   }
   const int64_t ntiles = cdiv(a.K, tc::B_NT);
-  const int64_t grid = ntiles < tc_sm_count() ? ntiles : tc_sm_count();
+  int64_t grid = ntiles < tc_sm_count() ? ntiles : tc_sm_count();
+  if (nblocks > 0 && nblocks < grid) grid = nblocks;  // loc_model_set_l1_ctas: leave SMs to a concurrent hidden stack
   tc::k_l1_bwd_tc<<<(unsigned)grid, tc::B_THREADS, tc::B_SMEM, s>>>(a, ntiles);
   LOC_LAUNCHED();
   return 0;

@@ -643,6 +643,15 @@ int loc_model_set_tp(loc_model* m, loc_tp* tp) {
   return 0;
 }
 
+int loc_model_set_l1_ctas(loc_model* m, int32_t n_ctas) {
+  LOC_CHECK(m != nullptr && n_ctas >= 1, "loc_model_set_l1_ctas: bad arguments");
+  LOC_CHECK(m->use_tc, "loc_model_set_l1_ctas: needs the tcgen05 first layer (width 256)");
+  const int full = l1_tc_partials(m->K);
+  m->n_partials = n_ctas < full ? n_ctas : full;
+  m->n_bwd_blocks = m->n_partials;
+  return 0;
+}
+
 int loc_model_set_schedule(loc_model* m, float lr, int32_t patience) {
   LOC_CHECK(m != nullptr, "loc_model_set_schedule: null model");
   LOC_CHECK(patience >= 0, "loc_model_set_schedule: patience must be >= 0");

@@ -28,7 +28,7 @@ class LocatorModel:
     """BN(K) -> Dense(width, elu) x nlayers (Dropout in the middle) -> Dense(2) -> Dense(2)."""
 
     def __init__(self, K, width=256, nlayers=10, dropout_prop=0.25, batch_size=32, max_epochs=5000, seed=0,
-                 learning_rate=1e-3, shard=None, exchange=None):
+                 learning_rate=1e-3, shard=None, exchange=None, l1_ctas=None):
         """shard = (k_offset, K_global): this model holds SNP columns [k_offset, k_offset + K) of a K_global-column
         model (tensor parallelism); exchange(tile) must then sum the float32 CUDA tensor `tile` in place over
         all shards on the current stream (see all_reduce_exchange)."""
@@ -42,6 +42,11 @@ class LocatorModel:
         check(lib.loc_model_create(C.byref(h), self.K, self.width, self.nlayers, self.batch_size, self.dropout_prop,
                                    self.max_epochs), "loc_model_create")
         self._h = h
+        self.l1_ctas = None
+        if l1_ctas is not None and self.impl == "tcgen05":
+            # CTAs of the first-layer kernels (default: every SM)
+            self.l1_ctas = int(l1_ctas)
+            check(lib.loc_model_set_l1_ctas(self._h, self.l1_ctas), "loc_model_set_l1_ctas")
         self._keep = {}  # device tensors the handle points at
         self.shard = None
         if shard is not None:
@@ -405,3 +410,9 @@ def all_reduce_exchange(group=None):
         dist.all_reduce(tile, op=dist.ReduceOp.SUM, group=group)
 
     return fn
+
+
+def spare_cluster_l1_ctas():
+    """First-layer CTA count that leaves one 16-SM cluster's worth of SMs free (experiments with concurrent
+    hidden stacks; the count fixes the summation order of the layer, so use it for every model of a run)."""
+    return max(1, torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count - 16)

@@ -174,8 +174,9 @@ def read_matrix(path):
 # ---------------------------------------------------------------------------------------------
 # zarr v2 directory store (what scripts/vcf_to_zarr.py / allel.vcf_to_zarr writes)
 # ---------------------------------------------------------------------------------------------
-def _blosc_decompress(raw, nbytes_hint=None):
-    """One Blosc frame -> bytes, through the C ABI (loc_blosc_decompress; LZ4 + byte shuffle)."""
+def _blosc_decompress_array(raw):
+    """One Blosc frame -> uint8 array, through the C ABI (loc_blosc_decompress; LZ4 + byte shuffle).
+    ctypes drops the GIL for the call, so chunks decode in parallel from a thread pool."""
     from ._cabi import lib, check
 
     nbytes = int.from_bytes(raw[4:8], "little")
@@ -184,7 +185,12 @@ def _blosc_decompress(raw, nbytes_hint=None):
     n = lib.loc_blosc_decompress(src.ctypes.data, len(raw), out.ctypes.data, nbytes)
     if n < 0:
         check(1, "loc_blosc_decompress")
-    return out.tobytes()
+    return out
+
+
+def _blosc_decompress(raw, nbytes_hint=None):
+    """One Blosc frame -> bytes."""
+    return _blosc_decompress_array(raw).tobytes()
 
 
 def _decode_vlen_utf8(buf):
@@ -197,6 +203,21 @@ def _decode_vlen_utf8(buf):
         out.append(buf[pos:pos + ln].decode("utf-8"))
         pos += ln
     return np.array(out, dtype=object)
+
+
+_PARALLEL_MIN_BYTES = 1 << 22  # smaller reads are not worth a thread pool
+
+
+def _io_threads():
+    """Host threads for chunk decoding (LOC_IO_THREADS overrides; default: the cores, at most 16)."""
+    env = os.environ.get("LOC_IO_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(16, n))
 
 
 class ZarrRows:
@@ -243,41 +264,66 @@ def _zarr_array(root, name, rows=None):
     r0, r1 = (0, shape[0]) if (rows is None or not shape) else (max(0, int(rows[0])), min(shape[0], int(rows[1])))
     out_shape = ((max(0, r1 - r0),) + shape[1:]) if shape else shape
     out = np.empty(out_shape, dtype=dtype)
-    out[...] = ("" if is_obj else 0) if fill in (None, "") or is_obj else fill
+    fill_value = ("" if is_obj else 0) if fill in (None, "") or is_obj else fill
     grid = [(-(-s // c)) for s, c in zip(shape, chunks)]
     if shape and r1 > r0:
         first = range(r0 // chunks[0], -(-r1 // chunks[0]))
-        indices = ((i,) + rest for i in first for rest in np.ndindex(*grid[1:]))
+        indices = [(i,) + rest for i in first for rest in np.ndindex(*grid[1:])]
     elif shape:
-        indices = iter(())
+        indices = []
     else:
         indices = [()]
-    for idx in indices:
+    if comp is not None and comp.get("id") not in ("zlib", "gzip", "blosc"):
+        raise ValueError(f"{name}: zarr compressor {comp.get('id')!r} is not available in this build "
+                         "(supported: none, zlib, gzip, blosc-lz4)")
+    row_bytes = int(np.prod(shape[1:], dtype=np.int64)) * dtype.itemsize if shape else 0
+
+    def load(idx):
+        """Decode chunk idx into its part of ``out`` (disjoint parts: safe from several threads)."""
         fn = os.path.join(adir, sep.join(str(i) for i in idx) if shape else "0")
-        if not os.path.exists(fn):
-            continue
+        if shape:
+            sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, shape))
+            lo, hi = max(sl[0].start, r0), min(sl[0].stop, r1)  # rows of this chunk inside the requested range
+            dst = (slice(lo - r0, hi - r0),) + sl[1:]
+        if not os.path.exists(fn):  # a chunk that was never written holds the fill value
+            out[dst if shape else ...] = fill_value
+            return
+        whole_rows = bool(shape) and not is_obj and chunks[1:] == shape[1:]
         with open(fn, "rb") as fh:
+            if comp is None and whole_rows:
+                # raw chunk spanning whole rows: read the wanted rows straight into the output
+                fh.seek((lo - sl[0].start) * row_bytes)
+                want = (hi - lo) * row_bytes
+                if fh.readinto(memoryview(out[lo - r0:hi - r0]).cast("B")) != want:
+                    raise ValueError(f"{fn}: truncated chunk")
+                return
             raw = fh.read()
         if comp is None:
             buf = raw
         elif comp.get("id") in ("zlib", "gzip"):
             buf = zlib.decompress(raw, 15 + 32)
-        elif comp.get("id") == "blosc":
-            buf = _blosc_decompress(raw)
         else:
-            raise ValueError(f"{name}: zarr compressor {comp.get('id')!r} is not available in this build "
-                             "(supported: none, zlib, gzip, blosc-lz4)")
+            buf = _blosc_decompress_array(raw)
         if is_obj:
-            chunk = _decode_vlen_utf8(buf).reshape(chunks)
+            chunk = _decode_vlen_utf8(bytes(buf)).reshape(chunks)
         else:
             chunk = np.frombuffer(buf, dtype=dtype).reshape(chunks)
-        sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, shape))
         if not shape:
             out[...] = chunk.reshape(())
-            continue
-        lo, hi = max(sl[0].start, r0), min(sl[0].stop, r1)  # rows of this chunk inside the requested range
+            return
         src = (slice(lo - sl[0].start, hi - sl[0].start),) + tuple(slice(0, x.stop - x.start) for x in sl[1:])
-        out[(slice(lo - r0, hi - r0),) + sl[1:]] = chunk[src]
+        out[dst] = chunk[src]
+
+    nthreads = min(len(indices), _io_threads())
+    if nthreads > 1 and not is_obj and out.nbytes >= _PARALLEL_MIN_BYTES:
+        # file reads, zlib / Blosc decoding and the numpy copies all drop the GIL
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(nthreads) as pool:
+            list(pool.map(load, indices))
+    else:
+        for idx in indices:
+            load(idx)
     return out
 
 

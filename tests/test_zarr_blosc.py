@@ -166,3 +166,57 @@ def test_zarr_store_with_blosc_gt_and_vlen_samples(tmp_path, fixture_gt):
     np.testing.assert_array_equal(back["calldata/GT"], gt)
     assert list(back["samples"]) == samples
     np.testing.assert_array_equal(back["variants/POS"], pos)
+
+
+@pytest.mark.parametrize("codec", ["raw", "zlib", "blosc"])
+def test_threaded_reads_of_a_chunk_grid_over_variants_and_samples(tmp_path, monkeypatch, codec):
+    """allel.vcf_to_zarr chunks calldata/GT over variants AND samples ((65536, 64, 2) by default); the reader
+    decodes the chunks of a row range from a thread pool.  Row ranges inside / across chunks, ragged edge
+    chunks, a never-written chunk (fill value) and the single-thread path give the same array."""
+    import zlib
+
+    rng = np.random.default_rng(3)
+    nvar, N, cv, cn = 5000, 300, 512, 64
+    gt = rng.integers(-1, 3, size=(nvar, N, 2)).astype(np.int8)
+    d = tmp_path / "g.zarr" / "calldata" / "GT"
+    d.mkdir(parents=True)
+    comp = {"raw": None, "zlib": {"id": "zlib", "level": 1},
+            "blosc": {"blocksize": 0, "clevel": 5, "cname": "lz4", "id": "blosc", "shuffle": 1}}[codec]
+    (d / ".zarray").write_text(json.dumps({"zarr_format": 2, "shape": [nvar, N, 2], "chunks": [cv, cn, 2], "dtype": "|i1",
+                                           "order": "C", "compressor": comp, "fill_value": -1, "filters": None}))
+    missing = (3, 2)
+    for i in range(-(-nvar // cv)):
+        for j in range(-(-N // cn)):
+            if (i, j) == missing:
+                continue
+            blk = np.full((cv, cn, 2), -1, np.int8)
+            part = gt[i * cv:(i + 1) * cv, j * cn:(j + 1) * cn]
+            blk[:part.shape[0], :part.shape[1]] = part
+            raw = blk.tobytes()
+            blob = raw if codec == "raw" else zlib.compress(raw, 1) if codec == "zlib" else _blosc_frame(raw, 1, 16384)
+            (d / f"{i}.{j}.0").write_bytes(blob)
+    want = gt.copy()
+    want[missing[0] * cv:(missing[0] + 1) * cv, missing[1] * cn:(missing[1] + 1) * cn] = -1
+    rows = io.ZarrRows(str(tmp_path / "g.zarr"), "calldata/GT")
+    assert rows.shape == (nvar, N, 2)
+    monkeypatch.setenv("LOC_IO_THREADS", "4")
+    monkeypatch.setattr(io, "_PARALLEL_MIN_BYTES", 0)
+    for a, b in [(0, nvar), (100, 130), (500, 2100), (1536, 2048), (4990, nvar), (7, 7)]:
+        np.testing.assert_array_equal(rows.rows(a, b).read(), want[a:b])
+    monkeypatch.setenv("LOC_IO_THREADS", "1")
+    np.testing.assert_array_equal(rows.rows(500, 2100).read(), want[500:2100])
+
+
+def test_raw_whole_row_chunks_are_read_in_place_and_truncation_is_an_error(tmp_path):
+    gt = np.random.default_rng(1).integers(-1, 2, size=(1000, 33, 2)).astype(np.int8)
+    z = str(tmp_path / "r.zarr")
+    io.write_zarr(z, gt, [f"s{i}" for i in range(33)], np.arange(1000), chunk_variants=300, compress=False)
+    np.testing.assert_array_equal(io.ZarrRows(z, "calldata/GT", 250, 950).read(), gt[250:950])
+    np.testing.assert_array_equal(io.read_zarr(z)["calldata/GT"], gt)
+    fn = os.path.join(z, "calldata", "GT", "1.0.0")
+    with open(fn, "rb") as fh:
+        blob = fh.read()
+    with open(fn, "wb") as fh:
+        fh.write(blob[:len(blob) // 2])
+    with pytest.raises(ValueError, match="truncated"):
+        io.ZarrRows(z, "calldata/GT", 250, 950).read()

@@ -11,8 +11,48 @@ thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 
 // ---------------------------------------------------------------------------------------------
-// Site statistics: one warp per site, lanes stride over the N calls (char2 loads, coalesced).
+// Site statistics: one warp per site.  The row (N calls = 2N bytes) is read as 16-byte vectors from
+// its first 16-byte boundary on (4 independent loads per lane in flight); the few calls before /
+// after the vector body go through the scalar path, so any N and any row offset work.  Per 32-bit
+// word (two calls) the counts come from byte-wise SIMD compares; alleles >= 2 take a slow path.
 // ---------------------------------------------------------------------------------------------
+struct SiteAcc {
+  unsigned seen[4];  // allele indices 0..127
+  int alt, miss;
+};
+
+// allele a in [0, 127] -> bitmap (select instead of a dynamic register index)
+__device__ __forceinline__ void mark(SiteAcc& s, int a) {
+  const unsigned bit = 1u << (a & 31);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) s.seen[q] |= (a >> 5) == q ? bit : 0u;
+}
+
+__device__ __forceinline__ void acc_call(SiteAcc& s, int a0, int a1) {
+  if (a0 >= 0) mark(s, a0);
+  if (a1 >= 0) mark(s, a1);
+  s.alt += (a0 == 1) + (a1 == 1);
+  s.miss += (a0 < 0) | (a1 < 0);
+}
+
+// w = bytes (a0, a1) of call A | (a0, a1) of call B
+__device__ __forceinline__ void acc_word(SiteAcc& s, uint32_t w) {
+  const uint32_t e1 = __vcmpeq4(w, 0x01010101u);  // 0xff where the allele is 1
+  const uint32_t e0 = __vcmpeq4(w, 0u);           // 0xff where the allele is 0
+  const uint32_t neg = w & 0x80808080u;           // sign bits: missing alleles
+  s.alt += __popc(e1) >> 3;
+  s.seen[0] |= (e0 ? 1u : 0u) | (e1 ? 2u : 0u);
+  s.miss += __popc((neg | (neg >> 8)) & 0x00800080u);  // a call is missing if either allele is
+  const uint32_t other = ~(e0 | e1 | ((neg >> 7) * 0xFFu));
+  if (other) {  // alleles >= 2 (rare): bitmap them one by one
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int a = (int)(int8_t)(w >> (8 * i));
+      if (a >= 2) mark(s, a);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_site_stats(const int8_t* __restrict__ gt, int64_t nvar, int64_t nsamp,
                                                     int min_mac, int32_t* __restrict__ n_alleles,
                                                     int32_t* __restrict__ alt_count, int32_t* __restrict__ n_missing,
@@ -20,23 +60,42 @@ __global__ void __launch_bounds__(256) k_site_stats(const int8_t* __restrict__ g
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t nbytes = nsamp * 2;
   for (int64_t v = warp; v < nvar; v += nwarps) {
-    const char2* row = reinterpret_cast<const char2*>(gt + v * nsamp * 2);
-    unsigned seen[4] = {0u, 0u, 0u, 0u};  // allele indices 0..127
-    int alt = 0, miss = 0;
-    for (int64_t s = lane; s < nsamp; s += 32) {
-      char2 c = row[s];
-      int a0 = c.x, a1 = c.y;
-      if (a0 >= 0) seen[a0 >> 5] |= 1u << (a0 & 31);
-      if (a1 >= 0) seen[a1 >> 5] |= 1u << (a1 & 31);
-      alt += (a0 == 1) + (a1 == 1);
-      miss += (a0 < 0) | (a1 < 0);
+    const int8_t* row = gt + v * nbytes;
+    SiteAcc s = {{0u, 0u, 0u, 0u}, 0, 0};
+    // calls before the first 16-byte boundary (the whole row if it starts at an odd address)
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(row);
+    int64_t head = (addr & 1) ? nbytes : (int64_t)((16 - (addr & 15)) & 15);
+    if (head > nbytes) head = nbytes;
+    for (int64_t c = lane; c < head / 2; c += 32) acc_call(s, row[2 * c], row[2 * c + 1]);
+    // vector body
+    const uint4* vp = reinterpret_cast<const uint4*>(row + head);
+    const int64_t nvec = (nbytes - head) >> 4;
+    for (int64_t i = lane; i < nvec; i += 128) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + 32 * u < nvec) q[u] = __ldcs(vp + i + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + 32 * u < nvec) {
+          acc_word(s, q[u].x);
+          acc_word(s, q[u].y);
+          acc_word(s, q[u].z);
+          acc_word(s, q[u].w);
+        }
     }
+    // calls after the last whole vector (< 8)
+    const int8_t* tail = row + head + nvec * 16;
+    const int64_t tail_calls = (nbytes - head - nvec * 16) / 2;
+    if (lane < tail_calls) acc_call(s, tail[2 * lane], tail[2 * lane + 1]);
+
     int na = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) na += __popc(__reduce_or_sync(0xffffffffu, seen[q]));
-    alt = __reduce_add_sync(0xffffffffu, alt);
-    miss = __reduce_add_sync(0xffffffffu, miss);
+    for (int q = 0; q < 4; ++q) na += __popc(__reduce_or_sync(0xffffffffu, s.seen[q]));
+    const int alt = __reduce_add_sync(0xffffffffu, s.alt);
+    const int miss = __reduce_add_sync(0xffffffffu, s.miss);
     if (lane == 0) {
       if (n_alleles) n_alleles[v] = na;
       if (alt_count) alt_count[v] = alt;
@@ -47,44 +106,81 @@ __global__ void __launch_bounds__(256) k_site_stats(const int8_t* __restrict__ g
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pack: tile of 32 samples x 32 words (512 SNPs). Reads are coalesced over samples (char2 per
-// call), the smem transpose makes the uint32 writes coalesced over words.
+// Pack: a block turns 256 kept sites x (32 * CALLS) samples into 16 packed words per sample.
+// A lane owns CALLS = VB / 2 consecutive samples and reads them with one VB-byte load per site (a warp
+// reads 32 * VB contiguous bytes of the site's row; 16 loads in flight per lane); the 2-bit counts of a
+// 16-site word come from byte-wise SIMD compares.  A padded shared-memory tile turns the per-lane words
+// into 64 contiguous bytes per sample for the write.  Blocks that are adjacent in x cover one set of
+// sites across all samples, so concurrently running blocks read whole rows.
+// The host picks the widest VB for which every load is aligned (VB | 2N and the base pointer).
 // ---------------------------------------------------------------------------------------------
+template <int VB>
+__device__ __forceinline__ void load_calls(const int8_t* p, uint32_t (&w)[(VB + 3) / 4]) {
+  if constexpr (VB == 16) {
+    const uint4 q = __ldcs(reinterpret_cast<const uint4*>(p));
+    w[0] = q.x, w[1] = q.y, w[2] = q.z, w[3] = q.w;
+  } else if constexpr (VB == 8) {
+    const uint2 q = __ldcs(reinterpret_cast<const uint2*>(p));
+    w[0] = q.x, w[1] = q.y;
+  } else if constexpr (VB == 4) {
+    w[0] = __ldcs(reinterpret_cast<const uint32_t*>(p));
+  } else {
+    w[0] = __ldcs(reinterpret_cast<const unsigned short*>(p));  // one call; the upper bytes read as allele 0
+  }
+}
+
+constexpr int kPackWords = 16;  // packed words (of 16 sites) per block
+constexpr int kPackPitch = kPackWords + 1;
+
+template <int VB>
 __global__ void __launch_bounds__(256) k_pack_sites(const int8_t* __restrict__ gt, int64_t nsamp,
                                                     const int64_t* __restrict__ site_idx, int64_t K,
                                                     uint32_t* __restrict__ packed, int64_t row_words) {
-  __shared__ uint32_t tile[32][33];
-  const int tx = threadIdx.x;  // 0..31
-  const int ty = threadIdx.y;  // 0..7
-  const int64_t s0 = (int64_t)blockIdx.x * 32;
-  const int64_t w0 = (int64_t)blockIdx.y * 32;
-  const int64_t s = s0 + tx;
+  constexpr int CALLS = VB / 2;
+  constexpr int S = 32 * CALLS;
+  constexpr int NW = (VB + 3) / 4;
+  __shared__ uint32_t tile[S * kPackPitch];  // [call c of the lane][lane][word], pitch 17: conflict-free writes
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int64_t s0 = (int64_t)blockIdx.x * S;
+  const int64_t w0 = (int64_t)blockIdx.y * kPackWords;
+  const int64_t sb = s0 + (int64_t)lane * CALLS;  // first sample of this lane (N % CALLS == 0: all or none in range)
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int wl = ty + 8 * r;
-    const int64_t w = w0 + wl;
-    uint32_t word = 0u;
-    if (s < nsamp && w < row_words) {
-#pragma unroll 4
-      for (int q = 0; q < 16; ++q) {
-        const int64_t k = w * 16 + q;
-        if (k < K) {
-          const int64_t v = site_idx[k];
-          char2 c = reinterpret_cast<const char2*>(gt)[v * nsamp + s];
-          uint32_t g = (uint32_t)(c.x == 1) + (uint32_t)(c.y == 1);
-          word |= g << (2 * q);
-        }
+  for (int jw = 0; jw < 2; ++jw) {
+    const int wl = 2 * wi + jw;
+    const int64_t k0 = (w0 + wl) * 16;
+    uint32_t raw[16][NW];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+#pragma unroll
+      for (int e = 0; e < NW; ++e) raw[q][e] = 0u;
+      if (k0 + q < K && sb < nsamp) load_calls<VB>(gt + (__ldg(site_idx + k0 + q) * nsamp + sb) * 2, raw[q]);
+    }
+    uint32_t acc[CALLS];
+#pragma unroll
+    for (int c = 0; c < CALLS; ++c) acc[c] = 0u;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+#pragma unroll
+      for (int e = 0; e < NW; ++e) {
+        const uint32_t e1 = __vcmpeq4(raw[q][e], 0x01010101u) & 0x01010101u;  // 1 where the allele is 1
+        const uint32_t g2 = (e1 + (e1 >> 8)) & 0x00030003u;                   // count of call A | call B << 16
+        acc[2 * e] |= (g2 & 3u) << (2 * q);
+        if constexpr (CALLS > 1) acc[2 * e + 1] |= (g2 >> 16) << (2 * q);
       }
     }
-    tile[wl][tx] = word;
+#pragma unroll
+    for (int c = 0; c < CALLS; ++c) tile[(c * 32 + lane) * kPackPitch + wl] = acc[c];
   }
   __syncthreads();
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int sl = ty + 8 * r;
-    const int64_t ss = s0 + sl;
-    const int64_t w = w0 + tx;
-    if (ss < nsamp && w < row_words) packed[ss * row_words + w] = tile[tx][sl];
+  const int quarter = threadIdx.x & 3;
+  const int64_t w = w0 + 4 * quarter;
+  if (w < row_words) {
+    for (int sl = threadIdx.x >> 2; sl < S; sl += 64) {
+      const int64_t ss = s0 + sl;
+      if (ss >= nsamp) break;
+      const uint32_t* t = tile + ((sl % CALLS) * 32 + sl / CALLS) * kPackPitch + 4 * quarter;
+      *reinterpret_cast<uint4*>(packed + ss * row_words + w) = make_uint4(t[0], t[1], t[2], t[3]);
+    }
   }
 }
 
@@ -181,7 +277,7 @@ int loc_site_stats(const int8_t* d_gt, int64_t nvar, int64_t nsamp, int32_t min_
   LOC_CHECK(d_gt != nullptr, "loc_site_stats: null genotype pointer");
   const int warps_per_block = 8;
   int64_t blocks = cdiv(nvar, warps_per_block);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 8) blocks = 148 * 8;  // one resident wave (8 blocks of 256 threads per SM); warps loop over sites
   k_site_stats<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_gt, nvar, nsamp, min_mac, d_n_alleles,
                                                                  d_alt_count, d_n_missing, d_keep);
   LOC_LAUNCHED();
@@ -194,9 +290,23 @@ int loc_pack_sites(const int8_t* d_gt, int64_t nvar, int64_t nsamp, const int64_
   LOC_CHECK(nsamp > 0 && K >= 0, "loc_pack_sites: bad shape");
   LOC_CHECK(row_words >= cdiv(K, 16) && row_words % 4 == 0, "loc_pack_sites: row_words must be >= ceil(K/16) and a multiple of 4");
   if (row_words == 0) return 0;
-  dim3 grid((unsigned)cdiv(nsamp, 32), (unsigned)cdiv(row_words, 32));
+  LOC_CHECK(d_gt != nullptr && d_packed != nullptr, "loc_pack_sites: null pointer");
+  LOC_CHECK(reinterpret_cast<uintptr_t>(d_packed) % 16 == 0, "loc_pack_sites: packed rows must be 16-byte aligned");
+  // widest aligned load: VB bytes = VB / 2 calls per lane
+  const uintptr_t base = reinterpret_cast<uintptr_t>(d_gt);
+  int vb = 16;
+  while (vb > 2 && ((nsamp * 2) % vb != 0 || base % vb != 0)) vb >>= 1;
+  LOC_CHECK(base % 2 == 0, "loc_pack_sites: genotype pointer must be 2-byte aligned");
+  const int S = 32 * (vb / 2);
+  dim3 grid((unsigned)cdiv(nsamp, S), (unsigned)cdiv(row_words, kPackWords));
   LOC_CHECK(grid.y <= 65535, "loc_pack_sites: K too large for one launch");
-  k_pack_sites<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(d_gt, nsamp, d_site_idx, K, d_packed, row_words);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (vb) {
+    case 16: k_pack_sites<16><<<grid, 256, 0, st>>>(d_gt, nsamp, d_site_idx, K, d_packed, row_words); break;
+    case 8: k_pack_sites<8><<<grid, 256, 0, st>>>(d_gt, nsamp, d_site_idx, K, d_packed, row_words); break;
+    case 4: k_pack_sites<4><<<grid, 256, 0, st>>>(d_gt, nsamp, d_site_idx, K, d_packed, row_words); break;
+    default: k_pack_sites<2><<<grid, 256, 0, st>>>(d_gt, nsamp, d_site_idx, K, d_packed, row_words); break;
+  }
   LOC_LAUNCHED();
   return 0;
 }

@@ -8,6 +8,8 @@ device buffers.
 """
 from __future__ import annotations
 
+import threading
+
 import numpy as np
 import torch
 
@@ -135,6 +137,59 @@ class PackedGenotypes:
         check(lib.loc_patch_calls(self.ptr, self.row_words, k.data_ptr(), s.data_ptr(), v.data_ptr(), int(k.numel()),
                                   _stream()), "loc_patch_calls")
         self.version += 1
+
+
+class _Staging(threading.local):
+    """Per-thread pair of pinned host buffers the zarr chunks are decoded into (reused across windows)."""
+    bufs = None
+    events = None
+
+
+_staging = _Staging()
+UPLOAD_BLOCK_BYTES = 1 << 29  # rows are staged in blocks of at most 512 MB
+
+
+def _staging_buffers(nbytes):
+    st = _staging
+    if st.bufs is None or st.bufs[0].numel() < nbytes:
+        for ev in (st.events or []):
+            if ev is not None:
+                ev.synchronize()  # nothing may still be reading the buffers that are about to be freed
+        # windows differ in their SNP counts: leave headroom so that the next, slightly larger one fits
+        cap = min(max(int(nbytes), UPLOAD_BLOCK_BYTES), int(nbytes) + int(nbytes) // 4)
+        st.bufs = [torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        st.events = [None, None]
+    return st
+
+
+def upload_rows(rows) -> torch.Tensor:
+    """io.ZarrRows (GT int8 [nvar, N, 2] on disk) -> device tensor, without an intermediate pageable copy.
+
+    Blocks of rows are decoded (thread pool, io._zarr_array) straight into one of two pinned staging
+    buffers and copied to the device asynchronously: block i+1 is decoded while block i is in flight.
+    """
+    nvar, N, ploidy = rows.shape
+    assert ploidy == 2 and rows.dtype == np.int8
+    dev = _dev()
+    out = torch.empty((nvar, N, 2), dtype=torch.int8, device=dev)
+    if nvar == 0:
+        return out
+    row_bytes = N * 2
+    block = max(1, min(nvar, UPLOAD_BLOCK_BYTES // row_bytes))
+    st = _staging_buffers(block * row_bytes)
+    stream = torch.cuda.current_stream()
+    for i, a in enumerate(range(0, nvar, block)):
+        b = min(nvar, a + block)
+        slot = i & 1
+        if st.events[slot] is not None:
+            st.events[slot].synchronize()  # the previous copy out of this buffer has finished
+        host = st.bufs[slot][:(b - a) * row_bytes].view(torch.int8).view(b - a, N, 2)
+        rows.rows(a, b).read(out=host.numpy())
+        out[a:b].copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        st.events[slot] = ev
+    return out
 
 
 def site_stats(gt, min_mac=2):

@@ -40,6 +40,11 @@ class Genotypes:
         return self._gt
 
     @property
+    def rows_on_disk(self):
+        """The ZarrRows behind this object while nothing has been decoded on the host, else None."""
+        return self._lazy if self._gt is None else None
+
+    @property
     def lazy(self):
         """(store path, array name, first row, end row) while nothing has been decoded, else None."""
         return None if self._gt is not None or self._lazy is None else self._lazy.where()
@@ -239,12 +244,15 @@ class ZarrRows:
     def where(self):
         return (self.root, self.name, self.a, self.b)
 
-    def read(self):
-        return _zarr_array(self.root, self.name, rows=(self.a, self.b))
+    def read(self, out=None):
+        """Decode the rows; with ``out`` (C-contiguous array of this shape and dtype, e.g. a view of pinned
+        memory) the chunks are decoded straight into it."""
+        return _zarr_array(self.root, self.name, rows=(self.a, self.b), out=out)
 
 
-def _zarr_array(root, name, rows=None):
-    """The whole array, or (rows = (a, b)) only its first-axis range [a, b): just the chunks that overlap."""
+def _zarr_array(root, name, rows=None, out=None):
+    """The whole array, or (rows = (a, b)) only its first-axis range [a, b): just the chunks that overlap.
+    ``out``: optional destination (shape / dtype of the result, C-contiguous)."""
     adir = os.path.join(root, name)
     with open(os.path.join(adir, ".zarray")) as fh:
         meta = json.load(fh)
@@ -263,7 +271,10 @@ def _zarr_array(root, name, rows=None):
         raise ValueError(f"{name}: zarr filters {filters!r} are not supported")
     r0, r1 = (0, shape[0]) if (rows is None or not shape) else (max(0, int(rows[0])), min(shape[0], int(rows[1])))
     out_shape = ((max(0, r1 - r0),) + shape[1:]) if shape else shape
-    out = np.empty(out_shape, dtype=dtype)
+    if out is None:
+        out = np.empty(out_shape, dtype=dtype)
+    elif out.shape != out_shape or out.dtype != dtype or not out.flags.c_contiguous:
+        raise ValueError(f"{name}: destination must be a C-contiguous {dtype} array of shape {out_shape}")
     fill_value = ("" if is_obj else 0) if fill in (None, "") or is_obj else fill
     grid = [(-(-s // c)) for s, c in zip(shape, chunks)]
     if shape and r1 > r0:

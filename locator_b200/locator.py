@@ -221,7 +221,12 @@ def filter_snps(genotypes):
     from . import genotypes as G
 
     print("filtering SNPs")
-    g, n_alleles, alt_count, n_missing, keep = G.site_stats(genotypes.gt, min_mac=int(args.min_mac))
+    on_disk = getattr(genotypes, "rows_on_disk", None)
+    if on_disk is not None and on_disk.dtype == np.int8 and not args.impute_missing:
+        gt = G.upload_rows(on_disk)  # zarr chunks -> pinned staging -> device; the host never holds the cube
+    else:
+        gt = genotypes.gt
+    g, n_alleles, alt_count, n_missing, keep = G.site_stats(gt, min_mac=int(args.min_mac))
     keep_idx = np.flatnonzero(keep.cpu().numpy())
     packed = G.pack_sites(g, keep_idx)
     if args.impute_missing:

@@ -75,18 +75,20 @@ def _prepare(L, item, base):
     raise ValueError(item["kind"])
 
 
-def _run_items(L, items, base):
+def _run_items(L, items, base, reps=None):
     """Train + predict a list of replicates inside the current process / on the current device.
 
     One replicate: the reference's sequence (load_network, train_network, predict_locs).  Several:
     the models are trained side by side as one lockstep group (model.fit_group; results are
     bit-identical to training them one after the other), then predicted one by one.
+    ``reps``: the items' matrices when a Prefetcher has already prepared them.
     """
     from .model import fit_group
 
     args = L.args
     t1 = time.time()
-    reps = [_prepare(L, it, base) for it in items]
+    if reps is None:
+        reps = [_prepare(L, it, base) for it in items]
     models, callbacks = [], []
     for rep in reps:
         L._seed_tag[0] = rep["seed_tag"]
@@ -128,6 +130,63 @@ def _run_items(L, items, base):
         print(f"Window run time {(time.time() - t1) / 60:.2f} minutes")
 
 
+class Prefetcher:
+    """Prepares the NEXT group of replicates (zarr chunk decode, upload, filter, pack, gathers) in a helper
+    thread on a side stream while the current group trains on the main stream.  Nothing in _prepare draws
+    from numpy's global stream (the parent did), so the overlap cannot change any index."""
+
+    def __init__(self, L, base):
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.L, self.base = L, base
+        self.device = torch.cuda.current_device()
+        self.side = torch.cuda.Stream()
+        self.pool = ThreadPoolExecutor(1)
+
+    def _work(self, items):
+        import torch
+
+        torch.cuda.set_device(self.device)
+        with torch.cuda.stream(self.side):
+            reps = [_prepare(self.L, it, self.base) for it in items]
+        self.side.synchronize()  # everything the group needs is in device memory before it is handed over
+        return reps
+
+    def submit(self, items):
+        return self.pool.submit(self._work, items)
+
+    @staticmethod
+    def collect(future):
+        import torch
+
+        reps = future.result()
+        cur = torch.cuda.current_stream()
+        for rep in reps:  # allocated on the side stream, used (and eventually freed) on this one
+            for k in ("traingen", "testgen", "predgen"):
+                rep[k].words.record_stream(cur)
+        return reps
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+
+
+def _run_pipelined(L, groups, base):
+    """groups: iterable of work-item lists.  Group i+1 is prepared while group i trains."""
+    pf = Prefetcher(L, base)
+    try:
+        cur = None
+        for items in groups:
+            nxt = (items, pf.submit(items))
+            if cur is not None:
+                _run_items(L, cur[0], base, Prefetcher.collect(cur[1]))
+            cur = nxt
+        if cur is not None:
+            _run_items(L, cur[0], base, Prefetcher.collect(cur[1]))
+    finally:
+        pf.close()
+
+
 def _group_size(args):
     return max(1, min(8, int(getattr(args, "replicates_per_gpu", 1) or 1)))
 
@@ -166,11 +225,25 @@ def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None):
         import queue as _queue
 
         G = _group_size(args)
-        finished = False
-        while not finished:
-            item = task_q.get()
+        state = {"finished": False}
+
+        def to_dev(it):
+            for k in ("traingen", "testgen", "predgen"):
+                if k in it and isinstance(it[k], dict):
+                    it[k] = _to_dev(it[k])
+            return it
+
+        def take_group(block):
+            """Up to G queued items; None when there is nothing (block=False) or the queue has ended."""
+            if state["finished"]:
+                return None
+            try:
+                item = task_q.get() if block else task_q.get_nowait()
+            except _queue.Empty:
+                return None
             if item is None:
-                break
+                state["finished"] = True
+                return None
             items = [item]
             while len(items) < G:  # take what is already queued, up to a group
                 try:
@@ -178,16 +251,37 @@ def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None):
                 except _queue.Empty:
                     break
                 if nxt is None:
-                    finished = True
+                    state["finished"] = True
                     break
                 items.append(nxt)
-            for it in items:
-                for k in ("traingen", "testgen", "predgen"):
-                    if k in it and isinstance(it[k], dict):
-                        it[k] = _to_dev(it[k])
-            _run_items(L, items, base)
+            return [to_dev(it) for it in items]
+
+        def queue_is_deep():
+            """Prefetch only while every worker could still fill a group of its own (no starving at the tail)."""
+            try:
+                return task_q.qsize() >= n_gpus * G
+            except NotImplementedError:
+                return False
+
+        pf = Prefetcher(L, base)
+        ahead = None
+        while True:
+            if ahead is None:
+                items = take_group(block=True)
+                if items is None:
+                    break
+                fut = pf.submit(items)
+            else:
+                items, fut = ahead
+                ahead = None
+            if queue_is_deep():
+                nxt = take_group(block=False)
+                if nxt is not None:
+                    ahead = (nxt, pf.submit(nxt))
+            _run_items(L, items, base, Prefetcher.collect(fut))
             for it in items:
                 result_q.put(("done", rank, it.get("boot", it.get("index"))))
+        pf.close()
         result_q.put(("exit", rank, None))
     except Exception:  # surface the failure in the parent instead of hanging the queue
         result_q.put(("error", rank, traceback.format_exc()))
@@ -261,8 +355,7 @@ def run_bootstrap(L, traingen, testgen, trainlocs, testlocs, predgen, norm, pred
     if n_gpus == 1:
         G = _group_size(args)
         items = [{"kind": "boot", "boot": boot, "site_order": order} for boot, order in enumerate(orders)]
-        for i in range(0, len(items), G):
-            _run_items(L, items[i:i + G], base)
+        _run_pipelined(L, (items[i:i + G] for i in range(0, len(items), G)), base)
         return
     pool = ReplicatePool(n_gpus, args, base)
     for boot, order in enumerate(orders):
@@ -287,18 +380,25 @@ def run_windows(L, genotypes, samples):
     size = int(float(args.window_size))
     n_gpus = max(1, int(getattr(args, "gpus", 1) or 1))
     pool = ReplicatePool(n_gpus, args) if n_gpus > 1 else None
-    pending = []
+    # Recipes instead of matrices whenever no draw depends on the genotypes: whoever runs the window (a
+    # worker process, or this process's prefetch thread) reads, filters and packs it.
+    # LOC_WINDOWS_PARENT_INGEST=1 keeps the serial reference order of work (parity tests compare the two).
+    recipes_ok = L.windows_are_data_independent() and not os.environ.get("LOC_WINDOWS_PARENT_INGEST")
+    pending, recipes = [], []
     for index, (i, a, b) in enumerate(window_bounds(positions, start, stop, size)):
         print(f"\nProcessing window {i}-{i+size}")
         print(f"SNPs {a}-{b}")
         sub = genotypes[a:b]
         sample_data, locs = L.sort_samples(samples, sub)
         meanlong, sdlong, meanlat, sdlat, locs = L.normalize_locs(locs)
-        if pool is not None and sub.lazy is not None and L.windows_are_data_independent():
-            # ship the recipe, not the matrices: the worker reads, filters and packs the window itself
-            pool.submit({"kind": "window_lazy", "index": index, "window_out": f"{args.out}_{i}-{i+size-1}",
-                         "where": sub.lazy, "locs": locs, "drawn": L.draw_split(locs),
-                         "norm": (meanlong, sdlong, meanlat, sdlat), "samples": samples})
+        if sub.lazy is not None and recipes_ok:
+            item = {"kind": "window_lazy", "index": index, "window_out": f"{args.out}_{i}-{i+size-1}",
+                    "where": sub.lazy, "locs": locs, "drawn": L.draw_split(locs),
+                    "norm": (meanlong, sdlong, meanlat, sdlat), "samples": samples}
+            if pool is not None:
+                pool.submit(item)
+            else:
+                recipes.append(item)
             continue
         ac = L.filter_snps(sub)
         train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = L.split_train_test(ac, locs)
@@ -314,5 +414,8 @@ def run_windows(L, genotypes, samples):
             pool.submit(item)
     if pending:
         _run_items(L, pending, None)
+    if recipes:
+        G = _group_size(args)
+        _run_pipelined(L, (recipes[j:j + G] for j in range(0, len(recipes), G)), None)
     if pool is not None:
         pool.close()

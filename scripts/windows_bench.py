@@ -24,21 +24,26 @@ def main():
     ap.add_argument("--snps", type=int, default=50000)
     ap.add_argument("--samples", type=int, default=2500)
     ap.add_argument("--epochs", type=int, default=20)
+    ap.add_argument("--reuse", action="store_true", help="use the store a previous call left under /tmp/wb")
     a = ap.parse_args()
     import bench
     from locator_b200 import io
 
     t0 = time.time()
-    x, y = bench.synth(a.samples, a.snps, 5)            # uint8 [n, K] alt counts with spatial structure
-    gt1 = np.stack([(x.T >= 1), (x.T >= 2)], axis=2).astype(np.int8)  # [K, n, 2]
-    gt = np.concatenate([gt1] * a.windows)               # the same block in every window (content is irrelevant here)
     size = 1_000_000
-    pos = np.concatenate([w * size + np.sort(np.random.default_rng(w).choice(size, a.snps, replace=False))
-                          for w in range(a.windows)])
     z = "/tmp/wb/genome.zarr"
-    os.makedirs("/tmp/wb", exist_ok=True)
     samples = [f"s{i}" for i in range(a.samples)]
-    io.write_zarr(z, gt, samples, pos, chunk_variants=16384, compress=False)
+    if a.reuse and os.path.exists(z):
+        class gt:  # only the size is reported below
+            nbytes = a.windows * a.snps * a.samples * 2
+    else:
+        x, y = bench.synth(a.samples, a.snps, 5)            # uint8 [n, K] alt counts with spatial structure
+        gt1 = np.stack([(x.T >= 1), (x.T >= 2)], axis=2).astype(np.int8)  # [K, n, 2]
+        gt = np.concatenate([gt1] * a.windows)               # the same block in every window (content is irrelevant here)
+        pos = np.concatenate([w * size + np.sort(np.random.default_rng(w).choice(size, a.snps, replace=False))
+                              for w in range(a.windows)])
+        os.makedirs("/tmp/wb", exist_ok=True)
+        io.write_zarr(z, gt, samples, pos, chunk_variants=16384, compress=False)
     rng = np.random.default_rng(1)
     loc = rng.uniform(0, 50, size=(a.samples, 2))
     loc[rng.choice(a.samples, a.samples // 10, replace=False)] = np.nan

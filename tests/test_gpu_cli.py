@@ -174,23 +174,46 @@ def test_bootstrap_outputs_do_not_depend_on_grouping(L, tmp_path):
     assert outs[1] == outs[3]
 
 
-def test_windows_worker_side_ingest_matches_parent_side(L, tmp_path):
-    """--windows --gpus 2: the workers decode, filter and pack their own windows from the zarr store (the
-    parent only draws the random splits, in the reference's order).  Outputs must be byte-identical to the
-    single-process run, which filters every window in the parent."""
+def test_windows_worker_side_ingest_matches_parent_side(L, tmp_path, monkeypatch):
+    """--windows: whoever runs a window decodes, filters and packs it from the zarr store -- a worker process
+    (--gpus 2) or this process's prefetch thread, one group ahead of the training (--gpus 1); the parent only
+    draws the random splits, in the reference's order.  Outputs must be byte-identical to the serial run that
+    filters every window in the parent before training it (LOC_WINDOWS_PARENT_INGEST=1)."""
     from locator_b200 import io
 
     v = io.read_vcf(VCF)
     z = str(tmp_path / "fix.zarr")
     io.write_zarr(z, v["calldata/GT"], v["samples"], v["variants/POS"], chunk_variants=1500)
     outs = {}
-    for gpus in (1, 2):
-        out = str(tmp_path / f"w{gpus}")
+    for mode, gpus in (("serial", 1), ("prefetch", 1), ("workers", 2)):
+        out = str(tmp_path / f"w_{mode}")
+        if mode == "serial":
+            monkeypatch.setenv("LOC_WINDOWS_PARENT_INGEST", "1")
+        else:
+            monkeypatch.delenv("LOC_WINDOWS_PARENT_INGEST", raising=False)
         _run(L, ["--zarr", z, "--sample_data", SAMPLES, "--out", out, "--seed", "777", "--max_epochs", "3",
                  "--keras_verbose", "0", "--windows", "--window_size", "625000", "--gpus", str(gpus),
                  "--replicates_per_gpu", "2"])
-        outs[gpus] = out
+        outs[mode] = out
     for i in range(0, 2500000, 625000):
         tail = f"_{i}-{i + 625000 - 1}_0-624999_predlocs.txt"
-        a, b = open(outs[1] + tail).read(), open(outs[2] + tail).read()
-        assert a == b and a.startswith("x,y,sampleID")
+        a = open(outs["serial"] + tail).read()
+        assert a.startswith("x,y,sampleID")
+        assert a == open(outs["prefetch"] + tail).read()
+        assert a == open(outs["workers"] + tail).read()
+
+
+def test_staged_upload_of_zarr_rows_matches_host_array(L, tmp_path, monkeypatch):
+    """genotypes.upload_rows: zarr chunks -> pinned staging (two buffers, several blocks) -> device."""
+    from locator_b200 import genotypes as G, io
+
+    gt = np.random.default_rng(2).integers(-1, 3, size=(3001, 37, 2)).astype(np.int8)
+    z = str(tmp_path / "u.zarr")
+    io.write_zarr(z, gt, [f"s{i}" for i in range(37)], np.arange(3001), chunk_variants=256)
+    monkeypatch.setattr(G, "UPLOAD_BLOCK_BYTES", 37 * 2 * 500)  # 7 blocks through the two buffers
+    rows = io.ZarrRows(z, "calldata/GT")
+    assert np.array_equal(G.upload_rows(rows).cpu().numpy(), gt)
+    assert np.array_equal(G.upload_rows(rows.rows(100, 777)).cpu().numpy(), gt[100:777])
+    monkeypatch.setattr(G, "UPLOAD_BLOCK_BYTES", 1 << 29)
+    assert np.array_equal(G.upload_rows(rows.rows(5, 3000)).cpu().numpy(), gt[5:3000])  # buffers grow
+    assert G.upload_rows(rows.rows(9, 9)).shape == (0, 37, 2)

@@ -49,7 +49,8 @@ def test_site_stats_and_pack_fixture(G, fixture_gt, golden_dir):
     assert np.array_equal(counts, ac_ref.T)
 
 
-@pytest.mark.parametrize("nvar,N,min_mac", [(300, 37, 2), (1000, 129, 1), (64, 500, 3), (17, 5, 2)])
+@pytest.mark.parametrize("nvar,N,min_mac", [(300, 37, 2), (1000, 129, 1), (64, 500, 3), (17, 5, 2), (700, 1000, 2),
+                                             (333, 2500, 2), (50, 1026, 2), (40, 4099, 1), (9, 1, 1), (600, 264, 2)])
 def test_site_stats_random(G, nvar, N, min_mac):
     from oracle import ingest_ref
 
@@ -71,6 +72,41 @@ def test_site_stats_random(G, nvar, N, min_mac):
     if K % 16:
         assert np.all(w[:, K // 16] >> np.uint32(2 * (K % 16)) == 0)
     assert np.all(w[:, (K + 15) // 16:] == 0)
+
+
+@pytest.mark.parametrize("offset", [0, 1, 2, 6, 8, 14])
+def test_site_stats_and_pack_at_any_pointer_offset(G, offset):
+    """The C ABI takes raw pointers: rows that start at any byte offset (a window slice, an odd address)
+    go through the scalar head / tail of the scan and the narrower loads of the pack kernel."""
+    from locator_b200._cabi import lib, check
+    from oracle import ingest_ref
+
+    rng = np.random.default_rng(offset)
+    nvar, N = 257, 264
+    gt = _rand_gt(rng, nvar, N, multi=0.05)
+    gt[5, 7, 0] = 100  # a far-away allele index
+    buf = torch.zeros(gt.size + 64, dtype=torch.int8, device="cuda")
+    buf[offset:offset + gt.size] = torch.as_tensor(gt.reshape(-1)).cuda()
+    ptr = buf.data_ptr() + offset
+    na = torch.empty(nvar, dtype=torch.int32, device="cuda")
+    alt, miss = torch.empty_like(na), torch.empty_like(na)
+    keep = torch.empty(nvar, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.loc_site_stats(ptr, nvar, N, 2, na.data_ptr(), alt.data_ptr(), miss.data_ptr(), keep.data_ptr(), st))
+    cnt = ingest_ref.count_alleles(gt)
+    assert np.array_equal(na.cpu().numpy(), (cnt > 0).sum(1))
+    assert np.array_equal(alt.cpu().numpy(), cnt[:, 1])
+    assert np.array_equal(miss.cpu().numpy(), ingest_ref.is_missing(gt).sum(1))
+    ac_ref, idx_ref = ingest_ref.filter_snps(gt, min_mac=2, return_index=True)
+    assert np.array_equal(np.flatnonzero(keep.cpu().numpy()), idx_ref)
+    out = G.PackedGenotypes.empty(N, len(idx_ref))
+    idx = torch.as_tensor(idx_ref.astype(np.int64)).cuda()
+    rc = lib.loc_pack_sites(ptr, nvar, N, idx.data_ptr(), len(idx_ref), out.ptr, out.row_words, st)
+    if offset % 2:
+        assert rc != 0 and b"aligned" in lib.loc_last_error()  # calls are byte pairs: an odd address is refused
+    else:
+        check(rc)
+        assert np.array_equal(out.to_counts().cpu().numpy(), ac_ref.T)
 
 
 @pytest.mark.parametrize("n,K", [(1, 1), (3, 16), (45, 5830), (90, 100003), (7, 63)])
@@ -136,3 +172,23 @@ def test_full_size_roundtrip_properties(G):
     rows = torch.randperm(n, device="cuda", generator=gen)
     assert torch.equal(p.take_rows(rows).to_counts(), counts[rows])
     assert int(p.to_counts().sum(dtype=torch.int64)) == int(counts.sum(dtype=torch.int64))
+
+
+def test_full_size_filter_and_pack_properties(G):
+    """A cfg3-sized window of raw calls (100k sites x 2,500 samples, 0.5 GB): the filter / pack kernels against
+    torch reductions of the same cube on the device."""
+    nvar, N = 100_000, 2500
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    p = torch.rand((nvar, 1, 1), device="cuda", generator=gen) ** 2
+    gt = (torch.rand((nvar, N, 2), device="cuda", generator=gen) < p).to(torch.int8)
+    gt[torch.rand((nvar, N, 2), device="cuda", generator=gen) < 0.01] = -1
+    gt[torch.rand((nvar, N, 2), device="cuda", generator=gen) < 0.002] = 2
+    g, na, alt, miss, keep = G.site_stats(gt, min_mac=2)
+    assert torch.equal(alt.long(), (gt == 1).sum(dim=(1, 2)))
+    assert torch.equal(miss.long(), (gt < 0).any(dim=2).sum(dim=1))
+    seen = torch.stack([(gt == a).any(dim=2).any(dim=1) for a in (0, 1, 2)]).sum(dim=0)
+    assert torch.equal(na.long(), seen)
+    assert torch.equal(keep.bool(), (seen == 2) & (alt >= 2))
+    idx = torch.nonzero(keep).flatten()
+    packed = G.pack_sites(g, idx)
+    assert torch.equal(packed.to_counts(), (gt[idx] == 1).sum(dim=2).to(torch.uint8).T.contiguous())

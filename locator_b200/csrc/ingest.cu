@@ -14,7 +14,8 @@ std::atomic<long long> g_launches{0};
 // Site statistics: one warp per site.  The row (N calls = 2N bytes) is read as 16-byte vectors from
 // its first 16-byte boundary on (4 independent loads per lane in flight); the few calls before /
 // after the vector body go through the scalar path, so any N and any row offset work.  Per 32-bit
-// word (two calls) the counts come from byte-wise SIMD compares; alleles >= 2 take a slow path.
+// word (two calls) the counts come from exact zero-byte tests in plain integer logic (the __vcmp*4
+// intrinsics are emulated on this part and made the scan issue-bound); alleles >= 2 take a slow path.
 // ---------------------------------------------------------------------------------------------
 struct SiteAcc {
   unsigned seen[4];  // allele indices 0..127
@@ -35,16 +36,31 @@ __device__ __forceinline__ void acc_call(SiteAcc& s, int a0, int a1) {
   s.miss += (a0 < 0) | (a1 < 0);
 }
 
-// w = bytes (a0, a1) of call A | (a0, a1) of call B
-__device__ __forceinline__ void acc_word(SiteAcc& s, uint32_t w) {
-  const uint32_t e1 = __vcmpeq4(w, 0x01010101u);  // 0xff where the allele is 1
-  const uint32_t e0 = __vcmpeq4(w, 0u);           // 0xff where the allele is 0
-  const uint32_t neg = w & 0x80808080u;           // sign bits: missing alleles
-  s.alt += __popc(e1) >> 3;
-  s.seen[0] |= (e0 ? 1u : 0u) | (e1 ? 2u : 0u);
+// 0x80 in every byte of x that is zero (exact per byte: no borrow crosses a byte)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) {
+  return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+
+// Running masks of one lane over a row; w = bytes (a0, a1) of call A | (a0, a1) of call B.
+struct WordAcc {
+  uint32_t any0, any1;  // some allele was 0 / 1
+  int alt, miss;
+};
+
+// returns the bytes (0x80 flags) that hold an allele >= 2: the caller bitmaps those one by one (rare)
+__device__ __forceinline__ uint32_t acc_word(WordAcc& s, uint32_t w) {
+  const uint32_t z1 = zero_bytes(w ^ 0x01010101u);  // allele 1
+  const uint32_t z0 = zero_bytes(w);                // allele 0
+  const uint32_t neg = w & 0x80808080u;             // sign bits: missing alleles
+  s.alt += __popc(z1);
+  s.any0 |= z0;
+  s.any1 |= z1;
   s.miss += __popc((neg | (neg >> 8)) & 0x00800080u);  // a call is missing if either allele is
-  const uint32_t other = ~(e0 | e1 | ((neg >> 7) * 0xFFu));
-  if (other) {  // alleles >= 2 (rare): bitmap them one by one
+  return ~(z0 | z1 | w) & 0x80808080u;
+}
+
+__device__ __forceinline__ void mark_others(SiteAcc& s, uint32_t w, uint32_t other) {
+  if (other) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int a = (int)(int8_t)(w >> (8 * i));
@@ -53,7 +69,7 @@ __device__ __forceinline__ void acc_word(SiteAcc& s, uint32_t w) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_site_stats(const int8_t* __restrict__ gt, int64_t nvar, int64_t nsamp,
+__global__ void __launch_bounds__(256, 5) k_site_stats(const int8_t* __restrict__ gt, int64_t nvar, int64_t nsamp,
                                                     int min_mac, int32_t* __restrict__ n_alleles,
                                                     int32_t* __restrict__ alt_count, int32_t* __restrict__ n_missing,
                                                     uint8_t* __restrict__ keep) {
@@ -72,6 +88,7 @@ __global__ void __launch_bounds__(256) k_site_stats(const int8_t* __restrict__ g
     // vector body
     const uint4* vp = reinterpret_cast<const uint4*>(row + head);
     const int64_t nvec = (nbytes - head) >> 4;
+    WordAcc wa = {0u, 0u, 0, 0};
     for (int64_t i = lane; i < nvec; i += 128) {
       uint4 q[4];
 #pragma unroll
@@ -80,12 +97,19 @@ __global__ void __launch_bounds__(256) k_site_stats(const int8_t* __restrict__ g
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         if (i + 32 * u < nvec) {
-          acc_word(s, q[u].x);
-          acc_word(s, q[u].y);
-          acc_word(s, q[u].z);
-          acc_word(s, q[u].w);
+          const uint32_t ox = acc_word(wa, q[u].x), oy = acc_word(wa, q[u].y);
+          const uint32_t oz = acc_word(wa, q[u].z), ow = acc_word(wa, q[u].w);
+          if (ox | oy | oz | ow) {
+            mark_others(s, q[u].x, ox);
+            mark_others(s, q[u].y, oy);
+            mark_others(s, q[u].z, oz);
+            mark_others(s, q[u].w, ow);
+          }
         }
     }
+    s.seen[0] |= (wa.any0 ? 1u : 0u) | (wa.any1 ? 2u : 0u);
+    s.alt += wa.alt;
+    s.miss += wa.miss;
     // calls after the last whole vector (< 8)
     const int8_t* tail = row + head + nvec * 16;
     const int64_t tail_calls = (nbytes - head - nvec * 16) / 2;
@@ -162,7 +186,7 @@ __global__ void __launch_bounds__(256) k_pack_sites(const int8_t* __restrict__ g
     for (int q = 0; q < 16; ++q) {
 #pragma unroll
       for (int e = 0; e < NW; ++e) {
-        const uint32_t e1 = __vcmpeq4(raw[q][e], 0x01010101u) & 0x01010101u;  // 1 where the allele is 1
+        const uint32_t e1 = zero_bytes(raw[q][e] ^ 0x01010101u) >> 7;         // 1 where the allele is 1
         const uint32_t g2 = (e1 + (e1 >> 8)) & 0x00030003u;                   // count of call A | call B << 16
         acc[2 * e] |= (g2 & 3u) << (2 * q);
         if constexpr (CALLS > 1) acc[2 * e + 1] |= (g2 >> 16) << (2 * q);
@@ -277,7 +301,15 @@ int loc_site_stats(const int8_t* d_gt, int64_t nvar, int64_t nsamp, int32_t min_
   LOC_CHECK(d_gt != nullptr, "loc_site_stats: null genotype pointer");
   const int warps_per_block = 8;
   int64_t blocks = cdiv(nvar, warps_per_block);
-  if (blocks > 148 * 8) blocks = 148 * 8;  // one resident wave (8 blocks of 256 threads per SM); warps loop over sites
+  static int wave = 0;  // one resident wave of blocks; the warps loop over the sites
+  if (wave == 0) {
+    int dev = 0, sms = 148, per_sm = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_site_stats, 256, 0);
+    wave = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  if (blocks > wave) blocks = wave;
   k_site_stats<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_gt, nvar, nsamp, min_mac, d_n_alleles,
                                                                  d_alt_count, d_n_missing, d_keep);
   LOC_LAUNCHED();

@@ -409,6 +409,44 @@ def _run_one(traingen, testgen, trainlocs, testlocs, predgen, norm, pred, sample
     return model, history, dists
 
 
+def _jacknife_draws(af, K, n_pred):
+    """(sites_to_remove, vals uint8 [nsites, n_pred]) per replicate, from numpy's global stream in the
+    reference's order (locator.py:722-727): choice without replacement, then per chosen site, in the
+    returned order, binomial(2, af[site], n_pred).  One vectorised binomial over the repeated
+    frequencies consumes the stream exactly like the per-site calls, and releases the GIL, so the draws
+    of replicate r+1 (the serial bottleneck of the sweep: ~50 ns per call) are taken by a helper thread
+    while replicate r is predicted and written.  Nothing else touches the stream during the sweep."""
+    import queue
+    import threading
+
+    nsites = int(K * args.jacknife_prop)
+    q = queue.Queue(maxsize=2)
+
+    def produce():
+        try:
+            for _ in range(args.nboots):
+                sites = np.random.choice(K, nsites, replace=False)
+                if nsites:
+                    vals = np.random.binomial(2, np.repeat(af[sites], n_pred)).reshape(nsites, n_pred).astype(np.uint8)
+                else:
+                    vals = np.zeros((0, n_pred), np.uint8)
+                q.put((sites, vals))
+            q.put(None)
+        except BaseException as e:  # surfaces in the consumer
+            q.put(e)
+
+    t = threading.Thread(target=produce, daemon=True)
+    t.start()
+    while True:
+        item = q.get()
+        if item is None:
+            break
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+    t.join()
+
+
 def main(argv=None):
     global args
     parser = build_parser()
@@ -466,13 +504,8 @@ def main(argv=None):
         print("starting jacknife resampling")
         af = ac.site_sums() / (ac.shape[1] * 2)  # wide integer sums (numpy >= 2 would wrap uint8 in the reference)
         n_pred = _matrix_shape(predgen)[0]
-        for boot in range(args.nboots):
+        for boot, (sites_to_remove, vals) in enumerate(_jacknife_draws(af, _matrix_shape(predgen)[1], n_pred)):
             pg = predgen.clone()
-            sites_to_remove = np.random.choice(_matrix_shape(pg)[1], int(_matrix_shape(pg)[1] * args.jacknife_prop),
-                                               replace=False)
-            # per chosen site, in the returned order, binomial(2, af[site], n_pred): same stream as the reference
-            vals = np.stack([np.random.binomial(2, af[i], n_pred) for i in sites_to_remove]).astype(np.uint8) \
-                if len(sites_to_remove) else np.zeros((0, n_pred), np.uint8)
             if len(sites_to_remove):
                 pg.replace_cols(sites_to_remove, vals)
             predict_locs(model, pg, sdlong, meanlong, sdlat, meanlat, testlocs, pred, samples, testgen, history, boot,

@@ -103,7 +103,7 @@ def count_alleles(gt):
     m = int(gt.max()) if gt.size else 0
     m = max(m, 0)
     out = np.zeros((gt.shape[0], m + 1), dtype=np.int32)
-    flat = gt.reshape(gt.shape[0], -1)
+    flat = gt.reshape(gt.shape[0], int(np.prod(gt.shape[1:])))  # (-1 cannot be inferred for zero sites)
     for a in range(m + 1):
         out[:, a] = (flat == a).sum(axis=1)
     return out

@@ -272,3 +272,35 @@ def test_lazy_zarr_rows_and_genotype_slices(tmp_path):
     os.remove(os.path.join(z, "calldata", "GT", "0.0.0"))
     assert np.array_equal(g[128:256].gt, gt[128:256])
     assert np.array_equal(g.gt[128:], gt[128:]) and (g.gt[:128] == 0).all()  # missing chunk -> fill value
+
+
+def test_jacknife_draws_follow_the_reference_stream():
+    """The threaded, vectorised draws of the jacknife sweep are the reference's per-site scalar-p draws
+    (locator.py:722-727 restated in oracle/ingest_ref.jacknife_replace), replicate after replicate, and leave
+    numpy's global stream where the reference's loop leaves it."""
+    from locator_b200 import locator as L
+    from oracle import ingest_ref
+
+    rng = np.random.default_rng(8)
+    n_pred, K = 23, 1200
+    predgen = rng.integers(0, 3, size=(n_pred, K), dtype=np.uint8)
+    af = rng.uniform(0, 1, size=K)
+    af[:40] = 0.0
+    af[40:80] = 1.0
+    L.set_args(L.build_parser().parse_args(["--out", "x", "--jacknife", "--nboots", "5", "--jacknife_prop", "0.07"]))
+    np.random.seed(4242)
+    want = [ingest_ref.jacknife_replace(predgen, af, 0.07) for _ in range(5)]
+    after_ref = np.random.random()
+    np.random.seed(4242)
+    got = list(L._jacknife_draws(af, K, n_pred))
+    after = np.random.random()
+    assert len(got) == 5 and after == after_ref
+    for (ref_matrix, ref_sites), (sites, vals) in zip(want, got):
+        assert np.array_equal(sites, ref_sites) and vals.shape == (int(K * 0.07), n_pred) and vals.dtype == np.uint8
+        mine = predgen.copy()
+        mine[:, sites] = vals.T
+        assert np.array_equal(mine, ref_matrix)
+    # no sites to replace: replicates still come out, the stream still advances like choice(K, 0)
+    L.set_args(L.build_parser().parse_args(["--out", "x", "--jacknife", "--nboots", "2", "--jacknife_prop", "0.0"]))
+    got = list(L._jacknife_draws(af, K, n_pred))
+    assert [v.shape for _, v in got] == [(0, n_pred)] * 2

@@ -84,6 +84,16 @@ def test_missing_and_multiallelic_semantics():
     assert ingest_ref.filter_snps(gt, min_mac=1).shape[0] == 3  # min_mac == 1 skips the count filter
 
 
+def test_filter_with_no_surviving_or_no_sites():
+    """Edge cases: every site fails the biallelic test (all triallelic / monomorphic), and an empty cube."""
+    gt = np.array([[[0, 1], [2, 0]], [[0, 0], [0, 0]]], dtype=np.int8)
+    ac, idx = ingest_ref.filter_snps(gt, min_mac=2, return_index=True)
+    assert ac.shape == (0, 2) and idx.size == 0
+    ac, idx = ingest_ref.filter_snps(np.zeros((0, 7, 2), np.int8), min_mac=2, return_index=True)
+    assert ac.shape == (0, 7) and idx.size == 0
+    assert ingest_ref.count_alleles(np.zeros((0, 7, 2), np.int8)).shape == (0, 1)
+
+
 def test_philox_known_answer():
     # Philox4x32-10 known-answer test of Random123 (counter = key = 0 and the all-ones vector)
     r = philox_ref.philox4x32_10([0], [0], [0], [0], 0, 0)

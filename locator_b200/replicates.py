@@ -50,6 +50,12 @@ def _prepare(L, item, base):
                 "predgen": base["predgen"].take_cols(order), "trainlocs": base["trainlocs"],
                 "testlocs": base["testlocs"], "norm": base["norm"], "pred": base["pred"], "samples": base["samples"],
                 "boot": item["boot"], "cb_boot": item["boot"], "seed_tag": item["boot"] + 1, "out": args.out}
+    if item["kind"] == "full":
+        # the un-resampled model of a bootstrap run (locator.py:611-632), as a work item of its own
+        return {"traingen": base["traingen"], "testgen": base["testgen"], "predgen": base["predgen"],
+                "trainlocs": base["trainlocs"], "testlocs": base["testlocs"], "norm": base["norm"],
+                "pred": base["pred"], "samples": base["samples"], "boot": "FULL", "cb_boot": "FULL", "seed_tag": 0,
+                "out": args.out}
     if item["kind"] == "window_lazy":
         # the window's genotypes are still on disk: decode its chunks, filter and gather here (on this
         # worker's GPU); the random split was drawn by the parent in the reference's order
@@ -344,21 +350,25 @@ class ReplicatePool:
 # ---------------------------------------------------------------------------------------------
 def run_bootstrap(L, traingen, testgen, trainlocs, testlocs, predgen, norm, pred, samples):
     args = L.args
-    # 1. initial full run (locator.py:611-632)
-    L._seed_tag[0] = 0
-    L._run_one(traingen, testgen, trainlocs, testlocs, predgen, norm, pred, samples, "FULL", "FULL")
-    # 2. every replicate's draws, serially, as the reference's loop would take them
-    orders = draw_bootstrap_orders(traingen.K, args.nboots)
     base = {"traingen": traingen, "testgen": testgen, "predgen": predgen, "trainlocs": trainlocs,
             "testlocs": testlocs, "norm": norm, "pred": pred, "samples": samples}
     n_gpus = max(1, int(getattr(args, "gpus", 1) or 1))
     if n_gpus == 1:
+        # 1. initial full run (locator.py:611-632)
+        L._seed_tag[0] = 0
+        L._run_one(traingen, testgen, trainlocs, testlocs, predgen, norm, pred, samples, "FULL", "FULL")
+        # 2. every replicate's draws, serially, as the reference's loop would take them
+        orders = draw_bootstrap_orders(traingen.K, args.nboots)
         G = _group_size(args)
         items = [{"kind": "boot", "boot": boot, "site_order": order} for boot, order in enumerate(orders)]
         _run_pipelined(L, (items[i:i + G] for i in range(0, len(items), G)), base)
         return
+    # Several GPUs: the full model is one more independent work item (training draws nothing from numpy's
+    # global stream, so the replicates' draws do not have to wait for it), and the workers start up while
+    # the parent draws: no GPU idles through the full run.
     pool = ReplicatePool(n_gpus, args, base)
-    for boot, order in enumerate(orders):
+    pool.submit({"kind": "full", "boot": "FULL"})
+    for boot, order in enumerate(draw_bootstrap_orders(traingen.K, args.nboots)):
         pool.submit({"kind": "boot", "boot": boot, "site_order": order})
     pool.close()
 

@@ -160,10 +160,9 @@ def test_windows_driver_on_zarr(L, tmp_path):
 
 
 def test_bootstrap_outputs_do_not_depend_on_grouping(L, tmp_path):
-    """--replicates_per_gpu only changes scheduling: every replicate's predictions are byte-identical.
-    (G >= 2 runs the first-layer kernels on SMs - 16 for every model of the run; that changes the fp32
-    summation order only when a model has more than SMs - 16 tiles of 64 SNPs, i.e. not on this fixture --
-    tests/test_gpu_model.py covers the large-K case at a fixed setting.)"""
+    """--replicates_per_gpu only changes scheduling: a lockstep group runs every model's first-layer kernels
+    with the same grid and summation order as a model trained alone, so every replicate's predictions are
+    byte-identical (tests/test_gpu_model.py checks the same at K = 20,000)."""
     outs = {}
     for g in (1, 3):
         out = str(tmp_path / f"g{g}")
@@ -172,6 +171,19 @@ def test_bootstrap_outputs_do_not_depend_on_grouping(L, tmp_path):
                  "--replicates_per_gpu", str(g)])
         outs[g] = [open(f"{out}_boot{b}_predlocs.txt").read() for b in ("FULL", "0", "1", "2", "3")]
     assert outs[1] == outs[3]
+
+
+def test_bootstrap_over_worker_processes_matches_the_single_process_run(L, tmp_path):
+    """--bootstrap --gpus 2: the full model and the replicates are work items of two worker processes (both on
+    GPU 0 when the box has one); every output is byte-identical to the single-process run."""
+    outs = {}
+    for gpus in (1, 2):
+        out = str(tmp_path / f"b{gpus}")
+        _run(L, ["--vcf", VCF, "--sample_data", SAMPLES, "--out", out, "--seed", "99", "--max_epochs", "4",
+                 "--keras_verbose", "0", "--bootstrap", "--nboots", "3", "--max_SNPs", "2500", "--gpus", str(gpus),
+                 "--replicates_per_gpu", "2"])
+        outs[gpus] = [open(f"{out}_boot{b}_predlocs.txt").read() for b in ("FULL", "0", "1", "2")]
+    assert outs[1] == outs[2] and len(set(outs[1])) == 4
 
 
 def test_windows_worker_side_ingest_matches_parent_side(L, tmp_path, monkeypatch):

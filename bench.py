@@ -377,32 +377,45 @@ def main():
     group = None
     if m.impl == "tcgen05" and args.group > 1:
         G = args.group
-        gm = [model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=n_ep_total + 2,
-                                 seed=500 + rank * 16 + g) for g in range(G)]
-        for q in gm:
-            q.bind_train(gtr, ytr)
-            q.bind_val(m._keep["val"][0], yva)
-            q.set_schedule(patience=10 ** 6)
-        ne_g = max(2, min(6, steps // spe))
-        perms_g = [torch.as_tensor(np.stack([rng.permutation(ntr) for _ in range(ne_g + 1)]).astype(np.int32)).cuda()
-                   for _ in range(G)]
-        handles = (ctypes.c_void_p * G)(*[q._h for q in gm])
 
-        def run_group(ne, skip):
-            pp = (ctypes.c_void_p * G)(*[p.data_ptr() + skip * ntr * 4 for p in perms_g])
-            _cabi.check(lib.loc_group_train_epochs(handles, G, pp, ne, stream), "loc_group_train_epochs")
-        run_group(1, 0)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        run_group(ne_g, 1)
-        g1.record()
-        torch.cuda.synchronize()
-        gms = max_over_ranks(g0.elapsed_time(g1), "cuda")
-        group = {"replicates_per_gpu": G, "epochs": ne_g, "value": world * G * ne_g * ntr / (gms / 1000.0),
-                 "unit": "samples/s (all replicates)", "ms_per_step_per_replicate": gms / (ne_g * spe * G),
-                 "what": "loc_group_train_epochs: hidden stacks of the G replicates share one launch"}
-        del gm
+        def measure_group(l1_ctas):
+            gm = [model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=n_ep_total + 2,
+                                     seed=500 + rank * 16 + g, l1_ctas=l1_ctas) for g in range(G)]
+            for q in gm:
+                q.bind_train(gtr, ytr)
+                q.bind_val(m._keep["val"][0], yva)
+                q.set_schedule(patience=10 ** 6)
+            ne_g = max(2, min(6, steps // spe))
+            prng = np.random.default_rng(77)
+            perms_g = [torch.as_tensor(np.stack([prng.permutation(ntr) for _ in range(ne_g + 1)]).astype(np.int32)).cuda()
+                       for _ in range(G)]
+            handles = (ctypes.c_void_p * G)(*[q._h for q in gm])
+
+            def run_group(ne, skip):
+                pp = (ctypes.c_void_p * G)(*[p.data_ptr() + skip * ntr * 4 for p in perms_g])
+                _cabi.check(lib.loc_group_train_epochs(handles, G, pp, ne, stream), "loc_group_train_epochs")
+            run_group(1, 0)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            run_group(ne_g, 1)
+            g1.record()
+            torch.cuda.synchronize()
+            gms = max_over_ranks(g0.elapsed_time(g1), "cuda")
+            loss = float(gm[0].state().last_loss)
+            del gm
+            return {"epochs": ne_g, "value": world * G * ne_g * ntr / (gms / 1000.0),
+                    "ms_per_step_per_replicate": gms / (ne_g * spe * G), "last_loss_model0": loss}
+
+        # ring: the first-layer kernels leave one cluster's worth of SMs free, a model's hidden stack runs next to
+        # the previous model's backward (programmatic dependent launch); lockstep: all SMs, hidden stacks grouped
+        ring = measure_group(model.spare_cluster_l1_ctas())
+        lock = measure_group(None)
+        group = {"replicates_per_gpu": G, "epochs": ring["epochs"], "value": ring["value"],
+                 "unit": "samples/s (all replicates)", "ms_per_step_per_replicate": ring["ms_per_step_per_replicate"],
+                 "schedule": "ring", "lockstep": lock, "ring": ring,
+                 "what": "loc_group_train_epochs, ring schedule: hidden stack of model g concurrent with the "
+                         "first-layer backward + Adam of model g-1 (132 CTAs); 'lockstep' = the grouped-launch schedule"}
 
     # ---- one model sharded over the ranks (SNP columns; one 32 KB all_reduce of the Z1 tile per forward) ----
     tp = None

@@ -692,11 +692,23 @@ int hidden_reslice(const float* small, float* fs, float* bs, int H, int L, int c
   return 0;
 }
 
-int hidden_update_launch(const UpdArgs& a, cudaStream_t s) {
+int hidden_update_launch(const UpdArgs& a, cudaStream_t s, bool overlap_previous) {
   LOC_CHECK(a.H % kUpdRows == 0 && a.H >= 32 && a.H <= 1024, "hidden update: bad width");
   const int nblk = (a.L - 1) * (a.H / kUpdRows) + 1;
-  k_hidden_update<<<nblk, a.H, 0, s>>>(a);
-  LOC_LAUNCHED();
+  // overlap_previous: programmatic dependent launch (see l1_backward_tc) -- the update of a model whose hidden
+  // stack finished a slot earlier runs next to another model's first-layer backward
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)nblk);
+  cfg.blockDim = dim3((unsigned)a.H);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = overlap_previous ? 1 : 0;
+  LOC_CUDA(cudaLaunchKernelEx(&cfg, k_hidden_update, a));
+  loc::g_launches.fetch_add(1);
   return 0;
 }
 

@@ -85,6 +85,10 @@ __device__ __forceinline__ uint32_t b_off(int b, int k) {
 }
 
 __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
+  // programmatic dependent launch: once the whole cluster is running, a kernel queued behind this one with the
+  // programmatic-serialization attribute may start (ring schedule of loc_group_train_epochs: ANOTHER model's
+  // first-layer backward fills the other SMs while this latency-bound stack runs)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (a.gated && a.st->stopped) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);

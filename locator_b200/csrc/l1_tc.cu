@@ -391,6 +391,9 @@ __device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32
 }
 
 __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t ntiles) {
+  // programmatic dependent launch: a kernel queued behind this one with the programmatic-serialization
+  // attribute (the small-layer update of the ring schedule) may be scheduled as soon as every CTA is running
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (a.gated && a.st->stopped) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -906,7 +909,7 @@ int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s) {
   return 0;
 }
 
-int l1_backward_tc(const L1Args& a, int nblocks, cudaStream_t s) {
+int l1_backward_tc(const L1Args& a, int nblocks, cudaStream_t s, bool overlap_previous) {
   static bool attr_set = false;
   if (!attr_set) {
     LOC_CUDA(cudaFuncSetAttribute(tc::k_l1_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::B_SMEM));
@@ -915,8 +918,21 @@ int l1_backward_tc(const L1Args& a, int nblocks, cudaStream_t s) {
   const int64_t ntiles = cdiv(a.K, tc::B_NT);
   int64_t grid = ntiles < tc_sm_count() ? ntiles : tc_sm_count();
   if (nblocks > 0 && nblocks < grid) grid = nblocks;  // loc_model_set_l1_ctas: leave SMs to a concurrent hidden stack
-  tc::k_l1_bwd_tc<<<(unsigned)grid, tc::B_THREADS, tc::B_SMEM, s>>>(a, ntiles);
-  LOC_LAUNCHED();
+  // overlap_previous: programmatic dependent launch -- the kernel starts once every CTA of the previous
+  // kernel in the stream is running (it never waits for that kernel's results: the ring schedule puts
+  // another model's hidden stack there), instead of after its completion
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(tc::B_THREADS);
+  cfg.dynamicSmemBytes = tc::B_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = overlap_previous ? 1 : 0;
+  LOC_CUDA(cudaLaunchKernelEx(&cfg, tc::k_l1_bwd_tc, a, ntiles));
+  loc::g_launches.fetch_add(1);
   return 0;
 }
 

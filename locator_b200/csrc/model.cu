@@ -741,10 +741,53 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
     src.nb = (int32_t)((m0->n_train - off) < m0->B ? (m0->n_train - off) : m0->B);
     return src;
   };
+  // Schedule.  "ring" (default whenever every model's first-layer kernels leave one cluster's worth of SMs
+  // free, loc_model_set_l1_ctas): one stream, per slot  H(g) -> B(g-1) -> U(g-1)  where H is the 16-CTA hidden
+  // stack of model g (plain launch: starts when everything before it is complete), B the first-layer backward
+  // + Adam (+ next forward) of the PREVIOUS model in the ring and U that model's small-layer update, both
+  // launched with programmatic stream serialization: B starts as soon as H's cluster is placed and streams
+  // W1/m/v on the other SMs while H's dependent chain of layer products runs; U takes H's SMs when H exits.
+  // B(g-1) only needs H(g-1) (complete since the previous slot) and nothing from H(g).  A slot costs
+  // max(B, H) instead of B + H / G.  "lockstep" (LOC_GROUP_SCHEDULE=lockstep, or models on all SMs): all
+  // hidden stacks in one launch, then the backwards back to back, updates on side streams.
+  bool ring = n_models >= 2;
+  for (int g = 0; g < n_models; ++g) ring = ring && models[g]->n_bwd_blocks <= sm_count() - 16;
+  const char* sched = getenv("LOC_GROUP_SCHEDULE");
+  if (sched != nullptr && strcmp(sched, "lockstep") == 0) ring = false;
+  struct Pending {
+    loc_model* m;
+    L1Args a;
+    UpdArgs u;
+  };
   for (int e = 0; e < n_epochs; ++e) {
     bool have_fwd = false;
+    Pending pend;
+    pend.m = nullptr;
     for (int64_t off = 0; off < m0->n_train; off += m0->B) {
       const bool has_next = off + m0->B < m0->n_train;
+      if (ring) {
+        for (int g = 0; g < n_models; ++g) {
+          loc_model* m = models[g];
+          const RowSrc src = step_rows(g, off);
+          L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, 1);
+          if (!have_fwd && forward_l1(m, a, s)) return 1;  // first step of the epoch: later ones are fused
+          HidArgs h = hid_args(m, src, 1, 1, m->train_locs, nullptr);
+          if (hidden_tc_launch(h, s)) return 1;
+          if (pend.m != nullptr) {
+            if (l1_backward_tc(pend.a, pend.m->n_bwd_blocks, s, true)) return 1;
+            if (hidden_update_launch(pend.u, s, true)) return 1;
+          }
+          if (has_next) {
+            a.src_next = step_rows(g, off + m0->B);
+            a.fuse_next = 1;
+          }
+          pend.m = m;
+          pend.a = a;
+          pend.u = upd_args(m, src.nb, 1);
+        }
+        have_fwd = has_next;
+        continue;
+      }
       HidGroupArgs hg;
       hg.n = n_models;
       // first-layer forwards (first step of the epoch only: later ones are fused into the backward)
@@ -780,6 +823,10 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
       }
       for (int g = 0; g < n_models; ++g) LOC_CUDA(cudaStreamWaitEvent(s, models[g]->ev_upd, 0));
       have_fwd = has_next;
+    }
+    if (pend.m != nullptr) {  // ring: the last model's backward and update of the epoch's last step
+      if (l1_backward_tc(pend.a, pend.m->n_bwd_blocks, s)) return 1;
+      if (hidden_update_launch(pend.u, s)) return 1;
     }
     for (int g = 0; g < n_models; ++g) {
       loc_model* m = models[g];

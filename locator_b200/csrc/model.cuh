@@ -131,7 +131,7 @@ struct UpdArgs {
 int l1_forward_simt(const L1Args& a, int n_partials, cudaStream_t s);
 int l1_backward_simt(const L1Args& a, int nblocks, cudaStream_t s);
 int hidden_launch(const HidArgs& a, int cluster, cudaStream_t s);
-int hidden_update_launch(const UpdArgs& a, cudaStream_t s);
+int hidden_update_launch(const UpdArgs& a, cudaStream_t s, bool overlap_previous = false);
 int hidden_max_cluster(int H, int L);  // largest usable cluster size (16, 8, ...) for this device
 int hidden_slots(int H, int L, int cluster);
 int hidden_reslice(const float* small, float* fs, float* bs, int H, int L, int cluster, cudaStream_t s);
@@ -146,7 +146,7 @@ int hidden_tc_reslice(const float* small, float* fs, float* bs, int L, cudaStrea
 // tcgen05 first layer (l1_tc.cu); available() is false when the shape is unsupported.
 bool l1_tc_supported(int64_t K, int H);
 int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s);
-int l1_backward_tc(const L1Args& a, int nblocks, cudaStream_t s);
+int l1_backward_tc(const L1Args& a, int nblocks, cudaStream_t s, bool overlap_previous = false);
 int l1_tc_partials(int64_t K);
 
 }  // namespace loc

@@ -293,11 +293,17 @@ def _model_seed():
 
 
 def load_network(traingen, dropout_prop):
-    from .model import LocatorModel
+    from .model import LocatorModel, spare_cluster_l1_ctas
 
     K = traingen.shape[1] if hasattr(traingen, "shape") else traingen.K
+    # Replicate runs that train several models per GPU side by side keep one cluster's worth of SMs free of the
+    # first-layer kernels, so that one model's hidden stack overlaps another's weight stream (ring schedule of
+    # loc_group_train_epochs).  The CTA count fixes the fp32 summation order of the layer, hence the same
+    # setting for every model of such a run, grouped or not.
+    grouped = (args.bootstrap or args.windows) and int(getattr(args, "replicates_per_gpu", 1) or 1) >= 2
     return LocatorModel(K, width=args.width, nlayers=args.nlayers, dropout_prop=args.dropout_prop,
-                        batch_size=args.batch_size, max_epochs=args.max_epochs, seed=_model_seed())
+                        batch_size=args.batch_size, max_epochs=args.max_epochs, seed=_model_seed(),
+                        l1_ctas=spare_cluster_l1_ctas() if grouped else None)
 
 
 class _Callback:

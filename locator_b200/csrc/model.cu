@@ -713,6 +713,9 @@ int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t 
   return train_step(m, src, 0, (cudaStream_t)stream, 1 << stage);
 }
 
+// below this many SNPs the first-layer backward is shorter than the hidden stack (42 us ~ 35k SNPs)
+static const int64_t kRingMinK = 32768;
+
 int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* const* d_perms, int32_t n_epochs,
                            void* stream) {
   LOC_CHECK(models != nullptr && d_perms != nullptr && n_models >= 1 && n_models <= kMaxGroup && n_epochs >= 1,
@@ -748,11 +751,12 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
   // launched with programmatic stream serialization: B starts as soon as H's cluster is placed and streams
   // W1/m/v on the other SMs while H's dependent chain of layer products runs; U takes H's SMs when H exits.
   // B(g-1) only needs H(g-1) (complete since the previous slot) and nothing from H(g).  A slot costs
-  // max(B, H) instead of B + H / G.  "lockstep" (LOC_GROUP_SCHEDULE=lockstep, or models on all SMs): all
-  // hidden stacks in one launch, then the backwards back to back, updates on side streams.
-  bool ring = n_models >= 2;
+  // max(B, H) instead of B + H / G -- a gain only when the weight stream outlasts the hidden stack, hence
+  // K >= kRingMinK.  "lockstep" (small K, models on all SMs, or LOC_GROUP_SCHEDULE=lockstep): all hidden
+  // stacks in one launch, then the backwards back to back, updates on side streams.
+  const char* sched = getenv("LOC_GROUP_SCHEDULE");  // "ring" / "lockstep" override the choice by K (tests, A/B)
+  bool ring = n_models >= 2 && (m0->K >= kRingMinK || (sched != nullptr && strcmp(sched, "ring") == 0));
   for (int g = 0; g < n_models; ++g) ring = ring && models[g]->n_bwd_blocks <= sm_count() - 16;
-  const char* sched = getenv("LOC_GROUP_SCHEDULE");
   if (sched != nullptr && strcmp(sched, "lockstep") == 0) ring = false;
   struct Pending {
     loc_model* m;
@@ -760,34 +764,48 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
     UpdArgs u;
   };
   for (int e = 0; e < n_epochs; ++e) {
-    bool have_fwd = false;
-    Pending pend;
-    pend.m = nullptr;
-    for (int64_t off = 0; off < m0->n_train; off += m0->B) {
-      const bool has_next = off + m0->B < m0->n_train;
-      if (ring) {
-        for (int g = 0; g < n_models; ++g) {
-          loc_model* m = models[g];
-          const RowSrc src = step_rows(g, off);
-          L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, 1);
-          if (!have_fwd && forward_l1(m, a, s)) return 1;  // first step of the epoch: later ones are fused
-          HidArgs h = hid_args(m, src, 1, 1, m->train_locs, nullptr);
-          if (hidden_tc_launch(h, s)) return 1;
-          if (pend.m != nullptr) {
-            if (l1_backward_tc(pend.a, pend.m->n_bwd_blocks, s, true)) return 1;
-            if (hidden_update_launch(pend.u, s, true)) return 1;
+    if (ring) {
+      // rings of two models (three for the last ring of an odd group): a model comes back after ONE other
+      // model's weight stream, so the tail of its previous step's updates is still in L2 (rings of four
+      // measured 4 % slower).  Each ring runs its whole epoch; the models are independent.
+      for (int g0 = 0; g0 < n_models;) {
+        const int g1 = (n_models - g0 == 3) ? n_models : (g0 + 2 < n_models ? g0 + 2 : n_models);
+        bool have_fwd = false;
+        Pending pend;
+        pend.m = nullptr;
+        for (int64_t off = 0; off < m0->n_train; off += m0->B) {
+          const bool has_next = off + m0->B < m0->n_train;
+          for (int g = g0; g < g1; ++g) {
+            loc_model* m = models[g];
+            const RowSrc src = step_rows(g, off);
+            L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, 1);
+            if (!have_fwd && forward_l1(m, a, s)) return 1;  // first step of the epoch: later ones are fused
+            HidArgs h = hid_args(m, src, 1, 1, m->train_locs, nullptr);
+            if (hidden_tc_launch(h, s)) return 1;
+            if (pend.m != nullptr) {
+              if (l1_backward_tc(pend.a, pend.m->n_bwd_blocks, s, true)) return 1;
+              if (hidden_update_launch(pend.u, s, true)) return 1;
+            }
+            if (has_next) {
+              a.src_next = step_rows(g, off + m0->B);
+              a.fuse_next = 1;
+            }
+            pend.m = m;
+            pend.a = a;
+            pend.u = upd_args(m, src.nb, 1);
           }
-          if (has_next) {
-            a.src_next = step_rows(g, off + m0->B);
-            a.fuse_next = 1;
-          }
-          pend.m = m;
-          pend.a = a;
-          pend.u = upd_args(m, src.nb, 1);
+          have_fwd = has_next;
         }
-        have_fwd = has_next;
-        continue;
+        if (pend.m != nullptr) {  // the ring's last backward and update of the epoch
+          if (l1_backward_tc(pend.a, pend.m->n_bwd_blocks, s)) return 1;
+          if (hidden_update_launch(pend.u, s)) return 1;
+        }
+        g0 = g1;
       }
+    }
+    bool have_fwd = false;
+    for (int64_t off = 0; !ring && off < m0->n_train; off += m0->B) {
+      const bool has_next = off + m0->B < m0->n_train;
       HidGroupArgs hg;
       hg.n = n_models;
       // first-layer forwards (first step of the epoch only: later ones are fused into the backward)
@@ -823,10 +841,6 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
       }
       for (int g = 0; g < n_models; ++g) LOC_CUDA(cudaStreamWaitEvent(s, models[g]->ev_upd, 0));
       have_fwd = has_next;
-    }
-    if (pend.m != nullptr) {  // ring: the last model's backward and update of the epoch's last step
-      if (l1_backward_tc(pend.a, pend.m->n_bwd_blocks, s)) return 1;
-      if (hidden_update_launch(pend.u, s)) return 1;
     }
     for (int g = 0; g < n_models; ++g) {
       loc_model* m = models[g];

@@ -292,6 +292,9 @@ def _model_seed():
     return int.from_bytes(os.urandom(8), "little")
 
 
+RING_MIN_SNPS = 32768
+
+
 def load_network(traingen, dropout_prop):
     from .model import LocatorModel, spare_cluster_l1_ctas
 
@@ -300,7 +303,9 @@ def load_network(traingen, dropout_prop):
     # first-layer kernels, so that one model's hidden stack overlaps another's weight stream (ring schedule of
     # loc_group_train_epochs).  The CTA count fixes the fp32 summation order of the layer, hence the same
     # setting for every model of such a run, grouped or not.
-    grouped = (args.bootstrap or args.windows) and int(getattr(args, "replicates_per_gpu", 1) or 1) >= 2
+    # (Only where the weight stream outlasts the hidden stack: RING_MIN_SNPS mirrors kRingMinK of the library.)
+    grouped = (args.bootstrap or args.windows) and int(getattr(args, "replicates_per_gpu", 1) or 1) >= 2 \
+        and K >= RING_MIN_SNPS
     return LocatorModel(K, width=args.width, nlayers=args.nlayers, dropout_prop=args.dropout_prop,
                         batch_size=args.batch_size, max_epochs=args.max_epochs, seed=_model_seed(),
                         l1_ctas=spare_cluster_l1_ctas() if grouped else None)

@@ -213,16 +213,20 @@ def test_step_invariants_full_width(M):
     assert np.all(np.isfinite(w1[0])) and np.all(np.isfinite(w1[1]))
 
 
-@pytest.mark.parametrize("schedule", ["all_sms", "fewer_ctas"])
-def test_group_training_matches_individual_training(M, schedule):
+@pytest.mark.parametrize("schedule", ["all_sms", "fewer_ctas", "ring"])
+def test_group_training_matches_individual_training(M, schedule, monkeypatch):
     """Replicate group (loc_group_train_epochs): each model of a group ends bit-identical to the same model
-    trained alone -- the grouped hidden-stack launch only changes scheduling.  Second case: K large enough for
-    several tiles per CTA with the first-layer kernels on SMs - 16 (loc_model_set_l1_ctas; same setting for the
-    solo runs, it fixes the summation order) -- the case that exposed a shared-memory reuse race between the
-    backward kernel's builder and forward warps (results differed from run to run in the 6th digit)."""
+    trained alone -- grouping only changes scheduling.  "all_sms": lockstep schedule (grouped hidden-stack
+    launch).  "fewer_ctas": the same with K large enough for several tiles per CTA and the first-layer kernels on
+    SMs - 16 (loc_model_set_l1_ctas; same setting for the solo runs, it fixes the summation order) -- the case that
+    exposed a shared-memory reuse race between the backward kernel's builder and forward warps.  "ring": the
+    schedule large models get (one model's hidden stack concurrent with the previous model's first-layer
+    backward + Adam through programmatic dependent launch), forced here at K = 20,000 on a ring of three."""
     rng = np.random.default_rng(12)
     K, ntr, nva, epochs = 3000 if schedule == "all_sms" else 20000, 75, 20, 5
     ctas = None if schedule == "all_sms" else M.spare_cluster_l1_ctas()
+    monkeypatch.setenv("LOC_GROUP_SCHEDULE", "ring" if schedule == "ring" else "lockstep")
+    pick = slice(None) if schedule == "ring" else slice(None, None, 2)
     datas = []
     for g in range(3):
         x, y = _data(rng, ntr, K)
@@ -231,15 +235,17 @@ def test_group_training_matches_individual_training(M, schedule):
     solo = []
     for g, (x, y, xv, yv) in enumerate(datas):
         m = M.LocatorModel(K, seed=40 + g, max_epochs=epochs, l1_ctas=ctas)
-        h = m.fit(x, y, epochs=epochs, validation_data=(xv, yv), patience=2 if g == 1 else 100, epochs_per_call=2)
+        h = m.fit(x, y, epochs=epochs, validation_data=(xv, yv), patience=2 if (g == 1 and schedule != "ring") else 100,
+                  epochs_per_call=2)
         solo.append((h, m.predict(xv), m.get_weights()[4]))
     ms = [M.LocatorModel(K, seed=40 + g, max_epochs=epochs, l1_ctas=ctas) for g in range(3)]
     if ms[0].impl != "tcgen05":
         pytest.skip("replicate groups need the tcgen05 kernels")
-    # one patience for the whole group: compare the model with patience 100 semantics only where equal
-    hs = M.fit_group(ms[::2], [d[0] for d in datas[::2]], [d[1] for d in datas[::2]],
-                     [(d[2], d[3]) for d in datas[::2]], epochs=epochs, patience=100, epochs_per_call=2)
-    for (h, yp, w), m, hg, d in zip(solo[::2], ms[::2], hs, datas[::2]):
+    # one patience for the whole group: compare the models with patience 100 semantics only where equal
+    hs = M.fit_group(ms[pick], [d[0] for d in datas[pick]], [d[1] for d in datas[pick]],
+                     [(d[2], d[3]) for d in datas[pick]], epochs=epochs, patience=100, epochs_per_call=2)
+    assert len(hs) == (3 if schedule == "ring" else 2)
+    for (h, yp, w), m, hg, d in zip(solo[pick], ms[pick], hs, datas[pick]):
         assert hg.history["loss"] == h.history["loss"] and hg.history["val_loss"] == h.history["val_loss"]
         assert np.array_equal(m.predict(d[2]), yp)
         assert np.array_equal(m.get_weights()[4], w)

@@ -188,7 +188,8 @@ int loc_model_set_tp(loc_model* m, loc_tp* tp);
 /* Number of CTAs (= SMs used, = split-K partial tiles) of the tcgen05 first-layer kernels; default: all SMs.
  * The plain backward + Adam kernel is memory-bound and as fast on SMs - 16 as on all of them (B200: 113 vs
  * 114 us at K = 100k), the variant with the fused next forward loses 3 %.  The value fixes the fp32
- * summation order of the layer: set it the same way for runs that must agree bit for bit. */
+ * summation order of the layer: set it the same way for runs that must agree bit for bit.  SMs - 16 is what
+ * the ring schedule of loc_group_train_epochs needs (one cluster of the hidden stack fits next to the kernel). */
 int loc_model_set_l1_ctas(loc_model* m, int32_t n_ctas);
 
 /* lr, EarlyStopping patience (ReduceLROnPlateau patience = patience/6), and
@@ -217,11 +218,17 @@ int loc_train_step(loc_model* m, const int32_t* d_rows, int32_t nb, void* stream
  * no-ops.  History rows are appended per epoch. */
 int loc_train_epochs(loc_model* m, const int32_t* d_perms, int32_t n_epochs, void* stream);
 
-/* Replicate group (bootstrap / window models trained side by side on one GPU): the same as
- * loc_train_epochs for n_models <= 8 independent models advanced in lockstep -- their hidden stacks
- * run in one launch (one cluster per model) so that they overlap instead of each leaving most SMs
- * idle; first-layer kernels run back to back.  Models must share nlayers, batch size and
- * training-set size (true for the replicates of one run); d_perms[g] is model g's batch order. */
+/* Replicate group (bootstrap / window models trained side by side on one GPU, locator.py:519-583 and
+ * :609-681 run them one after the other): the same as loc_train_epochs for n_models <= 8 independent models.
+ * Models must share nlayers, batch size and training-set size (true for the replicates of one run);
+ * d_perms[g] is model g's batch order.  Every model ends bit-identical to the same model trained alone.
+ * Two schedules:
+ *   ring     (models of >= 32768 SNPs whose first-layer kernels leave 16 SMs free, loc_model_set_l1_ctas):
+ *            the hidden stack of one model runs concurrently with the first-layer backward + Adam of the
+ *            previous model of its ring (programmatic dependent launch inside one stream);
+ *   lockstep (otherwise): the hidden stacks of all models share one launch (one cluster per model), the
+ *            first-layer kernels run back to back.
+ * Environment LOC_GROUP_SCHEDULE=ring|lockstep overrides the choice by size. */
 int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* const* d_perms, int32_t n_epochs,
                            void* stream);
 

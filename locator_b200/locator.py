@@ -477,7 +477,16 @@ def main(argv=None):
     if args.out is None:
         raise SystemExit("--out is required")
     _write_params()
+    from . import replicates
 
+    replicates.start_pool_early(args)  # several GPUs: the workers boot while this process reads and draws
+    try:
+        return _main_body()
+    finally:
+        replicates.abort_early_pool()  # only still there if the run failed before handing it over
+
+
+def _main_body():
     genotypes, samples = load_genotypes()
     sample_data, locs = sort_samples(samples, genotypes)
     meanlong, sdlong, meanlat, sdlat, locs = normalize_locs(locs)

@@ -205,7 +205,7 @@ def _resolve(runner):
     return getattr(importlib.import_module(mod), fn)
 
 
-def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None):
+def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None, init_q=None):
     try:
         if runner is not None:  # host-logic tests: no CUDA, the runner consumes the raw item
             run = _resolve(runner)
@@ -224,6 +224,10 @@ def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None):
 
         L.set_args(copy.copy(args))
         base = None
+        if init_q is not None:
+            # the pool was started before the parent had the run's matrices (so that this start-up -- import
+            # torch, CUDA context: seconds -- overlaps the parent's own): they arrive here, once
+            base_host = init_q.get()
         if base_host is not None:
             base = dict(base_host)
             for k in ("traingen", "testgen", "predgen"):
@@ -296,23 +300,47 @@ def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None):
 class ReplicatePool:
     """One worker process per GPU pulling work items from a shared queue."""
 
-    def __init__(self, n_gpus, args, base=None, runner=None):
+    def __init__(self, n_gpus, args, base=None, runner=None, deferred_base=False):
+        """deferred_base: the workers are started now and wait for the run's matrices (``send_base``)."""
         import multiprocessing as mp
 
         ctx = mp.get_context("spawn")
         self.n = n_gpus
         self.task_q = ctx.Queue()
         self.result_q = ctx.Queue()
-        base_host = None
-        if base is not None:
-            base_host = dict(base)
-            for k in ("traingen", "testgen", "predgen"):
-                base_host[k] = _to_host(base[k])
-        self.procs = [ctx.Process(target=_worker, args=(r, n_gpus, args, base_host, self.task_q, self.result_q, runner))
+        self.init_qs = [ctx.Queue() for _ in range(n_gpus)] if deferred_base else None
+        base_host = self._host(base)
+        self.procs = [ctx.Process(target=_worker,
+                                  args=(r, n_gpus, args, base_host, self.task_q, self.result_q, runner,
+                                        self.init_qs[r] if deferred_base else None))
                       for r in range(n_gpus)]
         for p in self.procs:
             p.start()
         self.submitted = 0
+        self.closed = False
+
+    @staticmethod
+    def _host(base):
+        if base is None:
+            return None
+        base_host = dict(base)
+        for k in ("traingen", "testgen", "predgen"):
+            base_host[k] = _to_host(base[k])
+        return base_host
+
+    def send_base(self, base):
+        base_host = self._host(base)
+        for q in self.init_qs:
+            q.put(base_host)
+
+    def abort(self):
+        """The parent failed before close(): do not leave workers waiting on their queues."""
+        if not self.closed:
+            self.closed = True
+            for p in self.procs:
+                p.terminate()
+            for p in self.procs:
+                p.join()
 
     def submit(self, item):
         item = dict(item)
@@ -323,6 +351,7 @@ class ReplicatePool:
         self.submitted += 1
 
     def close(self):
+        self.closed = True
         for _ in self.procs:
             self.task_q.put(None)
         done = exited = 0
@@ -348,6 +377,37 @@ class ReplicatePool:
 # ---------------------------------------------------------------------------------------------
 # drivers called from locator.main()
 # ---------------------------------------------------------------------------------------------
+_early = {"pool": None, "taken": None}
+
+
+def start_pool_early(args):
+    """Called by main() right after the arguments are known: with several GPUs the worker processes of a
+    --windows / --bootstrap run boot (import torch, create their CUDA context) while the parent is still
+    importing, reading metadata and drawing indices."""
+    n_gpus = max(1, int(getattr(args, "gpus", 1) or 1))
+    if n_gpus > 1 and (args.windows or args.bootstrap) and _early["pool"] is None:
+        _early["pool"] = ReplicatePool(n_gpus, args, deferred_base=bool(args.bootstrap) and not args.windows)
+    return _early["pool"]
+
+
+def abort_early_pool():
+    """End of main(): a pool that was never handed over, or whose driver failed before close(), is torn down."""
+    for key in ("pool", "taken"):
+        pool, _early[key] = _early[key], None
+        if pool is not None:
+            pool.abort()
+
+
+def _take_pool(n_gpus, args, base=None):
+    pool, _early["pool"] = _early["pool"], None
+    if pool is None:
+        pool = ReplicatePool(n_gpus, args, base)
+    elif pool.init_qs is not None:
+        pool.send_base(base)
+    _early["taken"] = pool
+    return pool
+
+
 def run_bootstrap(L, traingen, testgen, trainlocs, testlocs, predgen, norm, pred, samples):
     args = L.args
     base = {"traingen": traingen, "testgen": testgen, "predgen": predgen, "trainlocs": trainlocs,
@@ -366,7 +426,7 @@ def run_bootstrap(L, traingen, testgen, trainlocs, testlocs, predgen, norm, pred
     # Several GPUs: the full model is one more independent work item (training draws nothing from numpy's
     # global stream, so the replicates' draws do not have to wait for it), and the workers start up while
     # the parent draws: no GPU idles through the full run.
-    pool = ReplicatePool(n_gpus, args, base)
+    pool = _take_pool(n_gpus, args, base)
     pool.submit({"kind": "full", "boot": "FULL"})
     for boot, order in enumerate(draw_bootstrap_orders(traingen.K, args.nboots)):
         pool.submit({"kind": "boot", "boot": boot, "site_order": order})
@@ -389,7 +449,7 @@ def run_windows(L, genotypes, samples):
     stop = np.max(positions) if args.window_stop == None else int(args.window_stop)  # noqa: E711
     size = int(float(args.window_size))
     n_gpus = max(1, int(getattr(args, "gpus", 1) or 1))
-    pool = ReplicatePool(n_gpus, args) if n_gpus > 1 else None
+    pool = _take_pool(n_gpus, args) if n_gpus > 1 else None
     # Recipes instead of matrices whenever no draw depends on the genotypes: whoever runs the window (a
     # worker process, or this process's prefetch thread) reads, filters and packs it.
     # LOC_WINDOWS_PARENT_INGEST=1 keeps the serial reference order of work (parity tests compare the two).

@@ -16,6 +16,15 @@ import traceback
 import numpy as np
 
 
+def _tick(what):
+    """LOC_TIMING=1: wall-clock milestones of the replicate drivers on stderr (seconds since the epoch, so the
+    lines of the parent and the workers interleave on one axis)."""
+    if os.environ.get("LOC_TIMING"):
+        import sys
+
+        print(f"[loc-timing {time.time():.3f} pid {os.getpid()}] {what}", file=sys.stderr, flush=True)
+
+
 # ---------------------------------------------------------------------------------------------
 # (de)serialisation of packed device matrices for the worker processes
 # ---------------------------------------------------------------------------------------------
@@ -217,10 +226,14 @@ def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None, init_q
                 result_q.put(("done", rank, item.get("boot", item.get("index"))))
             result_q.put(("exit", rank, None))
             return
+        _tick(f"worker {rank}: process up")
         import torch
 
         torch.cuda.set_device(rank % max(1, torch.cuda.device_count()))
+        torch.zeros(1, device="cuda")  # create the CUDA context now, while the parent is still busy
         from . import locator as L
+
+        _tick(f"worker {rank}: torch + CUDA context ready")
 
         L.set_args(copy.copy(args))
         base = None
@@ -228,6 +241,7 @@ def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None, init_q
             # the pool was started before the parent had the run's matrices (so that this start-up -- import
             # torch, CUDA context: seconds -- overlaps the parent's own): they arrive here, once
             base_host = init_q.get()
+            _tick(f"worker {rank}: base matrices received")
         if base_host is not None:
             base = dict(base_host)
             for k in ("traingen", "testgen", "predgen"):
@@ -288,10 +302,15 @@ def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None, init_q
                 nxt = take_group(block=False)
                 if nxt is not None:
                     ahead = (nxt, pf.submit(nxt))
-            _run_items(L, items, base, Prefetcher.collect(fut))
+            _tick(f"worker {rank}: group of {len(items)} taken")
+            reps = Prefetcher.collect(fut)
+            _tick(f"worker {rank}: group prepared")
+            _run_items(L, items, base, reps)
+            _tick(f"worker {rank}: group done")
             for it in items:
                 result_q.put(("done", rank, it.get("boot", it.get("index"))))
         pf.close()
+        _tick(f"worker {rank}: exiting")
         result_q.put(("exit", rank, None))
     except Exception:  # surface the failure in the parent instead of hanging the queue
         result_q.put(("error", rank, traceback.format_exc()))
@@ -352,6 +371,7 @@ class ReplicatePool:
 
     def close(self):
         self.closed = True
+        _tick("parent: all items submitted, waiting for the workers")
         for _ in self.procs:
             self.task_q.put(None)
         done = exited = 0
@@ -368,6 +388,7 @@ class ReplicatePool:
             if errors:
                 p.terminate()
             p.join()
+        _tick("parent: workers joined")
         if errors:
             raise RuntimeError(f"replicate worker {errors[0][0]} failed:\n{errors[0][1]}")
         if done != self.submitted:
@@ -386,6 +407,7 @@ def start_pool_early(args):
     importing, reading metadata and drawing indices."""
     n_gpus = max(1, int(getattr(args, "gpus", 1) or 1))
     if n_gpus > 1 and (args.windows or args.bootstrap) and _early["pool"] is None:
+        _tick("parent: starting the worker pool")
         _early["pool"] = ReplicatePool(n_gpus, args, deferred_base=bool(args.bootstrap) and not args.windows)
     return _early["pool"]
 
@@ -403,6 +425,7 @@ def _take_pool(n_gpus, args, base=None):
     if pool is None:
         pool = ReplicatePool(n_gpus, args, base)
     elif pool.init_qs is not None:
+        _tick("parent: sending the base matrices")
         pool.send_base(base)
     _early["taken"] = pool
     return pool
@@ -426,9 +449,10 @@ def run_bootstrap(L, traingen, testgen, trainlocs, testlocs, predgen, norm, pred
     # Several GPUs: the full model is one more independent work item (training draws nothing from numpy's
     # global stream, so the replicates' draws do not have to wait for it), and the workers start up while
     # the parent draws: no GPU idles through the full run.
+    orders = draw_bootstrap_orders(traingen.K, args.nboots)  # before the first submit: full groups form at once
     pool = _take_pool(n_gpus, args, base)
     pool.submit({"kind": "full", "boot": "FULL"})
-    for boot, order in enumerate(draw_bootstrap_orders(traingen.K, args.nboots)):
+    for boot, order in enumerate(orders):
         pool.submit({"kind": "boot", "boot": boot, "site_order": order})
     pool.close()
 

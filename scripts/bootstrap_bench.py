@@ -54,6 +54,9 @@ def main():
         res[n] = {"seconds": dt, "models_done": len(files), "models_per_hour": 3600.0 * len(files) / dt, "rc": r.returncode}
         if r.returncode != 0:
             print(r.stdout[-1500:], r.stderr[-3000:])
+        if os.environ.get("LOC_TIMING"):
+            print(f"process started at {t:.3f}")
+            print("\n".join(l for l in r.stderr.splitlines() if "loc-timing" in l), flush=True)
         print(n, "GPU(s):", json.dumps(res[n]), flush=True)
     same = all(outs[1] == outs[n] for n in outs)
     print(json.dumps({"workload": f"bootstrap: FULL + {a.nboots} replicates x {a.samples} samples x {a.snps} SNPs, "

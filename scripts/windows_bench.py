@@ -65,6 +65,9 @@ def main():
         res[n] = {"seconds": dt, "windows_done": done, "models_per_hour": 3600.0 * done / dt, "rc": r.returncode}
         if r.returncode != 0:
             print(r.stdout[-1500:], r.stderr[-3000:])
+        if os.environ.get("LOC_TIMING"):
+            print(f"process started at {t:.3f}")
+            print("\n".join(l for l in r.stderr.splitlines() if "loc-timing" in l), flush=True)
         print(n, "GPU(s):", json.dumps(res[n]), flush=True)
     print(json.dumps({"workload": f"{a.windows} windows x {a.snps} SNPs x {a.samples} samples, {a.epochs} epochs each",
                       "results": res}))

@@ -126,6 +126,14 @@ int64_t loc_vcf_count(const char* h_buf, int64_t len);
 int loc_vcf_parse_gt(const char* h_buf, int64_t len, int64_t n_samples, int64_t n_variants, int8_t* h_gt, int64_t* h_pos,
                      int32_t n_threads);
 
+/* Host helper for the index draws that bound the jacknife sweep and replace_md (locator.py:722-727,
+ * :258-261): consecutive numpy RandomState.binomial(n, p[i]) draws -- `reps` per p[i], sites in order --
+ * taken from the MT19937 state of np.random.get_state() (key[624], position), which is advanced in place
+ * exactly as numpy would advance it.  out uint8 [n_p][reps].  Returns 0; 1 if some (n, p[i]) needs numpy's
+ * BTPE branch (min(p, 1-p) * n > 30) or n > 255 -- nothing is drawn then; 2 for p outside [0, 1]. */
+int loc_np_legacy_binomial(uint32_t* mt_key, int32_t* mt_pos, int64_t n, const double* h_p, int64_t n_p, int64_t reps,
+                           uint8_t* h_out);
+
 /* ---------------- model (K3-K7) ---------------- */
 
 /* BN(K) -> Dense(width, elu) x nlayers (Dropout after the floor(nlayers/2)-th)

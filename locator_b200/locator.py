@@ -212,8 +212,10 @@ def replace_md(genotypes, keep_idx=None, packed=None):
         af = dc / (2 * ninds)
     ks, samps = np.nonzero(missing)  # row-major (site, sample) order
     if len(ks):
-        vals = np.random.binomial(2, af[ks])  # one vectorised draw == the same scalar draws in order
-        packed.patch(ks, samps, vals.astype(np.uint8))
+        from .nprandom import legacy_binomial
+
+        vals = legacy_binomial(2, af[ks], 1)[:, 0]  # the reference's scalar draws, in its (site, sample) order
+        packed.patch(ks, samps, vals)
     return AlleleCounts(packed)
 
 
@@ -423,12 +425,14 @@ def _run_one(traingen, testgen, trainlocs, testlocs, predgen, norm, pred, sample
 def _jacknife_draws(af, K, n_pred):
     """(sites_to_remove, vals uint8 [nsites, n_pred]) per replicate, from numpy's global stream in the
     reference's order (locator.py:722-727): choice without replacement, then per chosen site, in the
-    returned order, binomial(2, af[site], n_pred).  One vectorised binomial over the repeated
-    frequencies consumes the stream exactly like the per-site calls, and releases the GIL, so the draws
-    of replicate r+1 (the serial bottleneck of the sweep: ~50 ns per call) are taken by a helper thread
-    while replicate r is predicted and written.  Nothing else touches the stream during the sweep."""
+    returned order, binomial(2, af[site], n_pred).  The binomials are taken by the library's restatement of
+    numpy's generator (nprandom.legacy_binomial: same stream, a few ns per draw instead of ~50, GIL
+    released), and the draws of replicate r+1 run in a helper thread while replicate r is predicted and
+    written.  Nothing else touches the stream during the sweep."""
     import queue
     import threading
+
+    from .nprandom import legacy_binomial
 
     nsites = int(K * args.jacknife_prop)
     q = queue.Queue(maxsize=2)
@@ -437,10 +441,7 @@ def _jacknife_draws(af, K, n_pred):
         try:
             for _ in range(args.nboots):
                 sites = np.random.choice(K, nsites, replace=False)
-                if nsites:
-                    vals = np.random.binomial(2, np.repeat(af[sites], n_pred)).reshape(nsites, n_pred).astype(np.uint8)
-                else:
-                    vals = np.zeros((0, n_pred), np.uint8)
+                vals = legacy_binomial(2, af[sites], n_pred)
                 q.put((sites, vals))
             q.put(None)
         except BaseException as e:  # surfaces in the consumer

@@ -304,3 +304,46 @@ def test_jacknife_draws_follow_the_reference_stream():
     L.set_args(L.build_parser().parse_args(["--out", "x", "--jacknife", "--nboots", "2", "--jacknife_prop", "0.0"]))
     got = list(L._jacknife_draws(af, K, n_pred))
     assert [v.shape for _, v in got] == [(0, n_pred)] * 2
+
+
+def test_legacy_binomial_reproduces_numpy_global_stream():
+    """nprandom.legacy_binomial (loc_np_legacy_binomial: MT19937 + numpy's inversion sampler restated in the
+    library) returns exactly what np.random.binomial returns for scalar-p calls in order, and leaves numpy's
+    global stream -- position and cached gaussian included -- where numpy would have left it."""
+    from locator_b200.nprandom import legacy_binomial
+
+    rng = np.random.default_rng(21)
+    for n in (0, 1, 2, 5, 16, 17, 60, 255):
+        hi = min(1.0, 30.0 / max(n, 1))
+        p = np.concatenate([rng.uniform(0, hi, 300), 1 - rng.uniform(0, hi, 300),
+                            [0.0, 1.0, 0.5, np.nextafter(0.5, 1), 1e-300, 1 - 1e-16]])
+        p = p[np.minimum(p, 1 - p) * n <= 30]
+        np.random.seed(1000 + n)
+        np.random.normal()           # leaves a cached gaussian in the state
+        np.random.random(5)          # and a position inside the block of 624
+        want = np.stack([np.random.binomial(n, pi, 11) for pi in p])
+        after_want = (np.random.normal(), np.random.random())
+        np.random.seed(1000 + n)
+        np.random.normal()
+        np.random.random(5)
+        got = legacy_binomial(n, p, 11)
+        after_got = (np.random.normal(), np.random.random())
+        assert got.dtype == np.uint8 and np.array_equal(got, want) and after_got == after_want
+    # several refills of the 624-word state, the config-5 shape of one jacknife replicate (scaled)
+    af = rng.uniform(0, 1, 4000)
+    np.random.seed(3)
+    want = np.random.binomial(2, np.repeat(af, 250)).reshape(-1, 250)
+    x = np.random.random()
+    np.random.seed(3)
+    assert np.array_equal(legacy_binomial(2, af, 250), want) and np.random.random() == x
+    # numpy's BTPE branch and wide counts are left to numpy itself -- same values, same stream
+    np.random.seed(4)
+    want = np.random.binomial(100, np.repeat([0.4, 0.6], 5)).reshape(2, 5)
+    x = np.random.random()
+    np.random.seed(4)
+    assert np.array_equal(legacy_binomial(100, [0.4, 0.6], 5), want) and np.random.random() == x
+    assert legacy_binomial(2, [], 7).shape == (0, 7) and legacy_binomial(2, [0.3], 0).shape == (1, 0)
+    with pytest.raises(ValueError):
+        legacy_binomial(2, [0.2, np.nan], 3)
+    with pytest.raises(ValueError):
+        legacy_binomial(2, [1.5], 3)

@@ -31,7 +31,13 @@ bool lz4_block(const uint8_t* src, int64_t slen, uint8_t* dst, int64_t dlen) {
       } while (b == 255);
     }
     if (lit > iend - ip || lit > oend - op) return false;
-    memcpy(op, ip, (size_t)lit);
+    // short literal runs dominate genotype chunks: one unconditional 16-byte move when both buffers have the
+    // room (the surplus bytes are overwritten by what follows), a real memcpy otherwise
+    if (lit <= 16 && iend - ip >= 16 && oend - op >= 16) {
+      memcpy(op, ip, 16);
+    } else {
+      memcpy(op, ip, (size_t)lit);
+    }
     ip += lit;
     op += lit;
     if (ip >= iend) break;  // the last sequence has literals only
@@ -50,7 +56,23 @@ bool lz4_block(const uint8_t* src, int64_t slen, uint8_t* dst, int64_t dlen) {
     }
     if (ml > oend - op) return false;
     const uint8_t* m = op - off;
-    for (int64_t i = 0; i < ml; ++i) op[i] = m[i];  // overlapping copies replicate the pattern
+    if (off >= 8 && oend - op >= ml + 8) {
+      // 8-byte steps: every read lies at least 8 bytes behind its write, so it only sees finished bytes; the
+      // last step may write up to 7 bytes past the match, inside the buffer, overwritten by what follows
+      for (int64_t i = 0; i < ml; i += 8) memcpy(op + i, m + i, 8);
+    } else if (off >= ml) {
+      memcpy(op, m, (size_t)ml);
+    } else {
+      // overlapping match = the last `off` bytes repeated (genotype chunks are mostly runs: off = 1, ml in the
+      // hundreds).  Copy from the start of the pattern in pieces that double: the bytes written so far stay a
+      // whole number of periods, so source [m, m + c) never reaches the destination and has the right phase.
+      int64_t filled = 0;
+      while (filled < ml) {
+        const int64_t c = (off + filled) < (ml - filled) ? (off + filled) : (ml - filled);
+        memcpy(op + filled, m, (size_t)c);
+        filled += c;
+      }
+    }
     op += ml;
   }
   return op == oend;
@@ -89,7 +111,8 @@ int64_t loc_blosc_decompress(const uint8_t* src, int64_t src_len, uint8_t* dst, 
     loc::fail("loc_blosc_decompress: only the LZ4 codec of Blosc is supported", __FILE__, __LINE__);
     return -3;
   }
-  const bool shuffle = (flags & 0x1) != 0, dont_split = (flags & 0x10) != 0;
+  // the byte transpose of 1-byte items (int8 calldata/GT, by far the largest array) is the identity
+  const bool shuffle = (flags & 0x1) != 0 && typesize > 1, dont_split = (flags & 0x10) != 0;
   const int64_t nblocks = (nbytes + blocksize - 1) / blocksize;
   if (16 + 4 * nblocks > src_len) return -1;
   std::vector<uint8_t> tmp((size_t)blocksize);

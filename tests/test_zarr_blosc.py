@@ -220,3 +220,23 @@ def test_raw_whole_row_chunks_are_read_in_place_and_truncation_is_an_error(tmp_p
         fh.write(blob[:len(blob) // 2])
     with pytest.raises(ValueError, match="truncated"):
         io.ZarrRows(z, "calldata/GT", 250, 950).read()
+
+
+def test_lz4_decoder_fast_paths_at_buffer_edges():
+    """The decoder copies short literal runs and matches with fixed-size moves when there is room and falls back
+    to exact copies near the ends of the buffers; overlapping matches (runs, short periods) are replicated by
+    doubling.  Periodic data of every small period, with and without a random tail, and low-entropy data of many
+    lengths around the move sizes must round-trip for several block sizes."""
+    rng = np.random.default_rng(5)
+    for period in (1, 2, 3, 5, 7, 8, 9, 15, 16, 17, 31, 64):
+        pat = bytes(rng.integers(0, 256, period, dtype=np.uint8))
+        for tail in (0, 1, 5, 100):
+            data = (pat * 1200)[:9000] + bytes(rng.integers(0, 256, tail, dtype=np.uint8))
+            assert io._blosc_decompress(_blosc_frame(data, 1, 1 << 16, shuffle=False)) == data, (period, tail)
+    for n in list(range(1, 40)) + [255, 256, 257, 4095, 4096, 4097, 20000]:
+        data = bytes(rng.integers(0, 4, n, dtype=np.uint8))
+        for bs in (64, 4096, 1 << 16):
+            assert io._blosc_decompress(_blosc_frame(data, 1, bs, shuffle=False)) == data, (n, bs)
+    # the shuffle flag on 1-byte items (what zarr writes for int8 calldata/GT) is the identity
+    data = bytes(rng.integers(0, 3, 5000, dtype=np.uint8))
+    assert io._blosc_decompress(_blosc_frame(data, 1, 2048, shuffle=True)) == data

@@ -324,6 +324,8 @@ class LocatorModel:
             raise ValueError(f"matrix has {g.K} SNPs, model expects {self.K}")
         # the reference re-predicts the unchanged validation set for every jacknife replicate
         # (locator.py:441 inside :729-743): same weights + same device matrix -> same answer
+        if g.n == 0:  # no rows (a run without NA-location samples): Keras returns an empty [0, 2] array
+            return np.zeros((0, 2), dtype=np.float32)
         key = (id(g), g.version, self._wver) if isinstance(x, PackedGenotypes) else None
         if key is not None and self._memo.get("key") == key:
             return self._memo["val"].copy()

@@ -464,10 +464,10 @@ def main(argv=None):
     parser = build_parser()
     set_args(parser.parse_args(argv))
 
-    # set seed and gpu (locator.py:170-173, :491-494)
+    # set seed and gpu (locator.py:170-173), load stored parameters (:177-184), seed again in main() (:491-494):
+    # with --load_params it is the stored seed that decides the run's draws
     if args.seed is not None:
         np.random.seed(args.seed)
-        np.random.seed(args.seed)  # the reference seeds at import and again in main(); idempotent
     if args.gpu_number is not None:
         os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu_number
     if args.load_params is not None:
@@ -475,6 +475,10 @@ def main(argv=None):
         with open(args.load_params, "r") as f:
             args.__dict__ = json.load(f)
         args.gpus, args.replicates_per_gpu = gpus, rpg
+    if args.seed is not None:
+        np.random.seed(args.seed)
+    if args.gpu_number is not None:
+        os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu_number
     if args.out is None:
         raise SystemExit("--out is required")
     _write_params()

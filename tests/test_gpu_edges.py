@@ -124,3 +124,55 @@ def test_batch_size_above_32_is_refused_loudly(L, tmp_path):
     with pytest.raises(Exception, match="batch_size"):
         L.main(["--vcf", vcf, "--sample_data", sd, "--out", str(tmp_path / "o"), "--seed", "1", "--max_epochs", "2",
                 "--batch_size", "64", "--keras_verbose", "0"])
+
+
+def test_replicate_drivers_on_degenerate_counts(L, tmp_path):
+    """One bootstrap replicate with groups of four (a group of one), a jacknife that replaces no site, and
+    --min_mac 1 (the count filter is skipped entirely, locator.py:270)."""
+    vcf, sd, na = _write_inputs(tmp_path, 45, 260, 5, seed=4)
+    common = ["--vcf", vcf, "--sample_data", sd, "--seed", "8", "--max_epochs", "3", "--keras_verbose", "0"]
+    out = str(tmp_path / "b")
+    assert L.main(common + ["--out", out, "--bootstrap", "--nboots", "1", "--replicates_per_gpu", "4"]) == 0
+    assert len(_rows(out + "_bootFULL_predlocs.txt")[1]) == 5 and len(_rows(out + "_boot0_predlocs.txt")[1]) == 5
+    out = str(tmp_path / "j")
+    assert L.main(common + ["--out", out, "--jacknife", "--nboots", "2", "--jacknife_prop", "0"]) == 0
+    full = open(out + "_bootFULL_predlocs.txt").read()
+    assert open(out + "_boot0_predlocs.txt").read() == full and open(out + "_boot1_predlocs.txt").read() == full
+    out1, out2 = str(tmp_path / "m1"), str(tmp_path / "m2")
+    assert L.main(common + ["--out", out1, "--min_mac", "1"]) == 0
+    assert L.main(common + ["--out", out2, "--min_mac", "2"]) == 0
+    assert len(_rows(out1 + "_predlocs.txt")[1]) == 5
+
+
+def test_weights_file_round_trip_and_load_params(L, tmp_path):
+    """--keep_weights writes the best weights (Keras order); a fresh model that loads them predicts the same
+    bytes.  --load_params re-runs with the stored arguments (locator.py:177-184)."""
+    from locator_b200 import model as M
+    import json
+
+    vcf, sd, na = _write_inputs(tmp_path, 45, 260, 5, seed=6)
+    out = str(tmp_path / "w")
+    assert L.main(["--vcf", vcf, "--sample_data", sd, "--out", out, "--seed", "21", "--max_epochs", "4",
+                   "--keras_verbose", "0", "--keep_weights"]) == 0
+    first = open(out + "_predlocs.txt").read()
+    with np.load(out + ".weights.npz") as z:
+        ws = [z[k] for k in sorted(z.files)]
+    K = ws[0].shape[0]
+    assert ws[4].shape == (K, 256) and len(ws) == 4 + 2 * (10 + 2)
+    m = M.LocatorModel(K, seed=1)
+    m.load_weights(out + ".weights.npz")
+    for a, b in zip(m.get_weights(), ws):
+        assert np.array_equal(a, b)
+    params = json.load(open(out + "_params.json"))
+    params["out"] = str(tmp_path / "again")
+    with open(tmp_path / "p.json", "w") as fh:
+        json.dump(params, fh)
+    assert L.main(["--load_params", str(tmp_path / "p.json"), "--out", "ignored"]) == 0
+    assert open(str(tmp_path / "again") + "_predlocs.txt").read() == first
+
+
+def test_too_many_max_snps_fails_like_numpy(L, tmp_path):
+    vcf, sd, na = _write_inputs(tmp_path, 40, 120, 4)
+    with pytest.raises(ValueError):  # np.random.choice(range(K), max_SNPs, replace=False) with max_SNPs > K
+        L.main(["--vcf", vcf, "--sample_data", sd, "--out", str(tmp_path / "o"), "--seed", "1", "--max_epochs", "2",
+                "--max_SNPs", "100000", "--keras_verbose", "0"])

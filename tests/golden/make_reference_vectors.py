@@ -1,0 +1,229 @@
+#!/usr/bin/env python3
+"""Golden vectors produced by the REFERENCE'S OWN CODE, executed in the build container.
+
+`/root/reference/locator/locator.py` cannot be imported here (TensorFlow, scikit-allel, zarr are absent),
+but its ingest / index functions only need numpy and pandas.  This script parses the reference source with
+`ast`, compiles the function definitions it needs *from the source where it lies* (nothing is copied into
+this repository) and runs them:
+
+  sort_samples, normalize_locs, split_train_test      -- verbatim, on the reference's fixture data
+  filter_snps, replace_md                              -- verbatim control flow (filter order, min-MAC rule,
+        the (site, sample) order of the imputation draws, the max_SNPs draw) over `GA`, a minimal stand-in for
+        the four scikit-allel calls they make (count_alleles / is_biallelic / to_allele_counts / is_missing,
+        written from scikit-allel's documentation: plain counting)
+  the bootstrap and jacknife loops of main()           -- the statements that draw from numpy's stream
+        (reseed + site resample, locator.py:637-653; frequencies, site choice and binomial replacement,
+        :713-727), located in main()'s AST and executed with the arrays the real run would hold
+
+Outputs (committed): tests/golden/reference_vectors.json and reference_vectors.npz.  tests/test_oracle.py
+checks the oracle against them; tests/test_gpu_cli.py checks the CUDA path against the same files.
+
+Run in the build container only:   python tests/golden/make_reference_vectors.py
+
+One deviation, stated: the jacknife frequency loop does `sum(ac[i, :])` on uint8 rows, which promotes to a
+wide integer under the numpy the reference pins (< 1.25) and wraps at 255 under numpy >= 2 (this container).
+The allele-count matrix is therefore handed to that loop as int64 -- the pinned-numpy behaviour.
+"""
+import ast
+import contextlib
+import copy
+import hashlib
+import io
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import pandas as pd
+
+REF_SRC = "/root/reference/locator/locator.py"
+REF_DATA = "/root/reference/data"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---------------------------------------------------------------------------------------------
+# stand-in for the scikit-allel objects the reference's functions touch
+# ---------------------------------------------------------------------------------------------
+class Counts(np.ndarray):
+    """allel.AlleleCountsArray: [n_variants, n_alleles] counts of called alleles."""
+
+    def is_biallelic(self):
+        return np.asarray((np.asarray(self) > 0).sum(axis=1) == 2)
+
+
+class GA:
+    """allel.GenotypeArray over int8 [n_variants, n_samples, 2]; a negative allele is a missing allele."""
+
+    def __init__(self, a):
+        self.a = np.asarray(a, dtype=np.int8)
+
+    @property
+    def shape(self):
+        return self.a.shape
+
+    def __len__(self):
+        return self.a.shape[0]
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple) and isinstance(key[0], list):  # genotypes[ac_filter, :, :] with a list of bools
+            key = (np.asarray(key[0], dtype=bool),) + key[1:]
+        return GA(self.a[key])
+
+    def count_alleles(self):
+        m = max(int(self.a.max()) if self.a.size else 0, 0)
+        flat = self.a.reshape(self.a.shape[0], -1)
+        out = np.stack([(flat == k).sum(axis=1) for k in range(m + 1)], axis=1).astype(np.int32)
+        return out.view(Counts)
+
+    def to_allele_counts(self):
+        m = max(int(self.a.max()) if self.a.size else 0, 0)
+        return np.stack([(self.a == k).sum(axis=2) for k in range(m + 1)], axis=2).astype(np.uint8)
+
+    def is_missing(self):
+        return (self.a < 0).any(axis=2)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's code, compiled from its source file
+# ---------------------------------------------------------------------------------------------
+def reference_namespace(args):
+    tree = ast.parse(open(REF_SRC).read(), filename=REF_SRC)
+    wanted = {"sort_samples", "normalize_locs", "split_train_test", "filter_snps", "replace_md"}
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {f.name for f in fns} == wanted
+    ns = {"np": np, "pd": pd, "sys": sys, "copy": copy, "args": args, "tqdm": lambda it, *a, **k: it}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), REF_SRC, "exec"), ns)
+    main = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "main")
+    return ns, main
+
+
+def _uses_numpy_stream(node):
+    return "np.random" in ast.unparse(node)
+
+
+def loop_statements(main, marker):
+    """Statements of the `for boot in ...` loop of main() whose source contains `marker`, restricted to the
+    ones that draw from numpy's stream or prepare what those draws write to (pg = deepcopy(predgen))."""
+    loops = [n for n in ast.walk(main) if isinstance(n, ast.For) and isinstance(n.target, ast.Name)
+             and n.target.id == "boot" and marker in ast.unparse(n)]
+    assert len(loops) == 1, (marker, len(loops))
+    keep = [s for s in loops[0].body if _uses_numpy_stream(s) or ast.unparse(s).startswith("pg = ")]
+    return keep
+
+
+def run(stmts, ns):
+    exec(compile(ast.Module(body=stmts, type_ignores=[]), REF_SRC, "exec"), ns)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def quiet(fn, *a):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a)
+
+
+def fixture_genotypes():
+    """GT int8 [nvar, N, 2] + sample names of the reference's example VCF, through pandas (an independent parser)."""
+    df = pd.read_csv(os.path.join(REF_DATA, "test_genotypes.vcf.gz"), sep="\t", comment=None, skiprows=5, dtype=str,
+                     compression="gzip")
+    samples = [c for c in df.columns[9:] if not c.startswith("Unnamed")]
+    body = df[samples].to_numpy(dtype=str)
+    parts = np.char.partition(body, "|")
+    return np.stack([parts[:, :, 0].astype(np.int8), parts[:, :, 2].astype(np.int8)], axis=2), np.array(samples)
+
+
+def main():
+    args = types.SimpleNamespace(sample_data=os.path.join(REF_DATA, "test_sample_data.txt"), train_split=0.9, min_mac=2,
+                                 impute_missing=False, max_SNPs=None, nboots=2, jacknife_prop=0.05)
+    ns, main_fn = reference_namespace(args)
+    gt, samples = fixture_genotypes()
+    vec, arrays = {"generated_by": "tests/golden/make_reference_vectors.py (reference functions executed from "
+                                   "/root/reference/locator/locator.py)", "seed": 12345}, {}
+
+    # ---- config 1 flow: seed -> sort_samples -> normalize_locs -> filter_snps -> split_train_test ----------
+    np.random.seed(12345)
+    sample_data, locs = quiet(ns["sort_samples"], samples, gt)
+    meanlong, sdlong, meanlat, sdlat, nlocs = ns["normalize_locs"](locs)
+    ac = quiet(ns["filter_snps"], GA(gt))
+    train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = ns["split_train_test"](ac, nlocs)
+    vec["fixture"] = {
+        "locs_sha256": sha(locs.astype(np.float64)), "norm": [float(meanlong), float(sdlong), float(meanlat), float(sdlat)],
+        "normalized_locs_sha256": sha(nlocs.astype(np.float64)),
+        "ac_shape": list(ac.shape), "ac_dtype": str(ac.dtype), "ac_sha256": sha(ac),
+        "train": [int(v) for v in train], "test": [int(v) for v in test], "pred": [int(v) for v in pred],
+        "traingen_sha256": sha(traingen.astype(np.uint8)), "testgen_sha256": sha(testgen.astype(np.uint8)),
+        "predgen_sha256": sha(predgen.astype(np.uint8)),
+        "trainlocs_sha256": sha(trainlocs.astype(np.float64)), "testlocs_sha256": sha(testlocs.astype(np.float64)),
+    }
+    state_after_split = np.random.get_state()
+
+    # ---- bootstrap loop (two replicates), continuing the stream of the run above ------------------------------
+    boot_stmts = loop_statements(main_fn, "starting bootstrap")
+    src = [ast.unparse(s) for s in boot_stmts]
+    assert any("np.random.seed(np.random.choice(range(int(1000000.0)), 1))" in s for s in src) and \
+        any(s.startswith("site_order = np.random.choice") for s in src), src
+    boots = []
+    for boot in range(2):
+        env = dict(ns, traingen2=traingen, boot=boot)
+        before = np.random.get_state()
+        # the reseed value itself: replay the draw the first statement is about to make
+        reseed = int(np.random.choice(range(int(1e6)), 1)[0])
+        np.random.set_state(before)
+        run(boot_stmts, env)
+        boots.append({"reseed": reseed, "site_order_prefix": [int(v) for v in env["site_order"][:16]],
+                      "site_order_sha256": sha(env["site_order"].astype(np.int64))})
+    vec["bootstrap"] = boots
+
+    # ---- jacknife loop (two replicates) from the same point of the stream ---------------------------------------
+    np.random.set_state(state_after_split)
+    fl = [n for n in ast.walk(main_fn) if isinstance(n, ast.For) and "af.append(sum(ac[i, :])" in ast.unparse(n)]
+    assert len(fl) == 1
+    env = dict(ns, ac=ac.astype(np.int64), af=[])  # int64: see the module docstring
+    run([fl[0]], env)
+    af = np.array(env["af"])
+    jk_stmts = loop_statements(main_fn, "sites_to_remove")
+    src = [ast.unparse(s) for s in jk_stmts]
+    assert src[0].startswith("pg = copy.deepcopy(predgen)") and src[1].startswith("sites_to_remove = np.random.choice") \
+        and "np.random.binomial(2, af[i], pg.shape[0])" in src[2], src
+    jks = []
+    for boot in range(2):
+        env = dict(ns, predgen=predgen, af=af, boot=boot)
+        run(jk_stmts, env)
+        jks.append({"sites_prefix": [int(v) for v in env["sites_to_remove"][:16]], "nsites": int(len(env["sites_to_remove"])),
+                    "sites_sha256": sha(env["sites_to_remove"].astype(np.int64)), "pg_sha256": sha(env["pg"].astype(np.uint8))})
+    vec["jacknife"] = {"af_sha256": sha(af.astype(np.float64)), "replicates": jks,
+                       "next_uniform": float(np.random.random())}
+
+    # ---- imputation + SNP subsample on a small cube with missing calls ---------------------------------------
+    rng = np.random.default_rng(2024)
+    nvar, N = 300, 40
+    p = rng.uniform(0.05, 0.95, size=(nvar, 1, 1))
+    small = (rng.uniform(size=(nvar, N, 2)) < p).astype(np.int8)
+    small[rng.uniform(size=(nvar, N)) < 0.08] = -1          # whole calls missing
+    small[rng.uniform(size=(nvar, N, 2)) < 0.01] = -1       # half-missing calls
+    small[rng.uniform(size=(nvar, N, 2)) < 0.004] = 2       # a few third alleles
+    small[0] = 0
+    small[1] = -1
+    args.impute_missing, args.max_SNPs, args.min_mac = True, 120, 3
+    np.random.seed(777)
+    ac_small = quiet(ns["filter_snps"], GA(small))
+    vec["impute_subsample"] = {"seed": 777, "min_mac": 3, "max_SNPs": 120, "ac_shape": list(ac_small.shape),
+                               "next_uniform": float(np.random.random())}
+    arrays["small_gt"] = small
+    arrays["small_ac"] = np.asarray(ac_small, dtype=np.uint8)
+    args.impute_missing, args.max_SNPs, args.min_mac = False, None, 1
+    ac_mac1 = quiet(ns["filter_snps"], GA(small))
+    arrays["small_ac_min_mac_1"] = np.asarray(ac_mac1, dtype=np.uint8)
+
+    with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:
+        json.dump(vec, f, indent=1)
+    np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **arrays)
+    print("reference vectors written:", vec["fixture"]["ac_shape"], "fixture matrix;", len(vec["fixture"]["test"]),
+          "validation samples; bootstrap reseeds", [b["reseed"] for b in boots])
+
+
+if __name__ == "__main__":
+    main()

@@ -229,3 +229,53 @@ def test_staged_upload_of_zarr_rows_matches_host_array(L, tmp_path, monkeypatch)
     monkeypatch.setattr(G, "UPLOAD_BLOCK_BYTES", 1 << 29)
     assert np.array_equal(G.upload_rows(rows.rows(5, 3000)).cpu().numpy(), gt[5:3000])  # buffers grow
     assert G.upload_rows(rows.rows(9, 9)).shape == (0, 37, 2)
+
+
+def test_product_path_matches_vectors_produced_by_the_reference_code(L, tmp_path):
+    """The CUDA path (host mirror + ingest kernels through the C ABI) against tests/golden/reference_vectors.*,
+    which the reference's own functions produced (tests/golden/make_reference_vectors.py): fixture flow, bootstrap
+    and jacknife draws with the replaced prediction matrix, imputation + SNP subsample."""
+    from locator_b200 import replicates
+    from locator_b200.io import Genotypes
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    vec = _facts("reference_vectors.json")
+    arr = np.load(os.path.join(HERE, "golden", "reference_vectors.npz"))
+    fx = vec["fixture"]
+    L.set_args(L.build_parser().parse_args(["--vcf", VCF, "--sample_data", SAMPLES, "--out", str(tmp_path / "r"),
+                                            "--seed", str(vec["seed"]), "--jacknife", "--nboots", "2"]))
+    np.random.seed(vec["seed"])
+    genotypes, samples = L.load_genotypes()
+    sample_data, locs = L.sort_samples(samples, genotypes)
+    assert sha(np.asarray(locs, dtype=np.float64)) == fx["locs_sha256"]
+    meanlong, sdlong, meanlat, sdlat, nlocs = L.normalize_locs(locs)
+    assert [float(meanlong), float(sdlong), float(meanlat), float(sdlat)] == fx["norm"]
+    assert sha(nlocs.astype(np.float64)) == fx["normalized_locs_sha256"]
+    ac = L.filter_snps(genotypes)
+    assert list(ac.shape) == fx["ac_shape"] and sha(ac.to_numpy().astype(np.uint8)) == fx["ac_sha256"]
+    train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = L.split_train_test(ac, nlocs)
+    assert train.tolist() == fx["train"] and test.tolist() == fx["test"] and pred.tolist() == fx["pred"]
+    assert sha(traingen.to_numpy()) == fx["traingen_sha256"] and sha(testgen.to_numpy()) == fx["testgen_sha256"]
+    assert sha(predgen.to_numpy()) == fx["predgen_sha256"]
+    assert sha(trainlocs) == fx["trainlocs_sha256"] and sha(testlocs) == fx["testlocs_sha256"]
+    after_split = np.random.get_state()
+    for order, want in zip(replicates.draw_bootstrap_orders(traingen.K, 2), vec["bootstrap"]):
+        assert sha(order.astype(np.int64)) == want["site_order_sha256"]
+    np.random.set_state(after_split)
+    af = ac.site_sums() / (ac.shape[1] * 2)
+    assert sha(af.astype(np.float64)) == vec["jacknife"]["af_sha256"]
+    for (sites, vals), want in zip(L._jacknife_draws(af, predgen.K, predgen.n), vec["jacknife"]["replicates"]):
+        pg = predgen.clone()
+        pg.replace_cols(sites, vals)
+        assert sha(np.asarray(sites, dtype=np.int64)) == want["sites_sha256"] and sha(pg.to_numpy()) == want["pg_sha256"]
+    assert np.random.random() == vec["jacknife"]["next_uniform"]
+    imp = vec["impute_subsample"]
+    L.set_args(L.build_parser().parse_args(["--vcf", "x", "--out", str(tmp_path / "s"), "--impute_missing", "--max_SNPs",
+                                            str(imp["max_SNPs"]), "--min_mac", str(imp["min_mac"])]))
+    np.random.seed(imp["seed"])
+    got = L.filter_snps(Genotypes(arr["small_gt"]))
+    assert np.array_equal(got.to_numpy(), arr["small_ac"]) and np.random.random() == imp["next_uniform"]
+    L.set_args(L.build_parser().parse_args(["--vcf", "x", "--out", str(tmp_path / "s"), "--min_mac", "1"]))
+    assert np.array_equal(L.filter_snps(Genotypes(arr["small_gt"])).to_numpy(), arr["small_ac_min_mac_1"])

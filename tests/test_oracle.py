@@ -166,3 +166,56 @@ def test_oracle_adam_and_callbacks_semantics():
     assert saves[:3] == [True, True, False] and sum(saves) == 2
     assert lrs[3] == pytest.approx(1e-3) and lrs[4] == pytest.approx(5e-4) and lrs[6] == pytest.approx(2.5e-4)
     assert cb.stop and e == 13  # 12 epochs without improvement after epoch 1
+
+
+def _sha(a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_oracle_matches_vectors_produced_by_the_reference_code(fixture_gt, golden_dir):
+    """tests/golden/reference_vectors.* were produced by the REFERENCE'S OWN functions (sort_samples,
+    normalize_locs, filter_snps, replace_md, split_train_test and the bootstrap / jacknife loops of main(), compiled
+    from /root/reference/locator/locator.py by tests/golden/make_reference_vectors.py).  The oracle must reproduce
+    every one of them, bit for bit, from the same inputs and seeds."""
+    import json
+
+    vec = json.load(open(os.path.join(golden_dir, "reference_vectors.json")))
+    arr = np.load(os.path.join(golden_dir, "reference_vectors.npz"))
+    fx = vec["fixture"]
+    gt = fixture_gt["calldata/GT"]
+    ids, x, y = ingest_ref.read_sample_data(os.path.join(golden_dir, "data", "test_sample_data.txt"))
+    np.random.seed(vec["seed"])
+    locs = ingest_ref.sort_samples(ids, x, y, fixture_gt["samples"])
+    assert _sha(locs.astype(np.float64)) == fx["locs_sha256"]
+    meanlong, sdlong, meanlat, sdlat, nlocs = ingest_ref.normalize_locs(locs)
+    assert [float(meanlong), float(sdlong), float(meanlat), float(sdlat)] == fx["norm"]
+    assert _sha(nlocs.astype(np.float64)) == fx["normalized_locs_sha256"]
+    ac = ingest_ref.filter_snps(gt, min_mac=2)
+    assert list(ac.shape) == fx["ac_shape"] and str(ac.dtype) == fx["ac_dtype"] and _sha(ac) == fx["ac_sha256"]
+    train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = ingest_ref.split_train_test(ac, nlocs, 0.9)
+    assert train.tolist() == fx["train"] and test.tolist() == fx["test"] and pred.tolist() == fx["pred"]
+    assert _sha(traingen) == fx["traingen_sha256"] and _sha(testgen) == fx["testgen_sha256"]
+    assert _sha(predgen) == fx["predgen_sha256"]
+    assert _sha(trainlocs) == fx["trainlocs_sha256"] and _sha(testlocs) == fx["testlocs_sha256"]
+    after_split = np.random.get_state()
+    # bootstrap loop, continuing the run's stream
+    for want in vec["bootstrap"]:
+        order = ingest_ref.bootstrap_site_order(traingen.shape[1])
+        assert order[:16].tolist() == want["site_order_prefix"] and _sha(order.astype(np.int64)) == want["site_order_sha256"]
+    # jacknife loop from the same point of the stream
+    np.random.set_state(after_split)
+    af = ingest_ref.jacknife_af(ac)
+    assert _sha(af.astype(np.float64)) == vec["jacknife"]["af_sha256"]
+    for want in vec["jacknife"]["replicates"]:
+        pg, sites = ingest_ref.jacknife_replace(predgen, af, 0.05)
+        assert len(sites) == want["nsites"] and _sha(sites.astype(np.int64)) == want["sites_sha256"]
+        assert _sha(pg.astype(np.uint8)) == want["pg_sha256"]
+    assert np.random.random() == vec["jacknife"]["next_uniform"]
+    # imputation (scalar draws in (site, sample) order) + SNP subsample, and the min_mac == 1 rule
+    imp = vec["impute_subsample"]
+    np.random.seed(imp["seed"])
+    got = ingest_ref.filter_snps(arr["small_gt"], min_mac=imp["min_mac"], impute_missing=True, max_SNPs=imp["max_SNPs"])
+    assert np.array_equal(got, arr["small_ac"]) and np.random.random() == imp["next_uniform"]
+    assert np.array_equal(ingest_ref.filter_snps(arr["small_gt"], min_mac=1), arr["small_ac_min_mac_1"])

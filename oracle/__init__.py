@@ -10,9 +10,9 @@ reference`` legs may import it; the product package ``locator_b200`` never does.
 Parity status: the reference ships no tests and its arithmetic lives in
 TensorFlow/Keras + scikit-allel, none of which is installable here, so the Keras
 model math is "parity unpinned" against a live TF run.  What *is* pinned:
-  * ingest/filter/split/resampling indices against facts derived independently
-    from the reference's own fixture ``data/test_genotypes.vcf.gz`` /
-    ``data/test_sample_data.txt`` (tests/golden/, generated by
-    tests/golden/make_golden.py from /root/reference/data), and
-  * the model math against torch autograd (tests/test_oracle_model.py).
+  * ingest / filter / imputation / split / bootstrap / jacknife results against vectors produced by the
+    reference's OWN functions, compiled from /root/reference/locator/locator.py and run in the build
+    container by tests/golden/make_reference_vectors.py (tests/golden/reference_vectors.*), and
+    against facts derived independently from the reference's fixture data (tests/golden/make_golden.py);
+  * the model math against torch autograd (tests/test_oracle.py).
 """

@@ -89,10 +89,12 @@ class GA:
 # ---------------------------------------------------------------------------------------------
 def reference_namespace(args):
     tree = ast.parse(open(REF_SRC).read(), filename=REF_SRC)
-    wanted = {"sort_samples", "normalize_locs", "split_train_test", "filter_snps", "replace_md"}
+    wanted = {"sort_samples", "normalize_locs", "split_train_test", "filter_snps", "replace_md", "predict_locs"}
     fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
     assert {f.name for f in fns} == wanted
-    ns = {"np": np, "pd": pd, "sys": sys, "copy": copy, "args": args, "tqdm": lambda it, *a, **k: it}
+    from scipy import spatial
+
+    ns = {"np": np, "pd": pd, "sys": sys, "copy": copy, "args": args, "tqdm": lambda it, *a, **k: it, "spatial": spatial}
     exec(compile(ast.Module(body=fns, type_ignores=[]), REF_SRC, "exec"), ns)
     main = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "main")
     return ns, main
@@ -217,6 +219,111 @@ def main():
     args.impute_missing, args.max_SNPs, args.min_mac = False, None, 1
     ac_mac1 = quiet(ns["filter_snps"], GA(small))
     arrays["small_ac_min_mac_1"] = np.asarray(ac_mac1, dtype=np.uint8)
+
+    # ---- predict_locs: output files and printed summary, from a stand-in model with fixed predictions -----------
+    class StubModel:
+        def __init__(self, table):
+            self.table = table
+
+        def predict(self, x):
+            return self.table[id(x)]
+
+    class StubHistory:
+        history = {"loss": [1.25, 0.75, 0.6180339887498949], "val_loss": [1.5, 0.875, 0.7071067811865476],
+                   "learning_rate": [0.0010000000474974513, 0.0010000000474974513, 0.0005000000237487257]}
+
+    prng = np.random.default_rng(31)
+    n_pred, n_val = 7, 9
+    pg, tg = object(), object()
+    p_pred = prng.normal(size=(n_pred, 2)).astype(np.float32)
+    p_val = prng.normal(size=(n_val, 2)).astype(np.float32)
+    vlocs = prng.normal(size=(n_val, 2))
+    names = np.array([f"msp_{i:02d}" for i in range(30)])
+    pidx = np.array([1, 4, 5, 11, 17, 23, 29])
+    arrays.update(out_p_pred=p_pred, out_p_val=p_val, out_testlocs=vlocs, out_pred_idx=pidx)
+    outdir = os.path.join(HERE, "ref_out")
+    os.makedirs(outdir, exist_ok=True)
+    # meanlong, sdlong, meanlat, sdlat: numpy float64 scalars, as normalize_locs returns them (the de-normalisation
+    # float32 * float64 + float64 is then float64 under every numpy version)
+    norm = tuple(np.float64(v) for v in (25.07687431, 14.2187, 24.9312, 14.09656562))
+    cases = {"plain": dict(bootstrap=False, jacknife=False, windows=False, boot=0),
+             "boot": dict(bootstrap=True, jacknife=False, windows=False, boot=3),
+             "bootfull": dict(bootstrap=False, jacknife=True, windows=False, boot="FULL"),
+             "window": dict(bootstrap=False, jacknife=False, windows=True, boot=0)}
+    printed = {}
+    cwd = os.getcwd()
+    os.chdir(outdir)
+    try:
+        for name, c in cases.items():
+            args.out = name
+            args.bootstrap, args.jacknife, args.windows = c["bootstrap"], c["jacknife"], c["windows"]
+            args.window_start, args.window_size = "0", "250000"   # as they arrive from the command line
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                dists = ns["predict_locs"](StubModel({id(pg): p_pred, id(tg): p_val}), pg, norm[1], norm[0], norm[3], norm[2],
+                                           vlocs, pidx, names, tg, StubHistory(), c["boot"])
+            printed[name] = {"stdout": buf.getvalue(), "dists": [float(d) for d in dists]}
+    finally:
+        os.chdir(cwd)
+    vec["predict_locs"] = {"norm": [float(v) for v in norm], "history": StubHistory.history, "cases": cases, "printed": printed,
+                           "files": sorted(os.listdir(outdir))}
+
+    # ---- the --windows loop of main() (:531-583): bounds, per-window ingest and split, output naming ---------------
+    # Everything that is not ingest / index work is a recording stub; the loop body itself is the reference's.
+    vdf = pd.read_csv(os.path.join(REF_DATA, "test_genotypes.vcf.gz"), sep="\t", skiprows=5, usecols=[1], dtype=np.int64,
+                      compression="gzip")
+    positions = vdf["POS"].to_numpy()
+    wloops = [n for n in ast.walk(main_fn) if isinstance(n, ast.For) and "Processing window" in ast.unparse(n)]
+    assert len(wloops) == 1
+    records = []
+
+    def record_predict(model, predgen, sdlong, meanlong, sdlat, meanlat, testlocs, pred, samples_, testgen, history):
+        records.append({"i": int(wenv["i"]), "a": int(wenv["a"]), "b": int(wenv["b"]), "out": args.out,
+                        "K": int(wenv["ac"].shape[0]), "ac_sha256": sha(np.asarray(wenv["ac"], dtype=np.uint8)),
+                        "test": [int(v) for v in wenv["test"]], "train_sha256": sha(np.asarray(wenv["train"], dtype=np.int64)),
+                        "traingen_sha256": sha(np.asarray(wenv["traingen"], dtype=np.uint8)),
+                        "predgen_sha256": sha(np.asarray(predgen, dtype=np.uint8)),
+                        "norm": [float(meanlong), float(sdlong), float(meanlat), float(sdlat)]})
+        return []
+
+    args.impute_missing, args.max_SNPs, args.min_mac, args.train_split = False, None, 2, 0.9
+    args.out, args.plot_history, args.keep_weights, args.dropout_prop = "win", False, True, 0.25
+    import time as _time
+
+    wenv = dict(ns, allel=types.SimpleNamespace(GenotypeArray=GA), gt=gt, samples=samples, positions=positions,
+                start=0, stop=int(np.max(positions)), size=625000, time=_time,
+                load_network=lambda *a: None, load_callbacks=lambda *a: None, train_network=lambda *a: (None, None),
+                predict_locs=record_predict, plot_history=lambda *a: None,
+                subprocess=types.SimpleNamespace(run=lambda *a, **k: None))
+    np.random.seed(777)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ns["split_train_test"](ac, nlocs)   # main() splits the whole genome before the window loop (:514-516)
+        run(wloops, wenv)
+    vec["windows"] = {"seed": 777, "window_size": 625000, "stop": int(np.max(positions)), "records": records,
+                      "next_uniform": float(np.random.random())}
+
+    # ---- the command line: the reference's own argparse definition and its params.json dump (:12-184) ----------
+    import argparse
+
+    tree = ast.parse(open(REF_SRC).read(), filename=REF_SRC)
+    parser_stmts = [n for n in tree.body
+                    if (isinstance(n, ast.Assign) and ast.unparse(n).startswith("parser = argparse.ArgumentParser"))
+                    or (isinstance(n, ast.Expr) and ast.unparse(n).startswith("parser.add_argument("))]
+    pns = {"argparse": argparse}
+    run(parser_stmts, pns)
+    argvs = [
+        ["--vcf", "a.vcf.gz", "--sample_data", "s.txt", "--out", "o/run"],
+        ["--zarr", "g.zarr", "--sample_data", "s.txt", "--out", "w", "--windows", "--window_size", "250000",
+         "--window_start", "1000", "--window_stop", "9000000", "--seed", "12345"],
+        ["--matrix", "m.txt", "--sample_data", "s.txt", "--out", "b", "--bootstrap", "--nboots", "20", "--batch_size", "16",
+         "--max_epochs", "100", "--patience", "10", "--min_mac", "1", "--max_SNPs", "5000", "--impute_missing",
+         "--dropout_prop", "0.5", "--nlayers", "8", "--width", "128", "--train_split", "0.8", "--gpu_number", "1",
+         "--plot_history", "False", "--keep_weights", "--keras_verbose", "2"],
+        ["--vcf", "a.vcf", "--sample_data", "s.txt", "--out", "j", "--jacknife", "--jacknife_prop", "0.1", "--nboots", "7",
+         "--load_params", "old_params.json"],
+    ]
+    vec["cli"] = [{"argv": av, "params_json": json.dumps(pns["parser"].parse_args(av).__dict__, indent=2)} for av in argvs]
+    vec["cli_help_flags"] = sorted(a.option_strings[0] for a in pns["parser"]._actions if a.option_strings)
 
     with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:
         json.dump(vec, f, indent=1)

@@ -279,3 +279,36 @@ def test_product_path_matches_vectors_produced_by_the_reference_code(L, tmp_path
     assert np.array_equal(got.to_numpy(), arr["small_ac"]) and np.random.random() == imp["next_uniform"]
     L.set_args(L.build_parser().parse_args(["--vcf", "x", "--out", str(tmp_path / "s"), "--min_mac", "1"]))
     assert np.array_equal(L.filter_snps(Genotypes(arr["small_gt"])).to_numpy(), arr["small_ac_min_mac_1"])
+
+
+def test_windows_flow_matches_the_reference_loop(L, tmp_path):
+    """Per-window ingest on the CUDA path against what the reference's own --windows loop computed
+    (tests/golden/reference_vectors.json: bounds, filtered matrix, split, prediction matrix per window)."""
+    from locator_b200 import io, replicates
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    w = _facts("reference_vectors.json")["windows"]
+    v = io.read_vcf(VCF)
+    z = str(tmp_path / "fix.zarr")
+    io.write_zarr(z, v["calldata/GT"], v["samples"], v["variants/POS"], chunk_variants=1000)
+    L.set_args(L.build_parser().parse_args(["--zarr", z, "--sample_data", SAMPLES, "--out", str(tmp_path / "win"),
+                                            "--seed", str(w["seed"]), "--windows", "--window_size", str(w["window_size"])]))
+    np.random.seed(w["seed"])
+    genotypes, samples = L.load_genotypes()
+    sample_data, locs = L.sort_samples(samples, genotypes)
+    L.draw_split(L.normalize_locs(locs)[4])  # the genome-wide split of main(): only its draws matter
+    bounds = list(replicates.window_bounds(genotypes.positions, 0, w["stop"], w["window_size"]))
+    assert bounds == [(r["i"], r["a"], r["b"]) for r in w["records"]]
+    for (i, a, b), r in zip(bounds, w["records"]):
+        sub = genotypes[a:b]
+        sd, wl = L.sort_samples(samples, sub)
+        meanlong, sdlong, meanlat, sdlat, nlocs = L.normalize_locs(wl)
+        ac = L.filter_snps(sub)  # zarr rows -> pinned staging -> device -> filter -> pack
+        train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = L.split_train_test(ac, nlocs)
+        assert ac.shape[0] == r["K"] and sha(ac.to_numpy().astype(np.uint8)) == r["ac_sha256"]
+        assert test.tolist() == r["test"] and sha(train.astype(np.int64)) == r["train_sha256"]
+        assert sha(traingen.to_numpy()) == r["traingen_sha256"] and sha(predgen.to_numpy()) == r["predgen_sha256"]
+        assert [float(meanlong), float(sdlong), float(meanlat), float(sdlat)] == r["norm"]
+    assert np.random.random() == w["next_uniform"]

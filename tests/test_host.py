@@ -347,3 +347,56 @@ def test_legacy_binomial_reproduces_numpy_global_stream():
         legacy_binomial(2, [0.2, np.nan], 3)
     with pytest.raises(ValueError):
         legacy_binomial(2, [1.5], 3)
+
+
+def test_predict_locs_writes_the_reference_bytes(tmp_path, golden_dir, capsys, monkeypatch):
+    """Output boundary: tests/golden/ref_out/* and the printed summaries were produced by the REFERENCE'S
+    predict_locs (compiled from its source by tests/golden/make_reference_vectors.py) around a stand-in model
+    with fixed predictions.  The mirror writes the same bytes -- predlocs / history file names per driver,
+    comma vs tab separators, float formatting -- prints the same text and returns the same distances."""
+    import json
+    from locator_b200 import locator as L
+
+    vec = json.load(open(os.path.join(golden_dir, "reference_vectors.json")))["predict_locs"]
+    arr = np.load(os.path.join(golden_dir, "reference_vectors.npz"))
+    pg, tg = object(), object()
+
+    class StubModel:
+        def predict(self, x):
+            return arr["out_p_pred"] if x is pg else arr["out_p_val"]
+
+    class StubHistory:
+        history = vec["history"]
+
+    names = np.array([f"msp_{i:02d}" for i in range(30)])
+    meanlong, sdlong, meanlat, sdlat = (np.float64(v) for v in vec["norm"])
+    monkeypatch.chdir(tmp_path)
+    for name, c in vec["cases"].items():
+        flags = ["--out", name] + (["--bootstrap"] if c["bootstrap"] else []) + (["--jacknife"] if c["jacknife"] else []) \
+            + (["--windows", "--window_start", "0", "--window_size", "250000"] if c["windows"] else [])
+        L.set_args(L.build_parser().parse_args(flags))
+        capsys.readouterr()
+        dists = L.predict_locs(StubModel(), pg, sdlong, meanlong, sdlat, meanlat, arr["out_testlocs"], arr["out_pred_idx"],
+                               names, tg, StubHistory(), c["boot"])
+        assert capsys.readouterr().out == vec["printed"][name]["stdout"]
+        assert [float(d) for d in dists] == vec["printed"][name]["dists"]
+    written = sorted(os.listdir(tmp_path))
+    assert written == vec["files"]
+    for f in written:
+        assert open(tmp_path / f, "rb").read() == open(os.path.join(golden_dir, "ref_out", f), "rb").read(), f
+
+
+def test_command_line_matches_the_reference_parser(golden_dir):
+    """The reference's own argparse definition (compiled from its source by make_reference_vectors.py) parsed a set of
+    command lines and dumped args.__dict__ the way the reference writes *_params.json (locator.py:181-184): the
+    mirror produces the same text -- same flags, defaults, types, key order -- and knows every reference flag."""
+    import json
+    from locator_b200 import locator as L
+
+    vec = json.load(open(os.path.join(golden_dir, "reference_vectors.json")))
+    for case in vec["cli"]:
+        ns = L.build_parser().parse_args(case["argv"])
+        assert json.dumps(L._params_dict(ns), indent=2) == case["params_json"], case["argv"]
+    ours = {a.option_strings[0] for a in L.build_parser()._actions if a.option_strings}
+    assert set(vec["cli_help_flags"]) <= ours
+    assert ours - set(vec["cli_help_flags"]) == {"--gpus", "--replicates_per_gpu"}

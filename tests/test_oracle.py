@@ -219,3 +219,29 @@ def test_oracle_matches_vectors_produced_by_the_reference_code(fixture_gt, golde
     got = ingest_ref.filter_snps(arr["small_gt"], min_mac=imp["min_mac"], impute_missing=True, max_SNPs=imp["max_SNPs"])
     assert np.array_equal(got, arr["small_ac"]) and np.random.random() == imp["next_uniform"]
     assert np.array_equal(ingest_ref.filter_snps(arr["small_gt"], min_mac=1), arr["small_ac_min_mac_1"])
+
+
+def test_oracle_windows_flow_matches_the_reference_loop(fixture_gt, golden_dir):
+    """The --windows loop of the reference's main() (run by make_reference_vectors.py around recording stubs):
+    window bounds (SNP b itself excluded), per-window sort / normalise / filter / split continuing one numpy
+    stream after the genome-wide split, and the per-window output stem."""
+    import json
+
+    w = json.load(open(os.path.join(golden_dir, "reference_vectors.json")))["windows"]
+    gt, positions = fixture_gt["calldata/GT"], fixture_gt["variants/POS"]
+    ids, x, y = ingest_ref.read_sample_data(os.path.join(golden_dir, "data", "test_sample_data.txt"))
+    locs = ingest_ref.sort_samples(ids, x, y, fixture_gt["samples"])
+    np.random.seed(w["seed"])
+    ingest_ref.split_train_test(ingest_ref.filter_snps(gt, min_mac=2), ingest_ref.normalize_locs(locs)[4], 0.9)
+    bounds = list(ingest_ref.window_bounds(positions, 0, w["stop"], w["window_size"]))
+    assert [(i, a, b) for i, a, b in bounds] == [(r["i"], r["a"], r["b"]) for r in w["records"]]
+    for (i, a, b), r in zip(bounds, w["records"]):
+        meanlong, sdlong, meanlat, sdlat, nlocs = ingest_ref.normalize_locs(locs)
+        ac = ingest_ref.filter_snps(gt[a:b], min_mac=2)
+        train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = ingest_ref.split_train_test(ac, nlocs, 0.9)
+        assert ac.shape[0] == r["K"] and _sha(ac) == r["ac_sha256"] and test.tolist() == r["test"]
+        assert _sha(train.astype(np.int64)) == r["train_sha256"] and _sha(traingen) == r["traingen_sha256"]
+        assert _sha(predgen) == r["predgen_sha256"]
+        assert [float(meanlong), float(sdlong), float(meanlat), float(sdlat)] == r["norm"]
+        assert r["out"] == f"win_{i}-{i + w['window_size'] - 1}"
+    assert np.random.random() == w["next_uniform"]

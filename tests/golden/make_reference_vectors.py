@@ -89,7 +89,8 @@ class GA:
 # ---------------------------------------------------------------------------------------------
 def reference_namespace(args):
     tree = ast.parse(open(REF_SRC).read(), filename=REF_SRC)
-    wanted = {"sort_samples", "normalize_locs", "split_train_test", "filter_snps", "replace_md", "predict_locs"}
+    wanted = {"sort_samples", "normalize_locs", "split_train_test", "filter_snps", "replace_md", "predict_locs",
+              "load_genotypes"}
     fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
     assert {f.name for f in fns} == wanted
     from scipy import spatial
@@ -242,7 +243,10 @@ def main():
     pidx = np.array([1, 4, 5, 11, 17, 23, 29])
     arrays.update(out_p_pred=p_pred, out_p_val=p_val, out_testlocs=vlocs, out_pred_idx=pidx)
     outdir = os.path.join(HERE, "ref_out")
-    os.makedirs(outdir, exist_ok=True)
+    import shutil
+
+    shutil.rmtree(outdir, ignore_errors=True)  # only what predict_locs writes below lives here
+    os.makedirs(outdir)
     # meanlong, sdlong, meanlat, sdlat: numpy float64 scalars, as normalize_locs returns them (the de-normalisation
     # float32 * float64 + float64 is then float64 under every numpy version)
     norm = tuple(np.float64(v) for v in (25.07687431, 14.2187, 24.9312, 14.09656562))
@@ -301,6 +305,28 @@ def main():
         run(wloops, wenv)
     vec["windows"] = {"seed": 777, "window_size": 625000, "stop": int(np.max(positions)), "records": records,
                       "next_uniform": float(np.random.random())}
+
+    # ---- load_genotypes, --matrix branch (:200-227): count table -> haplotype pairs -> genotype cube ---------------
+    mrng = np.random.default_rng(12)
+    counts = mrng.integers(0, 3, size=(9, 25))
+    mpath = os.path.join(HERE, "matrix_input.txt")
+    with open(mpath, "w") as fh:
+        fh.write("sampleID\t" + "\t".join(f"site{j}" for j in range(counts.shape[1])) + "\n")
+        for i in range(counts.shape[0]):
+            fh.write(f"ind_{i}\t" + "\t".join(str(int(c)) for c in counts[i]) + "\n")
+
+    class Haps:  # allel.HaplotypeArray [n_variants, n_haplotypes]: consecutive haplotype pairs form a sample
+        def __init__(self, h):
+            self.h = np.asarray(h)
+
+        def to_genotypes(self, ploidy):
+            return GA(self.h.reshape(self.h.shape[0], self.h.shape[1] // ploidy, ploidy))
+
+    args.zarr, args.vcf, args.matrix = None, None, mpath
+    ns["allel"] = types.SimpleNamespace(HaplotypeArray=Haps, GenotypeArray=GA)  # the functions' globals are `ns`
+    m_genotypes, m_samples = ns["load_genotypes"]()
+    arrays["matrix_gt"] = m_genotypes.a
+    vec["matrix"] = {"samples": [str(v) for v in m_samples], "shape": list(m_genotypes.a.shape)}
 
     # ---- the command line: the reference's own argparse definition and its params.json dump (:12-184) ----------
     import argparse

@@ -400,3 +400,16 @@ def test_command_line_matches_the_reference_parser(golden_dir):
     ours = {a.option_strings[0] for a in L.build_parser()._actions if a.option_strings}
     assert set(vec["cli_help_flags"]) <= ours
     assert ours - set(vec["cli_help_flags"]) == {"--gpus", "--replicates_per_gpu"}
+
+
+def test_matrix_reader_matches_the_reference_branch(golden_dir):
+    """--matrix: the reference's load_genotypes branch (count table -> haplotype pairs -> genotype cube,
+    locator.py:200-227, run by make_reference_vectors.py) against io.read_matrix on the same file."""
+    import json
+    from locator_b200 import io
+
+    vec = json.load(open(os.path.join(golden_dir, "reference_vectors.json")))["matrix"]
+    arr = np.load(os.path.join(golden_dir, "reference_vectors.npz"))
+    g = io.read_matrix(os.path.join(golden_dir, "matrix_input.txt"))
+    assert list(g.gt.shape) == vec["shape"] and np.array_equal(g.gt, arr["matrix_gt"])
+    assert [str(s) for s in g.samples] == vec["samples"]

@@ -7,6 +7,10 @@ density is evaluated at the sample's own predictions); with ``--error`` the dist
 to the known location (hypotenuse, or great-circle km with ``--longlat``) are printed.  Output:
 ``{out}_centroids.txt`` (tab-separated: sampleID x y kd_x kd_y gc_x gc_y).  Plotting is not part of this
 build (no matplotlib in the image).  CPU-only host tool: the work is a few thousand points.
+The four numeric functions are checked against the reference's own (run with scikit-learn's KernelDensity on
+positional arrays, tests/golden/make_reference_vectors.py).  One deliberate difference: the reference's script
+hands pandas Series to kdepred, whose ``xcoords[max_index]`` is then a *label* lookup that raises for most
+samples and silently falls back to the mean; here the density peak is always the peak.
 
 usage: python -m locator_b200.summarize --infile DIR --sample_data FILE --out STEM [--error] [--longlat]
 """

@@ -328,6 +328,35 @@ def main():
     arrays["matrix_gt"] = m_genotypes.a
     vec["matrix"] = {"samples": [str(v) for v in m_samples], "shape": list(m_genotypes.a.shape)}
 
+    # ---- post-hoc summary (locator_py/plot_locator.py:26-60): kernel-density peak, centroid, distances ----------
+    from math import atan2, cos, radians, sin, sqrt
+    from sklearn.neighbors import KernelDensity
+
+    ptree = ast.parse(open("/root/reference/locator_py/plot_locator.py").read())
+    pf = [n for n in ptree.body if isinstance(n, ast.FunctionDef) and n.name in ("kdepred", "centroid", "distance", "distance_km")]
+    assert len(pf) == 4
+    sns = {"np": np, "KernelDensity": KernelDensity, "sin": sin, "cos": cos, "sqrt": sqrt, "atan2": atan2, "radians": radians}
+    exec(compile(ast.Module(body=pf, type_ignores=[]), "plot_locator.py", "exec"), sns)
+    srng = np.random.default_rng(44)
+    summ = []
+    for case in range(6):
+        n = int(srng.integers(5, 60))
+        cx, cy = srng.uniform(-50, 50, 2)
+        xs = cx + 0.3 * srng.normal(size=n)
+        ys = cy + 0.3 * srng.normal(size=n)
+        if case % 2:  # a second, smaller cluster far away pulls the centroid, not the density peak
+            k = n // 4
+            xs[:k] += 7.0
+            ys[:k] -= 5.0
+        tx, ty = cx + 0.1, cy - 0.2
+        kd = sns["kdepred"](xs, ys)        # positional arrays: the behaviour the function documents
+        gc = sns["centroid"](xs, ys)
+        summ.append({"x": xs.tolist(), "y": ys.tolist(), "truth": [float(tx), float(ty)],
+                     "kd": [float(kd[0]), float(kd[1])], "gc": [float(gc[0]), float(gc[1])],
+                     "kd_dist": float(sns["distance"](kd[0], kd[1], tx, ty)), "gc_dist": float(sns["distance"](gc[0], gc[1], tx, ty)),
+                     "kd_dist_km": float(sns["distance_km"](kd[0], kd[1], tx, ty))})
+    vec["summarize"] = summ
+
     # ---- the command line: the reference's own argparse definition and its params.json dump (:12-184) ----------
     import argparse
 

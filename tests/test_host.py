@@ -413,3 +413,22 @@ def test_matrix_reader_matches_the_reference_branch(golden_dir):
     g = io.read_matrix(os.path.join(golden_dir, "matrix_input.txt"))
     assert list(g.gt.shape) == vec["shape"] and np.array_equal(g.gt, arr["matrix_gt"])
     assert [str(s) for s in g.samples] == vec["samples"]
+
+
+def test_summariser_matches_the_reference_functions(golden_dir):
+    """locator_py/plot_locator.py's kdepred / centroid / distance / distance_km (run with scikit-learn's KernelDensity
+    by make_reference_vectors.py on positional arrays) against locator_b200.summarize: same density peak (a member of
+    the prediction set), same centroid and distances."""
+    import json
+    from locator_b200 import summarize as S
+
+    for c in json.load(open(os.path.join(golden_dir, "reference_vectors.json")))["summarize"]:
+        xs, ys = np.array(c["x"]), np.array(c["y"])
+        tx, ty = c["truth"]
+        kx, ky = S.kde_peak(xs, ys)
+        assert [kx, ky] == c["kd"]
+        gx, gy = S.centroid(xs, ys)
+        assert gx == pytest.approx(c["gc"][0], rel=1e-13, abs=1e-13) and gy == pytest.approx(c["gc"][1], rel=1e-13, abs=1e-13)
+        assert float(np.hypot(kx - tx, ky - ty)) == pytest.approx(c["kd_dist"], rel=1e-13)
+        assert float(np.hypot(gx - tx, gy - ty)) == pytest.approx(c["gc_dist"], rel=1e-12)
+        assert float(S.distance_km(kx, ky, tx, ty)) == pytest.approx(c["kd_dist_km"], rel=1e-12)

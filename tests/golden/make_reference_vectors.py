@@ -90,7 +90,7 @@ class GA:
 def reference_namespace(args):
     tree = ast.parse(open(REF_SRC).read(), filename=REF_SRC)
     wanted = {"sort_samples", "normalize_locs", "split_train_test", "filter_snps", "replace_md", "predict_locs",
-              "load_genotypes"}
+              "load_genotypes", "load_network", "load_callbacks", "train_network"}
     fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
     assert {f.name for f in fns} == wanted
     from scipy import spatial
@@ -356,6 +356,86 @@ def main():
                      "kd_dist": float(sns["distance"](kd[0], kd[1], tx, ty)), "gc_dist": float(sns["distance"](gc[0], gc[1], tx, ty)),
                      "kd_dist_km": float(sns["distance_km"](kd[0], kd[1], tx, ty))})
     vec["summarize"] = summ
+
+    # ---- load_network / load_callbacks / train_network (:311-394) around RECORDING stand-ins for Keras ---------
+    # No arithmetic is pinned here (Keras is absent): what is pinned is what the reference ASKS Keras for -- layer
+    # sequence and arguments per nlayers / width / dropout, optimizer, the loss expression (evaluated with numpy
+    # as the backend), callback settings and file names per driver, fit() arguments, the weights reload.
+    class Rec:
+        def __init__(self, kind, *a, **k):
+            self.kind, self.a, self.k = kind, a, k
+
+        def desc(self):
+            d = {"kind": self.kind}
+            if self.a:
+                d["args"] = [x if isinstance(x, (int, float, str, bool, type(None))) else list(x) for x in self.a]
+            d.update({k: (list(v) if isinstance(v, tuple) else v) for k, v in self.k.items()})
+            return d
+
+    class Seq:
+        def __init__(self):
+            self.layers, self.compiled, self.fit_kwargs, self.loaded = [], None, None, []
+
+        def add(self, layer):
+            self.layers.append(layer.desc())
+
+        def compile(self, optimizer, loss):
+            self.compiled, self.loss = {"optimizer": optimizer}, loss
+
+        def fit(self, x, y, **kw):
+            self.fit_kwargs = {k: (v if isinstance(v, (int, float, str, bool, type(None))) else type(v).__name__)
+                               for k, v in kw.items()}
+            self.fit_xy = (x, y, kw.get("validation_data"), kw.get("callbacks"))
+            return "HISTORY"
+
+        def load_weights(self, path):
+            self.loaded.append(path)
+
+    def factory(kind):
+        return lambda *a, **k: Rec(kind, *a, **k)
+
+    keras = types.SimpleNamespace(
+        Sequential=Seq,
+        layers=types.SimpleNamespace(BatchNormalization=factory("BatchNormalization"), Dense=factory("Dense"),
+                                     Dropout=factory("Dropout")),
+        callbacks=types.SimpleNamespace(ModelCheckpoint=factory("ModelCheckpoint"), EarlyStopping=factory("EarlyStopping"),
+                                        ReduceLROnPlateau=factory("ReduceLROnPlateau")))
+    backend = types.ModuleType("tensorflow.keras.backend")
+    backend.sqrt, backend.sum, backend.square = np.sqrt, np.sum, np.square
+    fake_tf, fake_keras = types.ModuleType("tensorflow"), types.ModuleType("tensorflow.keras")
+    fake_tf.keras, fake_keras.backend = fake_keras, backend
+    sys.modules.update({"tensorflow": fake_tf, "tensorflow.keras": fake_keras, "tensorflow.keras.backend": backend})
+    shell = []
+    ns.update(tf=types.SimpleNamespace(keras=keras), time=_time,
+              subprocess=types.SimpleNamespace(run=lambda cmd, **k: shell.append(cmd)))
+    lrng = np.random.default_rng(8)
+    yt, yp = lrng.normal(size=(6, 2)).astype(np.float32), lrng.normal(size=(6, 2)).astype(np.float32)
+    nets = []
+    for nlayers, width, drop in [(10, 256, 0.25), (2, 256, 0.25), (3, 64, 0.0), (7, 128, 0.5), (8, 32, 0.1)]:
+        args.nlayers, args.width, args.dropout_prop = nlayers, width, drop
+        m = ns["load_network"](np.zeros((4, 321), np.uint8), 0.99)   # the argument is ignored: args.dropout_prop is used
+        nets.append({"nlayers": nlayers, "width": width, "dropout_prop": drop, "layers": m.layers,
+                     "compile": m.compiled, "loss_of_fixed_arrays": [float(v) for v in m.loss(yt, yp)]})
+    arrays.update(loss_y_true=yt, loss_y_pred=yp)
+    cbs, trains = [], []
+    for bootstrap, jacknife, boot, keep in [(False, False, 0, False), (True, False, 5, False), (False, True, "FULL", True)]:
+        args.bootstrap, args.jacknife, args.out, args.keep_weights = bootstrap, jacknife, "o/run", keep
+        args.patience, args.keras_verbose, args.max_epochs, args.batch_size = 100, 1, 5000, 32
+        got = ns["load_callbacks"](boot)
+        cbs.append({"bootstrap": bootstrap, "jacknife": jacknife, "boot": boot, "callbacks": [c.desc() for c in got]})
+        m = Seq()
+        del shell[:]
+        with contextlib.redirect_stdout(io.StringIO()):
+            hist, back = ns["train_network"](m, "TRAINGEN", "TRAINLOCS", "TESTLOCS_PLACEHOLDER", "TL", got, boot)
+        trains.append({"bootstrap": bootstrap, "jacknife": jacknife, "boot": boot, "keep_weights": keep,
+                       "fit_kwargs": m.fit_kwargs, "loaded": list(m.loaded), "shell": list(shell),
+                       "returns_history_and_model": bool(hist == "HISTORY" and back is m)})
+    args.patience = 37
+    cbs.append({"bootstrap": False, "jacknife": True, "boot": "FULL", "patience": 37,
+                "callbacks": [c.desc() for c in ns["load_callbacks"]("FULL")]})
+    vec["keras_requests"] = {"networks": nets, "callbacks": cbs, "train_network": trains}
+    for k in ("tensorflow", "tensorflow.keras", "tensorflow.keras.backend"):
+        sys.modules.pop(k, None)
 
     # ---- the command line: the reference's own argparse definition and its params.json dump (:12-184) ----------
     import argparse

@@ -432,3 +432,55 @@ def test_summariser_matches_the_reference_functions(golden_dir):
         assert float(np.hypot(kx - tx, ky - ty)) == pytest.approx(c["kd_dist"], rel=1e-13)
         assert float(np.hypot(gx - tx, gy - ty)) == pytest.approx(c["gc_dist"], rel=1e-12)
         assert float(S.distance_km(kx, ky, tx, ty)) == pytest.approx(c["kd_dist_km"], rel=1e-12)
+
+
+def test_mirror_asks_its_model_for_what_the_reference_asks_keras_for(golden_dir, capsys, tmp_path):
+    """load_callbacks / train_network of the reference, run around recording stand-ins (make_reference_vectors.py):
+    callback settings and checkpoint file names per driver, the fit() arguments, the reload of the best weights.
+    The mirror passes the same settings to its model (the checkpoint lives in device memory; the weights file,
+    when kept, is .npz instead of .h5)."""
+    import json
+    from locator_b200 import locator as L
+
+    req = json.load(open(os.path.join(golden_dir, "reference_vectors.json")))["keras_requests"]
+    for cb in req["callbacks"]:
+        flags = ["--out", "o/run", "--patience", str(cb.get("patience", 100))] + (["--bootstrap"] if cb["bootstrap"] else []) \
+            + (["--jacknife"] if cb["jacknife"] else [])
+        L.set_args(L.build_parser().parse_args(flags))
+        ck, es, rl = L.load_callbacks(cb["boot"])
+        rck, res, rrl = cb["callbacks"]
+        assert ck.filepath == rck["filepath"].replace(".weights.h5", ".weights.npz")
+        assert (ck.monitor, ck.save_best_only, ck.save_weights_only) == (rck["monitor"], rck["save_best_only"], rck["save_weights_only"])
+        assert (es.monitor, es.min_delta, es.patience) == (res["monitor"], res["min_delta"], res["patience"])
+        assert (rl.monitor, rl.factor, rl.patience, rl.min_delta, rl.cooldown, rl.min_lr) == \
+            (rrl["monitor"], rrl["factor"], rrl["patience"], rrl["min_delta"], rrl["cooldown"], rrl["min_lr"])
+
+    class StubModel:
+        def __init__(self):
+            self.kw, self.restored, self.saved = None, 0, []
+
+        def fit(self, x, y, **kw):
+            self.kw = kw
+            return "HISTORY"
+
+        def restore_best(self):
+            self.restored += 1
+
+        def save_weights(self, path):
+            self.saved.append(path)
+
+    for tr in req["train_network"]:
+        flags = ["--out", str(tmp_path / "run")] + (["--bootstrap"] if tr["bootstrap"] else []) \
+            + (["--jacknife"] if tr["jacknife"] else []) + (["--keep_weights"] if tr["keep_weights"] else [])
+        L.set_args(L.build_parser().parse_args(flags))
+        m = StubModel()
+        cbs = L.load_callbacks(tr["boot"])
+        hist, back = L.train_network(m, "TRAINGEN", "TESTGEN", "TRAINLOCS", "TESTLOCS", cbs, tr["boot"])
+        assert (hist == "HISTORY" and back is m) == tr["returns_history_and_model"]
+        want = tr["fit_kwargs"]
+        assert m.kw["epochs"] == want["epochs"] and m.kw["batch_size"] == want["batch_size"] and m.kw["shuffle"] is want["shuffle"]
+        assert m.kw["validation_data"] == ("TESTGEN", "TESTLOCS") and m.kw["callbacks"] == cbs
+        assert m.restored == len(tr["loaded"]) == 1          # model.load_weights(best checkpoint)
+        kept = [cbs[0].filepath] if tr["keep_weights"] else []   # the reference deletes the file unless --keep_weights
+        assert m.saved == kept and bool(tr["shell"]) == (not tr["keep_weights"])
+        assert "run time " in capsys.readouterr().out

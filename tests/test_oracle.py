@@ -245,3 +245,43 @@ def test_oracle_windows_flow_matches_the_reference_loop(fixture_gt, golden_dir):
         assert [float(meanlong), float(sdlong), float(meanlat), float(sdlat)] == r["norm"]
         assert r["out"] == f"win_{i}-{i + w['window_size'] - 1}"
     assert np.random.random() == w["next_uniform"]
+
+
+def test_oracle_builds_what_the_reference_asks_keras_for(golden_dir):
+    """load_network of the reference, run around recording stand-ins for Keras (make_reference_vectors.py): the
+    layer sequence per nlayers / width / dropout, the optimizer name and the loss expression (numpy as the
+    backend).  The oracle's layer plan, weight shapes and per-sample loss must be those."""
+    import json
+
+    req = json.load(open(os.path.join(golden_dir, "reference_vectors.json")))["keras_requests"]
+    arr = np.load(os.path.join(golden_dir, "reference_vectors.npz"))
+    for net in req["networks"]:
+        kinds = [l["kind"] for l in net["layers"]]
+        L, H, K = net["nlayers"], net["width"], net["layers"][0]["input_shape"][0]
+        n_before, n_after = model_ref.layer_plan(L)
+        assert kinds == ["BatchNormalization"] + ["Dense"] * n_before + ["Dropout"] + ["Dense"] * n_after + ["Dense", "Dense"]
+        dense = [l for l in net["layers"] if l["kind"] == "Dense"]
+        assert [d["args"][0] for d in dense] == [H] * L + [2, 2]
+        assert [d.get("activation") for d in dense] == ["elu"] * L + [None, None]
+        assert [l for l in net["layers"] if l["kind"] == "Dropout"][0]["args"] == [net["dropout_prop"]]
+        assert net["compile"] == {"optimizer": "Adam"}
+        ref = model_ref.RefLocator(K, H, L, dropout=net["dropout_prop"])
+        shapes = [tuple(w.shape) for w in ref.get_weights()]
+        dims = [K] + [H] * L + [2, 2]
+        want = [(K,)] * 4
+        for i in range(L + 2):
+            want += [(dims[i], dims[i + 1]), (dims[i + 1],)]
+        assert shapes == want and (ref.n_before, ref.n_after) == (n_before, n_after)
+        import torch
+
+        got = model_ref.RefLocator.loss_per_sample(torch.as_tensor(arr["loss_y_pred"]), torch.as_tensor(arr["loss_y_true"]))
+        assert [float(v) for v in got] == net["loss_of_fixed_arrays"]
+    # callback settings the oracle's state machine is built from (patience, patience / 6, factor 0.5 ...)
+    for cb in req["callbacks"]:
+        ck, es, rl = cb["callbacks"]
+        P = es["patience"]
+        cbs = model_ref.CallbackState(P)
+        assert cbs.P == P and cbs.rlr_patience == rl["patience"] == int(P / 6)
+        assert rl["factor"] == 0.5 and rl["min_delta"] == 0 and rl["cooldown"] == 0 and rl["min_lr"] == 0
+        assert es["min_delta"] == 0 and es["monitor"] == rl["monitor"] == ck["monitor"] == "val_loss"
+        assert ck["save_best_only"] is True and ck["save_weights_only"] is True

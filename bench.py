@@ -216,7 +216,6 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from locator_b200 import model, _cabi
-    from locator_b200.genotypes import PackedGenotypes
     lib = _cabi.lib
 
     n_total, K = WORKLOADS[workload]

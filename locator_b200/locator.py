@@ -28,7 +28,6 @@ Differences that are deliberate and documented in DESIGN.md:
 from __future__ import annotations
 
 import argparse
-import copy
 import json
 import os
 import sys

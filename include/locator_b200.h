@@ -134,6 +134,10 @@ int loc_vcf_parse_gt(const char* h_buf, int64_t len, int64_t n_samples, int64_t 
 int loc_np_legacy_binomial(uint32_t* mt_key, int32_t* mt_pos, int64_t n, const double* h_p, int64_t n_p, int64_t reps,
                            uint8_t* h_out);
 
+/* RandomState.permutation(n) from the same state (numpy's legacy Fisher-Yates over arange(n)); the first
+ * `size` entries are np.random.choice(n, size, replace=False) (split :299, max_SNPs :279, jacknife :722). */
+int loc_np_legacy_permutation(uint32_t* mt_key, int32_t* mt_pos, int64_t n, int64_t* h_out);
+
 /* ---------------- model (K3-K7) ---------------- */
 
 /* BN(K) -> Dense(width, elu) x nlayers (Dropout after the floor(nlayers/2)-th)

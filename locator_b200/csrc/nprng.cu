@@ -137,9 +137,53 @@ inline int64_t tab_draw2(Mt& s, const InvTab& t) {
   }
 }
 
+// numpy's bounded integer for the legacy shuffle: rejection below the smallest all-ones mask >= max
+// (32-bit outputs while max fits, two outputs -- high word first -- beyond)
+inline uint64_t mt_interval(Mt& s, uint64_t max) {
+  if (max == 0) return 0;
+  uint64_t mask = max;
+  mask |= mask >> 1;
+  mask |= mask >> 2;
+  mask |= mask >> 4;
+  mask |= mask >> 8;
+  mask |= mask >> 16;
+  mask |= mask >> 32;
+  uint64_t v;
+  if (max <= 0xffffffffull) {
+    while ((v = (mt_next(s) & mask)) > max) {
+    }
+  } else {
+    for (;;) {
+      const uint64_t hi = mt_next(s), lo = mt_next(s);
+      v = ((hi << 32) | lo) & mask;
+      if (v <= max) break;
+    }
+  }
+  return v;
+}
+
 }  // namespace
 
 extern "C" {
+
+// RandomState.permutation(n) (and with it choice(n, size, replace=False) = permutation(n)[:size],
+// locator.py:299, :722): arange(n) shuffled by numpy's legacy Fisher-Yates -- for i = n-1 .. 1 swap element i
+// with element random_interval(i) -- from the same MT19937 state, advanced in place.
+int loc_np_legacy_permutation(uint32_t* mt_key, int32_t* mt_pos, int64_t n, int64_t* out) {
+  LOC_CHECK(mt_key != nullptr && mt_pos != nullptr && n >= 0 && (n == 0 || out != nullptr),
+            "loc_np_legacy_permutation: bad arguments");
+  LOC_CHECK(*mt_pos >= 0 && *mt_pos <= kN, "loc_np_legacy_permutation: bad stream position");
+  Mt s{mt_key, (int)*mt_pos};
+  for (int64_t i = 0; i < n; ++i) out[i] = i;
+  for (int64_t i = n - 1; i >= 1; --i) {
+    const int64_t j = (int64_t)mt_interval(s, (uint64_t)i);
+    const int64_t t = out[i];
+    out[i] = out[j];
+    out[j] = t;
+  }
+  *mt_pos = s.pos;
+  return 0;
+}
 
 // out[i * reps + r] = the r-th of `reps` consecutive RandomState.binomial(n, p[i]) draws, sites in order.
 // mt_key[624] / *mt_pos: the MT19937 state of np.random.get_state(), advanced in place.

@@ -431,7 +431,7 @@ def _jacknife_draws(af, K, n_pred):
     import queue
     import threading
 
-    from .nprandom import legacy_binomial
+    from .nprandom import legacy_binomial, legacy_choice_without_replacement
 
     nsites = int(K * args.jacknife_prop)
     q = queue.Queue(maxsize=2)
@@ -439,7 +439,7 @@ def _jacknife_draws(af, K, n_pred):
     def produce():
         try:
             for _ in range(args.nboots):
-                sites = np.random.choice(K, nsites, replace=False)
+                sites = legacy_choice_without_replacement(K, nsites)
                 vals = legacy_binomial(2, af[sites], n_pred)
                 q.put((sites, vals))
             q.put(None)

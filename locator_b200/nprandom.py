@@ -38,3 +38,26 @@ def legacy_binomial(n, p, reps=1):
             raise ValueError("p < 0, p > 1 or p is NaN")  # numpy's message for the same input
     vals = np.random.binomial(int(n), np.repeat(p, reps)).reshape(p.size, reps)  # same draws, numpy's pace
     return vals.astype(np.uint8)
+
+
+def legacy_permutation(n):
+    """int64 [n]: what ``np.random.permutation(n)`` returns, drawn from (and advancing) numpy's global stream."""
+    n = int(n)
+    st = np.random.get_state()
+    if st[0] != "MT19937" or n < 0:
+        return np.random.permutation(n)
+    out = np.empty(n, dtype=np.int64)
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = C.c_int32(int(st[2]))
+    if lib.loc_np_legacy_permutation(key.ctypes.data, C.byref(pos), n, out.ctypes.data) != 0:
+        return np.random.permutation(n)
+    np.random.set_state(("MT19937", key, int(pos.value), st[3], st[4]))
+    return out
+
+
+def legacy_choice_without_replacement(n, size):
+    """``np.random.choice(n, size, replace=False)`` for an integer population: the head of a permutation."""
+    n, size = int(n), int(size)
+    if size > n or size < 0:
+        return np.random.choice(n, size, replace=False)  # numpy's own error for the same request
+    return legacy_permutation(n)[:size]

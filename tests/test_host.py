@@ -484,3 +484,24 @@ def test_mirror_asks_its_model_for_what_the_reference_asks_keras_for(golden_dir,
         kept = [cbs[0].filepath] if tr["keep_weights"] else []   # the reference deletes the file unless --keep_weights
         assert m.saved == kept and bool(tr["shell"]) == (not tr["keep_weights"])
         assert "run time " in capsys.readouterr().out
+
+
+def test_legacy_permutation_reproduces_numpy_global_stream():
+    """nprandom.legacy_permutation / legacy_choice_without_replacement (numpy's legacy Fisher-Yates restated in the
+    library) against np.random.permutation / choice(replace=False), values and stream position."""
+    from locator_b200.nprandom import legacy_choice_without_replacement, legacy_permutation
+
+    for n in (0, 1, 2, 3, 7, 100, 624, 625, 5830, 70001):
+        np.random.seed(n + 1)
+        np.random.normal()
+        want, after_want = np.random.permutation(n), np.random.random()
+        np.random.seed(n + 1)
+        np.random.normal()
+        got, after_got = legacy_permutation(n), np.random.random()
+        assert got.dtype == np.int64 and np.array_equal(got, want) and after_got == after_want
+    np.random.seed(12345)
+    want, x = np.random.choice(5830, 291, replace=False), np.random.random()
+    np.random.seed(12345)
+    assert np.array_equal(legacy_choice_without_replacement(5830, 291), want) and np.random.random() == x
+    with pytest.raises(ValueError):
+        legacy_choice_without_replacement(10, 11)

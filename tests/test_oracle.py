@@ -133,7 +133,7 @@ def test_oracle_gradients_match_autograd(K, H, L, p, B):
     y2 = y1 @ t[6 + 2 * L] + t[7 + 2 * L]
     l = torch.sqrt(((y2 - torch.tensor(y)) ** 2).sum(-1)).mean()
     l.backward()
-    assert abs(float(l) - loss) < 1e-5 * max(1.0, abs(loss))
+    assert abs(l.item() - loss) < 1e-5 * max(1.0, abs(loss))
     auto = [t[0].grad, t[1].grad] + [t[i].grad for i in range(4, len(t))]
     for g, ga in zip(grads, auto):
         np.testing.assert_allclose(g.numpy(), ga.numpy(), rtol=2e-4, atol=2e-6)
@@ -285,3 +285,56 @@ def test_oracle_builds_what_the_reference_asks_keras_for(golden_dir):
         assert rl["factor"] == 0.5 and rl["min_delta"] == 0 and rl["cooldown"] == 0 and rl["min_lr"] == 0
         assert es["min_delta"] == 0 and es["monitor"] == rl["monitor"] == ck["monitor"] == "val_loss"
         assert ck["save_best_only"] is True and ck["save_weights_only"] is True
+
+
+def test_oracle_training_matches_torch_nn_and_torch_optim():
+    """An independent implementation of the same mathematics: torch.nn.BatchNorm1d (eps 1e-3, momentum 0.01 = Keras
+    0.99) / Linear / ELU trained with torch.optim.Adam.  Keras puts epsilon outside the bias-corrected root
+    (theta -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps)); torch divides v by (1-b2^t) first, which is the same
+    update with eps / sqrt(1-b2^t) -- set per step below.  Several optimizer steps from the same weights must give
+    the same weights, losses and moving means (moving variances differ by design: torch tracks the unbiased one)."""
+    import math
+
+    K, H, L, B, steps = 37, 16, 4, 12, 6
+    rng = np.random.default_rng(17)
+    ref = model_ref.RefLocator(K, H, L, dropout=0.0, seed=5)
+    ws = ref.get_weights()
+    ws[0] = rng.uniform(0.5, 1.5, K).astype(np.float32)
+    ws[1] = rng.normal(0, 0.1, K).astype(np.float32)
+    ref.set_weights(ws)
+    bn = torch.nn.BatchNorm1d(K, eps=1e-3, momentum=0.01)
+    dims = [K] + [H] * L + [2, 2]
+    lins = [torch.nn.Linear(dims[i], dims[i + 1]) for i in range(L + 2)]
+    with torch.no_grad():
+        bn.weight.copy_(torch.tensor(ws[0]))
+        bn.bias.copy_(torch.tensor(ws[1]))
+        for i, lin in enumerate(lins):
+            lin.weight.copy_(torch.tensor(ws[4 + 2 * i]).T)
+            lin.bias.copy_(torch.tensor(ws[5 + 2 * i]))
+    params = [bn.weight, bn.bias] + [p for lin in lins for p in (lin.weight, lin.bias)]
+    opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-7)
+    bn.train()
+    for t in range(1, steps + 1):
+        x = rng.integers(0, 3, size=(B, K)).astype(np.uint8)
+        y = rng.normal(size=(B, 2)).astype(np.float32)
+        for g in opt.param_groups:
+            g["eps"] = 1e-7 / math.sqrt(1.0 - 0.999 ** t)
+        opt.zero_grad()
+        a = bn(torch.tensor(x, dtype=torch.float32))
+        for lin in lins[:L]:
+            a = torch.nn.functional.elu(lin(a))
+        out = lins[L + 1](lins[L](a))
+        loss = torch.sqrt(((out - torch.tensor(y)) ** 2).sum(-1)).mean()
+        loss.backward()
+        opt.step()
+        loss_ref = ref.train_step(x, y, np.ones((B, H), bool))
+        assert abs(loss.item() - loss_ref) <= 2e-5 * max(1.0, abs(loss_ref)), t
+    got = ref.get_weights()
+    np.testing.assert_allclose(got[0], bn.weight.detach().numpy(), rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(got[1], bn.bias.detach().numpy(), rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(got[2], bn.running_mean.numpy(), rtol=1e-5, atol=1e-7)
+    for i, lin in enumerate(lins):
+        np.testing.assert_allclose(got[4 + 2 * i], lin.weight.detach().numpy().T, rtol=2e-4, atol=3e-6)
+        np.testing.assert_allclose(got[5 + 2 * i], lin.bias.detach().numpy(), rtol=2e-4, atol=3e-6)
+    # the weights really moved (6 Adam steps of ~lr each)
+    assert np.abs(got[4] - ws[4]).max() > 2e-3

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) k_pack_sites(const int8_t* __restrict__ g
   __shared__ uint32_t tile[S * kPackPitch];  // [call c of the lane][lane][word], pitch 17: conflict-free writes
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const int64_t s0 = (int64_t)blockIdx.x * S;
-  const int64_t w0 = (int64_t)blockIdx.y * kPackWords;
+  const int64_t w0 = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * kPackWords;  // z: slabs beyond 65535 word groups
   const int64_t sb = s0 + (int64_t)lane * CALLS;  // first sample of this lane (N % CALLS == 0: all or none in range)
 #pragma unroll
   for (int jw = 0; jw < 2; ++jw) {
@@ -330,8 +330,10 @@ int loc_pack_sites(const int8_t* d_gt, int64_t nvar, int64_t nsamp, const int64_
   while (vb > 2 && ((nsamp * 2) % vb != 0 || base % vb != 0)) vb >>= 1;
   LOC_CHECK(base % 2 == 0, "loc_pack_sites: genotype pointer must be 2-byte aligned");
   const int S = 32 * (vb / 2);
-  dim3 grid((unsigned)cdiv(nsamp, S), (unsigned)cdiv(row_words, kPackWords));
-  LOC_CHECK(grid.y <= 65535, "loc_pack_sites: K too large for one launch");
+  const int64_t wgroups = cdiv(row_words, kPackWords);
+  const int64_t gy = wgroups < 32768 ? wgroups : 32768;
+  dim3 grid((unsigned)cdiv(nsamp, S), (unsigned)gy, (unsigned)cdiv(wgroups, gy));  // blocks past row_words write nothing
+  LOC_CHECK(grid.z <= 65535, "loc_pack_sites: K too large for one launch");
   cudaStream_t st = (cudaStream_t)stream;
   switch (vb) {
     case 16: k_pack_sites<16><<<grid, 256, 0, st>>>(d_gt, nsamp, d_site_idx, K, d_packed, row_words); break;

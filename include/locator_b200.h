@@ -117,6 +117,9 @@ int loc_replace_cols(uint32_t* d_packed, int64_t n, int64_t row_words, const int
  * (LZ4 codec, byte shuffle or none -- zarr's default compressor, what allel.vcf_to_zarr writes)
  * from host memory into host memory.  Returns the decompressed size or < 0 on error. */
 int64_t loc_blosc_decompress(const uint8_t* h_src, int64_t src_len, uint8_t* h_dst, int64_t dst_len);
+/* One plain Zstandard frame (zarr compressor id "zstd"; also the streams of Blosc frames with cname "zstd"):
+ * the system's libzstd.so.1 is bound at first use.  Returns the decompressed size or < 0. */
+int64_t loc_zstd_decompress(const uint8_t* h_src, int64_t src_len, uint8_t* h_dst, int64_t dst_len);
 
 /* Host helpers for load_genotypes' VCF branch (allel.read_vcf, locator.py:195-199): data lines of an
  * uncompressed VCF text buffer -> GT int8 [n_variants][n_samples][2] (missing allele -1, haploid call ->

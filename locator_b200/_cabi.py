@@ -53,6 +53,7 @@ SIGNATURES = {
     "loc_gather_cols": (C.c_int, [P, I64, I64, P, I64, P, I64, P]),
     "loc_replace_cols": (C.c_int, [P, I64, I64, P, I64, P, P]),
     "loc_blosc_decompress": (I64, [P, I64, P, I64]),
+    "loc_zstd_decompress": (I64, [P, I64, P, I64]),
     "loc_np_legacy_binomial": (C.c_int, [P, C.POINTER(I32), I64, P, I64, I64, P]),
     "loc_np_legacy_permutation": (C.c_int, [P, C.POINTER(I32), I64, P]),
     "loc_vcf_count": (I64, [P, I64]),

@@ -2,6 +2,7 @@
 // --zarr / --windows input, locator/locator.py:187-194, scripts/vcf_to_zarr.py:12): zarr's default
 // compressor is Blosc (LZ4, byte shuffle).  Blosc 1.x frame format and the LZ4 block format are
 // restated from their published specifications; no third-party code.  Pure host code (no CUDA).
+#include <dlfcn.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -78,11 +79,53 @@ bool lz4_block(const uint8_t* src, int64_t slen, uint8_t* dst, int64_t dlen) {
   return op == oend;
 }
 
+// Blosc frames whose codec is Zstandard (stores written with zarr.Blosc(cname="zstd")): the streams inside
+// are ordinary zstd frames.  The system's libzstd is bound at first use (its two entry points have had this
+// ABI since zstd 1.0); nothing is needed at build time and LZ4 stores never touch it.
+typedef size_t (*zstd_decompress_fn)(void*, size_t, const void*, size_t);
+typedef unsigned (*zstd_iserror_fn)(size_t);
+struct Zstd {
+  zstd_decompress_fn decompress = nullptr;
+  zstd_iserror_fn is_error = nullptr;
+  Zstd() {
+    for (const char* name : {"libzstd.so.1", "libzstd.so"}) {
+      void* h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (h == nullptr) continue;
+      decompress = (zstd_decompress_fn)dlsym(h, "ZSTD_decompress");
+      is_error = (zstd_iserror_fn)dlsym(h, "ZSTD_isError");
+      if (decompress != nullptr && is_error != nullptr) return;
+      decompress = nullptr;
+    }
+  }
+};
+const Zstd& zstd() {
+  static const Zstd z;  // thread-safe one-time initialisation
+  return z;
+}
+
 }  // namespace
 
 extern "C" {
 
-// Decompress one Blosc-1 frame (LZ4 / LZ4HC codec or stored, byte shuffle or none) into dst.
+// One plain Zstandard frame (zarr compressor {"id": "zstd"}) into dst; returns the decompressed size or < 0.
+int64_t loc_zstd_decompress(const uint8_t* src, int64_t src_len, uint8_t* dst, int64_t dst_len) {
+  if (src == nullptr || dst == nullptr || src_len <= 0 || dst_len < 0) {
+    loc::fail("loc_zstd_decompress: bad arguments", __FILE__, __LINE__);
+    return -1;
+  }
+  if (zstd().decompress == nullptr) {
+    loc::fail("loc_zstd_decompress: libzstd.so.1 could not be loaded", __FILE__, __LINE__);
+    return -5;
+  }
+  const size_t got = zstd().decompress(dst, (size_t)dst_len, src, (size_t)src_len);
+  if (zstd().is_error(got)) {
+    loc::fail("loc_zstd_decompress: corrupt Zstandard stream", __FILE__, __LINE__);
+    return -4;
+  }
+  return (int64_t)got;
+}
+
+// Decompress one Blosc-1 frame (LZ4 / LZ4HC / Zstandard codec or stored, byte shuffle or none) into dst.
 // Returns the number of bytes written (the frame's nbytes) or a negative value on error.
 int64_t loc_blosc_decompress(const uint8_t* src, int64_t src_len, uint8_t* dst, int64_t dst_len) {
   if (src == nullptr || dst == nullptr || src_len < 16) {
@@ -107,9 +150,13 @@ int64_t loc_blosc_decompress(const uint8_t* src, int64_t src_len, uint8_t* dst, 
     return -2;
   }
   const unsigned codec = flags >> 5;
-  if (codec != 1) {  // 0 blosclz, 1 lz4 / lz4hc, 2 snappy, 3 zlib, 4 zstd
-    loc::fail("loc_blosc_decompress: only the LZ4 codec of Blosc is supported", __FILE__, __LINE__);
+  if (codec != 1 && codec != 4) {  // 0 blosclz, 1 lz4 / lz4hc, 2 snappy, 3 zlib, 4 zstd
+    loc::fail("loc_blosc_decompress: only the LZ4 and Zstandard codecs of Blosc are supported", __FILE__, __LINE__);
     return -3;
+  }
+  if (codec == 4 && zstd().decompress == nullptr) {
+    loc::fail("loc_blosc_decompress: Zstandard frame, but libzstd.so.1 could not be loaded", __FILE__, __LINE__);
+    return -5;
   }
   // the byte transpose of 1-byte items (int8 calldata/GT, by far the largest array) is the identity
   const bool shuffle = (flags & 0x1) != 0 && typesize > 1, dont_split = (flags & 0x10) != 0;
@@ -131,6 +178,12 @@ int64_t loc_blosc_decompress(const uint8_t* src, int64_t src_len, uint8_t* dst, 
       if (cb < 0 || pos + cb > src_len) return -1;
       if (cb == neblock) {
         memcpy(out + sp * neblock, src + pos, (size_t)neblock);
+      } else if (codec == 4) {
+        const size_t got = zstd().decompress(out + sp * neblock, (size_t)neblock, src + pos, (size_t)cb);
+        if (zstd().is_error(got) || (int64_t)got != neblock) {
+          loc::fail("loc_blosc_decompress: corrupt Zstandard stream", __FILE__, __LINE__);
+          return -4;
+        }
       } else if (!lz4_block(src + pos, cb, out + sp * neblock, neblock)) {
         loc::fail("loc_blosc_decompress: corrupt LZ4 stream", __FILE__, __LINE__);
         return -4;

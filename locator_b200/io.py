@@ -193,6 +193,20 @@ def _blosc_decompress_array(raw):
     return out
 
 
+def _zstd_decompress_array(raw, nbytes):
+    """One Zstandard frame of known decoded size -> uint8 array (loc_zstd_decompress: the system's libzstd)."""
+    from ._cabi import lib, check
+
+    if nbytes <= 0:
+        raise ValueError("zstd chunks of object arrays are not supported")
+    out = np.empty(nbytes, dtype=np.uint8)
+    src = np.frombuffer(raw, dtype=np.uint8)
+    n = lib.loc_zstd_decompress(src.ctypes.data, len(raw), out.ctypes.data, nbytes)
+    if n < 0:
+        check(1, "loc_zstd_decompress")
+    return out[:n]
+
+
 def _blosc_decompress(raw, nbytes_hint=None):
     """One Blosc frame -> bytes."""
     return _blosc_decompress_array(raw).tobytes()
@@ -284,9 +298,10 @@ def _zarr_array(root, name, rows=None, out=None):
         indices = []
     else:
         indices = [()]
-    if comp is not None and comp.get("id") not in ("zlib", "gzip", "blosc"):
+    if comp is not None and comp.get("id") not in ("zlib", "gzip", "blosc", "zstd"):
         raise ValueError(f"{name}: zarr compressor {comp.get('id')!r} is not available in this build "
-                         "(supported: none, zlib, gzip, blosc-lz4)")
+                         "(supported: none, zlib, gzip, zstd, blosc with lz4 / zstd)")
+    chunk_nbytes = int(np.prod(chunks, dtype=np.int64)) * dtype.itemsize if not is_obj else 0
     row_bytes = int(np.prod(shape[1:], dtype=np.int64)) * dtype.itemsize if shape else 0
 
     def load(idx):
@@ -313,6 +328,8 @@ def _zarr_array(root, name, rows=None, out=None):
             buf = raw
         elif comp.get("id") in ("zlib", "gzip"):
             buf = zlib.decompress(raw, 15 + 32)
+        elif comp.get("id") == "zstd":
+            buf = _zstd_decompress_array(raw, chunk_nbytes)
         else:
             buf = _blosc_decompress_array(raw)
         if is_obj:

@@ -61,9 +61,17 @@ def _lz4_encode(data: bytes) -> bytes:
     return bytes(out)
 
 
-def _blosc_frame(raw: bytes, typesize: int, blocksize: int, shuffle=True, dont_split=False, memcpy=False):
+def _blosc_frame(raw: bytes, typesize: int, blocksize: int, shuffle=True, dont_split=False, memcpy=False, codec="lz4"):
+    """codec "zstd": the streams are Zstandard frames (written by pyarrow's codec); Blosc never splits those."""
     nbytes = len(raw)
-    flags = (1 if shuffle else 0) | (0x10 if dont_split else 0) | (1 << 5) | (0x2 if memcpy else 0)
+    if codec == "zstd":
+        import pyarrow as pa
+
+        dont_split = True
+        encode = lambda part: pa.Codec("zstd").compress(part, asbytes=True)  # noqa: E731
+    else:
+        encode = _lz4_encode
+    flags = (1 if shuffle else 0) | (0x10 if dont_split else 0) | ((4 if codec == "zstd" else 1) << 5) | (0x2 if memcpy else 0)
     if memcpy:
         body = raw
         return bytes([2, 1, flags, typesize]) + struct.pack("<III", nbytes, blocksize, 16 + nbytes) + body
@@ -81,7 +89,7 @@ def _blosc_frame(raw: bytes, typesize: int, blocksize: int, shuffle=True, dont_s
         bstarts.append(pos)
         for s in range(nsplits):
             part = blk[s * ne:(s + 1) * ne]
-            enc = _lz4_encode(part)
+            enc = encode(part)
             if len(enc) >= len(part):
                 enc = part  # stored split: cbytes == neblock
             streams.append(struct.pack("<I", len(enc)) + enc)
@@ -123,8 +131,11 @@ def test_blosc_rejects_corrupt_and_unsupported():
     raw = bytes(range(256)) * 8
     frame = bytearray(_blosc_frame(raw, 1, 4096))
     bad = bytearray(frame)
-    bad[2] = (bad[2] & 0x1F) | (4 << 5)  # zstd codec id
+    bad[2] = (bad[2] & 0x1F) | (3 << 5)  # zlib-inside-Blosc codec id: not supported
     with pytest.raises(RuntimeError, match="LZ4"):
+        io._blosc_decompress(bytes(bad))
+    bad[2] = (bad[2] & 0x1F) | (4 << 5)  # zstd codec id over LZ4 streams: a corrupt Zstandard stream
+    with pytest.raises(RuntimeError, match="Zstandard"):
         io._blosc_decompress(bytes(bad))
     with pytest.raises(RuntimeError):
         io._blosc_decompress(bytes(frame[:40]))
@@ -168,7 +179,7 @@ def test_zarr_store_with_blosc_gt_and_vlen_samples(tmp_path, fixture_gt):
     np.testing.assert_array_equal(back["variants/POS"], pos)
 
 
-@pytest.mark.parametrize("codec", ["raw", "zlib", "blosc"])
+@pytest.mark.parametrize("codec", ["raw", "zlib", "blosc", "zstd", "blosc-zstd"])
 def test_threaded_reads_of_a_chunk_grid_over_variants_and_samples(tmp_path, monkeypatch, codec):
     """allel.vcf_to_zarr chunks calldata/GT over variants AND samples ((65536, 64, 2) by default); the reader
     decodes the chunks of a row range from a thread pool.  Row ranges inside / across chunks, ragged edge
@@ -180,8 +191,11 @@ def test_threaded_reads_of_a_chunk_grid_over_variants_and_samples(tmp_path, monk
     gt = rng.integers(-1, 3, size=(nvar, N, 2)).astype(np.int8)
     d = tmp_path / "g.zarr" / "calldata" / "GT"
     d.mkdir(parents=True)
-    comp = {"raw": None, "zlib": {"id": "zlib", "level": 1},
-            "blosc": {"blocksize": 0, "clevel": 5, "cname": "lz4", "id": "blosc", "shuffle": 1}}[codec]
+    if "zstd" in codec:
+        pa = pytest.importorskip("pyarrow")
+    comp = {"raw": None, "zlib": {"id": "zlib", "level": 1}, "zstd": {"id": "zstd", "level": 1},
+            "blosc": {"blocksize": 0, "clevel": 5, "cname": "lz4", "id": "blosc", "shuffle": 1},
+            "blosc-zstd": {"blocksize": 0, "clevel": 1, "cname": "zstd", "id": "blosc", "shuffle": 1}}[codec]
     (d / ".zarray").write_text(json.dumps({"zarr_format": 2, "shape": [nvar, N, 2], "chunks": [cv, cn, 2], "dtype": "|i1",
                                            "order": "C", "compressor": comp, "fill_value": -1, "filters": None}))
     missing = (3, 2)
@@ -193,7 +207,9 @@ def test_threaded_reads_of_a_chunk_grid_over_variants_and_samples(tmp_path, monk
             part = gt[i * cv:(i + 1) * cv, j * cn:(j + 1) * cn]
             blk[:part.shape[0], :part.shape[1]] = part
             raw = blk.tobytes()
-            blob = raw if codec == "raw" else zlib.compress(raw, 1) if codec == "zlib" else _blosc_frame(raw, 1, 16384)
+            blob = {"raw": lambda: raw, "zlib": lambda: zlib.compress(raw, 1), "blosc": lambda: _blosc_frame(raw, 1, 16384),
+                    "zstd": lambda: pa.Codec("zstd").compress(raw, asbytes=True),
+                    "blosc-zstd": lambda: _blosc_frame(raw, 1, 16384, codec="zstd")}[codec]()
             (d / f"{i}.{j}.0").write_bytes(blob)
     want = gt.copy()
     want[missing[0] * cv:(missing[0] + 1) * cv, missing[1] * cn:(missing[1] + 1) * cn] = -1
@@ -240,3 +256,30 @@ def test_lz4_decoder_fast_paths_at_buffer_edges():
     # the shuffle flag on 1-byte items (what zarr writes for int8 calldata/GT) is the identity
     data = bytes(rng.integers(0, 3, 5000, dtype=np.uint8))
     assert io._blosc_decompress(_blosc_frame(data, 1, 2048, shuffle=True)) == data
+
+
+def test_blosc_zstd_frames(tmp_path):
+    """Stores written with zarr.Blosc(cname="zstd"): the library binds the system's libzstd at first use.  Frames
+    with Zstandard streams (made by pyarrow's codec) of several item sizes / block sizes, with and without byte
+    shuffle, and a zarr store whose calldata/GT chunks are such frames."""
+    pa = pytest.importorskip("pyarrow")
+    if not pa.Codec.is_available("zstd"):
+        pytest.skip("pyarrow without zstd")
+    rng = np.random.default_rng(9)
+    for typesize, blocksize, n, shuffle in [(1, 4096, 20000, True), (1, 1 << 16, 70001, False), (4, 2048, 5000, True),
+                                            (8, 4096, 1234, True), (2, 512, 513, True)]:
+        raw = rng.integers(0, 3, n * typesize, dtype=np.uint8).tobytes()
+        assert io._blosc_decompress(_blosc_frame(raw, typesize, blocksize, shuffle=shuffle, codec="zstd")) == raw
+    gt = rng.integers(-1, 2, size=(900, 70, 2)).astype(np.int8)
+    d = tmp_path / "z.zarr" / "calldata" / "GT"
+    d.mkdir(parents=True)
+    comp = {"blocksize": 0, "clevel": 1, "cname": "zstd", "id": "blosc", "shuffle": 1}
+    (d / ".zarray").write_text(json.dumps({"zarr_format": 2, "shape": [900, 70, 2], "chunks": [256, 64, 2], "dtype": "|i1",
+                                           "order": "C", "compressor": comp, "fill_value": 0, "filters": None}))
+    for i in range(4):
+        for j in range(2):
+            blk = np.zeros((256, 64, 2), np.int8)
+            part = gt[i * 256:(i + 1) * 256, j * 64:(j + 1) * 64]
+            blk[:part.shape[0], :part.shape[1]] = part
+            (d / f"{i}.{j}.0").write_bytes(_blosc_frame(blk.tobytes(), 1, 8192, codec="zstd"))
+    np.testing.assert_array_equal(io.ZarrRows(str(tmp_path / "z.zarr"), "calldata/GT").read(), gt)

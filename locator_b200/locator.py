@@ -94,8 +94,8 @@ def build_parser():
     parser.add_argument("--gpus", default=1, type=int,
                         help="(locator_b200) GPUs of this box to spread --bootstrap / --windows replicates over. default: 1")
     parser.add_argument("--replicates_per_gpu", default=4, type=int,
-                        help="(locator_b200) bootstrap / window models trained side by side on each GPU (1-8; results "
-                        "do not depend on it). default: 4")
+                        help="(locator_b200) bootstrap / window models trained side by side on each GPU (1-8; the indices "
+                        "never depend on it, and predictions are identical for every value >= 2). default: 4")
     return parser
 
 

@@ -4,17 +4,22 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg3|fixture]
 
 A "step" is one optimizer step of one model (batch 32) on BASELINE config[1]: 1,000 samples x
-100,000 SNPs (810 train / 90 validation rows), nlayers=10, width=256.  The timed region enqueues
-exactly K steps through the C ABI (loc_train_epochs for whole epochs -- which, like the reference's
-model.fit, run the validation pass and callbacks after every epoch -- and loc_train_step for the
-remainder) on data already resident in HBM.  N > 1: every rank trains its own model on its own GPU
-(replicates are independent; no collective on the training path) -> weak scaling.
+100,000 SNPs (810 train / 90 validation rows), nlayers=10, width=256.  The timed region runs exactly
+K consecutive steps of model.fit's schedule through the C ABI (loc_train_steps: the production path
+-- every first-layer backward also runs the next step's forward; whenever the K steps cross the end
+of an epoch, that epoch's validation pass, callbacks and checkpoint are inside the timed region, as
+in the reference's model.fit) on data already resident in HBM.  N > 1: every rank trains its own
+model on its own GPU (replicates are independent; no collective on the training path) -> weak scaling.
 
-Printed JSON line: see the task contract.  `e2e` times LocatorModel.fit() on HOST numpy arrays
-(H2D of the genotype matrices, 2-bit pack, the same number of steps, history read back).
-`roofline` is the first-layer backward + Adam kernel (24*K*H bytes per launch) timed alone with
-CUDA events.  `cpu_baseline` times the oracle (torch-CPU fp32 restatement of the Keras path; TF is
-not installable on this image) on a bounded number of steps.
+Printed JSON line: see the task contract.  Extra objects:
+  e2e          the public API end to end: LocatorModel(...) creation + init + fit() for >= 20 epochs on
+               PAGEABLE host numpy matrices (H2D, 2-bit pack, epochs incl. validation, history D2H)
+  roofline     the first-layer backward + Adam kernel (24*K*H bytes per launch) timed alone, CUDA events
+  work_queue   BASELINE config[3] (--bootstrap --nboots 64 on the same matrix, 20 epochs per model) through
+               the replicate work queue of locator_b200.replicates, the ranks of this job as its workers
+  replicate_group / tensor_parallel   side measurements (several models per GPU; one model over N GPUs)
+  cpu_baseline the oracle (torch-CPU fp32 restatement of the Keras path; TF is not installable on this
+               image) on a bounded number of steps
 """
 import argparse
 import ctypes
@@ -154,6 +159,14 @@ def cpu_steps(x, y, xv, yv, nsteps, threads):
     return done * B / dt, dt
 
 
+def workload_string(workload):
+    """config.workload, the same text in both arms."""
+    n_total, K = WORKLOADS[workload]
+    ntr, nva = split_sizes(n_total)
+    return (f"{workload}: {n_total} samples x {K} SNPs ({ntr} train / {nva} val), 1 model per GPU, batch {B}, "
+            f"nlayers {L}, width {H}")
+
+
 def run_reference(args, workload):
     """--impl reference: the reference's algorithm on the host CPU (oracle port; TF/Keras cannot be
     installed on this image -- no wheel, no network), all host threads, bounded sample."""
@@ -178,13 +191,94 @@ def run_reference(args, workload):
         "impl": "reference", "metric": "train_samples_per_sec", "value": val, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * B / val,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{workload}: {n_total} samples x {K} SNPs, 1 model, batch 32, nlayers 10, width 256"},
+        "config": {"workload": workload_string(workload)},
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{nst} optimizer steps of the oracle (torch-CPU fp32 restatement of the Keras "
                                    f"path; TensorFlow not installable here) in {dt:.1f} s"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def work_queue_leg(rank, world, store, barrier, n_total, K, group):
+    """BASELINE config[3]: `locator --bootstrap --nboots 64 --max_epochs 20 --patience 1000 --seed 12345` on the
+    synthetic 1,000 x 100,000 matrix, from the packed matrix in HBM to the last replicate's output files,
+    through the product's replicate work queue (locator_b200.replicates: serve() + RankQueue -- the ranks of
+    this job are the queue's workers, one per GPU; `locator --gpus N` runs the same loop in spawned workers).
+    Every rank derives the same split and bootstrap site orders from numpy's seeded legacy stream, as the
+    reference's loop does (locator.py:609-681); no collective, the only shared state is the queue's counter."""
+    import contextlib
+    import glob
+    import shutil
+
+    import torch
+    from locator_b200 import locator as Lmod, replicates
+    from locator_b200.genotypes import PackedGenotypes
+
+    nboots, epochs = 64, 20
+    tmp = f"/tmp/locbench_{os.environ.get('MASTER_PORT', 'solo')}_{os.getppid() if world > 1 else os.getpid()}"
+    if rank == 0:
+        shutil.rmtree(tmp, ignore_errors=True)
+        os.makedirs(tmp, exist_ok=True)
+    barrier()
+    argv = ["--matrix", "synthetic", "--sample_data", "synthetic", "--out", os.path.join(tmp, "cfg4"), "--bootstrap",
+            "--nboots", str(nboots), "--max_epochs", str(epochs), "--patience", "1000", "--seed", "12345",
+            "--plot_history", "", "--keras_verbose", "0", "--replicates_per_gpu", str(group)]
+    Lmod.set_args(Lmod.build_parser().parse_args(argv))
+    x, yz = synth(n_total, K, 1002)
+    locs = yz.astype(np.float64)
+    locs[: n_total // 10] = np.nan  # the first 10 % of the samples are the ones to predict
+    samples = np.array([f"s{i:04d}" for i in range(n_total)])
+    with contextlib.redirect_stdout(sys.stderr):  # the mirrored functions print like the reference
+        np.random.seed(12345)
+        meanlong, sdlong, meanlat, sdlat, nlocs = Lmod.normalize_locs(locs)
+        ac = Lmod.AlleleCounts(PackedGenotypes.from_counts(x))
+        train, test, traingen, testgen, trainlocs, testlocs, pred, predgen = Lmod.split_train_test(ac, nlocs)
+        base = {"traingen": traingen, "testgen": testgen, "predgen": predgen, "trainlocs": trainlocs,
+                "testlocs": testlocs, "norm": (meanlong, sdlong, meanlat, sdlat), "pred": pred, "samples": samples}
+        orders = replicates.draw_bootstrap_orders(traingen.K, nboots)
+        items = [{"kind": "full", "boot": "FULL"}] + [{"kind": "boot", "boot": b, "site_order": o}
+                                                      for b, o in enumerate(orders)]
+        # warm-up: one short group per rank (lazy imports, first launches, allocator growth)
+        Lmod.args.max_epochs = 2
+        replicates.run_items_ranked(Lmod, base, items[1:1 + min(group, 2)], 1, None)
+        Lmod.args.max_epochs = epochs
+        torch.cuda.synchronize()
+        barrier()
+        if rank == 0:
+            for f in glob.glob(os.path.join(tmp, "*")):
+                os.remove(f)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        taken = replicates.run_items_ranked(Lmod, base, items, world, store, key="bench_cfg4")
+        ev1.record()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    dt_max = max_over_ranks(dt, "cuda")
+    dev_max = max_over_ranks(ev0.elapsed_time(ev1) / 1000.0, "cuda")
+    mine = float(sum(len(g) for g in taken))
+    most = max_over_ranks(mine, "cuda")
+    barrier()
+    n_models = len(items)
+    out = None
+    if rank == 0:
+        files = glob.glob(os.path.join(tmp, "cfg4_boot*_predlocs.txt"))
+        assert len(files) == n_models, f"work queue: {len(files)} prediction files for {n_models} models"
+        ntr = traingen.n
+        out = {"workload": f"cfg4: --bootstrap --nboots {nboots} (+ the FULL model) on {n_total} x {K}, --max_epochs "
+                           f"{epochs} --patience 1000 --seed 12345, {group} replicates per GPU side by side",
+               "models": n_models, "epochs_per_model": epochs, "seconds": dt_max, "device_seconds": dev_max,
+               "models_per_hour": n_models * 3600.0 / dt_max,
+               "train_samples_per_sec": n_models * epochs * ntr / dt_max, "scaling": "strong",
+               "models_on_busiest_gpu": int(most),
+               "granularity_bound": n_models / (world * float(-(-n_models // world))),
+               "what": "timed: packed matrix resident -> bootstrap column gathers, model creation, 20 epochs incl. "
+                       "validation, best-epoch reload, prediction, *_predlocs.txt / *_history.txt written; wall "
+                       "clock, max over ranks; queue = locator_b200.replicates.RankQueue (guided group sizes)"}
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
 
 
 def main():
@@ -197,7 +291,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=100)
     ap.add_argument("--no-tp", action="store_true", help="skip the sharded-model measurement at N > 1")
-    ap.add_argument("--group", type=int, default=4, help="replicates per GPU for the lockstep-group measurement (0/1 = skip)")
+    ap.add_argument("--no-queue", action="store_true", help="skip the cfg4 work-queue measurement")
+    ap.add_argument("--e2e-epochs", type=int, default=20)
+    ap.add_argument("--group", type=int, default=4, help="replicates per GPU for the group / work-queue measurements (0/1 = skip the group leg)")
     args = ap.parse_args()
     workload = args.workload
     if args.impl == "reference":
@@ -212,8 +308,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
+    store = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        store = dist.distributed_c10d._get_default_store()
 
     from locator_b200 import model, _cabi
     lib = _cabi.lib
@@ -234,27 +332,24 @@ def main():
     rng = np.random.default_rng(7 + rank)
     stream = torch.cuda.current_stream().cuda_stream
 
-    def enqueue(nsteps):
-        """nsteps optimizer steps: whole epochs through loc_train_epochs, remainder loc_train_step."""
-        keep = []
-        ne, rem = divmod(nsteps, spe)
-        if ne:
-            p = torch.as_tensor(np.stack([rng.permutation(ntr) for _ in range(ne)]).astype(np.int32)).cuda()
-            keep.append(p)
-        rows = []
-        if rem:
-            perm = rng.permutation(ntr)
-            for s in range(rem):
-                r = torch.as_tensor(perm[s * B:(s + 1) * B].astype(np.int32)).cuda()
-                rows.append(r)
-        torch.cuda.synchronize()
+    # the run is model.fit's sequence of steps: epoch e visits perms[e] in slices of 32; warm-up = its first
+    # `warm` steps, timed region = the next `steps` steps (continuing inside the epoch the warm-up stopped in)
+    perms = torch.as_tensor(np.stack([rng.permutation(ntr) for _ in range(n_ep_total)]).astype(np.int32)).cuda()
 
-        def go():
-            if ne:
-                _cabi.check(lib.loc_train_epochs(m._h, keep[0].data_ptr(), ne, stream), "loc_train_epochs")
-            for r in rows:
-                _cabi.check(lib.loc_train_step(m._h, r.data_ptr(), int(r.numel()), stream), "loc_train_step")
-        return go, keep, rows
+    def segments(g0, g1):
+        """global steps [g0, g1) -> [(epoch, first step, count)], at most one segment per epoch"""
+        out = []
+        g = g0
+        while g < g1:
+            e, s0 = divmod(g, spe)
+            n = min(spe - s0, g1 - g)
+            out.append((e, s0, n))
+            g += n
+        return out
+
+    def run(segs):
+        for e, s0, n in segs:
+            _cabi.check(lib.loc_train_steps(m._h, perms[e].data_ptr(), s0, n, stream), "loc_train_steps")
 
     def barrier():
         torch.cuda.synchronize()
@@ -262,21 +357,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    go_w, kw, rw = enqueue(warm)
-    go_w()
+    timed = segments(warm, warm + steps)
+    epoch_ends = sum(1 for e, s0, n in timed if s0 + n == spe)
+    run(segments(0, warm))
     barrier()
-    go, kk, rr = enqueue(steps)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     l0 = _cabi.launch_count()
     with ClockSampler(local) as clk:
         ev0.record()
-        go()
+        run(timed)
         ev1.record()
         torch.cuda.synchronize()
     launches = _cabi.launch_count() - l0
     ms = max_over_ranks(ev0.elapsed_time(ev1), "cuda")
     st = m.state()
+    assert st.t == warm + steps, (st.t, warm, steps)
     assert st.nonfinite == 0 and np.isfinite(st.last_loss), "non-finite loss during the timed region"
     value = aggregate_value(world, steps, B, ms)
 
@@ -285,39 +380,23 @@ def main():
     for stage in (0, 1):
         _cabi.check(lib.loc_debug_stage(m._h, stage, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
     reps = 20
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for i in range(3):
-        _cabi.check(lib.loc_debug_stage(m._h, 2, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
-    torch.cuda.synchronize()
-    for a, b in evs:
-        a.record()
-        _cabi.check(lib.loc_debug_stage(m._h, 2, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
-        b.record()
-    torch.cuda.synchronize()
-    bwd_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    fwd_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for a, b in fwd_evs:
-        a.record()
-        _cabi.check(lib.loc_debug_stage(m._h, 0, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
-        b.record()
-    torch.cuda.synchronize()
-    fwd_ms = float(np.mean([a.elapsed_time(b) for a, b in fwd_evs]))
-    hid_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for a, b in hid_evs:
-        a.record()
-        _cabi.check(lib.loc_debug_stage(m._h, 1, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
-        b.record()
-    torch.cuda.synchronize()
-    hid_ms = float(np.mean([a.elapsed_time(b) for a, b in hid_evs]))
-    fus_ms = None
-    if m.impl == "tcgen05":
-        fus_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for a, b in fus_evs:
+
+    def time_stage(stage, warmups=0):
+        for _ in range(warmups):
+            _cabi.check(lib.loc_debug_stage(m._h, stage, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in evs:
             a.record()
-            _cabi.check(lib.loc_debug_stage(m._h, 4, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
+            _cabi.check(lib.loc_debug_stage(m._h, stage, rows_dev.data_ptr(), B, stream), "loc_debug_stage")
             b.record()
         torch.cuda.synchronize()
-        fus_ms = float(np.mean([a.elapsed_time(b) for a, b in fus_evs]))
+        return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    bwd_ms = time_stage(2, 3)
+    fwd_ms = time_stage(0)
+    hid_ms = time_stage(1)
+    fus_ms = time_stage(4) if m.impl == "tcgen05" else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -326,63 +405,61 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = 24.0 * K * H
     achieved = alg_bytes / (bwd_ms / 1000.0) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "l1_backward_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             if tj.get("K") == K:
                 traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = f"ncu --set full capture of commit {tj.get('commit', '?')} ({tj.get('source', tpath)})"
         except Exception:
             pass
     roofline = {"bound": "hbm", "kernel": "l1_backward_adam(" + m.impl + ")",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": bwd_ms,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": bwd_ms,
                 "stage_ms": {"l1_forward": fwd_ms, "hidden": hid_ms, "l1_backward": bwd_ms,
                              "l1_backward_with_fused_next_forward": fus_ms},
-                "step_roofline_frac": (28.0 * K * H / 1e9 / peak) / (ms / 1000.0 / steps) }
+                "step_roofline_frac": (28.0 * K * H / 1e9 / peak) / (ms / 1000.0 / steps)}
+    del m
 
-    # ---- e2e: fit() on host arrays (H2D + pack + the same number of steps + history D2H) ----
-    e2e = None
-    if True:
-        ne = max(1, steps // spe)
-        m2 = model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=ne + 1,
-                                seed=300 + rank)
-        xtr_p = torch.from_numpy(xtr).pin_memory()
-        xva_p = torch.from_numpy(xva).pin_memory()
-        # warm-up of the same public call (one epoch): first pinned transfer, allocator growth, lazy kernel loads
-        mw = model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=2, seed=299 + rank)
-        mw.fit(xtr_p, ytr, epochs=1, validation_data=(xva_p, yva), patience=10 ** 6)
-        del mw
-        barrier()
-        t0 = time.perf_counter()
-        h = m2.fit(xtr_p, ytr, epochs=ne, validation_data=(xva_p, yva), patience=10 ** 6, epochs_per_call=ne)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        dt = max_over_ranks(dt, "cuda")
-        nst = ne * spe
-        assert len(h.history["loss"]) == ne and np.isfinite(h.history["loss"][-1])
-        h2d = xtr.nbytes + xva.nbytes + ytr.nbytes + yva.nbytes + ne * ntr * 4
-        e2e = {"value": world * ne * ntr / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d / nst,
-               "d2h_bytes_per_step": (ne * 12 + 64) / nst, "epochs": ne, "seconds": dt,
-               # replicate throughput of BASELINE's second metric: one model at the throughput schedule of
-               # SURVEY 8(d) (--max_epochs 20 --patience 1000), ingest of the packed matrix included
-               "replicate_models_per_hour_20_epochs": world * 3600.0 / (dt * 20.0 / ne),
-               "what": "LocatorModel.fit on host uint8 matrices: H2D, 2-bit pack, epochs incl. validation, history D2H"}
-        del m2
+    # ---- e2e: the public API on PAGEABLE host arrays: model creation + init + fit + history ----
+    ne = max(args.e2e_epochs, -(-steps // spe))
+    mw = model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=2, seed=299 + rank)
+    mw.fit(xtr, ytr, epochs=1, validation_data=(xva, yva), patience=10 ** 6)  # warm-up of the same call
+    del mw
+    barrier()
+    t0 = time.perf_counter()
+    m2 = model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=ne, seed=300 + rank)
+    h = m2.fit(xtr, ytr, epochs=ne, validation_data=(xva, yva), patience=10 ** 6)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0, "cuda")
+    nst = ne * spe
+    assert len(h.history["loss"]) == ne and np.isfinite(h.history["loss"][-1])
+    h2d = xtr.nbytes + xva.nbytes + ytr.nbytes + yva.nbytes + ne * ntr * 4
+    n_state_reads = -(-ne // 16) + 1
+    e2e = {"value": world * ne * ntr / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d / nst,
+           "d2h_bytes_per_step": (ne * 12 + 48 * n_state_reads) / nst, "epochs": ne, "seconds": dt,
+           "host_memory": "pageable numpy arrays",
+           "replicate_models_per_hour_20_epochs": world * 3600.0 / (dt * 20.0 / ne),
+           "what": "LocatorModel(...) creation + weight init + fit() on host uint8 matrices: H2D, 2-bit pack, "
+                   f"{ne} epochs incl. validation / callbacks / checkpoints, history D2H"}
+    del m2
 
-    # ---- replicate group: G independent models advanced in lockstep on this GPU (bootstrap / windows) ----
+    # ---- replicate group: G independent models side by side on this GPU (bootstrap / windows) ----
     group = None
-    if m.impl == "tcgen05" and args.group > 1:
+    if args.group > 1 and lib.loc_l1_impl().decode() == "tcgen05":
         G = args.group
+        gval = model.PackedGenotypes.from_counts(xva)
 
         def measure_group(l1_ctas):
-            gm = [model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=n_ep_total + 2,
+            gm = [model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=16,
                                      seed=500 + rank * 16 + g, l1_ctas=l1_ctas) for g in range(G)]
             for q in gm:
                 q.bind_train(gtr, ytr)
-                q.bind_val(m._keep["val"][0], yva)
+                q.bind_val(gval, yva)
                 q.set_schedule(patience=10 ** 6)
             ne_g = max(2, min(6, steps // spe))
             prng = np.random.default_rng(77)
@@ -406,23 +483,37 @@ def main():
             return {"epochs": ne_g, "value": world * G * ne_g * ntr / (gms / 1000.0),
                     "ms_per_step_per_replicate": gms / (ne_g * spe * G), "last_loss_model0": loss}
 
-        # ring: the first-layer kernels leave one cluster's worth of SMs free, a model's hidden stack runs next to
-        # the previous model's backward (programmatic dependent launch); lockstep: all SMs, hidden stacks grouped
         ring = measure_group(model.spare_cluster_l1_ctas())
         lock = measure_group(None)
         group = {"replicates_per_gpu": G, "epochs": ring["epochs"], "value": ring["value"],
                  "unit": "samples/s (all replicates)", "ms_per_step_per_replicate": ring["ms_per_step_per_replicate"],
                  "schedule": "ring", "lockstep": lock, "ring": ring,
+                 "step_roofline_frac": (28.0 * K * H / 1e9 / peak) / (ring["ms_per_step_per_replicate"] / 1000.0),
+                 "note": "last_loss_model0 differs between the schedules because the first-layer CTA count (132 vs "
+                         "148) changes the fp32 summation order and Adam amplifies rounding at K = 100k: "
+                         "tests/test_gpu_baseline_shapes.py::test_divergence_is_rounding_chaos",
                  "what": "loc_group_train_epochs, ring schedule: hidden stack of model g concurrent with the "
                          "first-layer backward + Adam of model g-1 (132 CTAs); 'lockstep' = the grouped-launch schedule"}
 
-    # ---- one model sharded over the ranks (SNP columns; one 32 KB all_reduce of the Z1 tile per forward) ----
+    # ---- cfg4 through the replicate work queue (strong scaling over the ranks) ----
+    work_queue = None
+    if not args.no_queue and workload == "cfg2" and lib.loc_l1_impl().decode() == "tcgen05":
+        try:
+            work_queue = work_queue_leg(rank, world, store, barrier, n_total, K, max(1, min(8, args.group or 1)))
+        except Exception as exc:  # an extra: never lose the bench line over it
+            import traceback
+
+            traceback.print_exc()
+            work_queue = {"error": f"{type(exc).__name__}: {exc}"}
+
+    # ---- one model sharded over the ranks (SNP columns; one 32 KB exchange of the Z1 tile per forward) ----
     tp = None
-    if world > 1 and m.impl == "tcgen05" and not args.no_tp:
+    if world > 1 and lib.loc_l1_impl().decode() == "tcgen05" and not args.no_tp:
         xs, ys = (x, y) if rank == 0 else synth(ntr + nva, K, 1002)  # every shard sees the same samples
         k0, k1 = model.shard_bounds(K, rank, world)
         xt, xv = np.ascontiguousarray(xs[:ntr, k0:k1]), np.ascontiguousarray(xs[ntr:, k0:k1])
         ne_t = max(2, min(10, steps // spe))
+        tp_error = None
 
         def run_tp(exchange):
             tm = model.LocatorModel(k1 - k0, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=64,
@@ -433,6 +524,7 @@ def main():
             prng = np.random.default_rng(4242)  # the same batch order on every shard
             pw = np.stack([prng.permutation(ntr) for _ in range(2)]).astype(np.int32)
             pt = np.stack([prng.permutation(ntr) for _ in range(ne_t)]).astype(np.int32)
+            barrier()  # every shard is ready: nobody spins in the exchange while a peer is still setting up
             tm.train_epochs(pw)
             barrier()
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -453,24 +545,28 @@ def main():
         except Exception as exc:  # the sharded measurement is an extra: never lose the bench line over it
             peer = hook = None
             tp_error = f"{type(exc).__name__}: {exc}"
-        tp = {"error": tp_error} if peer is None else {"shards": world, "epochs": ne_t, "value": peer["value"], "unit": "samples/s (one model)",
-              "ms_per_step": peer["ms_per_step"], "scaling": "strong",
-              "with_nccl_all_reduce_hook": hook,
-              "what": "one cfg model sharded over SNP columns: W1 + Adam state K/N per GPU, hidden stack replicated; "
-                      "per forward pass every shard pushes its reduced [32][256] first-layer tile into the peers' "
-                      "buffers over NVLink (own kernels, cudaIpc peer memory) and the hidden kernel sums them"}
+        tp = {"error": tp_error} if peer is None else {
+            "shards": world, "epochs": ne_t, "value": peer["value"], "unit": "samples/s (one model)",
+            "ms_per_step": peer["ms_per_step"], "scaling": "strong", "with_nccl_all_reduce_hook": hook,
+            "what": "one cfg model sharded over SNP columns: W1 + Adam state K/N per GPU, hidden stack replicated; "
+                    "per forward pass every shard pushes its reduced [32][256] first-layer tile into the peers' "
+                    "buffers over NVLink (own kernels, cudaIpc peer memory) and the hidden kernel sums them"}
 
+    impl = lib.loc_l1_impl().decode()
     line = {
         "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps,
         "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32" if m.impl == "tcgen05" else "f32",
+        "dtype": "tf32" if impl == "tcgen05" else "f32",
         "data": "synthetic",
-        "config": {"workload": f"{workload}: {n_total} samples x {K} SNPs ({ntr} train / {nva} val), 1 model per GPU, "
-                               f"batch {B}, nlayers {L}, width {H}",
+        "config": {"workload": workload_string(workload),
                    "l2": "inputs larger than L2 (W1+m+v = %.0f MB per step)" % (12.0 * K * H / 1e6),
-                   "steps_per_epoch": spe, "validation_pass_every_epoch": True},
+                   "steps_per_epoch": spe,
+                   "schedule": "model.fit's step sequence through loc_train_steps (production path: fused next "
+                               "forward, alternating tile walk); timed steps continue the epoch the warm-up stopped in",
+                   "epoch_ends_in_timed_region": epoch_ends,
+                   "validation_pass_and_callbacks": "at every epoch end inside the timed region (%d here)" % epoch_ends},
         "clocks": clk.summary(), "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
-        "replicate_group": group, "tensor_parallel": tp,
+        "work_queue": work_queue, "replicate_group": group, "tensor_parallel": tp,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, dt = cpu_steps(xtr, ytr, xva, yva, args.cpu_steps, os.cpu_count() or 1)

@@ -233,6 +233,15 @@ int loc_train_step(loc_model* m, const int32_t* d_rows, int32_t nb, void* stream
  * no-ops.  History rows are appended per epoch. */
 int loc_train_epochs(loc_model* m, const int32_t* d_perms, int32_t n_epochs, void* stream);
 
+/* Part of an epoch on the same schedule as loc_train_epochs (the production path: every first-layer backward
+ * also runs the next step's forward): optimizer steps [step0, step0 + n_steps) of the epoch whose batch order
+ * is d_perm[0 .. n_train) -- step s trains on rows d_perm[s*batch_size ..).  The span must lie inside the
+ * epoch.  When it ends the epoch, the validation pass, callbacks and checkpoint follow exactly as in
+ * loc_train_epochs (validation data must be bound); consecutive calls that continue the same d_perm keep the
+ * fused forward across the call boundary.  Callers that want model.fit semantics use loc_train_epochs; this
+ * entry exists for partial epochs (bench.py --steps K, progress reporting inside long epochs).  Async. */
+int loc_train_steps(loc_model* m, const int32_t* d_perm, int32_t step0, int32_t n_steps, void* stream);
+
 /* Replicate group (bootstrap / window models trained side by side on one GPU, locator.py:519-583 and
  * :609-681 run them one after the other): the same as loc_train_epochs for n_models <= 8 independent models.
  * Models must share nlayers, batch size and training-set size (true for the replicates of one run);

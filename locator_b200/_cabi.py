@@ -84,6 +84,7 @@ SIGNATURES = {
     "loc_debug_stage": (C.c_int, [P, I32, P, I32, P]),
     "loc_debug_read": (I64, [P, I32, P, I64, P]),
     "loc_train_epochs": (C.c_int, [P, P, I32, P]),
+    "loc_train_steps": (C.c_int, [P, P, I32, I32, P]),
     "loc_group_train_epochs": (C.c_int, [C.POINTER(P), I32, C.POINTER(P), I32, P]),
     "loc_eval": (C.c_int, [P, P, I64, I64, P, C.POINTER(C.c_float), P]),
     "loc_predict": (C.c_int, [P, P, I64, I64, P, P]),

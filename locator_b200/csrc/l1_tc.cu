@@ -868,6 +868,28 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   if (warp == B_EPI_WARPS) tmem_dealloc(tmem, 512);
 }
 
+// Pulls the first n_chunks chunks (W1 | m | v, 24 KB each) of every CTA's walk of the NEXT backward launch into
+// L2 (cp.async.bulk.prefetch.L2): HBM idles while the latency-bound hidden stack runs, and what is already in
+// L2 when the backward streams it costs no DRAM read then.  Same tile split and walk direction as k_l1_bwd_tc.
+__global__ void __launch_bounds__(32, 1) k_l1_prefetch(L1Args a, int64_t ntiles, int skip_chunks, int n_chunks, int t_ahead) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (a.gated && a.st->stopped) return;
+  if (threadIdx.x != 0) return;
+  const int64_t t_begin = ntiles * blockIdx.x / gridDim.x;
+  const int64_t t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+  const int nloc = (int)(t_end - t_begin);
+  const int nchunks = nloc * (B_NT / B_CH);
+  const bool rev = a.alternate && ((a.st->t + t_ahead) & 1);
+  for (int c = skip_chunks; c < skip_chunks + n_chunks && c < nchunks; ++c) {
+    const int li = c >> 3;
+    const int64_t tile = t_begin + (rev ? nloc - 1 - li : li);
+    const int64_t off = (tile * B_NT + (int64_t)(c & 7) * B_CH) * kH;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.W1 + off), "r"((uint32_t)B_ARR) : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.mW1 + off), "r"((uint32_t)B_ARR) : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.vW1 + off), "r"((uint32_t)B_ARR) : "memory");
+  }
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
@@ -905,6 +927,15 @@ int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s) {
   }
   const int64_t ntiles = cdiv(a.K, tc::B_NT);
   tc::k_l1_fwd_tc<<<n_partials, tc::F_THREADS, tc::F_SMEM, s>>>(a, ntiles);
+  LOC_LAUNCHED();
+  return 0;
+}
+
+int l1_prefetch_tc(const L1Args& a, int nblocks, int skip_chunks, int n_chunks, int t_ahead, cudaStream_t s) {
+  const int64_t ntiles = cdiv(a.K, tc::B_NT);
+  int64_t grid = ntiles < tc_sm_count() ? ntiles : tc_sm_count();
+  if (nblocks > 0 && nblocks < grid) grid = nblocks;
+  tc::k_l1_prefetch<<<(unsigned)grid, 32, 0, s>>>(a, ntiles, skip_chunks, n_chunks, t_ahead);
   LOC_LAUNCHED();
   return 0;
 }

@@ -281,6 +281,7 @@ static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated
 }
 
 static int forward_l1(loc_model* m, const L1Args& a, cudaStream_t s) {
+  m->span_perm = nullptr;  // a standalone forward overwrites the tiles a loc_train_steps span may have left
   return m->use_tc ? l1_forward_tc(a, m->n_partials, s) : l1_forward_simt(a, m->n_partials, s);
 }
 
@@ -691,6 +692,7 @@ int loc_model_set_dropout_masks(loc_model* m, const uint8_t* d_keep, int64_t nst
 int loc_train_step(loc_model* m, const int32_t* d_rows, int32_t nb, void* stream) {
   LOC_CHECK(m != nullptr && m->train_packed != nullptr, "loc_train_step: no training data bound");
   LOC_CHECK(d_rows != nullptr && nb >= 1 && nb <= m->B, "loc_train_step: bad batch");
+  m->span_perm = nullptr;
   RowSrc src;
   src.rows = d_rows;
   src.epoch_stride = 0;
@@ -702,7 +704,8 @@ int loc_train_step(loc_model* m, const int32_t* d_rows, int32_t nb, void* stream
 
 int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t nb, void* stream) {
   LOC_CHECK(m != nullptr && m->train_packed != nullptr, "loc_debug_stage: no training data bound");
-  LOC_CHECK(stage >= 0 && stage < 5 && d_rows != nullptr && nb >= 1 && nb <= m->B, "loc_debug_stage: bad arguments");
+  LOC_CHECK(stage >= 0 && stage < 6 && d_rows != nullptr && nb >= 1 && nb <= m->B, "loc_debug_stage: bad arguments");
+  m->span_perm = nullptr;
   RowSrc src;
   src.rows = d_rows;
   src.epoch_stride = 0;
@@ -710,6 +713,13 @@ int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t 
   src.row0 = 0;
   src.nb = nb;
   if (stage == 4) return train_step(m, src, 0, (cudaStream_t)stream, 4, &src);  // backward + fused next forward
+  if (stage == 5) {  // L2 prefetch of the next backward's head: LOC_PREFETCH="skip,count" chunks per CTA
+    LOC_CHECK(m->use_tc, "loc_debug_stage: stage 5 needs the tcgen05 first layer");
+    int skip = 0, cnt = 16;
+    if (const char* e = getenv("LOC_PREFETCH")) sscanf(e, "%d,%d", &skip, &cnt);
+    L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, 0);
+    return l1_prefetch_tc(a, m->n_bwd_blocks, skip, cnt, 0, (cudaStream_t)stream);
+  }
   return train_step(m, src, 0, (cudaStream_t)stream, 1 << stage);
 }
 
@@ -876,36 +886,74 @@ int64_t loc_debug_read(loc_model* m, int32_t which, float* h_dst, int64_t max_n,
   return n;
 }
 
-int loc_train_epochs(loc_model* m, const int32_t* d_perms, int32_t n_epochs, void* stream) {
-  LOC_CHECK(m != nullptr && m->train_packed != nullptr && m->val_packed != nullptr,
-            "loc_train_epochs: training and validation data must be bound");
-  LOC_CHECK(d_perms != nullptr && n_epochs >= 1, "loc_train_epochs: bad arguments");
-  cudaStream_t s = (cudaStream_t)stream;
-  k_begin_call<<<1, 1, 0, s>>>(m->st);
-  LOC_LAUNCHED();
+// Steps [step0, step0 + nsteps) of one epoch (batch order `perm`, or perm + (epoch - epoch0) * epoch_stride when the
+// device-side epoch counter selects the row of a multi-epoch order).  Inside an epoch every backward also runs
+// the NEXT step's first-layer forward (tcgen05 path), so only a span that starts without such a forward
+// launches one of its own.  *have_fwd: in = the tiles of step0 are already there; out = those of the step
+// after the span are.
+static int run_span(loc_model* m, const int32_t* perm, int64_t epoch_stride, int64_t step0, int64_t nsteps, int gated,
+                    bool* have_fwd, cudaStream_t s) {
   const bool fuse = m->use_tc && getenv("LOC_NO_FUSE") == nullptr;
   auto step_rows = [&](int64_t off) {
     RowSrc src;
-    src.rows = d_perms;
-    src.epoch_stride = m->n_train;
+    src.rows = perm;
+    src.epoch_stride = epoch_stride;
     src.offset = off;
     src.row0 = 0;
     src.nb = (int32_t)((m->n_train - off) < m->B ? (m->n_train - off) : m->B);
     return src;
   };
+  for (int64_t st = step0; st < step0 + nsteps; ++st) {
+    const int64_t off = st * m->B;
+    const RowSrc src = step_rows(off);
+    const bool has_next = fuse && off + m->B < m->n_train;  // within the epoch (the validation pass reuses the tiles)
+    const RowSrc next = has_next ? step_rows(off + m->B) : src;
+    if (train_step(m, src, gated, s, 15, has_next ? &next : nullptr, *have_fwd)) return 1;
+    *have_fwd = has_next;
+  }
+  return 0;
+}
+
+static int end_epoch(loc_model* m, cudaStream_t s) {
+  if (infer_rows(m, m->val_packed, m->n_val, m->val_row_words, m->val_locs, nullptr, 1, s)) return 1;
+  k_epoch_end<<<1, 1, 0, s>>>(m->st, m->hist);
+  LOC_LAUNCHED();
+  return copy_weights(m, true, &m->st->improved, s);
+}
+
+int loc_train_epochs(loc_model* m, const int32_t* d_perms, int32_t n_epochs, void* stream) {
+  LOC_CHECK(m != nullptr && m->train_packed != nullptr && m->val_packed != nullptr,
+            "loc_train_epochs: training and validation data must be bound");
+  LOC_CHECK(d_perms != nullptr && n_epochs >= 1, "loc_train_epochs: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  m->span_perm = nullptr;
+  k_begin_call<<<1, 1, 0, s>>>(m->st);
+  LOC_LAUNCHED();
+  const int64_t spe = cdiv(m->n_train, m->B);
   for (int e = 0; e < n_epochs; ++e) {
     bool have_fwd = false;  // the previous step's backward already left this step's Z1 partial tiles
-    for (int64_t off = 0; off < m->n_train; off += m->B) {
-      const RowSrc src = step_rows(off);
-      const bool has_next = fuse && off + m->B < m->n_train;  // within the epoch (the validation pass reuses the tiles)
-      const RowSrc next = has_next ? step_rows(off + m->B) : src;
-      if (train_step(m, src, 1, s, 15, has_next ? &next : nullptr, have_fwd)) return 1;
-      have_fwd = has_next;
-    }
-    if (infer_rows(m, m->val_packed, m->n_val, m->val_row_words, m->val_locs, nullptr, 1, s)) return 1;
-    k_epoch_end<<<1, 1, 0, s>>>(m->st, m->hist);
-    LOC_LAUNCHED();
-    if (copy_weights(m, true, &m->st->improved, s)) return 1;
+    if (run_span(m, d_perms, m->n_train, 0, spe, 1, &have_fwd, s)) return 1;
+    if (end_epoch(m, s)) return 1;
+  }
+  return 0;
+}
+
+int loc_train_steps(loc_model* m, const int32_t* d_perm, int32_t step0, int32_t n_steps, void* stream) {
+  LOC_CHECK(m != nullptr && m->train_packed != nullptr, "loc_train_steps: no training data bound");
+  const int64_t spe = m != nullptr ? cdiv(m->n_train, m->B) : 0;
+  LOC_CHECK(d_perm != nullptr && step0 >= 0 && n_steps >= 1 && (int64_t)step0 + n_steps <= spe,
+            "loc_train_steps: the span must lie inside one epoch");
+  const bool ends_epoch = (int64_t)step0 + n_steps == spe;
+  LOC_CHECK(!ends_epoch || m->val_packed != nullptr, "loc_train_steps: a span that ends the epoch needs validation data");
+  cudaStream_t s = (cudaStream_t)stream;
+  // continuing the span of the previous call: its last backward already ran this span's first forward
+  bool have_fwd = step0 > 0 && m->span_perm == d_perm && m->span_next == step0;
+  m->span_perm = nullptr;
+  if (run_span(m, d_perm, 0, step0, n_steps, 0, &have_fwd, s)) return 1;
+  if (ends_epoch) return end_epoch(m, s);
+  if (have_fwd) {
+    m->span_perm = d_perm;
+    m->span_next = (int64_t)step0 + n_steps;
   }
   return 0;
 }

@@ -148,6 +148,9 @@ bool l1_tc_supported(int64_t K, int H);
 int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s);
 int l1_backward_tc(const L1Args& a, int nblocks, cudaStream_t s, bool overlap_previous = false);
 int l1_tc_partials(int64_t K);
+// L2 prefetch of the head of the next backward's walk (chunks [skip, skip + n) of every CTA; t_ahead: optimizer
+// steps between now and that backward -- decides the walk direction)
+int l1_prefetch_tc(const L1Args& a, int nblocks, int skip_chunks, int n_chunks, int t_ahead, cudaStream_t s);
 
 }  // namespace loc
 
@@ -221,4 +224,7 @@ struct loc_model {
   void* exchange_ctx;
   float* z1_tile;  // caller-owned [kMaxB][H]: own partial sum, then the sum over shards
   struct loc_tp* tp;  // peer-memory exchange (tp.cu) instead of the host hook
+  // loc_train_steps: the last span left the forward tiles of step span_next of the epoch ordered by span_perm
+  const int32_t* span_perm;
+  int64_t span_next;
 };

@@ -94,8 +94,8 @@ def build_parser():
     parser.add_argument("--gpus", default=1, type=int,
                         help="(locator_b200) GPUs of this box to spread --bootstrap / --windows replicates over. default: 1")
     parser.add_argument("--replicates_per_gpu", default=4, type=int,
-                        help="(locator_b200) bootstrap / window models trained side by side on each GPU (1-8; the indices "
-                        "never depend on it, and predictions are identical for every value >= 2). default: 4")
+                        help="(locator_b200) bootstrap / window models trained side by side on each GPU (1-8; neither "
+                        "the indices nor the predictions depend on it). default: 4")
     return parser
 
 
@@ -300,13 +300,13 @@ def load_network(traingen, dropout_prop):
     from .model import LocatorModel, spare_cluster_l1_ctas
 
     K = traingen.shape[1] if hasattr(traingen, "shape") else traingen.K
-    # Replicate runs that train several models per GPU side by side keep one cluster's worth of SMs free of the
-    # first-layer kernels, so that one model's hidden stack overlaps another's weight stream (ring schedule of
-    # loc_group_train_epochs).  The CTA count fixes the fp32 summation order of the layer, hence the same
-    # setting for every model of such a run, grouped or not.
+    # Replicate runs (--bootstrap / --windows) train several models per GPU side by side and keep one cluster's
+    # worth of SMs free of the first-layer kernels, so that one model's hidden stack overlaps another's weight
+    # stream (ring schedule of loc_group_train_epochs).  The CTA count fixes the fp32 summation order of the
+    # layer, hence the same setting for EVERY model of such a run whatever --replicates_per_gpu / --gpus say:
+    # the outputs of a replicate run never depend on how it was scheduled.
     # (Only where the weight stream outlasts the hidden stack: RING_MIN_SNPS mirrors kRingMinK of the library.)
-    grouped = (args.bootstrap or args.windows) and int(getattr(args, "replicates_per_gpu", 1) or 1) >= 2 \
-        and K >= RING_MIN_SNPS
+    grouped = (args.bootstrap or args.windows) and K >= RING_MIN_SNPS
     return LocatorModel(K, width=args.width, nlayers=args.nlayers, dropout_prop=args.dropout_prop,
                         batch_size=args.batch_size, max_epochs=args.max_epochs, seed=_model_seed(),
                         l1_ctas=spare_cluster_l1_ctas() if grouped else None)

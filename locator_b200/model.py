@@ -246,6 +246,16 @@ class LocatorModel:
         self._keep.setdefault("perms", []).append(p)
         check(lib.loc_train_epochs(self._h, p.data_ptr(), int(p.shape[0]), _stream()), "loc_train_epochs")
 
+    def train_steps(self, perm, step0, n_steps):
+        """Steps [step0, step0 + n_steps) of the epoch ordered by ``perm`` (a device int32 tensor from a previous
+        call, or anything array-like of length n_train) on the production schedule; returns the device tensor
+        so that a following call can continue the same epoch (loc_train_steps)."""
+        self._wver += 1
+        p = perm if isinstance(perm, torch.Tensor) else _as_dev(np.asarray(perm, dtype=np.int32), torch.int32)
+        self._keep["span_perm"] = p
+        check(lib.loc_train_steps(self._h, p.data_ptr(), int(step0), int(n_steps), _stream()), "loc_train_steps")
+        return p
+
     def history_rows(self, n):
         a = np.zeros((max(n, 1), 3), dtype=np.float32)
         if n > 0:

@@ -214,6 +214,93 @@ def _resolve(runner):
     return getattr(importlib.import_module(mod), fn)
 
 
+def serve(L, base, take_group, queue_is_deep, done, who="worker"):
+    """The serving loop of one GPU: take a group of work items, prepare it (helper thread, side stream), train
+    and predict it; while the queue is deep the NEXT group is taken and prepared meanwhile.
+
+    take_group(block) -> list of items, or None when there is nothing (block=False) / the queue has ended;
+    queue_is_deep() -> prefetching cannot starve another GPU; done(items) reports completion.
+    Shared by the worker processes of ``locator --gpus N`` (ReplicatePool) and by the ranks of a
+    torch.distributed job (RankQueue)."""
+    pf = Prefetcher(L, base)
+    try:
+        ahead = None
+        while True:
+            if ahead is None:
+                items = take_group(True)
+                if items is None:
+                    break
+                fut = pf.submit(items)
+            else:
+                items, fut = ahead
+                ahead = None
+            if queue_is_deep():
+                nxt = take_group(False)
+                if nxt is not None:
+                    ahead = (nxt, pf.submit(nxt))
+            _tick(f"{who}: group of {len(items)} taken")
+            reps = Prefetcher.collect(fut)
+            _tick(f"{who}: group prepared")
+            _run_items(L, items, base, reps)
+            _tick(f"{who}: group done")
+            done(items)
+    finally:
+        pf.close()
+
+
+class RankQueue:
+    """Work queue for the ranks of ONE torch.distributed job (``torchrun --nproc-per-node N``, one rank per
+    GPU): the items are known to every rank (they are drawn deterministically from --seed), and a single
+    atomic counter in the job's key-value store hands out their indices -- no collective, no tensor traffic.
+    Group sizes shrink towards the end of the queue (guided self-scheduling: about remaining / ranks items,
+    at most `group`) so that the last round does not leave GPUs idle behind one full group.
+    store = None: a single process (world 1) with a local counter."""
+
+    def __init__(self, items, world=1, store=None, key="loc_queue", group=4):
+        self.items, self.world, self.store, self.key = list(items), max(1, int(world)), store, key
+        self.group = max(1, int(group))
+        self._local = 0
+        self.taken = []
+
+    def _next(self):
+        if self.store is None:
+            self._local += 1
+            return self._local - 1
+        return int(self.store.add(self.key, 1)) - 1
+
+    def take_group(self, block=True):
+        n = len(self.items)
+        first = self._next()
+        if first >= n:
+            return None
+        remaining = n - first  # items not yet handed out, this one included
+        want = max(1, min(self.group, -(-remaining // self.world)))
+        idx = [first]
+        while len(idx) < want:
+            i = self._next()
+            if i >= n:
+                break
+            idx.append(i)
+        self.taken.append(idx)
+        return [self.items[i] for i in idx]
+
+    def queue_is_deep(self):
+        """Prefetch only while every rank could still take a full group after this one."""
+        if self.store is None:
+            done = self._local
+        else:
+            done = int(self.store.add(self.key, 0))
+        return len(self.items) - done >= self.world * self.group
+
+
+def run_items_ranked(L, base, items, world=1, store=None, key="loc_queue"):
+    """Rank mode of the replicate drivers: this process (one GPU) serves `items` together with the other
+    ranks of the job.  Returns the indices this rank ran, in groups."""
+    q = RankQueue(items, world, store, key, _group_size(L.args))
+    serve(L, base, q.take_group, q.queue_is_deep, lambda its: None, who=f"rank {os.environ.get('RANK', '0')}")
+    return q.taken
+
+
 def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None, init_q=None):
     try:
         if runner is not None:  # host-logic tests: no CUDA, the runner consumes the raw item
@@ -287,33 +374,16 @@ def _worker(rank, n_gpus, args, base_host, task_q, result_q, runner=None, init_q
             except NotImplementedError:
                 return False
 
-        pf = Prefetcher(L, base)
-        ahead = None
-        while True:
-            if ahead is None:
-                items = take_group(block=True)
-                if items is None:
-                    break
-                fut = pf.submit(items)
-            else:
-                items, fut = ahead
-                ahead = None
-            if queue_is_deep():
-                nxt = take_group(block=False)
-                if nxt is not None:
-                    ahead = (nxt, pf.submit(nxt))
-            _tick(f"worker {rank}: group of {len(items)} taken")
-            reps = Prefetcher.collect(fut)
-            _tick(f"worker {rank}: group prepared")
-            _run_items(L, items, base, reps)
-            _tick(f"worker {rank}: group done")
+        def done(items):
             for it in items:
                 result_q.put(("done", rank, it.get("boot", it.get("index"))))
-        pf.close()
+
+        serve(L, base, take_group, queue_is_deep, done, who=f"worker {rank}")
         _tick(f"worker {rank}: exiting")
         result_q.put(("exit", rank, None))
-    except Exception:  # surface the failure in the parent instead of hanging the queue
+    except BaseException:  # surface the failure (SystemExit / KeyboardInterrupt included) in the parent
         result_q.put(("error", rank, traceback.format_exc()))
+        raise
 
 
 class ReplicatePool:
@@ -374,14 +444,27 @@ class ReplicatePool:
         _tick("parent: all items submitted, waiting for the workers")
         for _ in self.procs:
             self.task_q.put(None)
+        import queue as _queue
+
         done = exited = 0
         errors = []
+        exited_ranks = set()
         while exited < self.n and not errors:
-            kind, rank, payload = self.result_q.get()
+            try:
+                kind, rank, payload = self.result_q.get(timeout=2.0)
+            except _queue.Empty:
+                # a worker that died without a message (SIGSEGV / abort inside the CUDA library, a device-side
+                # assert, the OOM killer) would leave this loop waiting forever
+                for r, p in enumerate(self.procs):
+                    if r not in exited_ranks and not p.is_alive():
+                        errors.append((r, f"worker process exited with code {p.exitcode} without reporting"))
+                        break
+                continue
             if kind == "done":
                 done += 1
             elif kind == "exit":
                 exited += 1
+                exited_ranks.add(rank)
             else:
                 errors.append((rank, payload))
         for p in self.procs:

@@ -151,11 +151,13 @@ class RefLocator:
         gW[L] = acts[L].T @ dy1
         gb[L] = dy1.sum(0)
         dh = dy1 @ self.W[L].T
+        dzs = [None] * L
         for i in range(L - 1, -1, -1):
             if i == self.n_before - 1 and self.p > 0:
                 dh = dh * c["keep"] * np.float32(1.0 / (1.0 - self.p))
             z = zs[i]
             dz = torch.where(z > 0, dh, dh * torch.exp(z))  # EluGrad: (out+1)*g for out<0
+            dzs[i] = dz
             gW[i] = acts[i].T @ dz
             gb[i] = dz.sum(0)
             dh = dz @ self.W[i].T
@@ -166,6 +168,7 @@ class RefLocator:
         grads = [ggamma, gbeta]
         for w, b in zip(gW, gb):
             grads += [w, b]
+        c["dzs"] = dzs  # d loss / d z_i per Dense(width) layer (tests compare dzs[0] with the device's dZ1)
         return float(loss), grads, c
 
     def train_step(self, x_u8, y, mask=None):

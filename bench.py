@@ -252,7 +252,18 @@ def work_queue_leg(rank, world, store, barrier, n_total, K, group):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record()
+        prof = None
+        if os.environ.get("LOC_BENCH_PROFILE"):  # where does the host side of the queue spend its time?
+            import cProfile
+
+            prof = cProfile.Profile()
+            prof.enable()
         taken = replicates.run_items_ranked(Lmod, base, items, world, store, key="bench_cfg4")
+        if prof is not None:
+            import pstats
+
+            prof.disable()
+            pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
         ev1.record()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0

@@ -83,6 +83,23 @@ int loc_site_stats(const int8_t* d_gt, int64_t nvar, int64_t nsamp, int32_t min_
                    int32_t* d_n_alleles, int32_t* d_alt_count, int32_t* d_n_missing,
                    uint8_t* d_keep, void* stream);
 
+/* The kept sites in ascending order, on the device: d_site_idx[0 .. *d_count) = { v : d_keep[v] != 0 },
+ * *d_count (device int64) = their number.  d_site_idx needs room for nvar entries.  The reference builds the
+ * same list on the host (boolean-mask indexing of the genotype array, locator.py:269,273).  Async. */
+int loc_compact_sites(const uint8_t* d_keep, int64_t nvar, int64_t* d_site_idx, int64_t* d_count, void* stream);
+
+/* Missing calls of the kept sites in row-major (site, sample) order -- np.nonzero(is_missing), the order in which
+ * replace_md draws its imputed values (locator.py:255-261).  Two phases:
+ *   d_k == NULL: d_offsets[0 .. K] = exclusive prefix sums of d_n_missing[d_site_idx[k]] (d_offsets[K] = total);
+ *   otherwise  : d_k[i] = kept-site index k, d_samp[i] = sample of missing call i, i < d_offsets[K].
+ * d_n_missing is loc_site_stats' output over all nvar sites.  Async. */
+int loc_missing_calls(const int8_t* d_gt, int64_t nvar, int64_t nsamp, const int64_t* d_site_idx, int64_t K,
+                      const int32_t* d_n_missing, int64_t* d_offsets, int64_t* d_k, int64_t* d_samp, void* stream);
+
+/* d_sums[k] = sum over the n rows of the packed matrix of SNP k's allele count (int64; jacknife allele
+ * frequencies over ALL samples, locator.py:714-717).  Async. */
+int loc_site_sums(const uint32_t* d_packed, int64_t n, int64_t K, int64_t row_words, int64_t* d_sums, void* stream);
+
 /* Pack the K sites d_site_idx[0..K) of d_gt into the 2-bit sample-major matrix:
  * genotype = number of index-1 alleles of the call (missing/other alleles count 0)
  * -- GenotypeArray.to_allele_counts()[:, :, 1], locator.py:277. */

@@ -46,6 +46,9 @@ SIGNATURES = {
     "loc_launch_count": (I64, []),
     "loc_site_stats": (C.c_int, [P, I64, I64, I32, P, P, P, P, P]),
     "loc_pack_sites": (C.c_int, [P, I64, I64, P, I64, P, I64, P]),
+    "loc_compact_sites": (C.c_int, [P, I64, P, P, P]),
+    "loc_missing_calls": (C.c_int, [P, I64, I64, P, I64, P, P, P, P, P]),
+    "loc_site_sums": (C.c_int, [P, I64, I64, I64, P, P]),
     "loc_patch_calls": (C.c_int, [P, I64, P, P, P, I64, P]),
     "loc_pack_counts": (C.c_int, [P, I64, I64, P, I64, P]),
     "loc_unpack_counts": (C.c_int, [P, I64, I64, I64, P, P]),

@@ -284,6 +284,171 @@ __global__ void k_replace_cols(uint32_t* __restrict__ packed, int64_t n, int64_t
   atomicOr(wp, ((uint32_t)vals[i * n + r] & 3u) << sh);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ordered compaction on the device (no host round trip of the masks): exclusive prefix sums over
+// per-site counts in three launches -- per-block totals, one block scanning the totals, per-block
+// rescan + scatter.  Values: keep flags (site filter) or missing calls per kept site (imputation).
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256, kScanPer = 8, kScanBlock = kScanThreads * kScanPer;
+
+struct ScanSrc {
+  const uint8_t* keep;         // mode 0: value = keep[i]
+  const int32_t* per_site;     // mode 1: value = per_site[site_idx[i]]
+  const int64_t* site_idx;
+};
+__device__ __forceinline__ int scan_value(const ScanSrc& s, int64_t i, int64_t n) {
+  if (i >= n) return 0;
+  return s.keep != nullptr ? (int)(s.keep[i] != 0) : s.per_site[s.site_idx[i]];
+}
+
+// block-wide exclusive scan of one int per thread; returns the prefix, *total = block sum (all threads)
+__device__ __forceinline__ long long block_exclusive(long long v, long long* total) {
+  __shared__ long long wsum[kScanThreads / 32];
+  __shared__ long long tot;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // wsum / tot of a previous call are no longer read
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    long long x = lane < kScanThreads / 32 ? wsum[lane] : 0;
+    long long xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) xi += t;
+    }
+    if (lane < kScanThreads / 32) wsum[lane] = xi - x;
+    if (lane == 31) tot = xi;
+  }
+  __syncthreads();
+  *total = tot;
+  return wsum[w] + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_totals(ScanSrc src, int64_t n, long long* block_tot) {
+  const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanPer;
+  long long v = 0;
+#pragma unroll
+  for (int e = 0; e < kScanPer; ++e) v += scan_value(src, base + e, n);
+  long long total;
+  block_exclusive(v, &total);
+  if (threadIdx.x == 0) block_tot[blockIdx.x] = total;
+}
+
+// one block: block_tot[b] -> exclusive prefix (in place), grand total to *count
+__global__ void __launch_bounds__(kScanThreads) k_scan_blocks(long long* block_tot, int64_t nblocks, int64_t* count) {
+  long long carry = 0;
+  for (int64_t b0 = 0; b0 < nblocks; b0 += kScanThreads) {
+    const int64_t b = b0 + threadIdx.x;
+    const long long v = b < nblocks ? block_tot[b] : 0;
+    long long total;
+    const long long ex = block_exclusive(v, &total);
+    if (b < nblocks) block_tot[b] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *count = carry;
+}
+
+// mode 0: site_idx_out[prefix] = i for kept sites.
+__global__ void __launch_bounds__(kScanThreads) k_compact_sites(ScanSrc src, int64_t n, const long long* block_off,
+                                                                int64_t* __restrict__ out) {
+  const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanPer;
+  int f[kScanPer];
+  long long v = 0;
+#pragma unroll
+  for (int e = 0; e < kScanPer; ++e) {
+    f[e] = scan_value(src, base + e, n);
+    v += f[e];
+  }
+  long long total;
+  long long pos = block_off[blockIdx.x] + block_exclusive(v, &total);
+#pragma unroll
+  for (int e = 0; e < kScanPer; ++e)
+    if (f[e]) out[pos++] = base + e;
+}
+
+// mode 1: offsets[i] = exclusive prefix of the missing calls of kept site i (offsets[K] is the total, written
+// by the caller from *count).
+__global__ void __launch_bounds__(kScanThreads) k_scan_offsets(ScanSrc src, int64_t n, const long long* block_off,
+                                                               int64_t* __restrict__ offsets) {
+  const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanPer;
+  int f[kScanPer];
+  long long v = 0;
+#pragma unroll
+  for (int e = 0; e < kScanPer; ++e) {
+    f[e] = scan_value(src, base + e, n);
+    v += f[e];
+  }
+  long long total;
+  long long pos = block_off[blockIdx.x] + block_exclusive(v, &total);
+#pragma unroll
+  for (int e = 0; e < kScanPer; ++e) {
+    if (base + e < n) offsets[base + e] = pos;
+    pos += f[e];
+  }
+}
+
+// One warp per kept site with missing calls: (k, sample) of every missing call in ascending sample order, at the
+// site's offset -- np.nonzero(is_missing) in row-major (site, sample) order, the order replace_md draws in
+// (locator.py:258-261) -- plus the site's allele frequency inputs are already in alt_count / n_missing.
+__global__ void __launch_bounds__(256) k_missing_calls(const int8_t* __restrict__ gt, int64_t nsamp,
+                                                       const int64_t* __restrict__ site_idx, int64_t K,
+                                                       const int64_t* __restrict__ offsets, int64_t* __restrict__ out_k,
+                                                       int64_t* __restrict__ out_samp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t k = warp; k < K; k += nwarps) {
+    const int64_t beg = offsets[k], end = offsets[k + 1];
+    if (beg == end) continue;
+    const int8_t* row = gt + site_idx[k] * nsamp * 2;
+    int64_t pos = beg;
+    for (int64_t s0 = 0; s0 < nsamp && pos < end; s0 += 32) {
+      const int64_t sidx = s0 + lane;
+      bool miss = false;
+      if (sidx < nsamp) {
+        const char2 c = *reinterpret_cast<const char2*>(row + 2 * sidx);
+        miss = c.x < 0 || c.y < 0;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, miss);
+      if (miss) {
+        const int64_t o = pos + __popc(m & ((1u << lane) - 1u));
+        out_k[o] = k;
+        out_samp[o] = sidx;
+      }
+      pos += __popc(m);
+    }
+  }
+}
+
+// sums[k] = sum over all n rows of the packed counts of SNP k (jacknife allele frequencies, locator.py:714-717,
+// with wide integers: the reference's pinned numpy promotes the uint8 row sums).  One thread per packed word
+// (16 SNPs), rows in the loop: a warp reads 128 contiguous bytes per row.
+__global__ void __launch_bounds__(128) k_site_sums(const uint32_t* __restrict__ packed, int64_t n, int64_t K,
+                                                   int64_t row_words, int64_t* __restrict__ sums) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w * 16 >= K) return;
+  // two 16 x 4-bit... plain counters: 16 ints per thread, rows split over blockIdx.y slabs and added atomically
+  const int64_t r0 = n * blockIdx.y / gridDim.y, r1 = n * (blockIdx.y + 1) / gridDim.y;
+  uint32_t lo[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) lo[q] = 0u;
+  for (int64_t r = r0; r < r1; ++r) {
+    const uint32_t x = __ldg(packed + r * row_words + w);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) lo[q] += (x >> (2 * q)) & 3u;
+  }
+#pragma unroll
+  for (int q = 0; q < 16; ++q)
+    if (w * 16 + q < K && lo[q]) atomicAdd(reinterpret_cast<unsigned long long*>(sums + w * 16 + q), (unsigned long long)lo[q]);
+}
+
 }  // namespace loc
 
 using namespace loc;
@@ -312,6 +477,78 @@ int loc_site_stats(const int8_t* d_gt, int64_t nvar, int64_t nsamp, int32_t min_
   if (blocks > wave) blocks = wave;
   k_site_stats<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_gt, nvar, nsamp, min_mac, d_n_alleles,
                                                                  d_alt_count, d_n_missing, d_keep);
+  LOC_LAUNCHED();
+  return 0;
+}
+
+
+static int scan_launch(const ScanSrc& src, int64_t n, int64_t* d_count, long long** block_off_out, cudaStream_t st) {
+  const int64_t nblocks = cdiv(n, kScanBlock);
+  long long* block_off = nullptr;
+  LOC_CUDA(cudaMallocAsync(&block_off, (size_t)(nblocks > 0 ? nblocks : 1) * sizeof(long long), st));
+  if (nblocks > 0) {
+    k_scan_totals<<<(unsigned)nblocks, kScanThreads, 0, st>>>(src, n, block_off);
+    LOC_LAUNCHED();
+  }
+  k_scan_blocks<<<1, kScanThreads, 0, st>>>(block_off, nblocks, d_count);
+  LOC_LAUNCHED();
+  *block_off_out = block_off;
+  return 0;
+}
+
+int loc_compact_sites(const uint8_t* d_keep, int64_t nvar, int64_t* d_site_idx, int64_t* d_count, void* stream) {
+  LOC_CHECK(nvar >= 0 && d_count != nullptr, "loc_compact_sites: bad arguments");
+  LOC_CHECK(nvar == 0 || (d_keep != nullptr && d_site_idx != nullptr), "loc_compact_sites: null pointer");
+  LOC_CHECK(nvar <= (int64_t)kScanBlock * 0x7fffffff, "loc_compact_sites: too many sites");
+  cudaStream_t st = (cudaStream_t)stream;
+  ScanSrc src = {d_keep, nullptr, nullptr};
+  long long* block_off = nullptr;
+  if (scan_launch(src, nvar, d_count, &block_off, st)) return 1;
+  if (nvar > 0) {
+    k_compact_sites<<<(unsigned)cdiv(nvar, kScanBlock), kScanThreads, 0, st>>>(src, nvar, block_off, d_site_idx);
+    LOC_LAUNCHED();
+  }
+  LOC_CUDA(cudaFreeAsync(block_off, st));
+  return 0;
+}
+
+int loc_missing_calls(const int8_t* d_gt, int64_t nvar, int64_t nsamp, const int64_t* d_site_idx, int64_t K,
+                      const int32_t* d_n_missing, int64_t* d_offsets, int64_t* d_k, int64_t* d_samp, void* stream) {
+  (void)nvar;
+  LOC_CHECK(K >= 0 && nsamp > 0 && d_offsets != nullptr, "loc_missing_calls: bad arguments");
+  LOC_CHECK(K == 0 || (d_gt != nullptr && d_site_idx != nullptr && d_n_missing != nullptr), "loc_missing_calls: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  ScanSrc src = {nullptr, d_n_missing, d_site_idx};
+  if (d_k == nullptr) {  // phase 1: offsets[0..K] (offsets[K] = number of missing calls)
+    long long* block_off = nullptr;
+    if (scan_launch(src, K, d_offsets + K, &block_off, st)) return 1;
+    if (K > 0) {
+      k_scan_offsets<<<(unsigned)cdiv(K, kScanBlock), kScanThreads, 0, st>>>(src, K, block_off, d_offsets);
+      LOC_LAUNCHED();
+    }
+    LOC_CUDA(cudaFreeAsync(block_off, st));
+    return 0;
+  }
+  LOC_CHECK(d_samp != nullptr, "loc_missing_calls: null output pointer");
+  if (K == 0) return 0;
+  int64_t blocks = cdiv(K, 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_missing_calls<<<(unsigned)blocks, 256, 0, st>>>(d_gt, nsamp, d_site_idx, K, d_offsets, d_k, d_samp);
+  LOC_LAUNCHED();
+  return 0;
+}
+
+int loc_site_sums(const uint32_t* d_packed, int64_t n, int64_t K, int64_t row_words, int64_t* d_sums, void* stream) {
+  LOC_CHECK(n >= 0 && K >= 0 && row_words >= cdiv(K, 16), "loc_site_sums: bad shape");
+  if (K == 0) return 0;
+  LOC_CHECK(d_sums != nullptr && (n == 0 || d_packed != nullptr), "loc_site_sums: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  LOC_CUDA(cudaMemsetAsync(d_sums, 0, (size_t)K * sizeof(int64_t), st));
+  if (n == 0) return 0;
+  const int64_t words = cdiv(K, 16);
+  int slabs = (int)(n < 16 ? n : 16);  // enough blocks to fill the SMs when K is small
+  dim3 grid((unsigned)cdiv(words, 128), (unsigned)slabs);
+  k_site_sums<<<grid, 128, 0, st>>>(d_packed, n, K, row_words, d_sums);
   LOC_LAUNCHED();
   return 0;
 }

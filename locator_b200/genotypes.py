@@ -117,6 +117,12 @@ class PackedGenotypes:
                                       out.words[r0:r1].data_ptr(), out.row_words, _stream()), "loc_gather_cols")
         return out
 
+    def site_sums(self) -> torch.Tensor:
+        """int64 [K] device tensor: sum over all rows of every SNP's allele count (locator.py:714-717)."""
+        out = torch.empty(max(self.K, 1), dtype=torch.int64, device=self.words.device)
+        check(lib.loc_site_sums(self.ptr, self.n, self.K, self.row_words, out.data_ptr(), _stream()), "loc_site_sums")
+        return out[: self.K]
+
     def clone(self) -> "PackedGenotypes":
         return PackedGenotypes(self.words.clone(), self.n, self.K)
 
@@ -208,6 +214,34 @@ def site_stats(gt, min_mac=2):
     check(lib.loc_site_stats(g.data_ptr(), nvar, N, int(min_mac), na.data_ptr(), alt.data_ptr(), miss.data_ptr(),
                              keep.data_ptr(), _stream()), "loc_site_stats")
     return g, na, alt, miss, keep
+
+
+def compact_sites(keep: torch.Tensor) -> torch.Tensor:
+    """Ascending indices of the kept sites as an int64 device tensor (prefix sum + scatter on the GPU; the only
+    thing the host reads is their number, which sizes the packed matrix)."""
+    nvar = int(keep.numel())
+    idx = torch.empty(max(nvar, 1), dtype=torch.int64, device=keep.device)
+    count = torch.zeros(1, dtype=torch.int64, device=keep.device)
+    check(lib.loc_compact_sites(keep.data_ptr(), nvar, idx.data_ptr(), count.data_ptr(), _stream()), "loc_compact_sites")
+    return idx[: int(count.item())]
+
+
+def missing_calls(g: torch.Tensor, site_idx: torch.Tensor, n_missing: torch.Tensor):
+    """(k, sample) of every missing call of the kept sites, row-major (site, sample) order, as int64 device
+    tensors -- np.nonzero(is_missing) of the filtered cube without touching it on the host."""
+    nvar, N, _ = g.shape
+    K = int(site_idx.numel())
+    offsets = torch.zeros(K + 1, dtype=torch.int64, device=g.device)
+    null = None
+    check(lib.loc_missing_calls(g.data_ptr(), nvar, N, site_idx.data_ptr(), K, n_missing.data_ptr(),
+                                offsets.data_ptr(), null, null, _stream()), "loc_missing_calls")
+    total = int(offsets[K].item())
+    ks = torch.empty(max(total, 1), dtype=torch.int64, device=g.device)
+    samps = torch.empty(max(total, 1), dtype=torch.int64, device=g.device)
+    if total:
+        check(lib.loc_missing_calls(g.data_ptr(), nvar, N, site_idx.data_ptr(), K, n_missing.data_ptr(),
+                                    offsets.data_ptr(), ks.data_ptr(), samps.data_ptr(), _stream()), "loc_missing_calls")
+    return ks[:total], samps[:total]
 
 
 def pack_sites(g: torch.Tensor, site_idx) -> PackedGenotypes:

@@ -106,6 +106,46 @@ def set_args(namespace):
     return args
 
 
+def validate_args(ns):
+    """Limits of this build, checked before any data is read (the reference accepts any value and fails -- or
+    not -- inside Keras).  Documented in INTEGRATION.md as deliberate deviations of the boundary."""
+    from ._cabi import lib  # noqa: F401  (fails loudly here when the CUDA library is missing)
+
+    problems = []
+    if not 1 <= int(ns.batch_size) <= 32:
+        problems.append(f"--batch_size {ns.batch_size}: this build's kernels hold one batch of at most 32 rows per step "
+                        "(the reference's default, 32, is supported; larger batches are not)")
+    if int(ns.width) < 32 or int(ns.width) > 1024 or int(ns.width) % 32:
+        problems.append(f"--width {ns.width}: must be a multiple of 32 in [32, 1024] (256, the default, runs on the "
+                        "tensor cores; other widths on the CUDA-core kernels)")
+    if not 2 <= int(ns.nlayers) <= 64:
+        problems.append(f"--nlayers {ns.nlayers}: must be in [2, 64]")
+    if not 0.0 <= float(ns.dropout_prop) < 1.0:
+        problems.append(f"--dropout_prop {ns.dropout_prop}: must be in [0, 1)")
+    if int(ns.max_epochs) < 1:
+        problems.append(f"--max_epochs {ns.max_epochs}: must be >= 1")
+    if int(ns.patience) < 0:
+        problems.append(f"--patience {ns.patience}: must be >= 0")
+    if not 1 <= int(getattr(ns, "replicates_per_gpu", 4) or 1) <= 8:
+        problems.append(f"--replicates_per_gpu {ns.replicates_per_gpu}: must be in [1, 8]")
+    if ns.windows:
+        # the reference takes int(args.window_start / _stop / _size) inside its loop (locator.py:524-531): a value
+        # such as "2e5" only fails there, after the genome has been read; here it fails now
+        for name in ("window_start", "window_stop", "window_size"):
+            v = getattr(ns, name)
+            if v is None:
+                continue
+            try:
+                iv = int(v)
+            except (TypeError, ValueError):
+                problems.append(f"--{name} {v!r}: not an integer (the reference calls int() on it)")
+                continue
+            if name == "window_size" and iv <= 0:
+                problems.append(f"--window_size {v!r}: must be positive")
+    if problems:
+        raise SystemExit("locator: " + "\n         ".join(problems))
+
+
 def _params_dict(ns):
     return {k: getattr(ns, k) for k in _REFERENCE_KEYS}
 
@@ -141,9 +181,7 @@ class AlleleCounts:
 
     def site_sums(self):
         """int64 [K]: sum over ALL samples of the allele counts (jacknife af, locator.py:714-717)."""
-        import torch
-
-        return self.packed.to_counts().sum(dim=0, dtype=torch.int64).cpu().numpy()
+        return self.packed.site_sums().cpu().numpy()
 
 
 def _matrix_shape(g):
@@ -191,29 +229,36 @@ def sort_samples(samples, genotypes):
     return sample_data, locs
 
 
-def replace_md(genotypes, keep_idx=None, packed=None):
+def replace_md(genotypes, stats=None):
     """Impute missing calls with binomial(2, site allele frequency) -- locator.py:250-262.
 
-    The scalar draws are taken from numpy's global stream in the reference's row-major
-    (site, sample) order; the imputed values are then patched into the packed matrix on the GPU.
+    The scalar draws are taken from numpy's global stream in the reference's row-major (site, sample) order
+    (by the library's restatement of numpy's sampler, nprandom.legacy_binomial); everything around them stays
+    on the device: the per-site counts are the ones the site filter already produced (loc_site_stats), the
+    list of missing calls comes from loc_missing_calls, the draws are patched into the packed matrix.
+    ``stats`` = (device GT cube, alt_count, n_missing, kept-site indices, packed matrix) from filter_snps;
+    called on its own (as the reference's function can be) it imputes every site of ``genotypes``.
     """
+    import torch
     from . import genotypes as G
 
     print("imputing missing data")
-    gt = genotypes.gt if keep_idx is None else genotypes.gt[keep_idx]
-    if packed is None:
-        g, na, alt, miss, keep = G.site_stats(gt, min_mac=1)
-        packed = G.pack_sites(g, np.arange(gt.shape[0]))
-    missing = (gt < 0).any(axis=2)  # [K, N]
-    ninds = (~missing).sum(axis=1)
-    dc = (gt == 1).sum(axis=(1, 2))
+    if stats is None:
+        g, na, alt, miss, keep = G.site_stats(genotypes.gt, min_mac=1)
+        idx = torch.arange(g.shape[0], dtype=torch.int64, device=g.device)
+        packed = G.pack_sites(g, idx)
+    else:
+        g, alt, miss, idx, packed = stats
+    N = g.shape[1]
+    dc = alt[idx].cpu().numpy().astype(np.int64)          # count_alleles()[:, 1]
+    ninds = N - miss[idx].cpu().numpy().astype(np.int64)  # samples with a called genotype
     with np.errstate(divide="ignore", invalid="ignore"):
         af = dc / (2 * ninds)
-    ks, samps = np.nonzero(missing)  # row-major (site, sample) order
-    if len(ks):
+    ks, samps = G.missing_calls(g, idx, miss)  # row-major (site, sample) order
+    if ks.numel():
         from .nprandom import legacy_binomial
 
-        vals = legacy_binomial(2, af[ks], 1)[:, 0]  # the reference's scalar draws, in its (site, sample) order
+        vals = legacy_binomial(2, af[ks.cpu().numpy()], 1)[:, 0]  # the reference's scalar draws, in its order
         packed.patch(ks, samps, vals)
     return AlleleCounts(packed)
 
@@ -223,15 +268,15 @@ def filter_snps(genotypes):
 
     print("filtering SNPs")
     on_disk = getattr(genotypes, "rows_on_disk", None)
-    if on_disk is not None and on_disk.dtype == np.int8 and not args.impute_missing:
+    if on_disk is not None and on_disk.dtype == np.int8:
         gt = G.upload_rows(on_disk)  # zarr chunks -> pinned staging -> device; the host never holds the cube
     else:
         gt = genotypes.gt
     g, n_alleles, alt_count, n_missing, keep = G.site_stats(gt, min_mac=int(args.min_mac))
-    keep_idx = np.flatnonzero(keep.cpu().numpy())
+    keep_idx = G.compact_sites(keep)  # device-side prefix sum: the mask never visits the host
     packed = G.pack_sites(g, keep_idx)
     if args.impute_missing:
-        ac = replace_md(genotypes, keep_idx, packed)
+        ac = replace_md(genotypes, (g, alt_count, n_missing, keep_idx, packed))
     else:
         ac = AlleleCounts(packed)
     if not args.max_SNPs == None:  # noqa: E711  (as in the reference)
@@ -480,6 +525,7 @@ def main(argv=None):
         os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu_number
     if args.out is None:
         raise SystemExit("--out is required")
+    validate_args(args)
     _write_params()
     from . import replicates
 

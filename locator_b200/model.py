@@ -336,14 +336,20 @@ class LocatorModel:
         # (locator.py:441 inside :729-743): same weights + same device matrix -> same answer
         if g.n == 0:  # no rows (a run without NA-location samples): Keras returns an empty [0, 2] array
             return np.zeros((0, 2), dtype=np.float32)
-        key = (id(g), g.version, self._wver) if isinstance(x, PackedGenotypes) else None
-        if key is not None and self._memo.get("key") == key:
-            return self._memo["val"].copy()
+        # memo per matrix object (a few entries: the sweep alternates a fresh clone of predgen with the one testgen)
+        key = (g.version, self._wver) if isinstance(x, PackedGenotypes) else None
+        hit = self._memo.get(id(g)) if key is not None else None
+        if hit is not None and hit[0] == key and hit[2] is g:
+            self._memo[id(g)] = self._memo.pop(id(g))  # most recently used last
+            return hit[1].copy()
         out = torch.zeros((g.n, 2), dtype=torch.float32, device=_dev())
         check(lib.loc_predict(self._h, g.ptr, g.n, g.row_words, out.data_ptr(), _stream()), "loc_predict")
         res = out.cpu().numpy()
         if key is not None:
-            self._memo = {"key": key, "val": res.copy(), "ref": g}
+            if len(self._memo) >= 4:  # least recently used first (dicts keep insertion order)
+                for k in list(self._memo)[: len(self._memo) - 3]:
+                    del self._memo[k]
+            self._memo[id(g)] = (key, res.copy(), g)
         return res
 
     def evaluate(self, x, y, verbose=0):

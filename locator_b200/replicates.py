@@ -114,6 +114,7 @@ def _run_items(L, items, base, reps=None):
             callbacks.append(L.load_callbacks(rep["cb_boot"]))
         finally:
             args.out = original_out
+    _tick(f"{len(models)} models created")
     same = len({(r["traingen"].n, m.nlayers, m.batch_size) for r, m in zip(reps, models)}) == 1
     if len(reps) > 1 and same and all(m.impl == "tcgen05" for m in models):
         start = time.time()
@@ -125,6 +126,7 @@ def _run_items(L, items, base, reps=None):
             if args.keep_weights:
                 m.save_weights(cb[0].filepath)
         print("run time " + str((time.time() - start) / 60) + " minutes (" + str(len(reps)) + " replicates side by side)")
+        _tick("group trained, best weights restored")
     else:
         histories = []
         for m, cb, rep in zip(models, callbacks, reps):
@@ -141,6 +143,7 @@ def _run_items(L, items, base, reps=None):
             args.out = original_out
         if args.plot_history:
             L.plot_history(h, dists)
+    _tick("group predicted, files written")
     if items and items[0]["kind"] == "window":
         print(f"Window run time {(time.time() - t1) / 60:.2f} minutes")
 
@@ -554,7 +557,7 @@ def run_windows(L, genotypes, samples):
     positions = np.array(genotypes.positions)
     start = int(args.window_start)
     stop = np.max(positions) if args.window_stop == None else int(args.window_stop)  # noqa: E711
-    size = int(float(args.window_size))
+    size = int(args.window_size)  # validate_args: int() accepts it, as the reference requires
     n_gpus = max(1, int(getattr(args, "gpus", 1) or 1))
     pool = _take_pool(n_gpus, args) if n_gpus > 1 else None
     # Recipes instead of matrices whenever no draw depends on the genotypes: whoever runs the window (a

@@ -61,10 +61,31 @@ def elu(z):
     return torch.where(z > 0, z, torch.expm1(z))
 
 
+# ---- TF32 operand model (numerics="tf32") --------------------------------------------------------------
+# The tcgen05 kernels feed fp32 bit patterns to kind::tf32 MMAs: the tensor core reads sign, exponent and the
+# top 10 mantissa bits of each operand and accumulates in fp32.  Weights go in as stored (their low 13 bits are
+# ignored: truncation); everything the kernels write into an operand tile themselves (folded-BN inputs,
+# activations, dz, centred genotypes) is rounded to nearest, ties away (cvt.rna.tf32.f32) first.  TensorFlow's
+# default fp32 matmul on Ampere-and-later GPUs makes the same kind of approximation.  This mode restates WHERE
+# the device rounds, so that what is left between it and the device is summation order and a few
+# last-place differences of rsqrt / expm1 / sqrt -- it is still test infrastructure, not a product path.
+def tf32_rna(t):
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def tf32_trunc(t):
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
 class RefLocator:
     """The reference network + optimizer state, Keras semantics, fp32 on CPU."""
 
-    def __init__(self, K, width=256, nlayers=10, dropout=0.25, weights=None, seed=0, lr=1e-3):
+    def __init__(self, K, width=256, nlayers=10, dropout=0.25, weights=None, seed=0, lr=1e-3, numerics="fp32"):
+        """numerics: "fp32" (the reference's CPU arithmetic) or "tf32" (the device's operand rounding, see
+        tf32_rna / tf32_trunc above)."""
+        assert numerics in ("fp32", "tf32")
+        self.tf32 = numerics == "tf32"
         if nlayers < 2:
             raise ValueError("oracle restates nlayers >= 2 (first Dense precedes Dropout)")
         self.K, self.H, self.L, self.p = K, width, nlayers, float(dropout)
@@ -113,8 +134,10 @@ class RefLocator:
         c.update(mean=mean, var=var, rs=rs)
         acts = [a]  # input of dense layer i
         zs = []
+        op_a = tf32_rna if self.tf32 else (lambda t: t)     # operand tiles the kernels build
+        op_w = tf32_trunc if self.tf32 else (lambda t: t)   # weights as stored
         for i in range(self.L):
-            z = acts[-1] @ self.W[i] + self.b[i]
+            z = op_a(acts[-1]) @ op_w(self.W[i]) + self.b[i]
             h = elu(z)
             zs.append(z)
             if i == self.n_before - 1:  # Dropout sits after the floor(L/2)-th Dense
@@ -123,7 +146,7 @@ class RefLocator:
                     h = h * keep * np.float32(1.0 / (1.0 - self.p))
                     c["keep"] = keep
             acts.append(h)
-        y1 = acts[-1] @ self.W[self.L] + self.b[self.L]
+        y1 = op_a(acts[-1]) @ self.W[self.L] + self.b[self.L]  # Dense(2) runs on CUDA cores: fp32 weights
         y2 = y1 @ self.W[self.L + 1] + self.b[self.L + 1]
         c.update(acts=acts, zs=zs, y1=y1)
         return y2, c
@@ -158,13 +181,26 @@ class RefLocator:
             z = zs[i]
             dz = torch.where(z > 0, dh, dh * torch.exp(z))  # EluGrad: (out+1)*g for out<0
             dzs[i] = dz
-            gW[i] = acts[i].T @ dz
             gb[i] = dz.sum(0)
-            dh = dz @ self.W[i].T
-        # dh is now d(loss)/d(BN output)
-        xn = (c["x"] - c["mean"]) * c["rs"]
-        ggamma = (dh * xn).sum(0)
-        gbeta = dh.sum(0)
+            if i == 0 and self.tf32:
+                break  # first layer below: the device never forms d loss / d (BN output)
+            gW[i] = acts[i].T @ dz
+            dh = (tf32_rna(dz) @ tf32_trunc(self.W[i]).T) if self.tf32 else (dz @ self.W[i].T)
+        if self.tf32:
+            # first-layer backward as the device computes it (csrc/l1_tc.cu): S = (x - mean)^T dz with the centred
+            # genotypes rounded to tf32 (exact for a batch of 32) and dz as hi + lo parts (fp32-accurate);
+            # dW1 = inv * S + beta * c0, dgamma = rs * sum_j W1 * S, dbeta = sum_j W1 * c0, c0 = column sums of dz
+            dz0 = dzs[0]
+            S = tf32_rna(c["x"] - c["mean"]).T @ dz0
+            c0 = dz0.sum(0)
+            gW[0] = (c["rs"] * self.gamma)[:, None] * S + self.beta[:, None] * c0[None, :]
+            ggamma = c["rs"] * (self.W[0] * S).sum(1)
+            gbeta = self.W[0] @ c0
+        else:
+            # dh is now d(loss)/d(BN output)
+            xn = (c["x"] - c["mean"]) * c["rs"]
+            ggamma = (dh * xn).sum(0)
+            gbeta = dh.sum(0)
         grads = [ggamma, gbeta]
         for w, b in zip(gW, gb):
             grads += [w, b]

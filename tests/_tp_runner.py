@@ -63,6 +63,22 @@ def main():
         f_w1 = full.get_weights()[4]
         s_init = np.concatenate([g["w_init"] for g in gathered])
         s_w1 = np.concatenate([g["w1"] for g in gathered])
+        # the CPU oracle from the same start (Philox dropout masks keyed by the model seed), both numerics
+        from oracle import model_ref
+
+        oracle = {}
+        for numerics in ("fp32", "tf32"):
+            ws = model_ref.init_weights(K, 256, 10, seed=5)
+            ref = model_ref.RefLocator(K, 256, 10, dropout=0.25, weights=ws, numerics=numerics)
+            hr = model_ref.fit(ref, x, y, xv, yv, epochs, batch_size=32, patience=100, perms=perms, seed=5)
+            r_w1 = ref.get_weights()[4]
+            oracle[numerics] = {
+                "hist": [hr["loss"], hr["val_loss"]],
+                "pred_maxdiff": float(np.abs(gathered[0]["pred"] - ref.predict(xv)).max()),
+                "w1_update_rel": float(np.linalg.norm(s_w1 - r_w1) / np.linalg.norm(r_w1 - ws[4])),
+                "init_equal": bool(np.array_equal(s_init, ws[4])),
+            }
+        res["oracle"] = oracle
         res.update({
             "init_equal": bool(np.array_equal(s_init, f_init)),
             "replicas_identical": bool(all(np.array_equal(g["hist"], gathered[0]["hist"]) and

@@ -5,13 +5,17 @@ oracle (oracle/model_ref.py, fp32) started from the same weights, batch order an
 
 Reference: model.fit inside train_network, /root/reference/locator/locator.py:367-376.
 
-What can and cannot agree.  The tcgen05 kernels multiply in TF32 (fp32 accumulate); the oracle is fp32.
-One optimizer step therefore agrees to TF32 rounding (stage tests below).  Over many steps Adam turns
-rounding differences into O(lr) differences of individual weights (a gradient that rounds to the other
-side of zero moves its weight the other way by the full step), and with K = 100k inputs feeding every
-unit the trajectories separate: test_divergence_is_rounding_chaos measures that separation between two
-ORACLE runs whose initial W1 differs by one unit in the last place and requires the CUDA runs (148 and
-132 first-layer CTAs, i.e. two fp32 summation orders) to stay within the same band.
+What can and cannot agree.  The tcgen05 kernels multiply in TF32 (fp32 accumulate); the reference's CPU
+arithmetic is fp32.  The oracle therefore runs in two modes: numerics="fp32" (the reference) and
+numerics="tf32" (the same algorithm with the device's operand rounding restated, oracle/model_ref.py);
+what is left between the tf32 mode and the device is summation order and last-place differences of
+rsqrt / expm1 / sqrt.  One optimizer step agrees with the fp32 oracle to TF32 rounding (stage tests).
+Over many steps Adam turns rounding differences into O(lr) differences of individual weights (a
+gradient that rounds to the other side of zero moves its weight the other way by the full step) and,
+with K = 100k inputs feeding every unit, trajectories separate exponentially (about e^0.17 per step
+here): test_divergence_is_rounding_chaos measures that separation between ORACLE runs whose initial W1
+differs by one unit in the last place -- in both numerics -- and requires the CUDA runs (148 and 132
+first-layer CTAs, i.e. two fp32 summation orders) to stay within the same band.
 
 Every test appends its measured deviations to gpurun_out/parity_baseline_shapes.jsonl.
 """
@@ -125,6 +129,12 @@ def test_step_stages_match_oracle(M, K, ctas):
     loss_ref, grads, c = ref.gradients(x[rows], y[rows], masks[0])
     z1_ref = (c["zs"][0] - ref.b[0]).numpy()
     dz1_ref = c["dzs"][0].numpy()
+    # the same step in the oracle's tf32 mode (the device's operand rounding restated)
+    reft = model_ref.RefLocator(K, H, L, dropout=P_DROP, weights=w0, numerics="tf32")
+    loss_t, _, ct = reft.gradients(x[rows], y[rows], masks[0])
+    z1_t = (ct["zs"][0] - reft.b[0]).numpy()
+    dz1_t = ct["dzs"][0].numpy()
+    reft.train_step(x[rows], y[rows], masks[0])
 
     m.debug_stage(0, rows)
     z1 = m.debug_read(0).sum(axis=0)
@@ -147,8 +157,15 @@ def test_step_stages_match_oracle(M, K, ctas):
     wc, wr = m.get_weights(), ref.get_weights()
     mW, vW = m.get_adam(4)
     dev = _update_deviation(w0, wc, wr, (mW, vW), (ref.m[2].numpy(), ref.v[2].numpy()))
+    wt = reft.get_weights()
+    devt = _update_deviation(w0, wc, wt, (mW, vW), (reft.m[2].numpy(), reft.v[2].numpy()))
+    tf32 = {"loss_rel": abs(loss - loss_t) / abs(loss_t), "z1_err": float(np.abs(z1 - z1_t).max() / (1.0 + np.abs(z1_t).max())),
+            "dz1_rel": _rel(dz1, dz1_t), **devt}
     _report(test="step_stages", K=K, l1_ctas=m.l1_ctas, loss=loss, loss_ref=loss_ref, z1_err=e_z1, dz1_rel=e_dz1,
-            z1_next_err=e_z1n, **dev)
+            z1_next_err=e_z1n, vs_tf32_oracle=tf32, **dev)
+    # against the tf32 mode only summation order is left
+    assert tf32["loss_rel"] <= 2e-3 and tf32["z1_err"] <= 2e-3 and tf32["dz1_rel"] <= 1e-2, tf32
+    assert devt["m_rel"] <= 1e-2 and devt["v_rel"] <= 2e-2 and devt["dW1_frac_opposite"] <= 0.02, devt
     # stated tolerances (TF32 products, fp32 accumulation; the dW GEMM itself is fp32-accurate)
     assert abs(loss - loss_ref) <= 2e-3 * abs(loss_ref)
     assert e_z1 <= 2e-3, e_z1
@@ -179,26 +196,31 @@ def test_epoch_production_path_matches_oracle(M, K, ntr, nva):
     w0 = m.get_weights()
     perms = np.stack([rng.permutation(ntr)])
     h = m.fit(xt, yt, epochs=1, validation_data=(xv, yv), patience=100, perms=perms)
-    ref = model_ref.RefLocator(K, H, L, dropout=P_DROP, weights=w0)
-    t0 = time.time()
-    hr = model_ref.fit(ref, xt, yt, xv, yv, 1, batch_size=B, patience=100, perms=perms, seed=seed)
-    t_oracle = time.time() - t0
-    dl, dv = _hist_dev(h.history, hr)
-    wc, wr = m.get_weights(), ref.get_weights()
-    mW, vW = m.get_adam(4)
-    dev = _update_deviation(w0, wc, wr, (mW, vW), (ref.m[2].numpy(), ref.v[2].numpy()))
-    yp, yr = m.predict(xv), ref.predict(xv)
-    e_pred = float(np.abs(yp - yr).max())
-    _report(test="epoch_fit", K=K, steps=int(np.ceil(ntr / B)), loss=h.history["loss"], loss_ref=hr["loss"],
-            val=h.history["val_loss"], val_ref=hr["val_loss"], loss_dev=dl, val_dev=dv, pred_max_abs=e_pred,
-            oracle_seconds=t_oracle, **dev)
+    out = {}
+    for numerics in ("fp32", "tf32"):
+        ref = model_ref.RefLocator(K, H, L, dropout=P_DROP, weights=w0, numerics=numerics)
+        t0 = time.time()
+        hr = model_ref.fit(ref, xt, yt, xv, yv, 1, batch_size=B, patience=100, perms=perms, seed=seed)
+        t_oracle = time.time() - t0
+        dl, dv = _hist_dev(h.history, hr)
+        wc, wr = m.get_weights(), ref.get_weights()
+        mW, vW = m.get_adam(4)
+        dev = _update_deviation(w0, wc, wr, (mW, vW), (ref.m[2].numpy(), ref.v[2].numpy()))
+        yp, yr = m.predict(xv), ref.predict(xv)
+        e_pred = float(np.abs(yp - yr).max())
+        out[numerics] = (dl, dv, dev)
+        _report(test="epoch_fit", oracle=numerics, K=K, steps=int(np.ceil(ntr / B)), loss=h.history["loss"],
+                loss_ref=hr["loss"], val=h.history["val_loss"], val_ref=hr["val_loss"], loss_dev=dl, val_dev=dv,
+                pred_max_abs=e_pred, oracle_seconds=t_oracle, **dev)
     assert m.state().t == int(np.ceil(ntr / B))
-    # the epoch's mean training loss is dominated by its first steps (before trajectories separate)
-    assert dl <= 2e-2, (dl, h.history, hr)
-    assert dv <= 1e-1, (dv, h.history, hr)
-    # the accumulated update of W1 points the same way and has the same size
-    assert 0.95 <= dev["dW1_norm_ratio"] <= 1.05, dev
-    assert dev["dW1_rel"] <= 0.35, dev
+    for numerics, (dl, dv, dev) in out.items():
+        # the epoch's mean training loss is dominated by its first steps (before trajectories separate); the
+        # validation loss is taken after the last step, where they have (see the module docstring)
+        assert dl <= 3e-2, (numerics, dl, h.history)
+        assert dv <= 3e-1, (numerics, dv, h.history)
+        # the accumulated update of W1 points the same way and has the same size
+        assert 0.98 <= dev["dW1_norm_ratio"] <= 1.02, (numerics, dev)
+        assert dev["dW1_rel"] <= 0.2, (numerics, dev)
 
 
 def _fit_variants(M, K, xt, yt, xv, yv, seeds, perms, epochs):
@@ -264,10 +286,10 @@ def test_schedules_match_oracle_and_each_other(M):
             dev = _update_deviation(w0, wc, wr)
             _report(test="schedules", schedule=name, seed=s, loss=h["loss"], loss_ref=hr["loss"], val=h["val_loss"],
                     val_ref=hr["val_loss"], loss_dev=dl, val_dev=dv, **dev)
-            assert dl <= 2e-2, (name, s, dl)
-            assert dv <= 1e-1, (name, s, dv)
-            assert 0.95 <= dev["dW1_norm_ratio"] <= 1.05, (name, dev)
-            assert dev["dW1_rel"] <= 0.35, (name, dev)
+            assert dl <= 1e-2, (name, s, dl)      # measured <= 0.3 % after 11 steps
+            assert dv <= 1.5e-1, (name, s, dv)    # measured <= 5.2 %
+            assert 0.99 <= dev["dW1_norm_ratio"] <= 1.01, (name, dev)
+            assert dev["dW1_rel"] <= 0.1, (name, dev)   # measured <= 3.3 %
     for i in range(len(seeds)):
         # grouping only changes scheduling: same CTA count -> same bits
         assert got["group_ring"][i][0] == got["solo_spare"][i][0]
@@ -299,30 +321,33 @@ def test_divergence_is_rounding_chaos(M):
         runs[name] = m.fit(xt, yt, epochs=epochs, validation_data=(xv, yv), patience=10 ** 6, perms=perms).history
         del m
     w0 = model_ref.init_weights(K, H, L, seed=seed)
-    for name, perturb in (("oracle", False), ("oracle_1ulp", True)):
+    for name, numerics, perturb in (("oracle", "fp32", False), ("oracle_1ulp", "fp32", True),
+                                    ("oracle_tf32", "tf32", False), ("oracle_tf32_1ulp", "tf32", True)):
         ws = [w.copy() for w in w0]
         if perturb:
             flip = np.random.default_rng(1).integers(0, 2, ws[4].shape, dtype=np.int32) * 2 - 1
             ws[4] = np.nextafter(ws[4], ws[4] + flip.astype(np.float32)).astype(np.float32)
-        ref = model_ref.RefLocator(K, H, L, dropout=P_DROP, weights=ws)
+        ref = model_ref.RefLocator(K, H, L, dropout=P_DROP, weights=ws, numerics=numerics)
         runs[name] = model_ref.fit(ref, xt, yt, xv, yv, epochs, batch_size=B, patience=10 ** 6, perms=perms, seed=seed)
 
     def sep(a, b):
         return [abs(p - q) / abs(q) for p, q in zip(runs[a]["loss"], runs[b]["loss"])]
 
     table = {n: r["loss"] for n, r in runs.items()}
-    seps = {"cuda148_vs_cuda132": sep("cuda_148", "cuda_132"), "cuda148_vs_oracle": sep("cuda_148", "oracle"),
-            "cuda132_vs_oracle": sep("cuda_132", "oracle"), "oracle1ulp_vs_oracle": sep("oracle_1ulp", "oracle")}
+    pairs = [("cuda_148", "cuda_132"), ("cuda_148", "oracle_tf32"), ("cuda_132", "oracle_tf32"), ("cuda_148", "oracle"),
+             ("cuda_132", "oracle"), ("oracle_1ulp", "oracle"), ("oracle_tf32_1ulp", "oracle_tf32"), ("oracle_tf32", "oracle")]
+    seps = {f"{a}_vs_{b}": sep(a, b) for a, b in pairs}
     _report(test="divergence", losses=table, val={n: r["val_loss"] for n, r in runs.items()}, separation=seps)
-    # epoch 1: every run is still on the same trajectory
+    # epoch 1 (26 steps): every run is still on the same trajectory
     for k, v in seps.items():
         assert v[0] <= 3e-2, (k, v, table)
-    # later epochs: the CUDA runs separate from the oracle no more than a few times what one unit in the
-    # last place does to the oracle itself (+ 2 % slack for the single sample this is)
-    band = [4.0 * s + 0.02 for s in seps["oracle1ulp_vs_oracle"]]
-    for k in ("cuda148_vs_cuda132", "cuda148_vs_oracle", "cuda132_vs_oracle"):
+    # later epochs: the CUDA runs separate from each other and from the oracle no more than a few times what a
+    # one-unit-in-the-last-place change of the initial W1 does to the oracle itself under the same numerics
+    # (+ 3 % slack: these are single samples of a chaotic system)
+    band = [4.0 * max(a, b) + 0.03 for a, b in zip(seps["oracle_tf32_1ulp_vs_oracle_tf32"], seps["oracle_1ulp_vs_oracle"])]
+    for k in ("cuda_148_vs_cuda_132", "cuda_148_vs_oracle_tf32", "cuda_132_vs_oracle_tf32"):
         for e in range(epochs):
-            assert seps[k][e] <= max(band[e], 3e-2), (k, e, seps, table)
+            assert seps[k][e] <= band[e], (k, e, seps, table)
     # and all of them learn: the third epoch's loss is well below the first's
     for n, r in runs.items():
         assert r["loss"][-1] < 0.8 * r["loss"][0], (n, r["loss"])

@@ -3,6 +3,7 @@ and its replicate drivers -- flags, output files and seed-reproducible indices."
 import hashlib
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -108,7 +109,11 @@ def test_default_run_on_reference_fixture(L, tmp_path, capsys):
     assert 10 <= len(h) <= 150 and np.all(np.isfinite(h))
     assert h[-1, 1] < h[0, 1] * 0.5  # validation loss fell
     med = float(text.split("median validation error ")[1].split()[0])
-    assert med < 10.0, med
+    print("ACCURACY default CLI run, 150 epochs: median validation error", med, file=sys.stderr)
+    # margin: tests/test_gpu_accuracy.py trains the oracle and the CUDA path from the same start with the full
+    # default schedule and requires their medians within 1.0 map units of each other; the README's own run reports
+    # 3.30.  This bounded (150-epoch) run must be within that margin + 1.5 of the README's figure.
+    assert med < 3.30 + 1.0 + 1.5, med
     assert not os.path.exists(out + ".weights.npz")
 
 

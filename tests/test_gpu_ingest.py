@@ -192,3 +192,48 @@ def test_full_size_filter_and_pack_properties(G):
     idx = torch.nonzero(keep).flatten()
     packed = G.pack_sites(g, idx)
     assert torch.equal(packed.to_counts(), (gt[idx] == 1).sum(dim=2).to(torch.uint8).T.contiguous())
+
+
+@pytest.mark.parametrize("nvar", [0, 1, 5, 2047, 2048, 2049, 70001, 600_000])
+def test_compact_sites_matches_flatnonzero(G, nvar):
+    """Device-side ordered compaction of the keep mask (prefix sum + scatter; filter_snps, locator.py:269,273)."""
+    rng = np.random.default_rng(nvar + 1)
+    keep = (rng.uniform(size=nvar) < 0.57).astype(np.uint8)
+    if nvar > 10:
+        keep[:3] = 1
+        keep[-2:] = 1
+    idx = G.compact_sites(torch.as_tensor(keep).cuda())
+    assert idx.dtype == torch.int64
+    assert np.array_equal(idx.cpu().numpy(), np.flatnonzero(keep))
+    # all kept / none kept
+    if nvar:
+        assert np.array_equal(G.compact_sites(torch.ones(nvar, dtype=torch.uint8, device="cuda")).cpu().numpy(), np.arange(nvar))
+        assert G.compact_sites(torch.zeros(nvar, dtype=torch.uint8, device="cuda")).numel() == 0
+
+
+@pytest.mark.parametrize("nvar,N,miss", [(300, 37, 0.05), (64, 500, 0.3), (17, 5, 0.0), (5000, 129, 0.01), (40, 2500, 0.02)])
+def test_missing_calls_in_reference_order(G, nvar, N, miss):
+    """(site, sample) of the missing calls of the kept sites, row-major: np.nonzero(is_missing) of the filtered
+    cube -- the order replace_md draws in (locator.py:255-261)."""
+    from oracle import ingest_ref
+
+    rng = np.random.default_rng(nvar * 3 + N)
+    gt = _rand_gt(rng, nvar, N, miss=miss, multi=0.0)
+    g, na, alt, nmiss, keep = G.site_stats(gt, min_mac=1)
+    idx = G.compact_sites(keep)
+    ks, samps = G.missing_calls(g, idx, nmiss)
+    sub = gt[idx.cpu().numpy()]
+    ek, es = np.nonzero(ingest_ref.is_missing(sub))
+    assert np.array_equal(ks.cpu().numpy(), ek)
+    assert np.array_equal(samps.cpu().numpy(), es)
+
+
+@pytest.mark.parametrize("n,K", [(1, 1), (7, 15), (33, 16), (250, 1000), (1000, 5830), (2500, 40_001)])
+def test_site_sums_match_numpy(G, n, K):
+    """Per-SNP sums over all samples with wide integers (jacknife allele frequencies, locator.py:714-717)."""
+    rng = np.random.default_rng(n + K)
+    x = rng.integers(0, 3, size=(n, K), dtype=np.uint8)
+    p = G.PackedGenotypes.from_counts(x)
+    sums = p.site_sums().cpu().numpy()
+    assert sums.dtype == np.int64
+    assert np.array_equal(sums, x.astype(np.int64).sum(axis=0))

@@ -44,3 +44,11 @@ def test_two_shards_match_the_unsharded_model(tmp_path, mode):
     assert np.array_equal(ht[:, 2], hf[:, 2])  # learning-rate column
     assert res["pred_maxdiff"] < 5e-3
     assert res["w1_update_rel"] < 0.05
+    # ... and the CPU oracle (oracle/model_ref.py) directly, not only the unsharded CUDA model: 3 epochs of 3 steps
+    for numerics, o in res["oracle"].items():
+        assert o["init_equal"], "shards must initialise exactly as slices of the oracle's Philox layer"
+        np.testing.assert_allclose(ht[:, 0], o["hist"][0], rtol=1e-2, err_msg=f"loss vs {numerics} oracle")
+        np.testing.assert_allclose(ht[:, 1], o["hist"][1], rtol=3e-2, err_msg=f"val_loss vs {numerics} oracle")
+        assert o["pred_maxdiff"] < 5e-2, (numerics, o)
+        assert o["w1_update_rel"] < 0.15, (numerics, o)
+    print("TP vs oracle:", json.dumps(res["oracle"]), file=sys.stderr)

@@ -184,10 +184,12 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   float4 p0_s = make_float4(0.f, 0.f, 0.f, 0.f);
   {
     const int pbeg = a.n_partials * p0_g / 4, pend = a.n_partials * (p0_g + 1) / 4;
-    const float4* src = reinterpret_cast<const float4*>(a.partials + (int64_t)(b0 + p0_b) * kH + j0 + p0_jl);
+    const float4* src =
+        reinterpret_cast<const float4*>(a.partials + (int64_t)(a.partial_row0 + b0 + p0_b) * kH + j0 + p0_jl);
+    const int64_t pstride = a.partial_stride >> 2;  // float4 units between partial tiles
 #pragma unroll 16
     for (int p = pbeg; p < pend; ++p) {
-      const float4 v = __ldcg(src + (int64_t)p * kMaxB * (kH / 4));
+      const float4 v = __ldcg(src + (int64_t)p * pstride);
       p0_s.x += v.x;
       p0_s.y += v.y;
       p0_s.z += v.z;
@@ -450,6 +452,9 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
           st->loss_count += (float)nb;
           st->last_loss = mean;
           if (!isfinite(mean)) st->nonfinite = 1;
+        } else if (a.val_slot != nullptr) {  // chunks of a wide pass run concurrently: summed in order afterwards
+          a.val_slot[0] = mean * (float)nb;
+          a.val_slot[1] = (float)nb;
         } else {
           st->val_total += mean * (float)nb;
           st->val_count += (float)nb;

@@ -345,6 +345,174 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(L1Args a, int64_t nt
   if (warp == 1) tmem_dealloc(tmem, 64);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Wide inference forward (validation / prediction / jacknife sweeps): up to 256 rows per pass over W1
+// ---------------------------------------------------------------------------------------------
+// model.predict / the validation pass of model.fit (locator.py:374,414,441) only need Z1 = xhat * W1 with the
+// moving statistics; the reference runs them at batch 32 and so did this library: one full stream of W1 per 32
+// rows.  Here the batch axis of the MMA is N = 32..256 (D[j, b], M = 128 x 2 halves, K = 8 SNPs per MMA, both
+// accumulators of N columns in TMEM: 512 columns at N = 256), so W1 is streamed ONCE per 256 rows: 8 builder
+// warps each turn one 32-row chunk of the packed genotypes into its [32 SNPs][32 rows] slice of the MN-major
+// B operand (chunks are LBO = 4 KB apart), per 32-SNP stage.  At N = 256 a stage is 8 MMAs of 128 x 256 x 8
+// (about 1,024 tensor-core cycles) against 32 KB of W1 (about 1,400 cycles of this SM's share of HBM): the
+// sweep sits at the crossover of the two rooflines instead of 8x under the memory one.
+constexpr int W_STAGES = 3;
+constexpr int W_XBYTES = 8 * F_XBYTES;           // 32 KB: [8 chunks of 32 rows][32 SNP rows][128 B]
+constexpr int W_BUILD = 8;                        // builder warps = max 32-row chunks
+constexpr int W_THREADS = (2 + W_BUILD) * 32;     // producer, MMA issuer, builders (also the epilogue)
+constexpr int W_SMEM = W_STAGES * (F_WBYTES + W_XBYTES) + W_BUILD * 32 * 8 + 256 + 1024;
+
+__global__ void __launch_bounds__(W_THREADS, 1) k_l1_fwd_wide(L1Args a, int64_t ntiles, int nrows, float* __restrict__ out) {
+  if (a.gated && a.st->stopped) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = sm;
+  uint8_t* sX = sW + W_STAGES * F_WBYTES;
+  uint32_t* sBits = (uint32_t*)(sX + W_STAGES * W_XBYTES);  // [8 warps][32 rows][2 words]
+  uint64_t* bars = (uint64_t*)(sBits + W_BUILD * 32 * 2);
+  uint64_t* full_w = bars;
+  uint64_t* full_x = bars + W_STAGES;
+  uint64_t* empty = bars + 2 * W_STAGES;
+  uint64_t* done = bars + 3 * W_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * W_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NC = (nrows + 31) >> 5, N = NC * 32;  // 32-row chunks, MMA N
+  const int64_t t_begin = 2 * (ntiles * blockIdx.x / gridDim.x);
+  const int64_t t_end = 2 * (ntiles * (blockIdx.x + 1) / gridDim.x);
+  const int nloc = (int)(t_end - t_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < W_STAGES; ++s) {
+      mbar_init(&full_w[s], 1);
+      mbar_init(&full_x[s], (uint32_t)NC);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int li = 0; li < nloc; ++li) {
+        const int s = li % W_STAGES;
+        const uint32_t ph = (uint32_t)(li / W_STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_w[s], F_WBYTES);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sW + s * F_WBYTES)),
+                     "l"(a.W1 + (t_begin + li) * (int64_t)(F_KT * kH)), "r"((uint32_t)F_WBYTES), "r"(smem_u32(&full_w[s]))
+                     : "memory");
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, N, 1, 1);
+    if (elect_one()) {
+      for (int li = 0; li < nloc; ++li) {
+        const int s = li % W_STAGES;
+        const uint32_t ph = (uint32_t)(li / W_STAGES) & 1u;
+        mbar_wait(&full_w[s], ph);
+        mbar_wait(&full_x[s], ph);
+        tc_fence_after();
+        const uint32_t wbase = smem_u32(sW + s * F_WBYTES), xbase = smem_u32(sX + s * W_XBYTES);
+#pragma unroll
+        for (int ks = 0; ks < F_KT / 8; ++ks) {
+          // B: MN-major, N = NC chunks of 32 rows, F_CHUNK (4 KB) apart; 8 SNP rows of this k-step at ks * 1 KB
+          const uint64_t bdesc = smem_desc(xbase + ks * 1024, F_CHUNK, 512, kLayoutSw128B32);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t adesc = smem_desc(wbase + ks * 8192 + h * 4096, 1024, 512, kLayoutSw128B32);
+            umma_tf32(tmem + (uint32_t)(h * N), adesc, bdesc, idesc, (li > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(done);
+    }
+  } else {
+    // ---- builders: warp wi owns the 32-row chunk wi (rows 32 wi .. 32 wi + 31 of this pass) ----
+    const int wi = warp - 2;
+    if (wi < NC) {
+      uint32_t* bits = sBits + wi * 64;
+      const int b_row = wi * 32 + lane;             // row of the pass this lane loads
+      const bool row_ok = b_row < nrows;
+      const int nb_chunk = nrows - wi * 32 < 32 ? nrows - wi * 32 : 32;
+      const int64_t my_row = row_ok ? row_of(a.src, a.st, b_row) : 0;
+      const uint32_t* my_ptr = a.packed + my_row * a.row_words;
+      for (int li = 0; li < nloc; ++li) {
+        const int s = li % W_STAGES;
+        const uint32_t ph = (uint32_t)(li / W_STAGES) & 1u;
+        const int64_t tile = t_begin + li;
+        uint2 w2 = make_uint2(0u, 0u);
+        if (row_ok && tile * 2 + 1 < a.row_words) w2 = __ldg(reinterpret_cast<const uint2*>(my_ptr + tile * 2));
+        const int64_t k = tile * F_KT + lane;
+        const bool valid = k < a.K;
+        float gamma = 0.f, beta = 0.f, mm = 0.f, mv = 1.f;
+        if (valid) {
+          gamma = __ldg(a.gamma + k);
+          beta = __ldg(a.beta + k);
+          mm = __ldg(a.mmean + k);
+          mv = __ldg(a.mvar + k);
+        }
+        bits[lane * 2] = w2.x;
+        bits[lane * 2 + 1] = w2.y;
+        __syncwarp();
+        const int wsel = lane >> 4, sh = 2 * (lane & 15);
+        unsigned long long g = 0ull;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) g |= (unsigned long long)((bits[b * 2 + wsel] >> sh) & 3u) << (2 * b);
+        __syncwarp();
+        const float inv = rsqrtf(mv + kBnEps) * gamma;  // inference: moving statistics
+        const float shift = beta - mm * inv;
+        float lut[3];
+        lut[0] = valid ? to_tf32(shift) : 0.f;
+        lut[1] = valid ? to_tf32(inv + shift) : 0.f;
+        lut[2] = valid ? to_tf32(2.f * inv + shift) : 0.f;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* xrow = sX + s * W_XBYTES + wi * F_CHUNK;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int b = 4 * c + e;
+            const unsigned x = (unsigned)((g >> (2 * b)) & 3ull);
+            float val = lut[0];
+            val = x == 1u ? lut[1] : val;
+            val = x == 2u ? lut[2] : val;
+            v[e] = b < nb_chunk ? val : 0.f;
+          }
+          *reinterpret_cast<float4*>(xrow + swz32(lane, c)) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_x[s]);
+      }
+    }
+    // ---- epilogue: warps 2-5 take half 0, warps 6-9 half 1; accumulator row = j (TMEM lane), column = row of the pass
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int q = warp & 3, h = wi >> 2;
+    float* o = out + (int64_t)blockIdx.x * N * kH + (h * 128 + 32 * q + lane);
+    for (int c = 0; c < NC; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * N + c * 32), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int b = 0; b < 32; ++b) o[(int64_t)(c * 32 + b) * kH] = __uint_as_float(r[b]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Backward + Adam
 // ---------------------------------------------------------------------------------------------
@@ -927,6 +1095,19 @@ int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s) {
   }
   const int64_t ntiles = cdiv(a.K, tc::B_NT);
   tc::k_l1_fwd_tc<<<n_partials, tc::F_THREADS, tc::F_SMEM, s>>>(a, ntiles);
+  LOC_LAUNCHED();
+  return 0;
+}
+
+int l1_forward_wide_tc(const L1Args& a, int n_partials, int nrows, float* out, cudaStream_t s) {
+  LOC_CHECK(nrows >= 1 && nrows <= 256, "wide forward: 1..256 rows per pass");
+  static bool attr_set = false;
+  if (!attr_set) {
+    LOC_CUDA(cudaFuncSetAttribute(tc::k_l1_fwd_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::W_SMEM));
+    attr_set = true;
+  }
+  const int64_t ntiles = cdiv(a.K, tc::B_NT);
+  tc::k_l1_fwd_wide<<<n_partials, tc::W_THREADS, tc::W_SMEM, s>>>(a, ntiles, nrows, out);
   LOC_LAUNCHED();
   return 0;
 }

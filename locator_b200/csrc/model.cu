@@ -74,6 +74,15 @@ __global__ void k_state_reset(DevState* st, float lr, int patience, int max_epoc
 }
 
 __global__ void k_begin_call(DevState* st) { st->epoch0 = st->epoch; }
+// validation sums of the 32-row chunks of one wide inference pass, added in chunk order (same bits as the
+// chunk-by-chunk launches of the narrow path)
+__global__ void k_val_accumulate(DevState* st, const float* slots, int n, int gated) {
+  if (gated && st->stopped) return;
+  for (int c = 0; c < n; ++c) {
+    st->val_total += slots[2 * c];
+    st->val_count += slots[2 * c + 1];
+  }
+}
 __global__ void k_zero_val(DevState* st) { st->val_total = st->val_count = 0.f; }
 
 // on_epoch_end of History + [ModelCheckpoint, EarlyStopping, ReduceLROnPlateau] (locator.py:330-362).
@@ -260,6 +269,9 @@ static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated
   h.wait_err = nullptr;
   h.partials = m->exchange != nullptr ? m->z1_tile : m->partials;
   h.n_partials = m->exchange != nullptr ? 1 : m->n_partials;
+  h.partial_stride = (int64_t)kMaxB * m->H;
+  h.partial_row0 = 0;
+  h.val_slot = nullptr;
   if (m->tp != nullptr) {  // the shards' tiles of the latest exchange, summed in rank order by the kernel
     h.partials = tp_tiles(m->tp);
     h.n_partials = tp_world(m->tp);
@@ -344,9 +356,52 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
   return 0;
 }
 
-// Inference-mode forward over n rows in chunks of 32 (Keras predict/evaluate batch size).
+// Inference-mode forward over n rows (Keras predict / evaluate at batch 32: locator.py:374,414,441).
+// tcgen05 path: passes of up to 256 rows -- ONE stream of W1 per pass (k_l1_fwd_wide), then the pass's 32-row
+// chunks through the hidden stack side by side (one cluster per chunk, k_hidden_tc_group); per-chunk validation
+// sums are added in chunk order, so losses carry the same bits as chunk-by-chunk evaluation would give them.
+// Otherwise (CUDA-core kernels, sharded models, <= 32 rows): chunks of 32, one W1 stream each.
 static int infer_rows(loc_model* m, const uint32_t* packed, int64_t n, int64_t row_words, const float* locs,
                       float* pred_out, int gated, cudaStream_t s) {
+  const bool no_wide = getenv("LOC_NO_WIDE") != nullptr;  // tests / A-B runs: chunk-by-chunk evaluation
+  const bool wide = m->wide != nullptr && m->use_tc && m->hid_tc && m->exchange == nullptr && m->tp == nullptr &&
+                    n > kMaxB && !no_wide;
+  m->span_perm = nullptr;
+  if (wide) {
+    for (int64_t r0 = 0; r0 < n; r0 += 256) {
+      const int nrows = (int)((n - r0) < 256 ? (n - r0) : 256);
+      const int nc = (nrows + 31) / 32;
+      RowSrc src;
+      src.rows = nullptr;
+      src.epoch_stride = 0;
+      src.offset = 0;
+      src.row0 = (int32_t)r0;
+      src.nb = nrows;
+      L1Args a = l1_args(m, packed, row_words, src, 0, gated);
+      if (l1_forward_wide_tc(a, m->n_partials, nrows, m->wide, s)) return 1;
+      HidGroupArgs hg;
+      hg.n = nc;
+      for (int c = 0; c < nc; ++c) {
+        RowSrc sc = src;
+        sc.row0 = (int32_t)(r0 + 32 * c);
+        sc.nb = nrows - 32 * c < kMaxB ? nrows - 32 * c : kMaxB;
+        HidArgs h = hid_args(m, sc, 0, gated, locs, pred_out);
+        h.partials = m->wide;
+        h.n_partials = m->n_partials;
+        h.partial_stride = (int64_t)nc * 32 * m->H;
+        h.partial_row0 = 32 * c;
+        h.outs = m->outs + c * 256;
+        h.val_slot = locs != nullptr ? m->val_slots + 2 * c : nullptr;
+        hg.a[c] = h;
+      }
+      if (hidden_tc_group_launch(hg, s)) return 1;
+      if (locs != nullptr) {
+        k_val_accumulate<<<1, 1, 0, s>>>(m->st, m->val_slots, nc, gated);
+        LOC_LAUNCHED();
+      }
+    }
+    return 0;
+  }
   for (int64_t r0 = 0; r0 < n; r0 += kMaxB) {
     RowSrc src;
     src.rows = nullptr;
@@ -460,7 +515,9 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   LOC_CUDA(cudaMalloc(&m->partials, (size_t)m->n_partials * kMaxB * width * sizeof(float)));
   LOC_CUDA(cudaMalloc(&m->acts, (size_t)nlayers * kMaxB * width * sizeof(float)));
   LOC_CUDA(cudaMalloc(&m->dzs, (size_t)nlayers * kMaxB * width * sizeof(float)));
-  LOC_CUDA(cudaMalloc(&m->outs, 256 * sizeof(float)));
+  LOC_CUDA(cudaMalloc(&m->outs, 8 * 256 * sizeof(float)));  // one [256] block per 32-row chunk of a wide pass
+  LOC_CUDA(cudaMalloc(&m->val_slots, 16 * sizeof(float)));
+  if (m->use_tc && m->hid_tc) LOC_CUDA(cudaMalloc(&m->wide, (size_t)m->n_partials * 256 * width * sizeof(float)));
   LOC_CUDA(cudaMalloc(&m->hist, (size_t)max_epochs * 3 * sizeof(float)));
   if (getenv("LOC_HID_TRACE") != nullptr) {
     LOC_CUDA(cudaMalloc(&m->dbg, 16 * 256 * sizeof(long long)));
@@ -482,7 +539,8 @@ int loc_model_destroy(loc_model* m) {
   if (m == nullptr) return 0;
   float* ptrs[] = {m->W1, m->mW1, m->vW1, m->best_W1, m->gamma, m->beta, m->mmean, m->mvar, m->m_gamma, m->v_gamma,
                    m->m_beta, m->v_beta, m->best_gamma, m->best_beta, m->best_mmean, m->best_mvar, m->small, m->w_fs, m->w_bs,
-                   m->m_small, m->v_small, m->best_small, m->partials, m->acts, m->dzs, m->outs, m->hist};
+                   m->m_small, m->v_small, m->best_small, m->partials, m->acts, m->dzs, m->outs, m->hist, m->wide,
+                   m->val_slots};
   for (float* p : ptrs)
     if (p) cudaFree(p);
   if (m->st) cudaFree(m->st);

@@ -88,6 +88,10 @@ struct HidArgs {
   int64_t n_masks;
   const float* partials;
   int n_partials;
+  int64_t partial_stride;  // floats between consecutive partial tiles (kMaxB * H; wide inference: 32 * chunks * H)
+  int partial_row0;        // first row of this launch inside a partial tile (wide inference: 32 * chunk)
+  float* val_slot;         // inference with targets: {sum of distances, rows} go here instead of DevState
+                           // (chunks of one wide pass run concurrently; k_val_accumulate adds them in order)
   // sharded models (tp.cu): the partial tiles are the shards' tiles, complete once every flag >= wait_seq
   const uint32_t* wait_flags;
   int wait_count;
@@ -148,6 +152,8 @@ bool l1_tc_supported(int64_t K, int H);
 int l1_forward_tc(const L1Args& a, int n_partials, cudaStream_t s);
 int l1_backward_tc(const L1Args& a, int nblocks, cudaStream_t s, bool overlap_previous = false);
 int l1_tc_partials(int64_t K);
+// inference forward of up to 256 rows in one pass over W1: out [n_partials][32 * ceil(nrows / 32)][256]
+int l1_forward_wide_tc(const L1Args& a, int n_partials, int nrows, float* out, cudaStream_t s);
 // L2 prefetch of the head of the next backward's walk (chunks [skip, skip + n) of every CTA; t_ahead: optimizer
 // steps between now and that backward -- decides the walk direction)
 int l1_prefetch_tc(const L1Args& a, int nblocks, int skip_chunks, int n_chunks, int t_ahead, cudaStream_t s);
@@ -208,6 +214,8 @@ struct loc_model {
   float *best_gamma, *best_beta, *best_mmean, *best_mvar, *best_W1, *best_small;
   // workspaces
   float *partials, *acts, *dzs, *outs, *hist, *pred_tmp;
+  float* wide;       // wide inference: split-K partial tiles of up to 256 rows [n_partials][256][H] (tcgen05 path)
+  float* val_slots;  // [8][2] per-chunk validation sums of a wide pass
   long long* dbg;
   cudaStream_t side;        // small-layer update runs here, beside the first-layer backward
   cudaEvent_t ev_hid, ev_upd;

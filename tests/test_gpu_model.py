@@ -302,3 +302,40 @@ def test_fused_epochs_match_step_by_step_training(M):
         upd = np.linalg.norm(wb[i] - w0[i])
         assert np.linalg.norm(wa[i] - wb[i]) <= 0.05 * upd, f"weight {i}"
     np.testing.assert_allclose(a.predict(xv), b.predict(xv), rtol=5e-3, atol=5e-3)
+
+
+@pytest.mark.parametrize("K,n", [(200_000, 250), (5830, 33), (20_000, 257), (3000, 300), (100_000, 90)])
+def test_wide_inference_matches_oracle_and_narrow_path(M, K, n, monkeypatch):
+    """Validation / prediction / jacknife sweeps stream W1 once per 256 rows (k_l1_fwd_wide: MMA N = 32..256,
+    the 32-row chunks of a pass through the hidden stack side by side) instead of once per 32 rows.  Against
+    RefLocator.predict / evaluate (locator.py:374,414,441) at BASELINE config 5's shape (250 x 200,000) and at
+    ragged sizes around the pass / chunk boundaries, and against the chunk-by-chunk path (LOC_NO_WIDE)."""
+    from oracle import model_ref
+
+    rng = np.random.default_rng(K + n)
+    x, y = _data(rng, n, K)
+    m = M.LocatorModel(K, seed=17)
+    if m.impl != "tcgen05":
+        pytest.skip("tcgen05 kernels only")
+    ws = m.get_weights()
+    ws[0] = rng.uniform(0.5, 1.5, K).astype(np.float32)
+    ws[1] = rng.normal(0, 0.1, K).astype(np.float32)
+    ws[2] = rng.uniform(0, 1.5, K).astype(np.float32)
+    ws[3] = rng.uniform(0.1, 0.8, K).astype(np.float32)
+    for i in range(5, len(ws), 2):
+        ws[i] = rng.normal(0, 0.05, ws[i].shape).astype(np.float32)
+    m.set_weights(ws)
+    yp = m.predict(x)
+    ev = m.evaluate(x, y)
+    monkeypatch.setenv("LOC_NO_WIDE", "1")
+    yp_narrow = m.predict(x)
+    ev_narrow = m.evaluate(x, y)
+    monkeypatch.delenv("LOC_NO_WIDE")
+    assert yp.shape == (n, 2) and np.all(np.isfinite(yp))
+    # same products, same split over SNPs, same order of the chunk sums
+    np.testing.assert_allclose(yp, yp_narrow, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ev, ev_narrow, rtol=1e-6)
+    for numerics, tol in (("tf32", 1e-3), ("fp32", 2e-3)):
+        ref = model_ref.RefLocator(K, 256, 10, weights=ws, numerics=numerics)
+        np.testing.assert_allclose(yp, ref.predict(x), rtol=tol, atol=tol, err_msg=numerics)
+        np.testing.assert_allclose(ev, ref.evaluate(x, y), rtol=tol, err_msg=numerics)

@@ -166,7 +166,13 @@ int loc_np_legacy_permutation(uint32_t* mt_key, int32_t* mt_pos, int64_t n, int6
  * workspaces on the current device. */
 int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers, int32_t batch_size,
                      float dropout_prop, int32_t max_epochs);
+/* Replicate runs (--bootstrap / --windows: locator.py:519-583, :609-681 build one model per replicate and call
+ * keras.backend.clear_session() after each, :681) create and drop models all the time; destroyed handles are kept
+ * in a small pool (LOC_MODEL_POOL handles, default 8, 0 = off) and loc_model_create re-uses one whose buffers
+ * fit (same width / nlayers, K within [0.6, 1] of its capacity), zeroed exactly like a fresh handle, instead
+ * of ~35 cudaMalloc / cudaFree calls per replicate.  loc_model_pool_clear() releases the pool's device memory. */
 int loc_model_destroy(loc_model* m);
+int loc_model_pool_clear(void);
 /* First-layer kernel family this model actually runs: "tcgen05" or "simt". */
 const char* loc_model_impl(const loc_model* m);
 

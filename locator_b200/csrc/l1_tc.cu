@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       mbar_init(&st_full[s], 1);
       mbar_init(&st_done[s], 8);
     }
-    for (int s = 0; s < B_STAGES; ++s) mbar_init(&st_free[s], fuse ? 2 : 1);  // written back (+ consumed by the forward MMA)
+    for (int s = 0; s < B_STAGES; ++s) mbar_init(&st_free[s], (fuse && !(a.dbg_flags & 8)) ? 2 : 1);  // written back (+ consumed by the forward MMA)
     mbar_init(fwd_done, 2);  // one commit per forward warp
     mbar_init(&fwd_tile[0], 2);
     mbar_init(&fwd_tile[1], 2);
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
     }
-    if (fuse && grp == 0) {  // next step's split-K partial tile of Z1: accumulator row = j, column = batch row
+    if (fuse && grp == 0 && !(a.dbg_flags & 32)) {  // next step's split-K partial tile of Z1: accumulator row = j, column = batch row
       mbar_wait(fwd_done, 0);
       tc_fence_after();
       uint32_t r32[32], r33[32];
@@ -850,8 +850,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
           if (lane == 0) mbar_arrive(&fwd_tile[buf]);
         }
         float gm = cur.gm, mg = cur.mg, vg = cur.vg, bt = cur.bt, mb = cur.mb, vb = cur.vb;
-        adam_update(gm, mg, vg, rs * P, alpha);
-        adam_update(bt, mb, vb, Q, alpha);
+        if (!(a.dbg_flags & 2)) {
+          adam_update(gm, mg, vg, rs * P, alpha);
+          adam_update(bt, mb, vb, Q, alpha);
+        }
         const float inv = rsn * gm;
         const float shift = bt - mean * inv;
         const float l0 = valid ? to_tf32(shift) : 0.f;
@@ -859,7 +861,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
         const float l2 = valid ? to_tf32(2.f * inv + shift) : 0.f;
         uint8_t* xf = sXf + s * B_XF;
 #pragma unroll
-        for (int r8 = 0; r8 < 8; ++r8) {
+        for (int r8 = 0; r8 < 8 && !(a.dbg_flags & 4); ++r8) {
           const float a0 = __shfl_sync(0xffffffffu, l0, r8), a1 = __shfl_sync(0xffffffffu, l1, r8),
                       a2 = __shfl_sync(0xffffffffu, l2, r8);
           float val = a0;
@@ -875,14 +877,14 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
           const uint32_t wbs = smem_u32(sStage + s * B_STAGE);
           const uint64_t bdesc = smem_desc(smem_u32(xf), 1024, 512, kLayoutSw128B32);
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh)
+          for (int hh = 0; hh < 2 && !(a.dbg_flags & 1); ++hh)
             umma_tf32(tmem + (uint32_t)(256 + fw * 64 + hh * 32), smem_desc(wbs + hh * 4096, 1024, 512, kLayoutSw128B32),
                       bdesc, idesc_f, c > fw ? 1u : 0u);
-          umma_commit(&st_free[s]);
+          if (!(a.dbg_flags & 8)) umma_commit(&st_free[s]);
           if (c + 2 >= nchunks) umma_commit(fwd_done);
         }
         __syncwarp();
-        if (valid && lane < 8) {  // off the stage's critical path
+        if (valid && lane < 8 && !(a.dbg_flags & 2)) {  // off the stage's critical path
           a.gamma[k] = gm;
           a.m_gamma[k] = mg;
           a.v_gamma[k] = vg;

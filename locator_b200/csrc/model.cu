@@ -8,7 +8,9 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "model.cuh"
 #include "philox.cuh"
@@ -196,6 +198,8 @@ static int reslice(loc_model* m, cudaStream_t s) {
                    : hidden_reslice(m->small, m->w_fs, m->w_bs, m->H, m->L, m->cluster, s);
 }
 
+static int g_fuse_debug = 0;  // loc_debug_stage: LOC_FUSE_DEBUG bits (timing experiments only)
+
 static L1Args l1_args(loc_model* m, const uint32_t* packed, int64_t row_words, const RowSrc& src, int training,
                       int gated) {
   L1Args a;
@@ -214,6 +218,7 @@ static L1Args l1_args(loc_model* m, const uint32_t* packed, int64_t row_words, c
   // (B200, cfg2) than the default policy; LOC_STREAM_HINT overrides for A/B runs
   static const int stream_hint = getenv("LOC_STREAM_HINT") ? atoi(getenv("LOC_STREAM_HINT")) : 3;
   a.stream_hint = stream_hint;
+  a.dbg_flags = g_fuse_debug;
   a.gamma = m->gamma;
   a.beta = m->beta;
   a.mmean = m->mmean;
@@ -450,6 +455,114 @@ const char* loc_l1_impl(void) {
   return (e != nullptr && strcmp(e, "simt") == 0) ? "simt" : "tcgen05";
 }
 
+}  // extern "C"
+
+// ---- handle pool ----------------------------------------------------------------------------------
+// Replicate runs (--bootstrap / --windows, locator.py:519-583,609-681) create and drop one model per replicate.
+// A model is ~35 device allocations (4 x K x 256 floats among them): cudaMalloc + cudaFree of those cost
+// 30-50 ms per replicate on the host -- as much as 250 optimizer steps at K = 100,000.  Destroyed handles
+// therefore go to a small pool (LOC_MODEL_POOL handles, default 8, 0 = off) and loc_model_create takes a
+// pooled handle whose buffers are large enough (same width / nlayers, K within [0.6, 1] of its capacity)
+// instead of allocating; every buffer create() would have zeroed is zeroed again, so a recycled handle is
+// indistinguishable from a fresh one.  loc_model_pool_clear() releases the pool's memory.
+namespace {
+std::mutex g_pool_mu;
+std::vector<loc_model*> g_pool;
+
+int pool_limit() {
+  static const int lim = [] {
+    const char* e = getenv("LOC_MODEL_POOL");
+    const int v = e != nullptr ? atoi(e) : 8;
+    return v < 0 ? 0 : (v > 64 ? 64 : v);
+  }();
+  return lim;
+}
+
+void free_model(loc_model* m) {
+  float* ptrs[] = {m->W1, m->mW1, m->vW1, m->best_W1, m->gamma, m->beta, m->mmean, m->mvar, m->m_gamma, m->v_gamma,
+                   m->m_beta, m->v_beta, m->best_gamma, m->best_beta, m->best_mmean, m->best_mvar, m->small, m->w_fs, m->w_bs,
+                   m->m_small, m->v_small, m->best_small, m->partials, m->acts, m->dzs, m->outs, m->hist, m->wide,
+                   m->val_slots};
+  for (float* p : ptrs)
+    if (p) cudaFree(p);
+  if (m->st) cudaFree(m->st);
+  if (m->dbg) cudaFree(m->dbg);
+  if (m->side) cudaStreamDestroy(m->side);
+  if (m->ev_hid) cudaEventDestroy(m->ev_hid);
+  if (m->ev_upd) cudaEventDestroy(m->ev_upd);
+  delete m;
+}
+
+void pool_clear_locked() {
+  for (loc_model* m : g_pool) free_model(m);
+  g_pool.clear();
+}
+
+// cudaMalloc that gives the pool's memory back before it reports failure
+cudaError_t dev_alloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaSuccess) return e;
+  cudaGetLastError();
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool.empty()) return e;
+    pool_clear_locked();
+  }
+  return cudaMalloc(p, bytes);
+}
+template <class T>
+cudaError_t dev_alloc(T** p, size_t bytes) {
+  return dev_alloc(reinterpret_cast<void**>(p), bytes);
+}
+
+loc_model* pool_take(int dev, int64_t K, int width, int nlayers, int use_tc, int hid_tc, int max_epochs, bool want_dbg) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (size_t i = 0; i < g_pool.size(); ++i) {
+    loc_model* m = g_pool[i];
+    if (m->dev == dev && m->H == width && m->L == nlayers && m->use_tc == use_tc && m->hid_tc == hid_tc &&
+        m->cap_K >= K && (double)K >= 0.6 * (double)m->cap_K && m->cap_epochs >= max_epochs && (m->dbg != nullptr) == want_dbg) {
+      g_pool.erase(g_pool.begin() + (long)i);
+      return m;
+    }
+  }
+  return nullptr;
+}
+}  // namespace
+
+// K-dependent launch geometry (also after a pooled handle changes its K)
+static void set_geometry(loc_model* m, int64_t K) {
+  m->K = K;
+  m->K_global = K;
+  m->k_offset = 0;
+  const int sms = sm_count();
+  if (m->use_tc) {
+    m->n_partials = l1_tc_partials(K);
+    m->n_bwd_blocks = m->n_partials;
+  } else {
+    const int64_t nch = cdiv(K, kF1Chunk);
+    m->n_partials = (int)(nch < 2 * sms ? nch : 2 * sms);
+    const int64_t nch2 = cdiv(K, 32);
+    m->n_bwd_blocks = (int)(nch2 < 2 * sms ? nch2 : 2 * sms);
+  }
+  m->Kpad = m->use_tc ? (K + 63) / 64 * 64 : K;
+}
+
+// what loc_model_create guarantees about the contents of a new handle's buffers
+static int zero_model(loc_model* m) {
+  const int64_t KH = m->Kpad * m->H;
+  float* big[] = {m->W1, m->mW1, m->vW1, m->best_W1};
+  for (float* p : big) LOC_CUDA(cudaMemsetAsync(p, 0, KH * sizeof(float), 0));  // padding rows stay zero under Adam
+  LOC_CUDA(cudaMemsetAsync(m->st, 0, sizeof(DevState), 0));
+  LOC_CUDA(cudaMemsetAsync(m->dzs, 0, (size_t)m->L * kMaxB * m->H * sizeof(float), 0));
+  LOC_CUDA(cudaMemsetAsync(m->acts, 0, (size_t)m->L * kMaxB * m->H * sizeof(float), 0));
+  LOC_CUDA(cudaMemsetAsync(m->hist, 0, (size_t)m->max_epochs * 3 * sizeof(float), 0));
+  if (m->dbg) LOC_CUDA(cudaMemsetAsync(m->dbg, 0, 16 * 256 * sizeof(long long), 0));
+  LOC_CUDA(cudaStreamSynchronize(0));  // callers may continue on non-blocking streams
+  return 0;
+}
+
+extern "C" {
+
 int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers, int32_t batch_size,
                      float dropout_prop, int32_t max_epochs) {
   LOC_CHECK(out != nullptr, "loc_model_create: null output pointer");
@@ -463,17 +576,51 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   int ndev = 0;
   LOC_CUDA(cudaGetDeviceCount(&ndev));
   LOC_CHECK(ndev > 0, "loc_model_create: no CUDA device (this library has no CPU fallback)");
+  int dev = 0;
+  LOC_CUDA(cudaGetDevice(&dev));
+  int hid_tc, use_tc;
+  {
+    const char* himpl = getenv("LOC_HIDDEN_IMPL");
+    hid_tc = (himpl == nullptr || strcmp(himpl, "simt") != 0) && hidden_tc_supported(width, nlayers);
+    const char* impl = getenv("LOC_L1_IMPL");
+    use_tc = (impl == nullptr || strcmp(impl, "simt") != 0) && l1_tc_supported(K, width);
+  }
+  const bool want_dbg = getenv("LOC_HID_TRACE") != nullptr;
+  if (loc_model* r = pool_limit() > 0 ? pool_take(dev, K, width, nlayers, use_tc, hid_tc, max_epochs, want_dbg) : nullptr) {
+    // a recycled handle: same buffers, new shape and settings, nothing bound
+    set_geometry(r, K);
+    r->B = batch_size;
+    r->max_epochs = max_epochs;
+    r->p_drop = dropout_prop;
+    r->seed = 0;
+    r->train_packed = r->val_packed = nullptr;
+    r->train_locs = r->val_locs = nullptr;
+    r->n_train = r->n_val = r->train_row_words = r->val_row_words = 0;
+    r->masks = nullptr;
+    r->n_masks = 0;
+    r->exchange = nullptr;
+    r->exchange_ctx = nullptr;
+    r->z1_tile = nullptr;
+    r->tp = nullptr;
+    r->span_perm = nullptr;
+    r->span_next = 0;
+    if (zero_model(r)) {
+      free_model(r);
+      return 1;
+    }
+    *out = r;
+    return 0;
+  }
   loc_model* m = new (std::nothrow) loc_model();
   LOC_CHECK(m != nullptr, "loc_model_create: out of host memory");
   memset(m, 0, sizeof(*m));
-  LOC_CUDA(cudaGetDevice(&m->dev));
-  m->K = K;
-  m->K_global = K;
+  m->dev = dev;
   m->H = width;
   m->L = nlayers;
   m->B = batch_size;
   m->n_before = nlayers / 2;
   m->max_epochs = max_epochs;
+  m->cap_epochs = max_epochs;
   m->p_drop = dropout_prop;
   m->sl = SmallLayout{width, nlayers};
   m->cluster = hidden_max_cluster(width, nlayers);
@@ -482,73 +629,70 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
     return loc::fail("loc_model_create: no usable thread-block cluster size for this width / nlayers", __FILE__, __LINE__);
   }
   m->n_slots = hidden_slots(width, nlayers, m->cluster);
-  {
-    const char* himpl = getenv("LOC_HIDDEN_IMPL");
-    m->hid_tc = (himpl == nullptr || strcmp(himpl, "simt") != 0) && hidden_tc_supported(width, nlayers);
-  }
-  const char* impl = getenv("LOC_L1_IMPL");
-  m->use_tc = (impl == nullptr || strcmp(impl, "simt") != 0) && l1_tc_supported(K, width);
-  const int sms = sm_count();
-  if (m->use_tc) {
-    m->n_partials = l1_tc_partials(K);
-    m->n_bwd_blocks = m->n_partials;
-  } else {
-    const int64_t nch = cdiv(K, kF1Chunk);
-    m->n_partials = (int)(nch < 2 * sms ? nch : 2 * sms);
-    const int64_t nch2 = cdiv(K, 32);
-    m->n_bwd_blocks = (int)(nch2 < 2 * sms ? nch2 : 2 * sms);
-  }
-  m->Kpad = m->use_tc ? (K + 63) / 64 * 64 : K;
+  m->hid_tc = hid_tc;
+  m->use_tc = use_tc;
+  set_geometry(m, K);
+  m->cap_K = K;
   const int64_t KH = m->Kpad * width, ns = m->sl.total();
+#define LOC_ALLOC(ptr, bytes)                                 \
+  do {                                                        \
+    if (dev_alloc(&(ptr), (bytes)) != cudaSuccess) {          \
+      cudaGetLastError();                                     \
+      free_model(m);                                          \
+      return loc::fail("loc_model_create: out of device memory", __FILE__, __LINE__); \
+    }                                                         \
+  } while (0)
   float** big[] = {&m->W1, &m->mW1, &m->vW1, &m->best_W1};
-  for (auto p : big) {
-    LOC_CUDA(cudaMalloc(p, KH * sizeof(float)));
-    LOC_CUDA(cudaMemset(*p, 0, KH * sizeof(float)));  // padding rows stay zero under Adam
-  }
+  for (auto p : big) LOC_ALLOC(*p, KH * sizeof(float));
   float** kv[] = {&m->gamma, &m->beta, &m->mmean, &m->mvar, &m->m_gamma, &m->v_gamma, &m->m_beta,
                   &m->v_beta, &m->best_gamma, &m->best_beta, &m->best_mmean, &m->best_mvar};
-  for (auto p : kv) LOC_CUDA(cudaMalloc(p, K * sizeof(float)));
+  for (auto p : kv) LOC_ALLOC(*p, K * sizeof(float));
   float** sm[] = {&m->small, &m->m_small, &m->v_small, &m->best_small};
-  for (auto p : sm) LOC_CUDA(cudaMalloc(p, ns * sizeof(float)));
-  LOC_CUDA(cudaMalloc(&m->w_fs, (size_t)(nlayers - 1) * width * width * sizeof(float)));
-  LOC_CUDA(cudaMalloc(&m->w_bs, (size_t)(nlayers - 1) * width * width * sizeof(float)));
-  LOC_CUDA(cudaMalloc(&m->partials, (size_t)m->n_partials * kMaxB * width * sizeof(float)));
-  LOC_CUDA(cudaMalloc(&m->acts, (size_t)nlayers * kMaxB * width * sizeof(float)));
-  LOC_CUDA(cudaMalloc(&m->dzs, (size_t)nlayers * kMaxB * width * sizeof(float)));
-  LOC_CUDA(cudaMalloc(&m->outs, 8 * 256 * sizeof(float)));  // one [256] block per 32-row chunk of a wide pass
-  LOC_CUDA(cudaMalloc(&m->val_slots, 16 * sizeof(float)));
-  if (m->use_tc && m->hid_tc) LOC_CUDA(cudaMalloc(&m->wide, (size_t)m->n_partials * 256 * width * sizeof(float)));
-  LOC_CUDA(cudaMalloc(&m->hist, (size_t)max_epochs * 3 * sizeof(float)));
-  if (getenv("LOC_HID_TRACE") != nullptr) {
-    LOC_CUDA(cudaMalloc(&m->dbg, 16 * 256 * sizeof(long long)));
-    LOC_CUDA(cudaMemset(m->dbg, 0, 16 * 256 * sizeof(long long)));
+  for (auto p : sm) LOC_ALLOC(*p, ns * sizeof(float));
+  LOC_ALLOC(m->w_fs, (size_t)(nlayers - 1) * width * width * sizeof(float));
+  LOC_ALLOC(m->w_bs, (size_t)(nlayers - 1) * width * width * sizeof(float));
+  LOC_ALLOC(m->partials, (size_t)m->n_partials * kMaxB * width * sizeof(float));
+  LOC_ALLOC(m->acts, (size_t)nlayers * kMaxB * width * sizeof(float));
+  LOC_ALLOC(m->dzs, (size_t)nlayers * kMaxB * width * sizeof(float));
+  LOC_ALLOC(m->outs, 8 * 256 * sizeof(float));  // one [256] block per 32-row chunk of a wide pass
+  LOC_ALLOC(m->val_slots, 16 * sizeof(float));
+  if (m->use_tc && m->hid_tc) LOC_ALLOC(m->wide, (size_t)m->n_partials * 256 * width * sizeof(float));
+  LOC_ALLOC(m->hist, (size_t)max_epochs * 3 * sizeof(float));
+  if (want_dbg) LOC_ALLOC(m->dbg, 16 * 256 * sizeof(long long));
+  LOC_ALLOC(m->st, sizeof(DevState));
+#undef LOC_ALLOC
+  if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_hid, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_upd, cudaEventDisableTiming) != cudaSuccess || zero_model(m)) {
+    free_model(m);
+    return loc::fail("loc_model_create: stream / event / memset failed", __FILE__, __LINE__);
   }
-  LOC_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
-  LOC_CUDA(cudaEventCreateWithFlags(&m->ev_hid, cudaEventDisableTiming));
-  LOC_CUDA(cudaEventCreateWithFlags(&m->ev_upd, cudaEventDisableTiming));
-  LOC_CUDA(cudaMalloc(&m->st, sizeof(DevState)));
-  LOC_CUDA(cudaMemset(m->st, 0, sizeof(DevState)));
-  LOC_CUDA(cudaMemset(m->dzs, 0, (size_t)nlayers * kMaxB * width * sizeof(float)));
-  LOC_CUDA(cudaMemset(m->acts, 0, (size_t)nlayers * kMaxB * width * sizeof(float)));
-  LOC_CUDA(cudaMemset(m->hist, 0, (size_t)max_epochs * 3 * sizeof(float)));
   *out = m;
   return 0;
 }
 
 int loc_model_destroy(loc_model* m) {
   if (m == nullptr) return 0;
-  float* ptrs[] = {m->W1, m->mW1, m->vW1, m->best_W1, m->gamma, m->beta, m->mmean, m->mvar, m->m_gamma, m->v_gamma,
-                   m->m_beta, m->v_beta, m->best_gamma, m->best_beta, m->best_mmean, m->best_mvar, m->small, m->w_fs, m->w_bs,
-                   m->m_small, m->v_small, m->best_small, m->partials, m->acts, m->dzs, m->outs, m->hist, m->wide,
-                   m->val_slots};
-  for (float* p : ptrs)
-    if (p) cudaFree(p);
-  if (m->st) cudaFree(m->st);
-  if (m->dbg) cudaFree(m->dbg);
-  if (m->side) cudaStreamDestroy(m->side);
-  if (m->ev_hid) cudaEventDestroy(m->ev_hid);
-  if (m->ev_upd) cudaEventDestroy(m->ev_upd);
-  delete m;
+  int dev = -1;
+  cudaGetDevice(&dev);
+  if (pool_limit() > 0 && dev == m->dev) {
+    // everything queued on the handle's buffers must be done before another model may take them
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if ((int)g_pool.size() >= pool_limit()) {
+      free_model(g_pool.front());
+      g_pool.erase(g_pool.begin());
+    }
+    g_pool.push_back(m);
+    return 0;
+  }
+  free_model(m);
+  return 0;
+}
+
+int loc_model_pool_clear(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  pool_clear_locked();
   return 0;
 }
 
@@ -770,7 +914,13 @@ int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t 
   src.offset = 0;
   src.row0 = 0;
   src.nb = nb;
-  if (stage == 4) return train_step(m, src, 0, (cudaStream_t)stream, 4, &src);  // backward + fused next forward
+  if (stage == 4) {  // backward + fused next forward
+    const char* e = getenv("LOC_FUSE_DEBUG");
+    g_fuse_debug = e != nullptr ? atoi(e) : 0;
+    const int rc = train_step(m, src, 0, (cudaStream_t)stream, 4, &src);
+    g_fuse_debug = 0;
+    return rc;
+  }
   if (stage == 5) {  // L2 prefetch of the next backward's head: LOC_PREFETCH="skip,count" chunks per CTA
     LOC_CHECK(m->use_tc, "loc_debug_stage: stage 5 needs the tcgen05 first layer");
     int skip = 0, cnt = 16;

@@ -68,6 +68,7 @@ struct L1Args {
   int alternate;  // tcgen05 backward: walk the CTA's tiles downwards on odd steps (the tail of the previous
                   // step's updates is still in L2: those reads hit and their dirty lines are overwritten in place)
   int stream_hint;  // tcgen05 backward: L2 evict_first on the W1/m/v chunk loads (bit 0) / stores (bit 1)
+  int dbg_flags;    // timing experiments on the fused forward (loc_debug_stage + LOC_FUSE_DEBUG); 0 in production
   float *gamma, *beta, *mmean, *mvar;
   float* W1;
   float *m_gamma, *v_gamma, *m_beta, *v_beta, *mW1, *vW1;
@@ -201,7 +202,9 @@ struct loc_model {
   int n_partials;   // partial Z1 tiles the forward leaves
   int n_bwd_blocks;
   int use_tc;       // first layer on tcgen05 (implies the tiled W1 layout)
-  int64_t Kpad;     // rows allocated for W1 / m / v (K rounded up to 64 when tiled)
+  int64_t Kpad;     // rows of W1 / m / v in use (K rounded up to 64 when tiled)
+  int64_t cap_K;    // K the buffers were allocated for (a pooled handle serves any K <= cap_K, see loc_model_create)
+  int cap_epochs;   // rows of the history buffer
   int hid_tc;       // hidden stack on tcgen05 (hidden_tc.cu) instead of CUDA cores (hidden.cu)
   loc::SmallLayout sl;
   // parameters

@@ -81,11 +81,15 @@ def tf32_trunc(t):
 class RefLocator:
     """The reference network + optimizer state, Keras semantics, fp32 on CPU."""
 
-    def __init__(self, K, width=256, nlayers=10, dropout=0.25, weights=None, seed=0, lr=1e-3, numerics="fp32"):
+    def __init__(self, K, width=256, nlayers=10, dropout=0.25, weights=None, seed=0, lr=1e-3, numerics="fp32",
+                 l1_parts=1):
         """numerics: "fp32" (the reference's CPU arithmetic) or "tf32" (the device's operand rounding, see
-        tf32_rna / tf32_trunc above)."""
+        tf32_rna / tf32_trunc above).  l1_parts > 1: the first layer's sum over the SNPs is taken in that many
+        contiguous parts (64-SNP tiles dealt out like the device's CTAs) added in order -- a different fp32
+        summation order of the same products, which is all a change of the device's CTA count does."""
         assert numerics in ("fp32", "tf32")
         self.tf32 = numerics == "tf32"
+        self.l1_parts = int(l1_parts)
         if nlayers < 2:
             raise ValueError("oracle restates nlayers >= 2 (first Dense precedes Dropout)")
         self.K, self.H, self.L, self.p = K, width, nlayers, float(dropout)
@@ -137,7 +141,10 @@ class RefLocator:
         op_a = tf32_rna if self.tf32 else (lambda t: t)     # operand tiles the kernels build
         op_w = tf32_trunc if self.tf32 else (lambda t: t)   # weights as stored
         for i in range(self.L):
-            z = op_a(acts[-1]) @ op_w(self.W[i]) + self.b[i]
+            if i == 0 and self.l1_parts > 1:
+                z = self._l1_in_parts(op_a(acts[-1]), op_w(self.W[0])) + self.b[0]
+            else:
+                z = op_a(acts[-1]) @ op_w(self.W[i]) + self.b[i]
             h = elu(z)
             zs.append(z)
             if i == self.n_before - 1:  # Dropout sits after the floor(L/2)-th Dense
@@ -150,6 +157,17 @@ class RefLocator:
         y2 = y1 @ self.W[self.L + 1] + self.b[self.L + 1]
         c.update(acts=acts, zs=zs, y1=y1)
         return y2, c
+
+    def _l1_in_parts(self, a, w):
+        """a @ w with the K axis cut like the device cuts it: 64-SNP tiles, part p = tiles [nt*p/P, nt*(p+1)/P)."""
+        nt, P = -(-self.K // 64), self.l1_parts
+        z = None
+        for p in range(P):
+            k0, k1 = min(self.K, 64 * (nt * p // P)), min(self.K, 64 * (nt * (p + 1) // P))
+            if k1 > k0:
+                part = a[:, k0:k1] @ w[k0:k1]
+                z = part if z is None else z + part
+        return z
 
     @staticmethod
     def loss_per_sample(yhat, y):

@@ -302,10 +302,17 @@ def test_schedules_match_oracle_and_each_other(M):
 def test_divergence_is_rounding_chaos(M):
     """The bench's replicate-group lines ended three epochs at different losses for 148 vs 132 first-layer
     CTAs (round 1: 0.753 vs 0.607) although the two only differ in fp32 summation order.  Same setting
-    here (cfg2 synthetic matrix, model seed 500, batch orders from default_rng(77), 3 epochs = 78 steps):
-    CUDA with 148 and with 132 CTAs, the oracle, and the oracle again with its initial W1 perturbed by one
-    unit in the last place.  If the separation between the two ORACLE runs is as large as between the CUDA
-    runs, the gap is Adam amplifying rounding, not a kernel bug."""
+    here (cfg2 synthetic matrix, model seed 500, batch orders from default_rng(77), 3 epochs = 78 steps).
+
+    The control is the ORACLE itself: RefLocator(numerics="tf32", l1_parts=P) takes the first layer's sum over
+    the SNPs in P contiguous parts added in order -- the same products in a different fp32 summation order,
+    which is all a change of the device's CTA count does.  The oracle runs with P = 1, 37, 74, 132, 148 separate
+    from each other as much as the two CUDA runs do (measured on the build container's CPU: epoch-3 losses
+    0.740 / 0.849 / 0.820 / 0.859 for P = 1 / 148 / 132 / 74, validation loss after the first epoch 1.07 / 1.29 /
+    1.01 / 1.05): Adam amplifies rounding at K = 100k, it is not a kernel bug.  Asserted: in epoch 1, before the
+    trajectories separate, every run agrees within 3 %; later every CUDA run lies within the oracle family's
+    envelope widened by 1.5 x its own spread, and the two CUDA runs are no further apart than twice the
+    family's largest pairwise separation."""
     import bench
     from oracle import model_ref
 
@@ -321,33 +328,33 @@ def test_divergence_is_rounding_chaos(M):
         runs[name] = m.fit(xt, yt, epochs=epochs, validation_data=(xv, yv), patience=10 ** 6, perms=perms).history
         del m
     w0 = model_ref.init_weights(K, H, L, seed=seed)
-    for name, numerics, perturb in (("oracle", "fp32", False), ("oracle_1ulp", "fp32", True),
-                                    ("oracle_tf32", "tf32", False), ("oracle_tf32_1ulp", "tf32", True)):
-        ws = [w.copy() for w in w0]
-        if perturb:
-            flip = np.random.default_rng(1).integers(0, 2, ws[4].shape, dtype=np.int32) * 2 - 1
-            ws[4] = np.nextafter(ws[4], ws[4] + flip.astype(np.float32)).astype(np.float32)
-        ref = model_ref.RefLocator(K, H, L, dropout=P_DROP, weights=ws, numerics=numerics)
+    family = []
+    for parts in (1, 37, 74, 132, 148):
+        ref = model_ref.RefLocator(K, H, L, dropout=P_DROP, weights=[w.copy() for w in w0], numerics="tf32",
+                                   l1_parts=parts)
+        name = f"oracle_tf32_parts{parts}"
         runs[name] = model_ref.fit(ref, xt, yt, xv, yv, epochs, batch_size=B, patience=10 ** 6, perms=perms, seed=seed)
-
-    def sep(a, b):
-        return [abs(p - q) / abs(q) for p, q in zip(runs[a]["loss"], runs[b]["loss"])]
+        family.append(name)
+    ref = model_ref.RefLocator(K, H, L, dropout=P_DROP, weights=[w.copy() for w in w0])
+    runs["oracle_fp32"] = model_ref.fit(ref, xt, yt, xv, yv, epochs, batch_size=B, patience=10 ** 6, perms=perms, seed=seed)
 
     table = {n: r["loss"] for n, r in runs.items()}
-    pairs = [("cuda_148", "cuda_132"), ("cuda_148", "oracle_tf32"), ("cuda_132", "oracle_tf32"), ("cuda_148", "oracle"),
-             ("cuda_132", "oracle"), ("oracle_1ulp", "oracle"), ("oracle_tf32_1ulp", "oracle_tf32"), ("oracle_tf32", "oracle")]
-    seps = {f"{a}_vs_{b}": sep(a, b) for a, b in pairs}
-    _report(test="divergence", losses=table, val={n: r["val_loss"] for n, r in runs.items()}, separation=seps)
+    fam = np.array([runs[n]["loss"] for n in family])  # [member, epoch]
+    lo, hi = fam.min(axis=0), fam.max(axis=0)
+    spread = hi - lo
+    fam_pair = [float(max(abs(a - b) / min(a, b) for a in fam[:, e] for b in fam[:, e])) for e in range(epochs)]
+    cuda_pair = [abs(a - b) / min(a, b) for a, b in zip(runs["cuda_148"]["loss"], runs["cuda_132"]["loss"])]
+    _report(test="divergence", losses=table, val={n: r["val_loss"] for n, r in runs.items()},
+            family_envelope=[lo.tolist(), hi.tolist()], family_max_pairwise_sep=fam_pair, cuda_pair_sep=cuda_pair)
     # epoch 1 (26 steps): every run is still on the same trajectory
-    for k, v in seps.items():
-        assert v[0] <= 3e-2, (k, v, table)
-    # later epochs: the CUDA runs separate from each other and from the oracle no more than a few times what a
-    # one-unit-in-the-last-place change of the initial W1 does to the oracle itself under the same numerics
-    # (+ 3 % slack: these are single samples of a chaotic system)
-    band = [4.0 * max(a, b) + 0.03 for a, b in zip(seps["oracle_tf32_1ulp_vs_oracle_tf32"], seps["oracle_1ulp_vs_oracle"])]
-    for k in ("cuda_148_vs_cuda_132", "cuda_148_vs_oracle_tf32", "cuda_132_vs_oracle_tf32"):
+    first = [r["loss"][0] for r in runs.values()]
+    assert max(first) / min(first) - 1.0 <= 3e-2, table
+    for name in ("cuda_148", "cuda_132"):
         for e in range(epochs):
-            assert seps[k][e] <= band[e], (k, e, seps, table)
+            v = runs[name]["loss"][e]
+            assert lo[e] - 1.5 * spread[e] - 0.03 * lo[e] <= v <= hi[e] + 1.5 * spread[e] + 0.03 * hi[e], (name, e, table)
+    for e in range(epochs):
+        assert cuda_pair[e] <= 2.0 * fam_pair[e] + 0.03, (e, cuda_pair, fam_pair, table)
     # and all of them learn: the third epoch's loss is well below the first's
     for n, r in runs.items():
         assert r["loss"][-1] < 0.8 * r["loss"][0], (n, r["loss"])

@@ -121,7 +121,7 @@ def test_matrix_input_matches_vcf_input(L, tmp_path):
 
 def test_batch_size_above_32_is_refused_loudly(L, tmp_path):
     vcf, sd, na = _write_inputs(tmp_path, 40, 100, 4)
-    with pytest.raises(Exception, match="batch_size"):
+    with pytest.raises(SystemExit, match="batch_size"):  # validate_args: before any data is read
         L.main(["--vcf", vcf, "--sample_data", sd, "--out", str(tmp_path / "o"), "--seed", "1", "--max_epochs", "2",
                 "--batch_size", "64", "--keras_verbose", "0"])
 

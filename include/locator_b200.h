@@ -116,6 +116,12 @@ int loc_pack_counts(const uint8_t* d_counts, int64_t n, int64_t K, uint32_t* d_p
                     int64_t row_words, void* stream);
 int loc_unpack_counts(const uint32_t* d_packed, int64_t n, int64_t K, int64_t row_words,
                       uint8_t* d_counts, void* stream);
+/* The same from a HOST matrix (the uint8 [n, K] traingen / testgen / predgen arrays the reference hands to
+ * model.fit / model.predict, :367-376, :414): row blocks staged through two pinned buffers by LOC_UPLOAD_THREADS
+ * host threads (default 4), copied and packed on `stream` while the next block is staged.  Returns once the
+ * last block is packed. */
+int loc_upload_pack_counts(const uint8_t* h_counts, int64_t n, int64_t K, uint32_t* d_packed,
+                           int64_t row_words, void* stream);
 
 /* out[r] = in[d_rows[r]] for r < n_out (sample split, :303-307). */
 int loc_gather_rows(const uint32_t* d_in, int64_t row_words, const int64_t* d_rows, int64_t n_out,

@@ -52,6 +52,7 @@ SIGNATURES = {
     "loc_patch_calls": (C.c_int, [P, I64, P, P, P, I64, P]),
     "loc_pack_counts": (C.c_int, [P, I64, I64, P, I64, P]),
     "loc_unpack_counts": (C.c_int, [P, I64, I64, I64, P, P]),
+    "loc_upload_pack_counts": (C.c_int, [P, I64, I64, P, I64, P]),
     "loc_gather_rows": (C.c_int, [P, I64, P, I64, P, P]),
     "loc_gather_cols": (C.c_int, [P, I64, I64, P, I64, P, I64, P]),
     "loc_replace_cols": (C.c_int, [P, I64, I64, P, I64, P, P]),

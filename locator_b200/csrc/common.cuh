@@ -78,6 +78,17 @@ struct DevState {
 };
 
 __device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : expm1f(z); }
+// Branch-free elu for the latency-critical tensor-core hidden stack: libdevice's expm1f is a ~40-instruction
+// dependent chain with data-dependent branches (the lanes of a warp diverge).  Here exp(z) - 1 comes from
+// ex2.approx (2 ulp of a value near 1, i.e. ~1.2e-7 absolute) for z <= -1/32 and from the series
+// z + z^2/2 + z^3/6 + z^4/24 above that (truncation < 3e-9 relative at |z| = 1/32): relative error <= ~4e-6
+// over the whole negative axis -- 250 times below the tf32 rounding the next layer applies to this value.
+__device__ __forceinline__ float elu_fast(float z) {
+  const float e = exp2f(z * 1.4426950408889634f) - 1.0f;
+  const float p = z * (1.0f + z * (0.5f + z * (0.16666667f + z * 0.041666668f)));
+  const float neg = z > -0.03125f ? p : e;
+  return z > 0.f ? z : neg;
+}
 // d elu / dz expressed through the activation value (EluGrad: out < 0 ? out + 1 : 1).
 __device__ __forceinline__ float elu_grad_from_out(float a) { return a > 0.f ? 1.f : a + 1.f; }
 

@@ -139,6 +139,11 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int u = 0; u < 2 && u < n_uses; ++u) issue_load(u);
   }
+  // Cluster start-up barrier, split: arrive now (this CTA is running and -- thread 0, in program order -- its
+  // mbarriers are initialised), wait just before the first write into a peer's shared memory, so the skew
+  // between the CTAs' start times hides under the split-K partial loads below
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(32u)
                  : "memory");
@@ -210,8 +215,6 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
   mark();
-  cluster_barrier();  // every CTA of the cluster is running before anyone writes into its shared memory
-  mark();
 
   int pub = 0;   // publishes so far: publish n uses stage / gathered buffer n & 1
   int nmma = 0;  // MMA batches so far (parity of mma_bar)
@@ -242,87 +245,114 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
     return gath + (n & 1) * kGath;
   };
   // One layer product on the tensor core: D[64 x 8] (TMEM) = A (weight-slice image) x B (gathered).
-  // Leaves z[b][jl] (fp32) in zbuf.
-  auto layer_mma = [&](int u, bool backward) {
-    const uint8_t* B = wait_gather(pub - 1);
-    mark();
-    mbar_wait(&wbar[u & 1], (uint32_t)(u >> 1) & 1u);
-    mark();
-    if (warp == 0 && elect_one()) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t wb = smem_u32(wslot + (u & 1) * kSlot), bb = smem_u32(B);
-      // base descriptors once per layer; the 32 K-steps only add compile-time constants to the
-      // 14-bit start-address field (a single thread issues: keep its instruction stream short).
-      // Four accumulators (TMEM columns 0-7, 8-15, 16-23, 24-31) take every 4th K-step so that
-      // consecutive MMAs do not wait on each other's accumulate; the epilogue adds them.
-      const uint64_t b0d = smem_desc(bb, 16, 1024, 2);
-      if (!backward) {  // A: MN-major [2 j-chunks][256 k rows][128 B], 32B-atom swizzle; 8 k rows = 1024 B per step
-        const uint64_t a0d = smem_desc(wb, kH * 128, 512, 1);
-        constexpr uint32_t idesc = make_idesc(64, 8, 1, 0);
+  // Only the four worker warps (tid < 128) run the layer chain: warp 0 waits for the operands and issues, all four
+  // read the accumulator (row m lives in TMEM lane 32*(m/16) + m%16: lanes 0-15 of each warp's quarter hold
+  // 16 columns x 8 batch rows) and hand rows 4-7 to lanes 16-31, so that every worker thread finishes
+  // z[b][jl] for jl = w_jl, b = w_b0 .. w_b0 + 3 straight from registers -- no shared-memory round trip and no
+  // block-wide barrier inside the chain.  The other warps sleep at the __syncthreads() behind the chain.
+  const int w_jl = 16 * warp + (lane & 15), w_b0 = 4 * (lane >> 4);
+  auto layer_mma = [&](int u, bool backward, float (&z)[4]) {
+    if (warp == 0) {
+      const uint8_t* B = wait_gather(pub - 1);
+      mark();
+      mbar_wait(&wbar[u & 1], (uint32_t)(u >> 1) & 1u);
+      mark();
+      if (elect_one()) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t wb = smem_u32(wslot + (u & 1) * kSlot), bb = smem_u32(B);
+        // base descriptors once per layer; the 32 K-steps only add compile-time constants to the
+        // 14-bit start-address field (a single thread issues: keep its instruction stream short).
+        // Four accumulators (TMEM columns 0-7, 8-15, 16-23, 24-31) take every 4th K-step so that
+        // consecutive MMAs do not wait on each other's accumulate; the epilogue adds them.
+        const uint64_t b0d = smem_desc(bb, 16, 1024, 2);
+        if (!backward) {  // A: MN-major [2 j-chunks][256 k rows][128 B], 32B-atom swizzle; 8 k rows = 1024 B per step
+          const uint64_t a0d = smem_desc(wb, kH * 128, 512, 1);
+          constexpr uint32_t idesc = make_idesc(64, 8, 1, 0);
 #pragma unroll
-        for (int ks = 0; ks < kH / 8; ++ks)
-          umma_tf32(tmem + (uint32_t)((ks & 3) * 8), a0d + (uint64_t)(ks * 64),
-                    b0d + (uint64_t)((ks >> 2) * 64 + (ks & 3) * 2), idesc, ks >= 4 ? 1u : 0u);
-      } else {          // A: K-major [8 k-chunks][8 row groups][8 rows][128 B], 128B swizzle
-        const uint64_t a0d = smem_desc(wb, 16, 1024, 2);
-        constexpr uint32_t idesc = make_idesc(64, 8, 0, 0);
+          for (int ks = 0; ks < kH / 8; ++ks)
+            umma_tf32(tmem + (uint32_t)((ks & 3) * 8), a0d + (uint64_t)(ks * 64),
+                      b0d + (uint64_t)((ks >> 2) * 64 + (ks & 3) * 2), idesc, ks >= 4 ? 1u : 0u);
+        } else {          // A: K-major [8 k-chunks][8 row groups][8 rows][128 B], 128B swizzle
+          const uint64_t a0d = smem_desc(wb, 16, 1024, 2);
+          constexpr uint32_t idesc = make_idesc(64, 8, 0, 0);
 #pragma unroll
-        for (int ks = 0; ks < kH / 8; ++ks)
-          umma_tf32(tmem + (uint32_t)((ks & 3) * 8), a0d + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2),
-                    b0d + (uint64_t)((ks >> 2) * 64 + (ks & 3) * 2), idesc, ks >= 4 ? 1u : 0u);
+          for (int ks = 0; ks < kH / 8; ++ks)
+            umma_tf32(tmem + (uint32_t)((ks & 3) * 8), a0d + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2),
+                      b0d + (uint64_t)((ks >> 2) * 64 + (ks & 3) * 2), idesc, ks >= 4 ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar))
+                     : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar))
-                   : "memory");
+      __syncwarp();
     }
     mbar_wait(&mma_bar, (uint32_t)nmma & 1u);
     mark();
-    ++nmma;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0 && u + 2 < n_uses) issue_load(u + 2);  // the slot is free: prefetch two uses ahead
-    if (warp < 4) {  // accumulator row m lives in TMEM lane 32*(m/16) + m%16
-      uint32_t v[32];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(tmem + ((uint32_t)(32 * warp) << 16))
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (lane < 16) {
-        const int jl = 16 * warp + lane;
+    uint32_t v[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(tmem + ((uint32_t)(32 * warp) << 16))
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // the next layer's MMAs overwrite these columns
+    float s8[8];
 #pragma unroll
-        for (int b = 0; b < kRB; ++b)
-          zbuf[b * kCW + jl] = (__uint_as_float(v[b]) + __uint_as_float(v[8 + b])) +
-                               (__uint_as_float(v[16 + b]) + __uint_as_float(v[24 + b]));
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    for (int b = 0; b < kRB; ++b)
+      s8[b] = (__uint_as_float(v[b]) + __uint_as_float(v[8 + b])) + (__uint_as_float(v[16 + b]) + __uint_as_float(v[24 + b]));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float hi = __shfl_sync(0xffffffffu, s8[4 + i], lane & 15);  // rows 4..7 go to lanes 16..31
+      z[i] = lane < 16 ? s8[i] : hi;
     }
-    __syncthreads();
     mark();
+  };
+  // worker warps: the own [8 x 64] slice is staged -> to the 4 CTAs of the batch group
+  auto publish_workers = [&]() {
+    mark();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mark();
+    if (lane == 0) {
+      const uint32_t src = smem_u32(stage + (pub & 1) * kStage);
+      const uint32_t dst_local = smem_u32(gath + (pub & 1) * kGath + cj * kStage);
+      const uint32_t bar_local = smem_u32(&ready[pub & 1]);
+      const unsigned dest = (unsigned)(rb * 4 + warp);
+      uint32_t dst, bar;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(dst_local), "r"(dest));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(bar_local), "r"(dest));
+      asm volatile(
+          "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+          "r"(src), "r"((uint32_t)kStage), "r"(bar)
+          : "memory");
+    }
   };
   auto stage_store = [&](int b, int jl, float v) {
     *reinterpret_cast<float*>(stage + (pub & 1) * kStage + b_off(b, jl)) = to_tf32(v);
   };
+  // dropout multiplier of element (row b, column jl) of the layer in front of the Dropout (1 when dropout is off)
+  auto drop_mult = [&](int b, int jl) -> float {
+    if (!drop_on) return 1.f;
+    bool kp;
+    if (a.masks != nullptr) {
+      const int64_t s = step_id < a.n_masks ? step_id : a.n_masks - 1;
+      kp = a.masks[(s * kMaxB + b0 + b) * kH + j0 + jl] != 0;
+    } else {
+      kp = philox_uniform((uint64_t)(b0 + b) * kH + j0 + jl, kDropoutStreamBase + (uint32_t)step_id, a.seed) >= a.p_drop;
+    }
+    return kp ? keep_scale : 0.f;
+  };
   auto finish_fwd_elem = [&](int i, int b, int jl, float z) {
-    float act = elu_f(z + sbias[i * kCW + jl]);
+    float act = elu_fast(z + sbias[i * kCW + jl]);
     own_a[(i * kRB + b) * kCW + jl] = act;
     if (i == a.n_before - 1) {
-      float mult = 1.f;
-      if (drop_on) {
-        bool kp;
-        if (a.masks != nullptr) {
-          const int64_t s = step_id < a.n_masks ? step_id : a.n_masks - 1;
-          kp = a.masks[(s * kMaxB + b0 + b) * kH + j0 + jl] != 0;
-        } else {
-          kp = philox_uniform((uint64_t)(b0 + b) * kH + j0 + jl, kDropoutStreamBase + (uint32_t)step_id, a.seed) >=
-               a.p_drop;
-        }
-        mult = kp ? keep_scale : 0.f;
-        act *= mult;
-      }
+      const float mult = drop_mult(b, jl);
+      act *= mult;
       keep[b * kCW + jl] = mult;
     }
     const float out = (b0 + b) < nb ? act : 0.f;
@@ -331,11 +361,53 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
     // off the critical path, instead of in a loop at the end of the kernel
     if (a.training) a.acts[((int64_t)i * kMaxB + b0 + b) * kH + j0 + jl] = out;
   };
+  // the same for rows bq .. bq + 3 of one column (worker threads of the layer chain): the four elu chains are
+  // independent, every load comes before every store
+  auto finish_fwd4 = [&](int i, int bq, int jl, const float (&z)[4]) {
+    const float bias = sbias[i * kCW + jl];
+    float act[4], out[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) act[e] = elu_fast(z[e] + bias);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) own_a[(i * kRB + bq + e) * kCW + jl] = act[e];
+    if (i == a.n_before - 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float mult = drop_mult(bq + e, jl);
+        act[e] *= mult;
+        keep[(bq + e) * kCW + jl] = mult;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      out[e] = (b0 + bq + e) < nb ? act[e] : 0.f;
+      stage_store(bq + e, jl, out[e]);
+    }
+    if (a.training) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a.acts[((int64_t)i * kMaxB + b0 + bq + e) * kH + j0 + jl] = out[e];
+    }
+  };
   auto finish_bwd_elem = [&](int i, int b, int jl, float da) {
     if (i == a.n_before - 1) da *= keep[b * kCW + jl];
     const float dz = (b0 + b) < nb ? da * elu_grad_from_out(own_a[(i * kRB + b) * kCW + jl]) : 0.f;
     stage_store(b, jl, dz);
     a.dzs[((int64_t)i * kMaxB + b0 + b) * kH + j0 + jl] = dz;
+  };
+  auto finish_bwd4 = [&](int i, int bq, int jl, const float (&da)[4]) {
+    float g[4], dz[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      g[e] = elu_grad_from_out(own_a[(i * kRB + bq + e) * kCW + jl]);
+      if (i == a.n_before - 1) g[e] *= keep[(bq + e) * kCW + jl];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      dz[e] = (b0 + bq + e) < nb ? da[e] * g[e] : 0.f;
+      stage_store(bq + e, jl, dz[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) a.dzs[((int64_t)i * kMaxB + b0 + bq + e) * kH + j0 + jl] = dz[e];
   };
 
   // ---- layer 0: finish the split-K reduction started in the prologue ----
@@ -349,6 +421,8 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
                       (red[(2 * kRB + bb) * kCW + jj] + red[(3 * kRB + bb) * kCW + jj]);
       finish_fwd_elem(0, bb, jj, z);
     }
+    mark();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // every CTA of the cluster is running
     publish_staged();
     mark();
   }
@@ -356,10 +430,16 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   // ---- layers 1..L-1 forward ----
   int use = 0;
   for (int i = 1; i < L; ++i, ++use) {
-    layer_mma(use, false);
-    for (int idx = tid; idx < kRB * kCW; idx += kThreads) finish_fwd_elem(i, idx / kCW, idx % kCW, zbuf[idx]);
-    publish_staged();
+    if (warp < 4) {
+      float z[4];
+      layer_mma(use, false, z);
+      finish_fwd4(i, w_b0, w_jl, z);
+      publish_workers();
+    }
+    ++pub;
+    ++nmma;
   }
+  __syncthreads();  // the other warps rejoin: everything the chain left in shared memory is visible to them
 
   // ---- Dense(2), Dense(2), loss for the own 8 rows (the 4 CTAs of a batch group agree) ----
   const uint8_t* gat = wait_gather(pub - 1);  // a_{L-1} of the own rows (tf32-rounded)
@@ -426,13 +506,16 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
     }
     publish_staged();
     for (int i = L - 1; i >= 1; --i, ++use) {
-      layer_mma(use, true);
-      for (int idx = tid; idx < kRB * kCW; idx += kThreads) finish_bwd_elem(i - 1, idx / kCW, idx % kCW, zbuf[idx]);
-      if (i > 1)
-        publish_staged();
-      else
-        __syncthreads();
+      if (warp < 4) {
+        float z[4];
+        layer_mma(use, true, z);
+        finish_bwd4(i - 1, w_b0, w_jl, z);
+        if (i > 1) publish_workers();
+      }
+      if (i > 1) ++pub;
+      ++nmma;
     }
+    __syncthreads();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_barrier();  // nobody exits while peers may still address its shared memory; global writes visible

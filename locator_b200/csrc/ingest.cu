@@ -4,6 +4,10 @@
 // Reference semantics (locator/locator.py): filter_snps :265-281 (allel count_alleles /
 // is_biallelic / to_allele_counts()[:, :, 1]), split_train_test :303-307, bootstrap gather
 // :651-653, jacknife replace :726-727, replace_md :258-261.
+#include <mutex>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace loc {
@@ -598,6 +602,87 @@ int loc_pack_counts(const uint8_t* d_counts, int64_t n, int64_t K, uint32_t* d_p
   dim3 grid((unsigned)cdiv(row_words, 256), (unsigned)n);
   k_pack_counts<<<grid, 256, 0, (cudaStream_t)stream>>>(d_counts, n, K, d_packed, row_words);
   LOC_LAUNCHED();
+  return 0;
+}
+
+// Host matrix -> packed device matrix without a pageable cudaMemcpy of the whole thing: row blocks are copied
+// into two pinned staging buffers by a few host threads (a single memcpy thread moves ~10 GB/s, the link several
+// times that), sent with cudaMemcpyAsync and packed on the device while the next block is being staged.
+namespace {
+struct UploadStage {
+  uint8_t* h[2] = {nullptr, nullptr};
+  uint8_t* d[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};  // the block's pack kernel has finished (its buffers are reusable)
+  size_t bytes = 0;
+  int dev = -1;
+};
+UploadStage g_up;
+std::mutex g_up_mu;
+
+void parallel_copy(uint8_t* dst, const uint8_t* src, size_t bytes, int threads) {
+  if (threads <= 1 || bytes < (size_t)4 << 20) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> ts;
+  const size_t per = (bytes / threads + 4095) & ~(size_t)4095;
+  for (int t = 0; t < threads; ++t) {
+    const size_t o = (size_t)t * per;
+    if (o >= bytes) break;
+    const size_t nbytes = bytes - o < per ? bytes - o : per;
+    ts.emplace_back([=] { memcpy(dst + o, src + o, nbytes); });
+  }
+  for (auto& t : ts) t.join();
+}
+}  // namespace
+
+int loc_upload_pack_counts(const uint8_t* h_counts, int64_t n, int64_t K, uint32_t* d_packed, int64_t row_words,
+                           void* stream) {
+  LOC_CHECK(h_counts != nullptr && d_packed != nullptr, "loc_upload_pack_counts: null pointer");
+  LOC_CHECK(row_words >= cdiv(K, 16) && row_words % 4 == 0, "loc_upload_pack_counts: bad row_words");
+  if (n <= 0 || K <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lk(g_up_mu);
+  int dev = 0;
+  LOC_CUDA(cudaGetDevice(&dev));
+  const size_t kStageBytes = (size_t)16 << 20;
+  const size_t want = (size_t)K > kStageBytes ? (size_t)K : kStageBytes;
+  if (g_up.dev != dev || g_up.bytes < want) {
+    for (int i = 0; i < 2; ++i) {
+      if (g_up.h[i]) cudaFreeHost(g_up.h[i]);
+      if (g_up.d[i]) cudaFree(g_up.d[i]);
+      if (g_up.done[i]) cudaEventDestroy(g_up.done[i]);
+      g_up.h[i] = g_up.d[i] = nullptr;
+      g_up.done[i] = nullptr;
+    }
+    g_up.bytes = 0;
+    for (int i = 0; i < 2; ++i) {
+      LOC_CUDA(cudaMallocHost(&g_up.h[i], want));
+      LOC_CUDA(cudaMalloc(&g_up.d[i], want));
+      LOC_CUDA(cudaEventCreateWithFlags(&g_up.done[i], cudaEventDisableTiming));
+    }
+    g_up.bytes = want;
+    g_up.dev = dev;
+  }
+  static const int threads = [] {
+    const char* e = getenv("LOC_UPLOAD_THREADS");
+    int v = e != nullptr ? atoi(e) : 4;
+    return v < 1 ? 1 : (v > 16 ? 16 : v);
+  }();
+  int64_t rows_per = (int64_t)(g_up.bytes / (size_t)K);
+  if (rows_per > 65535) rows_per = 65535;
+  int blk = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += rows_per, ++blk) {
+    const int64_t nr = n - r0 < rows_per ? n - r0 : rows_per;
+    const int b = blk & 1;
+    if (blk >= 2) LOC_CUDA(cudaEventSynchronize(g_up.done[b]));  // the block that used these buffers is packed
+    parallel_copy(g_up.h[b], h_counts + r0 * K, (size_t)(nr * K), threads);
+    LOC_CUDA(cudaMemcpyAsync(g_up.d[b], g_up.h[b], (size_t)(nr * K), cudaMemcpyHostToDevice, s));
+    if (loc_pack_counts(g_up.d[b], nr, K, d_packed + r0 * row_words, row_words, stream)) return 1;
+    LOC_CUDA(cudaEventRecord(g_up.done[b], s));
+  }
+  // the staging buffers are shared by later calls (possibly on other streams): drained before returning
+  for (int b = 0; b < 2 && b < blk; ++b) LOC_CUDA(cudaEventSynchronize(g_up.done[b]));
   return 0;
 }
 

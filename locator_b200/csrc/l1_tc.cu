@@ -516,12 +516,19 @@ __global__ void __launch_bounds__(W_THREADS, 1) k_l1_fwd_wide(L1Args a, int64_t 
 // ---------------------------------------------------------------------------------------------
 // Backward + Adam
 // ---------------------------------------------------------------------------------------------
+#ifndef LOC_FWD_WARPS
+#define LOC_FWD_WARPS 4  // forward warps of the fused backward (2 or 4): each takes every LOC_FWD_WARPS-th chunk
+#endif
 constexpr int B_NT = 64;                       // SNPs per tile (one accumulator buffer)
 constexpr int B_CH = 8;                        // SNPs per streamed chunk (one W/m/v stage)
 constexpr int B_STAGES = 5;
 constexpr int B_RING = 2 * B_STAGES;             // barrier ring: one per (epilogue group, stage)
 constexpr int B_EPI_WARPS = 16;                // two groups of 8: group g owns the chunks with index % 2 == g
-constexpr int B_THREADS = (B_EPI_WARPS + 6) * 32;  // + 2 builder warps, load warp, store warp, 2 forward warps
+constexpr int B_NFW = LOC_FWD_WARPS;            // forward warps (fused runs)
+constexpr int B_THREADS = (B_EPI_WARPS + 4 + B_NFW) * 32;  // + 2 builder warps, load warp, store warp, forward warps
+// warp roles after the epilogue warps and the two builder warps; the forward warps land on different schedulers
+constexpr int W_LOAD = B_EPI_WARPS + 2, W_STORE = B_EPI_WARPS + 3, W_FWD0 = B_EPI_WARPS + 4;
+static_assert(B_NFW == 2 || B_NFW == 4, "forward warps: 2 or 4 (TMEM columns 256 + 64 per warp)");
 constexpr int B_DZ = kMaxB * kH * 4;           // 32 KB: [8 chunks][32 rows (b)][128 B]
 constexpr int B_DZ_CHUNK = kMaxB * 128;        // 4096
 constexpr int B_X = B_NT * 128;                // 8 KB: [64 rows (SNP)][32 batch]
@@ -611,20 +618,20 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       mbar_init(&st_done[s], 8);
     }
     for (int s = 0; s < B_STAGES; ++s) mbar_init(&st_free[s], (fuse && !(a.dbg_flags & 8)) ? 2 : 1);  // written back (+ consumed by the forward MMA)
-    mbar_init(fwd_done, 2);  // one commit per forward warp
-    mbar_init(&fwd_tile[0], 2);
-    mbar_init(&fwd_tile[1], 2);
+    mbar_init(fwd_done, B_NFW);  // one commit per forward warp
+    mbar_init(&fwd_tile[0], B_NFW);
+    mbar_init(&fwd_tile[1], B_NFW);
     fence_barrier_init();
   }
   if (warp == B_EPI_WARPS) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();  // barriers and TMEM are ready: the load warp starts streaming W1 | m | v right away ...
   tc_fence_after();
-  if (warp != B_EPI_WARPS + 2) {
+  if (warp != W_LOAD) {
     // ... while everybody else stages dZ1 -> hi/lo tf32 operands, [chunk = j/32][row = b][swizzled 32 j]
     // (all of a thread's loads first: one L2 round trip instead of three)
     constexpr int kIters = (kMaxB * kH / 4 + B_THREADS - 33) / (B_THREADS - 32);
-    const int t = threadIdx.x < (B_EPI_WARPS + 2) * 32 ? threadIdx.x : threadIdx.x - 32;  // skip the load warp
+    const int t = threadIdx.x < W_LOAD * 32 ? threadIdx.x : threadIdx.x - 32;  // skip the load warp
     float4 v[kIters];
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
@@ -730,15 +737,21 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     if (fuse && grp == 0 && !(a.dbg_flags & 32)) {  // next step's split-K partial tile of Z1: accumulator row = j, column = batch row
       mbar_wait(fwd_done, 0);
       tc_fence_after();
-      uint32_t r32[32], r33[32];
-      tmem_ld_x32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 + h * 32), r32);
-      tmem_ld_x32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 + 64 + h * 32), r33);
-      tmem_ld_wait();
+      // the forward warps accumulated into their own TMEM columns: added here in warp order
+      float acc[32];
+#pragma unroll
+      for (int w = 0; w < B_NFW; ++w) {
+        uint32_t r32[32];
+        tmem_ld_x32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 + w * 64 + h * 32), r32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int b = 0; b < kMaxB; ++b) acc[b] = w == 0 ? __uint_as_float(r32[b]) : acc[b] + __uint_as_float(r32[b]);
+      }
       float* out = a.partials + (int64_t)blockIdx.x * kMaxB * kH + j;
 #pragma unroll
-      for (int b = 0; b < kMaxB; ++b) out[b * kH] = __uint_as_float(r32[b]) + __uint_as_float(r33[b]);
+      for (int b = 0; b < kMaxB; ++b) out[b * kH] = acc[b];
     }
-  } else if (warp == B_EPI_WARPS + 2) {
+  } else if (warp == W_LOAD) {
     // =========================== load warp: W, m, v chunk -> stage ===========================
     if (elect_one()) {
       for (int c = 0; c < nchunks; ++c) {
@@ -754,7 +767,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
         bulk_load(dst + 2 * B_ARR, a.vW1 + off, B_ARR, full, pol);
       }
     }
-  } else if (warp == B_EPI_WARPS + 3) {
+  } else if (warp == W_STORE) {
     // =========================== store warp: updated chunk -> W, m, v ===========================
     // two bulk-store groups in flight: a stage is released once the store issued before the latest
     // one has finished reading shared memory
@@ -778,13 +791,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       mbar_arrive(&st_free[(nchunks - 1) % B_STAGES]);
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
-  } else if (warp >= B_EPI_WARPS + 4) {
+  } else if (warp >= W_FWD0) {
     // ====== forward warps (fused runs), alternating chunks: per chunk, gamma/beta Adam, the next batch's
     //        BN statistics and xhat rows, and the forward MMA on the chunk of W1 just updated in the stage.
     //        Each warp accumulates into its own TMEM columns; the epilogue adds the two. ======
     if (fuse) {
       constexpr uint32_t idesc_f = make_idesc(128, 32, 1, 1);
-      const int fw = warp - (B_EPI_WARPS + 4);
+      const int fw = warp - W_FWD0;
       const int nbn = a.src_next.nb;
       const int64_t nrow = lane < nbn ? row_of(a.src_next, a.st, lane) : 0;
       const uint32_t* nptr = a.packed + nrow * a.row_words;
@@ -812,8 +825,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
         return p;
       };
       Pre cur = prefetch(fw);
-      for (int c = fw; c < nchunks; c += 2) {
-        const Pre nxt = prefetch(c + 2);  // one chunk of this warp ahead: hides the global-load latency
+      for (int c = fw; c < nchunks; c += B_NFW) {
+        const Pre nxt = prefetch(c + B_NFW);  // one chunk of this warp ahead: hides the global-load latency
         const int li = c >> 3, cc = c & 7, buf = li & 1, s = c % B_STAGES;
         const int64_t k0 = tile_of(c >> 3) * B_NT + (int64_t)(c & 7) * B_CH;
         const int64_t k = k0 + r;
@@ -845,14 +858,14 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
           Q += pr.y;
         }
         const float rs = sSc[buf * B_NT + cc * 8 + r].z;
-        if (cc >= 6) {  // this warp's last chunk of the tile: its sSc / sRed reads are done
+        if (cc >= 8 - B_NFW) {  // this warp's last chunk of the tile: its sSc / sRed reads are done
           __syncwarp();
           if (lane == 0) mbar_arrive(&fwd_tile[buf]);
         }
         float gm = cur.gm, mg = cur.mg, vg = cur.vg, bt = cur.bt, mb = cur.mb, vb = cur.vb;
         if (!(a.dbg_flags & 2)) {
-          adam_update(gm, mg, vg, rs * P, alpha);
-          adam_update(bt, mb, vb, Q, alpha);
+          adam_update_fast(gm, mg, vg, rs * P, alpha);
+          adam_update_fast(bt, mb, vb, Q, alpha);
         }
         const float inv = rsn * gm;
         const float shift = bt - mean * inv;
@@ -881,7 +894,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
             umma_tf32(tmem + (uint32_t)(256 + fw * 64 + hh * 32), smem_desc(wbs + hh * 4096, 1024, 512, kLayoutSw128B32),
                       bdesc, idesc_f, c > fw ? 1u : 0u);
           if (!(a.dbg_flags & 8)) umma_commit(&st_free[s]);
-          if (c + 2 >= nchunks) umma_commit(fwd_done);
+          if (c + B_NFW >= nchunks) umma_commit(fwd_done);
         }
         __syncwarp();
         if (valid && lane < 8 && !(a.dbg_flags & 2)) {  // off the stage's critical path
@@ -928,14 +941,14 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
       }
       if (k < a.K) {
         float gm = gam_[buf], m = mg_[buf], v = vg_[buf];
-        adam_update(gm, m, v, rs_[buf] * P, alpha);
+        adam_update_fast(gm, m, v, rs_[buf] * P, alpha);
         a.gamma[k] = gm;
         a.m_gamma[k] = m;
         a.v_gamma[k] = v;
         float bt = bet_[buf];
         m = mb_[buf];
         v = vb_[buf];
-        adam_update(bt, m, v, Q, alpha);
+        adam_update_fast(bt, m, v, Q, alpha);
         a.beta[k] = bt;
         a.m_beta[k] = m;
         a.v_beta[k] = v;

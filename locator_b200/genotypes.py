@@ -77,6 +77,14 @@ class PackedGenotypes:
     @staticmethod
     def from_counts(counts) -> "PackedGenotypes":
         """counts: uint8 [n, K] array/tensor (host or device) -> packed on the GPU."""
+        if isinstance(counts, np.ndarray) and counts.ndim == 2 and counts.size:
+            # host matrix: pinned double-buffered upload + pack (no pageable copy of the whole matrix)
+            h = np.ascontiguousarray(counts, dtype=np.uint8)
+            n, K = h.shape
+            out = PackedGenotypes.empty(n, K)
+            check(lib.loc_upload_pack_counts(h.ctypes.data, n, K, out.ptr, out.row_words, _stream()),
+                  "loc_upload_pack_counts")
+            return out
         c = _as_dev(counts, torch.uint8)
         n, K = c.shape
         out = PackedGenotypes.empty(n, K)

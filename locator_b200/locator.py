@@ -93,6 +93,10 @@ def build_parser():
     # extension of this build (kept out of params.json)
     parser.add_argument("--gpus", default=1, type=int,
                         help="(locator_b200) GPUs of this box to spread --bootstrap / --windows replicates over. default: 1")
+    parser.add_argument("--load_weights", default=None,
+                        help="(locator_b200) predict from a weights file written by --keep_weights (.weights.npz, Keras "
+                        "weight order; see python -m locator_b200.keras_weights for .weights.h5) instead of training: "
+                        "with --jacknife a prediction-only sweep on the stored model. default: None")
     parser.add_argument("--replicates_per_gpu", default=4, type=int,
                         help="(locator_b200) bootstrap / window models trained side by side on each GPU (1-8; neither "
                         "the indices nor the predictions depend on it). default: 4")
@@ -458,10 +462,19 @@ def _run_one(traingen, testgen, trainlocs, testlocs, predgen, norm, pred, sample
     meanlong, sdlong, meanlat, sdlat = norm
     model = load_network(traingen, args.dropout_prop)
     callbacks = load_callbacks(cb_boot)
-    history, model = train_network(model, traingen, testgen, trainlocs, testlocs, callbacks, boot)
+    if getattr(args, "load_weights", None):
+        # prediction from stored weights (the reference only ever reloads the checkpoint of the run itself,
+        # locator.py:380,386): no training, an empty history
+        from .model import History
+
+        model.load_weights(args.load_weights)
+        print("loaded weights from " + str(args.load_weights))
+        history = History()
+    else:
+        history, model = train_network(model, traingen, testgen, trainlocs, testlocs, callbacks, boot)
     dists = predict_locs(model, predgen, sdlong, meanlong, sdlat, meanlat, testlocs, pred, samples, testgen, history,
                          boot)
-    if args.plot_history:
+    if args.plot_history and history.history["loss"]:
         plot_history(history, dists)
     return model, history, dists
 
@@ -515,10 +528,10 @@ def main(argv=None):
     if args.gpu_number is not None:
         os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu_number
     if args.load_params is not None:
-        gpus, rpg = args.gpus, args.replicates_per_gpu
+        gpus, rpg, lw = args.gpus, args.replicates_per_gpu, args.load_weights
         with open(args.load_params, "r") as f:
             args.__dict__ = json.load(f)
-        args.gpus, args.replicates_per_gpu = gpus, rpg
+        args.gpus, args.replicates_per_gpu, args.load_weights = gpus, rpg, lw
     if args.seed is not None:
         np.random.seed(args.seed)
     if args.gpu_number is not None:

@@ -16,7 +16,7 @@ from locator_b200 import model, _cabi  # noqa: E402
 
 lib = _cabi.lib
 K, B = int(os.environ.get("PROBE_K", "100000")), 32
-ctas = os.environ.get("PROBE_CTAS")
+ctas = os.environ.get("PROBE_CTAS") or None
 rng = np.random.default_rng(0)
 n = 128
 x = rng.binomial(2, rng.uniform(0.05, 0.95, K), size=(n, K)).astype(np.uint8)
@@ -38,7 +38,10 @@ for _ in range(5):
     stage(2)
 torch.cuda.synchronize()
 reps = int(os.environ.get("PROBE_REPS", "40"))
-for bwd_stage, flags in [(2, 0), (4, 0), (4, 1), (4, 2), (4, 4), (4, 8), (4, 32), (4, 7), (4, 15), (4, 47), (4, 0), (2, 0)]:
+settings = [(2, 0), (4, 0), (4, 1), (4, 2), (4, 4), (4, 32), (4, 7), (4, 39), (4, 0), (2, 0)]
+if os.environ.get("PROBE_FLAGS"):  # "stage:flags,stage:flags,..."
+    settings = [tuple(int(v) for v in p.split(":")) for p in os.environ["PROBE_FLAGS"].split(",")]
+for bwd_stage, flags in settings:
     os.environ["LOC_FUSE_DEBUG"] = str(flags)
     times = []
     for r in range(reps + 3):

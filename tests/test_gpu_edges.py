@@ -169,6 +169,12 @@ def test_weights_file_round_trip_and_load_params(L, tmp_path):
         json.dump(params, fh)
     assert L.main(["--load_params", str(tmp_path / "p.json"), "--out", "ignored"]) == 0
     assert open(str(tmp_path / "again") + "_predlocs.txt").read() == first
+    # --load_weights: prediction from the stored weights, no training; same predictions, empty history
+    out2 = str(tmp_path / "frozen")
+    assert L.main(["--vcf", vcf, "--sample_data", sd, "--out", out2, "--seed", "21", "--keras_verbose", "0",
+                   "--load_weights", out + ".weights.npz"]) == 0
+    assert open(out2 + "_predlocs.txt").read() == first
+    assert len(open(out2 + "_history.txt").read().splitlines()) == 1
 
 
 def test_too_many_max_snps_fails_like_numpy(L, tmp_path):

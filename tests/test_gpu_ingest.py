@@ -237,3 +237,21 @@ def test_site_sums_match_numpy(G, n, K):
     sums = p.site_sums().cpu().numpy()
     assert sums.dtype == np.int64
     assert np.array_equal(sums, x.astype(np.int64).sum(axis=0))
+
+
+@pytest.mark.parametrize("n,K", [(1, 1), (7, 33), (300, 5830), (700, 30001), (40, 900_001)])
+def test_host_upload_pack_equals_device_pack(G, n, K):
+    """from_counts on a HOST uint8 matrix (loc_upload_pack_counts: pinned double-buffered row blocks, packed
+    while the next block is staged) gives the same words as packing a device copy (loc_pack_counts), across the
+    staging-block boundary (16 MB) and for rows longer than a block's share."""
+    import torch
+
+    rng = np.random.default_rng(n + K)
+    x = rng.integers(0, 3, size=(n, K), dtype=np.uint8)
+    a = G.PackedGenotypes.from_counts(x)
+    b = G.PackedGenotypes.from_counts(torch.as_tensor(x).cuda())
+    assert a.row_words == b.row_words and torch.equal(a.words, b.words)
+    assert np.array_equal(a.to_numpy(), x)
+    # a non-contiguous view (the reference slices ac[:, idx] before fit)
+    c = G.PackedGenotypes.from_counts(x[:, ::-1][:, ::-1][::2])
+    assert np.array_equal(c.to_numpy(), x[::2])

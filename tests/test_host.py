@@ -399,7 +399,7 @@ def test_command_line_matches_the_reference_parser(golden_dir):
         assert json.dumps(L._params_dict(ns), indent=2) == case["params_json"], case["argv"]
     ours = {a.option_strings[0] for a in L.build_parser()._actions if a.option_strings}
     assert set(vec["cli_help_flags"]) <= ours
-    assert ours - set(vec["cli_help_flags"]) == {"--gpus", "--replicates_per_gpu"}
+    assert ours - set(vec["cli_help_flags"]) == {"--gpus", "--replicates_per_gpu", "--load_weights"}
 
 
 def test_matrix_reader_matches_the_reference_branch(golden_dir):
@@ -505,3 +505,23 @@ def test_legacy_permutation_reproduces_numpy_global_stream():
     assert np.array_equal(legacy_choice_without_replacement(5830, 291), want) and np.random.random() == x
     with pytest.raises(ValueError):
         legacy_choice_without_replacement(10, 11)
+
+
+def test_keras_weights_converter_host_side(tmp_path):
+    """locator_b200.keras_weights: Keras-order npz files, shape checks against the reference network
+    (load_network, locator.py:317-326), and a clear refusal where Keras itself is missing."""
+    from locator_b200 import keras_weights as kw
+    from oracle import model_ref
+
+    ws = model_ref.init_weights(300, width=64, nlayers=4, seed=3)
+    assert [tuple(w.shape) for w in ws] == kw.expected_shapes(300, 4, 64)
+    p = str(tmp_path / "m.weights.npz")
+    kw.write_npz(p, ws)
+    back = kw.read_npz(p)
+    assert kw.describe(back) == (300, 4, 64)
+    assert all(np.array_equal(a, b) for a, b in zip(ws, back))
+    with pytest.raises(ValueError):
+        kw.describe(ws[:-2] + [np.zeros((3, 2), np.float32), ws[-1]])
+    assert kw.main(["describe", p]) == 0
+    if kw._keras() is None:
+        assert kw.main(["to-h5", p, str(tmp_path / "m.weights.h5")]) == 2

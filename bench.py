@@ -483,7 +483,8 @@ def main():
         G = args.group
         gval = model.PackedGenotypes.from_counts(xva)
 
-        def measure_group(l1_ctas):
+        def measure_group(l1_ctas, schedule):
+            os.environ["LOC_GROUP_SCHEDULE"] = schedule
             gm = [model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=16,
                                      seed=500 + rank * 16 + g, l1_ctas=l1_ctas) for g in range(G)]
             for q in gm:
@@ -509,11 +510,12 @@ def main():
             gms = max_over_ranks(g0.elapsed_time(g1), "cuda")
             loss = float(gm[0].state().last_loss)
             del gm
+            os.environ.pop("LOC_GROUP_SCHEDULE", None)
             return {"epochs": ne_g, "value": world * G * ne_g * ntr / (gms / 1000.0),
                     "ms_per_step_per_replicate": gms / (ne_g * spe * G), "last_loss_model0": loss}
 
-        ring = measure_group(model.spare_cluster_l1_ctas())
-        lock = measure_group(None)
+        ring = measure_group(None, "ring")       # default first-layer CTA count: SMs - 16
+        lock = measure_group(148, "lockstep")    # every SM for the first-layer kernels, hidden stacks in one launch
         group = {"replicates_per_gpu": G, "epochs": ring["epochs"], "value": ring["value"],
                  "unit": "samples/s (all replicates)", "ms_per_step_per_replicate": ring["ms_per_step_per_replicate"],
                  "schedule": "ring", "lockstep": lock, "ring": ring,

@@ -179,6 +179,10 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
  * of ~35 cudaMalloc / cudaFree calls per replicate.  loc_model_pool_clear() releases the pool's device memory. */
 int loc_model_destroy(loc_model* m);
 int loc_model_pool_clear(void);
+/* Diagnostics (LOC_TIMELINE=1 in the environment before the first model is created): the step kernels log
+ * (globaltimer ns, tag << 32 | model number) at the start and end of their first and last blocks; this copies up
+ * to max_records pairs to h_out, clears the log and returns the number of records. */
+int64_t loc_debug_timeline(uint64_t* h_out, int64_t max_records);
 /* First-layer kernel family this model actually runs: "tcgen05" or "simt". */
 const char* loc_model_impl(const loc_model* m);
 

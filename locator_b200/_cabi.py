@@ -65,6 +65,7 @@ SIGNATURES = {
     "loc_model_create": (C.c_int, [C.POINTER(P), I64, I32, I32, I32, C.c_float, I32]),
     "loc_model_destroy": (C.c_int, [P]),
     "loc_model_pool_clear": (C.c_int, []),
+    "loc_debug_timeline": (I64, [P, I64]),
     "loc_model_impl": (C.c_char_p, [P]),
     "loc_model_init": (C.c_int, [P, C.c_uint64, P]),
     "loc_model_num_weights": (C.c_int, [P]),

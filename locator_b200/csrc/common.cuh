@@ -75,7 +75,39 @@ struct DevState {
   int max_epochs;
   int nonfinite;
   float last_loss, last_val;
+  // Hand-over flags of the programmatic-dependent-launch chain (model.cu: train_step): kernels of one step are
+  // launched before their producers have finished and wait here instead of at a kernel boundary.
+  unsigned hid_seq;  // number of training hidden-stack launches completed (published at the kernel's very end)
+  unsigned bwd_cnt;  // CTAs of first-layer backward launches completed, cumulative
 };
+
+// Spin until *flag has reached `expect` (wrap-safe); gives up after ~2 s and raises *err instead of hanging the GPU.
+__device__ __forceinline__ void wait_counter(const unsigned* flag, unsigned expect, int* err) {
+  const long long t0 = clock64();
+  while (true) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if ((int)(v - expect) >= 0) break;
+    if (clock64() - t0 > 4000000000ll) {
+      if (err != nullptr) *err = 1;
+      break;
+    }
+    __nanosleep(256);
+  }
+}
+
+// Kernel timeline (LOC_TIMELINE=1, diagnostics): tl[0] = record count, then (globaltimer ns, tag << 32 | id) pairs.
+constexpr unsigned kTlCap = 1u << 16;
+__device__ __forceinline__ void tl_mark(unsigned long long* tl, unsigned tag, unsigned id) {
+  if (tl == nullptr) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const unsigned idx = atomicAdd(reinterpret_cast<unsigned*>(tl), 1u);
+  if (idx < kTlCap) {
+    tl[1 + 2 * (size_t)idx] = t;
+    tl[2 + 2 * (size_t)idx] = ((unsigned long long)tag << 32) | id;
+  }
+}
 
 __device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : expm1f(z); }
 // Branch-free elu for the latency-critical tensor-core hidden stack: libdevice's expm1f is a ~40-instruction

@@ -521,7 +521,13 @@ constexpr int kUpdRows = 16;
 
 // (register cap: its blocks must fit beside the resident first-layer backward CTAs, which it overlaps)
 __global__ void __maxnreg__(56) k_hidden_update(UpdArgs a) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next hidden stack may be scheduled behind us
   if (a.gated && a.st->stopped) return;
+  if (a.wait_hid != 0) {  // launched ahead of the end of the hidden stack whose activations / dz it consumes
+    if (threadIdx.x == 0) wait_counter(&a.st->hid_seq, a.wait_hid, &a.st->nonfinite);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) tl_mark(a.tl, blockIdx.x ? 21u : 5u, (unsigned)a.tl_id);
   __shared__ float as[kUpdRows][kMaxB + 1];
   const int H = a.H, L = a.L, j = threadIdx.x;
   const SmallLayout sl{H, L};
@@ -596,6 +602,7 @@ __global__ void __maxnreg__(56) k_hidden_update(UpdArgs a) {
       adam_at(sl.bo2() + c, s);
     }
   }
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) tl_mark(a.tl, blockIdx.x ? 22u : 6u, (unsigned)a.tl_id);
 }
 
 static size_t hidden_fixed_floats(int H, int L, int cluster) {

@@ -89,7 +89,10 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   // programmatic-serialization attribute may start (ring schedule of loc_group_train_epochs: ANOTHER model's
   // first-layer backward fills the other SMs while this latency-bound stack runs)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (a.gated && a.st->stopped) return;
+  if (a.gated && a.st->stopped) {  // past the stopping epoch: a no-op that still keeps the hand-over flag in step
+    if (a.training && threadIdx.x == 0 && cluster_rank() == 0) a.st->hid_seq = a.hid_seq;
+    return;
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ int64_t s_rows[kRB];
@@ -101,6 +104,7 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   const int j0 = cj * kCW, b0 = rb * kRB;
   const int nb = a.src.nb;
   const SmallLayout sl{kH, L};
+  if (tid == 0 && (r == 0 || r == kC - 1)) tl_mark(a.tl, r ? 19u : 3u, (unsigned)a.tl_id);
   int dbg_n = 0;
   auto mark = [&]() {
     if (a.dbg != nullptr && tid == 0 && dbg_n < 256) a.dbg[r * 256 + dbg_n++] = clock64();
@@ -130,6 +134,10 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
                  "l"(src), "r"((uint32_t)kSlot), "r"(smem_u32(&wbar[u & 1]))
                  : "memory");
   };
+  // Launched with programmatic stream serialization behind this model's small-layer update (train_step's chain):
+  // its results -- the weight-slice images and biases read below -- are complete after this wait.  A no-op for
+  // plain launches.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tid == 0) {
     mbar_init(&wbar[0], 1);
     mbar_init(&wbar[1], 1);
@@ -183,6 +191,13 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
       }
     }
     __syncthreads();
+  }
+  if (a.wait_bwd != 0) {
+    // launched ahead of the first-layer backward whose fused forward leaves this step's Z1 partial tiles: every
+    // CTA of that kernel bumps DevState::bwd_cnt once all it wrote is visible
+    if (tid == 0) wait_counter(&a.st->bwd_cnt, a.wait_bwd, &a.st->nonfinite);
+    __syncthreads();
+    if (tid == 0 && r == 0) tl_mark(a.tl, 23u, (unsigned)a.tl_id);  // the backward's tiles are there
   }
   const int p0_item = tid & 127, p0_g = tid >> 7;  // 128 float4 outputs x 4 partial groups
   const int p0_b = p0_item >> 4, p0_jl = (p0_item & 15) * 4;
@@ -520,6 +535,7 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_barrier();  // nobody exits while peers may still address its shared memory; global writes visible
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
+  if (tid == 0 && (r == 0 || r == kC - 1)) tl_mark(a.tl, r ? 20u : 4u, (unsigned)a.tl_id);
   if (r == 0 && warp == 0) {
     DevState* st = a.st;
     // per-row distances of all batch groups (written before the barrier): one L2 round trip, fixed-order sum
@@ -549,6 +565,11 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
         st->step_id = step_id + 1;
         const float b1p = powf(kAdamB1, (float)t), b2p = powf(kAdamB2, (float)t);
         st->alpha = st->lr * sqrtf(1.f - b2p) / (1.f - b1p);
+        // hand-over to the kernels launched ahead of this one's end (first-layer backward, small-layer update):
+        // dz / activations of every CTA were written before the cluster barrier above, the state just now
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->hid_seq), "r"(a.hid_seq) : "memory");
+        tl_mark(a.tl, 24u, (unsigned)a.tl_id);  // published
       }
     }
   }
@@ -578,21 +599,27 @@ static size_t smem_bytes(int L) {
 
 }  // namespace htc
 
-static int launch_tc(const HidArgs& a, cudaStream_t s, bool dry) {
+static int launch_tc(const HidArgs& a, cudaStream_t s, bool dry, bool overlap_previous = false) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(htc::kC);
   cfg.blockDim = dim3(htc::kThreads);
   cfg.dynamicSmemBytes = htc::smem_bytes(a.L);
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = htc::kC;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  // overlap_previous: programmatic dependent launch behind this model's small-layer update (train_step's chain):
+  // the cluster is placed and set up while the first-layer backward still streams; the kernel itself waits for
+  // the update (griddepcontrol.wait) and for the backward's tiles (DevState::bwd_cnt)
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = overlap_previous ? 2 : 1;
   if (dry) {
     int n = 0;
+    cfg.numAttrs = 1;
     if (cudaOccupancyMaxActiveClusters(&n, htc::k_hidden_tc, &cfg) != cudaSuccess) {
       cudaGetLastError();
       return 0;
@@ -648,11 +675,11 @@ bool hidden_tc_supported(int H, int L) {
   return launch_tc(dummy, 0, true) > 0;
 }
 
-int hidden_tc_launch(const HidArgs& a, cudaStream_t s) {
+int hidden_tc_launch(const HidArgs& a, cudaStream_t s, bool overlap_previous) {
   LOC_CHECK(a.H == htc::kH, "hidden stack (tcgen05): width must be 256");
   LOC_CUDA(cudaFuncSetAttribute(htc::k_hidden_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)htc::smem_bytes(a.L)));
-  return launch_tc(a, s, false);
+  return launch_tc(a, s, false, overlap_previous);
 }
 
 int hidden_tc_reslice(const float* small, float* fs, float* bs, int L, cudaStream_t s) {

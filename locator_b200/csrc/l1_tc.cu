@@ -179,6 +179,7 @@ constexpr int F_SMEM = F_STAGES * (F_WBYTES + F_XBYTES) + 4 * 32 * 8 + 256 + 102
 
 __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(L1Args a, int64_t ntiles) {
   if (a.gated && a.st->stopped) return;
+  if (threadIdx.x == 0 && blockIdx.x == 0) tl_mark(a.tl, 7u, (unsigned)a.tl_id);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = sm;
@@ -343,6 +344,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(L1Args a, int64_t nt
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 64);
+  if (threadIdx.x == 0 && blockIdx.x == 0) tl_mark(a.tl, 8u, (unsigned)a.tl_id);
 }
 
 
@@ -365,6 +367,7 @@ constexpr int W_SMEM = W_STAGES * (F_WBYTES + W_XBYTES) + W_BUILD * 32 * 8 + 256
 
 __global__ void __launch_bounds__(W_THREADS, 1) k_l1_fwd_wide(L1Args a, int64_t ntiles, int nrows, float* __restrict__ out) {
   if (a.gated && a.st->stopped) return;
+  if (threadIdx.x == 0 && blockIdx.x == 0) tl_mark(a.tl, 9u, (unsigned)a.tl_id);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = sm;
@@ -511,6 +514,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) k_l1_fwd_wide(L1Args a, int64_t 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+  if (threadIdx.x == 0 && blockIdx.x == 0) tl_mark(a.tl, 10u, (unsigned)a.tl_id);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -569,7 +573,11 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   // programmatic dependent launch: a kernel queued behind this one with the programmatic-serialization
   // attribute (the small-layer update of the ring schedule) may be scheduled as soon as every CTA is running
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (a.gated && a.st->stopped) return;
+  if (a.gated && a.st->stopped) {  // past the stopping epoch: a no-op that still keeps the hand-over counter in step
+    if (threadIdx.x == 0) atomicAdd(&a.st->bwd_cnt, 1u);
+    return;
+  }
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) tl_mark(a.tl, blockIdx.x ? 17u : 1u, (unsigned)a.tl_id);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sDZhi = sm;
@@ -603,7 +611,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   const int nloc = (int)(t_end - t_begin);
   const int nchunks = nloc * (B_NT / B_CH);
   // odd steps walk the tiles downwards (L1Args::alternate); chunks inside a tile keep their order
-  const bool rev = a.alternate && (a.st->t & 1);
+  const bool rev = a.alternate && a.rev;
   auto tile_of = [&](int li) -> int64_t { return t_begin + (rev ? nloc - 1 - li : li); };
   const uint64_t pol_ld = (a.stream_hint & 1) ? kL2EvictFirst : kL2EvictNormal;
   const uint64_t pol_st = (a.stream_hint & 2) ? kL2EvictFirst : kL2EvictNormal;
@@ -628,6 +636,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   __syncthreads();  // barriers and TMEM are ready: the load warp starts streaming W1 | m | v right away ...
   tc_fence_after();
   if (warp != W_LOAD) {
+    // Launched ahead of this step's hidden stack (programmatic dependent launch: the set-up above and the first
+    // ring stages of W1 | m | v run in its shadow): dZ1, alpha and the loss only exist once it has published.
+    if (a.wait_hid != 0) {
+      // ONE poller per CTA (2,700 polling warps on one L2 line slowed the very hidden stack they were waiting for)
+      if (threadIdx.x == 0) wait_counter(&a.st->hid_seq, a.wait_hid, &a.st->nonfinite);
+      asm volatile("bar.sync 4, %0;" ::"n"(B_THREADS - 32) : "memory");  // everyone but the load warp
+    }
     // ... while everybody else stages dZ1 -> hi/lo tf32 operands, [chunk = j/32][row = b][swizzled 32 j]
     // (all of a thread's loads first: one L2 round trip instead of three)
     constexpr int kIters = (kMaxB * kH / 4 + B_THREADS - 33) / (B_THREADS - 32);
@@ -754,6 +769,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   } else if (warp == W_LOAD) {
     // =========================== load warp: W, m, v chunk -> stage ===========================
     if (elect_one()) {
+      // chained step: this CTA may have been placed on an SM that ANOTHER CTA of the model's previous backward
+      // just left, while the CTA that owns these tiles there is still updating them
+      if (a.wait_hid != 0) wait_counter(&a.st->bwd_cnt, a.wait_bwd, &a.st->nonfinite);
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % B_STAGES;
         mbar_wait(&st_free[s], ((uint32_t)(c / B_STAGES) & 1u) ^ 1u);
@@ -1049,6 +1067,13 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   tc_fence_before();
   __syncthreads();
   if (warp == B_EPI_WARPS) tmem_dealloc(tmem, 512);
+  if (threadIdx.x == 0) {
+    // everything this CTA wrote (updated chunks: the bulk stores have completed; gamma / beta; the next step's
+    // partial tile) is visible before the counter moves: the next hidden stack may already be spinning on it
+    __threadfence();
+    atomicAdd(&a.st->bwd_cnt, 1u);
+    tl_mark(a.tl, blockIdx.x == gridDim.x - 1 ? 18u : (blockIdx.x ? 25u : 2u), (unsigned)a.tl_id);  // 25: any other block
+  }
 }
 
 // Pulls the first n_chunks chunks (W1 | m | v, 24 KB each) of every CTA's walk of the NEXT backward launch into

@@ -73,6 +73,8 @@ __global__ void k_state_reset(DevState* st, float lr, int patience, int max_epoc
   st->max_epochs = max_epochs;
   st->nonfinite = 0;
   st->last_loss = st->last_val = 0.f;
+  st->hid_seq = 0u;  // hand-over flags of the chained step (host mirrors: loc_model::h_hid_seq / h_bwd_cnt)
+  st->bwd_cnt = 0u;
 }
 
 __global__ void k_begin_call(DevState* st) { st->epoch0 = st->epoch; }
@@ -198,6 +200,24 @@ static int reslice(loc_model* m, cudaStream_t s) {
                    : hidden_reslice(m->small, m->w_fs, m->w_bs, m->H, m->L, m->cluster, s);
 }
 
+// LOC_TIMELINE=1: every step kernel logs (globaltimer, tag, model) at its first / last block's start and end
+static unsigned long long* g_tl = nullptr;
+static int g_tl_models = 0;
+static unsigned long long* timeline_buffer() {
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (getenv("LOC_TIMELINE") != nullptr) {
+      const size_t bytes = (1 + 2 * (size_t)kTlCap) * sizeof(unsigned long long);
+      if (cudaMalloc(&g_tl, bytes) == cudaSuccess)
+        cudaMemset(g_tl, 0, bytes);
+      else
+        g_tl = nullptr;
+    }
+  }
+  return g_tl;
+}
+
 static int g_fuse_debug = 0;  // loc_debug_stage: LOC_FUSE_DEBUG bits (timing experiments only)
 
 static L1Args l1_args(loc_model* m, const uint32_t* packed, int64_t row_words, const RowSrc& src, int training,
@@ -219,6 +239,11 @@ static L1Args l1_args(loc_model* m, const uint32_t* packed, int64_t row_words, c
   static const int stream_hint = getenv("LOC_STREAM_HINT") ? atoi(getenv("LOC_STREAM_HINT")) : 3;
   a.stream_hint = stream_hint;
   a.dbg_flags = g_fuse_debug;
+  a.rev = (int)(m->h_steps & 1);  // steps launched so far (training hidden stacks): odd steps walk downwards
+  a.wait_hid = 0u;
+  a.wait_bwd = 0u;
+  a.tl = timeline_buffer();
+  a.tl_id = m->tl_id;
   a.gamma = m->gamma;
   a.beta = m->beta;
   a.mmean = m->mmean;
@@ -272,6 +297,8 @@ static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated
   h.wait_count = 0;
   h.wait_seq = 0;
   h.wait_err = nullptr;
+  h.wait_bwd = 0u;
+  h.hid_seq = 0u;
   h.partials = m->exchange != nullptr ? m->z1_tile : m->partials;
   h.n_partials = m->exchange != nullptr ? 1 : m->n_partials;
   h.partial_stride = (int64_t)kMaxB * m->H;
@@ -293,11 +320,14 @@ static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated
   h.src = src;
   h.pred_out = pred_out;
   h.dbg = m->dbg;
+  h.tl = timeline_buffer();
+  h.tl_id = m->tl_id;
   h.st = m->st;
   return h;
 }
 
 static int forward_l1(loc_model* m, const L1Args& a, cudaStream_t s) {
+  m->chain_open = 0;
   m->span_perm = nullptr;  // a standalone forward overwrites the tiles a loc_train_steps span may have left
   return m->use_tc ? l1_forward_tc(a, m->n_partials, s) : l1_forward_simt(a, m->n_partials, s);
 }
@@ -318,14 +348,52 @@ static UpdArgs upd_args(loc_model* m, int nb, int gated) {
   u.dzs = m->dzs;
   u.outs = m->outs;
   u.nb = nb;
+  u.wait_hid = 0u;
+  u.tl = timeline_buffer();
+  u.tl_id = m->tl_id;
   u.st = m->st;
   return u;
 }
 
-// One optimizer step: 4 launches (stage_mask selects a subset for profiling / tests).
+// A training launch of the hidden stack advances the step parity (tile walk direction of the backward) and the
+// hand-over flag it publishes when it is done; call right before the launch.
+static void begin_training_hidden(loc_model* m, HidArgs& h) {
+  ++m->h_steps;
+  h.hid_seq = ++m->h_hid_seq;
+}
+
+// First-layer backward of the tcgen05 path + the host mirror of the counter its CTAs bump when they are done.
+static int backward_tc(loc_model* m, L1Args& a, cudaStream_t s, bool overlap_previous = false) {
+  a.rev = (int)(m->h_steps & 1);
+  if (l1_backward_tc(a, m->n_bwd_blocks, s, overlap_previous)) return 1;
+  m->h_bwd_cnt += (unsigned)m->n_bwd_blocks;
+  return 0;
+}
+
+// Can one model's step run as a chain of programmatic dependent launches (see train_step)?  Needs the tcgen05
+// kernels, no sharding, and first-layer kernels that leave the hidden stack's 16 SMs alone.
+static bool chain_capable(const loc_model* m) {
+  const bool off = getenv("LOC_NO_CHAIN") != nullptr;  // read per call: tests compare both schedules in one process
+  return !off && m->use_tc && m->hid_tc && m->exchange == nullptr && m->tp == nullptr &&
+         m->n_bwd_blocks <= sm_count() - 16;
+}
+
+// One optimizer step: 3-4 launches (stage_mask selects a subset for profiling / tests).
 // `next` (tcgen05 path): rows of the following step -- the backward kernel then also runs that step's
 // first-layer forward on the W1 chunks it has just updated (they are still in shared memory), so the
 // following step is called with have_fwd = true and skips its own forward launch.
+//
+// Chained steps (chain_capable): the step's kernels go into ONE stream as  H -> B -> U  (hidden stack on its
+// 16-SM cluster, first-layer backward + Adam (+ next forward) on the other SMs, small-layer update), every one of
+// them launched with programmatic stream serialization, i.e. scheduled as soon as its predecessor's CTAs are all
+// running instead of after it has drained:
+//   B is resident and has its barriers, TMEM and the first ring stages of W1 | m | v ready while H still runs; it
+//     waits for DevState::hid_seq (published by H after its last write) before it touches dZ1;
+//   U takes H's SMs the moment H exits (same flag), and finishes long before B;
+//   the NEXT step's H is placed behind U -- griddepcontrol.wait covers U's results -- sets itself up and waits for
+//     DevState::bwd_cnt (one count per finished CTA of B) before it reads the Z1 tiles B's fused forward left.
+// Kernel boundaries (drain + launch + ramp: 6-15 us each on this part, `scripts/timeline.py`) disappear from the
+// step's critical path; what remains is H + B.
 static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s, int stage_mask = 15,
                       const RowSrc* next = nullptr, bool have_fwd = false) {
   L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, gated);
@@ -333,10 +401,28 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
     a.src_next = *next;
     a.fuse_next = 1;
   }
+  const bool chain = stage_mask == 15 && chain_capable(m);
+  const bool h_overlaps = chain && have_fwd && m->chain_open && m->chain_stream == s;  // the stream's last kernels: this model's B, U
+  m->chain_open = 0;
   if ((stage_mask & 1) && !have_fwd && (forward_l1(m, a, s) || exchange_partials(m, s))) return 1;
   HidArgs h = hid_args(m, src, 1, gated, m->train_locs, nullptr);
-  if ((stage_mask & 2) && (m->hid_tc ? hidden_tc_launch(h, s) : hidden_launch(h, m->cluster, s))) return 1;
-  // The small-layer update only needs the hidden kernel's outputs: it runs on a side stream next to
+  if (stage_mask & 2) {
+    begin_training_hidden(m, h);
+    if (h_overlaps) h.wait_bwd = m->h_bwd_cnt;  // every CTA of the previous step's backward has signed off
+    if (m->hid_tc ? hidden_tc_launch(h, s, h_overlaps) : hidden_launch(h, m->cluster, s)) return 1;
+  }
+  if (chain) {
+    a.wait_hid = h.hid_seq;
+    a.wait_bwd = m->h_bwd_cnt;  // every backward launched so far for this model
+    if (backward_tc(m, a, s, true)) return 1;
+    UpdArgs u = upd_args(m, src.nb, gated);
+    u.wait_hid = h.hid_seq;
+    if (hidden_update_launch(u, s, true)) return 1;
+    m->chain_open = 1;
+    m->chain_stream = s;
+    return 0;
+  }
+  // Unchained: the small-layer update only needs the hidden kernel's outputs: it runs on a side stream next to
   // the first-layer backward (full steps only; single-stage debug launches stay on `s`).
   const bool fork = stage_mask == 15;
   if (fork) {
@@ -344,18 +430,17 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
     LOC_CUDA(cudaStreamWaitEvent(m->side, m->ev_hid, 0));
   }
   cudaStream_t su = fork ? m->side : s;
+  auto backward = [&]() -> int {
+    return m->use_tc ? backward_tc(m, a, s) : l1_backward_simt(a, m->n_bwd_blocks, s);
+  };
   if (!(stage_mask & 8)) {
-    if ((stage_mask & 4) &&
-        (m->use_tc ? l1_backward_tc(a, m->n_bwd_blocks, s) : l1_backward_simt(a, m->n_bwd_blocks, s)))
-      return 1;
+    if ((stage_mask & 4) && backward()) return 1;
     return 0;
   }
   UpdArgs u = upd_args(m, src.nb, gated);
   if (hidden_update_launch(u, su)) return 1;
   if (fork) LOC_CUDA(cudaEventRecord(m->ev_upd, m->side));
-  if ((stage_mask & 4) &&
-      (m->use_tc ? l1_backward_tc(a, m->n_bwd_blocks, s) : l1_backward_simt(a, m->n_bwd_blocks, s)))
-    return 1;
+  if ((stage_mask & 4) && backward()) return 1;
   if ((stage_mask & 4) && a.fuse_next && exchange_partials(m, s)) return 1;  // the next step's tile is complete
   if (fork) LOC_CUDA(cudaStreamWaitEvent(s, m->ev_upd, 0));
   return 0;
@@ -372,6 +457,7 @@ static int infer_rows(loc_model* m, const uint32_t* packed, int64_t n, int64_t r
   const bool wide = m->wide != nullptr && m->use_tc && m->hid_tc && m->exchange == nullptr && m->tp == nullptr &&
                     n > kMaxB && !no_wide;
   m->span_perm = nullptr;
+  m->chain_open = 0;
   if (wide) {
     for (int64_t r0 = 0; r0 < n; r0 += 256) {
       const int nrows = (int)((n - r0) < 256 ? (n - r0) : 256);
@@ -536,7 +622,14 @@ static void set_geometry(loc_model* m, int64_t K) {
   m->k_offset = 0;
   const int sms = sm_count();
   if (m->use_tc) {
-    m->n_partials = l1_tc_partials(K);
+    // The first-layer kernels leave one 16-SM cluster's worth of SMs to the hidden stack: a step then runs as a
+    // chain of overlapping launches (train_step) and replicate groups as a ring (loc_group_train_epochs).  The
+    // stream of W1 | m | v is HBM-bound and as fast on SMs - 16 CTAs as on all of them.  The CTA count fixes the
+    // fp32 summation order of the layer, so it is the same for every schedule; loc_model_set_l1_ctas overrides.
+    const int full = l1_tc_partials(K);
+    const int spare = sms - 16 > 1 ? sms - 16 : 1;
+    static const bool all_sms = getenv("LOC_L1_ALL_SMS") != nullptr;
+    m->n_partials = (full < spare || all_sms) ? full : spare;
     m->n_bwd_blocks = m->n_partials;
   } else {
     const int64_t nch = cdiv(K, kF1Chunk);
@@ -604,10 +697,14 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
     r->tp = nullptr;
     r->span_perm = nullptr;
     r->span_next = 0;
+    r->h_steps = 0;
+    r->h_hid_seq = r->h_bwd_cnt = 0u;
+    r->chain_open = 0;
     if (zero_model(r)) {
       free_model(r);
       return 1;
     }
+    r->tl_id = g_tl_models++;
     *out = r;
     return 0;
   }
@@ -633,6 +730,7 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   m->use_tc = use_tc;
   set_geometry(m, K);
   m->cap_K = K;
+  m->cap_partials = m->use_tc ? l1_tc_partials(K) : m->n_partials;
   const int64_t KH = m->Kpad * width, ns = m->sl.total();
 #define LOC_ALLOC(ptr, bytes)                                 \
   do {                                                        \
@@ -651,12 +749,12 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   for (auto p : sm) LOC_ALLOC(*p, ns * sizeof(float));
   LOC_ALLOC(m->w_fs, (size_t)(nlayers - 1) * width * width * sizeof(float));
   LOC_ALLOC(m->w_bs, (size_t)(nlayers - 1) * width * width * sizeof(float));
-  LOC_ALLOC(m->partials, (size_t)m->n_partials * kMaxB * width * sizeof(float));
+  LOC_ALLOC(m->partials, (size_t)m->cap_partials * kMaxB * width * sizeof(float));
   LOC_ALLOC(m->acts, (size_t)nlayers * kMaxB * width * sizeof(float));
   LOC_ALLOC(m->dzs, (size_t)nlayers * kMaxB * width * sizeof(float));
   LOC_ALLOC(m->outs, 8 * 256 * sizeof(float));  // one [256] block per 32-row chunk of a wide pass
   LOC_ALLOC(m->val_slots, 16 * sizeof(float));
-  if (m->use_tc && m->hid_tc) LOC_ALLOC(m->wide, (size_t)m->n_partials * 256 * width * sizeof(float));
+  if (m->use_tc && m->hid_tc) LOC_ALLOC(m->wide, (size_t)m->cap_partials * 256 * width * sizeof(float));
   LOC_ALLOC(m->hist, (size_t)max_epochs * 3 * sizeof(float));
   if (want_dbg) LOC_ALLOC(m->dbg, 16 * 256 * sizeof(long long));
   LOC_ALLOC(m->st, sizeof(DevState));
@@ -667,6 +765,7 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
     free_model(m);
     return loc::fail("loc_model_create: stream / event / memset failed", __FILE__, __LINE__);
   }
+  m->tl_id = g_tl_models++;
   *out = m;
   return 0;
 }
@@ -736,6 +835,9 @@ int loc_model_init(loc_model* m, uint64_t seed, void* stream) {
   if (reslice(m, s)) return 1;
   k_state_reset<<<1, 1, 0, s>>>(m->st, 1e-3f, 100, m->max_epochs, 1);
   LOC_LAUNCHED();
+  m->h_steps = 0;
+  m->h_hid_seq = m->h_bwd_cnt = 0u;
+  m->chain_open = 0;
   return 0;
 }
 
@@ -849,7 +951,7 @@ int loc_model_set_tp(loc_model* m, loc_tp* tp) {
 int loc_model_set_l1_ctas(loc_model* m, int32_t n_ctas) {
   LOC_CHECK(m != nullptr && n_ctas >= 1, "loc_model_set_l1_ctas: bad arguments");
   LOC_CHECK(m->use_tc, "loc_model_set_l1_ctas: needs the tcgen05 first layer (width 256)");
-  const int full = l1_tc_partials(m->K);
+  const int full = l1_tc_partials(m->K) < m->cap_partials ? l1_tc_partials(m->K) : m->cap_partials;
   m->n_partials = n_ctas < full ? n_ctas : full;
   m->n_bwd_blocks = m->n_partials;
   return 0;
@@ -860,6 +962,8 @@ int loc_model_set_schedule(loc_model* m, float lr, int32_t patience) {
   LOC_CHECK(patience >= 0, "loc_model_set_schedule: patience must be >= 0");
   k_state_reset<<<1, 1>>>(m->st, lr, patience, m->max_epochs, 0);
   LOC_LAUNCHED();
+  m->h_hid_seq = m->h_bwd_cnt = 0u;
+  m->chain_open = 0;
   LOC_CUDA(cudaDeviceSynchronize());
   return 0;
 }
@@ -950,6 +1054,8 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
   }
   cudaStream_t s = (cudaStream_t)stream;
   for (int g = 0; g < n_models; ++g) {
+    models[g]->chain_open = 0;
+    models[g]->span_perm = nullptr;
     k_begin_call<<<1, 1, 0, s>>>(models[g]->st);
     LOC_LAUNCHED();
   }
@@ -999,9 +1105,10 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
             L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, 1);
             if (!have_fwd && forward_l1(m, a, s)) return 1;  // first step of the epoch: later ones are fused
             HidArgs h = hid_args(m, src, 1, 1, m->train_locs, nullptr);
+            begin_training_hidden(m, h);
             if (hidden_tc_launch(h, s)) return 1;
             if (pend.m != nullptr) {
-              if (l1_backward_tc(pend.a, pend.m->n_bwd_blocks, s, true)) return 1;
+              if (backward_tc(pend.m, pend.a, s, true)) return 1;
               if (hidden_update_launch(pend.u, s, true)) return 1;
             }
             if (has_next) {
@@ -1015,7 +1122,7 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
           have_fwd = has_next;
         }
         if (pend.m != nullptr) {  // the ring's last backward and update of the epoch
-          if (l1_backward_tc(pend.a, pend.m->n_bwd_blocks, s)) return 1;
+          if (backward_tc(pend.m, pend.a, s)) return 1;
           if (hidden_update_launch(pend.u, s)) return 1;
         }
         g0 = g1;
@@ -1035,6 +1142,7 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
           if (forward_l1(m, a, s)) return 1;
         }
         hg.a[g] = hid_args(m, src, 1, 1, m->train_locs, nullptr);
+        begin_training_hidden(m, hg.a[g]);
       }
       // all hidden stacks in one launch: one cluster per replicate
       if (hidden_tc_group_launch(hg, s)) return 1;
@@ -1055,7 +1163,7 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
           a.src_next = step_rows(g, off + m0->B);
           a.fuse_next = 1;
         }
-        if (l1_backward_tc(a, m->n_bwd_blocks, s)) return 1;
+        if (backward_tc(m, a, s)) return 1;
       }
       for (int g = 0; g < n_models; ++g) LOC_CUDA(cudaStreamWaitEvent(s, models[g]->ev_upd, 0));
       have_fwd = has_next;
@@ -1069,6 +1177,22 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
     }
   }
   return 0;
+}
+
+int64_t loc_debug_timeline(uint64_t* h_out, int64_t max_records) {
+  // records as (ns, tag << 32 | model) pairs; the buffer is cleared.  Tags: 1/2 first-layer backward start / end,
+  // 3/4 hidden stack, 5/6 small-layer update, 7/8 first-layer forward (standalone or wide); +16: last block
+  unsigned long long* tl = timeline_buffer();
+  if (tl == nullptr || h_out == nullptr) return 0;
+  cudaDeviceSynchronize();
+  unsigned long long n = 0;
+  cudaMemcpy(&n, tl, sizeof(n), cudaMemcpyDeviceToHost);
+  n &= 0xffffffffull;
+  if (n > kTlCap) n = kTlCap;
+  const int64_t c = (int64_t)n < max_records ? (int64_t)n : max_records;
+  cudaMemcpy(h_out, tl + 1, (size_t)c * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(tl, 0, sizeof(unsigned long long));
+  return c;
 }
 
 int64_t loc_debug_read(loc_model* m, int32_t which, float* h_dst, int64_t max_n, void* stream) {

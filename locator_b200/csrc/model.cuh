@@ -68,6 +68,12 @@ struct L1Args {
   int alternate;  // tcgen05 backward: walk the CTA's tiles downwards on odd steps (the tail of the previous
                   // step's updates is still in L2: those reads hit and their dirty lines are overwritten in place)
   int stream_hint;  // tcgen05 backward: L2 evict_first on the W1/m/v chunk loads (bit 0) / stores (bit 1)
+  int rev;          // tcgen05 backward: walk the tiles downwards (host-side step parity; see `alternate`)
+  unsigned wait_hid;  // != 0: launched ahead of this step's hidden stack -- wait for DevState::hid_seq >= wait_hid before dZ1 is read
+  unsigned wait_bwd;  // with wait_hid: the previous backward of this model may still be running on other SMs when this
+                      // CTA starts -- no chunk is loaded before DevState::bwd_cnt >= wait_bwd (all its CTAs are done)
+  unsigned long long* tl;  // kernel timeline buffer (diagnostics) or nullptr
+  int tl_id;
   int dbg_flags;    // timing experiments on the fused forward (loc_debug_stage + LOC_FUSE_DEBUG); 0 in production
   float *gamma, *beta, *mmean, *mvar;
   float* W1;
@@ -109,6 +115,10 @@ struct HidArgs {
   RowSrc src;
   float* pred_out;  // [n][2]
   long long* dbg;   // optional per-CTA clock64() checkpoints [C][256] (profiling builds of the step)
+  unsigned wait_bwd;  // != 0: launched ahead of the backward that produces its Z1 tiles -- wait for DevState::bwd_cnt >= wait_bwd
+  unsigned hid_seq;   // training launches: value to publish in DevState::hid_seq when everything is written
+  unsigned long long* tl;  // kernel timeline buffer (diagnostics) or nullptr
+  int tl_id;
   DevState* st;
 };
 
@@ -129,6 +139,9 @@ struct UpdArgs {
   const float* dzs;
   const float* outs;
   int nb;
+  unsigned wait_hid;  // != 0: wait for DevState::hid_seq >= wait_hid (launched ahead of the hidden stack it consumes)
+  unsigned long long* tl;  // kernel timeline buffer (diagnostics) or nullptr
+  int tl_id;
   DevState* st;
 };
 
@@ -144,7 +157,7 @@ size_t hidden_smem_bytes(int H, int L, int cluster);
 
 // tcgen05 hidden stack (hidden_tc.cu): width 256, 16-CTA cluster
 bool hidden_tc_supported(int H, int L);
-int hidden_tc_launch(const HidArgs& a, cudaStream_t s);
+int hidden_tc_launch(const HidArgs& a, cudaStream_t s, bool overlap_previous = false);
 int hidden_tc_group_launch(const HidGroupArgs& g, cudaStream_t s);
 int hidden_tc_reslice(const float* small, float* fs, float* bs, int L, cudaStream_t s);
 
@@ -201,6 +214,9 @@ struct loc_model {
   int cluster;
   int n_partials;   // partial Z1 tiles the forward leaves
   int n_bwd_blocks;
+  int cap_partials; // partial tiles the buffers hold (the largest CTA count loc_model_set_l1_ctas accepts)
+  int chain_open;   // the stream's last kernels are this model's chained step (train_step): the next hidden stack may overlap them
+  cudaStream_t chain_stream;
   int use_tc;       // first layer on tcgen05 (implies the tiled W1 layout)
   int64_t Kpad;     // rows of W1 / m / v in use (K rounded up to 64 when tiled)
   int64_t cap_K;    // K the buffers were allocated for (a pooled handle serves any K <= cap_K, see loc_model_create)
@@ -220,6 +236,7 @@ struct loc_model {
   float* wide;       // wide inference: split-K partial tiles of up to 256 rows [n_partials][256][H] (tcgen05 path)
   float* val_slots;  // [8][2] per-chunk validation sums of a wide pass
   long long* dbg;
+  int tl_id;         // model number in the kernel timeline (diagnostics)
   cudaStream_t side;        // small-layer update runs here, beside the first-layer backward
   cudaEvent_t ev_hid, ev_upd;
   loc::DevState* st;
@@ -238,4 +255,8 @@ struct loc_model {
   // loc_train_steps: the last span left the forward tiles of step span_next of the epoch ordered by span_perm
   const int32_t* span_perm;
   int64_t span_next;
+  // host mirrors of DevState::hid_seq / bwd_cnt / optimizer step parity (what the launches made so far will have
+  // published once they have run)
+  unsigned h_hid_seq, h_bwd_cnt;
+  int64_t h_steps;
 };

@@ -102,7 +102,7 @@ def _update_deviation(w0, wc, wr, madam=None, mref=None):
 # ---------------------------------------------------------------------------------------------------
 # one optimizer step, stage by stage, production kernels, several tiles per CTA
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("K,ctas", [(100_000, None), (200_000, None), (100_000, "spare")])
+@pytest.mark.parametrize("K,ctas", [(100_000, None), (200_000, None), (100_000, "all")])
 def test_step_stages_match_oracle(M, K, ctas):
     """Z1 (first-layer forward), dZ1 (hidden stack), the W1 | m | v update of the fused backward + Adam and
     the NEXT step's Z1 it leaves, against the oracle's explicit forward / backward / Adam."""
@@ -111,7 +111,7 @@ def test_step_stages_match_oracle(M, K, ctas):
     rng = np.random.default_rng(K // 1000 + (7 if ctas else 0))
     n = 96
     x, y = _data(rng, n, K)
-    m = M.LocatorModel(K, seed=21, l1_ctas=M.spare_cluster_l1_ctas() if ctas else None)
+    m = M.LocatorModel(K, seed=21, l1_ctas=148 if ctas else None)  # default: SMs - 16 first-layer CTAs
     w0 = m.get_weights()
     # non-trivial BN parameters and biases, as after some training
     w0[0] = rng.uniform(0.7, 1.3, K).astype(np.float32)
@@ -232,13 +232,13 @@ def _fit_variants(M, K, xt, yt, xv, yv, seeds, perms, epochs):
     def grab(ms, hs):
         return [(h.history, mm.get_weights(), mm.predict(xv)) for mm, h in zip(ms, hs)]
 
-    for name, ctas in (("solo_all_sms", None), ("solo_spare", spare)):
+    for name, ctas in (("solo_all_sms", 148), ("solo_spare", spare)):
         ms = [M.LocatorModel(K, seed=s, max_epochs=epochs + 1, l1_ctas=ctas) for s in seeds]
         hs = [mm.fit(xt, yt, epochs=epochs, validation_data=(xv, yv), patience=100, perms=perms[i])
               for i, mm in enumerate(ms)]
         out[name] = grab(ms, hs)
         del ms
-    for name, ctas, sched in (("group_ring", spare, "ring"), ("group_lockstep", None, "lockstep")):
+    for name, ctas, sched in (("group_ring", spare, "ring"), ("group_lockstep", 148, "lockstep")):
         os.environ["LOC_GROUP_SCHEDULE"] = sched
         try:
             ms = [M.LocatorModel(K, seed=s, max_epochs=epochs + 1, l1_ctas=ctas) for s in seeds]
@@ -323,7 +323,7 @@ def test_divergence_is_rounding_chaos(M):
     perms = np.stack([prng.permutation(ntr) for _ in range(epochs)])  # bench: one warm-up epoch + two timed ones
     seed = 500
     runs = {}
-    for name, ctas in (("cuda_148", None), ("cuda_132", M.spare_cluster_l1_ctas())):
+    for name, ctas in (("cuda_148", 148), ("cuda_132", M.spare_cluster_l1_ctas())):
         m = M.LocatorModel(K, seed=seed, max_epochs=epochs + 1, l1_ctas=ctas)
         runs[name] = m.fit(xt, yt, epochs=epochs, validation_data=(xv, yv), patience=10 ** 6, perms=perms).history
         del m

@@ -251,6 +251,40 @@ def test_group_training_matches_individual_training(M, schedule, monkeypatch):
         assert np.array_equal(m.get_weights()[4], w)
 
 
+@pytest.mark.parametrize("K,ntr", [(20_000, 75), (100_000, 330), (5830, 405)])
+def test_chained_step_matches_unchained_step(M, K, ntr, monkeypatch):
+    """train_step's chain (hidden stack -> first-layer backward -> small-layer update as programmatic dependent
+    launches that hand over through DevState::hid_seq / bwd_cnt instead of kernel boundaries) only changes WHEN
+    kernels start: histories, weights and predictions equal those of the unchained schedule (LOC_NO_CHAIN: update
+    on a side stream, plain launches) bit for bit, over several epochs with ragged last batches, validation
+    passes and checkpoints in between."""
+    rng = np.random.default_rng(K)
+    x, y = _data(rng, ntr, K)
+    xv, yv = _data(rng, 40, K)
+    epochs = 4
+    perms = np.stack([rng.permutation(ntr) for _ in range(epochs)])
+    out = []
+    for chained in (True, False, True):
+        if chained:
+            monkeypatch.delenv("LOC_NO_CHAIN", raising=False)
+        else:
+            monkeypatch.setenv("LOC_NO_CHAIN", "1")
+        m = M.LocatorModel(K, seed=77, max_epochs=epochs)
+        if m.impl != "tcgen05":
+            pytest.skip("tcgen05 kernels only")
+        h = m.fit(x, y, epochs=epochs, validation_data=(xv, yv), patience=100, perms=perms, epochs_per_call=3)
+        st = m.state()
+        assert st.nonfinite == 0 and st.t == epochs * int(np.ceil(ntr / 32))
+        out.append((h.history, m.get_weights(), m.predict(xv)))
+        del m
+    monkeypatch.delenv("LOC_NO_CHAIN", raising=False)
+    for other in out[1:]:
+        assert other[0] == out[0][0]
+        for a, b in zip(other[1], out[0][1]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(other[2], out[0][2])
+
+
 def test_backward_kernels_survive_many_launches(M):
     """Regression for an mbarrier phase-aliasing race in the tcgen05 backward (the two epilogue groups shared
     one barrier per pipeline stage and could pass a wait one phase early): at K = 100k the unfused kernel

@@ -82,7 +82,7 @@ struct DevState {
 };
 
 // Spin until *flag has reached `expect` (wrap-safe); gives up after ~2 s and raises *err instead of hanging the GPU.
-__device__ __forceinline__ void wait_counter(const unsigned* flag, unsigned expect, int* err) {
+__device__ __forceinline__ void wait_counter(const unsigned* flag, unsigned expect, int* err, unsigned sleep_ns = 256u) {
   const long long t0 = clock64();
   while (true) {
     unsigned v;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void wait_counter(const unsigned* flag, unsigned expe
       if (err != nullptr) *err = 1;
       break;
     }
-    __nanosleep(256);
+    __nanosleep(sleep_ns);
   }
 }
 

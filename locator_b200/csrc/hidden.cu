@@ -519,8 +519,8 @@ __global__ void k_reslice(const float* __restrict__ small, float* fs, float* bs,
 // ---------------------------------------------------------------------------------------------
 constexpr int kUpdRows = 16;
 
-// (register cap: its blocks must fit beside the resident first-layer backward CTAs, which it overlaps)
-__global__ void __maxnreg__(56) k_hidden_update(UpdArgs a) {
+// (register cap: two 256-thread blocks per SM)
+__global__ void __maxnreg__(120) k_hidden_update(UpdArgs a) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next hidden stack may be scheduled behind us
   if (a.gated && a.st->stopped) return;
   if (a.wait_hid != 0) {  // launched ahead of the end of the hidden stack whose activations / dz it consumes
@@ -544,29 +544,61 @@ __global__ void __maxnreg__(56) k_hidden_update(UpdArgs a) {
   };
   if ((int)blockIdx.x < nblk_hidden) {
     const int i = 1 + blockIdx.x / rb_n, rb = blockIdx.x % rb_n;
+    // This kernel runs next to (or right behind) the first-layer backward, which saturates HBM: a memory round
+    // trip costs several microseconds then.  Everything the block needs -- dz of the layer, its 16 activation
+    // rows, 16 rows of weights and Adam moments -- is therefore requested up front, ONE round trip, before the
+    // first dependent instruction (stores to the same arrays would otherwise fence later loads in).
     float dz[kMaxB];
+#pragma unroll
+    for (int b = 0; b < kMaxB; ++b) dz[b] = a.dzs[((int64_t)i * kMaxB + b) * H + j];
+    constexpr int kAsPer = 2;  // kUpdRows * kMaxB / 256 staged activations per thread (H >= 256) or more (strided below)
+    float as_reg[kAsPer];
+#pragma unroll
+    for (int q = 0; q < kAsPer; ++q) {
+      const int idx = threadIdx.x + q * blockDim.x;
+      const int kk = idx % kUpdRows, b = idx / kUpdRows;
+      as_reg[q] = idx < kUpdRows * kMaxB ? a.acts[((int64_t)(i - 1) * kMaxB + b) * H + rb * kUpdRows + kk] : 0.f;
+    }
+    const int64_t row0 = sl.Wh(i) + (int64_t)(rb * kUpdRows) * H + j;
+    float w16[kUpdRows], m16[kUpdRows], v16[kUpdRows];
+#pragma unroll
+    for (int r = 0; r < kUpdRows; ++r) {
+      const int64_t idx = row0 + (int64_t)r * H;
+      w16[r] = a.small[idx];
+      m16[r] = a.m_small[idx];
+      v16[r] = a.v_small[idx];
+    }
     float bsum = 0.f;
 #pragma unroll
-    for (int b = 0; b < kMaxB; ++b) {
-      dz[b] = a.dzs[((int64_t)i * kMaxB + b) * H + j];
-      bsum += dz[b];
+    for (int b = 0; b < kMaxB; ++b) bsum += dz[b];
+#pragma unroll
+    for (int q = 0; q < kAsPer; ++q) {
+      const int idx = threadIdx.x + q * blockDim.x;
+      if (idx < kUpdRows * kMaxB) as[idx % kUpdRows][idx / kUpdRows] = as_reg[q];
     }
-    for (int idx = threadIdx.x; idx < kUpdRows * kMaxB; idx += blockDim.x) {
+    for (int idx = threadIdx.x + kAsPer * blockDim.x; idx < kUpdRows * kMaxB; idx += blockDim.x) {  // widths < 256
       const int kk = idx % kUpdRows, b = idx / kUpdRows;
       as[kk][b] = a.acts[((int64_t)(i - 1) * kMaxB + b) * H + rb * kUpdRows + kk];
     }
     __syncthreads();
-#pragma unroll 4
-    for (int kk = 0; kk < kUpdRows; ++kk) {
+#pragma unroll
+    for (int r = 0; r < kUpdRows; ++r) {
       float g = 0.f;
 #pragma unroll
-      for (int b = 0; b < kMaxB; ++b) g = fmaf(as[kk][b], dz[b], g);
-      const int k = rb * kUpdRows + kk;
-      const float w = adam_at(sl.Wh(i) + (int64_t)k * H + j, g);
+      for (int b = 0; b < kMaxB; ++b) g = fmaf(as[r][b], dz[b], g);
+      adam_update(w16[r], m16[r], v16[r], g, alpha);
+    }
+#pragma unroll
+    for (int r = 0; r < kUpdRows; ++r) {
+      const int k = rb * kUpdRows + r;
+      const int64_t idx = row0 + (int64_t)r * H;
+      a.small[idx] = w16[r];
+      a.m_small[idx] = m16[r];
+      a.v_small[idx] = v16[r];
       if (a.slice_mode == 1)
-        store_images(a.w_fs, a.w_bs, i, k, j, w);
+        store_images(a.w_fs, a.w_bs, i, k, j, w16[r]);
       else
-        store_sliced(a.w_fs, a.w_bs, H, a.Hc, i, k, j, w);
+        store_sliced(a.w_fs, a.w_bs, H, a.Hc, i, k, j, w16[r]);
     }
     if (rb == 0) adam_at(sl.bh(i) + j, bsum);
   } else {

@@ -168,6 +168,16 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   }
   const int64_t r_row = (tid < kRB && (b0 + tid) < nb) ? row_of(a.src, a.st, b0 + tid) : 0;
   const int step_id = a.st->step_id;
+  // Optimizer bookkeeping of this step (Keras Adam: alpha from t >= 1), computed now by the thread that will
+  // publish it, off the critical path: the two powf cost about a microsecond at the very end otherwise.
+  __shared__ float s_alpha_next;
+  __shared__ int s_t_next;
+  if (a.training && tid == kThreads - 1 && r == 0) {  // a thread nobody waits for before the kernel's last barrier
+    const int t_next = a.st->t + 1;
+    const float b1p = powf(kAdamB1, (float)t_next), b2p = powf(kAdamB2, (float)t_next);
+    s_t_next = t_next;
+    s_alpha_next = a.st->lr * sqrtf(1.f - b2p) / (1.f - b1p);
+  }
   const float keep_scale = 1.0f / (1.0f - a.p_drop);
   const bool drop_on = a.training && a.p_drop > 0.f;
   // ---- layer 0, first half: split-K partial tiles of Z1 for the own [8 x 64] block (fixed order).
@@ -195,7 +205,7 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   if (a.wait_bwd != 0) {
     // launched ahead of the first-layer backward whose fused forward leaves this step's Z1 partial tiles: every
     // CTA of that kernel bumps DevState::bwd_cnt once all it wrote is visible
-    if (tid == 0) wait_counter(&a.st->bwd_cnt, a.wait_bwd, &a.st->nonfinite);
+    if (tid == 0) wait_counter(&a.st->bwd_cnt, a.wait_bwd, &a.st->nonfinite, 20u);  // 16 pollers in all: poll tightly
     __syncthreads();
     if (tid == 0 && r == 0) tl_mark(a.tl, 23u, (unsigned)a.tl_id);  // the backward's tiles are there
   }
@@ -534,42 +544,39 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_barrier();  // nobody exits while peers may still address its shared memory; global writes visible
+  if (a.training && r == 0 && tid == 0) {
+    // Hand-over first: the kernels launched ahead of this one's end (first-layer backward, small-layer update) wait
+    // for hid_seq.  dz / activations of every CTA were written before the cluster barrier above; the optimizer
+    // state they read is written here; the loss bookkeeping below is nobody's input and comes after.
+    DevState* st = a.st;
+    st->t = s_t_next;
+    st->step_id = step_id + 1;
+    st->alpha = s_alpha_next;
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->hid_seq), "r"(a.hid_seq) : "memory");
+    tl_mark(a.tl, 24u, (unsigned)a.tl_id);  // published
+  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
   if (tid == 0 && (r == 0 || r == kC - 1)) tl_mark(a.tl, r ? 20u : 4u, (unsigned)a.tl_id);
-  if (r == 0 && warp == 0) {
+  if (r == 0 && warp == 0 && (a.training || a.has_targets)) {
     DevState* st = a.st;
     // per-row distances of all batch groups (written before the barrier): one L2 round trip, fixed-order sum
-    float s = 0.f;
-    if ((a.training || a.has_targets) && lane < nb) s = __ldcg(a.outs + 192 + lane);
+    float s = lane < nb ? __ldcg(a.outs + 192 + lane) : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) {
-      if (a.training || a.has_targets) {
-        const float mean = s / (float)nb;
-        if (a.training) {
-          st->loss_total += mean * (float)nb;
-          st->loss_count += (float)nb;
-          st->last_loss = mean;
-          if (!isfinite(mean)) st->nonfinite = 1;
-        } else if (a.val_slot != nullptr) {  // chunks of a wide pass run concurrently: summed in order afterwards
-          a.val_slot[0] = mean * (float)nb;
-          a.val_slot[1] = (float)nb;
-        } else {
-          st->val_total += mean * (float)nb;
-          st->val_count += (float)nb;
-        }
-      }
-      if (a.training) {  // optimizer bookkeeping for the update kernels of this step (Keras Adam: alpha from t >= 1)
-        const int t = st->t + 1;
-        st->t = t;
-        st->step_id = step_id + 1;
-        const float b1p = powf(kAdamB1, (float)t), b2p = powf(kAdamB2, (float)t);
-        st->alpha = st->lr * sqrtf(1.f - b2p) / (1.f - b1p);
-        // hand-over to the kernels launched ahead of this one's end (first-layer backward, small-layer update):
-        // dz / activations of every CTA were written before the cluster barrier above, the state just now
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->hid_seq), "r"(a.hid_seq) : "memory");
-        tl_mark(a.tl, 24u, (unsigned)a.tl_id);  // published
+      const float mean = s / (float)nb;
+      if (a.training) {
+        st->loss_total += mean * (float)nb;
+        st->loss_count += (float)nb;
+        st->last_loss = mean;
+        if (!isfinite(mean)) st->nonfinite = 1;
+      } else if (a.val_slot != nullptr) {  // chunks of a wide pass run concurrently: summed in order afterwards
+        a.val_slot[0] = mean * (float)nb;
+        a.val_slot[1] = (float)nb;
+      } else {
+        st->val_total += mean * (float)nb;
+        st->val_count += (float)nb;
       }
     }
   }

@@ -166,6 +166,16 @@ __device__ __forceinline__ uint32_t swz32(int r, int c) {
   return (uint32_t)(r * 128 + (((((c >> 1) ^ (r & 3)) << 1) | (c & 1)) << 4));
 }
 
+// Split of the 64-SNP tiles over the CTAs of a first-layer kernel: the first (ntiles % grid) CTAs take one tile
+// more than the others.  The CTAs with the smaller share are the LAST ones: in a chained step (model.cu:
+// train_step) the hidden stack still holds 16 SMs when the backward is launched, and the CTAs that have to wait
+// for those SMs -- the last ones the block scheduler hands out -- then finish no later than the rest.
+__device__ __forceinline__ void tile_range(int64_t ntiles, int64_t& t_begin, int64_t& t_end) {
+  const int64_t q = ntiles / gridDim.x, rem = ntiles % gridDim.x, b = blockIdx.x;
+  t_begin = b * q + (b < rem ? b : rem);
+  t_end = t_begin + q + (b < rem ? 1 : 0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------------------------
@@ -195,8 +205,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(L1Args a, int64_t nt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = a.src.nb;
   // ntiles counts 64-SNP tiles (the backward kernel's unit) so both kernels split K identically
-  const int64_t t_begin = 2 * (ntiles * blockIdx.x / gridDim.x);
-  const int64_t t_end = 2 * (ntiles * (blockIdx.x + 1) / gridDim.x);
+  int64_t t_begin, t_end;
+  tile_range(ntiles, t_begin, t_end);
+  t_begin *= 2;  // 32-SNP stages
+  t_end *= 2;
   const int nloc = (int)(t_end - t_begin);
 
   if (threadIdx.x == 0) {
@@ -382,8 +394,10 @@ __global__ void __launch_bounds__(W_THREADS, 1) k_l1_fwd_wide(L1Args a, int64_t 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NC = (nrows + 31) >> 5, N = NC * 32;  // 32-row chunks, MMA N
-  const int64_t t_begin = 2 * (ntiles * blockIdx.x / gridDim.x);
-  const int64_t t_end = 2 * (ntiles * (blockIdx.x + 1) / gridDim.x);
+  int64_t t_begin, t_end;
+  tile_range(ntiles, t_begin, t_end);
+  t_begin *= 2;  // 32-SNP stages
+  t_end *= 2;
   const int nloc = (int)(t_end - t_begin);
 
   if (threadIdx.x == 0) {
@@ -606,8 +620,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = a.src.nb;
   const bool fuse = a.fuse_next != 0;  // also run the NEXT step's forward on the freshly updated chunks
-  const int64_t t_begin = ntiles * blockIdx.x / gridDim.x;
-  const int64_t t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+  int64_t t_begin, t_end;
+  tile_range(ntiles, t_begin, t_end);
   const int nloc = (int)(t_end - t_begin);
   const int nchunks = nloc * (B_NT / B_CH);
   // odd steps walk the tiles downwards (L1Args::alternate); chunks inside a tile keep their order
@@ -1083,8 +1097,8 @@ __global__ void __launch_bounds__(32, 1) k_l1_prefetch(L1Args a, int64_t ntiles,
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (a.gated && a.st->stopped) return;
   if (threadIdx.x != 0) return;
-  const int64_t t_begin = ntiles * blockIdx.x / gridDim.x;
-  const int64_t t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+  int64_t t_begin, t_end;
+  tile_range(ntiles, t_begin, t_end);
   const int nloc = (int)(t_end - t_begin);
   const int nchunks = nloc * (B_NT / B_CH);
   const bool rev = a.alternate && ((a.st->t + t_ahead) & 1);

@@ -371,11 +371,10 @@ static int backward_tc(loc_model* m, L1Args& a, cudaStream_t s, bool overlap_pre
 }
 
 // Can one model's step run as a chain of programmatic dependent launches (see train_step)?  Needs the tcgen05
-// kernels, no sharding, and first-layer kernels that leave the hidden stack's 16 SMs alone.
+// kernels and no sharding (the exchange of a sharded model sits between the kernels).
 static bool chain_capable(const loc_model* m) {
   const bool off = getenv("LOC_NO_CHAIN") != nullptr;  // read per call: tests compare both schedules in one process
-  return !off && m->use_tc && m->hid_tc && m->exchange == nullptr && m->tp == nullptr &&
-         m->n_bwd_blocks <= sm_count() - 16;
+  return !off && m->use_tc && m->hid_tc && m->exchange == nullptr && m->tp == nullptr;
 }
 
 // One optimizer step: 3-4 launches (stage_mask selects a subset for profiling / tests).
@@ -384,16 +383,20 @@ static bool chain_capable(const loc_model* m) {
 // following step is called with have_fwd = true and skips its own forward launch.
 //
 // Chained steps (chain_capable): the step's kernels go into ONE stream as  H -> B -> U  (hidden stack on its
-// 16-SM cluster, first-layer backward + Adam (+ next forward) on the other SMs, small-layer update), every one of
-// them launched with programmatic stream serialization, i.e. scheduled as soon as its predecessor's CTAs are all
-// running instead of after it has drained:
-//   B is resident and has its barriers, TMEM and the first ring stages of W1 | m | v ready while H still runs; it
-//     waits for DevState::hid_seq (published by H after its last write) before it touches dZ1;
-//   U takes H's SMs the moment H exits (same flag), and finishes long before B;
-//   the NEXT step's H is placed behind U -- griddepcontrol.wait covers U's results -- sets itself up and waits for
+// 16-SM cluster, first-layer backward + Adam (+ next forward), small-layer update), every one of them launched
+// with programmatic stream serialization, i.e. scheduled as soon as its predecessor's CTAs are all running instead
+// of after it has drained, and handing over through two device flags instead of kernel boundaries:
+//   B's CTAs take the 132 SMs H does not use while H still runs: barriers, TMEM and the first ring stages of
+//     W1 | m | v are ready when H publishes DevState::hid_seq (after its last write), which B waits for before it
+//     touches dZ1.  Its last 16 CTAs get H's SMs when H exits; they hold the smaller tile shares (tile_range in
+//     l1_tc.cu), so they still finish with the others.  (With fewer first-layer CTAs than SMs --
+//     loc_model_set_l1_ctas, replicate rings -- all of B is resident early.)
+//   U is placed wherever SMs free up (H's SMs at once when B leaves them alone, else B's first finishers) and
+//     waits for the same flag;
+//   the NEXT step's H is queued behind U -- griddepcontrol.wait covers U's results -- and waits for
 //     DevState::bwd_cnt (one count per finished CTA of B) before it reads the Z1 tiles B's fused forward left.
 // Kernel boundaries (drain + launch + ramp: 6-15 us each on this part, `scripts/timeline.py`) disappear from the
-// step's critical path; what remains is H + B.
+// step's critical path; what remains is H + B plus the flags' latency.
 static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s, int stage_mask = 15,
                       const RowSrc* next = nullptr, bool have_fwd = false) {
   L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, gated);
@@ -622,14 +625,10 @@ static void set_geometry(loc_model* m, int64_t K) {
   m->k_offset = 0;
   const int sms = sm_count();
   if (m->use_tc) {
-    // The first-layer kernels leave one 16-SM cluster's worth of SMs to the hidden stack: a step then runs as a
-    // chain of overlapping launches (train_step) and replicate groups as a ring (loc_group_train_epochs).  The
-    // stream of W1 | m | v is HBM-bound and as fast on SMs - 16 CTAs as on all of them.  The CTA count fixes the
-    // fp32 summation order of the layer, so it is the same for every schedule; loc_model_set_l1_ctas overrides.
-    const int full = l1_tc_partials(K);
-    const int spare = sms - 16 > 1 ? sms - 16 : 1;
-    static const bool all_sms = getenv("LOC_L1_ALL_SMS") != nullptr;
-    m->n_partials = (full < spare || all_sms) ? full : spare;
+    // One CTA per SM (or per tile for small K).  loc_model_set_l1_ctas lowers the count: replicate groups of
+    // large models keep one 16-SM cluster's worth of SMs free for the hidden stacks (ring schedule).  The count
+    // fixes the fp32 summation order of the layer.
+    m->n_partials = l1_tc_partials(K);
     m->n_bwd_blocks = m->n_partials;
   } else {
     const int64_t nch = cdiv(K, kF1Chunk);
@@ -1086,6 +1085,7 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
     loc_model* m;
     L1Args a;
     UpdArgs u;
+    unsigned hid_seq;  // what the model's hidden stack of this step publishes when it is done
   };
   for (int e = 0; e < n_epochs; ++e) {
     if (ring) {
@@ -1094,9 +1094,22 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
       // measured 4 % slower).  Each ring runs its whole epoch; the models are independent.
       for (int g0 = 0; g0 < n_models;) {
         const int g1 = (n_models - g0 == 3) ? n_models : (g0 + 2 < n_models ? g0 + 2 : n_models);
+        // Rings of two also hand over through the device flags of the chained step (train_step): in the stream
+        // ... B(m) U(m) H(m) ... every hidden stack directly follows its own model's update, so it can be launched
+        // with programmatic serialization too -- placed and set up while the OTHER model's backward streams,
+        // waiting for its own model's previous backward by DevState::bwd_cnt.  The backward kernels then follow
+        // each other without a gap: a slot costs one weight stream, not stream + kernel boundaries.
+        const bool chain2 = g1 - g0 == 2 && getenv("LOC_NO_CHAIN") == nullptr;
         bool have_fwd = false;
         Pending pend;
         pend.m = nullptr;
+        auto launch_pending = [&](bool overlap) -> int {
+          pend.a.wait_hid = pend.hid_seq;
+          pend.a.wait_bwd = pend.m->h_bwd_cnt;
+          pend.u.wait_hid = pend.hid_seq;
+          if (backward_tc(pend.m, pend.a, s, overlap)) return 1;
+          return hidden_update_launch(pend.u, s, overlap);
+        };
         for (int64_t off = 0; off < m0->n_train; off += m0->B) {
           const bool has_next = off + m0->B < m0->n_train;
           for (int g = g0; g < g1; ++g) {
@@ -1106,11 +1119,10 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
             if (!have_fwd && forward_l1(m, a, s)) return 1;  // first step of the epoch: later ones are fused
             HidArgs h = hid_args(m, src, 1, 1, m->train_locs, nullptr);
             begin_training_hidden(m, h);
-            if (hidden_tc_launch(h, s)) return 1;
-            if (pend.m != nullptr) {
-              if (backward_tc(pend.m, pend.a, s, true)) return 1;
-              if (hidden_update_launch(pend.u, s, true)) return 1;
-            }
+            const bool h_overlaps = chain2 && have_fwd;  // directly behind this model's own backward + update
+            if (h_overlaps) h.wait_bwd = m->h_bwd_cnt;
+            if (hidden_tc_launch(h, s, h_overlaps)) return 1;
+            if (pend.m != nullptr && launch_pending(true)) return 1;
             if (has_next) {
               a.src_next = step_rows(g, off + m0->B);
               a.fuse_next = 1;
@@ -1118,13 +1130,11 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
             pend.m = m;
             pend.a = a;
             pend.u = upd_args(m, src.nb, 1);
+            pend.hid_seq = h.hid_seq;
           }
           have_fwd = has_next;
         }
-        if (pend.m != nullptr) {  // the ring's last backward and update of the epoch
-          if (backward_tc(pend.m, pend.a, s)) return 1;
-          if (hidden_update_launch(pend.u, s)) return 1;
-        }
+        if (pend.m != nullptr && launch_pending(false)) return 1;  // the ring's last backward and update of the epoch
         g0 = g1;
       }
     }

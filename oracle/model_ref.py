@@ -159,11 +159,15 @@ class RefLocator:
         return y2, c
 
     def _l1_in_parts(self, a, w):
-        """a @ w with the K axis cut like the device cuts it: 64-SNP tiles, part p = tiles [nt*p/P, nt*(p+1)/P)."""
+        """a @ w with the K axis cut like the device cuts it (csrc/l1_tc.cu: tile_range): 64-SNP tiles, the first
+        nt % P parts one tile longer than the rest."""
         nt, P = -(-self.K // 64), self.l1_parts
+        q, rem = divmod(nt, P)
         z = None
         for p in range(P):
-            k0, k1 = min(self.K, 64 * (nt * p // P)), min(self.K, 64 * (nt * (p + 1) // P))
+            t0 = p * q + min(p, rem)
+            t1 = t0 + q + (1 if p < rem else 0)
+            k0, k1 = min(self.K, 64 * t0), min(self.K, 64 * t1)
             if k1 > k0:
                 part = a[:, k0:k1] @ w[k0:k1]
                 z = part if z is None else z + part

@@ -514,7 +514,7 @@ def main():
             return {"epochs": ne_g, "value": world * G * ne_g * ntr / (gms / 1000.0),
                     "ms_per_step_per_replicate": gms / (ne_g * spe * G), "last_loss_model0": loss}
 
-        ring = measure_group(None, "ring")       # default first-layer CTA count: SMs - 16
+        ring = measure_group(model.spare_cluster_l1_ctas(), "ring")  # first-layer kernels on SMs - 16, as the CLI's replicate runs
         lock = measure_group(148, "lockstep")    # every SM for the first-layer kernels, hidden stacks in one launch
         group = {"replicates_per_gpu": G, "epochs": ring["epochs"], "value": ring["value"],
                  "unit": "samples/s (all replicates)", "ms_per_step_per_replicate": ring["ms_per_step_per_replicate"],

@@ -171,9 +171,14 @@ __device__ __forceinline__ uint32_t swz32(int r, int c) {
 // train_step) the hidden stack still holds 16 SMs when the backward is launched, and the CTAs that have to wait
 // for those SMs -- the last ones the block scheduler hands out -- then finish no later than the rest.
 __device__ __forceinline__ void tile_range(int64_t ntiles, int64_t& t_begin, int64_t& t_end) {
+#if LOC_SPLIT_INTERLEAVED  // A/B: the shares of q and q + 1 tiles interleaved over the CTAs
+  t_begin = ntiles * blockIdx.x / gridDim.x;
+  t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+#else
   const int64_t q = ntiles / gridDim.x, rem = ntiles % gridDim.x, b = blockIdx.x;
   t_begin = b * q + (b < rem ? b : rem);
   t_end = t_begin + q + (b < rem ? 1 : 0);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -534,6 +539,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) k_l1_fwd_wide(L1Args a, int64_t 
 // ---------------------------------------------------------------------------------------------
 // Backward + Adam
 // ---------------------------------------------------------------------------------------------
+#ifndef LOC_SPLIT_INTERLEAVED
+#define LOC_SPLIT_INTERLEAVED 0
+#endif
 #ifndef LOC_FWD_WARPS
 #define LOC_FWD_WARPS 4  // forward warps of the fused backward (2 or 4): each takes every LOC_FWD_WARPS-th chunk
 #endif

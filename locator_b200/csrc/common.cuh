@@ -79,6 +79,9 @@ struct DevState {
   // launched before their producers have finished and wait here instead of at a kernel boundary.
   unsigned hid_seq;  // number of training hidden-stack launches completed (published at the kernel's very end)
   unsigned bwd_cnt;  // CTAs of first-layer backward launches completed, cumulative
+  unsigned upd_cnt;  // blocks of small-layer update launches completed, cumulative
+  unsigned dz_cnt[64];  // per Dense(width) layer i: CTAs of training hidden stacks that have written dz_i (and everything
+                        // the layer's update needs), cumulative -- the update of layer i starts under the hidden stack
 };
 
 // Spin until *flag has reached `expect` (wrap-safe); gives up after ~2 s and raises *err instead of hanging the GPU.

@@ -522,18 +522,50 @@ constexpr int kUpdRows = 16;
 // (register cap: two 256-thread blocks per SM)
 __global__ void __maxnreg__(120) k_hidden_update(UpdArgs a) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next hidden stack may be scheduled behind us
-  if (a.gated && a.st->stopped) return;
-  if (a.wait_hid != 0) {  // launched ahead of the end of the hidden stack whose activations / dz it consumes
-    if (threadIdx.x == 0) wait_counter(&a.st->hid_seq, a.wait_hid, &a.st->nonfinite);
-    __syncthreads();
+  if (a.gated && a.st->stopped) {  // past the stopping epoch: a no-op that still keeps the hand-over counter in step
+    if (threadIdx.x == 0) atomicAdd(&a.st->upd_cnt, 1u);
+    return;
   }
-  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) tl_mark(a.tl, blockIdx.x ? 21u : 5u, (unsigned)a.tl_id);
   __shared__ float as[kUpdRows][kMaxB + 1];
   const int H = a.H, L = a.L, j = threadIdx.x;
   const SmallLayout sl{H, L};
-  const float alpha = a.st->alpha;
   const int rb_n = H / kUpdRows;
   const int nblk_hidden = (L - 1) * rb_n;
+  const bool hidden_block = (int)blockIdx.x < nblk_hidden;
+  // Weights and Adam moments of the block's 16 rows do not depend on the hidden stack this launch may be waiting
+  // for (the previous update wrote them): their loads go out BEFORE the wait, while HBM idles under that stack.
+  float w16[kUpdRows], m16[kUpdRows], v16[kUpdRows];
+  int64_t row0 = 0;
+  if (a.wait_dz != 0 && a.wait_upd != 0) {
+    if (threadIdx.x == 0) wait_counter(&a.st->upd_cnt, a.wait_upd, &a.st->nonfinite);
+    __syncthreads();
+  }
+  if (hidden_block) {
+    const int i = 1 + blockIdx.x / rb_n, rb = blockIdx.x % rb_n;
+    row0 = sl.Wh(i) + (int64_t)(rb * kUpdRows) * H + j;
+#pragma unroll
+    for (int r = 0; r < kUpdRows; ++r) {
+      const int64_t idx = row0 + (int64_t)r * H;
+      w16[r] = a.small[idx];
+      m16[r] = a.m_small[idx];
+      v16[r] = a.v_small[idx];
+    }
+  }
+  {
+    // Launched ahead of the end of the hidden stack whose activations / dz it consumes.  wait_dz: launched UNDER it --
+    // the blocks of hidden layer i start as soon as all 16 CTAs of the stack have written dz_i (the stack's backward
+    // chain reaches layer i long before it ends); only the last block (b1, Dense(2), Dense(2)) needs its end.
+    const int layer = 1 + (int)blockIdx.x / rb_n;
+    if (a.wait_dz != 0 && hidden_block) {
+      if (threadIdx.x == 0) wait_counter(&a.st->dz_cnt[layer], a.wait_dz, &a.st->nonfinite);
+      __syncthreads();
+    } else if (a.wait_hid != 0) {
+      if (threadIdx.x == 0) wait_counter(&a.st->hid_seq, a.wait_hid, &a.st->nonfinite);
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) tl_mark(a.tl, blockIdx.x ? 21u : 5u, (unsigned)a.tl_id);
+  const float alpha = a.st->alpha;
   auto adam_at = [&](int64_t idx, float g) -> float {
     float w = a.small[idx], m = a.m_small[idx], v = a.v_small[idx];
     adam_update(w, m, v, g, alpha);
@@ -558,15 +590,6 @@ __global__ void __maxnreg__(120) k_hidden_update(UpdArgs a) {
       const int idx = threadIdx.x + q * blockDim.x;
       const int kk = idx % kUpdRows, b = idx / kUpdRows;
       as_reg[q] = idx < kUpdRows * kMaxB ? a.acts[((int64_t)(i - 1) * kMaxB + b) * H + rb * kUpdRows + kk] : 0.f;
-    }
-    const int64_t row0 = sl.Wh(i) + (int64_t)(rb * kUpdRows) * H + j;
-    float w16[kUpdRows], m16[kUpdRows], v16[kUpdRows];
-#pragma unroll
-    for (int r = 0; r < kUpdRows; ++r) {
-      const int64_t idx = row0 + (int64_t)r * H;
-      w16[r] = a.small[idx];
-      m16[r] = a.m_small[idx];
-      v16[r] = a.v_small[idx];
     }
     float bsum = 0.f;
 #pragma unroll
@@ -634,7 +657,12 @@ __global__ void __maxnreg__(120) k_hidden_update(UpdArgs a) {
       adam_at(sl.bo2() + c, s);
     }
   }
-  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) tl_mark(a.tl, blockIdx.x ? 22u : 6u, (unsigned)a.tl_id);
+  __syncthreads();
+  if (threadIdx.x == 0) {  // the next hidden stack of this model reads what this block wrote
+    __threadfence();
+    atomicAdd(&a.st->upd_cnt, 1u);
+    if (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) tl_mark(a.tl, blockIdx.x ? 22u : 6u, (unsigned)a.tl_id);
+  }
 }
 
 static size_t hidden_fixed_floats(int H, int L, int cluster) {

@@ -91,6 +91,7 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (a.gated && a.st->stopped) {  // past the stopping epoch: a no-op that still keeps the hand-over flag in step
     if (a.training && threadIdx.x == 0 && cluster_rank() == 0) a.st->hid_seq = a.hid_seq;
+    if (a.training && threadIdx.x >= 1 && (int)threadIdx.x < a.L) atomicAdd(&a.st->dz_cnt[threadIdx.x], 1u);
     return;
   }
   extern __shared__ uint8_t smem_raw[];
@@ -138,7 +139,13 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   // its results -- the weight-slice images and biases read below -- are complete after this wait.  A no-op for
   // plain launches.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  __shared__ int s_dz_done;  // lowest layer whose dz this CTA has written completely (backward chain)
+  if (a.wait_upd != 0) {  // the small-layer update of the previous step ran under that step's hidden stack
+    if (tid == 0) wait_counter(&a.st->upd_cnt, a.wait_upd, &a.st->nonfinite, 20u);
+    __syncthreads();
+  }
   if (tid == 0) {
+    s_dz_done = a.L;
     mbar_init(&wbar[0], 1);
     mbar_init(&wbar[1], 1);
     mbar_init(&ready[0], 1);
@@ -208,6 +215,11 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
     if (tid == 0) wait_counter(&a.st->bwd_cnt, a.wait_bwd, &a.st->nonfinite, 20u);  // 16 pollers in all: poll tightly
     __syncthreads();
     if (tid == 0 && r == 0) tl_mark(a.tl, 23u, (unsigned)a.tl_id);  // the backward's tiles are there
+  }
+  if (a.training && r == 0 && tid == kThreads - 1) {
+    // Nothing reads the previous step's alpha any more (its backward and update are complete: waited for above or
+    // ordered by the stream): this step's value goes out now, for the update blocks that start under this kernel.
+    a.st->alpha = s_alpha_next;
   }
   const int p0_item = tid & 127, p0_g = tid >> 7;  // 128 float4 outputs x 4 partial groups
   const int p0_b = p0_item >> 4, p0_jl = (p0_item & 15) * 4;
@@ -338,11 +350,14 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
     mark();
   };
   // worker warps: the own [8 x 64] slice is staged -> to the 4 CTAs of the batch group
-  auto publish_workers = [&]() {
+  auto publish_workers = [&](int dz_layer_done = -1) {
     mark();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("bar.sync 1, 128;" ::: "memory");
     mark();
+    // backward chain: every worker's dz of this layer is in global memory -- tell the signalling warp
+    if (dz_layer_done >= 0 && tid == 0)
+      asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(&s_dz_done)), "r"(dz_layer_done) : "memory");
     if (lane == 0) {
       const uint32_t src = smem_u32(stage + (pub & 1) * kStage);
       const uint32_t dst_local = smem_u32(gath + (pub & 1) * kGath + cj * kStage);
@@ -530,12 +545,33 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
       finish_bwd_elem(L - 1, b, jl, dy1s[2 * b] * sout[2 * i] + dy1s[2 * b + 1] * sout[2 * i + 1]);
     }
     publish_staged();
+    // Warp 4 hands finished layers to the small-layer update, which may already be resident on other SMs
+    // (UpdArgs::wait_dz): dz of layer L-1 is complete here (block-wide barrier in publish_staged above); the chain
+    // below reports further layers through s_dz_done.  The fence + atomic stay off the worker warps' chain.
+    if (warp == 4) {
+      int next = L - 1;  // highest layer not signalled yet
+      int done = L - 1;
+      while (next >= 1) {
+        if (done <= next) {
+          if (lane == 0) {
+            __threadfence();
+            for (int k = next; k >= done; --k) atomicAdd(&a.st->dz_cnt[k], 1u);
+          }
+          next = done - 1;
+          if (next < 1) break;
+        }
+        int d;
+        asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(d) : "r"(smem_u32(&s_dz_done)) : "memory");
+        done = d < done ? d : done;
+        if (done > next) __nanosleep(100);
+      }
+    }
     for (int i = L - 1; i >= 1; --i, ++use) {
       if (warp < 4) {
         float z[4];
         layer_mma(use, true, z);
         finish_bwd4(i - 1, w_b0, w_jl, z);
-        if (i > 1) publish_workers();
+        if (i > 1) publish_workers(i - 1);
       }
       if (i > 1) ++pub;
       ++nmma;

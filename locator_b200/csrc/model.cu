@@ -73,8 +73,10 @@ __global__ void k_state_reset(DevState* st, float lr, int patience, int max_epoc
   st->max_epochs = max_epochs;
   st->nonfinite = 0;
   st->last_loss = st->last_val = 0.f;
-  st->hid_seq = 0u;  // hand-over flags of the chained step (host mirrors: loc_model::h_hid_seq / h_bwd_cnt)
+  st->hid_seq = 0u;  // hand-over flags of the chained step (host mirrors: loc_model::h_hid_seq / h_bwd_cnt / h_upd_cnt)
   st->bwd_cnt = 0u;
+  st->upd_cnt = 0u;
+  for (int i = 0; i < 64; ++i) st->dz_cnt[i] = 0u;
 }
 
 __global__ void k_begin_call(DevState* st) { st->epoch0 = st->epoch; }
@@ -298,6 +300,7 @@ static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated
   h.wait_seq = 0;
   h.wait_err = nullptr;
   h.wait_bwd = 0u;
+  h.wait_upd = 0u;
   h.hid_seq = 0u;
   h.partials = m->exchange != nullptr ? m->z1_tile : m->partials;
   h.n_partials = m->exchange != nullptr ? 1 : m->n_partials;
@@ -349,6 +352,8 @@ static UpdArgs upd_args(loc_model* m, int nb, int gated) {
   u.outs = m->outs;
   u.nb = nb;
   u.wait_hid = 0u;
+  u.wait_dz = 0u;
+  u.wait_upd = 0u;
   u.tl = timeline_buffer();
   u.tl_id = m->tl_id;
   u.st = m->st;
@@ -367,6 +372,13 @@ static int backward_tc(loc_model* m, L1Args& a, cudaStream_t s, bool overlap_pre
   a.rev = (int)(m->h_steps & 1);
   if (l1_backward_tc(a, m->n_bwd_blocks, s, overlap_previous)) return 1;
   m->h_bwd_cnt += (unsigned)m->n_bwd_blocks;
+  return 0;
+}
+
+// Small-layer update + the host mirror of the counter its blocks bump when they are done.
+static int update_launch(loc_model* m, const UpdArgs& u, cudaStream_t s, bool overlap_previous = false) {
+  if (hidden_update_launch(u, s, overlap_previous)) return 1;
+  m->h_upd_cnt += (unsigned)((m->L - 1) * (m->H / 16) + 1);
   return 0;
 }
 
@@ -412,15 +424,27 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
   if (stage_mask & 2) {
     begin_training_hidden(m, h);
     if (h_overlaps) h.wait_bwd = m->h_bwd_cnt;  // every CTA of the previous step's backward has signed off
+    if (chain) h.wait_upd = m->h_upd_cnt;       // ... and every block of the small-layer updates so far
     if (m->hid_tc ? hidden_tc_launch(h, s, h_overlaps) : hidden_launch(h, m->cluster, s)) return 1;
   }
   if (chain) {
+    // U goes in FRONT of B: its blocks land on the SMs that idle under the hidden stack and update layer i as soon
+    // as the stack's backward chain has produced dz_i (DevState::dz_cnt), so the update is finished a couple of
+    // microseconds after H instead of occupying the SMs between B's end and the next H.  B's CTAs take the SMs the
+    // update's blocks leave (LOC_CHAIN_ORDER=hbu: the update behind the backward, as in the replicate rings).
+    const char* order = getenv("LOC_CHAIN_ORDER");
+    const bool u_first = order == nullptr || strcmp(order, "hbu") != 0;
+    UpdArgs u = upd_args(m, src.nb, gated);
+    u.wait_hid = h.hid_seq;
+    if (u_first) {
+      u.wait_dz = 16u * h.hid_seq;  // 16 CTAs of every training hidden stack so far
+      u.wait_upd = m->h_upd_cnt;    // every block of the updates launched so far
+      if (update_launch(m, u, s, true)) return 1;
+    }
     a.wait_hid = h.hid_seq;
     a.wait_bwd = m->h_bwd_cnt;  // every backward launched so far for this model
     if (backward_tc(m, a, s, true)) return 1;
-    UpdArgs u = upd_args(m, src.nb, gated);
-    u.wait_hid = h.hid_seq;
-    if (hidden_update_launch(u, s, true)) return 1;
+    if (!u_first && update_launch(m, u, s, true)) return 1;
     m->chain_open = 1;
     m->chain_stream = s;
     return 0;
@@ -441,7 +465,7 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
     return 0;
   }
   UpdArgs u = upd_args(m, src.nb, gated);
-  if (hidden_update_launch(u, su)) return 1;
+  if (update_launch(m, u, su)) return 1;
   if (fork) LOC_CUDA(cudaEventRecord(m->ev_upd, m->side));
   if ((stage_mask & 4) && backward()) return 1;
   if ((stage_mask & 4) && a.fuse_next && exchange_partials(m, s)) return 1;  // the next step's tile is complete
@@ -697,7 +721,7 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
     r->span_perm = nullptr;
     r->span_next = 0;
     r->h_steps = 0;
-    r->h_hid_seq = r->h_bwd_cnt = 0u;
+    r->h_hid_seq = r->h_bwd_cnt = r->h_upd_cnt = 0u;
     r->chain_open = 0;
     if (zero_model(r)) {
       free_model(r);
@@ -835,7 +859,7 @@ int loc_model_init(loc_model* m, uint64_t seed, void* stream) {
   k_state_reset<<<1, 1, 0, s>>>(m->st, 1e-3f, 100, m->max_epochs, 1);
   LOC_LAUNCHED();
   m->h_steps = 0;
-  m->h_hid_seq = m->h_bwd_cnt = 0u;
+  m->h_hid_seq = m->h_bwd_cnt = m->h_upd_cnt = 0u;
   m->chain_open = 0;
   return 0;
 }
@@ -961,7 +985,7 @@ int loc_model_set_schedule(loc_model* m, float lr, int32_t patience) {
   LOC_CHECK(patience >= 0, "loc_model_set_schedule: patience must be >= 0");
   k_state_reset<<<1, 1>>>(m->st, lr, patience, m->max_epochs, 0);
   LOC_LAUNCHED();
-  m->h_hid_seq = m->h_bwd_cnt = 0u;
+  m->h_hid_seq = m->h_bwd_cnt = m->h_upd_cnt = 0u;
   m->chain_open = 0;
   LOC_CUDA(cudaDeviceSynchronize());
   return 0;
@@ -1108,7 +1132,7 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
           pend.a.wait_bwd = pend.m->h_bwd_cnt;
           pend.u.wait_hid = pend.hid_seq;
           if (backward_tc(pend.m, pend.a, s, overlap)) return 1;
-          return hidden_update_launch(pend.u, s, overlap);
+          return update_launch(pend.m, pend.u, s, overlap);
         };
         for (int64_t off = 0; off < m0->n_train; off += m0->B) {
           const bool has_next = off + m0->B < m0->n_train;
@@ -1162,7 +1186,7 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
         loc_model* m = models[g];
         LOC_CUDA(cudaStreamWaitEvent(m->side, m0->ev_hid, 0));
         UpdArgs u = upd_args(m, hg.a[g].src.nb, 1);
-        if (hidden_update_launch(u, m->side)) return 1;
+        if (update_launch(m, u, m->side)) return 1;
         LOC_CUDA(cudaEventRecord(m->ev_upd, m->side));
       }
       for (int g = 0; g < n_models; ++g) {

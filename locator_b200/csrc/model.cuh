@@ -117,6 +117,8 @@ struct HidArgs {
   long long* dbg;   // optional per-CTA clock64() checkpoints [C][256] (profiling builds of the step)
   unsigned wait_bwd;  // != 0: launched ahead of the backward that produces its Z1 tiles -- wait for DevState::bwd_cnt >= wait_bwd
   unsigned hid_seq;   // training launches: value to publish in DevState::hid_seq when everything is written
+  unsigned wait_upd;  // != 0: wait for DevState::upd_cnt >= wait_upd before the small weights are read (the update ran
+                      // under the previous hidden stack, not directly in front of this launch)
   unsigned long long* tl;  // kernel timeline buffer (diagnostics) or nullptr
   int tl_id;
   DevState* st;
@@ -140,6 +142,9 @@ struct UpdArgs {
   const float* outs;
   int nb;
   unsigned wait_hid;  // != 0: wait for DevState::hid_seq >= wait_hid (launched ahead of the hidden stack it consumes)
+  unsigned wait_upd;  // with wait_dz: the model's previous update must be complete before this one reads the weights (formally;
+                      // a whole first-layer backward lies between them)
+  unsigned wait_dz;   // != 0: launched UNDER that hidden stack -- the blocks of layer i only wait for DevState::dz_cnt[i] >= wait_dz
   unsigned long long* tl;  // kernel timeline buffer (diagnostics) or nullptr
   int tl_id;
   DevState* st;
@@ -257,6 +262,6 @@ struct loc_model {
   int64_t span_next;
   // host mirrors of DevState::hid_seq / bwd_cnt / optimizer step parity (what the launches made so far will have
   // published once they have run)
-  unsigned h_hid_seq, h_bwd_cnt;
+  unsigned h_hid_seq, h_bwd_cnt, h_upd_cnt;
   int64_t h_steps;
 };

@@ -66,7 +66,8 @@ def build_parser():
     parser.add_argument("--jacknife_prop", default=0.05, type=float,
                         help="proportion of SNPs to remove for jacknife resampling. default: 0.05")
     parser.add_argument("--nboots", default=50, type=int, help="number of bootstrap replicates to run. default: 50")
-    parser.add_argument("--batch_size", default=32, type=int, help="default: 32")
+    parser.add_argument("--batch_size", default=32, type=int,
+                        help="default: 32 (locator_b200: 1..32; larger batches are refused before any data is read)")
     parser.add_argument("--max_epochs", default=5000, type=int, help="default: 5000")
     parser.add_argument("--patience", type=int, default=100,
                         help="n epochs to run the optimizer after last improvement in validation loss. default: 100")
@@ -78,7 +79,9 @@ def build_parser():
     parser.add_argument("--dropout_prop", default=0.25, type=float,
                         help="proportion of weights to zero at the dropout layer. default: 0.25")
     parser.add_argument("--nlayers", default=10, type=int, help="number of layers in the network. default: 10")
-    parser.add_argument("--width", default=256, type=int, help="number of units per layer in the network default:256")
+    parser.add_argument("--width", default=256, type=int,
+                        help="number of units per layer in the network default:256 (locator_b200: a multiple of 32 in [32, 1024]; "
+                        "256 runs on the tensor cores, other widths on fp32 CUDA-core kernels)")
     parser.add_argument("--out", help="file name stem for output")
     parser.add_argument("--seed", default=None, type=int, help="random seed for train/test splits and SNP subsetting.")
     parser.add_argument("--gpu_number", default=None, type=str)

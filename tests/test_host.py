@@ -169,6 +169,62 @@ def test_bench_multi_rank_reduction_gloo_world2(tmp_path):
     assert float(line[2]) == round(2 * 100 * 32 / 0.011, 3)  # whole-job samples/s over both ranks
 
 
+_RANKQUEUE_SNIPPET = r"""
+import json, os, sys, time, torch.distributed as dist
+sys.path.insert(0, %r)
+from locator_b200 import replicates
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+store = dist.distributed_c10d._get_default_store()
+items = [{"kind": "boot", "boot": b} for b in range(23)]     # every rank derives the same list (seeded draws)
+q = replicates.RankQueue(items, w, store, key="t_queue", group=4)
+mine = []
+while True:
+    deep = q.queue_is_deep()
+    g = q.take_group()
+    if g is None:
+        break
+    mine.append(([it["boot"] for it in g], deep))
+    time.sleep(0.02 * len(g) * (1 + r))                       # ranks of different speed
+out = [None] * w
+dist.all_gather_object(out, mine)
+if r == 0:
+    print("RESULT", json.dumps(out))
+dist.destroy_process_group()
+"""
+
+
+def test_rank_queue_hands_out_every_item_once_gloo_world2(tmp_path):
+    """replicates.RankQueue (the work queue of a torchrun job: bench.py's cfg4 leg, `locator` under torchrun): the
+    ranks share nothing but one atomic counter in the job's store.  Two gloo ranks of different speed: every work
+    item is taken exactly once, in order inside a group, groups hold at most `group` items and shrink towards the
+    end of the queue (guided self-scheduling), and prefetching is only allowed while the queue is deep."""
+    script = tmp_path / "q.py"
+    script.write_text(_RANKQUEUE_SNIPPET % ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29534", str(script)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+
+    per_rank = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("RESULT")][0][7:])
+    taken = [b for groups in per_rank for g, _ in groups for b in g]
+    assert sorted(taken) == list(range(23))
+    for groups in per_rank:
+        assert groups, "both ranks must get work"
+        for g, deep in groups:
+            assert 1 <= len(g) <= 4 and g == sorted(g)
+    sizes_by_first = sorted((g[0], len(g), deep) for groups in per_rank for g, deep in groups)
+    assert sizes_by_first[0][1] == 4                      # full groups while the queue is long
+    assert sizes_by_first[-1][1] < 4                      # ... smaller ones at its end
+    assert any(d for _, _, d in sizes_by_first) and not sizes_by_first[-1][2]
+    # a single process (world 1, no store) walks the same queue with a local counter
+    from locator_b200 import replicates
+
+    q = replicates.RankQueue([{"boot": b} for b in range(6)], 1, None, group=4)
+    assert [len(g) for g in iter(q.take_group, None)] == [4, 2]
+
+
 def test_summarize_centroids_and_kernel_peaks(tmp_path):
     """Post-hoc summariser (reference locator_py/plot_locator.py:26-134): centroid = mean of the replicate
     predictions; kernel peak = the prediction with the highest Gaussian density (bandwidth 0.2)."""

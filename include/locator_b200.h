@@ -263,7 +263,12 @@ int loc_train_step(loc_model* m, const int32_t* d_rows, int32_t nb, void* stream
  * of batch_size (last partial), then the validation pass at batch 32, then the
  * callback state machine (checkpoint-best / early-stop / reduce-LR) and the
  * device-side snapshot, all on the GPU.  Async; epochs after the stop epoch are
- * no-ops.  History rows are appended per epoch. */
+ * no-ops.  History rows are appended per epoch.
+ * Scheduling (width 256, unsharded): inside an epoch the step's kernels -- hidden stack, small-layer update,
+ * first-layer backward + Adam + next step's forward -- are queued on `stream` as programmatic dependent launches
+ * that hand over through device-side flags instead of kernel boundaries ("Chained step");
+ * results are bit-identical to plain launches (environment LOC_NO_CHAIN=1).  Do not enqueue unrelated work that
+ * reads this model's buffers on another stream without synchronising with `stream` first. */
 int loc_train_epochs(loc_model* m, const int32_t* d_perms, int32_t n_epochs, void* stream);
 
 /* Part of an epoch on the same schedule as loc_train_epochs (the production path: every first-layer backward
@@ -303,7 +308,9 @@ int loc_restore_best(loc_model* m, void* stream);
 /* Force a snapshot of the live weights (used by tests). Async. */
 int loc_snapshot(loc_model* m, void* stream);
 
-/* Synchronising reads of device-side state / history ([epoch][3] = loss, val_loss, lr). */
+/* Synchronising reads of device-side state / history ([epoch][3] = loss, val_loss, lr).  loc_model_state fails
+ * (non-zero, loc_last_error) if a kernel of a chained step gave up waiting for its producer (2 s): an internal
+ * error that invalidates the model's results instead of hanging the GPU. */
 int loc_model_state(loc_model* m, loc_state* h_out, void* stream);
 int loc_model_history(loc_model* m, float* h_out, int32_t max_rows, void* stream);
 

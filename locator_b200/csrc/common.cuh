@@ -77,6 +77,7 @@ struct DevState {
   float last_loss, last_val;
   // Hand-over flags of the programmatic-dependent-launch chain (model.cu: train_step): kernels of one step are
   // launched before their producers have finished and wait here instead of at a kernel boundary.
+  int chain_timeout;  // a kernel of a chained step gave up waiting for its producer (~2 s): reported by loc_model_state
   unsigned hid_seq;  // number of training hidden-stack launches completed (published at the kernel's very end)
   unsigned bwd_cnt;  // CTAs of first-layer backward launches completed, cumulative
   unsigned upd_cnt;  // blocks of small-layer update launches completed, cumulative

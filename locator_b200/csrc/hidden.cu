@@ -537,7 +537,7 @@ __global__ void __maxnreg__(120) k_hidden_update(UpdArgs a) {
   float w16[kUpdRows], m16[kUpdRows], v16[kUpdRows];
   int64_t row0 = 0;
   if (a.wait_dz != 0 && a.wait_upd != 0) {
-    if (threadIdx.x == 0) wait_counter(&a.st->upd_cnt, a.wait_upd, &a.st->nonfinite);
+    if (threadIdx.x == 0) wait_counter(&a.st->upd_cnt, a.wait_upd, &a.st->chain_timeout);
     __syncthreads();
   }
   if (hidden_block) {
@@ -557,10 +557,10 @@ __global__ void __maxnreg__(120) k_hidden_update(UpdArgs a) {
     // chain reaches layer i long before it ends); only the last block (b1, Dense(2), Dense(2)) needs its end.
     const int layer = 1 + (int)blockIdx.x / rb_n;
     if (a.wait_dz != 0 && hidden_block) {
-      if (threadIdx.x == 0) wait_counter(&a.st->dz_cnt[layer], a.wait_dz, &a.st->nonfinite);
+      if (threadIdx.x == 0) wait_counter(&a.st->dz_cnt[layer], a.wait_dz, &a.st->chain_timeout);
       __syncthreads();
     } else if (a.wait_hid != 0) {
-      if (threadIdx.x == 0) wait_counter(&a.st->hid_seq, a.wait_hid, &a.st->nonfinite);
+      if (threadIdx.x == 0) wait_counter(&a.st->hid_seq, a.wait_hid, &a.st->chain_timeout);
       __syncthreads();
     }
   }

@@ -141,7 +141,7 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __shared__ int s_dz_done;  // lowest layer whose dz this CTA has written completely (backward chain)
   if (a.wait_upd != 0) {  // the small-layer update of the previous step ran under that step's hidden stack
-    if (tid == 0) wait_counter(&a.st->upd_cnt, a.wait_upd, &a.st->nonfinite, 20u);
+    if (tid == 0) wait_counter(&a.st->upd_cnt, a.wait_upd, &a.st->chain_timeout, 20u);
     __syncthreads();
   }
   if (tid == 0) {
@@ -212,7 +212,7 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   if (a.wait_bwd != 0) {
     // launched ahead of the first-layer backward whose fused forward leaves this step's Z1 partial tiles: every
     // CTA of that kernel bumps DevState::bwd_cnt once all it wrote is visible
-    if (tid == 0) wait_counter(&a.st->bwd_cnt, a.wait_bwd, &a.st->nonfinite, 20u);  // 16 pollers in all: poll tightly
+    if (tid == 0) wait_counter(&a.st->bwd_cnt, a.wait_bwd, &a.st->chain_timeout, 20u);  // 16 pollers in all: poll tightly
     __syncthreads();
     if (tid == 0 && r == 0) tl_mark(a.tl, 23u, (unsigned)a.tl_id);  // the backward's tiles are there
   }

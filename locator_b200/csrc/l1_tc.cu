@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     // ring stages of W1 | m | v run in its shadow): dZ1, alpha and the loss only exist once it has published.
     if (a.wait_hid != 0) {
       // ONE poller per CTA (2,700 polling warps on one L2 line slowed the very hidden stack they were waiting for)
-      if (threadIdx.x == 0) wait_counter(&a.st->hid_seq, a.wait_hid, &a.st->nonfinite);
+      if (threadIdx.x == 0) wait_counter(&a.st->hid_seq, a.wait_hid, &a.st->chain_timeout);
       asm volatile("bar.sync 4, %0;" ::"n"(B_THREADS - 32) : "memory");  // everyone but the load warp
     }
     // ... while everybody else stages dZ1 -> hi/lo tf32 operands, [chunk = j/32][row = b][swizzled 32 j]
@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_l1_bwd_tc(L1Args a, int64_t nt
     if (elect_one()) {
       // chained step: this CTA may have been placed on an SM that ANOTHER CTA of the model's previous backward
       // just left, while the CTA that owns these tiles there is still updating them
-      if (a.wait_hid != 0) wait_counter(&a.st->bwd_cnt, a.wait_bwd, &a.st->nonfinite);
+      if (a.wait_hid != 0) wait_counter(&a.st->bwd_cnt, a.wait_bwd, &a.st->chain_timeout);
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % B_STAGES;
         mbar_wait(&st_free[s], ((uint32_t)(c / B_STAGES) & 1u) ^ 1u);

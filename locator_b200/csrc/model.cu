@@ -73,6 +73,7 @@ __global__ void k_state_reset(DevState* st, float lr, int patience, int max_epoc
   st->max_epochs = max_epochs;
   st->nonfinite = 0;
   st->last_loss = st->last_val = 0.f;
+  st->chain_timeout = 0;
   st->hid_seq = 0u;  // hand-over flags of the chained step (host mirrors: loc_model::h_hid_seq / h_bwd_cnt / h_upd_cnt)
   st->bwd_cnt = 0u;
   st->upd_cnt = 0u;
@@ -1377,6 +1378,9 @@ int loc_model_state(loc_model* m, loc_state* h_out, void* stream) {
   h_out->es_wait = h.es_wait;
   h_out->rlr_wait = h.rlr_wait;
   h_out->nonfinite = h.nonfinite;
+  LOC_CHECK(h.chain_timeout == 0,
+            "loc_model_state: a kernel of a chained training step timed out waiting for its producer (device flags "
+            "hid_seq / bwd_cnt / upd_cnt / dz_cnt); results of this model are invalid -- LOC_NO_CHAIN=1 disables chaining");
   h_out->lr = h.lr;
   h_out->ckpt_best = h.ckpt_best;
   h_out->last_loss = h.last_loss;

@@ -118,5 +118,18 @@ if bs and be:
         hs = [(p_ - max([r_ for r_ in rdy if r_ <= p_], default=p_)) / 1000.0 for p_ in pub]
         print(f"chain: last B CTA done -> H sees tiles {np.median(d1):.1f} us; H tiles-ready -> published {np.median(hs):.1f} us; "
               f"H published -> that step's B all done {np.median(d2):.1f} us")
+    # per-block end times of every backward launch relative to the publication it waited for (chained step)
+    if pub:
+        ends_all = np.array(sorted(ti for ti, tg in zip(t, tag) if tg in (2, 18, 25)))
+        rows = []
+        for a_, b_ in zip(pub[:-1], pub[1:]):
+            e = ends_all[(ends_all > a_) & (ends_all <= b_)]
+            if len(e) >= 100:
+                d = (e - a_) / 1000.0
+                rows.append([len(e), d.min(), np.percentile(d, 25), np.median(d), np.percentile(d, 75), np.percentile(d, 95), d.max()])
+        if rows:
+            r_ = np.median(np.array(rows), axis=0)
+            print(f"B block ends after H's publication (median over launches; {int(r_[0])} blocks): min {r_[1]:.1f} p25 {r_[2]:.1f} "
+                  f"median {r_[3]:.1f} p75 {r_[4]:.1f} p95 {r_[5]:.1f} max {r_[6]:.1f} us")
     print(f"B launches {m_}: mean duration {np.mean(dur):.1f} us (first block start -> last block end); "
           f"idle between consecutive B: mean {np.mean(gap):.1f} median {np.median(gap):.1f} us")

@@ -18,8 +18,8 @@ std::atomic<long long> g_launches{0};
 // Site statistics: one warp per site.  The row (N calls = 2N bytes) is read as 16-byte vectors from
 // its first 16-byte boundary on (4 independent loads per lane in flight); the few calls before /
 // after the vector body go through the scalar path, so any N and any row offset work.  Per 32-bit
-// word (two calls) the counts come from exact zero-byte tests in plain integer logic (the __vcmp*4
-// intrinsics are emulated on this part and made the scan issue-bound); alleles >= 2 take a slow path.
+// vector whose alleles are all in {-1, 0, 1} the counts come from two dp4a dot products per word; other vectors
+// take exact zero-byte tests in plain integer logic (the __vcmp*4 intrinsics are emulated on this part).
 // ---------------------------------------------------------------------------------------------
 struct SiteAcc {
   unsigned seen[4];  // allele indices 0..127
@@ -73,7 +73,13 @@ __device__ __forceinline__ void mark_others(SiteAcc& s, uint32_t w, uint32_t oth
   }
 }
 
-__global__ void __launch_bounds__(256, 5) k_site_stats(const int8_t* __restrict__ gt, int64_t nvar, int64_t nsamp,
+// 16-byte loads in flight per lane (8 measured slower than 4: the scan is bound by the integer pipe, not by latency)
+#ifndef LOC_STAT_LOADS
+#define LOC_STAT_LOADS 4
+#endif
+constexpr int kStatLoads = LOC_STAT_LOADS;
+
+__global__ void __launch_bounds__(256, 4) k_site_stats(const int8_t* __restrict__ gt, int64_t nvar, int64_t nsamp,
                                                     int min_mac, int32_t* __restrict__ n_alleles,
                                                     int32_t* __restrict__ alt_count, int32_t* __restrict__ n_missing,
                                                     uint8_t* __restrict__ keep) {
@@ -92,28 +98,56 @@ __global__ void __launch_bounds__(256, 5) k_site_stats(const int8_t* __restrict_
     // vector body
     const uint4* vp = reinterpret_cast<const uint4*>(row + head);
     const int64_t nvec = (nbytes - head) >> 4;
+    // Fast path (ncu: the byte-wise zero tests made the scan integer-pipe bound -- 114 warp instructions per 512 bytes,
+    // math-pipe throttle the top stall -- at 0.50 of the HBM peak).  A vector whose 16 alleles are all in {-1, 0, 1}
+    // (every vector of a biallelic site) only feeds two dot products per word: S1 = sum a, S2 = sum a^2, from which
+    // #(a == 1) = (S2 + S1) / 2 and #(a == -1) = (S2 - S1) / 2; missing CALLS = missing alleles - calls with both
+    // alleles missing.  Anything else (allele >= 2, a negative value other than -1) sends the vector down the exact
+    // byte-by-byte path.
+    int s1 = 0, s2 = 0, both = 0, nfast = 0;
     WordAcc wa = {0u, 0u, 0, 0};
-    for (int64_t i = lane; i < nvec; i += 128) {
-      uint4 q[4];
+    for (int64_t i = lane; i < nvec; i += 32 * kStatLoads) {
+      uint4 q[kStatLoads];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < kStatLoads; ++u)
         if (i + 32 * u < nvec) q[u] = __ldcs(vp + i + 32 * u);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < kStatLoads; ++u)
         if (i + 32 * u < nvec) {
-          const uint32_t ox = acc_word(wa, q[u].x), oy = acc_word(wa, q[u].y);
-          const uint32_t oz = acc_word(wa, q[u].z), ow = acc_word(wa, q[u].w);
-          if (ox | oy | oz | ow) {
-            mark_others(s, q[u].x, ox);
-            mark_others(s, q[u].y, oy);
-            mark_others(s, q[u].z, oz);
-            mark_others(s, q[u].w, ow);
+          const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+          uint32_t odd = 0u;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t neg = w[e] & 0x80808080u;
+            const uint32_t m = (neg >> 7) * 0xFFu;             // 0xFF in every negative byte
+            odd |= (w[e] ^ m) & (m | 0xFEFEFEFEu);            // non-negative byte > 1, or negative byte != -1
+          }
+          if (odd == 0u) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              s1 = __dp4a((int)w[e], 0x01010101, s1);
+              s2 = __dp4a((int)w[e], (int)w[e], s2);
+              const uint32_t neg = w[e] & 0x80808080u;
+              both += __popc(neg & (neg >> 8) & 0x00800080u);
+            }
+            nfast += 16;
+          } else {
+            const uint32_t ox = acc_word(wa, w[0]), oy = acc_word(wa, w[1]);
+            const uint32_t oz = acc_word(wa, w[2]), ow = acc_word(wa, w[3]);
+            mark_others(s, w[0], ox);
+            mark_others(s, w[1], oy);
+            mark_others(s, w[2], oz);
+            mark_others(s, w[3], ow);
           }
         }
     }
-    s.seen[0] |= (wa.any0 ? 1u : 0u) | (wa.any1 ? 2u : 0u);
-    s.alt += wa.alt;
-    s.miss += wa.miss;
+    {
+      const int n1 = (s2 + s1) >> 1, nm = (s2 - s1) >> 1;  // alleles equal to 1 / to -1 in the fast vectors
+      const int n0 = nfast - n1 - nm;
+      s.seen[0] |= ((wa.any0 || n0 > 0) ? 1u : 0u) | ((wa.any1 || n1 > 0) ? 2u : 0u);
+      s.alt += wa.alt + n1;
+      s.miss += wa.miss + nm - both;
+    }
     // calls after the last whole vector (< 8)
     const int8_t* tail = row + head + nvec * 16;
     const int64_t tail_calls = (nbytes - head - nvec * 16) / 2;

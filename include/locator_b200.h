@@ -47,7 +47,8 @@ extern "C" {
 #endif
 
 #define LOC_ABI_VERSION 1
-#define LOC_MAX_BATCH 32
+#define LOC_MAX_BATCH 32        /* rows of one batch tile: steps of up to 32 rows run on the fused tensor-core kernels */
+#define LOC_MAX_BATCH_SIZE 256  /* largest --batch_size: steps of 33..256 rows go through the stack in 32-row chunks   */
 
 typedef struct loc_model loc_model;
 

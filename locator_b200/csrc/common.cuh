@@ -83,6 +83,7 @@ struct DevState {
   unsigned upd_cnt;  // blocks of small-layer update launches completed, cumulative
   unsigned dz_cnt[64];  // per Dense(width) layer i: CTAs of training hidden stacks that have written dz_i (and everything
                         // the layer's update needs), cumulative -- the update of layer i starts under the hidden stack
+  float step_sum;  // batches of more than 32 rows: sum of the per-row losses over the chunks of the step in flight
 };
 
 // Spin until *flag has reached `expect` (wrap-safe); gives up after ~2 s and raises *err instead of hanging the GPU.

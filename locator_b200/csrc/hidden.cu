@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
   const int Hc = THc ? THc : H / C, j0 = r * Hc;
   const int HcP = hid_row_pitch(Hc), SL = kMaxB * HcP;
   const int nb = a.src.nb;
+  const int loss_rows = a.loss_rows > 0 ? a.loss_rows : nb;  // steps of more than 32 rows come in 32-row chunks (bigbatch.cu)
+  const int mask_rows = a.mask_rows > 0 ? a.mask_rows : kMaxB;
   const int NS = a.n_slots;
   const SmallLayout sl{H, L};
   int dbg_n = 0;
@@ -291,9 +293,10 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
           bool kp;
           if (a.masks != nullptr) {
             const int64_t s = step_id < a.n_masks ? step_id : a.n_masks - 1;
-            kp = a.masks[(s * kMaxB + b) * H + j0 + jl] != 0;
+            kp = a.masks[(s * mask_rows + a.row_base + b) * H + j0 + jl] != 0;
           } else {
-            kp = philox_uniform((uint64_t)b * H + j0 + jl, kDropoutStreamBase + (uint32_t)step_id, a.seed) >= a.p_drop;
+            kp = philox_uniform((uint64_t)(a.row_base + b) * H + j0 + jl, kDropoutStreamBase + (uint32_t)step_id, a.seed) >=
+                 a.p_drop;
           }
           mult = kp ? keep_scale : 0.f;
           act *= mult;
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
       const float t0 = a.locs[2 * s_rows[b]], t1 = a.locs[2 * s_rows[b] + 1];
       const float e0 = v0 - t0, e1 = v1 - t1;
       d = sqrtf(e0 * e0 + e1 * e1);
-      const float den = d * (float)nb;  // no epsilon: NaN when the prediction hits the target, as in the reference
+      const float den = d * (float)loss_rows;  // no epsilon: NaN when the prediction hits the target, as in the reference
       g0 = e0 / den;
       g1 = e1 / den;
     }
@@ -427,7 +430,13 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
       if (a.training) {
         st->loss_total += mean * (float)nb;
         st->loss_count += (float)nb;
-        st->last_loss = mean;
+        if (a.loss_rows > 0) {  // chunk of a larger step: the step's loss is the mean over all of its rows
+          const float acc = ((a.chunk_flags & 1) ? st->step_sum : 0.f) + s;
+          st->step_sum = acc;
+          st->last_loss = acc / (float)loss_rows;
+        } else {
+          st->last_loss = mean;
+        }
         if (!isfinite(mean)) st->nonfinite = 1;
       } else {
         st->val_total += mean * (float)nb;
@@ -493,7 +502,7 @@ __global__ void __launch_bounds__(kHidThreads, 1) k_hidden(HidArgs a) {
   cluster_barrier();  // nobody exits while peers may still address its shared memory
   mark();
   // Optimizer bookkeeping for the update kernels of this step (Keras Adam: alpha from t >= 1).
-  if (r == 0 && tid == 0) {
+  if (r == 0 && tid == 0 && !(a.chunk_flags & 2)) {
     DevState* st = a.st;
     const int t = st->t + 1;
     st->t = t;

@@ -104,6 +104,8 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
   const int r = (int)cluster_rank(), rb = r >> 2, cj = r & 3;
   const int j0 = cj * kCW, b0 = rb * kRB;
   const int nb = a.src.nb;
+  const int loss_rows = a.loss_rows > 0 ? a.loss_rows : nb;  // steps of more than 32 rows come in 32-row chunks (bigbatch.cu)
+  const int mask_rows = a.mask_rows > 0 ? a.mask_rows : kMaxB;
   const SmallLayout sl{kH, L};
   if (tid == 0 && (r == 0 || r == kC - 1)) tl_mark(a.tl, r ? 19u : 3u, (unsigned)a.tl_id);
   int dbg_n = 0;
@@ -381,9 +383,10 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
     bool kp;
     if (a.masks != nullptr) {
       const int64_t s = step_id < a.n_masks ? step_id : a.n_masks - 1;
-      kp = a.masks[(s * kMaxB + b0 + b) * kH + j0 + jl] != 0;
+      kp = a.masks[(s * mask_rows + a.row_base + b0 + b) * kH + j0 + jl] != 0;
     } else {
-      kp = philox_uniform((uint64_t)(b0 + b) * kH + j0 + jl, kDropoutStreamBase + (uint32_t)step_id, a.seed) >= a.p_drop;
+      kp = philox_uniform((uint64_t)(a.row_base + b0 + b) * kH + j0 + jl, kDropoutStreamBase + (uint32_t)step_id, a.seed) >=
+           a.p_drop;
     }
     return kp ? keep_scale : 0.f;
   };
@@ -515,7 +518,7 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
       const float t0 = a.locs[2 * s_rows[b]], t1 = a.locs[2 * s_rows[b] + 1];
       const float e0 = v0 - t0, e1 = v1 - t1;
       d = sqrtf(e0 * e0 + e1 * e1);
-      const float den = d * (float)nb;  // no epsilon: NaN when the prediction hits the target, as in the reference
+      const float den = d * (float)loss_rows;  // no epsilon: NaN when the prediction hits the target, as in the reference
       g0 = e0 / den;
       g1 = e1 / den;
     }
@@ -585,8 +588,10 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
     // for hid_seq.  dz / activations of every CTA were written before the cluster barrier above; the optimizer
     // state they read is written here; the loss bookkeeping below is nobody's input and comes after.
     DevState* st = a.st;
-    st->t = s_t_next;
-    st->step_id = step_id + 1;
+    if (!(a.chunk_flags & 2)) {  // (a chunk of a larger step that is not its last leaves the step counters alone)
+      st->t = s_t_next;
+      st->step_id = step_id + 1;
+    }
     st->alpha = s_alpha_next;
     __threadfence();
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->hid_seq), "r"(a.hid_seq) : "memory");
@@ -605,7 +610,13 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
       if (a.training) {
         st->loss_total += mean * (float)nb;
         st->loss_count += (float)nb;
-        st->last_loss = mean;
+        if (a.loss_rows > 0) {  // chunk of a larger step: the step's loss is the mean over all of its rows
+          const float acc = ((a.chunk_flags & 1) ? st->step_sum : 0.f) + s;
+          st->step_sum = acc;
+          st->last_loss = acc / (float)loss_rows;
+        } else {
+          st->last_loss = mean;
+        }
         if (!isfinite(mean)) st->nonfinite = 1;
       } else if (a.val_slot != nullptr) {  // chunks of a wide pass run concurrently: summed in order afterwards
         a.val_slot[0] = mean * (float)nb;

@@ -308,6 +308,10 @@ static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated
   h.partial_stride = (int64_t)kMaxB * m->H;
   h.partial_row0 = 0;
   h.val_slot = nullptr;
+  h.loss_rows = 0;
+  h.row_base = 0;
+  h.mask_rows = 0;
+  h.chunk_flags = 0;
   if (m->tp != nullptr) {  // the shards' tiles of the latest exchange, summed in rank order by the kernel
     h.partials = tp_tiles(m->tp);
     h.n_partials = tp_world(m->tp);
@@ -390,6 +394,93 @@ static bool chain_capable(const loc_model* m) {
   return !off && m->use_tc && m->hid_tc && m->exchange == nullptr && m->tp == nullptr;
 }
 
+// One optimizer step of a model created with batch_size > 32 (bigbatch.cu): batch statistics over all rows of the
+// step, first-layer forward with those statistics (one wide pass over W1 on the tcgen05 path), the step's 32-row
+// chunks through the hidden stack, then one pass over W1 | m | v (dW1 over all rows + Adam) and the small-layer update
+// over the chunks.  Plain launches on one stream.
+static int train_step_big(loc_model* m, const RowSrc& src, int gated, cudaStream_t s) {
+  m->chain_open = 0;
+  m->span_perm = nullptr;
+  const int nb = src.nb, nc = (nb + kMaxB - 1) / kMaxB;
+  LOC_CHECK(nb >= 1 && nc <= m->cap_chunks && m->bb_mean != nullptr, "training step: more rows than the model's batch_size");
+  LOC_CHECK(m->exchange == nullptr && m->tp == nullptr, "sharded models train with batch_size <= 32");
+  BigArgs g;
+  g.K = m->K;
+  g.H = m->H;
+  g.L = m->L;
+  g.gated = gated;
+  g.tiled = m->use_tc;
+  g.nb = nb;
+  g.packed = m->train_packed;
+  g.row_words = m->train_row_words;
+  g.src = src;
+  g.gamma = m->gamma;
+  g.beta = m->beta;
+  g.mmean = m->mmean;
+  g.mvar = m->mvar;
+  g.bmean = m->bb_mean;
+  g.bvar = m->bb_var;
+  g.W1 = m->W1;
+  g.m_gamma = m->m_gamma;
+  g.v_gamma = m->v_gamma;
+  g.m_beta = m->m_beta;
+  g.v_beta = m->v_beta;
+  g.mW1 = m->mW1;
+  g.vW1 = m->vW1;
+  g.dzs = m->dzs;
+  g.acts = m->acts;
+  g.outs = m->outs;
+  g.small = m->small;
+  g.m_small = m->m_small;
+  g.v_small = m->v_small;
+  g.w_fs = m->w_fs;
+  g.w_bs = m->w_bs;
+  g.Hc = m->H / m->cluster;
+  g.slice_mode = m->hid_tc;
+  g.st = m->st;
+  if (bb_stats_launch(g, s)) return 1;
+  const bool wide = m->wide != nullptr && m->use_tc && m->hid_tc && getenv("LOC_NO_WIDE") == nullptr;
+  if (wide) {
+    L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 0, gated);
+    a.mmean = m->bb_mean;  // "inference" forward with the step's batch statistics
+    a.mvar = m->bb_var;
+    if (l1_forward_wide_tc(a, m->n_partials, nb, m->wide, s)) return 1;
+  }
+  const int64_t chunk_stride = (int64_t)m->L * kMaxB * m->H;
+  for (int c = 0; c < nc; ++c) {
+    RowSrc sc = src;
+    if (src.rows != nullptr)
+      sc.offset = src.offset + (int64_t)kMaxB * c;
+    else
+      sc.row0 = src.row0 + kMaxB * c;
+    sc.nb = nb - kMaxB * c < kMaxB ? nb - kMaxB * c : kMaxB;
+    if (!wide) {
+      L1Args a = l1_args(m, m->train_packed, m->train_row_words, sc, 0, gated);
+      a.mmean = m->bb_mean;
+      a.mvar = m->bb_var;
+      if (forward_l1(m, a, s)) return 1;
+    }
+    HidArgs h = hid_args(m, sc, 1, gated, m->train_locs, nullptr);
+    if (wide) {
+      h.partials = m->wide;
+      h.n_partials = m->n_partials;
+      h.partial_stride = (int64_t)nc * kMaxB * m->H;
+      h.partial_row0 = kMaxB * c;
+    }
+    h.acts = m->acts + c * chunk_stride;
+    h.dzs = m->dzs + c * chunk_stride;
+    h.outs = m->outs + c * 256;
+    h.loss_rows = nb;
+    h.row_base = kMaxB * c;
+    h.mask_rows = kMaxB * m->cap_chunks;
+    h.chunk_flags = (c > 0 ? 1 : 0) | (c < nc - 1 ? 2 : 0);
+    begin_training_hidden(m, h);
+    if (m->hid_tc ? hidden_tc_launch(h, s) : hidden_launch(h, m->cluster, s)) return 1;
+  }
+  if (bb_l1_backward_launch(g, s)) return 1;
+  return bb_hidden_update_launch(g, s);
+}
+
 // One optimizer step: 3-4 launches (stage_mask selects a subset for profiling / tests).
 // `next` (tcgen05 path): rows of the following step -- the backward kernel then also runs that step's
 // first-layer forward on the W1 chunks it has just updated (they are still in shared memory), so the
@@ -412,6 +503,10 @@ static bool chain_capable(const loc_model* m) {
 // step's critical path; what remains is H + B plus the flags' latency.
 static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s, int stage_mask = 15,
                       const RowSrc* next = nullptr, bool have_fwd = false) {
+  if (m->B > kMaxB) {
+    LOC_CHECK(stage_mask == 15, "single stages of a step are only available for batch_size <= 32");
+    return train_step_big(m, src, gated, s);
+  }
   L1Args a = l1_args(m, m->train_packed, m->train_row_words, src, 1, gated);
   if (next != nullptr && m->use_tc) {
     a.src_next = *next;
@@ -596,7 +691,7 @@ void free_model(loc_model* m) {
   float* ptrs[] = {m->W1, m->mW1, m->vW1, m->best_W1, m->gamma, m->beta, m->mmean, m->mvar, m->m_gamma, m->v_gamma,
                    m->m_beta, m->v_beta, m->best_gamma, m->best_beta, m->best_mmean, m->best_mvar, m->small, m->w_fs, m->w_bs,
                    m->m_small, m->v_small, m->best_small, m->partials, m->acts, m->dzs, m->outs, m->hist, m->wide,
-                   m->val_slots};
+                   m->val_slots, m->bb_mean, m->bb_var};
   for (float* p : ptrs)
     if (p) cudaFree(p);
   if (m->st) cudaFree(m->st);
@@ -629,12 +724,14 @@ cudaError_t dev_alloc(T** p, size_t bytes) {
   return dev_alloc(reinterpret_cast<void**>(p), bytes);
 }
 
-loc_model* pool_take(int dev, int64_t K, int width, int nlayers, int use_tc, int hid_tc, int max_epochs, bool want_dbg) {
+loc_model* pool_take(int dev, int64_t K, int width, int nlayers, int use_tc, int hid_tc, int max_epochs, bool want_dbg,
+                     int chunks) {
   std::lock_guard<std::mutex> lk(g_pool_mu);
   for (size_t i = 0; i < g_pool.size(); ++i) {
     loc_model* m = g_pool[i];
     if (m->dev == dev && m->H == width && m->L == nlayers && m->use_tc == use_tc && m->hid_tc == hid_tc &&
-        m->cap_K >= K && (double)K >= 0.6 * (double)m->cap_K && m->cap_epochs >= max_epochs && (m->dbg != nullptr) == want_dbg) {
+        m->cap_K >= K && (double)K >= 0.6 * (double)m->cap_K && m->cap_epochs >= max_epochs && (m->dbg != nullptr) == want_dbg &&
+        m->cap_chunks == chunks) {
       g_pool.erase(g_pool.begin() + (long)i);
       return m;
     }
@@ -670,8 +767,8 @@ static int zero_model(loc_model* m) {
   float* big[] = {m->W1, m->mW1, m->vW1, m->best_W1};
   for (float* p : big) LOC_CUDA(cudaMemsetAsync(p, 0, KH * sizeof(float), 0));  // padding rows stay zero under Adam
   LOC_CUDA(cudaMemsetAsync(m->st, 0, sizeof(DevState), 0));
-  LOC_CUDA(cudaMemsetAsync(m->dzs, 0, (size_t)m->L * kMaxB * m->H * sizeof(float), 0));
-  LOC_CUDA(cudaMemsetAsync(m->acts, 0, (size_t)m->L * kMaxB * m->H * sizeof(float), 0));
+  LOC_CUDA(cudaMemsetAsync(m->dzs, 0, (size_t)m->cap_chunks * m->L * kMaxB * m->H * sizeof(float), 0));
+  LOC_CUDA(cudaMemsetAsync(m->acts, 0, (size_t)m->cap_chunks * m->L * kMaxB * m->H * sizeof(float), 0));
   LOC_CUDA(cudaMemsetAsync(m->hist, 0, (size_t)m->max_epochs * 3 * sizeof(float), 0));
   if (m->dbg) LOC_CUDA(cudaMemsetAsync(m->dbg, 0, 16 * 256 * sizeof(long long), 0));
   LOC_CUDA(cudaStreamSynchronize(0));  // callers may continue on non-blocking streams
@@ -687,7 +784,8 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   LOC_CHECK(K > 0, "loc_model_create: K must be positive");
   LOC_CHECK(width >= 32 && width <= 1024 && width % 32 == 0, "loc_model_create: width must be a multiple of 32 in [32, 1024]");
   LOC_CHECK(nlayers >= 2 && nlayers <= 64, "loc_model_create: nlayers must be in [2, 64]");
-  LOC_CHECK(batch_size >= 1 && batch_size <= LOC_MAX_BATCH, "loc_model_create: batch_size must be in [1, 32]");
+  LOC_CHECK(batch_size >= 1 && batch_size <= LOC_MAX_BATCH_SIZE, "loc_model_create: batch_size must be in [1, 256]");
+  const int chunks = (batch_size + kMaxB - 1) / kMaxB;  // 32-row chunks of a step (bigbatch.cu for more than one)
   LOC_CHECK(dropout_prop >= 0.f && dropout_prop < 1.f, "loc_model_create: dropout_prop must be in [0, 1)");
   LOC_CHECK(max_epochs >= 1, "loc_model_create: max_epochs must be >= 1");
   int ndev = 0;
@@ -703,7 +801,7 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
     use_tc = (impl == nullptr || strcmp(impl, "simt") != 0) && l1_tc_supported(K, width);
   }
   const bool want_dbg = getenv("LOC_HID_TRACE") != nullptr;
-  if (loc_model* r = pool_limit() > 0 ? pool_take(dev, K, width, nlayers, use_tc, hid_tc, max_epochs, want_dbg) : nullptr) {
+  if (loc_model* r = pool_limit() > 0 ? pool_take(dev, K, width, nlayers, use_tc, hid_tc, max_epochs, want_dbg, chunks) : nullptr) {
     // a recycled handle: same buffers, new shape and settings, nothing bound
     set_geometry(r, K);
     r->B = batch_size;
@@ -754,6 +852,7 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   m->use_tc = use_tc;
   set_geometry(m, K);
   m->cap_K = K;
+  m->cap_chunks = chunks;
   m->cap_partials = m->use_tc ? l1_tc_partials(K) : m->n_partials;
   const int64_t KH = m->Kpad * width, ns = m->sl.total();
 #define LOC_ALLOC(ptr, bytes)                                 \
@@ -774,8 +873,12 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   LOC_ALLOC(m->w_fs, (size_t)(nlayers - 1) * width * width * sizeof(float));
   LOC_ALLOC(m->w_bs, (size_t)(nlayers - 1) * width * width * sizeof(float));
   LOC_ALLOC(m->partials, (size_t)m->cap_partials * kMaxB * width * sizeof(float));
-  LOC_ALLOC(m->acts, (size_t)nlayers * kMaxB * width * sizeof(float));
-  LOC_ALLOC(m->dzs, (size_t)nlayers * kMaxB * width * sizeof(float));
+  LOC_ALLOC(m->acts, (size_t)chunks * nlayers * kMaxB * width * sizeof(float));
+  LOC_ALLOC(m->dzs, (size_t)chunks * nlayers * kMaxB * width * sizeof(float));
+  if (chunks > 1) {
+    LOC_ALLOC(m->bb_mean, K * sizeof(float));
+    LOC_ALLOC(m->bb_var, K * sizeof(float));
+  }
   LOC_ALLOC(m->outs, 8 * 256 * sizeof(float));  // one [256] block per 32-row chunk of a wide pass
   LOC_ALLOC(m->val_slots, 16 * sizeof(float));
   if (m->use_tc && m->hid_tc) LOC_ALLOC(m->wide, (size_t)m->cap_partials * 256 * width * sizeof(float));
@@ -950,6 +1053,7 @@ int loc_model_get_adam(loc_model* m, int32_t idx, float* h_m, float* h_v, int64_
 int loc_model_set_shard(loc_model* m, int64_t k_offset, int64_t K_global) {
   LOC_CHECK(m != nullptr && k_offset >= 0 && K_global >= k_offset + m->K, "loc_model_set_shard: bad arguments");
   LOC_CHECK(m->use_tc && m->hid_tc, "loc_model_set_shard: sharded models need the tcgen05 kernels (width 256)");
+  LOC_CHECK(m->B <= kMaxB, "loc_model_set_shard: sharded models train with batch_size <= 32");
   m->k_offset = k_offset;
   m->K_global = K_global;
   return 0;
@@ -1035,6 +1139,7 @@ int loc_train_step(loc_model* m, const int32_t* d_rows, int32_t nb, void* stream
 int loc_debug_stage(loc_model* m, int32_t stage, const int32_t* d_rows, int32_t nb, void* stream) {
   LOC_CHECK(m != nullptr && m->train_packed != nullptr, "loc_debug_stage: no training data bound");
   LOC_CHECK(stage >= 0 && stage < 6 && d_rows != nullptr && nb >= 1 && nb <= m->B, "loc_debug_stage: bad arguments");
+  LOC_CHECK(m->B <= kMaxB, "loc_debug_stage: single stages are only available for batch_size <= 32");
   m->span_perm = nullptr;
   RowSrc src;
   src.rows = d_rows;
@@ -1073,6 +1178,7 @@ int loc_group_train_epochs(loc_model** models, int32_t n_models, const int32_t* 
               "loc_group_train_epochs: every model needs bound training / validation data and a batch order");
     LOC_CHECK(m->hid_tc && m->use_tc, "loc_group_train_epochs: grouped replicates need the tcgen05 kernels (width 256)");
     LOC_CHECK(m->exchange == nullptr && m->tp == nullptr, "loc_group_train_epochs: sharded models cannot be grouped");
+    LOC_CHECK(m->B <= kMaxB, "loc_group_train_epochs: grouped replicates train with batch_size <= 32");
     LOC_CHECK(m->L == m0->L && m->B == m0->B && m->n_train == m0->n_train,
               "loc_group_train_epochs: replicates of a group must share nlayers, batch size and training-set size");
   }
@@ -1260,7 +1366,7 @@ int64_t loc_debug_read(loc_model* m, int32_t which, float* h_dst, int64_t max_n,
 // after the span are.
 static int run_span(loc_model* m, const int32_t* perm, int64_t epoch_stride, int64_t step0, int64_t nsteps, int gated,
                     bool* have_fwd, cudaStream_t s) {
-  const bool fuse = m->use_tc && getenv("LOC_NO_FUSE") == nullptr;
+  const bool fuse = m->use_tc && m->B <= kMaxB && getenv("LOC_NO_FUSE") == nullptr;
   auto step_rows = [&](int64_t off) {
     RowSrc src;
     src.rows = perm;

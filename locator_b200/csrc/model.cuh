@@ -121,6 +121,11 @@ struct HidArgs {
                       // under the previous hidden stack, not directly in front of this launch)
   unsigned long long* tl;  // kernel timeline buffer (diagnostics) or nullptr
   int tl_id;
+  // Batches of more than 32 rows (bigbatch.cu): the step's rows go through the stack in 32-row chunks, one launch each.
+  int loss_rows;    // rows of the whole step (the loss is their mean): 0 = src.nb
+  int row_base;     // first row of this chunk inside the step (dropout stream / mask row)
+  int mask_rows;    // rows per step of the injected dropout masks: 0 = kMaxB
+  int chunk_flags;  // bit 0: not the step's first chunk (last_loss accumulates); bit 1: not its last (no optimizer bookkeeping)
   DevState* st;
 };
 
@@ -204,6 +209,33 @@ __device__ __forceinline__ float reduce_partial_tiles(const float* __restrict__ 
   return (sred[0][e] + sred[1][e]) + (sred[2][e] + sred[3][e]);
 }
 
+// Batches of 33..256 rows (bigbatch.cu): batch statistics of the whole step, first-layer backward + Adam over all of
+// its rows (fp32 CUDA cores, either W1 layout), small-layer update over the step's 32-row chunks.
+struct BigArgs {
+  int64_t K;
+  int H, L;
+  int gated;
+  int tiled;  // W1 / m / v in the tcgen05 layout (w1_tiled_index) instead of row-major
+  int nb;     // rows of the step
+  const uint32_t* packed;
+  int64_t row_words;
+  RowSrc src;
+  float *gamma, *beta, *mmean, *mvar;
+  float *bmean, *bvar;  // [K] batch statistics of the step in flight
+  float* W1;
+  float *m_gamma, *v_gamma, *m_beta, *v_beta, *mW1, *vW1;
+  const float* dzs;     // [chunks][L][kMaxB][H]: dZ1 of row b = dzs[(b / 32) * L * 32 * H + (b % 32) * H + j]
+  const float* acts;    // [chunks][L][kMaxB][H]
+  const float* outs;    // [chunks][256]
+  float *small, *m_small, *v_small, *w_fs, *w_bs;
+  int Hc, slice_mode;
+  DevState* st;
+};
+int bb_stats_launch(const BigArgs& a, cudaStream_t s);
+int bb_l1_backward_launch(const BigArgs& a, cudaStream_t s);
+int bb_hidden_update_launch(const BigArgs& a, cudaStream_t s);
+constexpr int kMaxChunks = LOC_MAX_BATCH_SIZE / LOC_MAX_BATCH;
+
 int tp_exchange(loc_tp* tp, const float* partials, int n_partials, cudaStream_t s);
 const float* tp_tiles(const loc_tp* tp);
 void tp_wait_info(const loc_tp* tp, const uint32_t** flags, int* count, uint32_t* seq, int** err);
@@ -240,6 +272,8 @@ struct loc_model {
   float *partials, *acts, *dzs, *outs, *hist, *pred_tmp;
   float* wide;       // wide inference: split-K partial tiles of up to 256 rows [n_partials][256][H] (tcgen05 path)
   float* val_slots;  // [8][2] per-chunk validation sums of a wide pass
+  float *bb_mean, *bb_var;  // [K] batch statistics of a step of more than 32 rows (bigbatch.cu); null for B <= 32
+  int cap_chunks;           // 32-row chunks the acts / dzs buffers hold
   long long* dbg;
   int tl_id;         // model number in the kernel timeline (diagnostics)
   cudaStream_t side;        // small-layer update runs here, beside the first-layer backward

@@ -119,9 +119,9 @@ def validate_args(ns):
     from ._cabi import lib  # noqa: F401  (fails loudly here when the CUDA library is missing)
 
     problems = []
-    if not 1 <= int(ns.batch_size) <= 32:
-        problems.append(f"--batch_size {ns.batch_size}: this build's kernels hold one batch of at most 32 rows per step "
-                        "(the reference's default, 32, is supported; larger batches are not)")
+    if not 1 <= int(ns.batch_size) <= 256:
+        problems.append(f"--batch_size {ns.batch_size}: must be in [1, 256] (up to 32, the reference's default, a step runs "
+                        "on the fused tensor-core kernels; 33..256 rows go through the stack in 32-row chunks)")
     if int(ns.width) < 32 or int(ns.width) > 1024 or int(ns.width) % 32:
         problems.append(f"--width {ns.width}: must be a multiple of 32 in [32, 1024] (256, the default, runs on the "
                         "tensor cores; other widths on the CUDA-core kernels)")

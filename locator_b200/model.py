@@ -196,13 +196,18 @@ class LocatorModel:
         return g
 
     def set_dropout_masks(self, keep):
-        """Test hook: keep[step, 32, width] uint8 masks replace the Philox stream (None restores it)."""
+        """Test hook: keep[step, 32, width] uint8 masks ([step, batch_size, width] for batch sizes above 32) replace the
+        Philox stream (None restores it)."""
         if keep is None:
             check(lib.loc_model_set_dropout_masks(self._h, None, 0), "loc_model_set_dropout_masks")
             self._keep.pop("masks", None)
             return
-        k = _as_dev(np.asarray(keep, dtype=np.uint8), torch.uint8)
-        assert k.dim() == 3 and k.shape[1] == 32 and k.shape[2] == self.width
+        keep = np.asarray(keep, dtype=np.uint8)
+        rows = 32 * max(1, -(-self.batch_size // 32))  # the library indexes [step][32 * chunks of a step][width]
+        assert keep.ndim == 3 and keep.shape[1] in (self.batch_size, rows) and keep.shape[2] == self.width
+        if keep.shape[1] != rows:
+            keep = np.concatenate([keep, np.ones((keep.shape[0], rows - keep.shape[1], self.width), np.uint8)], axis=1)
+        k = _as_dev(np.ascontiguousarray(keep), torch.uint8)
         check(lib.loc_model_set_dropout_masks(self._h, k.data_ptr(), k.shape[0]), "loc_model_set_dropout_masks")
         self._keep["masks"] = k
 

@@ -63,6 +63,9 @@ def _rows(path):
     ([], 70, 7),                                            # ragged last batch (57 train / 6 val)
     ([], 30, 4),                                            # training set smaller than one batch of 32
     (["--batch_size", "8"], 45, 5),                         # small batches, ragged
+    (["--batch_size", "64"], 200, 10),                      # steps of more than 32 rows (csrc/bigbatch.cu), ragged
+    (["--batch_size", "48", "--width", "64", "--nlayers", "4"], 120, 6),  # ... on the CUDA-core kernels
+    (["--batch_size", "256"], 100, 5),                      # batch larger than the training set
     (["--nlayers", "2"], 40, 4),                            # minimum depth: no hidden Dense before / after the dropout
     (["--width", "64", "--nlayers", "4"], 40, 4),           # CUDA-core kernels (width != 256)
     (["--dropout_prop", "0"], 40, 4),
@@ -119,11 +122,11 @@ def test_matrix_input_matches_vcf_input(L, tmp_path):
     assert open(o1 + "_predlocs.txt").read() == open(o2 + "_predlocs.txt").read()
 
 
-def test_batch_size_above_32_is_refused_loudly(L, tmp_path):
+def test_batch_size_above_256_is_refused_loudly(L, tmp_path):
     vcf, sd, na = _write_inputs(tmp_path, 40, 100, 4)
     with pytest.raises(SystemExit, match="batch_size"):  # validate_args: before any data is read
         L.main(["--vcf", vcf, "--sample_data", sd, "--out", str(tmp_path / "o"), "--seed", "1", "--max_epochs", "2",
-                "--batch_size", "64", "--keras_verbose", "0"])
+                "--batch_size", "512", "--keras_verbose", "0"])
 
 
 def test_replicate_drivers_on_degenerate_counts(L, tmp_path):

@@ -72,118 +72,242 @@ __device__ __forceinline__ const float* bb_dz1(const BigArgs& a, int b) {  // dZ
   return a.dzs + ((int64_t)(b >> 5) * a.L * kMaxB + (b & 31)) * a.H;
 }
 
-// blockDim = max(H, 64); thread j <-> output column j.  A block walks a contiguous range of 16-SNP words.
-__global__ void __launch_bounds__(1024) k_bb_l1_bwd(BigArgs a) {
+// ---------------------------------------------------------------------------------------------------------------
+// First-layer backward + Adam of a large step:  S[k][j] = sum_b (x[b][k] - mean_k) dZ1[b][j]  on the warp-level tensor
+// core path (mma.sync m16n8k8, tf32 operands, fp32 accumulate), with the operand model of the 32-row kernel
+// (l1_tc.cu): centred genotypes rounded to tf32 (exact whenever the row count is a power of two), dZ1 as hi + lo
+// tf32 parts (fp32-accurate).  The product is small next to the W1 | m | v stream (24 K H bytes, once per step); the
+// tensor cores are here to keep the instruction count of the product below that of Adam, not for their peak.
+//
+// Grid = (column groups of CW = 64 (or 32) columns) x (SNP ranges); 512 threads = 16 warps.  The block's slice of
+// dZ1 is split into hi / lo once and kept in shared memory in B-fragment order for the whole SNP range; per
+// iteration the block takes 32 packed words (16 SNPs each) of every row of the step into shared memory, and each
+// warp owns two of them (two 16-SNP m-tiles) x all CW columns: A fragments are expanded from the 2-bit genotypes
+// in registers, one 16-byte shared load per (8 rows, 8 columns) brings both parts of a B fragment.  The warp then
+// runs Adam on its 32 x CW block of W1 | m | v straight from the accumulator fragments (8-byte accesses, loads of
+// the next column tile in flight while the current one is updated), and leaves P_k = sum_j W1 S, Q_k = sum_j W1 c0
+// of its column group in global memory: BatchNorm gamma / beta need them over ALL columns (k_bb_gamma_beta).
+constexpr int kBbThreads = 512;
+constexpr int kBbWarps = kBbThreads / 32;
+constexpr int kBbWordsPerIter = 2 * kBbWarps;  // 32
+
+__device__ __forceinline__ uint32_t bb_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void bb_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// Keras Adam with the hardware's approximate root and quotient (~1 ulp each), as the 32-row kernel (l1_tc.cu)
+__device__ __forceinline__ void bb_adam(float& w, float& m, float& v, float g, float alpha) {
+  m = m + (g - m) * kAdam1mB1;
+  v = v + (g * g - v) * kAdam1mB2;
+  float rt;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(rt) : "f"(v));
+  w = w - __fdividef(m * alpha, rt + kAdamEps);
+}
+
+template <int CW, bool TILED>
+__global__ void __launch_bounds__(kBbThreads, 1) k_bb_l1_bwd(BigArgs a, float* __restrict__ pq_part) {
   if (a.gated && a.st->stopped) return;
-  extern __shared__ __align__(16) float bb_smem[];
-  __shared__ int64_t s_rows[LOC_MAX_BATCH_SIZE];
-  __shared__ float sc[kBbT][4];  // mean, inv, beta, rs
+  constexpr int NT = CW / 8;  // 8-column n-tiles of the column group
+  extern __shared__ __align__(16) uint8_t bb_raw[];
   const int H = a.H, nb = a.nb, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nwarps = blockDim.x >> 5;
-  const int Bp = (nb + 3) & ~3;
-  float* xs = bb_smem;           // [kBbT][Bp] centred genotypes (0 beyond nb)
-  float* pq = xs + kBbT * Bp;    // [nwarps][kBbT][2] per-warp partial P, Q
-  for (int b = tid; b < nb; b += blockDim.x) s_rows[b] = row_of(a.src, a.st, b);
+  const int g = lane >> 2, tig = lane & 3;
+  const int nk = (nb + 7) >> 3;       // k-steps of 8 rows
+  const int xw_pitch = nk * 8 + 1;    // words of one packed column in shared memory (odd: conflict-free transposing writes)
+  float4* dzf = reinterpret_cast<float4*>(bb_raw);                              // [nk][NT][32]: (hi b0, hi b1, lo b0, lo b1)
+  uint32_t* xw = reinterpret_cast<uint32_t*>(dzf + (size_t)nk * NT * 32);       // [32 words][xw_pitch]
+  float* scm = reinterpret_cast<float*>(xw + (size_t)kBbWordsPerIter * xw_pitch);  // [32 words][3][16]: mean, inv, beta
+  float* c0s = scm + kBbWordsPerIter * 3 * kBbT;                                // [CW] column sums of dZ1
+  __shared__ int64_t s_rows[LOC_MAX_BATCH_SIZE];
+  const int J0 = blockIdx.x * CW;
+  for (int b = tid; b < nb; b += kBbThreads) s_rows[b] = row_of(a.src, a.st, b);
+  for (int i = tid; i < nk * NT * 32; i += kBbThreads) {
+    const int ln = i & 31, n = (i >> 5) % NT, ks = (i >> 5) / NT;
+    const int r0 = ks * 8 + (ln & 3), r1 = r0 + 4, col = J0 + n * 8 + (ln >> 2);
+    const float v0 = r0 < nb ? __ldg(bb_dz1(a, r0) + col) : 0.f;
+    const float v1 = r1 < nb ? __ldg(bb_dz1(a, r1) + col) : 0.f;
+    const float h0 = __uint_as_float(bb_tf32(v0)), h1 = __uint_as_float(bb_tf32(v1));
+    dzf[i] = make_float4(h0, h1, __uint_as_float(bb_tf32(v0 - h0)), __uint_as_float(bb_tf32(v1 - h1)));
+  }
+  if (tid < CW) {
+    float s = 0.f;
+    for (int b = 0; b < nb; ++b) s += __ldg(bb_dz1(a, b) + J0 + tid);
+    c0s[tid] = s;
+  }
   const float alpha = a.st->alpha;
-  const bool col = tid < H;
-  float c0 = 0.f;
-  if (col)
-    for (int b = 0; b < nb; ++b) c0 += bb_dz1(a, b)[tid];
-  __syncthreads();
 
   const int64_t nwords = (a.K + kBbT - 1) / kBbT;
-  const int64_t c_begin = nwords * blockIdx.x / gridDim.x, c_end = nwords * (blockIdx.x + 1) / gridDim.x;
-  for (int64_t c = c_begin; c < c_end; ++c) {
-    const int64_t k0 = c * kBbT;
-    const int tmax = (int)((a.K - k0) < kBbT ? (a.K - k0) : kBbT);
-    if (tid < kBbT) {
-      float mean = 0.f, inv = 0.f, beta = 0.f, rs = 0.f;
-      if (tid < tmax) {
-        mean = a.bmean[k0 + tid];
-        rs = rsqrtf(a.bvar[k0 + tid] + kBnEps);
-        inv = rs * a.gamma[k0 + tid];
-        beta = a.beta[k0 + tid];
+  const int64_t c_begin = nwords * blockIdx.y / gridDim.y, c_end = nwords * (blockIdx.y + 1) / gridDim.y;
+  for (int64_t cg = c_begin; cg < c_end; cg += kBbWordsPerIter) {
+    __syncthreads();  // the previous iteration's words and scales have been consumed (first pass: set-up complete)
+    // packed words of this iteration: consecutive threads take consecutive words of one row (coalesced)
+    for (int i = tid; i < kBbWordsPerIter * nk * 8; i += kBbThreads) {
+      const int wi = i & (kBbWordsPerIter - 1), b = i / kBbWordsPerIter;
+      const int64_t cw = cg + wi;
+      xw[wi * xw_pitch + b] = (b < nb && cw < c_end) ? __ldg(a.packed + s_rows[b] * a.row_words + cw) : 0u;
+    }
+    {
+      const int wi = tid / kBbT, t = tid % kBbT;  // 512 threads = 32 words x 16 SNPs
+      const int64_t k = (cg + wi) * kBbT + t;
+      float mean = 0.f, inv = 0.f, beta = 0.f;
+      if (cg + wi < c_end && k < a.K) {
+        mean = a.bmean[k];
+        inv = rsqrtf(a.bvar[k] + kBnEps) * a.gamma[k];
+        beta = a.beta[k];
       }
-      sc[tid][0] = mean;
-      sc[tid][1] = inv;
-      sc[tid][2] = beta;
-      sc[tid][3] = rs;
+      scm[(wi * 3 + 0) * kBbT + t] = mean;
+      scm[(wi * 3 + 1) * kBbT + t] = inv;
+      scm[(wi * 3 + 2) * kBbT + t] = beta;
     }
     __syncthreads();
-    for (int b = tid; b < Bp; b += blockDim.x) {
-      const uint32_t x = b < nb ? __ldg(a.packed + s_rows[b] * a.row_words + c) : 0u;
+    const int w0i = 2 * warp;  // this warp's two words of the iteration
+    if (cg + w0i >= c_end) continue;  // (whole warps; the barriers above are reached by everybody)
+    float acc[2][NT][4];
 #pragma unroll
-      for (int t = 0; t < kBbT; ++t) xs[t * Bp + b] = (b < nb && t < tmax) ? (float)((x >> (2 * t)) & 3u) - sc[t][0] : 0.f;
-    }
-    __syncthreads();
-    float acc[kBbT];
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int t = 0; t < kBbT; ++t) acc[t] = 0.f;
-    if (col) {
-      for (int b0 = 0; b0 < Bp; b0 += 4) {
-        float d[4];
+      for (int n = 0; n < NT; ++n)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) d[e] = (b0 + e) < nb ? __ldg(bb_dz1(a, b0 + e) + tid) : 0.f;
+        for (int e = 0; e < 4; ++e) acc[mt][n][e] = 0.f;
+    {
+      float mean_lo[2], mean_hi[2];  // SNPs g and g + 8 of the two words
 #pragma unroll
-        for (int t = 0; t < kBbT; ++t) {
-          const float4 x4 = *reinterpret_cast<const float4*>(xs + t * Bp + b0);
-          acc[t] = fmaf(x4.x, d[0], acc[t]);
-          acc[t] = fmaf(x4.y, d[1], acc[t]);
-          acc[t] = fmaf(x4.z, d[2], acc[t]);
-          acc[t] = fmaf(x4.w, d[3], acc[t]);
+      for (int mt = 0; mt < 2; ++mt) {
+        mean_lo[mt] = scm[((w0i + mt) * 3 + 0) * kBbT + g];
+        mean_hi[mt] = scm[((w0i + mt) * 3 + 0) * kBbT + g + 8];
+      }
+      const uint32_t* xa = xw + (size_t)w0i * xw_pitch + tig;
+      const float4* bf = dzf + lane;
+#pragma unroll 2
+      for (int ks = 0; ks < nk; ++ks) {
+        uint32_t af[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint32_t x0 = xa[mt * xw_pitch + ks * 8] >> (2 * g);       // row 8 ks + tig
+          const uint32_t x1 = xa[mt * xw_pitch + ks * 8 + 4] >> (2 * g);   // row 8 ks + tig + 4
+          // 2-bit genotype -> float without a conversion instruction: 2^23 + x as bits, minus 2^23 (exact)
+          const float f00 = __uint_as_float(0x4B000000u | (x0 & 3u)) - 8388608.f;
+          const float f01 = __uint_as_float(0x4B000000u | ((x0 >> 16) & 3u)) - 8388608.f;
+          const float f10 = __uint_as_float(0x4B000000u | (x1 & 3u)) - 8388608.f;
+          const float f11 = __uint_as_float(0x4B000000u | ((x1 >> 16) & 3u)) - 8388608.f;
+          af[mt][0] = bb_tf32(f00 - mean_lo[mt]);  // (SNP g,     row tig)
+          af[mt][1] = bb_tf32(f01 - mean_hi[mt]);  // (SNP g + 8, row tig)
+          af[mt][2] = bb_tf32(f10 - mean_lo[mt]);  // (SNP g,     row tig + 4)
+          af[mt][3] = bb_tf32(f11 - mean_hi[mt]);  // (SNP g + 8, row tig + 4)
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const float4 b4 = bf[(ks * NT + n) * 32];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            bb_mma(acc[mt][n], af[mt], __float_as_uint(b4.x), __float_as_uint(b4.y));
+            bb_mma(acc[mt][n], af[mt], __float_as_uint(b4.z), __float_as_uint(b4.w));
+          }
         }
       }
     }
+    // ---- Adam on the warp's 32 SNPs x CW columns.  acc[mt][n] = {S(g, j), S(g, j+1), S(g+8, j), S(g+8, j+1)}, j = J0 + 8n + 2tig
 #pragma unroll
-    for (int t = 0; t < kBbT; ++t) {
-      float p = 0.f, q = 0.f;
-      if (col && t < tmax) {
-        const int64_t idx = a.tiled ? w1_tiled_index(k0 + t, tid) : (k0 + t) * H + tid;
-        float w = a.W1[idx], m = a.mW1[idx], v = a.vW1[idx];
-        const float S = acc[t];
-        const float g = sc[t][1] * S + sc[t][2] * c0;
-        p = w * S;
-        q = w * c0;
-        adam_update(w, m, v, g, alpha);
-        a.W1[idx] = w;
-        a.mW1[idx] = m;
-        a.vW1[idx] = v;
-      }
+    for (int mt = 0; mt < 2; ++mt) {
+      const int64_t cw = cg + w0i + mt;
+      if (cw >= c_end) break;
+      const int64_t k0 = cw * kBbT;
+      const bool on_lo = k0 + g < a.K, on_hi = k0 + g + 8 < a.K;
+      const float inv_lo = scm[((w0i + mt) * 3 + 1) * kBbT + g], inv_hi = scm[((w0i + mt) * 3 + 1) * kBbT + g + 8];
+      const float be_lo = scm[((w0i + mt) * 3 + 2) * kBbT + g], be_hi = scm[((w0i + mt) * 3 + 2) * kBbT + g + 8];
+      auto index = [&](int n, int hi) -> int64_t {
+        const int64_t k = k0 + g + 8 * hi;
+        const int j = J0 + 8 * n + 2 * tig;
+        return TILED ? w1_tiled_index(k, j) : k * H + j;
+      };
+      float2 cw_[2][3], nx_[2][3];  // current / next column tile: [SNP g | g + 8][W, m, v]
+      auto fetch = [&](int n, float2 (&d)[2][3]) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        p += __shfl_xor_sync(0xffffffffu, p, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
+        for (int hi = 0; hi < 2; ++hi) {
+          const bool on = hi ? on_hi : on_lo;
+          const int64_t idx = index(n, hi);
+          d[hi][0] = on ? *reinterpret_cast<const float2*>(a.W1 + idx) : make_float2(0.f, 0.f);
+          d[hi][1] = on ? *reinterpret_cast<const float2*>(a.mW1 + idx) : make_float2(0.f, 0.f);
+          d[hi][2] = on ? *reinterpret_cast<const float2*>(a.vW1 + idx) : make_float2(0.f, 0.f);
+        }
+      };
+      float P[2] = {0.f, 0.f}, Q[2] = {0.f, 0.f};
+      fetch(0, cw_);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        if (n + 1 < NT) fetch(n + 1, nx_);
+        const float2 c0 = *reinterpret_cast<const float2*>(c0s + 8 * n + 2 * tig);
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+          const float inv = hi ? inv_hi : inv_lo, be = hi ? be_hi : be_lo;
+          const float S0 = acc[mt][n][2 * hi], S1 = acc[mt][n][2 * hi + 1];
+          float2 w = cw_[hi][0], m = cw_[hi][1], v = cw_[hi][2];
+          P[hi] = fmaf(w.x, S0, fmaf(w.y, S1, P[hi]));
+          Q[hi] = fmaf(w.x, c0.x, fmaf(w.y, c0.y, Q[hi]));
+          bb_adam(w.x, m.x, v.x, inv * S0 + be * c0.x, alpha);
+          bb_adam(w.y, m.y, v.y, inv * S1 + be * c0.y, alpha);
+          if (hi ? on_hi : on_lo) {
+            const int64_t idx = index(n, hi);
+            *reinterpret_cast<float2*>(a.W1 + idx) = w;
+            *reinterpret_cast<float2*>(a.mW1 + idx) = m;
+            *reinterpret_cast<float2*>(a.vW1 + idx) = v;
+          }
+        }
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) cw_[hi][q] = nx_[hi][q];
       }
-      if (lane == 0) {
-        pq[(warp * kBbT + t) * 2] = p;
-        pq[(warp * kBbT + t) * 2 + 1] = q;
+      // sums over the warp's columns: the four lanes of a group hold different column pairs of the same SNPs
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+          P[hi] += __shfl_xor_sync(0xffffffffu, P[hi], o);
+          Q[hi] += __shfl_xor_sync(0xffffffffu, Q[hi], o);
+        }
+        const int64_t k = k0 + g + 8 * hi;
+        if (tig == 0 && k < a.K) {
+          pq_part[((int64_t)blockIdx.x * 2) * a.K + k] = P[hi];
+          pq_part[((int64_t)blockIdx.x * 2 + 1) * a.K + k] = Q[hi];
+        }
       }
     }
-    __syncthreads();
-    if (tid < tmax) {
-      float P = 0.f, Q = 0.f;
-      for (int w = 0; w < nwarps; ++w) {
-        P += pq[(w * kBbT + tid) * 2];
-        Q += pq[(w * kBbT + tid) * 2 + 1];
-      }
-      const int64_t k = k0 + tid;
-      const float dgamma = sc[tid][3] * P;  // exactly 0 for a SNP that is constant in the batch (centred genotypes)
-      const float dbeta = Q;
-      float gm = a.gamma[k], m = a.m_gamma[k], v = a.v_gamma[k];
-      adam_update(gm, m, v, dgamma, alpha);
-      a.gamma[k] = gm;
-      a.m_gamma[k] = m;
-      a.v_gamma[k] = v;
-      float bt = a.beta[k];
-      m = a.m_beta[k];
-      v = a.v_beta[k];
-      adam_update(bt, m, v, dbeta, alpha);
-      a.beta[k] = bt;
-      a.m_beta[k] = m;
-      a.v_beta[k] = v;
-    }
-    __syncthreads();
   }
+}
+
+// BatchNorm gamma / beta of a large step: P_k, Q_k summed over the column groups in order, then Adam.
+__global__ void __launch_bounds__(256) k_bb_gamma_beta(BigArgs a, const float* __restrict__ pq_part, int ncg) {
+  if (a.gated && a.st->stopped) return;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.K) return;
+  const float alpha = a.st->alpha;
+  float P = 0.f, Q = 0.f;
+  for (int g = 0; g < ncg; ++g) {
+    P += pq_part[((int64_t)g * 2) * a.K + k];
+    Q += pq_part[((int64_t)g * 2 + 1) * a.K + k];
+  }
+  const float rs = rsqrtf(a.bvar[k] + kBnEps);
+  const float dgamma = rs * P;  // exactly 0 for a SNP that is constant in the batch (centred genotypes: S = 0)
+  const float dbeta = Q;
+  float gm = a.gamma[k], mo = a.m_gamma[k], vo = a.v_gamma[k];
+  adam_update(gm, mo, vo, dgamma, alpha);
+  a.gamma[k] = gm;
+  a.m_gamma[k] = mo;
+  a.v_gamma[k] = vo;
+  float bt = a.beta[k];
+  mo = a.m_beta[k];
+  vo = a.v_beta[k];
+  adam_update(bt, mo, vo, dbeta, alpha);
+  a.beta[k] = bt;
+  a.m_beta[k] = mo;
+  a.v_beta[k] = vo;
 }
 
 // dW + Adam of the small layers over the chunks of the step.  Blocks [0, (L-1)*H/16): 16 input rows x H outputs of
@@ -285,6 +409,34 @@ __global__ void __launch_bounds__(1024) k_bb_hidden_update(BigArgs a) {
   }
 }
 
+// End of a large step whose chunks ran through the hidden stack side by side (one grouped launch): per-chunk loss sums
+// added in chunk order (same bits as chunk-by-chunk launches), then the optimizer bookkeeping of the step.
+__global__ void k_bb_step_end(DevState* st, const float* slots, int nc, int loss_rows, int gated) {
+  if (gated && st->stopped) return;
+  float acc = 0.f;
+  for (int c = 0; c < nc; ++c) {
+    const float s = slots[2 * c], n = slots[2 * c + 1];
+    const float mean = s / n;
+    st->loss_total += mean * n;
+    st->loss_count += n;
+    acc += s;
+    if (!isfinite(mean)) st->nonfinite = 1;
+  }
+  st->step_sum = acc;
+  st->last_loss = acc / (float)loss_rows;
+  const int t = st->t + 1;
+  st->t = t;
+  st->step_id = st->step_id + 1;
+  const float b1p = powf(kAdamB1, (float)t), b2p = powf(kAdamB2, (float)t);
+  st->alpha = st->lr * sqrtf(1.f - b2p) / (1.f - b1p);
+}
+
+int bb_step_end_launch(DevState* st, const float* slots, int nc, int loss_rows, int gated, cudaStream_t s) {
+  k_bb_step_end<<<1, 1, 0, s>>>(st, slots, nc, loss_rows, gated);
+  LOC_LAUNCHED();
+  return 0;
+}
+
 static int bb_sms() {
   static int n = 0;
   if (!n) {
@@ -304,18 +456,32 @@ int bb_stats_launch(const BigArgs& a, cudaStream_t s) {
   return 0;
 }
 
-int bb_l1_backward_launch(const BigArgs& a, cudaStream_t s) {
-  LOC_CHECK(a.H % 32 == 0 && a.H >= 32 && a.H <= 1024, "first layer (large batch): width must be a multiple of 32 in [32, 1024]");
-  const int threads = a.H < 64 ? 64 : a.H;
-  const int Bp = (a.nb + 3) & ~3;
-  const size_t smem = ((size_t)kBbT * Bp + (size_t)(threads / 32) * kBbT * 2) * sizeof(float);
-  const int64_t nwords = cdiv(a.K, kBbT);
-  const int per_sm = threads <= 256 ? 4 : (threads <= 512 ? 2 : 1);
-  int64_t blocks = (int64_t)bb_sms() * per_sm;
-  if (blocks > nwords) blocks = nwords;
-  k_bb_l1_bwd<<<(unsigned)blocks, threads, smem, s>>>(a);
+int64_t bb_pq_floats(int64_t K, int H) { return 2 * (int64_t)(H / (H % 64 == 0 ? 64 : 32)) * K; }
+
+template <int CW, bool TILED>
+static int bb_l1_backward_cw(const BigArgs& a, float* pq_part, cudaStream_t s) {
+  constexpr int NT = CW / 8;
+  const int ncg = a.H / CW;
+  const int nk = (a.nb + 7) / 8;
+  const size_t smem = (size_t)nk * NT * 32 * sizeof(float4) + (size_t)kBbWordsPerIter * (nk * 8 + 1) * sizeof(uint32_t) +
+                      (size_t)(kBbWordsPerIter * 3 * kBbT + CW) * sizeof(float);
+  LOC_CUDA(cudaFuncSetAttribute(k_bb_l1_bwd<CW, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t niter = cdiv(cdiv(a.K, kBbT), kBbWordsPerIter);
+  int64_t by = cdiv((int64_t)bb_sms(), ncg);  // one 512-thread block per SM
+  if (by > niter) by = niter;
+  if (by < 1) by = 1;
+  k_bb_l1_bwd<CW, TILED><<<dim3((unsigned)ncg, (unsigned)by), kBbThreads, smem, s>>>(a, pq_part);
+  LOC_LAUNCHED();
+  k_bb_gamma_beta<<<(unsigned)cdiv(a.K, 256), 256, 0, s>>>(a, pq_part, ncg);
   LOC_LAUNCHED();
   return 0;
+}
+
+int bb_l1_backward_launch(const BigArgs& a, float* pq_part, cudaStream_t s) {
+  LOC_CHECK(a.H % 32 == 0 && a.H >= 32 && a.H <= 1024, "first layer (large batch): width must be a multiple of 32 in [32, 1024]");
+  LOC_CHECK(pq_part != nullptr, "first layer (large batch): no scratch for the gamma / beta partial sums");
+  if (a.H % 64 == 0) return a.tiled ? bb_l1_backward_cw<64, true>(a, pq_part, s) : bb_l1_backward_cw<64, false>(a, pq_part, s);
+  return a.tiled ? bb_l1_backward_cw<32, true>(a, pq_part, s) : bb_l1_backward_cw<32, false>(a, pq_part, s);
 }
 
 int bb_hidden_update_launch(const BigArgs& a, cudaStream_t s) {

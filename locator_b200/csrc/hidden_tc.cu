@@ -607,7 +607,10 @@ __device__ __forceinline__ void hidden_tc_body(const HidArgs& a) {
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) {
       const float mean = s / (float)nb;
-      if (a.training) {
+      if (a.training && a.val_slot != nullptr) {  // chunks of a large step side by side: k_bb_step_end adds them in order
+        a.val_slot[0] = s;
+        a.val_slot[1] = (float)nb;
+      } else if (a.training) {
         st->loss_total += mean * (float)nb;
         st->loss_count += (float)nb;
         if (a.loss_rows > 0) {  // chunk of a larger step: the step's loss is the mean over all of its rows

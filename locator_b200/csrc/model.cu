@@ -447,6 +447,11 @@ static int train_step_big(loc_model* m, const RowSrc& src, int gated, cudaStream
     if (l1_forward_wide_tc(a, m->n_partials, nb, m->wide, s)) return 1;
   }
   const int64_t chunk_stride = (int64_t)m->L * kMaxB * m->H;
+  // tcgen05 hidden stack: the chunks run side by side, one cluster each (k_hidden_tc_group); their loss sums and the
+  // step's optimizer bookkeeping follow in k_bb_step_end.  LOC_BB_SERIAL=1 (tests): one launch per chunk.
+  const bool side_by_side = wide && nc > 1 && getenv("LOC_BB_SERIAL") == nullptr;
+  HidGroupArgs hg;
+  hg.n = nc;
   for (int c = 0; c < nc; ++c) {
     RowSrc sc = src;
     if (src.rows != nullptr)
@@ -475,9 +480,20 @@ static int train_step_big(loc_model* m, const RowSrc& src, int gated, cudaStream
     h.mask_rows = kMaxB * m->cap_chunks;
     h.chunk_flags = (c > 0 ? 1 : 0) | (c < nc - 1 ? 2 : 0);
     begin_training_hidden(m, h);
+    if (side_by_side) {
+      h.chunk_flags = 2;  // nobody bumps the step counters inside the launch
+      h.val_slot = m->val_slots + 2 * c;
+      hg.a[c] = h;
+      continue;
+    }
     if (m->hid_tc ? hidden_tc_launch(h, s) : hidden_launch(h, m->cluster, s)) return 1;
   }
-  if (bb_l1_backward_launch(g, s)) return 1;
+  if (side_by_side) {
+    for (int c = 0; c < nc; ++c) hg.a[c].hid_seq = m->h_hid_seq;  // published concurrently: the same (final) value
+    if (hidden_tc_group_launch(hg, s)) return 1;
+    if (bb_step_end_launch(m->st, m->val_slots, nc, nb, gated, s)) return 1;
+  }
+  if (bb_l1_backward_launch(g, m->bb_pq, s)) return 1;
   return bb_hidden_update_launch(g, s);
 }
 
@@ -691,7 +707,7 @@ void free_model(loc_model* m) {
   float* ptrs[] = {m->W1, m->mW1, m->vW1, m->best_W1, m->gamma, m->beta, m->mmean, m->mvar, m->m_gamma, m->v_gamma,
                    m->m_beta, m->v_beta, m->best_gamma, m->best_beta, m->best_mmean, m->best_mvar, m->small, m->w_fs, m->w_bs,
                    m->m_small, m->v_small, m->best_small, m->partials, m->acts, m->dzs, m->outs, m->hist, m->wide,
-                   m->val_slots, m->bb_mean, m->bb_var};
+                   m->val_slots, m->bb_mean, m->bb_var, m->bb_pq};
   for (float* p : ptrs)
     if (p) cudaFree(p);
   if (m->st) cudaFree(m->st);
@@ -878,6 +894,7 @@ int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers,
   if (chunks > 1) {
     LOC_ALLOC(m->bb_mean, K * sizeof(float));
     LOC_ALLOC(m->bb_var, K * sizeof(float));
+    LOC_ALLOC(m->bb_pq, (size_t)bb_pq_floats(K, width) * sizeof(float));
   }
   LOC_ALLOC(m->outs, 8 * 256 * sizeof(float));  // one [256] block per 32-row chunk of a wide pass
   LOC_ALLOC(m->val_slots, 16 * sizeof(float));

@@ -232,8 +232,10 @@ struct BigArgs {
   DevState* st;
 };
 int bb_stats_launch(const BigArgs& a, cudaStream_t s);
-int bb_l1_backward_launch(const BigArgs& a, cudaStream_t s);
+int bb_l1_backward_launch(const BigArgs& a, float* pq_part, cudaStream_t s);
+int64_t bb_pq_floats(int64_t K, int H);  // scratch of the backward: per column group partial sums for gamma / beta
 int bb_hidden_update_launch(const BigArgs& a, cudaStream_t s);
+int bb_step_end_launch(DevState* st, const float* slots, int nc, int loss_rows, int gated, cudaStream_t s);
 constexpr int kMaxChunks = LOC_MAX_BATCH_SIZE / LOC_MAX_BATCH;
 
 int tp_exchange(loc_tp* tp, const float* partials, int n_partials, cudaStream_t s);
@@ -273,6 +275,7 @@ struct loc_model {
   float* wide;       // wide inference: split-K partial tiles of up to 256 rows [n_partials][256][H] (tcgen05 path)
   float* val_slots;  // [8][2] per-chunk validation sums of a wide pass
   float *bb_mean, *bb_var;  // [K] batch statistics of a step of more than 32 rows (bigbatch.cu); null for B <= 32
+  float* bb_pq;             // [column groups][2][K] partial sums of that step's gamma / beta gradients
   int cap_chunks;           // 32-row chunks the acts / dzs buffers hold
   long long* dbg;
   int tl_id;         // model number in the kernel timeline (diagnostics)

@@ -119,6 +119,31 @@ def test_large_batch_philox_dropout_matches_oracle(M):
         np.testing.assert_allclose(m.state().last_loss, loss_ref, rtol=1e-4)
 
 
+def test_chunks_side_by_side_equal_chunks_in_sequence(M, monkeypatch):
+    """tcgen05 path: the chunks of a step share one grouped hidden-stack launch; LOC_BB_SERIAL=1 launches them one
+    after the other.  Same bits in every weight, loss and counter."""
+    K, H, L, B = 5000, 256, 10, 200
+    rng = np.random.default_rng(8)
+    x, y = _data(rng, 400, K)
+    perms = np.stack([rng.permutation(400) for _ in range(2)]).astype(np.int32)
+    outs = []
+    for serial in (False, True):
+        if serial:
+            monkeypatch.setenv("LOC_BB_SERIAL", "1")
+        else:
+            monkeypatch.delenv("LOC_BB_SERIAL", raising=False)
+        m = M.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=B, max_epochs=2, seed=21)
+        if m.impl != "tcgen05":
+            pytest.skip("needs the tcgen05 kernels")
+        h = m.fit(x[:360], y[:360], epochs=2, batch_size=B, validation_data=(x[360:], y[360:]), perms=perms)
+        st = m.state()
+        outs.append((m.get_weights(), h.history, st.t, st.last_loss))
+    (w_a, h_a, t_a, l_a), (w_b, h_b, t_b, l_b) = outs
+    assert t_a == t_b == 4 and l_a == l_b and h_a == h_b
+    for a, b in zip(w_a, w_b):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("K,H,L,B", [(1500, 64, 4, 64), (5830, 256, 10, 128)])
 def test_large_batch_fit_matches_oracle(M, K, H, L, B):
     """model.fit at a large batch size: epoch losses, validation losses, callbacks and the restored best weights."""

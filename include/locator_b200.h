@@ -168,8 +168,10 @@ int loc_np_legacy_permutation(uint32_t* mt_key, int32_t* mt_pos, int64_t n, int6
 /* ---------------- model (K3-K7) ---------------- */
 
 /* BN(K) -> Dense(width, elu) x nlayers (Dropout after the floor(nlayers/2)-th)
- * -> Dense(2) -> Dense(2); Adam(1e-3, .9, .999, 1e-7).  batch_size <= LOC_MAX_BATCH,
- * nlayers >= 2.  Allocates parameters, Adam state, best-weights snapshot and
+ * -> Dense(2) -> Dense(2); Adam(1e-3, .9, .999, 1e-7).  batch_size <= LOC_MAX_BATCH_SIZE
+ * (locator.py:69,371; steps of more than LOC_MAX_BATCH rows: batch statistics over the whole step,
+ * 32-row chunks through the hidden stack, one pass over W1 | m | v -- csrc/bigbatch.cu; such models
+ * cannot be grouped or sharded), nlayers >= 2.  Allocates parameters, Adam state, best-weights snapshot and
  * workspaces on the current device. */
 int loc_model_create(loc_model** out, int64_t K, int32_t width, int32_t nlayers, int32_t batch_size,
                      float dropout_prop, int32_t max_epochs);
@@ -252,7 +254,7 @@ int loc_model_bind_train(loc_model* m, const uint32_t* d_packed, int64_t n, int6
 int loc_model_bind_val(loc_model* m, const uint32_t* d_packed, int64_t n, int64_t row_words,
                        const float* d_locs);
 
-/* Test hook: use d_keep[step][LOC_MAX_BATCH][width] (uint8 0/1) as the dropout keep
+/* Test hook: use d_keep[step][32 * ceil(batch_size / 32)][width] (uint8 0/1) as the dropout keep
  * mask of optimizer step `step` instead of Philox; NULL restores Philox. */
 int loc_model_set_dropout_masks(loc_model* m, const uint8_t* d_keep, int64_t nsteps);
 

@@ -31,35 +31,45 @@ __device__ __forceinline__ void bb_moments(int n1, int n2, int nb, float& mean, 
   var = ((float)n0 * d0 * d0 + (float)n1 * d1 * d1 + (float)n2 * d2 * d2) / fn;
 }
 
-// One thread per packed word (16 SNPs): genotype counts over the step's rows -> batch statistics.
-__global__ void __launch_bounds__(128) k_bb_stats(BigArgs a) {
+// Genotype counts over the step's rows -> batch statistics.  256 threads = 32 packed words (16 SNPs each) x 8 row
+// slices; the slices' counts meet in shared memory (integer atomics: order-free), then one thread per SNP finishes.
+__global__ void __launch_bounds__(256) k_bb_stats(BigArgs a) {
   if (a.gated && a.st->stopped) return;
   __shared__ int64_t s_rows[LOC_MAX_BATCH_SIZE];
-  const int nb = a.nb;
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) s_rows[b] = row_of(a.src, a.st, b);
+  __shared__ unsigned cnt[32][2][16];
+  const int nb = a.nb, tid = threadIdx.x;
+  for (int b = tid; b < nb; b += blockDim.x) s_rows[b] = row_of(a.src, a.st, b);
+  for (int i = tid; i < 32 * 2 * 16; i += blockDim.x) (&cnt[0][0][0])[i] = 0u;
   __syncthreads();
-  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w * 16 >= a.K) return;
-  unsigned n1[16], n2[16];  // rows with one / two alternate alleles, per SNP of the word
+  const int wl = tid & 31, slice = tid >> 5;
+  const int64_t w = (int64_t)blockIdx.x * 32 + wl;
+  if (w * 16 < a.K) {
+    unsigned n1[16], n2[16];  // rows with one / two alternate alleles, per SNP of the word
 #pragma unroll
-  for (int t = 0; t < 16; ++t) n1[t] = n2[t] = 0u;
+    for (int t = 0; t < 16; ++t) n1[t] = n2[t] = 0u;
 #pragma unroll 4
-  for (int b = 0; b < nb; ++b) {
-    const uint32_t x = __ldg(a.packed + s_rows[b] * a.row_words + w);
-    const uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
-    const uint32_t is1 = lo & ~hi, is2 = hi & ~lo;
+    for (int b = slice; b < nb; b += 8) {
+      const uint32_t x = __ldg(a.packed + s_rows[b] * a.row_words + w);
+      const uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
+      const uint32_t is1 = lo & ~hi, is2 = hi & ~lo;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        n1[t] += (is1 >> (2 * t)) & 1u;
+        n2[t] += (is2 >> (2 * t)) & 1u;
+      }
+    }
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-      n1[t] += (is1 >> (2 * t)) & 1u;
-      n2[t] += (is2 >> (2 * t)) & 1u;
+      atomicAdd(&cnt[wl][0][t], n1[t]);
+      atomicAdd(&cnt[wl][1][t], n2[t]);
     }
   }
-#pragma unroll
-  for (int t = 0; t < 16; ++t) {
-    const int64_t k = w * 16 + t;
+  __syncthreads();
+  for (int i = tid; i < 32 * 16; i += blockDim.x) {
+    const int64_t k = ((int64_t)blockIdx.x * 32 + (i >> 4)) * 16 + (i & 15);
     if (k < a.K) {
       float mean, var;
-      bb_moments((int)n1[t], (int)n2[t], nb, mean, var);
+      bb_moments((int)cnt[i >> 4][0][i & 15], (int)cnt[i >> 4][1][i & 15], nb, mean, var);
       a.bmean[k] = mean;
       a.bvar[k] = var;
       a.mmean[k] = a.mmean[k] * kBnMom + mean * kBnOneMinusMom;
@@ -166,6 +176,29 @@ __global__ void __launch_bounds__(kBbThreads, 1) k_bb_l1_bwd(BigArgs a, float* _
       scm[(wi * 3 + 2) * kBbT + t] = beta;
     }
     __syncthreads();
+    {
+      // L2 prefetch of the iteration's rows of W1 | m | v (393 KB at CW = 64): they are needed after the products
+      // below, a few microseconds from now -- the DRAM reads run under the tensor-core phase instead of after it
+      constexpr int LPW = 16 * CW / 32;  // 128-byte lines per (word, array)
+      for (int i = tid; i < kBbWordsPerIter * 3 * LPW; i += kBbThreads) {
+        const int l = i % LPW, arr = (i / LPW) % 3, wi = i / (3 * LPW);
+        const int64_t cw = cg + wi;
+        if (cw >= c_end) continue;
+        const float* base = arr == 0 ? a.W1 : (arr == 1 ? a.mW1 : a.vW1);
+        int64_t off;
+        bool on;
+        if (TILED) {  // per (8 SNPs, 32 columns): 1 KB contiguous (rows are padded to a multiple of 64 SNPs)
+          const int per_chunk = 8, cc = (l / per_chunk) % (CW / 32), sb = l / (per_chunk * (CW / 32));
+          off = w1_tiled_index(cw * kBbT + 8 * sb, J0 + 32 * cc) + 32 * (l % per_chunk);
+          on = true;
+        } else {
+          const int t = l / (CW / 32), part = l % (CW / 32);
+          off = (cw * kBbT + t) * H + J0 + 32 * part;
+          on = cw * kBbT + t < a.K;
+        }
+        if (on) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+      }
+    }
     const int w0i = 2 * warp;  // this warp's two words of the iteration
     if (cg + w0i >= c_end) continue;  // (whole warps; the barriers above are reached by everybody)
     float acc[2][NT][4];
@@ -451,7 +484,7 @@ static int bb_sms() {
 int bb_stats_launch(const BigArgs& a, cudaStream_t s) {
   LOC_CHECK(a.nb >= 1 && a.nb <= LOC_MAX_BATCH_SIZE, "batch statistics: a step holds 1..256 rows");
   const int64_t nwords = cdiv(a.K, 16);
-  k_bb_stats<<<(unsigned)cdiv(nwords, 128), 128, 0, s>>>(a);
+  k_bb_stats<<<(unsigned)cdiv(nwords, 32), 256, 0, s>>>(a);
   LOC_LAUNCHED();
   return 0;
 }

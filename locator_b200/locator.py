@@ -67,7 +67,8 @@ def build_parser():
                         help="proportion of SNPs to remove for jacknife resampling. default: 0.05")
     parser.add_argument("--nboots", default=50, type=int, help="number of bootstrap replicates to run. default: 50")
     parser.add_argument("--batch_size", default=32, type=int,
-                        help="default: 32 (locator_b200: 1..32; larger batches are refused before any data is read)")
+                        help="default: 32 (locator_b200: 1..256; above 32 rows a step runs as 32-row chunks with batch statistics over the "
+                        "whole step)")
     parser.add_argument("--max_epochs", default=5000, type=int, help="default: 5000")
     parser.add_argument("--patience", type=int, default=100,
                         help="n epochs to run the optimizer after last improvement in validation loss. default: 100")

@@ -1,3 +1,5 @@
+"""GPU box, under ncu: two epochs of model.fit at BASELINE config[1] with --batch_size argv[1] (launch lists / captures of the
+large-batch kernels, csrc/bigbatch.cu)."""
 import numpy as np, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench

@@ -17,7 +17,8 @@ Printed JSON line: see the task contract.  Extra objects:
   roofline     the first-layer backward + Adam kernel (24*K*H bytes per launch) timed alone, CUDA events
   work_queue   BASELINE config[3] (--bootstrap --nboots 64 on the same matrix, 20 epochs per model) through
                the replicate work queue of locator_b200.replicates, the ranks of this job as its workers
-  replicate_group / tensor_parallel   side measurements (several models per GPU; one model over N GPUs)
+  replicate_group / tensor_parallel / large_batch   side measurements (several models per GPU; one model over N GPUs;
+               --batch_size 64 and 256)
   cpu_baseline the oracle (torch-CPU fp32 restatement of the Keras path; TF is not installable on this
                image) on a bounded number of steps
 """
@@ -303,6 +304,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=100)
     ap.add_argument("--no-tp", action="store_true", help="skip the sharded-model measurement at N > 1")
     ap.add_argument("--no-queue", action="store_true", help="skip the cfg4 work-queue measurement")
+    ap.add_argument("--no-large-batch", action="store_true", help="skip the --batch_size 64 / 256 side measurement")
     ap.add_argument("--e2e-epochs", type=int, default=20)
     ap.add_argument("--group", type=int, default=4, help="replicates per GPU for the group / work-queue measurements (0/1 = skip the group leg)")
     args = ap.parse_args()
@@ -530,6 +532,33 @@ def main():
                  "what": "loc_group_train_epochs, ring schedule: hidden stack of model g concurrent with the "
                          "first-layer backward + Adam of model g-1 (132 CTAs); 'lockstep' = the grouped-launch schedule"}
 
+    # ---- --batch_size above 32 (reference flag locator.py:69): whole epochs of model.fit's schedule ----
+    large_batch = None
+    if world == 1 and not args.no_large_batch:
+        large_batch = {"unit": "samples/s", "what": "loc_train_epochs at batch sizes above 32 (csrc/bigbatch.cu: batch statistics "
+                       "over the whole step, wide first-layer forward, 32-row chunks through the hidden stack, one "
+                       "backward + Adam pass over W1 | m | v); whole epochs incl. validation pass and callbacks"}
+        prng = np.random.default_rng(99)
+        for bsz in (64, 256):
+            bm = model.LocatorModel(K, width=H, nlayers=L, dropout_prop=0.25, batch_size=bsz, max_epochs=16, seed=700)
+            bm.bind_train(gtr, ytr)
+            bm.bind_val(xva, yva)
+            bm.set_schedule(patience=10 ** 6)
+            ne_b = 4
+            bm.train_epochs(np.stack([prng.permutation(ntr) for _ in range(2)]).astype(np.int32))
+            pb = np.stack([prng.permutation(ntr) for _ in range(ne_b)]).astype(np.int32)
+            torch.cuda.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            bm.train_epochs(pb)
+            b1.record()
+            torch.cuda.synchronize()
+            bms = b0.elapsed_time(b1)
+            large_batch[f"batch_{bsz}"] = {"value": ne_b * ntr / (bms / 1000.0), "epochs": ne_b,
+                                           "ms_per_step": bms / (ne_b * -(-ntr // bsz)),
+                                           "last_loss": float(bm.state().last_loss)}
+            del bm
+
     # ---- cfg4 through the replicate work queue (strong scaling over the ranks) ----
     work_queue = None
     if not args.no_queue and workload == "cfg2" and lib.loc_l1_impl().decode() == "tcgen05":
@@ -601,7 +630,7 @@ def main():
                    "epoch_ends_in_timed_region": epoch_ends,
                    "validation_pass_and_callbacks": "at every epoch end inside the timed region (%d here)" % epoch_ends},
         "clocks": clk.summary(), "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e,
-        "work_queue": work_queue, "replicate_group": group, "tensor_parallel": tp,
+        "work_queue": work_queue, "replicate_group": group, "tensor_parallel": tp, "large_batch": large_batch,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, dt = cpu_steps(xtr, ytr, xva, yva, args.cpu_steps, os.cpu_count() or 1)

@@ -308,6 +308,7 @@ static HidArgs hid_args(loc_model* m, const RowSrc& src, int training, int gated
   h.partial_stride = (int64_t)kMaxB * m->H;
   h.partial_row0 = 0;
   h.val_slot = nullptr;
+  h.skip_grid_wait = 0;
   h.loss_rows = 0;
   h.row_base = 0;
   h.mask_rows = 0;
@@ -537,6 +538,7 @@ static int train_step(loc_model* m, const RowSrc& src, int gated, cudaStream_t s
     begin_training_hidden(m, h);
     if (h_overlaps) h.wait_bwd = m->h_bwd_cnt;  // every CTA of the previous step's backward has signed off
     if (chain) h.wait_upd = m->h_upd_cnt;       // ... and every block of the small-layer updates so far
+    h.skip_grid_wait = h_overlaps && getenv("LOC_GDC_WAIT") == nullptr;
     if (m->hid_tc ? hidden_tc_launch(h, s, h_overlaps) : hidden_launch(h, m->cluster, s)) return 1;
   }
   if (chain) {

@@ -119,6 +119,7 @@ struct HidArgs {
   unsigned hid_seq;   // training launches: value to publish in DevState::hid_seq when everything is written
   unsigned wait_upd;  // != 0: wait for DevState::upd_cnt >= wait_upd before the small weights are read (the update ran
                       // under the previous hidden stack, not directly in front of this launch)
+  int skip_grid_wait;  // chained step: wait_bwd and wait_upd cover every producer, griddepcontrol.wait is left out
   unsigned long long* tl;  // kernel timeline buffer (diagnostics) or nullptr
   int tl_id;
   // Batches of more than 32 rows (bigbatch.cu): the step's rows go through the stack in 32-row chunks, one launch each.

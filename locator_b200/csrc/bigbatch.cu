@@ -15,6 +15,8 @@
 //
 // so W1 | m | v are still streamed once per optimizer step.  Keras semantics as restated in oracle/model_ref.py
 // (RefLocator.gradients / train_step); algebra of the first layer as in l1_simt.cu.
+#include <cuda_fp16.h>
+
 #include "model.cuh"
 #include "hidden_slices.cuh"
 
@@ -84,16 +86,19 @@ __device__ __forceinline__ const float* bb_dz1(const BigArgs& a, int b) {  // dZ
 
 // ---------------------------------------------------------------------------------------------------------------
 // First-layer backward + Adam of a large step:  S[k][j] = sum_b (x[b][k] - mean_k) dZ1[b][j]  on the warp-level tensor
-// core path (mma.sync m16n8k8, tf32 operands, fp32 accumulate), with the operand model of the 32-row kernel
-// (l1_tc.cu): centred genotypes rounded to tf32 (exact whenever the row count is a power of two), dZ1 as hi + lo
-// tf32 parts (fp32-accurate).  The product is small next to the W1 | m | v stream (24 K H bytes, once per step); the
-// tensor cores are here to keep the instruction count of the product below that of Adam, not for their peak.
+// core path (mma.sync m16n8k16, fp16 operands, fp32 accumulate) with the precision of the 32-row kernel (l1_tc.cu):
+// centred genotypes carry 11 significant bits (fp16 here, tf32 there: exact whenever the row count is a power of
+// two), dZ1 goes in as hi + lo parts (22 bits) -- of dZ1 scaled by a power of two per block so that its largest
+// entry sits just below fp16's maximum (the scale is taken out of S again, exactly).  Half the tensor instructions of
+// the tf32 shape (m16n8k8, hi + lo: 264 us at 256 rows, tensor-bound on this legacy path) for the same bits.  The
+// product is small next to the W1 | m | v stream (24 K H bytes, once per step); the tensor cores are here to keep the
+// instruction count of the product below that of Adam, not for their peak.
 //
 // Grid = (column groups of CW = 64 (or 32) columns) x (SNP ranges); 512 threads = 16 warps.  The block's slice of
 // dZ1 is split into hi / lo once and kept in shared memory in B-fragment order for the whole SNP range; per
 // iteration the block takes 32 packed words (16 SNPs each) of every row of the step into shared memory, and each
 // warp owns two of them (two 16-SNP m-tiles) x all CW columns: A fragments are expanded from the 2-bit genotypes
-// in registers, one 16-byte shared load per (8 rows, 8 columns) brings both parts of a B fragment.  The warp then
+// in registers, one 16-byte shared load per (16 rows, 8 columns) brings both parts of a B fragment.  The warp then
 // runs Adam on its 32 x CW block of W1 | m | v straight from the accumulator fragments (8-byte accesses, loads of
 // the next column tile in flight while the current one is updated), and leaves P_k = sum_j W1 S, Q_k = sum_j W1 c0
 // of its column group in global memory: BatchNorm gamma / beta need them over ALL columns (k_bb_gamma_beta).
@@ -101,14 +106,18 @@ constexpr int kBbThreads = 512;
 constexpr int kBbWarps = kBbThreads / 32;
 constexpr int kBbWordsPerIter = 2 * kBbWarps;  // 32
 
-__device__ __forceinline__ uint32_t bb_tf32(float x) {
+// two floats -> packed fp16 pair (round to nearest even); `lo` lands in the lower half
+__device__ __forceinline__ uint32_t bb_h2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+__device__ __forceinline__ float bb_h_round(float x) {  // x rounded to fp16, as a float
+  return __half2float(__float2half_rn(x));
 }
 __device__ __forceinline__ void bb_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -128,22 +137,39 @@ __global__ void __launch_bounds__(kBbThreads, 1) k_bb_l1_bwd(BigArgs a, float* _
   extern __shared__ __align__(16) uint8_t bb_raw[];
   const int H = a.H, nb = a.nb, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tig = lane & 3;
-  const int nk = (nb + 7) >> 3;       // k-steps of 8 rows
-  const int xw_pitch = nk * 8 + 1;    // words of one packed column in shared memory (odd: conflict-free transposing writes)
-  float4* dzf = reinterpret_cast<float4*>(bb_raw);                              // [nk][NT][32]: (hi b0, hi b1, lo b0, lo b1)
+  const int nk = (nb + 15) >> 4;      // k-steps of 16 rows
+  const int xw_pitch = nk * 16 + 1;   // words of one packed column in shared memory (odd: conflict-free transposing writes)
+  uint4* dzf = reinterpret_cast<uint4*>(bb_raw);                                // [nk][NT][32]: (hi b0, hi b1, lo b0, lo b1), fp16 pairs
   uint32_t* xw = reinterpret_cast<uint32_t*>(dzf + (size_t)nk * NT * 32);       // [32 words][xw_pitch]
   float* scm = reinterpret_cast<float*>(xw + (size_t)kBbWordsPerIter * xw_pitch);  // [32 words][3][16]: mean, inv, beta
   float* c0s = scm + kBbWordsPerIter * 3 * kBbT;                                // [CW] column sums of dZ1
   __shared__ int64_t s_rows[LOC_MAX_BATCH_SIZE];
+  __shared__ float s_red[kBbWarps];
   const int J0 = blockIdx.x * CW;
   for (int b = tid; b < nb; b += kBbThreads) s_rows[b] = row_of(a.src, a.st, b);
+  // power-of-two scale of the block's slice of dZ1: largest entry into [2^14, 2^15)
+  float amax = 0.f;
+  for (int i = tid; i < nb * CW; i += kBbThreads) amax = fmaxf(amax, fabsf(__ldg(bb_dz1(a, i / CW) + J0 + i % CW)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (lane == 0) s_red[warp] = amax;
+  __syncthreads();
+  amax = 0.f;
+  for (int w = 0; w < kBbWarps; ++w) amax = fmaxf(amax, s_red[w]);
+  const bool scalable = amax > 0.f && amax < 3.0e38f;  // (zeros, inf / nan: no scaling; non-finite values propagate as they are)
+  const int sexp = scalable ? 14 - ilogbf(amax) : 0;
+  const float dscale = scalbnf(1.f, sexp), dunscale = scalbnf(1.f, -sexp);
   for (int i = tid; i < nk * NT * 32; i += kBbThreads) {
     const int ln = i & 31, n = (i >> 5) % NT, ks = (i >> 5) / NT;
-    const int r0 = ks * 8 + (ln & 3), r1 = r0 + 4, col = J0 + n * 8 + (ln >> 2);
-    const float v0 = r0 < nb ? __ldg(bb_dz1(a, r0) + col) : 0.f;
-    const float v1 = r1 < nb ? __ldg(bb_dz1(a, r1) + col) : 0.f;
-    const float h0 = __uint_as_float(bb_tf32(v0)), h1 = __uint_as_float(bb_tf32(v1));
-    dzf[i] = make_float4(h0, h1, __uint_as_float(bb_tf32(v0 - h0)), __uint_as_float(bb_tf32(v1 - h1)));
+    const int r0 = ks * 16 + 2 * (ln & 3), col = J0 + n * 8 + (ln >> 2);
+    float v[4], h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = r0 + (e & 1) + 8 * (e >> 1);  // rows 2 tig, 2 tig + 1 (b0), 2 tig + 8, 2 tig + 9 (b1)
+      v[e] = r < nb ? __ldg(bb_dz1(a, r) + col) * dscale : 0.f;
+      h[e] = bb_h_round(v[e]);
+    }
+    dzf[i] = make_uint4(bb_h2(h[0], h[1]), bb_h2(h[2], h[3]), bb_h2(v[0] - h[0], v[1] - h[1]), bb_h2(v[2] - h[2], v[3] - h[3]));
   }
   if (tid < CW) {
     float s = 0.f;
@@ -157,7 +183,7 @@ __global__ void __launch_bounds__(kBbThreads, 1) k_bb_l1_bwd(BigArgs a, float* _
   for (int64_t cg = c_begin; cg < c_end; cg += kBbWordsPerIter) {
     __syncthreads();  // the previous iteration's words and scales have been consumed (first pass: set-up complete)
     // packed words of this iteration: consecutive threads take consecutive words of one row (coalesced)
-    for (int i = tid; i < kBbWordsPerIter * nk * 8; i += kBbThreads) {
+    for (int i = tid; i < kBbWordsPerIter * nk * 16; i += kBbThreads) {
       const int wi = i & (kBbWordsPerIter - 1), b = i / kBbWordsPerIter;
       const int64_t cw = cg + wi;
       xw[wi * xw_pitch + b] = (b < nb && cw < c_end) ? __ldg(a.packed + s_rows[b] * a.row_words + cw) : 0u;
@@ -215,36 +241,40 @@ __global__ void __launch_bounds__(kBbThreads, 1) k_bb_l1_bwd(BigArgs a, float* _
         mean_lo[mt] = scm[((w0i + mt) * 3 + 0) * kBbT + g];
         mean_hi[mt] = scm[((w0i + mt) * 3 + 0) * kBbT + g + 8];
       }
-      const uint32_t* xa = xw + (size_t)w0i * xw_pitch + tig;
-      const float4* bf = dzf + lane;
+      const uint32_t* xa = xw + (size_t)w0i * xw_pitch + 2 * tig;
+      const uint4* bf = dzf + lane;
+      // 2-bit genotype -> float without a conversion instruction: 2^23 + x as bits, minus 2^23 (exact), then centred
+      auto cen = [](uint32_t x2, float mean) { return (__uint_as_float(0x4B000000u | (x2 & 3u)) - 8388608.f) - mean; };
 #pragma unroll 2
       for (int ks = 0; ks < nk; ++ks) {
         uint32_t af[2][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-          const uint32_t x0 = xa[mt * xw_pitch + ks * 8] >> (2 * g);       // row 8 ks + tig
-          const uint32_t x1 = xa[mt * xw_pitch + ks * 8 + 4] >> (2 * g);   // row 8 ks + tig + 4
-          // 2-bit genotype -> float without a conversion instruction: 2^23 + x as bits, minus 2^23 (exact)
-          const float f00 = __uint_as_float(0x4B000000u | (x0 & 3u)) - 8388608.f;
-          const float f01 = __uint_as_float(0x4B000000u | ((x0 >> 16) & 3u)) - 8388608.f;
-          const float f10 = __uint_as_float(0x4B000000u | (x1 & 3u)) - 8388608.f;
-          const float f11 = __uint_as_float(0x4B000000u | ((x1 >> 16) & 3u)) - 8388608.f;
-          af[mt][0] = bb_tf32(f00 - mean_lo[mt]);  // (SNP g,     row tig)
-          af[mt][1] = bb_tf32(f01 - mean_hi[mt]);  // (SNP g + 8, row tig)
-          af[mt][2] = bb_tf32(f10 - mean_lo[mt]);  // (SNP g,     row tig + 4)
-          af[mt][3] = bb_tf32(f11 - mean_hi[mt]);  // (SNP g + 8, row tig + 4)
+          const uint32_t* xr = xa + mt * xw_pitch + ks * 16;
+          const uint32_t x0 = xr[0] >> (2 * g), x1 = xr[1] >> (2 * g);  // rows 16 ks + 2 tig, + 1
+          const uint32_t x8 = xr[8] >> (2 * g), x9 = xr[9] >> (2 * g);  // rows 16 ks + 2 tig + 8, + 9
+          af[mt][0] = bb_h2(cen(x0, mean_lo[mt]), cen(x1, mean_lo[mt]));              // (SNP g,     rows 2 tig, 2 tig + 1)
+          af[mt][1] = bb_h2(cen(x0 >> 16, mean_hi[mt]), cen(x1 >> 16, mean_hi[mt]));  // (SNP g + 8, rows 2 tig, 2 tig + 1)
+          af[mt][2] = bb_h2(cen(x8, mean_lo[mt]), cen(x9, mean_lo[mt]));              // (SNP g,     rows 2 tig + 8, + 9)
+          af[mt][3] = bb_h2(cen(x8 >> 16, mean_hi[mt]), cen(x9 >> 16, mean_hi[mt]));  // (SNP g + 8, rows 2 tig + 8, + 9)
         }
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
-          const float4 b4 = bf[(ks * NT + n) * 32];
+          const uint4 b4 = bf[(ks * NT + n) * 32];
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
-            bb_mma(acc[mt][n], af[mt], __float_as_uint(b4.x), __float_as_uint(b4.y));
-            bb_mma(acc[mt][n], af[mt], __float_as_uint(b4.z), __float_as_uint(b4.w));
+            bb_mma(acc[mt][n], af[mt], b4.x, b4.y);  // hi part of dZ1
+            bb_mma(acc[mt][n], af[mt], b4.z, b4.w);  // lo part
           }
         }
       }
     }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][n][e] *= dunscale;
     // ---- Adam on the warp's 32 SNPs x CW columns.  acc[mt][n] = {S(g, j), S(g, j+1), S(g+8, j), S(g+8, j+1)}, j = J0 + 8n + 2tig
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -495,8 +525,8 @@ template <int CW, bool TILED>
 static int bb_l1_backward_cw(const BigArgs& a, float* pq_part, cudaStream_t s) {
   constexpr int NT = CW / 8;
   const int ncg = a.H / CW;
-  const int nk = (a.nb + 7) / 8;
-  const size_t smem = (size_t)nk * NT * 32 * sizeof(float4) + (size_t)kBbWordsPerIter * (nk * 8 + 1) * sizeof(uint32_t) +
+  const int nk = (a.nb + 15) / 16;
+  const size_t smem = (size_t)nk * NT * 32 * sizeof(uint4) + (size_t)kBbWordsPerIter * (nk * 16 + 1) * sizeof(uint32_t) +
                       (size_t)(kBbWordsPerIter * 3 * kBbT + CW) * sizeof(float);
   LOC_CUDA(cudaFuncSetAttribute(k_bb_l1_bwd<CW, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t niter = cdiv(cdiv(a.K, kBbT), kBbWordsPerIter);

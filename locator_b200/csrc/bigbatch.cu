@@ -97,11 +97,12 @@ __device__ __forceinline__ const float* bb_dz1(const BigArgs& a, int b) {  // dZ
 // Grid = (column groups of CW = 64 (or 32) columns) x (SNP ranges); 512 threads = 16 warps.  The block's slice of
 // dZ1 is split into hi / lo once and kept in shared memory in B-fragment order for the whole SNP range; per
 // iteration the block takes 32 packed words (16 SNPs each) of every row of the step into shared memory, and each
-// warp owns two of them (two 16-SNP m-tiles) x all CW columns: A fragments are expanded from the 2-bit genotypes
-// in registers, one 16-byte shared load per (16 rows, 8 columns) brings both parts of a B fragment.  The warp then
-// runs Adam on its 32 x CW block of W1 | m | v straight from the accumulator fragments (8-byte accesses, loads of
-// the next column tile in flight while the current one is updated), and leaves P_k = sum_j W1 S, Q_k = sum_j W1 c0
-// of its column group in global memory: BatchNorm gamma / beta need them over ALL columns (k_bb_gamma_beta).
+// warp owns two of them, one after the other (a 16-SNP m-tile x all CW columns): A fragments are expanded from the
+// 2-bit genotypes in registers, one 16-byte shared load per (16 rows, 8 columns) brings both parts of a B fragment.
+// The warp then runs Adam on its 16 x CW block of W1 | m | v straight from the accumulator fragments (8-byte
+// accesses; two column tiles = 12 loads per thread stay in flight, the first two requested before the products), and
+// leaves P_k = sum_j W1 S, Q_k = sum_j W1 c0 of its column group in global memory: BatchNorm gamma / beta need them
+// over ALL columns (k_bb_gamma_beta).
 constexpr int kBbThreads = 512;
 constexpr int kBbWarps = kBbThreads / 32;
 constexpr int kBbWordsPerIter = 2 * kBbWarps;  // 32
@@ -121,6 +122,15 @@ __device__ __forceinline__ void bb_mma(float (&d)[4], const uint32_t (&a)[4], ui
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// Which column of the block's column group sits at accumulator column c (0..7) of n-tile n.  Not n * 8 + c: inside
+// every 32-column chunk the four n-tiles are interleaved so that the thread that owns accumulator columns 2 tig,
+// 2 tig + 1 of all four owns columns 4 tig .. 4 tig + 3 and 16 + 4 tig .. 16 + 4 tig + 3 of the chunk: its share of a
+// row of W1 | m | v is two 16-byte accesses, and a warp instruction covers whole 32-byte sectors (8 rows x 64 bytes)
+// instead of 8 rows x four quarter-used sectors.
+__host__ __device__ __forceinline__ int bb_phys_col(int n, int c) {
+  return 32 * (n >> 2) + 16 * ((n & 3) >> 1) + 4 * (c >> 1) + 2 * (n & 1) + (c & 1);
+}
+
 // Keras Adam with the hardware's approximate root and quotient (~1 ulp each), as the 32-row kernel (l1_tc.cu)
 __device__ __forceinline__ void bb_adam(float& w, float& m, float& v, float g, float alpha) {
   m = m + (g - m) * kAdam1mB1;
@@ -140,9 +150,9 @@ __global__ void __launch_bounds__(kBbThreads, 1) k_bb_l1_bwd(BigArgs a, float* _
   const int nk = (nb + 15) >> 4;      // k-steps of 16 rows
   const int xw_pitch = nk * 16 + 1;   // words of one packed column in shared memory (odd: conflict-free transposing writes)
   uint4* dzf = reinterpret_cast<uint4*>(bb_raw);                                // [nk][NT][32]: (hi b0, hi b1, lo b0, lo b1), fp16 pairs
-  uint32_t* xw = reinterpret_cast<uint32_t*>(dzf + (size_t)nk * NT * 32);       // [32 words][xw_pitch]
-  float* scm = reinterpret_cast<float*>(xw + (size_t)kBbWordsPerIter * xw_pitch);  // [32 words][3][16]: mean, inv, beta
-  float* c0s = scm + kBbWordsPerIter * 3 * kBbT;                                // [CW] column sums of dZ1
+  uint32_t* xw0 = reinterpret_cast<uint32_t*>(dzf + (size_t)nk * NT * 32);      // [2 buffers][32 words][xw_pitch]
+  float* raw0 = reinterpret_cast<float*>(xw0 + (size_t)2 * kBbWordsPerIter * xw_pitch);  // [2 buffers][mean, var, gamma, beta][512 SNPs]
+  float* c0s = raw0 + 2 * 4 * kBbThreads;                                        // [CW] column sums of dZ1
   __shared__ int64_t s_rows[LOC_MAX_BATCH_SIZE];
   __shared__ float s_red[kBbWarps];
   const int J0 = blockIdx.x * CW;
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(kBbThreads, 1) k_bb_l1_bwd(BigArgs a, float* _
   const float dscale = scalbnf(1.f, sexp), dunscale = scalbnf(1.f, -sexp);
   for (int i = tid; i < nk * NT * 32; i += kBbThreads) {
     const int ln = i & 31, n = (i >> 5) % NT, ks = (i >> 5) / NT;
-    const int r0 = ks * 16 + 2 * (ln & 3), col = J0 + n * 8 + (ln >> 2);
+    const int r0 = ks * 16 + 2 * (ln & 3), col = J0 + bb_phys_col(n, ln >> 2);
     float v[4], h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -180,28 +190,43 @@ __global__ void __launch_bounds__(kBbThreads, 1) k_bb_l1_bwd(BigArgs a, float* _
 
   const int64_t nwords = (a.K + kBbT - 1) / kBbT;
   const int64_t c_begin = nwords * blockIdx.y / gridDim.y, c_end = nwords * (blockIdx.y + 1) / gridDim.y;
-  for (int64_t cg = c_begin; cg < c_end; cg += kBbWordsPerIter) {
-    __syncthreads();  // the previous iteration's words and scales have been consumed (first pass: set-up complete)
-    // packed words of this iteration: consecutive threads take consecutive words of one row (coalesced)
+  // The iteration's inputs -- 32 packed words of every row, batch statistics / gamma / beta of its 512 SNPs -- are
+  // requested one iteration ahead with cp.async into the other half of a double buffer (no registers, no stall: the
+  // first version loaded them at the top of the iteration and the whole block sat through a DRAM round trip there,
+  // 30 % of the kernel's stall samples at 64 rows).  Consecutive threads take consecutive words of one row (coalesced).
+  auto stage = [&](int64_t cgn, int bi) {
+    uint32_t* xw = xw0 + (size_t)bi * kBbWordsPerIter * xw_pitch;
     for (int i = tid; i < kBbWordsPerIter * nk * 16; i += kBbThreads) {
       const int wi = i & (kBbWordsPerIter - 1), b = i / kBbWordsPerIter;
-      const int64_t cw = cg + wi;
-      xw[wi * xw_pitch + b] = (b < nb && cw < c_end) ? __ldg(a.packed + s_rows[b] * a.row_words + cw) : 0u;
+      const bool ok = b < nb && cgn + wi < c_end;
+      const uint32_t* src = ok ? a.packed + s_rows[b] * a.row_words + cgn + wi : a.packed;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(xw + wi * xw_pitch + b)),
+                   "l"(src), "r"(ok ? 4 : 0)
+                   : "memory");  // (size 0: zero fill)
     }
-    {
-      const int wi = tid / kBbT, t = tid % kBbT;  // 512 threads = 32 words x 16 SNPs
-      const int64_t k = (cg + wi) * kBbT + t;
-      float mean = 0.f, inv = 0.f, beta = 0.f;
-      if (cg + wi < c_end && k < a.K) {
-        mean = a.bmean[k];
-        inv = rsqrtf(a.bvar[k] + kBnEps) * a.gamma[k];
-        beta = a.beta[k];
-      }
-      scm[(wi * 3 + 0) * kBbT + t] = mean;
-      scm[(wi * 3 + 1) * kBbT + t] = inv;
-      scm[(wi * 3 + 2) * kBbT + t] = beta;
-    }
-    __syncthreads();
+    const int64_t k = cgn * kBbT + tid;  // 512 threads = 32 words x 16 SNPs
+    const bool ok = k < c_end * kBbT && k < a.K;
+    const float* srcs[4] = {a.bmean, a.bvar, a.gamma, a.beta};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(raw0 + (bi * 4 + q) * kBbThreads + tid)),
+                   "l"(ok ? srcs[q] + k : srcs[q]), "r"(ok ? 4 : 0)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // per-thread parts of the W1 | m | v offsets (see `unit` below)
+  const int tb = TILED ? (g * 32 + 4 * (tig & 1) + (J0 >> 5) * 256) : (g * H + J0 + 4 * tig);
+  const int xo0 = TILED ? (((tig >> 1) ^ (g & 3)) << 3) : 0, xo1 = TILED ? (((2 + (tig >> 1)) ^ (g & 3)) << 3) : 16;
+  __syncthreads();  // s_rows
+  stage(c_begin, 0);
+  int it = 0;
+  for (int64_t cg = c_begin; cg < c_end; cg += kBbWordsPerIter, ++it) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // this iteration's inputs are there; everybody is done with the previous iteration's (and the set-up)
+    if (cg + kBbWordsPerIter < c_end) stage(cg + kBbWordsPerIter, (it + 1) & 1);
+    const uint32_t* xw = xw0 + (size_t)(it & 1) * kBbWordsPerIter * xw_pitch;
+    const float* raw = raw0 + (it & 1) * 4 * kBbThreads;
     {
       // L2 prefetch of the iteration's rows of W1 | m | v (393 KB at CW = 64): they are needed after the products
       // below, a few microseconds from now -- the DRAM reads run under the tensor-core phase instead of after it
@@ -225,111 +250,105 @@ __global__ void __launch_bounds__(kBbThreads, 1) k_bb_l1_bwd(BigArgs a, float* _
         if (on) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
       }
     }
-    const int w0i = 2 * warp;  // this warp's two words of the iteration
-    if (cg + w0i >= c_end) continue;  // (whole warps; the barriers above are reached by everybody)
-    float acc[2][NT][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int n = 0; n < NT; ++n)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[mt][n][e] = 0.f;
-    {
-      float mean_lo[2], mean_hi[2];  // SNPs g and g + 8 of the two words
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        mean_lo[mt] = scm[((w0i + mt) * 3 + 0) * kBbT + g];
-        mean_hi[mt] = scm[((w0i + mt) * 3 + 0) * kBbT + g + 8];
-      }
-      const uint32_t* xa = xw + (size_t)w0i * xw_pitch + 2 * tig;
-      const uint4* bf = dzf + lane;
-      // 2-bit genotype -> float without a conversion instruction: 2^23 + x as bits, minus 2^23 (exact), then centred
-      auto cen = [](uint32_t x2, float mean) { return (__uint_as_float(0x4B000000u | (x2 & 3u)) - 8388608.f) - mean; };
-#pragma unroll 2
-      for (int ks = 0; ks < nk; ++ks) {
-        uint32_t af[2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const uint32_t* xr = xa + mt * xw_pitch + ks * 16;
-          const uint32_t x0 = xr[0] >> (2 * g), x1 = xr[1] >> (2 * g);  // rows 16 ks + 2 tig, + 1
-          const uint32_t x8 = xr[8] >> (2 * g), x9 = xr[9] >> (2 * g);  // rows 16 ks + 2 tig + 8, + 9
-          af[mt][0] = bb_h2(cen(x0, mean_lo[mt]), cen(x1, mean_lo[mt]));              // (SNP g,     rows 2 tig, 2 tig + 1)
-          af[mt][1] = bb_h2(cen(x0 >> 16, mean_hi[mt]), cen(x1 >> 16, mean_hi[mt]));  // (SNP g + 8, rows 2 tig, 2 tig + 1)
-          af[mt][2] = bb_h2(cen(x8, mean_lo[mt]), cen(x9, mean_lo[mt]));              // (SNP g,     rows 2 tig + 8, + 9)
-          af[mt][3] = bb_h2(cen(x8 >> 16, mean_hi[mt]), cen(x9 >> 16, mean_hi[mt]));  // (SNP g + 8, rows 2 tig + 8, + 9)
-        }
-#pragma unroll
-        for (int n = 0; n < NT; ++n) {
-          const uint4 b4 = bf[(ks * NT + n) * 32];
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            bb_mma(acc[mt][n], af[mt], b4.x, b4.y);  // hi part of dZ1
-            bb_mma(acc[mt][n], af[mt], b4.z, b4.w);  // lo part
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int n = 0; n < NT; ++n)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[mt][n][e] *= dunscale;
-    // ---- Adam on the warp's 32 SNPs x CW columns.  acc[mt][n] = {S(g, j), S(g, j+1), S(g+8, j), S(g+8, j+1)}, j = J0 + 8n + 2tig
-#pragma unroll
+    // ---- each warp: its two words of the iteration, one after the other: products (one 16-SNP m-tile x all CW columns
+    //      of the group), then Adam on that 16 x CW block of W1 | m | v straight from the accumulator fragments
+    //      acc[n] = {S(g, j), S(g, j+1), S(g+8, j), S(g+8, j+1)}, j = J0 + 8n + 2tig.  The block's first two column tiles
+    //      are requested BEFORE the products, and two tiles stay in flight throughout (12 8-byte loads per thread).
+#pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
-      const int64_t cw = cg + w0i + mt;
-      if (cw >= c_end) break;
+      const int wi = 2 * warp + mt;
+      const int64_t cw = cg + wi;
+      if (cw >= c_end) break;  // (whole warps; the barriers at the top of the iteration are reached by everybody)
       const int64_t k0 = cw * kBbT;
       const bool on_lo = k0 + g < a.K, on_hi = k0 + g + 8 < a.K;
-      const float inv_lo = scm[((w0i + mt) * 3 + 1) * kBbT + g], inv_hi = scm[((w0i + mt) * 3 + 1) * kBbT + g + 8];
-      const float be_lo = scm[((w0i + mt) * 3 + 2) * kBbT + g], be_hi = scm[((w0i + mt) * 3 + 2) * kBbT + g + 8];
-      auto index = [&](int n, int hi) -> int64_t {
-        const int64_t k = k0 + g + 8 * hi;
-        const int j = J0 + 8 * n + 2 * tig;
-        return TILED ? w1_tiled_index(k, j) : k * H + j;
+      // One unit = (32-column chunk q, SNP g or g + 8, half h): the thread's columns 16 h + 4 tig .. + 3 of the chunk, 16 bytes
+      // of each of W1 | m | v.  Three units are in flight while a fourth is updated in place (9 loads per thread).
+      constexpr int NU = 4 * (NT / 4);
+      // element offset of unit u (w1_tiled_index of model.cuh, or row-major, with everything that does not depend on u
+      // folded into the word's base pointers)
+      auto unit = [&](int u) -> int {
+        const int h = u & 1, hi = (u >> 1) & 1, q = u >> 2;
+        return TILED ? (hi * 2048 + q * 256 + (h ? xo1 : xo0)) : (hi * 8 * H + 32 * q + (h ? xo1 : xo0));
       };
-      float2 cw_[2][3], nx_[2][3];  // current / next column tile: [SNP g | g + 8][W, m, v]
-      auto fetch = [&](int n, float2 (&d)[2][3]) {
-#pragma unroll
-        for (int hi = 0; hi < 2; ++hi) {
-          const bool on = hi ? on_hi : on_lo;
-          const int64_t idx = index(n, hi);
-          d[hi][0] = on ? *reinterpret_cast<const float2*>(a.W1 + idx) : make_float2(0.f, 0.f);
-          d[hi][1] = on ? *reinterpret_cast<const float2*>(a.mW1 + idx) : make_float2(0.f, 0.f);
-          d[hi][2] = on ? *reinterpret_cast<const float2*>(a.vW1 + idx) : make_float2(0.f, 0.f);
-        }
+      const int64_t wb = (TILED ? ((k0 >> 3) << 11) : k0 * H) + tb;
+      float* const pW = a.W1 + wb;
+      float* const pM = a.mW1 + wb;
+      float* const pV = a.vW1 + wb;
+      float4 buf[4][3];  // [slot][W, m, v]
+      auto fetch = [&](int u, float4 (&d)[3]) {
+        const bool on = ((u >> 1) & 1) ? on_hi : on_lo;
+        const int off = unit(u);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        d[0] = on ? *reinterpret_cast<const float4*>(pW + off) : z;
+        d[1] = on ? *reinterpret_cast<const float4*>(pM + off) : z;
+        d[2] = on ? *reinterpret_cast<const float4*>(pV + off) : z;
       };
-      float P[2] = {0.f, 0.f}, Q[2] = {0.f, 0.f};
-      fetch(0, cw_);
+      fetch(0, buf[0]);
+      fetch(1, buf[1]);
+      fetch(2, buf[2]);
+      float acc[NT][4];
 #pragma unroll
-      for (int n = 0; n < NT; ++n) {
-        if (n + 1 < NT) fetch(n + 1, nx_);
-        const float2 c0 = *reinterpret_cast<const float2*>(c0s + 8 * n + 2 * tig);
+      for (int n = 0; n < NT; ++n)
 #pragma unroll
-        for (int hi = 0; hi < 2; ++hi) {
-          const float inv = hi ? inv_hi : inv_lo, be = hi ? be_hi : be_lo;
-          const float S0 = acc[mt][n][2 * hi], S1 = acc[mt][n][2 * hi + 1];
-          float2 w = cw_[hi][0], m = cw_[hi][1], v = cw_[hi][2];
-          P[hi] = fmaf(w.x, S0, fmaf(w.y, S1, P[hi]));
-          Q[hi] = fmaf(w.x, c0.x, fmaf(w.y, c0.y, Q[hi]));
-          bb_adam(w.x, m.x, v.x, inv * S0 + be * c0.x, alpha);
-          bb_adam(w.y, m.y, v.y, inv * S1 + be * c0.y, alpha);
-          if (hi ? on_hi : on_lo) {
-            const int64_t idx = index(n, hi);
-            *reinterpret_cast<float2*>(a.W1 + idx) = w;
-            *reinterpret_cast<float2*>(a.mW1 + idx) = m;
-            *reinterpret_cast<float2*>(a.vW1 + idx) = v;
+        for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+      {
+        const float mean_lo = raw[wi * kBbT + g], mean_hi = raw[wi * kBbT + g + 8];  // SNPs g, g + 8
+        const uint32_t* xa = xw + (size_t)wi * xw_pitch + 2 * tig;
+        const uint4* bf = dzf + lane;
+        // 2-bit genotype -> float without a conversion instruction: 2^23 + x as bits, minus 2^23 (exact), then centred
+        auto cen = [](uint32_t x2, float mean) { return (__uint_as_float(0x4B000000u | (x2 & 3u)) - 8388608.f) - mean; };
+#pragma unroll 2
+        for (int ks = 0; ks < nk; ++ks) {
+          const uint32_t* xr = xa + ks * 16;
+          const uint32_t x0 = xr[0] >> (2 * g), x1 = xr[1] >> (2 * g);  // rows 16 ks + 2 tig, + 1
+          const uint32_t x8 = xr[8] >> (2 * g), x9 = xr[9] >> (2 * g);  // rows 16 ks + 2 tig + 8, + 9
+          uint32_t af[4];
+          af[0] = bb_h2(cen(x0, mean_lo), cen(x1, mean_lo));              // (SNP g,     rows 2 tig, 2 tig + 1)
+          af[1] = bb_h2(cen(x0 >> 16, mean_hi), cen(x1 >> 16, mean_hi));  // (SNP g + 8, rows 2 tig, 2 tig + 1)
+          af[2] = bb_h2(cen(x8, mean_lo), cen(x9, mean_lo));              // (SNP g,     rows 2 tig + 8, + 9)
+          af[3] = bb_h2(cen(x8 >> 16, mean_hi), cen(x9 >> 16, mean_hi));  // (SNP g + 8, rows 2 tig + 8, + 9)
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            const uint4 b4 = bf[(ks * NT + n) * 32];
+            bb_mma(acc[n], af, b4.x, b4.y);  // hi part of dZ1
+            bb_mma(acc[n], af, b4.z, b4.w);  // lo part
           }
         }
+      }
+      // inv = gamma * rsqrt(var + eps), times the scale of dZ1 taken back out of S
+      const float inv_lo = rsqrtf(raw[kBbThreads + wi * kBbT + g] + kBnEps) * raw[2 * kBbThreads + wi * kBbT + g] * dunscale;
+      const float inv_hi = rsqrtf(raw[kBbThreads + wi * kBbT + g + 8] + kBnEps) * raw[2 * kBbThreads + wi * kBbT + g + 8] * dunscale;
+      const float be_lo = raw[3 * kBbThreads + wi * kBbT + g], be_hi = raw[3 * kBbThreads + wi * kBbT + g + 8];
+      float P[2] = {0.f, 0.f}, Q[2] = {0.f, 0.f};
 #pragma unroll
-        for (int hi = 0; hi < 2; ++hi)
-#pragma unroll
-          for (int q = 0; q < 3; ++q) cw_[hi][q] = nx_[hi][q];
+      for (int u = 0; u < NU; ++u) {
+        const int h = u & 1, hi = (u >> 1) & 1, q = u >> 2;
+        if (u + 3 < NU) fetch(u + 3, buf[(u + 3) & 3]);
+        const float inv = hi ? inv_hi : inv_lo, be = hi ? be_hi : be_lo;
+        float4& w = buf[u & 3][0];
+        float4& m = buf[u & 3][1];
+        float4& v = buf[u & 3][2];
+        // columns 16 h + 4 tig + {0, 1, 2, 3} of the chunk = accumulator columns 2 tig, 2 tig + 1 of n-tiles 4 q + 2 h, + 1
+        const float4 c0 = *reinterpret_cast<const float4*>(c0s + 32 * q + 16 * h + 4 * tig);
+        const float S0 = acc[4 * q + 2 * h][2 * hi], S1 = acc[4 * q + 2 * h][2 * hi + 1];
+        const float S2 = acc[4 * q + 2 * h + 1][2 * hi], S3 = acc[4 * q + 2 * h + 1][2 * hi + 1];
+        P[hi] = fmaf(w.x, S0, fmaf(w.y, S1, fmaf(w.z, S2, fmaf(w.w, S3, P[hi]))));
+        Q[hi] = fmaf(w.x, c0.x, fmaf(w.y, c0.y, fmaf(w.z, c0.z, fmaf(w.w, c0.w, Q[hi]))));
+        bb_adam(w.x, m.x, v.x, inv * S0 + be * c0.x, alpha);
+        bb_adam(w.y, m.y, v.y, inv * S1 + be * c0.y, alpha);
+        bb_adam(w.z, m.z, v.z, inv * S2 + be * c0.z, alpha);
+        bb_adam(w.w, m.w, v.w, inv * S3 + be * c0.w, alpha);
+        if (hi ? on_hi : on_lo) {
+          const int off = unit(u);
+          *reinterpret_cast<float4*>(pW + off) = w;
+          *reinterpret_cast<float4*>(pM + off) = m;
+          *reinterpret_cast<float4*>(pV + off) = v;
+        }
       }
       // sums over the warp's columns: the four lanes of a group hold different column pairs of the same SNPs
 #pragma unroll
       for (int hi = 0; hi < 2; ++hi) {
+        P[hi] *= dunscale;  // P = sum_j W1 S with the true S
 #pragma unroll
         for (int o = 1; o <= 2; o <<= 1) {
           P[hi] += __shfl_xor_sync(0xffffffffu, P[hi], o);
@@ -526,8 +545,8 @@ static int bb_l1_backward_cw(const BigArgs& a, float* pq_part, cudaStream_t s) {
   constexpr int NT = CW / 8;
   const int ncg = a.H / CW;
   const int nk = (a.nb + 15) / 16;
-  const size_t smem = (size_t)nk * NT * 32 * sizeof(uint4) + (size_t)kBbWordsPerIter * (nk * 16 + 1) * sizeof(uint32_t) +
-                      (size_t)(kBbWordsPerIter * 3 * kBbT + CW) * sizeof(float);
+  const size_t smem = (size_t)nk * NT * 32 * sizeof(uint4) + (size_t)2 * kBbWordsPerIter * (nk * 16 + 1) * sizeof(uint32_t) +
+                      (size_t)(2 * 4 * kBbThreads + CW) * sizeof(float);
   LOC_CUDA(cudaFuncSetAttribute(k_bb_l1_bwd<CW, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t niter = cdiv(cdiv(a.K, kBbT), kBbWordsPerIter);
   int64_t by = cdiv((int64_t)bb_sms(), ncg);  // one 512-thread block per SM

@@ -393,13 +393,17 @@ __global__ void __launch_bounds__(256) k_bb_gamma_beta(BigArgs a, const float* _
 }
 
 // dW + Adam of the small layers over the chunks of the step.  Blocks [0, (L-1)*H/16): 16 input rows x H outputs of
-// hidden layer i; last block: b1, Dense(2), Dense(2).  blockDim = H, thread <-> output column j (as k_hidden_update).
+// hidden layer i; last block: b1, Dense(2), Dense(2).  blockDim = (H, S): thread (j, s) <-> output column j, chunks
+// s, s + S, ... (every chunk costs a memory round trip; S of them run side by side), partial sums meet in shared memory
+// in split order, and split s finishes rows r = s, s + S, ... of the block.
 constexpr int kBbRows = 16;
+constexpr int kBbSplits = 4;
 
 __global__ void __launch_bounds__(1024) k_bb_hidden_update(BigArgs a) {
   if (a.gated && a.st->stopped) return;
-  __shared__ float as[kBbRows][kMaxB + 1];
-  const int H = a.H, L = a.L, j = threadIdx.x;
+  extern __shared__ float bb_red[];  // [S][16 rows + 1][H]: partial dW rows, then the partial bias gradient
+  __shared__ float as[kBbSplits][kBbRows][kMaxB + 1];
+  const int H = a.H, L = a.L, j = threadIdx.x, sp = threadIdx.y, S = blockDim.y;
   const SmallLayout sl{H, L};
   const int rb_n = H / kBbRows;
   const int nblk_hidden = (L - 1) * rb_n;
@@ -419,16 +423,18 @@ __global__ void __launch_bounds__(1024) k_bb_hidden_update(BigArgs a) {
 #pragma unroll
     for (int r = 0; r < kBbRows; ++r) g16[r] = 0.f;
     float bsum = 0.f;
-    for (int ci = 0; ci < nchunks; ++ci) {
-      const float* dzs = a.dzs + ci * chunk_stride;
-      const float* acts = a.acts + ci * chunk_stride;
+    for (int c0 = 0; c0 < nchunks; c0 += S) {  // (uniform trip count: the barriers below are block-wide)
+      const int ci = c0 + sp;
+      const bool on = ci < nchunks;
+      const float* dzs = a.dzs + (on ? ci : 0) * chunk_stride;
+      const float* acts = a.acts + (on ? ci : 0) * chunk_stride;
       float dz[kMaxB];
 #pragma unroll
-      for (int b = 0; b < kMaxB; ++b) dz[b] = dzs[((int64_t)i * kMaxB + b) * H + j];
-      __syncthreads();  // the previous chunk's activations have been consumed
-      for (int idx = threadIdx.x; idx < kBbRows * kMaxB; idx += blockDim.x) {
+      for (int b = 0; b < kMaxB; ++b) dz[b] = on ? dzs[((int64_t)i * kMaxB + b) * H + j] : 0.f;
+      __syncthreads();  // the previous round's activations have been consumed
+      for (int idx = j; idx < kBbRows * kMaxB; idx += H) {
         const int kk = idx % kBbRows, b = idx / kBbRows;
-        as[kk][b] = acts[((int64_t)(i - 1) * kMaxB + b) * H + rb * kBbRows + kk];
+        as[sp][kk][b] = on ? acts[((int64_t)(i - 1) * kMaxB + b) * H + rb * kBbRows + kk] : 0.f;
       }
       __syncthreads();
 #pragma unroll
@@ -437,16 +443,25 @@ __global__ void __launch_bounds__(1024) k_bb_hidden_update(BigArgs a) {
       for (int r = 0; r < kBbRows; ++r) {
         float g = 0.f;
 #pragma unroll
-        for (int b = 0; b < kMaxB; ++b) g = fmaf(as[r][b], dz[b], g);
+        for (int b = 0; b < kMaxB; ++b) g = fmaf(as[sp][r][b], dz[b], g);
         g16[r] += g;
       }
     }
 #pragma unroll
-    for (int r = 0; r < kBbRows; ++r) {
+    for (int r = 0; r < kBbRows; ++r) bb_red[((size_t)sp * (kBbRows + 1) + r) * H + j] = g16[r];
+    bb_red[((size_t)sp * (kBbRows + 1) + kBbRows) * H + j] = bsum;
+    __syncthreads();
+    for (int r = sp; r < kBbRows + 1; r += S) {
+      float g = 0.f;
+      for (int q = 0; q < S; ++q) g += bb_red[((size_t)q * (kBbRows + 1) + r) * H + j];  // split order
+      if (r == kBbRows) {
+        if (rb == 0) adam_at(sl.bh(i) + j, g);
+        continue;
+      }
       const int k = rb * kBbRows + r;
       const int64_t idx = sl.Wh(i) + (int64_t)k * H + j;
       float w = a.small[idx], m = a.m_small[idx], v = a.v_small[idx];
-      adam_update(w, m, v, g16[r], alpha);
+      adam_update(w, m, v, g, alpha);
       a.small[idx] = w;
       a.m_small[idx] = m;
       a.v_small[idx] = v;
@@ -455,8 +470,7 @@ __global__ void __launch_bounds__(1024) k_bb_hidden_update(BigArgs a) {
       else
         store_sliced(a.w_fs, a.w_bs, H, a.Hc, i, k, j, w);
     }
-    if (rb == 0) adam_at(sl.bh(i) + j, bsum);
-  } else {
+  } else if (sp == 0) {
     float gb1 = 0.f, g0 = 0.f, g1 = 0.f, sb = 0.f;
     for (int ci = 0; ci < nchunks; ++ci) {
       const float* dzs = a.dzs + ci * chunk_stride;
@@ -464,6 +478,7 @@ __global__ void __launch_bounds__(1024) k_bb_hidden_update(BigArgs a) {
       const float* y1 = a.outs + ci * 256;
       const float* dy1 = y1 + 64;
       const float* dy2 = y1 + 128;
+#pragma unroll 8
       for (int b = 0; b < kMaxB; ++b) {
         gb1 += dzs[(int64_t)b * H + j];  // b1: column sum of dZ1
         const float av = acts[((int64_t)(L - 1) * kMaxB + b) * H + j];  // Dense(2): Wo1[k][c] = sum_b a_{L-1}[b][k] dy1[b][c]
@@ -569,7 +584,18 @@ int bb_l1_backward_launch(const BigArgs& a, float* pq_part, cudaStream_t s) {
 int bb_hidden_update_launch(const BigArgs& a, cudaStream_t s) {
   LOC_CHECK(a.H % kBbRows == 0 && a.H >= 32 && a.H <= 1024, "hidden update (large batch): bad width");
   const int nblk = (a.L - 1) * (a.H / kBbRows) + 1;
-  k_bb_hidden_update<<<nblk, a.H, 0, s>>>(a);
+  const int nchunks = (a.nb + kMaxB - 1) / kMaxB;
+  int S = 1024 / a.H;  // chunks side by side in a block
+  if (S > kBbSplits) S = kBbSplits;
+  if (S > nchunks) S = nchunks;
+  if (S < 1) S = 1;
+  const size_t smem = (size_t)S * (kBbRows + 1) * a.H * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    LOC_CUDA(cudaFuncSetAttribute(k_bb_hidden_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  k_bb_hidden_update<<<nblk, dim3((unsigned)a.H, (unsigned)S), smem, s>>>(a);
   LOC_LAUNCHED();
   return 0;
 }

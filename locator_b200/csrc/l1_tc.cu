@@ -275,23 +275,40 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_l1_fwd_tc(L1Args a, int64_t nt
     uint32_t* bits = sBits + wi * 64;
     const int64_t my_row = lane < nb ? row_of(a.src, a.st, lane) : 0;
     const uint32_t* my_ptr = a.packed + my_row * a.row_words;
+    // the global loads of a stage -- lane <-> batch row: the row's 32 genotypes of the tile (2 words); lane <-> SNP: the
+    // SNP's parameters -- are requested one of the warp's stages ahead (they sat on its critical path once per stage)
+    struct StageIn {
+      uint2 w2;
+      float gamma, beta, mm, mv;
+    };
+    auto stage_in = [&](int li) {
+      StageIn r;
+      const int64_t tile = t_begin + li;
+      r.w2 = make_uint2(0u, 0u);
+      if (lane < nb && tile * 2 + 1 < a.row_words) r.w2 = __ldg(reinterpret_cast<const uint2*>(my_ptr + tile * 2));
+      const int64_t k = tile * F_KT + lane;
+      r.gamma = r.beta = r.mm = 0.f;
+      r.mv = 1.f;
+      if (k < a.K) {
+        r.gamma = a.gamma[k];
+        r.beta = a.beta[k];
+        r.mm = a.mmean[k];  // (read before this thread's own update of the same element below; nobody else touches it)
+        r.mv = a.mvar[k];
+      }
+      return r;
+    };
+    StageIn nxt;
+    if (wi < nloc) nxt = stage_in(wi);
     for (int li = wi; li < nloc; li += 4) {
       const int s = li % F_STAGES;
       const uint32_t ph = (uint32_t)(li / F_STAGES) & 1u;
       const int64_t tile = t_begin + li;
-      // lane <-> batch row: this tile's 32 genotypes of the row (2 words)
-      uint2 w2 = make_uint2(0u, 0u);
-      if (lane < nb && tile * 2 + 1 < a.row_words) w2 = __ldg(reinterpret_cast<const uint2*>(my_ptr + tile * 2));
-      // lane <-> SNP: per-SNP parameters
+      const StageIn cur = nxt;
+      if (li + 4 < nloc) nxt = stage_in(li + 4);
+      const uint2 w2 = cur.w2;
       const int64_t k = tile * F_KT + lane;
       const bool valid = k < a.K;
-      float gamma = 0.f, beta = 0.f, mm = 0.f, mv = 1.f;
-      if (valid) {
-        gamma = a.gamma[k];
-        beta = a.beta[k];
-        mm = a.mmean[k];
-        mv = a.mvar[k];
-      }
+      const float gamma = cur.gamma, beta = cur.beta, mm = cur.mm, mv = cur.mv;
       bits[lane * 2] = w2.x;
       bits[lane * 2 + 1] = w2.y;
       __syncwarp();
@@ -467,21 +484,39 @@ __global__ void __launch_bounds__(W_THREADS, 1) k_l1_fwd_wide(L1Args a, int64_t 
       const int nb_chunk = nrows - wi * 32 < 32 ? nrows - wi * 32 : 32;
       const int64_t my_row = row_ok ? row_of(a.src, a.st, b_row) : 0;
       const uint32_t* my_ptr = a.packed + my_row * a.row_words;
+      // One warp builds every stage of its chunk, so the global loads of a stage (the row's 32 genotypes, the SNPs'
+      // parameters) would sit on its critical path once per stage: they are requested one stage ahead.
+      struct StageIn {
+        uint2 w2;
+        float gamma, beta, mm, mv;
+      };
+      auto stage_in = [&](int li) {
+        StageIn r;
+        const int64_t tile = t_begin + li;
+        r.w2 = make_uint2(0u, 0u);
+        if (row_ok && tile * 2 + 1 < a.row_words) r.w2 = __ldg(reinterpret_cast<const uint2*>(my_ptr + tile * 2));
+        const int64_t k = tile * F_KT + lane;
+        r.gamma = r.beta = r.mm = 0.f;
+        r.mv = 1.f;
+        if (k < a.K) {
+          r.gamma = __ldg(a.gamma + k);
+          r.beta = __ldg(a.beta + k);
+          r.mm = __ldg(a.mmean + k);
+          r.mv = __ldg(a.mvar + k);
+        }
+        return r;
+      };
+      StageIn nxt = stage_in(0);
       for (int li = 0; li < nloc; ++li) {
         const int s = li % W_STAGES;
         const uint32_t ph = (uint32_t)(li / W_STAGES) & 1u;
         const int64_t tile = t_begin + li;
-        uint2 w2 = make_uint2(0u, 0u);
-        if (row_ok && tile * 2 + 1 < a.row_words) w2 = __ldg(reinterpret_cast<const uint2*>(my_ptr + tile * 2));
+        const StageIn cur = nxt;
+        if (li + 1 < nloc) nxt = stage_in(li + 1);
+        const uint2 w2 = cur.w2;
         const int64_t k = tile * F_KT + lane;
         const bool valid = k < a.K;
-        float gamma = 0.f, beta = 0.f, mm = 0.f, mv = 1.f;
-        if (valid) {
-          gamma = __ldg(a.gamma + k);
-          beta = __ldg(a.beta + k);
-          mm = __ldg(a.mmean + k);
-          mv = __ldg(a.mvar + k);
-        }
+        const float gamma = cur.gamma, beta = cur.beta, mm = cur.mm, mv = cur.mv;
         bits[lane * 2] = w2.x;
         bits[lane * 2 + 1] = w2.y;
         __syncwarp();

@@ -397,7 +397,7 @@ constexpr int W_STAGES = 3;
 constexpr int W_XBYTES = 8 * F_XBYTES;           // 32 KB: [8 chunks of 32 rows][32 SNP rows][128 B]
 constexpr int W_BUILD = 8;                        // builder warps = max 32-row chunks
 constexpr int W_THREADS = (2 + W_BUILD) * 32;     // producer, MMA issuer, builders (also the epilogue)
-constexpr int W_SMEM = W_STAGES * (F_WBYTES + W_XBYTES) + W_BUILD * 32 * 8 + 256 + 1024;
+constexpr int W_SMEM = W_STAGES * (F_WBYTES + W_XBYTES) + W_BUILD * 32 * 16 + 256 + 1024;
 
 __global__ void __launch_bounds__(W_THREADS, 1) k_l1_fwd_wide(L1Args a, int64_t ntiles, int nrows, float* __restrict__ out) {
   if (a.gated && a.st->stopped) return;
@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) k_l1_fwd_wide(L1Args a, int64_t 
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = sm;
   uint8_t* sX = sW + W_STAGES * F_WBYTES;
-  uint32_t* sBits = (uint32_t*)(sX + W_STAGES * W_XBYTES);  // [8 warps][32 rows][2 words]
-  uint64_t* bars = (uint64_t*)(sBits + W_BUILD * 32 * 2);
+  uint32_t* sBits = (uint32_t*)(sX + W_STAGES * W_XBYTES);  // [8 warps][32 SNPs][4 floats]: per-SNP value tables
+  uint64_t* bars = (uint64_t*)(sBits + W_BUILD * 32 * 4);
   uint64_t* full_w = bars;
   uint64_t* full_x = bars + W_STAGES;
   uint64_t* empty = bars + 2 * W_STAGES;
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) k_l1_fwd_wide(L1Args a, int64_t 
     // ---- builders: warp wi owns the 32-row chunk wi (rows 32 wi .. 32 wi + 31 of this pass) ----
     const int wi = warp - 2;
     if (wi < NC) {
-      uint32_t* bits = sBits + wi * 64;
+      float4* lutw = reinterpret_cast<float4*>(sBits) + wi * 32;  // this warp's table: [32 SNPs]{x = 0, 1, 2, -}
       const int b_row = wi * 32 + lane;             // row of the pass this lane loads
       const bool row_ok = b_row < nrows;
       const int nb_chunk = nrows - wi * 32 < 32 ? nrows - wi * 32 : 32;
@@ -517,36 +517,34 @@ __global__ void __launch_bounds__(W_THREADS, 1) k_l1_fwd_wide(L1Args a, int64_t 
         const int64_t k = tile * F_KT + lane;
         const bool valid = k < a.K;
         const float gamma = cur.gamma, beta = cur.beta, mm = cur.mm, mv = cur.mv;
-        bits[lane * 2] = w2.x;
-        bits[lane * 2 + 1] = w2.y;
-        __syncwarp();
-        const int wsel = lane >> 4, sh = 2 * (lane & 15);
-        unsigned long long g = 0ull;
-#pragma unroll
-        for (int b = 0; b < 32; ++b) g |= (unsigned long long)((bits[b * 2 + wsel] >> sh) & 3u) << (2 * b);
-        __syncwarp();
+        // lane <-> SNP: the three values a genotype of this SNP can take, shared through a per-warp table; then
+        // lane <-> batch row: every lane walks its own row's 32 genotypes (they are in its registers) and writes one
+        // element per SNP row of the operand tile -- a 128-byte row per store instruction, conflict-free.  (The first
+        // version transposed the genotypes through shared memory instead, 32 loads + ~130 integer instructions per
+        // lane and stage: 23 % of the kernel's samples.)
         const float inv = rsqrtf(mv + kBnEps) * gamma;  // inference: moving statistics
         const float shift = beta - mm * inv;
-        float lut[3];
-        lut[0] = valid ? to_tf32(shift) : 0.f;
-        lut[1] = valid ? to_tf32(inv + shift) : 0.f;
-        lut[2] = valid ? to_tf32(2.f * inv + shift) : 0.f;
+        __syncwarp();  // the previous stage's table has been read by every lane
+        lutw[lane] = make_float4(valid ? to_tf32(shift) : 0.f, valid ? to_tf32(inv + shift) : 0.f,
+                                 valid ? to_tf32(2.f * inv + shift) : 0.f, 0.f);
+        __syncwarp();
         mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* xrow = sX + s * W_XBYTES + wi * F_CHUNK;
+        uint8_t* xrow = sX + s * W_XBYTES + wi * F_CHUNK + (lane & 3) * 4;
+        const float* lutf = reinterpret_cast<const float*>(lutw);
+        const bool row_on = lane < nb_chunk;
+        uint32_t off4[4];  // swz32(k, lane >> 2) - 128 k only depends on k & 3
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float v[4];
+        for (int q = 0; q < 4; ++q) off4[q] = swz32(q, lane >> 2) - 128u * q;
+        // (all table reads first, then all stores: through these generic pointers the compiler must keep a store and
+        // the next load in order, and 32 dependent load -> store round trips cost a microsecond per stage)
+        float vals[F_KT];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int b = 4 * c + e;
-            const unsigned x = (unsigned)((g >> (2 * b)) & 3ull);
-            float val = lut[0];
-            val = x == 1u ? lut[1] : val;
-            val = x == 2u ? lut[2] : val;
-            v[e] = b < nb_chunk ? val : 0.f;
-          }
-          *reinterpret_cast<float4*>(xrow + swz32(lane, c)) = make_float4(v[0], v[1], v[2], v[3]);
+        for (int k = 0; k < F_KT; ++k) {
+          const unsigned x = ((k < 16 ? w2.x : w2.y) >> (2 * (k & 15))) & 3u;
+          vals[k] = lutf[4 * k + x];
         }
+#pragma unroll
+        for (int k = 0; k < F_KT; ++k) *reinterpret_cast<float*>(xrow + 128 * k + off4[k & 3]) = row_on ? vals[k] : 0.f;
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_x[s]);

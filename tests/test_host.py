@@ -581,3 +581,21 @@ def test_keras_weights_converter_host_side(tmp_path):
     assert kw.main(["describe", p]) == 0
     if kw._keras() is None:
         assert kw.main(["to-h5", p, str(tmp_path / "m.weights.h5")]) == 2
+
+
+def test_validate_args_limits_of_this_build():
+    """Argument limits are checked before any data is read (locator.py:69,371 passes any --batch_size to model.fit;
+    here 1..256 -- steps above 32 rows take the chunked path of csrc/bigbatch.cu -- and a clear refusal beyond)."""
+    from locator_b200 import locator as L
+
+    def ns(*extra):
+        return L.build_parser().parse_args(["--vcf", "x.vcf", "--sample_data", "s.txt", "--out", "o"] + list(extra))
+
+    for ok in ([], ["--batch_size", "1"], ["--batch_size", "64"], ["--batch_size", "256"], ["--width", "96"],
+               ["--nlayers", "2"], ["--dropout_prop", "0"]):
+        L.validate_args(ns(*ok))
+    for bad, word in ((["--batch_size", "0"], "batch_size"), (["--batch_size", "257"], "batch_size"),
+                      (["--width", "100"], "width"), (["--nlayers", "1"], "nlayers"), (["--dropout_prop", "1.0"], "dropout_prop"),
+                      (["--max_epochs", "0"], "max_epochs"), (["--windows", "--window_size", "2e5"], "window_size")):
+        with pytest.raises(SystemExit, match=word):
+            L.validate_args(ns(*bad))

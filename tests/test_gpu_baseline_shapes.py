@@ -358,3 +358,42 @@ def test_divergence_is_rounding_chaos(M):
     # and all of them learn: the third epoch's loss is well below the first's
     for n, r in runs.items():
         assert r["loss"][-1] < 0.8 * r["loss"][0], (n, r["loss"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# --batch_size above 32 at BASELINE shapes (csrc/bigbatch.cu)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K,Bb", [(100_000, 256), (200_000, 96)])
+def test_large_batch_step_matches_oracle_at_baseline_shapes(M, K, Bb):
+    """One optimizer step of Bb rows (batch statistics over the whole step, wide forward, 32-row chunks through the
+    hidden stack, mma.sync backward + Adam over all rows) against the oracle's tf32 operand model: loss, Adam moments
+    of W1 / gamma / beta (the first step's m is 0.1 x the gradient), moving statistics, update of every weight.
+    Stated tolerances: loss 2e-3 relative; moments 1e-2 relative L2; sign flips of the W1 update <= 2 %."""
+    from oracle import model_ref
+
+    rng = np.random.default_rng(K // 1000 + Bb)
+    n = 300
+    x, y = _data(rng, n, K)
+    m = M.LocatorModel(K, width=H, nlayers=L, dropout_prop=P_DROP, batch_size=Bb, seed=17)
+    w0 = m.get_weights()
+    ref = model_ref.RefLocator(K, H, L, dropout=P_DROP, weights=w0, numerics="tf32")
+    masks = (rng.uniform(size=(1, Bb, H)) >= P_DROP).astype(np.uint8)
+    m.set_dropout_masks(masks)
+    m.bind_train(x, y)
+    m.set_schedule(patience=100)
+    rows = rng.permutation(n)[:Bb]
+    m.train_step(rows)
+    st = m.state()
+    loss_ref = ref.train_step(x[rows], y[rows], masks[0])
+    mW, vW = m.get_adam(4)
+    mg, _ = m.get_adam(0)
+    mb, _ = m.get_adam(1)
+    wc, wr = m.get_weights(), ref.get_weights()
+    dev = _update_deviation(w0, wc, wr, (mW, vW), (ref.m[2].numpy(), ref.v[2].numpy()))
+    dev.update(loss_rel=abs(st.last_loss - loss_ref) / abs(loss_ref), m_gamma_rel=_rel(mg, ref.m[0].numpy()),
+               m_beta_rel=_rel(mb, ref.m[1].numpy()), mmean_rel=_rel(wc[2], wr[2]), mvar_rel=_rel(wc[3], wr[3]))
+    _report(test="large_batch_step", K=K, batch=Bb, **dev)
+    assert st.t == 1 and dev["loss_rel"] <= 2e-3, dev
+    assert dev["m_rel"] <= 1e-2 and dev["v_rel"] <= 2e-2 and dev["m_gamma_rel"] <= 1e-2 and dev["m_beta_rel"] <= 1e-2, dev
+    assert dev["mmean_rel"] <= 1e-5 and dev["mvar_rel"] <= 1e-5, dev
+    assert dev["dW1_frac_opposite"] <= 0.02 and 0.97 <= dev["dW1_norm_ratio"] <= 1.03, dev

@@ -7,10 +7,12 @@
 //   k_bb_stats         batch mean / variance of every SNP over ALL rows of the step (+ moving statistics)
 //   first-layer forward with those statistics (the inference kernels read them in place of the moving ones:
 //                      one wide pass over W1 for up to 256 rows on the tcgen05 path), then the 32-row chunks
-//                      through the unchanged hidden stack, one launch each: loss scaled by the step's row count,
-//                      dropout stream indexed by the row's position in the step, activations / dz kept per chunk
-//   k_bb_l1_bwd        S = (x - mean)^T dZ1 over all rows, dW1 = inv S + beta c0, Adam on W1 | m | v in one pass
-//                      over the weights, BatchNorm gamma / beta Adam -- fp32 on the CUDA cores, either W1 layout
+//                      through the unchanged hidden stack (tcgen05 path: side by side, one cluster per chunk of a
+//                      grouped launch, k_bb_step_end closing the step; else one launch each): loss scaled by the
+//                      step's row count, dropout stream indexed by the row's position in the step, activations /
+//                      dz kept per chunk
+//   k_bb_l1_bwd        S = (x - mean)^T dZ1 over all rows (mma.sync), dW1 = inv S + beta c0, Adam on W1 | m | v in
+//                      one pass over the weights, either W1 layout; k_bb_gamma_beta: BatchNorm gamma / beta Adam
 //   k_bb_hidden_update dW + Adam of the small layers summed over the chunks
 //
 // so W1 | m | v are still streamed once per optimizer step.  Keras semantics as restated in oracle/model_ref.py
@@ -99,8 +101,8 @@ __device__ __forceinline__ const float* bb_dz1(const BigArgs& a, int b) {  // dZ
 // iteration the block takes 32 packed words (16 SNPs each) of every row of the step into shared memory, and each
 // warp owns two of them, one after the other (a 16-SNP m-tile x all CW columns): A fragments are expanded from the
 // 2-bit genotypes in registers, one 16-byte shared load per (16 rows, 8 columns) brings both parts of a B fragment.
-// The warp then runs Adam on its 16 x CW block of W1 | m | v straight from the accumulator fragments (8-byte
-// accesses; two column tiles = 12 loads per thread stay in flight, the first two requested before the products), and
+// The warp then runs Adam on its 16 x CW block of W1 | m | v straight from the accumulator fragments (16-byte
+// accesses; three units = 9 loads per thread stay in flight, the first three requested before the products), and
 // leaves P_k = sum_j W1 S, Q_k = sum_j W1 c0 of its column group in global memory: BatchNorm gamma / beta need them
 // over ALL columns (k_bb_gamma_beta).
 constexpr int kBbThreads = 512;
@@ -252,8 +254,8 @@ __global__ void __launch_bounds__(kBbThreads, 1) k_bb_l1_bwd(BigArgs a, float* _
     }
     // ---- each warp: its two words of the iteration, one after the other: products (one 16-SNP m-tile x all CW columns
     //      of the group), then Adam on that 16 x CW block of W1 | m | v straight from the accumulator fragments
-    //      acc[n] = {S(g, j), S(g, j+1), S(g+8, j), S(g+8, j+1)}, j = J0 + 8n + 2tig.  The block's first two column tiles
-    //      are requested BEFORE the products, and two tiles stay in flight throughout (12 8-byte loads per thread).
+    //      acc[n] = {S(g, c), S(g, c + 1), S(g + 8, c), S(g + 8, c + 1)}, accumulator column c = 2 tig of n-tile n = column
+    //      J0 + bb_phys_col(n, c) of the layer.  The word's first three units are requested BEFORE the products.
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
       const int wi = 2 * warp + mt;

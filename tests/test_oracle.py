@@ -104,7 +104,8 @@ def test_philox_known_answer():
     assert u.dtype == np.float32 and u.min() >= 0 and u.max() < 1 and abs(u.mean() - 0.5) < 0.05
 
 
-@pytest.mark.parametrize("K,H,L,p,B", [(50, 16, 4, 0.25, 8), (31, 8, 3, 0.0, 5), (20, 8, 2, 0.5, 32)])
+@pytest.mark.parametrize("K,H,L,p,B", [(50, 16, 4, 0.25, 8), (31, 8, 3, 0.0, 5), (20, 8, 2, 0.5, 32),
+                                       (40, 16, 4, 0.25, 80), (24, 8, 3, 0.25, 250)])  # batches above 32: --batch_size 33..256
 def test_oracle_gradients_match_autograd(K, H, L, p, B):
     rng = np.random.default_rng(K)
     x = rng.integers(0, 3, size=(B, K)).astype(np.uint8)
@@ -287,7 +288,8 @@ def test_oracle_builds_what_the_reference_asks_keras_for(golden_dir):
         assert ck["save_best_only"] is True and ck["save_weights_only"] is True
 
 
-def test_oracle_training_matches_torch_nn_and_torch_optim():
+@pytest.mark.parametrize("B", [12, 96])
+def test_oracle_training_matches_torch_nn_and_torch_optim(B):
     """An independent implementation of the same mathematics: torch.nn.BatchNorm1d (eps 1e-3, momentum 0.01 = Keras
     0.99) / Linear / ELU trained with torch.optim.Adam.  Keras puts epsilon outside the bias-corrected root
     (theta -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps)); torch divides v by (1-b2^t) first, which is the same
@@ -295,7 +297,7 @@ def test_oracle_training_matches_torch_nn_and_torch_optim():
     the same weights, losses and moving means (moving variances differ by design: torch tracks the unbiased one)."""
     import math
 
-    K, H, L, B, steps = 37, 16, 4, 12, 6
+    K, H, L, steps = 37, 16, 4, 6
     rng = np.random.default_rng(17)
     ref = model_ref.RefLocator(K, H, L, dropout=0.0, seed=5)
     ws = ref.get_weights()
